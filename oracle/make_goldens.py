@@ -1,0 +1,204 @@
+"""Generate tests/golden/*.npz by RUNNING THE UNMODIFIED REFERENCE (/root/reference) on seeded inputs.
+
+ORACLE / TEST INFRASTRUCTURE.  Run in the build container only:  python -m oracle.make_goldens
+The reference ships no golden vectors for this path, so these are produced by importing its
+own classes behind stub gym/gymnasium/mpi4py modules (oracle/ref_loader.py):
+
+    buffer_*.npz   DummyOnPolicyBuffer.store/finish_path/sample   xuance/common/memory_tools.py:143-245
+                   driven with the exact call protocol of PPOCLIP_Agent.train (ppoclip_agent.py:68-100)
+    loss_*.npz     PPOCLIP_Learner.update                          xuance/torch/learners/policy_gradient/ppoclip_learner.py:24-65
+                   with the reference's own policy modules (policies/categorical.py, policies/gaussian.py)
+    vecenv_*.npz   DummyVecEnv_Gym.reset/step                      xuance/environment/gym/gym_vec_env.py:155-212
+                   over the RESTATED physics (gym itself is absent: "parity unpinned" for the physics)
+    physics_*.npz  action tapes through the C oracle, flavour "cr" (self-derived KATs, Tier-1 target)
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+OUT = os.path.join(REPO, "tests", "golden")
+sys.path.insert(0, REPO)
+
+from oracle import ref_loader, c_oracle  # noqa: E402
+
+
+def _spaces():
+    import gym.spaces as S
+    return S
+
+
+def gen_buffer(name, seed, n_envs, n_size, discrete, use_gae, use_advnorm, gamma, lam, p_term=0.04, p_trunc=0.04):
+    """Replays a synthetic rollout into the reference buffer with the agent's finish_path protocol."""
+    from xuance.common import DummyOnPolicyBuffer
+    S = _spaces()
+    rng = np.random.default_rng(seed)
+    obs_dim = 4 if discrete else 3
+    obs_space = S.Box(-np.ones(obs_dim, np.float32), np.ones(obs_dim, np.float32))
+    act_space = S.Discrete(2) if discrete else S.Box(-2.0, 2.0, shape=(1,))
+    buf = DummyOnPolicyBuffer(obs_space, act_space, {"old_logp": ()}, n_envs, n_size, use_gae, use_advnorm, gamma, lam)
+    T, N = n_size, n_envs
+    obs = rng.standard_normal((T, N, obs_dim)).astype(np.float32)
+    act = rng.integers(0, 2, (T, N)).astype(np.int64) if discrete else rng.standard_normal((T, N, 1)).astype(np.float32)
+    rew = rng.standard_normal((T, N)).astype(np.float32)
+    val = rng.standard_normal((T, N)).astype(np.float32)
+    logp = (-rng.random((T, N))).astype(np.float32)
+    term = rng.random((T, N)) < p_term
+    trunc = rng.random((T, N)) < p_trunc
+    boot = rng.standard_normal((T, N)).astype(np.float32)      # V(next/terminal obs) after step t
+    for t in range(T):
+        buf.store(obs[t], act[t], rew[t], val[t], term[t], {"old_logp": logp[t]})
+        if buf.full:                                            # ppoclip_agent.py:69-75
+            for i in range(N):
+                buf.finish_path(0.0 if term[t, i] else boot[t, i], i)
+            break
+        for i in range(N):                                      # ppoclip_agent.py:89-100
+            if term[t, i] or trunc[t, i]:
+                buf.finish_path(0.0 if term[t, i] else boot[t, i], i)
+    idx_all = rng.permutation(N * T).astype(np.int64)
+    B = (N * T) // 4
+    batches = [buf.sample(idx_all[k * B:(k + 1) * B]) for k in range(2)]
+    out = dict(obs=obs, act=act, rew=rew, val=val, logp=logp, term=term, trunc=trunc, boot=boot,
+               returns=buf.returns, advantages=buf.advantages, observations=buf.observations, actions=buf.actions,
+               idx=idx_all[:2 * B].reshape(2, B),
+               s_obs=np.stack([b[0] for b in batches]), s_act=np.stack([b[1] for b in batches]),
+               s_ret=np.stack([b[2] for b in batches]), s_val=np.stack([b[3] for b in batches]),
+               s_adv=np.stack([b[4] for b in batches]), s_logp=np.stack([b[5]["old_logp"] for b in batches]),
+               meta=np.array(json.dumps(dict(n_envs=N, n_size=T, discrete=discrete, use_gae=use_gae,
+                                             use_advnorm=use_advnorm, gamma=gamma, lam=lam))))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name)
+
+
+def _ref_policy(discrete, hidden, seed):
+    from xuance.torch.representations import Basic_MLP
+    from xuance.torch.policies import Categorical_AC_Policy, Gaussian_AC_Policy
+    S = _spaces()
+    torch.manual_seed(seed)
+    act = torch.nn.LeakyReLU
+    init = torch.nn.init.orthogonal_
+    if discrete:
+        rep = Basic_MLP((4,), [hidden], None, init, act, "cpu")
+        return Categorical_AC_Policy(S.Discrete(2), rep, [hidden], [hidden], None, init, act, "cpu")
+    rep = Basic_MLP((3,), [hidden], None, init, act, "cpu")
+    return Gaussian_AC_Policy(S.Box(-2.0, 2.0, shape=(1,)), rep, [hidden], [hidden], None, init, act, "cpu")
+
+
+def gen_loss(name, seed, discrete, hidden, B, hp):
+    """Reference PPOCLIP_Learner.update: grads (clip off), and info + params after one clipped Adam step."""
+    from xuance.torch.learners import PPOCLIP_Learner
+    rng = np.random.default_rng(seed)
+    obs_dim = 4 if discrete else 3
+    obs = rng.standard_normal((B, obs_dim)).astype(np.float32)
+    policy = _ref_policy(discrete, hidden, seed)
+    with torch.no_grad():
+        # perturb so logits / logstd are not at their symmetric init
+        for p in policy.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    sd0 = {k: v.detach().clone().numpy() for k, v in policy.state_dict().items()}
+    with torch.no_grad():
+        _, dist, v0 = policy(obs)
+        act_t = dist.stochastic_sample()
+        logp0 = dist.log_prob(act_t).numpy()
+    act = act_t.numpy().astype(np.float32)                     # the buffer stores actions as float32 (memory_tools.py:173)
+    old_logp = (logp0 + 0.1 * rng.standard_normal(B)).astype(np.float32)
+    adv = rng.standard_normal(B).astype(np.float32)
+    ret = (v0.numpy() + rng.standard_normal(B)).astype(np.float32)
+    val = v0.numpy().astype(np.float32)
+    out = dict(obs=obs, act=act, ret=ret, val=val, adv=adv, old_logp=old_logp,
+               meta=np.array(json.dumps(dict(discrete=discrete, hidden=hidden, B=B, **hp))))
+    for k, v in sd0.items():
+        out["p0/" + k] = v
+    for clip in (False, True):
+        policy.load_state_dict({k: torch.as_tensor(v) for k, v in sd0.items()})
+        opt = torch.optim.Adam(policy.parameters(), 4e-4, eps=1e-5)
+        sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=1000)
+        learner = PPOCLIP_Learner(policy, opt, sched, "cpu", "/tmp/xb200_goldens_models", vf_coef=hp["vf_coef"],
+                                  ent_coef=hp["ent_coef"], clip_range=hp["clip_range"],
+                                  clip_grad_norm=hp["clip_grad_norm"], use_grad_clip=clip)
+        info = learner.update(obs, act, ret, val, adv, old_logp)
+        tag = "clip" if clip else "noclip"
+        for k, v in info.items():
+            out["info_%s/%s" % (tag, k)] = np.asarray(float(v))
+        for k, p in policy.named_parameters():
+            out["grad_%s/%s" % (tag, k)] = p.grad.detach().numpy().copy()
+            out["p1_%s/%s" % (tag, k)] = p.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name)
+
+
+def gen_vecenv(name, env_id, n, steps, seed=1):
+    """Reference DummyVecEnv_Gym protocol over the restated physics (libm flavour, as gym would run on a host)."""
+    from xuance.environment import DummyVecEnv_Gym, Gym_Env
+    envs = DummyVecEnv_Gym([lambda: Gym_Env(env_id, seed, "rgb_array") for _ in range(n)])
+    obs0, infos0 = envs.reset()
+    rng = np.random.default_rng(7)
+    rec = dict(obs0=obs0, actions=[], obs=[], rew=[], term=[], trunc=[], ep_step=[], ep_score=[], reset_obs=[])
+    for t in range(steps):
+        if env_id == "CartPole-v1":
+            # alternate a stabilising heuristic (reaches the 500-step truncation) with random actions
+            th, thd = envs.buf_obs[:, 2], envs.buf_obs[:, 3]
+            a = np.where(rng.random(n) < 0.85, (th + 0.5 * thd > 0).astype(np.int64), rng.integers(0, 2, n))
+            a[n // 2:] = rng.integers(0, 2, n - n // 2)
+        else:
+            a = (1.5 * rng.standard_normal((n, 1))).astype(np.float32)
+        o, r, d, tr, infos = envs.step(a)
+        ro = np.full_like(o, np.nan)
+        for i, inf in enumerate(infos):
+            if "reset_obs" in inf:
+                ro[i] = inf["reset_obs"]
+        rec["actions"].append(a); rec["obs"].append(o); rec["rew"].append(r); rec["term"].append(d)
+        rec["trunc"].append(tr); rec["reset_obs"].append(ro)
+        rec["ep_step"].append([inf["episode_step"] for inf in infos])
+        rec["ep_score"].append([inf["episode_score"] for inf in infos])
+    out = {k: (np.asarray(v) if k != "obs0" else v) for k, v in rec.items()}
+    out["meta"] = np.array(json.dumps(dict(env_id=env_id, n=n, steps=steps, seed=seed, trig="libm",
+                                           max_episode_length=int(envs.max_episode_length))))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, "terminals", int(out["term"].sum()), "truncations", int(out["trunc"].sum()))
+
+
+def gen_physics(name, env_id, n, steps, seed=1):
+    """Tier-1 tapes: the C oracle with correctly-rounded trig; fp64 states recorded bit-for-bit."""
+    env = c_oracle.VecEnvC(env_id, n, seed=seed, flavour="cr")
+    rng = np.random.default_rng(11)
+    rec = dict(obs0=env.obs.copy(), state0=env.state.copy(), actions=[], obs=[], rew=[], term=[], trunc=[],
+               state=[], reset_obs=[], ep_step=[], ep_score=[])
+    for t in range(steps):
+        if env_id == "CartPole-v1":
+            th, thd = env.obs[:, 2], env.obs[:, 3]
+            a = np.where(rng.random(n) < 0.9, (th + 0.5 * thd > 0).astype(np.int64), rng.integers(0, 2, n))
+            a[n // 2:] = rng.integers(0, 2, n - n // 2)
+        else:
+            a = (1.5 * rng.standard_normal(n)).astype(np.float32)
+        o = env.step(a)
+        rec["actions"].append(a)
+        for k in ("obs", "rew", "term", "trunc", "state", "reset_obs", "ep_step", "ep_score"):
+            rec[k].append(o[k])
+    out = {k: np.asarray(v) for k, v in rec.items()}
+    out["meta"] = np.array(json.dumps(dict(env_id=env_id, n=n, steps=steps, seed=seed, trig="cr")))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, "terminals", int(out["term"].sum()), "truncations", int(out["trunc"].sum()))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref_loader.load(trig="libm")
+    hp = dict(vf_coef=0.25, ent_coef=0.01, clip_range=0.2, clip_grad_norm=0.5)
+    gen_buffer("buffer_cat_gae", 101, 6, 48, True, True, True, 0.99, 0.95)
+    gen_buffer("buffer_box_gae_noadvnorm", 102, 5, 40, False, True, False, 0.98, 0.95)
+    gen_buffer("buffer_cat_nogae", 103, 4, 32, True, False, True, 0.99, 0.95)
+    gen_loss("loss_cat_h64", 201, True, 64, 512, hp)
+    gen_loss("loss_gauss_h128", 202, False, 128, 1024, hp)
+    gen_vecenv("vecenv_cartpole", "CartPole-v1", 6, 700)
+    gen_vecenv("vecenv_pendulum", "Pendulum-v1", 4, 450)
+    gen_physics("physics_cartpole_cr", "CartPole-v1", 12, 1100)
+    gen_physics("physics_pendulum_cr", "Pendulum-v1", 8, 450)
+
+
+if __name__ == "__main__":
+    main()

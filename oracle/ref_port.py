@@ -1,0 +1,280 @@
+"""CPU restatement ("port") of the reference's on-policy PPO hot path, numpy + torch-CPU.
+
+ORACLE / TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this; the product (xuanpolicy_b200/) never does.
+
+The reference is Python and lives at /root/reference, which does not travel to the GPU box.  This file
+restates — in the reference's own cost structure (per-env Python loops, host numpy buffers, torch eager
+CPU) — the functions on the path, so that (i) GPU parity tests have a checker there and (ii) the CPU
+baseline timed beside the B200 numbers is the reference's algorithm, not a vectorised rewrite:
+
+    VecEnvPort          DummyVecEnv_Gym.reset/step_async/step_wait   xuance/environment/gym/gym_vec_env.py:155-212
+                        + Gym_Env.reset/step bookkeeping              xuance/environment/gym/gym_env.py:36-49
+    OnPolicyBufferPort  DummyOnPolicyBuffer.store/finish_path/sample  xuance/common/memory_tools.py:143-245
+    ppo_clip_update     PPOCLIP_Learner.update                        xuance/torch/learners/policy_gradient/ppoclip_learner.py:24-65
+    RunningMeanStdPort  RunningMeanStd                                xuance/common/statistic_tools.py:35-112
+    PPOAgentPort.train  PPOCLIP_Agent.train                           xuance/torch/agents/policy_gradient/ppoclip_agent.py:59-111
+
+PINNING: tests/test_oracle_vs_reference.py runs these against the live reference (through
+oracle/ref_loader.py) when /root/reference is present, and against tests/golden/*.npz (generated from the
+live reference by oracle/make_goldens.py) everywhere.  The physics underneath (oracle/gym_restated.py) is
+"parity unpinned" — see its header.
+"""
+import numpy as np
+import torch
+
+from . import gym_restated
+
+
+# ------------------------------------------------------------------------------------------------ vec env
+class VecEnvPort:
+    """Serial vector env with xuance's auto-reset protocol (terminal obs in buf_obs, reset obs in infos)."""
+
+    def __init__(self, env_id, num_envs, seed=1, trig="libm"):
+        self.num_envs = num_envs
+        self.envs = []
+        for _ in range(num_envs):
+            env = gym_restated.make(env_id, trig=trig)
+            env.reset(seed=seed)                          # gym_env.py:19 (every env gets the same seed)
+            self.envs.append(env)
+        self.max_episode_length = self.envs[0]._max_episode_steps
+        self.observation_space = self.envs[0].observation_space
+        self.action_space = self.envs[0].action_space
+        odim = self.observation_space.shape[0]
+        self.buf_obs = np.zeros((num_envs, odim), np.float32)
+        self.buf_rews = np.zeros(num_envs, np.float32)
+        self.buf_dones = np.zeros(num_envs, bool)
+        self.buf_trunctions = np.zeros(num_envs, bool)
+        self.buf_infos = [{} for _ in range(num_envs)]
+        self._ep_step = [0] * num_envs
+        self._ep_score = [0.0] * num_envs
+
+    def _reset_one(self, e):
+        obs, info = self.envs[e].reset()
+        self._ep_step[e], self._ep_score[e] = 0, 0.0
+        info["episode_step"] = 0
+        return obs, info
+
+    def reset(self):
+        for e in range(self.num_envs):
+            self.buf_obs[e], self.buf_infos[e] = self._reset_one(e)
+        return self.buf_obs.copy(), self.buf_infos.copy()
+
+    def step(self, actions):
+        for e in range(self.num_envs):
+            obs, rew, term, trunc, info = self.envs[e].step(actions[e])
+            self._ep_step[e] += 1
+            self._ep_score[e] += rew
+            info["episode_step"], info["episode_score"] = self._ep_step[e], self._ep_score[e]
+            self.buf_rews[e], self.buf_dones[e], self.buf_trunctions[e], self.buf_infos[e] = rew, term, trunc, info
+            if term or trunc:
+                info["reset_obs"], _ = self._reset_one(e)
+            self.buf_obs[e] = obs
+        return (self.buf_obs.copy(), self.buf_rews.copy(), self.buf_dones.copy(), self.buf_trunctions.copy(),
+                self.buf_infos.copy())
+
+
+# ------------------------------------------------------------------------------------------------ buffer
+class OnPolicyBufferPort:
+    """Env-major [n_envs, n_size] float32 host buffer; GAE by a per-env reverse loop.
+
+    Precision: the recurrence is carried in float64 and rounded once on store, which is what the pinned
+    numpy 1.21.6 does (np.float32 * python-float promotes to float64, memory_tools.py:218-221); under
+    numpy >= 2 the live reference mixes float32/float64.  Both lie within the 1e-5
+    GAE tolerance of each other.
+    """
+
+    def __init__(self, obs_shape, act_shape, n_envs, n_size, use_gae=True, use_advnorm=True, gamma=0.99, gae_lam=0.95):
+        self.obs_shape, self.act_shape = tuple(obs_shape), tuple(act_shape)
+        self.n_envs, self.n_size = n_envs, n_size
+        self.buffer_size = n_envs * n_size
+        self.use_gae, self.use_advnorm, self.gamma, self.gae_lam = use_gae, use_advnorm, gamma, gae_lam
+        self.start_ids = np.zeros(n_envs, np.int64)
+        self.clear()
+
+    def _zeros(self, shape=()):
+        return np.zeros((self.n_envs, self.n_size) + tuple(shape), np.float32)
+
+    def clear(self):
+        self.ptr, self.size = 0, 0
+        self.observations, self.actions = self._zeros(self.obs_shape), self._zeros(self.act_shape)
+        self.rewards, self.returns, self.values = self._zeros(), self._zeros(), self._zeros()
+        self.terminals, self.advantages = self._zeros(), self._zeros()
+        self.auxiliary_infos = {"old_logp": self._zeros()}
+
+    @property
+    def full(self):
+        return self.size >= self.n_size
+
+    def store(self, obs, acts, rews, value, terminals, aux_info=None):
+        p = self.ptr
+        self.observations[:, p], self.actions[:, p] = obs, acts
+        self.rewards[:, p], self.values[:, p], self.terminals[:, p] = rews, value, terminals
+        if aux_info is not None:
+            for k, v in aux_info.items():
+                self.auxiliary_infos[k][:, p] = v
+        self.ptr = (p + 1) % self.n_size
+        self.size = min(self.size + 1, self.n_size)
+
+    def finish_path(self, val, i):
+        lo, hi = int(self.start_ids[i]), (self.n_size if self.full else self.ptr)
+        r = self.rewards[i, lo:hi].astype(np.float64)
+        v = np.append(self.values[i, lo:hi].astype(np.float64), float(val))
+        if self.use_gae:
+            d = self.terminals[i, lo:hi].astype(np.float64)
+            adv = np.zeros(hi - lo, np.float64)
+            acc = 0.0
+            for t in range(hi - lo - 1, -1, -1):
+                delta = r[t] + (1 - d[t]) * self.gamma * v[t + 1] - v[t]
+                acc = delta + (1 - d[t]) * self.gamma * self.gae_lam * acc
+                adv[t] = acc
+            ret = adv + v[:-1]
+        else:
+            ret = np.zeros(hi - lo, np.float64)
+            run = float(val)
+            for t in range(hi - lo - 1, -1, -1):          # == discount_cumsum(append(r,[val]))[:-1]
+                run = r[t] + self.gamma * run
+                ret[t] = run
+            adv = r + self.gamma * v[1:] - v[:-1]
+        self.returns[i, lo:hi] = ret
+        self.advantages[i, lo:hi] = adv
+        self.start_ids[i] = self.ptr
+
+    def sample(self, indexes):
+        assert self.full, "Not enough transitions for on-policy buffer to random sample"
+        env, step = np.divmod(np.asarray(indexes), self.n_size)
+        adv = self.advantages[env, step]
+        if self.use_advnorm:
+            adv = (adv - np.mean(adv)) / (np.std(adv) + 1e-8)
+        return (self.observations[env, step], self.actions[env, step], self.returns[env, step],
+                self.values[env, step], adv, {k: a[env, step] for k, a in self.auxiliary_infos.items()})
+
+
+# ------------------------------------------------------------------------------------------------ learner
+def policy_logp_entropy(policy, obs, act):
+    """Runs a reference-shaped actor-critic module: returns (log_prob, entropy, v_pred)."""
+    _, dist, v = policy(obs)
+    return dist.log_prob(act), dist.entropy(), v
+
+
+def ppo_clip_loss(logp, entropy, v_pred, ret, adv, old_logp, vf_coef, ent_coef, clip_range):
+    ratio = (logp - old_logp).exp().float()
+    unclipped = adv * ratio
+    clipped = ratio.clamp(1.0 - clip_range, 1.0 + clip_range) * adv
+    a_loss = -torch.minimum(clipped, unclipped).mean()
+    c_loss = torch.nn.functional.mse_loss(v_pred, ret)
+    e_loss = entropy.mean()
+    return a_loss - ent_coef * e_loss + vf_coef * c_loss, a_loss, c_loss, e_loss, ratio
+
+
+def ppo_clip_update(policy, optimizer, scheduler, batch, vf_coef=0.25, ent_coef=0.005, clip_range=0.25,
+                    clip_grad_norm=0.25, use_grad_clip=True, device="cpu"):
+    """One PPOCLIP_Learner.update step.  `batch` = (obs, act, ret, value, adv, old_logp) as sample() returns."""
+    obs, act, ret, _value_unused, adv, old_logp = batch
+    act, ret, adv, old_logp = (torch.as_tensor(a, device=device) for a in (act, ret, adv, old_logp))
+    logp, ent, v_pred = policy_logp_entropy(policy, obs, act)
+    loss, a_loss, c_loss, e_loss, ratio = ppo_clip_loss(logp, ent, v_pred, ret, adv, old_logp, vf_coef, ent_coef, clip_range)
+    optimizer.zero_grad()
+    loss.backward()
+    if use_grad_clip:
+        torch.nn.utils.clip_grad_norm_(policy.parameters(), clip_grad_norm)
+    optimizer.step()
+    if scheduler is not None:
+        scheduler.step()
+    n_clipped = (ratio < 1 - clip_range).sum() + (ratio > 1 + clip_range).sum()
+    return {"actor-loss": a_loss.item(), "critic-loss": c_loss.item(), "entropy": e_loss.item(),
+            "learning_rate": optimizer.state_dict()["param_groups"][0]["lr"],
+            "predict_value": v_pred.mean().item(), "clip_ratio": n_clipped / ratio.shape[0]}
+
+
+# ------------------------------------------------------------------------------------------------ normaliser
+class RunningMeanStdPort:
+    def __init__(self, shape, epsilon=1e-4):
+        self.mean, self.var, self.count = np.zeros(shape, np.float32), np.ones(shape, np.float32), epsilon
+
+    @property
+    def std(self):
+        return np.sqrt(self.var)
+
+    def update(self, x):
+        b_mean, b_var, b_n = np.mean(x, axis=0), np.square(np.std(x, axis=0)), x.shape[0]
+        delta, tot = b_mean - self.mean, self.count + b_n
+        m2 = self.var * self.count + b_var * b_n + np.square(delta) * self.count * b_n / tot
+        self.mean, self.var, self.count = self.mean + delta * b_n / tot, m2 / tot, tot
+
+
+# ------------------------------------------------------------------------------------------------ agent loop
+class PPOAgentPort:
+    """PPOCLIP_Agent.train restated (logging/Atari branches removed)."""
+
+    def __init__(self, envs, policy, optimizer, scheduler, n_steps, n_epoch, n_minibatch, gamma, gae_lam,
+                 vf_coef=0.25, ent_coef=0.01, clip_range=0.2, clip_grad_norm=0.5, use_grad_clip=True,
+                 use_gae=True, use_advnorm=True, use_obsnorm=False, use_rewnorm=False, obsnorm_range=5, rewnorm_range=5):
+        self.envs, self.policy, self.optimizer, self.scheduler = envs, policy, optimizer, scheduler
+        self.n_envs, self.n_steps, self.n_epoch = envs.num_envs, n_steps, n_epoch
+        self.buffer_size = self.n_envs * n_steps
+        self.batch_size = self.buffer_size // n_minibatch
+        self.gamma = gamma
+        act_shape = () if not hasattr(envs.action_space, "low") else envs.action_space.shape
+        self.memory = OnPolicyBufferPort(envs.observation_space.shape, act_shape, self.n_envs, n_steps,
+                                         use_gae, use_advnorm, gamma, gae_lam)
+        self.hp = dict(vf_coef=vf_coef, ent_coef=ent_coef, clip_range=clip_range, clip_grad_norm=clip_grad_norm,
+                       use_grad_clip=use_grad_clip)
+        self.use_obsnorm, self.use_rewnorm = use_obsnorm, use_rewnorm
+        self.obsnorm_range, self.rewnorm_range = obsnorm_range, rewnorm_range
+        self.obs_rms = RunningMeanStdPort(envs.observation_space.shape)
+        self.ret_rms = RunningMeanStdPort(())
+        self.returns = np.zeros(self.n_envs, np.float32)
+        self.current_step, self.episodes, self.last_info = 0, 0, {}
+
+    def _obs(self, o):
+        if not self.use_obsnorm:
+            return o
+        return np.clip((o - self.obs_rms.mean) / (self.obs_rms.std + 1e-8), -self.obsnorm_range, self.obsnorm_range)
+
+    def _rew(self, r):
+        if not self.use_rewnorm:
+            return r
+        return np.clip(r / np.clip(self.ret_rms.std, 0.1, 100), -self.rewnorm_range, self.rewnorm_range)
+
+    def _action(self, obs):
+        _, dist, v = self.policy(obs)
+        a = dist.stochastic_sample()
+        lp = dist.log_prob(a)
+        return a.detach().cpu().numpy(), v.detach().cpu().numpy(), lp.detach().cpu().numpy()
+
+    def train(self, train_steps):
+        obs = self.envs.buf_obs
+        mem = self.memory
+        for _ in range(train_steps):
+            self.obs_rms.update(obs)
+            obs = self._obs(obs)
+            acts, value, logps = self._action(obs)
+            next_obs, rewards, terminals, truncations, infos = self.envs.step(acts)
+            mem.store(obs, acts, self._rew(rewards), value, terminals, {"old_logp": logps})
+            if mem.full:
+                _, vals, _ = self._action(self._obs(next_obs))
+                for i in range(self.n_envs):
+                    mem.finish_path(0.0 if terminals[i] else vals[i], i)
+                indexes = np.arange(self.buffer_size)
+                for _ in range(self.n_epoch):
+                    np.random.shuffle(indexes)
+                    for start in range(0, self.buffer_size, self.batch_size):
+                        batch = mem.sample(indexes[start:start + self.batch_size])
+                        self.last_info = ppo_clip_update(self.policy, self.optimizer, self.scheduler,
+                                                         batch[:5] + (batch[5]["old_logp"],), **self.hp)
+                mem.clear()
+            self.returns = (1 - terminals) * self.gamma * self.returns + rewards
+            obs = next_obs
+            for i in range(self.n_envs):
+                if terminals[i] or truncations[i]:
+                    self.ret_rms.update(self.returns[i:i + 1])
+                    self.returns[i] = 0.0
+                    if terminals[i]:
+                        mem.finish_path(0.0, i)
+                    else:
+                        _, vals, _ = self._action(self._obs(next_obs))
+                        mem.finish_path(vals[i], i)
+                    obs[i] = infos[i]["reset_obs"]
+                    self.episodes += 1
+            self.current_step += self.n_envs

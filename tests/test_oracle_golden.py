@@ -1,0 +1,171 @@
+"""CPU: pin the oracle (oracle/ref_port.py, oracle/classic_control.c, oracle/gym_restated.py) against the
+golden vectors generated from the live reference (oracle/make_goldens.py), and against numpy's PCG64."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, gym_restated, ref_port
+from tests.helpers import gae_close, load_golden, rel_close, replay_buffer_protocol
+from xuanpolicy_b200 import policies, spaces
+
+
+def test_pcg64_matches_numpy():
+    for seed in (0, 1, 12345):
+        rng = c_oracle.pcg64_state(seed)
+        got = c_oracle.pcg64_uniform(rng, -0.05, 0.05, 64)
+        g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+        assert np.array_equal(got, g.uniform(-0.05, 0.05, size=64))
+    rng = c_oracle.pcg64_state(1)
+    g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(1)))
+    high = np.array([math.pi, 1.0])
+    for _ in range(5):
+        ref = g.uniform(low=-high, high=high)
+        got = [c_oracle.pcg64_uniform(rng, -math.pi, math.pi, 1)[0], c_oracle.pcg64_uniform(rng, -1.0, 1.0, 1)[0]]
+        assert np.array_equal(ref, got)
+
+
+def test_survey_kats():
+    """SURVEY.md §8(c) known-answer vectors (self-derived from the published equations)."""
+    e = gym_restated.CartPoleRestated("cr", with_spaces=False)
+    e.state = (0.01, 0.02, 0.03, 0.04)
+    e.step(1)
+    assert [v.hex() for v in e.state] == ["0x1.54c985f06f694p-7", "0x1.b7a9b9e6f04bcp-3", "0x1.f8a0902de00d1p-6",
+                                          "-0x1.f1ce03128d125p-3"]
+    e.step(0)
+    assert [v.hex() for v in e.state] == ["0x1.e17ab73018774p-7", "0x1.3971dd068cec8p-6", "0x1.a8fa7b3525a3cp-6",
+                                          "0x1.e4b44a16b46c4p-5"]
+    p = gym_restated.PendulumRestated("cr", with_spaces=False)
+    p.state = (1.0, 0.5)
+    _, r, _, _, _ = p.step(np.array([0.7], np.float32))
+    assert [v.hex() for v in p.state] == ["0x1.0fd2768cd4a2ap+0", "0x1.3c7143009cb40p+0"]
+    assert (-(-r)).hex() == "-0x1.0686833c4da90p+0"
+    g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(1)))
+    assert g.uniform(-0.05, 0.05, 4).tolist() == [0.0011821624700256717, 0.045046369632593536,
+                                                   -0.03558403872803663, 0.04486494471372439]
+
+
+def test_c_sincos_cr_matches_mpmath():
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-0.5, 0.5, 1500), rng.uniform(-90, 90, 1500), [0.0, -0.0, 1e-300, math.pi / 2]])
+    s, c = c_oracle.sincos(x, "cr")
+    for xi, si, ci in zip(x, s, c):
+        assert si == gym_restated._sin_cr(float(xi)) and ci == gym_restated._cos_cr(float(xi))
+
+
+@pytest.mark.parametrize("name", ["physics_cartpole_cr", "physics_pendulum_cr"])
+def test_physics_tape_c_and_python_agree(name):
+    g = load_golden(name)
+    m = g["meta"]
+    env = c_oracle.VecEnvC(m["env_id"], m["n"], seed=m["seed"], flavour="cr")
+    assert np.array_equal(env.state, g["state0"]) and np.array_equal(env.obs, g["obs0"])
+    pys = [gym_restated.make(m["env_id"], trig="cr") for _ in range(2)]
+    for pe in pys:
+        pe.reset(seed=m["seed"])
+        pe.reset()
+    for t in range(m["steps"]):
+        o = env.step(g["actions"][t])
+        for k in ("obs", "rew", "term", "trunc", "state", "ep_step", "ep_score"):
+            assert np.array_equal(o[k], g[k][t]), (k, t)
+        done = o["term"] | o["trunc"]
+        assert np.array_equal(o["reset_obs"][done], g["reset_obs"][t][done])
+        if t < 260:  # the (slow, mpmath) Python restatement follows the first two envs
+            for i, pe in enumerate(pys):
+                a = g["actions"][t][i]
+                ob, rw, te, tr, _ = pe.step(int(a) if m["env_id"] == "CartPole-v1" else np.array([a], np.float32))
+                assert np.array_equal(ob, g["obs"][t][i]) and np.float32(rw) == g["rew"][t][i]
+                if te or tr:     # the tape's fp64 state is recorded after the auto-reset
+                    ro, _ = pe.reset()
+                    assert np.array_equal(ro, g["reset_obs"][t][i])
+                assert np.array_equal(np.array(pe.env.state), g["state"][t][i])
+
+
+@pytest.mark.parametrize("name", ["vecenv_cartpole", "vecenv_pendulum"])
+def test_vecenv_port_matches_reference_golden(name):
+    """ref_port.VecEnvPort and the C oracle (libm flavour) vs the reference DummyVecEnv_Gym run."""
+    g = load_golden(name)
+    m = g["meta"]
+    port = ref_port.VecEnvPort(m["env_id"], m["n"], seed=m["seed"], trig="libm")
+    cenv = c_oracle.VecEnvC(m["env_id"], m["n"], seed=m["seed"], flavour="libm")
+    obs0, _ = port.reset()
+    assert np.array_equal(obs0, g["obs0"]) and np.array_equal(cenv.obs, g["obs0"])
+    assert port.max_episode_length == m["max_episode_length"]
+    for t in range(m["steps"]):
+        a = g["actions"][t]
+        o, r, d, tr, infos = port.step(a)
+        co = cenv.step(a)
+        assert np.array_equal(o, g["obs"][t]) and np.array_equal(r, g["rew"][t])
+        assert np.array_equal(d, g["term"][t]) and np.array_equal(tr, g["trunc"][t])
+        assert [i["episode_step"] for i in infos] == g["ep_step"][t].tolist()
+        assert [i["episode_score"] for i in infos] == g["ep_score"][t].tolist()
+        assert np.array_equal(co["obs"], g["obs"][t]) and np.array_equal(co["rew"], g["rew"][t])
+        assert np.array_equal(co["term"], g["term"][t]) and np.array_equal(co["trunc"], g["trunc"][t])
+        assert np.array_equal(co["ep_step"], g["ep_step"][t]) and np.array_equal(co["ep_score"], g["ep_score"][t])
+        for i, inf in enumerate(infos):
+            if d[i] or tr[i]:
+                assert np.array_equal(inf["reset_obs"], g["reset_obs"][t][i])
+                assert np.array_equal(co["reset_obs"][i], g["reset_obs"][t][i])
+            else:
+                assert "reset_obs" not in inf
+
+
+@pytest.mark.parametrize("name", ["buffer_cat_gae", "buffer_box_gae_noadvnorm", "buffer_cat_nogae"])
+def test_buffer_port_matches_reference_golden(name):
+    g = load_golden(name)
+    m = g["meta"]
+    obs_shape = g["obs"].shape[2:]
+    act_shape = g["act"].shape[2:]
+    buf = ref_port.OnPolicyBufferPort(obs_shape, act_shape, m["n_envs"], m["n_size"], m["use_gae"], m["use_advnorm"],
+                                      m["gamma"], m["lam"])
+    replay_buffer_protocol(buf, g)
+    assert np.array_equal(buf.observations, g["observations"]) and np.array_equal(buf.actions, g["actions"])
+    ok, err = gae_close(buf.advantages, g["advantages"])
+    assert ok, err
+    ok, err = gae_close(buf.returns, g["returns"])
+    assert ok, err
+    # the batched fp64 form used as the GPU target
+    adv64, ret64 = c_oracle.gae(g["rew"], g["val"], g["term"].astype(np.float32), g["boot"][-1], m["gamma"], m["lam"],
+                                segend=g["trunc"].astype(np.uint8), boot=g["boot"], use_gae=m["use_gae"])
+    ok, err = gae_close(adv64.T, g["advantages"])
+    assert ok, err
+    ok, err = gae_close(ret64.T, g["returns"])
+    assert ok, err
+    for k in range(g["idx"].shape[0]):
+        o, a, r, v, adv, aux = buf.sample(g["idx"][k])
+        assert np.array_equal(o, g["s_obs"][k]) and np.array_equal(a, g["s_act"][k])
+        assert np.array_equal(v, g["s_val"][k]) and np.array_equal(aux["old_logp"], g["s_logp"][k])
+        assert gae_close(r, g["s_ret"][k])[0]
+        assert np.allclose(adv, g["s_adv"][k], rtol=0, atol=2e-5), np.abs(adv - g["s_adv"][k]).max()
+
+
+def _policy_from_golden(g):
+    m = g["meta"]
+    if m["discrete"]:
+        obs_space, act_space = spaces.Box(-1, 1, (4,)), spaces.Discrete(2)
+    else:
+        obs_space, act_space = spaces.Box(-1, 1, (3,)), spaces.Box(-2.0, 2.0, (1,))
+    pol = policies.make_policy(obs_space, act_space, hidden=(m["hidden"],), device="cpu")
+    sd = {k[3:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("p0/")}
+    pol.load_state_dict(sd, strict=True)     # same parameter names as the reference modules
+    return pol
+
+
+@pytest.mark.parametrize("name", ["loss_cat_h64", "loss_gauss_h128"])
+def test_learner_port_matches_reference_golden(name):
+    g = load_golden(name)
+    m = g["meta"]
+    for tag, clip in (("noclip", False), ("clip", True)):
+        pol = _policy_from_golden(g)
+        opt = torch.optim.Adam(pol.parameters(), 4e-4, eps=1e-5)
+        sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=1000)
+        info = ref_port.ppo_clip_update(pol, opt, sched, (g["obs"], g["act"], g["ret"], g["val"], g["adv"], g["old_logp"]),
+                                        vf_coef=m["vf_coef"], ent_coef=m["ent_coef"], clip_range=m["clip_range"],
+                                        clip_grad_norm=m["clip_grad_norm"], use_grad_clip=clip)
+        for k in ("actor-loss", "critic-loss", "entropy", "learning_rate", "predict_value", "clip_ratio"):
+            assert abs(float(info[k]) - float(g["info_%s/%s" % (tag, k)])) <= 1e-5 * max(1.0, abs(float(g["info_%s/%s" % (tag, k)]))), k
+        for k, p in pol.named_parameters():
+            ok, err = rel_close(p.grad.numpy(), g["grad_%s/%s" % (tag, k)], 1e-4)
+            assert ok, (k, err)
+            ok, err = rel_close(p.detach().numpy(), g["p1_%s/%s" % (tag, k)], 1e-5)
+            assert ok, (k, err)

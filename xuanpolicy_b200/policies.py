@@ -1,0 +1,174 @@
+"""Actor-critic torch modules for the PPO path (the GEMMs stay in torch / cuBLAS by design).
+
+These mirror the *interface and parameter naming* of the reference modules so a `state_dict` moves between
+the two unchanged and `PPOCLIP_Learner.update` can drive either:
+
+    MLPRepresentation      <-> Basic_MLP               xuance/torch/representations/mlp.py:21-51
+    CategoricalActorCritic <-> Categorical_AC_Policy   xuance/torch/policies/categorical.py:16-85
+    GaussianActorCritic    <-> Gaussian_AC_Policy      xuance/torch/policies/gaussian.py:8-77
+    distributions          <-> xuance/torch/utils/distributions.py:39-101
+
+`forward(obs)` returns `(outputs_dict, dist, value)` exactly like the reference.  When the drop-in classes are
+used behind the reference's own runner, the reference's modules are used instead and these are not needed.
+"""
+import math
+from typing import Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+_HALF_LOG_2PI = 0.5 * math.log(2.0 * math.pi)
+
+
+def _dense_stack(sizes: Sequence[int], act, init, device, last_plain=False, last_init=True):
+    """[Linear, act, Linear, act, ...]; with last_plain the final Linear has no activation."""
+    mods = []
+    for k in range(len(sizes) - 1):
+        lin = nn.Linear(sizes[k], sizes[k + 1], device=device)
+        final = k == len(sizes) - 2
+        if init is not None and (last_init or not final):
+            init(lin.weight)
+            nn.init.zeros_(lin.bias)
+        mods.append(lin)
+        if not (final and last_plain):
+            mods.append(act())
+    return nn.Sequential(*mods)
+
+
+class MLPRepresentation(nn.Module):
+    def __init__(self, input_shape, hidden_sizes, normalize=None, initialize=nn.init.orthogonal_,
+                 activation=nn.LeakyReLU, device=None):
+        super().__init__()
+        assert normalize is None, "normalisation layers are not on the PPO classic-control path"
+        self.input_shape, self.hidden_sizes, self.device = tuple(input_shape), list(hidden_sizes), device
+        self.output_shapes = {"state": (self.hidden_sizes[-1],)}
+        self.model = _dense_stack([self.input_shape[0]] + self.hidden_sizes, activation, initialize, device)
+
+    def forward(self, observations):
+        x = torch.as_tensor(observations, dtype=torch.float32, device=self.device)
+        return {"state": self.model(x)}
+
+
+class CategoricalDistribution:
+    def __init__(self, action_dim):
+        self.action_dim = action_dim
+        self.logits = None
+
+    def set_param(self, logits):
+        self.logits = logits
+        self._logp = logits - logits.logsumexp(dim=-1, keepdim=True)
+
+    def get_param(self):
+        return self.logits
+
+    def log_prob(self, x):
+        return self._logp.gather(-1, x.long().unsqueeze(-1)).squeeze(-1)
+
+    def entropy(self):
+        return -(self._logp.exp() * self._logp).sum(-1)
+
+    def stochastic_sample(self):
+        return torch.multinomial(self._logp.exp(), 1).squeeze(-1)
+
+    def deterministic_sample(self):
+        return torch.argmax(self._logp, dim=1)
+
+
+class DiagGaussianDistribution:
+    def __init__(self, action_dim):
+        self.action_dim = action_dim
+        self.mu = self.std = None
+
+    def set_param(self, mu, std):
+        self.mu, self.std = mu, std
+
+    def get_param(self):
+        return self.mu, self.std
+
+    def log_prob(self, x):
+        var = self.std ** 2
+        return (-((x - self.mu) ** 2) / (2 * var) - self.std.log() - _HALF_LOG_2PI).sum(-1)
+
+    def entropy(self):
+        return (0.5 + _HALF_LOG_2PI + self.std.log()).expand_as(self.mu).sum(-1)
+
+    def stochastic_sample(self):
+        with torch.no_grad():
+            return torch.normal(self.mu, self.std.expand_as(self.mu))
+
+    def deterministic_sample(self):
+        return self.mu
+
+
+class _CategoricalActor(nn.Module):
+    def __init__(self, state_dim, action_dim, hidden, act, init, device):
+        super().__init__()
+        self.model = _dense_stack([state_dim] + list(hidden) + [action_dim], act, init, device, last_plain=True)
+        self.dist = CategoricalDistribution(action_dim)
+
+    def forward(self, x):
+        self.dist.set_param(self.model(x))
+        return self.dist
+
+
+class _GaussianActor(nn.Module):
+    def __init__(self, state_dim, action_dim, hidden, act, init, device):
+        super().__init__()
+        self.mu = _dense_stack([state_dim] + list(hidden) + [action_dim], act, init, device, last_plain=True)
+        self.logstd = nn.Parameter(-torch.ones((action_dim,), device=device))
+        self.dist = DiagGaussianDistribution(action_dim)
+
+    def forward(self, x):
+        self.dist.set_param(self.mu(x), self.logstd.exp())
+        return self.dist
+
+
+class _Critic(nn.Module):
+    def __init__(self, state_dim, hidden, act, init, device, last_init=True):
+        super().__init__()
+        self.model = _dense_stack([state_dim] + list(hidden) + [1], act, init, device, last_plain=True,
+                                  last_init=last_init)
+
+    def forward(self, x):
+        return self.model(x)[:, 0]
+
+
+class _ActorCritic(nn.Module):
+    def forward(self, observation):
+        outputs = self.representation(observation)
+        return outputs, self.actor(outputs["state"]), self.critic(outputs["state"])
+
+
+class CategoricalActorCritic(_ActorCritic):
+    def __init__(self, action_space, representation, actor_hidden_size, critic_hidden_size, normalize=None,
+                 initialize=nn.init.orthogonal_, activation=nn.LeakyReLU, device=None):
+        super().__init__()
+        self.device, self.action_dim, self.representation = device, action_space.n, representation
+        self.representation_info_shape = representation.output_shapes
+        sd = representation.output_shapes["state"][0]
+        self.actor = _CategoricalActor(sd, self.action_dim, actor_hidden_size, activation, initialize, device)
+        self.critic = _Critic(sd, critic_hidden_size, activation, initialize, device)
+
+
+class GaussianActorCritic(_ActorCritic):
+    def __init__(self, action_space, representation, actor_hidden_size, critic_hidden_size, normalize=None,
+                 initialize=nn.init.orthogonal_, activation=nn.LeakyReLU, device=None):
+        super().__init__()
+        self.device, self.action_dim, self.representation = device, action_space.shape[0], representation
+        self.representation_info_shape = representation.output_shapes
+        sd = representation.output_shapes["state"][0]
+        self.actor = _GaussianActor(sd, self.action_dim, actor_hidden_size, activation, initialize, device)
+        # the reference leaves the Gaussian critic's last layer at torch's default init (gaussian.py:47)
+        self.critic = _Critic(sd, critic_hidden_size, activation, initialize, device, last_init=False)
+
+
+def make_policy(observation_space, action_space, hidden=(128,), device=None, seed=None):
+    """Builds the `representation_hidden_size=actor_hidden_size=critic_hidden_size=hidden` policy of the yaml configs."""
+    from .spaces import is_discrete
+    if seed is not None:
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+    rep = MLPRepresentation(observation_space.shape, list(hidden), device=device)
+    cls = CategoricalActorCritic if is_discrete(action_space) else GaussianActorCritic
+    return cls(action_space, rep, list(hidden), list(hidden), device=device)
