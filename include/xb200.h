@@ -1,0 +1,182 @@
+/*
+ * xb200.h — C ABI of the B200-native PPO hot path (libxb200.so, hand-written sm_100a CUDA kernels).
+ *
+ * This is the drop-in boundary.  The reference (fanliaoooo/xuanpolicy, a XuanCe 1.0.5 fork) is pure Python;
+ * its own native-boundary idiom is a ctypes-loaded C library (xuance/environment/magent2/c_lib.py:10-23),
+ * and that is how this library is bound (xuanpolicy_b200/_lib.py; INTEGRATION.md shows the reference-side stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t): no allocation, no synchronisation, so every
+ *     call is CUDA-graph capturable;
+ *   - return value: 0 = ok, > 0 = a cudaError_t, < 0 = an XB_E_* argument error.  Nothing throws.
+ *   - rollout storage is TIME-MAJOR: element (step t, env e) of a per-transition scalar lives at [t*N + e];
+ *     the reference's flat sample index k means (env = k / T, step = k % T)  (memory_tools.py:234).
+ *   - observations are stored in rows of `XB_OBS_STRIDE` floats (16 B) so every row is one float4.
+ *
+ * Each entry point cites the reference code it replaces (paths relative to the reference root).
+ */
+#ifndef XB200_H
+#define XB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XB_VERSION 100
+#define XB_OBS_STRIDE 4
+
+#define XB_ENV_CARTPOLE 0 /* CartPole-v1: state (x, x_dot, theta, theta_dot), action int64 {0,1}, limit 500 */
+#define XB_ENV_PENDULUM 1 /* Pendulum-v1: state (theta, theta_dot), action float32 torque, limit 200 */
+
+#define XB_E_BADARG (-1)
+#define XB_E_UNSUPPORTED (-2)
+#define XB_E_DRIVER (-3)
+
+#define XB_GAE_AUTO 0
+#define XB_GAE_LDG 1 /* register-prefetch variant */
+#define XB_GAE_TMA 2 /* cp.async.bulk.tensor + mbarrier ring variant */
+
+typedef void* xb_stream_t; /* cudaStream_t */
+
+int xb_version(void);
+/* static string for a code returned by any entry point */
+const char* xb_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (1) Batched classic-control environments.  One thread per env, fp64 state in registers, every fp64 operation
+ * individually rounded (__dadd_rn/__dmul_rn/__ddiv_rn, TU built with -fmad=false), correctly-rounded sin/cos.
+ * Replaces  DummyVecEnv_Gym.reset / step_wait   xuance/environment/gym/gym_vec_env.py:177-212
+ *           Gym_Env.reset / step                xuance/environment/gym/gym_env.py:36-49
+ *           gym 0.26.2 CartPoleEnv / PendulumEnv / TimeLimit / np_random (third party, restated: SURVEY.md App. A/B)
+ *
+ * state     fp64 [S][N] (SoA; S = 4 CartPole, 2 Pendulum)
+ * rng       u64  [4][N] (SoA) numpy PCG64: state_hi, state_lo, inc_hi, inc_lo
+ * elapsed   i32  [N]    TimeLimit._elapsed_steps == Gym_Env._episode_step
+ * ep_score  fp64 [N]    Gym_Env._episode_score
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* n_draws consecutive env.reset() calls per env (xuance does 2 before the first step: gym_env.py:19 and
+ * runner_basic.py:12); zeroes elapsed/ep_score; writes the observation of the last draw to obs [N][4]. */
+int xb_env_reset(int env_kind, double* state, uint64_t* rng, int32_t* elapsed, double* ep_score, float* obs,
+                 int n_draws, int64_t N, xb_stream_t stream);
+
+/* One vector step with auto-reset.
+ * actions      int64 [N] (CartPole) or float32 [N] (Pendulum)
+ * obs          f32 [N][4]  observation after the step: the TERMINAL observation for finished envs (buf_obs, :210)
+ * next_obs     f32 [N][4]  nullable; obs with finished envs replaced by their reset observation (what the policy sees next)
+ * rew          f32 [N];  term, trunc  u8 [N]
+ * reset_obs    f32 [N][4]  written only where term|trunc (infos[e]["reset_obs"], :207-209)
+ * ep_step_out  i32 [N], ep_score_out fp64 [N]   infos[e]["episode_step"/"episode_score"] of this step (gym_env.py:45-48)
+ */
+int xb_env_step(int env_kind, double* state, uint64_t* rng, int32_t* elapsed, double* ep_score, const void* actions,
+                float* obs, float* next_obs, float* rew, uint8_t* term, uint8_t* trunc, float* reset_obs,
+                int32_t* ep_step_out, double* ep_score_out, int max_episode_steps, int64_t N, xb_stream_t stream);
+
+/* Test hook: the kernel's correctly-rounded sin/cos on an array (fp64 [n] each). */
+int xb_sincos_f64(const double* x, double* s, double* c, int64_t n, xb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (2) Device-resident rollout buffer.  Replaces DummyOnPolicyBuffer.store / store_element
+ *     xuance/common/memory_tools.py:39-54,196-204  (memory[:, ptr] = data).
+ * Writes row t of the time-major arrays (the *_row pointers already point at row t).  float4 stores for obs.
+ * act: int64 [N] (act_is_i64=1, stored as float32 like the reference, memory_tools.py:173) or float32 [N][act_dim].
+ * term/trunc are u8 in, term is stored as float32 0/1 (memory_tools.py:177), trunc as u8 (segment-end flag).
+ * rew_scale: nullable device scalar multiplied into rew and clipped to +-rew_clip (reward normalisation hook).
+ * ---------------------------------------------------------------------------------------------------------- */
+int xb_store(const float* obs, const void* act, int act_is_i64, int act_dim, const float* rew, const float* val,
+             const uint8_t* term, const uint8_t* trunc, const float* logp, float* obs_row, float* act_row,
+             float* rew_row, float* val_row, float* term_row, uint8_t* trunc_row, float* logp_row,
+             const float* rew_scale, float rew_clip, int64_t N, xb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (3) GAE / discounted-return reverse scan over T, parallel over envs, + advantage statistics.
+ * Replaces DummyOnPolicyBuffer.finish_path (memory_tools.py:206-229) for ALL envs and ALL path segments of a
+ * rollout at once (batched form) and discount_cumsum (common_tools.py:199-200).
+ *   rew, val, term   f32 [T][N]        trunc  u8 [T][N] nullable (segment ends that are not terminals)
+ *   boot             f32 [T][N] nullable: V(terminal obs) where trunc is set (read only there)
+ *   boot_last        f32 [N]           V(next obs) after the last step
+ *   adv, ret         f32 [T][N] out    stats fp64 [2] nullable: (sum adv, sum adv^2) over the whole rollout
+ * The recurrence is carried in fp64 registers and rounded once on store.
+ * ---------------------------------------------------------------------------------------------------------- */
+int xb_gae(const float* rew, const float* val, const float* term, const uint8_t* trunc, const float* boot,
+           const float* boot_last, float* adv, float* ret, double* stats, int64_t T, int64_t N, double gamma,
+           double lam, int use_gae, int variant, xb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (4a) Minibatch gather.  Replaces DummyOnPolicyBuffer.sample / sample_batch (memory_tools.py:57-72,231-245).
+ * idx int64 [B] are the reference's flat indices (env = k / T, step = k % T).
+ * xb_gather_obs: obs rows -> obs_out [B][obs_dim] (the MLP input) and, if stats != NULL, the minibatch
+ *   advantage statistics stats fp64 [2] = (sum, sum of squares) (np.mean/np.std at memory_tools.py:241-242).
+ * xb_gather_batch: every field sample() returns, densely (compat path); any output may be NULL.
+ * xb_normalize_adv: adv[i] = (adv[i] - mean) / (std + 1e-8) from stats over `count` samples, in place.
+ * ---------------------------------------------------------------------------------------------------------- */
+int xb_gather_obs(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* b_obs, int obs_dim,
+                  const float* b_adv, float* obs_out, double* stats, xb_stream_t stream);
+int xb_gather_batch(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* b_obs, int obs_dim,
+                    const float* b_act, int act_dim, const float* b_ret, const float* b_val, const float* b_adv,
+                    const float* b_logp, float* obs_out, float* act_out, float* ret_out, float* val_out,
+                    float* adv_out, float* logp_out, double* stats, xb_stream_t stream);
+int xb_normalize_adv(float* adv, const double* stats, int64_t count, int64_t B, xb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (4b) PPO-Clip loss forward + backward, fused with the gather of the per-transition scalars.
+ * Replaces the loss arithmetic and its autograd backward in PPOCLIP_Learner.update
+ *   xuance/torch/learners/policy_gradient/ppoclip_learner.py:33-44, and Categorical/Normal log_prob+entropy
+ *   xuance/torch/utils/distributions.py:51-55,83-87  (closed forms: SURVEY.md App. C).
+ * If idx != NULL, act/ret/adv/old_logp/val_old are the rollout arrays ([T][N], act [T][N][A]) read through idx;
+ * if idx == NULL they are dense [B] minibatch arrays (compat path: update(obs, act, ret, value, adv, old_logp)).
+ *   adv_stats fp64[2] nullable: (sum, sumsq) of the advantages of the (global) minibatch of adv_count samples;
+ *             when given, advantages are normalised on the fly (x-mean)/(std+1e-8).
+ *   value_clip <= 0 : plain MSE value loss (the reference).  > 0: max((v-R)^2, (v_old+clip(v-v_old,+-c)-R)^2)
+ *             (opt-in, formula of xuance/torch/learners/multi_agent_rl/mappo_learner.py:78-87; needs val_old).
+ *   inv_batch = 1 / (global minibatch size): the mean() of the reference.
+ * Outputs: gradients of  L = a_loss - ent_coef*entropy + vf_coef*c_loss  w.r.t. the network outputs, and
+ *   scalars fp64 [8] = sums over THIS call's samples of {min-surrogate, value loss term, entropy, v_pred,
+ *   clipped-ratio count, 0, 0, 0} (zeroed by the call).
+ * Gaussian: logstd f32 [A] is shared by the batch; dlogstd_acc fp64 [A] (zeroed by the call) receives its gradient.
+ * ---------------------------------------------------------------------------------------------------------- */
+int xb_ppo_loss_categorical(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* logits, int A,
+                            const float* v_pred, const float* act, const float* ret, const float* adv,
+                            const float* old_logp, const float* val_old, const double* adv_stats, int64_t adv_count,
+                            float clip_range, float vf_coef, float ent_coef, float value_clip, float inv_batch,
+                            float* dlogits, float* dv, double* scalars, xb_stream_t stream);
+int xb_ppo_loss_gaussian(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* mu, const float* logstd,
+                         int A, const float* v_pred, const float* act, const float* ret, const float* adv,
+                         const float* old_logp, const float* val_old, const double* adv_stats, int64_t adv_count,
+                         float clip_range, float vf_coef, float ent_coef, float value_clip, float inv_batch,
+                         float* dmu, double* dlogstd_acc, float* dv, double* scalars, xb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Action sampling fused with log-prob (after the actor GEMM).  Replaces dists.stochastic_sample()+log_prob in
+ * PPOCLIP_Agent._action (ppoclip_agent.py:50-57; distributions.py:57-58,89-90).  Philox4x32-10, counter-based:
+ * stream position = (*counter_dev + offset, env index), so a captured graph replays with fresh numbers once
+ * xb_counter_add has advanced the device counter.
+ * ---------------------------------------------------------------------------------------------------------- */
+int xb_sample_categorical(const float* logits, int A, uint64_t seed, const uint64_t* counter_dev, uint64_t offset,
+                          int64_t* act_out, float* logp_out, int64_t N, xb_stream_t stream);
+int xb_sample_gaussian(const float* mu, const float* logstd, int A, uint64_t seed, const uint64_t* counter_dev,
+                       uint64_t offset, float* act_out, float* logp_out, int64_t N, xb_stream_t stream);
+int xb_counter_add(uint64_t* counter_dev, uint64_t inc, xb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Optimiser tail of PPOCLIP_Learner.update (ppoclip_learner.py:45-51) over ONE flat fp32 parameter/gradient
+ * buffer: global-L2-norm clip (torch.nn.utils.clip_grad_norm_: scale = min(1, max_norm/(norm+1e-6))), Adam
+ * (torch.optim.Adam semantics, eps inside the sqrt denominator, bias correction from *step_dev) and the
+ * LinearLR factor  lr = lr0 * (1 + (end-1) * min(it, total)/total), all on device so it is graph-replayable.
+ *   state: step_dev i64[1] (number of updates done so far; incremented by the call)
+ *   grad_scale multiplies the gradient first (1/world_size after a sum-allreduce).
+ *   workspace fp64 [8 + 1024] scratch, ZERO-INITIALISED once by the caller.  lr_out / gnorm_out f32[1] nullable:
+ *   the lr used by this step and the pre-clip gradient norm.
+ * ---------------------------------------------------------------------------------------------------------- */
+int xb_clip_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      int64_t* step_dev, float lr0, float lr_end_factor, int64_t lr_total_iters, float beta1,
+                      float beta2, float eps, float max_norm /* <=0: no clip */, float grad_scale,
+                      double* workspace, float* lr_out, float* gnorm_out, xb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XB200_H */

@@ -1,0 +1,217 @@
+// buffer.cu — device-resident rollout buffer: per-step store and minibatch gather.
+//
+// Replaces  store_element / DummyOnPolicyBuffer.store      xuance/common/memory_tools.py:39-54,196-204
+//           sample_batch / DummyOnPolicyBuffer.sample      xuance/common/memory_tools.py:57-72,231-245
+//
+// Layout: time-major.  The reference keeps env-major [n_envs, n_size] numpy arrays, which makes the per-step
+// write `memory[:, ptr] = data` a stride-T scatter.  Here a step is one contiguous row of N entries per field
+// (observations: N float4), so the store is a pure streaming write and the GAE scan (gae.cu) reads columns
+// with unit stride across threads.  The reference's flat sample index k = env*T + step (memory_tools.py:234)
+// is honoured by the gather: row = (k % T) * N + k / T.
+//
+// HBM traffic: store 36 B/transition written (+36 B read of the step's staging vectors);
+// obs gather 8 B index + 16 B row read + 4*obs_dim B written (+4 B advantage for the statistics).
+#include "common.cuh"
+
+namespace xb {
+
+__global__ void __launch_bounds__(256)
+    store_kernel(const float4* __restrict__ obs, const void* __restrict__ act, int act_is_i64, int act_dim,
+                 const float* __restrict__ rew, const float* __restrict__ val, const uint8_t* __restrict__ term,
+                 const uint8_t* __restrict__ trunc, const float* __restrict__ logp, float4* __restrict__ obs_row,
+                 float* __restrict__ act_row, float* __restrict__ rew_row, float* __restrict__ val_row,
+                 float* __restrict__ term_row, uint8_t* __restrict__ trunc_row, float* __restrict__ logp_row,
+                 const float* __restrict__ rew_scale, float rew_clip, int64_t N) {
+    float scale = rew_scale ? *rew_scale : 1.0f;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N; e += (int64_t)gridDim.x * blockDim.x) {
+        obs_row[e] = obs[e];
+        if (act_is_i64) {
+            act_row[e] = (float)((const int64_t*)act)[e];
+        } else {
+            for (int k = 0; k < act_dim; ++k) act_row[e * act_dim + k] = ((const float*)act)[e * act_dim + k];
+        }
+        float r = rew[e];
+        if (rew_scale) {
+            r = r * scale;
+            r = fminf(fmaxf(r, -rew_clip), rew_clip);
+        }
+        rew_row[e] = r;
+        val_row[e] = val[e];
+        term_row[e] = term[e] ? 1.0f : 0.0f;
+        if (trunc_row) trunc_row[e] = trunc ? trunc[e] : (uint8_t)0;
+        logp_row[e] = logp[e];
+    }
+}
+
+__device__ __forceinline__ int64_t flat_to_row(int64_t k, int64_t T, int64_t N) {
+    int64_t env = k / T;
+    int64_t step = k - env * T;
+    return step * N + env;
+}
+
+// Last-block-done reduction of per-block (sum, sumsq) partials into stats[0..1]; deterministic order.
+__device__ __forceinline__ void finish_stats(double s, double ss, double* partials, unsigned int* ticket,
+                                             double* stats, double* smem) {
+    __shared__ bool is_last;
+    double v[2] = {s, ss};
+    block_sum<2>(v, smem);
+    if (threadIdx.x == 0) {
+        partials[2 * blockIdx.x] = v[0];
+        partials[2 * blockIdx.x + 1] = v[1];
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double a[2] = {0.0, 0.0};
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+            a[0] += partials[2 * b];
+            a[1] += partials[2 * b + 1];
+        }
+        block_sum<2>(a, smem);
+        if (threadIdx.x == 0) {
+            stats[0] = a[0];
+            stats[1] = a[1];
+            *ticket = 0u;  // re-arm for the next launch
+        }
+    }
+}
+
+constexpr int kGatherBlock = 256;
+constexpr int kGatherMaxGrid = kNumSMs * 8;
+
+// scratch for the statistics reduction (one per process; launches on one stream are serialised)
+__device__ double g_partials[2 * kGatherMaxGrid];
+__device__ unsigned int g_ticket = 0;
+
+template <int OBS_DIM>
+__global__ void __launch_bounds__(kGatherBlock)
+    gather_obs_kernel(const int64_t* __restrict__ idx, int64_t B, int64_t T, int64_t N,
+                      const float4* __restrict__ b_obs, const float* __restrict__ b_adv, float* __restrict__ obs_out,
+                      double* __restrict__ stats) {
+    __shared__ double smem[64];
+    double s = 0.0, ss = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t row = flat_to_row(idx[i], T, N);
+        float4 o = b_obs[row];
+        if (OBS_DIM == 4) {
+            reinterpret_cast<float4*>(obs_out)[i] = o;
+        } else {
+            float* dst = obs_out + i * OBS_DIM;
+            dst[0] = o.x;
+            if (OBS_DIM > 1) dst[1] = o.y;
+            if (OBS_DIM > 2) dst[2] = o.z;
+        }
+        if (stats) {
+            double a = (double)b_adv[row];
+            s += a;
+            ss += a * a;
+        }
+    }
+    if (stats) finish_stats(s, ss, g_partials, &g_ticket, stats, smem);
+}
+
+__global__ void __launch_bounds__(kGatherBlock)
+    gather_batch_kernel(const int64_t* __restrict__ idx, int64_t B, int64_t T, int64_t N,
+                        const float4* __restrict__ b_obs, int obs_dim, const float* __restrict__ b_act, int act_dim,
+                        const float* __restrict__ b_ret, const float* __restrict__ b_val,
+                        const float* __restrict__ b_adv, const float* __restrict__ b_logp,
+                        float* __restrict__ obs_out, float* __restrict__ act_out, float* __restrict__ ret_out,
+                        float* __restrict__ val_out, float* __restrict__ adv_out, float* __restrict__ logp_out,
+                        double* __restrict__ stats) {
+    __shared__ double smem[64];
+    double s = 0.0, ss = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t row = flat_to_row(idx[i], T, N);
+        if (obs_out) {
+            float4 o = b_obs[row];
+            float v[4] = {o.x, o.y, o.z, o.w};
+            for (int k = 0; k < obs_dim; ++k) obs_out[i * obs_dim + k] = v[k];
+        }
+        if (act_out)
+            for (int k = 0; k < act_dim; ++k) act_out[i * act_dim + k] = b_act[row * act_dim + k];
+        if (ret_out) ret_out[i] = b_ret[row];
+        if (val_out) val_out[i] = b_val[row];
+        if (logp_out) logp_out[i] = b_logp[row];
+        if (adv_out || stats) {
+            float a = b_adv[row];
+            if (adv_out) adv_out[i] = a;
+            s += (double)a;
+            ss += (double)a * (double)a;
+        }
+    }
+    if (stats) finish_stats(s, ss, g_partials, &g_ticket, stats, smem);
+}
+
+__global__ void __launch_bounds__(256)
+    normalize_adv_kernel(float* __restrict__ adv, const double* __restrict__ stats, double inv_count, int64_t B) {
+    double mean = stats[0] * inv_count;
+    double var = stats[1] * inv_count - mean * mean;
+    float std = (float)sqrt(var > 0.0 ? var : 0.0);
+    float m = (float)mean;
+    float denom = std + 1e-8f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x)
+        adv[i] = (adv[i] - m) / denom;
+}
+
+}  // namespace xb
+
+using namespace xb;
+
+extern "C" int xb_store(const float* obs, const void* act, int act_is_i64, int act_dim, const float* rew,
+                        const float* val, const uint8_t* term, const uint8_t* trunc, const float* logp,
+                        float* obs_row, float* act_row, float* rew_row, float* val_row, float* term_row,
+                        uint8_t* trunc_row, float* logp_row, const float* rew_scale, float rew_clip, int64_t N,
+                        xb_stream_t stream) {
+    if (N <= 0 || act_dim < 1 || !obs || !act || !rew || !val || !term || !logp || !obs_row || !act_row ||
+        !rew_row || !val_row || !term_row || !logp_row)
+        return XB_E_BADARG;
+    store_kernel<<<grid_for(N, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)obs, act, act_is_i64, act_dim, rew, val, term, trunc, logp, (float4*)obs_row, act_row, rew_row,
+        val_row, term_row, trunc_row, logp_row, rew_scale, rew_clip, N);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_gather_obs(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* b_obs, int obs_dim,
+                             const float* b_adv, float* obs_out, double* stats, xb_stream_t stream) {
+    if (B <= 0 || T <= 0 || N <= 0 || !idx || !b_obs || !obs_out || (stats && !b_adv)) return XB_E_BADARG;
+    if (obs_dim < 1 || obs_dim > 4) return XB_E_UNSUPPORTED;
+    int grid = grid_for(B, kGatherBlock, 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    const float4* o = (const float4*)b_obs;
+    switch (obs_dim) {
+        case 4: gather_obs_kernel<4><<<grid, kGatherBlock, 0, s>>>(idx, B, T, N, o, b_adv, obs_out, stats); break;
+        case 3: gather_obs_kernel<3><<<grid, kGatherBlock, 0, s>>>(idx, B, T, N, o, b_adv, obs_out, stats); break;
+        case 2: gather_obs_kernel<2><<<grid, kGatherBlock, 0, s>>>(idx, B, T, N, o, b_adv, obs_out, stats); break;
+        default: gather_obs_kernel<1><<<grid, kGatherBlock, 0, s>>>(idx, B, T, N, o, b_adv, obs_out, stats); break;
+    }
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_gather_batch(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* b_obs, int obs_dim,
+                               const float* b_act, int act_dim, const float* b_ret, const float* b_val,
+                               const float* b_adv, const float* b_logp, float* obs_out, float* act_out,
+                               float* ret_out, float* val_out, float* adv_out, float* logp_out, double* stats,
+                               xb_stream_t stream) {
+    if (B <= 0 || T <= 0 || N <= 0 || !idx) return XB_E_BADARG;
+    if (obs_dim < 1 || obs_dim > 4 || act_dim < 1) return XB_E_UNSUPPORTED;
+    if ((obs_out && !b_obs) || (act_out && !b_act) || (ret_out && !b_ret) || (val_out && !b_val) ||
+        ((adv_out || stats) && !b_adv) || (logp_out && !b_logp))
+        return XB_E_BADARG;
+    gather_batch_kernel<<<grid_for(B, kGatherBlock, 8), kGatherBlock, 0, (cudaStream_t)stream>>>(
+        idx, B, T, N, (const float4*)b_obs, obs_dim, b_act, act_dim, b_ret, b_val, b_adv, b_logp, obs_out, act_out,
+        ret_out, val_out, adv_out, logp_out, stats);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_normalize_adv(float* adv, const double* stats, int64_t count, int64_t B, xb_stream_t stream) {
+    if (B <= 0 || count <= 0 || !adv || !stats) return XB_E_BADARG;
+    normalize_adv_kernel<<<grid_for(B, 256, 4), 256, 0, (cudaStream_t)stream>>>(adv, stats, 1.0 / (double)count, B);
+    XB_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,257 @@
+// env_classic.cu — batched CartPole-v1 / Pendulum-v1 step + auto-reset, one thread per environment.
+//
+// Replaces the per-env Python loop of DummyVecEnv_Gym.step_wait (xuance/environment/gym/gym_vec_env.py:201-212)
+// over Gym_Env.step (xuance/environment/gym/gym_env.py:43-49) over gym 0.26.2's CartPoleEnv / PendulumEnv /
+// TimeLimit (third party, not vendored; equations per SURVEY.md App. A, reset stream per App. B).
+//
+// Bit-exactness contract: fp64 state lives in registers for the whole step; every fp64 operation is an
+// individually rounded __dadd_rn/__dmul_rn/__ddiv_rn (no FMA contraction — this TU is also built with
+// -fmad=false); sin/cos are correctly rounded (crtrig.cuh); squares are v*v.  Under identical actions the
+// fp64 states, float32 observations/rewards, flags, counters and reset draws equal the CPU oracle's bit for bit.
+//
+// Memory traffic per env-step (no reset): CartPole 4x8 R + 4x8 W state, 8 action, 4+4 elapsed, 8+8 score,
+// 16 obs (+16 next_obs), 4 rew, 2 flags, 4+8 episode outputs; all accesses are SoA and fully coalesced,
+// observations are one float4 per env.
+#include "common.cuh"
+#include "crtrig.cuh"
+
+namespace xb {
+
+// ---------------------------------------------------------------- numpy PCG64 (XSL-RR 128/64) ----------------
+struct Pcg64 {
+    uint64_t hi, lo, inc_hi, inc_lo;
+};
+
+__device__ __forceinline__ uint64_t pcg64_next(Pcg64& g) {
+    const uint64_t MH = 0x2360ED051FC65DA4ULL, ML = 0x4385DF649FCCF645ULL;
+    // state = state * mult + inc  (mod 2^128)
+    uint64_t lo = g.lo * ML;
+    uint64_t hi = __umul64hi(g.lo, ML) + g.hi * ML + g.lo * MH;
+    uint64_t nlo = lo + g.inc_lo;
+    uint64_t carry = nlo < lo ? 1ULL : 0ULL;
+    g.hi = hi + g.inc_hi + carry;
+    g.lo = nlo;
+    uint64_t x = g.hi ^ g.lo;
+    unsigned rot = (unsigned)(g.hi >> 58);
+    return (x >> rot) | (x << ((64u - rot) & 63u));
+}
+// Generator.uniform: low + (high - low) * next_double, two roundings
+__device__ __forceinline__ double pcg64_uniform(Pcg64& g, double low, double range) {
+    double u = __dmul_rn((double)(pcg64_next(g) >> 11), 1.0 / 9007199254740992.0);
+    return __dadd_rn(low, __dmul_rn(range, u));
+}
+
+constexpr double kPi = 3.141592653589793;
+
+// ---------------------------------------------------------------- per-env dynamics ---------------------------
+struct CartPole {
+    static constexpr int S = 4;
+    typedef int64_t action_t;
+    __device__ static void draw(double (&st)[4], Pcg64& g) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) st[k] = pcg64_uniform(g, -0.05, 0.05 - (-0.05));
+    }
+    __device__ static float4 observe(const double (&st)[4]) {
+        return make_float4((float)st[0], (float)st[1], (float)st[2], (float)st[3]);
+    }
+    // returns reward (fp64); sets terminated
+    __device__ static double step(double (&st)[4], action_t action, bool& terminated) {
+        const double gravity = 9.8, masspole = 0.1, total_mass = 0.1 + 1.0, length = 0.5;
+        const double polemass_length = 0.1 * 0.5, force_mag = 10.0, tau = 0.02;
+        const double theta_thr = 12 * 2 * kPi / 360, x_thr = 2.4;
+        double x = st[0], x_dot = st[1], theta = st[2], theta_dot = st[3];
+        double force = action == 1 ? force_mag : -force_mag;
+        double s, c;
+        sincos_cr(theta, &s, &c);
+        double td2 = __dmul_rn(theta_dot, theta_dot);
+        double temp = __ddiv_rn(__dadd_rn(force, __dmul_rn(__dmul_rn(polemass_length, td2), s)), total_mass);
+        double c2 = __dmul_rn(c, c);
+        double denom = __dmul_rn(length, __dsub_rn(4.0 / 3.0, __ddiv_rn(__dmul_rn(masspole, c2), total_mass)));
+        double thetaacc = __ddiv_rn(__dsub_rn(__dmul_rn(gravity, s), __dmul_rn(c, temp)), denom);
+        double xacc = __dsub_rn(temp, __ddiv_rn(__dmul_rn(__dmul_rn(polemass_length, thetaacc), c), total_mass));
+        x = __dadd_rn(x, __dmul_rn(tau, x_dot));
+        x_dot = __dadd_rn(x_dot, __dmul_rn(tau, xacc));
+        theta = __dadd_rn(theta, __dmul_rn(tau, theta_dot));
+        theta_dot = __dadd_rn(theta_dot, __dmul_rn(tau, thetaacc));
+        st[0] = x; st[1] = x_dot; st[2] = theta; st[3] = theta_dot;
+        terminated = (x < -x_thr) || (x > x_thr) || (theta < -theta_thr) || (theta > theta_thr);
+        return 1.0;
+    }
+};
+
+struct Pendulum {
+    static constexpr int S = 2;
+    typedef float action_t;
+    __device__ static void draw(double (&st)[2], Pcg64& g) {
+        st[0] = pcg64_uniform(g, -kPi, kPi - (-kPi));
+        st[1] = pcg64_uniform(g, -1.0, 1.0 - (-1.0));
+    }
+    __device__ static float4 observe(const double (&st)[2]) {
+        double s, c;
+        sincos_cr(st[0], &s, &c);
+        return make_float4((float)c, (float)s, (float)st[1], 0.0f);
+    }
+    __device__ static double angle_normalize(double x) {
+        const double two_pi = 2 * kPi;
+        double r = fmod(__dadd_rn(x, kPi), two_pi);  // fmod is exact; then numpy's floor-mod sign fix
+        if (r != 0.0) {
+            if (r < 0.0) r = __dadd_rn(r, two_pi);
+        } else {
+            r = 0.0;
+        }
+        return __dsub_rn(r, kPi);
+    }
+    __device__ static double step(double (&st)[2], action_t action, bool& terminated) {
+        const double dt = 0.05;
+        double th = st[0], thdot = st[1];
+        float u32 = action < -2.0f ? -2.0f : (action > 2.0f ? 2.0f : action);
+        double u = (double)u32;  // pinned numpy 1.21.6 promotion: float32 scalar (x) python float -> float64
+        double an = angle_normalize(th);
+        double costs = __dadd_rn(__dadd_rn(__dmul_rn(an, an), __dmul_rn(0.1, __dmul_rn(thdot, thdot))),
+                                 __dmul_rn(0.001, __dmul_rn(u, u)));
+        double s, c;
+        sincos_cr(th, &s, &c);
+        double newthdot = __dadd_rn(thdot, __dmul_rn(__dadd_rn(__dmul_rn(15.0, s), __dmul_rn(3.0, u)), dt));
+        newthdot = newthdot < -8.0 ? -8.0 : (newthdot > 8.0 ? 8.0 : newthdot);
+        double newth = __dadd_rn(th, __dmul_rn(newthdot, dt));
+        st[0] = newth; st[1] = newthdot;
+        terminated = false;
+        return -costs;
+    }
+};
+
+// ---------------------------------------------------------------- kernels ------------------------------------
+template <class Env>
+__device__ __forceinline__ Pcg64 load_rng(const uint64_t* rng, int64_t N, int64_t e) {
+    return Pcg64{rng[e], rng[N + e], rng[2 * N + e], rng[3 * N + e]};
+}
+
+template <class Env>
+__global__ void __launch_bounds__(128) env_reset_kernel(double* __restrict__ state, uint64_t* __restrict__ rng,
+                                                         int32_t* __restrict__ elapsed, double* __restrict__ ep_score,
+                                                         float4* __restrict__ obs, int n_draws, int64_t N) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    Pcg64 g = load_rng<Env>(rng, N, e);
+    double st[Env::S];
+#pragma unroll
+    for (int k = 0; k < Env::S; ++k) st[k] = state[k * N + e];
+    for (int d = 0; d < n_draws; ++d) Env::draw(st, g);
+#pragma unroll
+    for (int k = 0; k < Env::S; ++k) state[k * N + e] = st[k];
+    rng[e] = g.hi;
+    rng[N + e] = g.lo;
+    elapsed[e] = 0;
+    ep_score[e] = 0.0;
+    obs[e] = Env::observe(st);
+}
+
+template <class Env>
+__global__ void __launch_bounds__(128)
+    env_step_kernel(double* __restrict__ state, uint64_t* __restrict__ rng, int32_t* __restrict__ elapsed,
+                    double* __restrict__ ep_score, const typename Env::action_t* __restrict__ actions,
+                    float4* __restrict__ obs, float4* __restrict__ next_obs, float* __restrict__ rew,
+                    uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, float4* __restrict__ reset_obs,
+                    int32_t* __restrict__ ep_step_out, double* __restrict__ ep_score_out, int max_steps, int64_t N) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    double st[Env::S];
+#pragma unroll
+    for (int k = 0; k < Env::S; ++k) st[k] = state[k * N + e];
+    typename Env::action_t a = actions[e];
+    int32_t el = elapsed[e];
+    double score = ep_score[e];
+
+    bool terminated;
+    double reward = Env::step(st, a, terminated);
+    el += 1;                                   // TimeLimit.step / Gym_Env.step
+    bool truncated = el >= max_steps;
+    score = __dadd_rn(score, reward);          // Gym_Env._episode_score += reward (fp64)
+
+    float4 o = Env::observe(st);
+    obs[e] = o;
+    rew[e] = (float)reward;
+    term[e] = terminated ? 1 : 0;
+    trunc[e] = truncated ? 1 : 0;
+    ep_step_out[e] = el;
+    ep_score_out[e] = score;
+
+    if (terminated || truncated) {             // gym_vec_env.py:207-209: immediate reset, reset obs travels aside
+        Pcg64 g = load_rng<Env>(rng, N, e);
+        Env::draw(st, g);
+        rng[e] = g.hi;
+        rng[N + e] = g.lo;
+        el = 0;
+        score = 0.0;
+        o = Env::observe(st);
+        reset_obs[e] = o;
+    }
+    if (next_obs) next_obs[e] = o;
+#pragma unroll
+    for (int k = 0; k < Env::S; ++k) state[k * N + e] = st[k];
+    elapsed[e] = el;
+    ep_score[e] = score;
+}
+
+__global__ void sincos_kernel(const double* __restrict__ x, double* __restrict__ s, double* __restrict__ c, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sincos_cr(x[i], &s[i], &c[i]);
+}
+
+static inline int env_block(int64_t N) {
+    // small batches are latency bound: spread them over more SMs with narrower CTAs
+    if (N <= (int64_t)kNumSMs * 32 * 2) return 32;
+    if (N <= (int64_t)kNumSMs * 64 * 4) return 64;
+    return 128;
+}
+
+}  // namespace xb
+
+using namespace xb;
+
+extern "C" int xb_env_reset(int env_kind, double* state, uint64_t* rng, int32_t* elapsed, double* ep_score,
+                            float* obs, int n_draws, int64_t N, xb_stream_t stream) {
+    if (N <= 0 || n_draws < 0 || !state || !rng || !elapsed || !ep_score || !obs) return XB_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int block = env_block(N), grid = ceil_div_i64(N, block);
+    if (env_kind == XB_ENV_CARTPOLE)
+        env_reset_kernel<CartPole><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (float4*)obs, n_draws, N);
+    else if (env_kind == XB_ENV_PENDULUM)
+        env_reset_kernel<Pendulum><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (float4*)obs, n_draws, N);
+    else
+        return XB_E_UNSUPPORTED;
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_env_step(int env_kind, double* state, uint64_t* rng, int32_t* elapsed, double* ep_score,
+                           const void* actions, float* obs, float* next_obs, float* rew, uint8_t* term,
+                           uint8_t* trunc, float* reset_obs, int32_t* ep_step_out, double* ep_score_out,
+                           int max_episode_steps, int64_t N, xb_stream_t stream) {
+    if (N <= 0 || !state || !rng || !elapsed || !ep_score || !actions || !obs || !rew || !term || !trunc ||
+        !reset_obs || !ep_step_out || !ep_score_out)
+        return XB_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int block = env_block(N), grid = ceil_div_i64(N, block);
+    if (env_kind == XB_ENV_CARTPOLE)
+        env_step_kernel<CartPole><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (const int64_t*)actions,
+                                                         (float4*)obs, (float4*)next_obs, rew, term, trunc,
+                                                         (float4*)reset_obs, ep_step_out, ep_score_out,
+                                                         max_episode_steps, N);
+    else if (env_kind == XB_ENV_PENDULUM)
+        env_step_kernel<Pendulum><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (const float*)actions,
+                                                         (float4*)obs, (float4*)next_obs, rew, term, trunc,
+                                                         (float4*)reset_obs, ep_step_out, ep_score_out,
+                                                         max_episode_steps, N);
+    else
+        return XB_E_UNSUPPORTED;
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_sincos_f64(const double* x, double* s, double* c, int64_t n, xb_stream_t stream) {
+    if (n <= 0 || !x || !s || !c) return XB_E_BADARG;
+    sincos_kernel<<<ceil_div_i64(n, 128), 128, 0, (cudaStream_t)stream>>>(x, s, c, n);
+    XB_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,249 @@
+// ppo_loss.cu — PPO-Clip loss forward + backward w.r.t. the network outputs, fused with the minibatch
+// gather of the per-transition scalars and with the on-the-fly advantage normalisation.
+//
+// Replaces, in PPOCLIP_Learner.update (xuance/torch/learners/policy_gradient/ppoclip_learner.py):
+//     :33     a_dist.log_prob(act_batch)                 (distributions.py:51-52 / :83-84)
+//     :36-39  ratio, clipped surrogate, a_loss
+//     :41     c_loss = mse_loss(v_pred, ret)             (value_batch is unused there; opt-in value clip below)
+//     :43     e_loss = a_dist.entropy().mean()           (distributions.py:54-55 / :86-87)
+//     :44-46  loss, and the part of loss.backward() between the loss and the network outputs
+//     :54     clip_ratio,  :61 predict_value
+// and the four scalar fancy-index gathers + advantage normalisation of DummyOnPolicyBuffer.sample
+// (xuance/common/memory_tools.py:236-243).  Closed-form gradients: SURVEY.md App. C.
+//
+// One thread per sample.  HBM traffic per sample (Categorical, A=2): 8 B index + 4x4 B gathered scalars +
+// 8 B logits + 4 B v read, 8 B dlogits + 4 B dv written = 48 B.  The scalar reductions (loss terms for the
+// log) are warp-shuffle + one fp64 atomic per block.
+#include "common.cuh"
+
+namespace xb {
+
+struct LossCommon {
+    const int64_t* idx;  // nullable
+    int64_t B, T, N;
+    const float* v_pred;
+    const float* act;
+    const float* ret;
+    const float* adv;
+    const float* old_logp;
+    const float* val_old;     // nullable
+    const double* adv_stats;  // nullable
+    double inv_adv_count;
+    float clip_range, vf_coef, ent_coef, value_clip, inv_batch;
+    float* dv;
+    double* scalars;
+};
+
+__device__ __forceinline__ int64_t sample_row(const LossCommon& c, int64_t i) {
+    if (!c.idx) return i;
+    int64_t k = c.idx[i];
+    int64_t env = k / c.T;
+    return (k - env * c.T) * c.N + env;
+}
+
+struct AdvNorm {
+    float mean, denom;
+    bool on;
+};
+__device__ __forceinline__ AdvNorm load_adv_norm(const LossCommon& c) {
+    AdvNorm n{0.0f, 1.0f, false};
+    if (c.adv_stats) {
+        double mean = c.adv_stats[0] * c.inv_adv_count;
+        double var = c.adv_stats[1] * c.inv_adv_count - mean * mean;
+        n.mean = (float)mean;
+        n.denom = (float)sqrt(var > 0.0 ? var : 0.0) + 1e-8f;
+        n.on = true;
+    }
+    return n;
+}
+
+// surrogate + value terms shared by both policy heads.  Returns dL/dlogp; writes dv; accumulates log scalars.
+__device__ __forceinline__ float surrogate_and_value(const LossCommon& c, const AdvNorm& nrm, int64_t i, int64_t row,
+                                                     float logp, double (&acc)[5]) {
+    float A = c.adv[row];
+    if (nrm.on) A = (A - nrm.mean) / nrm.denom;
+    const float ratio = expf(logp - c.old_logp[row]);
+    const float lo = 1.0f - c.clip_range, hi = 1.0f + c.clip_range;
+    const float s1 = fminf(fmaxf(ratio, lo), hi) * A;
+    const float s2 = A * ratio;
+    const float m = fminf(s1, s2);
+    const bool inactive = (A > 0.0f && ratio > hi) || (A < 0.0f && ratio < lo);
+    const float dlogp = inactive ? 0.0f : -c.inv_batch * A * ratio;
+
+    const float v = c.v_pred[i], R = c.ret[row];
+    float verr = v - R;
+    float vloss = verr * verr;
+    float dvl = 2.0f * verr;
+    if (c.value_clip > 0.0f) {  // opt-in: max((v-R)^2, (v_old + clip(v - v_old, +-c) - R)^2)
+        const float vo = c.val_old[row];
+        const float dlt = v - vo;
+        const float dc = fminf(fmaxf(dlt, -c.value_clip), c.value_clip);
+        const float e2 = vo + dc - R;
+        const float l2 = e2 * e2;
+        if (l2 > vloss) {
+            vloss = l2;
+            dvl = (dlt == dc) ? 2.0f * e2 : 0.0f;
+        }
+    }
+    c.dv[i] = c.vf_coef * c.inv_batch * dvl;
+
+    acc[0] += (double)m;
+    acc[1] += (double)vloss;
+    acc[3] += (double)v;
+    acc[4] += (ratio < lo || ratio > hi) ? 1.0 : 0.0;
+    return dlogp;
+}
+
+__device__ __forceinline__ void flush_scalars(double (&acc)[5], double* scalars, double* smem) {
+    block_sum<5>(acc, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) atomicAdd(&scalars[k], acc[k]);
+    }
+}
+
+constexpr int kLossBlock = 256;
+
+// ------------------------------------------------------------------------------------------------ Categorical
+template <int A_STATIC>
+__global__ void __launch_bounds__(kLossBlock)
+    loss_categorical_kernel(LossCommon c, const float* __restrict__ logits, int A_rt, float* __restrict__ dlogits) {
+    __shared__ double smem[5 * 32];
+    const int A = A_STATIC > 0 ? A_STATIC : A_rt;
+    const AdvNorm nrm = load_adv_norm(c);
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < c.B; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = sample_row(c, i);
+        const float* z = logits + i * A;
+        float* dz = dlogits + i * A;
+        const int a = (int)c.act[row];  // stored as float32 (memory_tools.py:173); torch casts with .long()
+        float zmax = z[0];
+        for (int j = 1; j < A; ++j) zmax = fmaxf(zmax, z[j]);
+        float se = 0.0f;
+        for (int j = 0; j < A; ++j) se += expf(z[j] - zmax);
+        const float lse = zmax + logf(se);
+        float H = 0.0f;
+        for (int j = 0; j < A; ++j) {
+            const float lp = z[j] - lse;
+            H -= expf(lp) * lp;
+        }
+        const float logp = z[a] - lse;
+        const float dlogp = surrogate_and_value(c, nrm, i, row, logp, acc);
+        acc[2] += (double)H;
+        const float ge = c.ent_coef * c.inv_batch;  // d(-ent_coef * mean H)/dz_j = +ge * p_j (logp_j + H)
+        for (int j = 0; j < A; ++j) {
+            const float lp = z[j] - lse;
+            const float pj = expf(lp);
+            dz[j] = dlogp * ((j == a ? 1.0f : 0.0f) - pj) + ge * pj * (lp + H);
+        }
+    }
+    flush_scalars(acc, c.scalars, smem);
+}
+
+// ------------------------------------------------------------------------------------------------ Gaussian
+constexpr int kMaxGaussA = 8;
+constexpr float kHalfLog2Pi = 0.9189385332046727f;
+
+__global__ void __launch_bounds__(kLossBlock)
+    loss_gaussian_kernel(LossCommon c, const float* __restrict__ mu, const float* __restrict__ logstd, int A,
+                         float* __restrict__ dmu, double* __restrict__ dlogstd_acc) {
+    __shared__ double smem[kMaxGaussA * 32];
+    const AdvNorm nrm = load_adv_norm(c);
+    float ls[kMaxGaussA], inv_var[kMaxGaussA];
+    float H = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kMaxGaussA; ++k) {
+        ls[k] = k < A ? logstd[k] : 0.0f;
+        const float sd = expf(ls[k]);
+        inv_var[k] = 1.0f / (sd * sd);
+        if (k < A) H += 0.5f + kHalfLog2Pi + ls[k];
+    }
+    double acc[5] = {0, 0, 0, 0, 0};
+    double gls[kMaxGaussA];
+#pragma unroll
+    for (int k = 0; k < kMaxGaussA; ++k) gls[k] = 0.0;
+    const float ge = c.ent_coef * c.inv_batch;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < c.B; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = sample_row(c, i);
+        float logp = 0.0f;
+        float diff[kMaxGaussA];
+#pragma unroll
+        for (int k = 0; k < kMaxGaussA; ++k) {
+            if (k < A) {
+                diff[k] = c.act[row * A + k] - mu[i * A + k];
+                logp += -(diff[k] * diff[k]) * (0.5f * inv_var[k]) - ls[k] - kHalfLog2Pi;
+            }
+        }
+        const float dlogp = surrogate_and_value(c, nrm, i, row, logp, acc);
+        acc[2] += (double)H;
+#pragma unroll
+        for (int k = 0; k < kMaxGaussA; ++k) {
+            if (k < A) {
+                dmu[i * A + k] = dlogp * diff[k] * inv_var[k];
+                gls[k] += (double)(dlogp * (diff[k] * diff[k] * inv_var[k] - 1.0f)) - (double)ge;
+            }
+        }
+    }
+    block_sum<kMaxGaussA>(gls, smem);
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < A; ++k) atomicAdd(&dlogstd_acc[k], gls[k]);
+    }
+    __syncthreads();
+    flush_scalars(acc, c.scalars, smem);
+}
+
+static int check_common(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* v_pred, const float* act,
+                        const float* ret, const float* adv, const float* old_logp, const float* val_old,
+                        const double* adv_stats, int64_t adv_count, float value_clip, float* dv, double* scalars) {
+    if (B <= 0 || !v_pred || !act || !ret || !adv || !old_logp || !dv || !scalars) return XB_E_BADARG;
+    if (idx && (T <= 0 || N <= 0)) return XB_E_BADARG;
+    if (adv_stats && adv_count <= 0) return XB_E_BADARG;
+    if (value_clip > 0.0f && !val_old) return XB_E_BADARG;
+    return 0;
+}
+
+}  // namespace xb
+
+using namespace xb;
+
+extern "C" int xb_ppo_loss_categorical(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* logits, int A,
+                                       const float* v_pred, const float* act, const float* ret, const float* adv,
+                                       const float* old_logp, const float* val_old, const double* adv_stats,
+                                       int64_t adv_count, float clip_range, float vf_coef, float ent_coef,
+                                       float value_clip, float inv_batch, float* dlogits, float* dv, double* scalars,
+                                       xb_stream_t stream) {
+    int rc = check_common(idx, B, T, N, v_pred, act, ret, adv, old_logp, val_old, adv_stats, adv_count, value_clip, dv, scalars);
+    if (rc) return rc;
+    if (!logits || !dlogits || A < 2) return XB_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    XB_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(double), s));
+    LossCommon c{idx, B, T, N, v_pred, act, ret, adv, old_logp, val_old, adv_stats,
+                 adv_stats ? 1.0 / (double)adv_count : 0.0, clip_range, vf_coef, ent_coef, value_clip, inv_batch, dv, scalars};
+    int grid = grid_for(B, kLossBlock, 8);
+    if (A == 2)
+        loss_categorical_kernel<2><<<grid, kLossBlock, 0, s>>>(c, logits, A, dlogits);
+    else
+        loss_categorical_kernel<0><<<grid, kLossBlock, 0, s>>>(c, logits, A, dlogits);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_ppo_loss_gaussian(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* mu,
+                                    const float* logstd, int A, const float* v_pred, const float* act, const float* ret,
+                                    const float* adv, const float* old_logp, const float* val_old,
+                                    const double* adv_stats, int64_t adv_count, float clip_range, float vf_coef,
+                                    float ent_coef, float value_clip, float inv_batch, float* dmu, double* dlogstd_acc,
+                                    float* dv, double* scalars, xb_stream_t stream) {
+    int rc = check_common(idx, B, T, N, v_pred, act, ret, adv, old_logp, val_old, adv_stats, adv_count, value_clip, dv, scalars);
+    if (rc) return rc;
+    if (!mu || !logstd || !dmu || !dlogstd_acc || A < 1) return XB_E_BADARG;
+    if (A > kMaxGaussA) return XB_E_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    XB_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(double), s));
+    XB_CUDA(cudaMemsetAsync(dlogstd_acc, 0, A * sizeof(double), s));
+    LossCommon c{idx, B, T, N, v_pred, act, ret, adv, old_logp, val_old, adv_stats,
+                 adv_stats ? 1.0 / (double)adv_count : 0.0, clip_range, vf_coef, ent_coef, value_clip, inv_batch, dv, scalars};
+    loss_gaussian_kernel<<<grid_for(B, kLossBlock, 8), kLossBlock, 0, s>>>(c, mu, logstd, A, dmu, dlogstd_acc);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
