@@ -70,10 +70,13 @@ int xb_env_reset(int env_kind, double* state, uint64_t* rng, int32_t* elapsed, d
  * rew          f32 [N];  term, trunc  u8 [N]
  * reset_obs    f32 [N][4]  written only where term|trunc (infos[e]["reset_obs"], :207-209)
  * ep_step_out  i32 [N], ep_score_out fp64 [N]   infos[e]["episode_step"/"episode_score"] of this step (gym_env.py:45-48)
+ * ep_stats     fp64 [3] nullable: running (finished episodes, sum of their scores, sum of their lengths), the
+ *              totals behind the per-episode log lines of ppoclip_agent.py:102-109 (atomically accumulated).
  */
 int xb_env_step(int env_kind, double* state, uint64_t* rng, int32_t* elapsed, double* ep_score, const void* actions,
                 float* obs, float* next_obs, float* rew, uint8_t* term, uint8_t* trunc, float* reset_obs,
-                int32_t* ep_step_out, double* ep_score_out, int max_episode_steps, int64_t N, xb_stream_t stream);
+                int32_t* ep_step_out, double* ep_score_out, double* ep_stats, int max_episode_steps, int64_t N,
+                xb_stream_t stream);
 
 /* Test hook: the kernel's correctly-rounded sin/cos on an array (fp64 [n] each). */
 int xb_sincos_f64(const double* x, double* s, double* c, int64_t n, xb_stream_t stream);

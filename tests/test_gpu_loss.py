@@ -1,0 +1,184 @@
+"""GPU parity: fused PPO loss fwd/bwd, the learner drop-in, action sampling and the fused clip+Adam step."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import load_golden, rel_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _policy(g, device):
+    from xuanpolicy_b200 import policies, spaces
+    m = g["meta"]
+    if m["discrete"]:
+        obs_space, act_space = spaces.Box(-1, 1, (4,)), spaces.Discrete(2)
+    else:
+        obs_space, act_space = spaces.Box(-1, 1, (3,)), spaces.Box(-2.0, 2.0, (1,))
+    pol = policies.make_policy(obs_space, act_space, hidden=(m["hidden"],), device=device)
+    pol.load_state_dict({k[3:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("p0/")})
+    return pol
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("name", ["loss_cat_h64", "loss_gauss_h128"])
+def test_learner_update_matches_reference_golden(name):
+    """PPOCLIP_Learner.update drop-in vs the reference's own update: info scalars, param.grad (1e-4 rel, fp32),
+    parameters after the clipped Adam step."""
+    import xuanpolicy_b200 as xb
+    g = load_golden(name)
+    m = g["meta"]
+    for tag, clip in (("noclip", False), ("clip", True)):
+        pol = _policy(g, "cuda")
+        opt = torch.optim.Adam(pol.parameters(), 4e-4, eps=1e-5)
+        sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=1000)
+        learner = xb.PPOCLIP_Learner(pol, opt, sched, "cuda", "/tmp", vf_coef=m["vf_coef"], ent_coef=m["ent_coef"],
+                                     clip_range=m["clip_range"], clip_grad_norm=m["clip_grad_norm"], use_grad_clip=clip)
+        info = learner.update(g["obs"], g["act"], g["ret"], g["val"], g["adv"], g["old_logp"])
+        assert learner.iterations == 1 and torch.is_tensor(info["clip_ratio"])
+        for k in ("actor-loss", "critic-loss", "entropy", "learning_rate", "predict_value", "clip_ratio"):
+            ref = float(g["info_%s/%s" % (tag, k)])
+            assert abs(float(info[k]) - ref) <= 1e-4 * max(1.0, abs(ref)), (k, float(info[k]), ref)
+        for k, p in pol.named_parameters():
+            ok, err = rel_close(p.grad.cpu().numpy(), g["grad_%s/%s" % (tag, k)], 1e-4)
+            assert ok, (tag, k, err)
+            ok, err = rel_close(p.detach().cpu().numpy(), g["p1_%s/%s" % (tag, k)], 1e-5)
+            assert ok, (tag, k, err)
+
+
+@pytest.mark.parametrize("discrete,B,A", [(True, 512, 2), (True, 4097, 5), (False, 1000, 1), (False, 777, 3)])
+@pytest.mark.parametrize("value_clip", [0.0, 0.2])
+def test_loss_kernel_vs_torch_autograd(discrete, B, A, value_clip):
+    """Kernel gradients w.r.t. network outputs and log scalars vs a plain torch fp32 autograd evaluation of the
+    reference formulas (oracle/ref_port.ppo_clip_loss), dense and through the fused index gather."""
+    from oracle import ref_port
+    from xuanpolicy_b200 import ops
+    from xuanpolicy_b200.policies import CategoricalDistribution, DiagGaussianDistribution
+    gen = torch.Generator(device="cuda").manual_seed(B + A)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=gen)
+    clip, vf, ent = 0.2, 0.25, 0.01
+    T, N = 16, (B + 15) // 16 + 3
+    v = rnd(B).requires_grad_()
+    ret, adv_raw, val_old = rnd(B), rnd(B) * 1.7 + 0.3, rnd(B)
+    if discrete:
+        logits = rnd(B, A).requires_grad_()
+        dist = CategoricalDistribution(A)
+        dist.set_param(logits)
+        act = torch.randint(0, A, (B,), device="cuda", generator=gen).float()
+    else:
+        mu = rnd(B, A).requires_grad_()
+        logstd = (rnd(A) * 0.3 - 0.5).requires_grad_()
+        dist = DiagGaussianDistribution(A)
+        dist.set_param(mu, logstd.exp())
+        act = (mu.detach() + rnd(B, A) * logstd.detach().exp())
+    with torch.no_grad():
+        old_logp = dist.log_prob(act) + 0.1 * rnd(B)
+    adv = (adv_raw - adv_raw.mean()) / (adv_raw.std(unbiased=False) + 1e-8)
+    loss, a_loss, c_loss, e_loss, ratio = ref_port.ppo_clip_loss(dist.log_prob(act), dist.entropy(), v, ret, adv, old_logp, vf, ent, clip)
+    if value_clip > 0:
+        vc = val_old + (v - val_old).clamp(-value_clip, value_clip)
+        c_loss = torch.max((v - ret) ** 2, (vc - ret) ** 2).mean()
+        loss = a_loss - ent * e_loss + vf * c_loss
+    loss.backward()
+    stats = torch.stack([adv_raw.double().sum(), (adv_raw.double() ** 2).sum()])
+    scal = torch.zeros(8, dtype=torch.float64, device="cuda")
+    dvk = torch.empty(B, device="cuda")
+    # scatter the minibatch into a [T, N] rollout at random flat indices so the fused gather path is exercised too
+    perm = torch.randperm(T * N, device="cuda", generator=gen)[:B]
+    row = (perm % T) * N + perm // T
+    def scat(x, width=1):
+        full = torch.zeros((T * N, width), device="cuda")
+        full[row] = x.reshape(B, width)
+        return full.reshape(-1) if width == 1 else full
+    for idx in (None, perm):
+        kw = dict(clip_range=clip, vf_coef=vf, ent_coef=ent, inv_batch=1.0 / B, adv_stats=stats, adv_count=B,
+                  value_clip=value_clip)
+        if idx is None:
+            f = lambda x, w=1: x.contiguous()
+            kw.update(val_old=val_old)
+        else:
+            f = scat
+            kw.update(idx=idx, T=T, N=N, val_old=scat(val_old))
+        if discrete:
+            dl = torch.empty(B, A, device="cuda")
+            ops.ppo_loss_categorical(logits.detach(), v.detach(), f(act), f(ret), f(adv_raw), f(old_logp), dl, dvk, scal, **kw)
+            grads = [(dl, logits.grad)]
+        else:
+            dm = torch.empty(B, A, device="cuda")
+            dls = torch.empty(A, dtype=torch.float64, device="cuda")
+            ops.ppo_loss_gaussian(mu.detach(), logstd.detach(), v.detach(), f(act, A), f(ret), f(adv_raw), f(old_logp), dm, dls,
+                                  dvk, scal, **kw)
+            grads = [(dm, mu.grad), (dls.float(), logstd.grad)]
+        grads.append((dvk, v.grad))
+        for got, ref in grads:
+            ok, err = rel_close(got.cpu().numpy(), ref.cpu().numpy(), 1e-4)   # 1e-4 relative, fp32 (north_star)
+            assert ok, err
+        s = scal.cpu().numpy() / B
+        n_clip = ((ratio < 1 - clip).sum() + (ratio > 1 + clip).sum()).item() / B
+        for got, ref in ((-s[0], a_loss.item()), (s[1], c_loss.item()), (s[2], e_loss.item()), (s[3], v.mean().item()),
+                         (s[4], n_clip)):
+            assert abs(got - ref) <= 1e-4 * max(1.0, abs(ref)), (got, ref)
+
+
+def test_sampling_kernels_logp_and_distribution():
+    from xuanpolicy_b200 import ops
+    N = 200_000
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    ctr = torch.zeros(1, dtype=torch.int64, device="cuda")
+    logits = torch.randn(3, device="cuda", generator=gen).repeat(N, 1).contiguous()
+    act, logp = torch.empty(N, dtype=torch.int64, device="cuda"), torch.empty(N, device="cuda")
+    ops.sample_categorical(logits, 7, ctr, 0, act, logp)
+    ref_lp = torch.log_softmax(logits, -1)
+    assert torch.allclose(logp, ref_lp.gather(1, act[:, None])[:, 0], atol=1e-6)
+    freq = torch.bincount(act, minlength=3).double() / N
+    assert torch.allclose(freq, ref_lp[0].exp().double(), atol=5e-3)
+    act2 = torch.empty_like(act)
+    ops.sample_categorical(logits, 7, ctr, 0, act2, logp)
+    assert torch.equal(act, act2)                      # same (seed, counter, offset) -> same draw
+    ops.counter_add(ctr, 1)
+    ops.sample_categorical(logits, 7, ctr, 0, act2, logp)
+    assert not torch.equal(act, act2) and int(ctr.item()) == 1
+    mu = torch.randn(N, 2, device="cuda", generator=gen)
+    logstd = torch.tensor([-1.0, 0.3], device="cuda")
+    a, lp = torch.empty(N, 2, device="cuda"), torch.empty(N, device="cuda")
+    ops.sample_gaussian(mu, logstd, 11, ctr, 5, a, lp)
+    ref = torch.distributions.Normal(mu, logstd.exp()).log_prob(a).sum(-1)
+    assert torch.allclose(lp, ref, atol=2e-5, rtol=1e-5)
+    z = (a - mu) / logstd.exp()
+    assert abs(z.mean().item()) < 0.01 and abs(z.std().item() - 1.0) < 0.01
+    assert abs((z[:, 0] * z[:, 1]).mean().item()) < 0.01
+
+
+def test_fused_clip_adam_matches_torch():
+    """csrc/optim.cu vs clip_grad_norm_ + torch.optim.Adam(eps=1e-5) + LinearLR over several steps."""
+    from xuanpolicy_b200 import ops
+    torch.manual_seed(0)
+    n = 8835
+    p_ref = torch.randn(n, device="cuda").requires_grad_()
+    opt = torch.optim.Adam([p_ref], 4e-4, eps=1e-5)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=50)
+    p = p_ref.detach().clone()
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ws = torch.zeros(8 + 1024, dtype=torch.float64, device="cuda")
+    lr_out, gn = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    for it in range(12):
+        g = torch.randn(n, device="cuda") * (3.0 if it % 2 else 0.001)
+        p_ref.grad = g.clone()
+        norm = torch.nn.utils.clip_grad_norm_([p_ref], 0.5)
+        lr_used = opt.param_groups[0]["lr"]
+        opt.step()
+        sched.step()
+        ops.clip_adam_step(p, g, m, v, step, 4e-4, 0.0, 50, 0.9, 0.999, 1e-5, 0.5, 1.0, ws, lr_out, gn)
+        assert abs(gn.item() - norm.item()) <= 1e-5 * norm.item()
+        assert abs(lr_out.item() - lr_used) <= 1e-6 * 4e-4
+        ok, err = rel_close(p.cpu().numpy(), p_ref.detach().cpu().numpy(), 1e-6)
+        assert ok, (it, err)
+    assert int(step.item()) == 12

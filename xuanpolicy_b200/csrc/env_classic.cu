@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(128)
                     double* __restrict__ ep_score, const typename Env::action_t* __restrict__ actions,
                     float4* __restrict__ obs, float4* __restrict__ next_obs, float* __restrict__ rew,
                     uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, float4* __restrict__ reset_obs,
-                    int32_t* __restrict__ ep_step_out, double* __restrict__ ep_score_out, int max_steps, int64_t N) {
+                    int32_t* __restrict__ ep_step_out, double* __restrict__ ep_score_out,
+                    double* __restrict__ ep_stats, int max_steps, int64_t N) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= N) return;
     double st[Env::S];
@@ -177,6 +178,11 @@ __global__ void __launch_bounds__(128)
     ep_score_out[e] = score;
 
     if (terminated || truncated) {             // gym_vec_env.py:207-209: immediate reset, reset obs travels aside
+        if (ep_stats) {                        // running totals for the episode log (ppoclip_agent.py:102-109)
+            atomicAdd(&ep_stats[0], 1.0);
+            atomicAdd(&ep_stats[1], score);
+            atomicAdd(&ep_stats[2], (double)el);
+        }
         Pcg64 g = load_rng<Env>(rng, N, e);
         Env::draw(st, g);
         rng[e] = g.hi;
@@ -227,7 +233,7 @@ extern "C" int xb_env_reset(int env_kind, double* state, uint64_t* rng, int32_t*
 extern "C" int xb_env_step(int env_kind, double* state, uint64_t* rng, int32_t* elapsed, double* ep_score,
                            const void* actions, float* obs, float* next_obs, float* rew, uint8_t* term,
                            uint8_t* trunc, float* reset_obs, int32_t* ep_step_out, double* ep_score_out,
-                           int max_episode_steps, int64_t N, xb_stream_t stream) {
+                           double* ep_stats, int max_episode_steps, int64_t N, xb_stream_t stream) {
     if (N <= 0 || !state || !rng || !elapsed || !ep_score || !actions || !obs || !rew || !term || !trunc ||
         !reset_obs || !ep_step_out || !ep_score_out)
         return XB_E_BADARG;
@@ -236,12 +242,12 @@ extern "C" int xb_env_step(int env_kind, double* state, uint64_t* rng, int32_t* 
     if (env_kind == XB_ENV_CARTPOLE)
         env_step_kernel<CartPole><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (const int64_t*)actions,
                                                          (float4*)obs, (float4*)next_obs, rew, term, trunc,
-                                                         (float4*)reset_obs, ep_step_out, ep_score_out,
+                                                         (float4*)reset_obs, ep_step_out, ep_score_out, ep_stats,
                                                          max_episode_steps, N);
     else if (env_kind == XB_ENV_PENDULUM)
         env_step_kernel<Pendulum><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (const float*)actions,
                                                          (float4*)obs, (float4*)next_obs, rew, term, trunc,
-                                                         (float4*)reset_obs, ep_step_out, ep_score_out,
+                                                         (float4*)reset_obs, ep_step_out, ep_score_out, ep_stats,
                                                          max_episode_steps, N);
     else
         return XB_E_UNSUPPORTED;

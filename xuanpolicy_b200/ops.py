@@ -1,0 +1,126 @@
+"""Torch-tensor front-end of the C ABI: derives raw device pointers + the current CUDA stream and calls
+libxb200.  No arithmetic happens here and nothing falls back to torch ops: a CPU tensor is an error.
+
+Every function only enqueues work on `torch.cuda.current_stream()` (graph-capturable).
+"""
+import torch
+
+from . import _lib
+
+ENV_KINDS = {"CartPole-v1": 0, "Pendulum-v1": 1}
+GAE_VARIANTS = {"auto": 0, "ldg": 1, "tma": 2}
+
+
+def _p(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.XB200Error("xb200 kernels take CUDA tensors (got a %s tensor); there is no CPU path" % t.device)
+    if not t.is_contiguous():
+        raise _lib.XB200Error("xb200 kernels take contiguous tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.XB200Error("expected dtype %s, got %s" % (dtype, t.dtype))
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+F32, F64, I64, I32, U8 = torch.float32, torch.float64, torch.int64, torch.int32, torch.uint8
+
+
+def env_reset(kind, state, rng, elapsed, ep_score, obs, n_draws):
+    N = elapsed.numel()
+    _lib.call("xb_env_reset", kind, _p(state, F64), _p(rng, I64), _p(elapsed, I32), _p(ep_score, F64), _p(obs, F32),
+              n_draws, N, _stream())
+
+
+def env_step(kind, state, rng, elapsed, ep_score, actions, obs, next_obs, rew, term, trunc, reset_obs, ep_step_out,
+             ep_score_out, max_steps, ep_stats=None):
+    N = elapsed.numel()
+    _lib.call("xb_env_step", kind, _p(state, F64), _p(rng, I64), _p(elapsed, I32), _p(ep_score, F64),
+              _p(actions, I64 if kind == 0 else F32), _p(obs, F32), _p(next_obs, F32), _p(rew, F32), _p(term, U8),
+              _p(trunc, U8), _p(reset_obs, F32), _p(ep_step_out, I32), _p(ep_score_out, F64), _p(ep_stats, F64), max_steps,
+              N, _stream())
+
+
+def sincos_f64(x):
+    s, c = torch.empty_like(x), torch.empty_like(x)
+    _lib.call("xb_sincos_f64", _p(x, F64), _p(s, F64), _p(c, F64), x.numel(), _stream())
+    return s, c
+
+
+def store(obs, act, rew, val, term, trunc, logp, obs_row, act_row, rew_row, val_row, term_row, trunc_row, logp_row,
+          rew_scale=None, rew_clip=0.0):
+    N = rew.numel()
+    is_i64 = act.dtype == I64
+    act_dim = 1 if is_i64 else act.numel() // N
+    _lib.call("xb_store", _p(obs, F32), _p(act), int(is_i64), act_dim, _p(rew, F32), _p(val, F32), _p(term, U8),
+              _p(trunc, U8), _p(logp, F32), _p(obs_row, F32), _p(act_row, F32), _p(rew_row, F32), _p(val_row, F32),
+              _p(term_row, F32), _p(trunc_row, U8), _p(logp_row, F32), _p(rew_scale, F32), float(rew_clip), N, _stream())
+
+
+def gae(rew, val, term, boot_last, adv, ret, gamma, lam, trunc=None, boot=None, stats=None, use_gae=True, variant="auto"):
+    T, N = rew.shape
+    _lib.call("xb_gae", _p(rew, F32), _p(val, F32), _p(term, F32), _p(trunc, U8), _p(boot, F32), _p(boot_last, F32),
+              _p(adv, F32), _p(ret, F32), _p(stats, F64), T, N, float(gamma), float(lam), int(bool(use_gae)),
+              GAE_VARIANTS[variant], _stream())
+
+
+def gather_obs(idx, T, N, b_obs, obs_dim, obs_out, b_adv=None, stats=None):
+    _lib.call("xb_gather_obs", _p(idx, I64), idx.numel(), T, N, _p(b_obs, F32), obs_dim, _p(b_adv, F32),
+              _p(obs_out, F32), _p(stats, F64), _stream())
+
+
+def gather_batch(idx, T, N, b_obs, obs_dim, b_act, act_dim, b_ret, b_val, b_adv, b_logp, obs_out, act_out, ret_out,
+                 val_out, adv_out, logp_out, stats=None):
+    _lib.call("xb_gather_batch", _p(idx, I64), idx.numel(), T, N, _p(b_obs, F32), obs_dim, _p(b_act, F32), act_dim,
+              _p(b_ret, F32), _p(b_val, F32), _p(b_adv, F32), _p(b_logp, F32), _p(obs_out, F32), _p(act_out, F32),
+              _p(ret_out, F32), _p(val_out, F32), _p(adv_out, F32), _p(logp_out, F32), _p(stats, F64), _stream())
+
+
+def normalize_adv(adv, stats, count):
+    _lib.call("xb_normalize_adv", _p(adv, F32), _p(stats, F64), count, adv.numel(), _stream())
+
+
+def ppo_loss_categorical(logits, v_pred, act, ret, adv, old_logp, dlogits, dv, scalars, clip_range, vf_coef, ent_coef,
+                         inv_batch, idx=None, T=0, N=0, val_old=None, adv_stats=None, adv_count=0, value_clip=0.0):
+    B, A = logits.shape
+    _lib.call("xb_ppo_loss_categorical", _p(idx, I64), B, T, N, _p(logits, F32), A, _p(v_pred, F32), _p(act, F32),
+              _p(ret, F32), _p(adv, F32), _p(old_logp, F32), _p(val_old, F32), _p(adv_stats, F64), adv_count,
+              float(clip_range), float(vf_coef), float(ent_coef), float(value_clip), float(inv_batch),
+              _p(dlogits, F32), _p(dv, F32), _p(scalars, F64), _stream())
+
+
+def ppo_loss_gaussian(mu, logstd, v_pred, act, ret, adv, old_logp, dmu, dlogstd_acc, dv, scalars, clip_range, vf_coef,
+                      ent_coef, inv_batch, idx=None, T=0, N=0, val_old=None, adv_stats=None, adv_count=0, value_clip=0.0):
+    B, A = mu.shape
+    _lib.call("xb_ppo_loss_gaussian", _p(idx, I64), B, T, N, _p(mu, F32), _p(logstd, F32), A, _p(v_pred, F32),
+              _p(act, F32), _p(ret, F32), _p(adv, F32), _p(old_logp, F32), _p(val_old, F32), _p(adv_stats, F64),
+              adv_count, float(clip_range), float(vf_coef), float(ent_coef), float(value_clip), float(inv_batch),
+              _p(dmu, F32), _p(dlogstd_acc, F64), _p(dv, F32), _p(scalars, F64), _stream())
+
+
+def sample_categorical(logits, seed, counter, offset, act_out, logp_out):
+    N, A = logits.shape
+    _lib.call("xb_sample_categorical", _p(logits, F32), A, seed, _p(counter, I64), offset, _p(act_out, I64),
+              _p(logp_out, F32), N, _stream())
+
+
+def sample_gaussian(mu, logstd, seed, counter, offset, act_out, logp_out):
+    N, A = mu.shape
+    _lib.call("xb_sample_gaussian", _p(mu, F32), _p(logstd, F32), A, seed, _p(counter, I64), offset, _p(act_out, F32),
+              _p(logp_out, F32), N, _stream())
+
+
+def counter_add(counter, inc=1):
+    _lib.call("xb_counter_add", _p(counter, I64), inc, _stream())
+
+
+def clip_adam_step(param, grad, exp_avg, exp_avg_sq, step_dev, lr0, lr_end_factor, lr_total_iters, beta1, beta2, eps,
+                   max_norm, grad_scale, workspace, lr_out=None, gnorm_out=None):
+    _lib.call("xb_clip_adam_step", _p(param, F32), _p(grad, F32), _p(exp_avg, F32), _p(exp_avg_sq, F32), param.numel(),
+              _p(step_dev, I64), float(lr0), float(lr_end_factor), int(lr_total_iters), float(beta1), float(beta2),
+              float(eps), float(max_norm), float(grad_scale), _p(workspace, F64), _p(lr_out, F32), _p(gnorm_out, F32),
+              _stream())
