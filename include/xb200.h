@@ -179,6 +179,13 @@ int xb_clip_adam_step(float* param, const float* grad, float* exp_avg, float* ex
                       float beta2, float eps, float max_norm /* <=0: no clip */, float grad_scale,
                       double* workspace, float* lr_out, float* gnorm_out, xb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * HOST helper (host pointers, runs on the calling CPU thread; releases nothing on the device).
+ * Uniform random permutation of 0..n-1 into out[n] (a pinned staging buffer): the host side of the minibatch
+ * index feed, replacing np.random.shuffle(indexes) in PPOCLIP_Agent.train (ppoclip_agent.py:76-78).
+ * ---------------------------------------------------------------------------------------------------------- */
+int xb_host_permutation(int64_t* out /* host */, int64_t n, uint64_t seed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -179,7 +179,7 @@ void oc_gae(const float* rew, const float* val, const float* term, const uint8_t
             long k = t * N + e;
             int seg_end = (t == T - 1) || term[k] != 0.0f || (segend && segend[k]);
             if (seg_end) {
-                double b = (t == T - 1) ? (double)boot_last[e] : (double)boot[k];
+                double b = (t == T - 1) ? (double)boot_last[e] : (boot ? (double)boot[k] : 0.0);
                 if (term[k] != 0.0f) b = 0.0;     /* ppoclip_agent.py:73,97: finish_path(0.0, i) on terminal */
                 nextv = b; last = 0.0; run = b;
             }

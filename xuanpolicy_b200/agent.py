@@ -1,0 +1,342 @@
+"""Vectorised, device-resident PPOCLIP_Agent: the caller of the hot path.
+
+Mirrors PPOCLIP_Agent (xuance/torch/agents/policy_gradient/ppoclip_agent.py:4-165): same constructor
+`(config, envs, policy, optimizer, scheduler, device)`, same `train(train_steps)` semantics (train_steps vector
+steps; one PPO update phase of n_epoch x n_minibatch SGD steps every n_steps), same hyper-parameter names.
+
+What changes is the shape of the loop, not its arithmetic:
+  * one rollout of n_steps vector steps is ONE CUDA graph: policy forward (torch) -> fused sample+log-prob kernel
+    -> env step kernel -> rollout store kernel, per step, then the bootstrap forward and the batched GAE scan;
+    the reference's O(N) Python loops (:71-75, :89-109), per-step D2H copies (:54-56) and list-of-dict infos are gone;
+  * truncation bootstraps: the reference runs a full-batch forward per finished env (:99); here every step's
+    forward also evaluates V(terminal obs of the previous step) on rows [N, 2N) of the same batch, so the
+    values are there for whichever envs were truncated;
+  * the update phase is n_epoch graph launches (n_minibatch fused updates each); with env-sharded data
+    parallelism the two NCCL all-reduces per update sit between graph stages.
+Index permutations follow the reference (`np.random.shuffle` of a persistent arange, :76-78) when
+`config.shuffle == "host"` (copied H2D from pinned memory each epoch), or are drawn on device ("device").
+
+Not yet on this path (next rows): use_obsnorm / use_rewnorm — constructing with them raises.
+"""
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .buffer import DummyOnPolicyBuffer
+from .learner import PPOCLIP_Learner
+from .spaces import is_discrete
+
+
+class HostPermutationFeeder:
+    """Host side of the minibatch-index feed: the role of `np.random.shuffle(indexes)` (ppoclip_agent.py:76-78).
+    Permutations for rollout k+1 are drawn by worker threads (native xb_host_permutation, GIL released) into
+    pinned staging buffers while the GPU is busy with rollout k; two buffer sets alternate."""
+
+    def __init__(self, n, n_epoch, seed, workers=4):
+        from concurrent.futures import ThreadPoolExecutor
+        self.n, self.n_epoch, self.seed = n, n_epoch, seed
+        self.sets = [[torch.empty(n, dtype=torch.int64).pin_memory() for _ in range(n_epoch)] for _ in range(2)]
+        self.pool = ThreadPoolExecutor(max_workers=max(1, workers))
+        self.futures = {}
+        self.consumed = [None, None]
+
+    def _draw(self, buf, seed):
+        _lib.call("xb_host_permutation", buf.data_ptr(), self.n, seed)
+        return buf
+
+    def prefetch(self, iteration):
+        if iteration in self.futures:
+            return
+        ev = self.consumed[iteration & 1]
+        if ev is not None:
+            ev.synchronize()                                        # the H2D copies that read this set have finished
+        self.futures[iteration] = [self.pool.submit(self._draw, self.sets[iteration & 1][ep],
+                                                    (self.seed * 1000003 + iteration) * 64 + ep)
+                                   for ep in range(self.n_epoch)]
+
+    def get(self, iteration, ep):
+        self.prefetch(iteration)
+        return self.futures[iteration][ep].result()
+
+    def mark_consumed(self, iteration):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.consumed[iteration & 1] = ev
+        self.futures.pop(iteration, None)
+
+
+class PPOCLIP_Agent:
+    def __init__(self, config, envs, policy, optimizer, scheduler=None, device=None, process_group=None):
+        if getattr(config, "use_obsnorm", False) or getattr(config, "use_rewnorm", False):
+            raise NotImplementedError("device-side observation/reward normalisation is not implemented yet "
+                                      "(SURVEY.md §8 f1); run with use_obsnorm=False, use_rewnorm=False")
+        self.config, self.envs, self.policy = config, envs, policy
+        self.device = torch.device(device if device is not None else "cuda")
+        self.n_envs, self.n_steps = envs.num_envs, config.n_steps
+        self.n_minibatch, self.n_epoch = config.n_minibatch, config.n_epoch
+        self.gamma, self.gae_lam = config.gamma, config.gae_lambda
+        self.observation_space, self.action_space = envs.observation_space, envs.action_space
+        self.discrete = is_discrete(self.action_space)
+        self.buffer_size = self.n_envs * self.n_steps
+        self.batch_size = self.buffer_size // self.n_minibatch
+        self.use_graphs = bool(getattr(config, "use_cuda_graphs", True))
+        self.shuffle = getattr(config, "shuffle", "host")
+        self.seed = int(getattr(config, "seed", 1))
+        self.memory = DummyOnPolicyBuffer(self.observation_space, self.action_space, {"old_logp": ()}, self.n_envs,
+                                          self.n_steps, config.use_gae, config.use_advnorm, self.gamma, self.gae_lam,
+                                          device=self.device, native=True,
+                                          gae_variant=getattr(config, "gae_variant", "auto"))
+        self.learner = PPOCLIP_Learner(policy, optimizer, scheduler, self.device, getattr(config, "model_dir", "./"),
+                                       vf_coef=config.vf_coef, ent_coef=config.ent_coef, clip_range=config.clip_range,
+                                       clip_grad_norm=config.clip_grad_norm, use_grad_clip=config.use_grad_clip,
+                                       value_clip=getattr(config, "value_clip", None))
+        self.learner.enable_fused_optimizer(process_group)
+        self.world_size = self.learner.world_size
+        N, dev = self.n_envs, self.device
+        obs_dim = self.memory.obs_dim
+        self._obs_dim = obs_dim
+        # ping-pong policy-input buffers: rows [0,N) = obs the policy acts on, rows [N,2N) = terminal obs of the last step
+        self._x = [torch.zeros((2 * N, 4), dtype=torch.float32, device=dev) for _ in range(2)]
+        self._cur = 0
+        self._act = torch.zeros(N if self.discrete else (N, self.memory.act_dim),
+                                dtype=torch.int64 if self.discrete else torch.float32, device=dev)
+        self._logp = torch.zeros(N, dtype=torch.float32, device=dev)
+        self._boot_last = torch.zeros(N, dtype=torch.float32, device=dev)
+        self._ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._perm = torch.zeros(self.buffer_size, dtype=torch.int64, device=dev)
+        self._feeder = None
+        if self.shuffle == "host":
+            self._feeder = HostPermutationFeeder(self.buffer_size, self.n_epoch, self.seed + 7919 * self._rank(),
+                                                 workers=int(getattr(config, "feeder_threads", 4)))
+            self._feeder.prefetch(0)
+        self._iteration = 0
+        self.sync_info = bool(getattr(config, "sync_info", True))
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self._rollout_graph = None
+        self._epoch_graph = None
+        self._stage_graphs = None
+        self.current_step = 0
+        self.current_episode = 0
+        self.last_info = {}
+        # first observation: whatever the envs currently hold (Runner_Base calls envs.reset() before the agent, runner_basic.py:12)
+        self._x[0][:N].copy_(envs._obs)
+        self._x[0][N:].copy_(envs._obs)
+
+    @staticmethod
+    def _rank():
+        d = torch.distributed
+        return d.get_rank() if (d.is_available() and d.is_initialized()) else 0
+
+    # ---------------------------------------------------------------------------------------------- rollout
+    def _policy_forward(self, x):
+        _, dist, v = self.policy(x[:, :self._obs_dim])
+        return dist, v
+
+    def _sample(self, dist, offset):
+        N = self.n_envs
+        if self.discrete:
+            logits = dist.get_param()
+            ops.sample_categorical(logits[:N].contiguous(), self.seed, self._ctr, offset, self._act, self._logp)
+        else:
+            mu, std = dist.get_param()
+            logstd = getattr(getattr(self.policy, "actor", None), "logstd", None)   # gaussian.py:25
+            logstd = logstd.detach() if logstd is not None else std.log().contiguous()
+            ops.sample_gaussian(mu[:N].contiguous(), logstd, self.seed, self._ctr, offset, self._act, self._logp)
+
+    def _rollout_step(self, t):
+        """One vector step into buffer row t (reference loop body, ppoclip_agent.py:62-68,88,101)."""
+        N, env, mem = self.n_envs, self.envs, self.memory
+        x_cur, x_nxt = self._x[self._cur], self._x[self._cur ^ 1]
+        dist, v = self._policy_forward(x_cur)                     # V on [obs_t ; terminal obs of step t-1]
+        if t > 0:
+            mem._boot[t - 1].copy_(v[N:])                         # bootstrap for envs truncated at step t-1 (:99)
+        self._sample(dist, t)
+        ops.env_step(env._kind, env._state, env._rng, env._elapsed, env._ep_score, self._act.reshape(N),
+                     x_nxt[N:], x_nxt[:N], env._rew, env._term, env._trunc, env._reset_obs, env._ep_step_out,
+                     env._ep_score_out, env.max_episode_length, ep_stats=env.ep_stats)
+        mem.store_device(x_cur[:N], self._act, env._rew, v[:N].contiguous(), env._term, env._trunc, self._logp, t)
+        self._cur ^= 1
+
+    def _rollout(self):
+        """n_steps vector steps, the bootstrap forward (:70) and the batched GAE for every env and segment (:71-75)."""
+        N = self.n_envs
+        with torch.no_grad():
+            for t in range(self.n_steps):
+                self._rollout_step(t)
+            _, v = self._policy_forward(self._x[self._cur])
+            self._boot_last.copy_(v[N:])
+            self.memory.finish_rollout(self._boot_last)
+            ops.counter_add(self._ctr, self.n_steps)
+        if self.n_steps % 2:   # keep the ping-pong phase identical for every replay of the captured graph
+            self._x[self._cur ^ 1].copy_(self._x[self._cur])
+            self._cur ^= 1
+
+    # ---------------------------------------------------------------------------------------------- update phase
+    def _epoch_body(self):
+        B = self.batch_size
+        for start in range(0, self.buffer_size - B + 1, B):
+            idx = self._perm[start:start + B]
+            mb = self.learner.stage_gather(self.memory, idx)
+            self.learner.stage_forward_backward(self.memory, idx, mb)
+            self.learner.stage_optimizer()
+
+    def _epoch_distributed(self):
+        """Env-sharded data parallel epoch: every rank updates on its local minibatch; the only exchanges are the
+        two-scalar advantage statistics and the flat gradient, between (graph) stages."""
+        B, lr, mem = self.batch_size, self.learner, self.memory
+        for k, start in enumerate(range(0, self.buffer_size - B + 1, B)):
+            idx = self._perm[start:start + B]
+            g = self._stage_graphs[k] if self._stage_graphs is not None else None
+            if g is not None:
+                g[0].replay()
+                mb = lr._mb[(B, mem.obs_dim)]
+            else:
+                mb = lr.stage_gather(mem, idx)
+            if mem.use_advnorm:
+                torch.distributed.all_reduce(mb["stats"], group=lr.process_group)
+            if g is not None:
+                g[1].replay()
+            else:
+                lr.stage_forward_backward(mem, idx, mb)
+            torch.distributed.all_reduce(lr._flat.flat_grad, group=lr.process_group)
+            if g is not None:
+                g[2].replay()
+            else:
+                lr.stage_optimizer()
+
+    def _update_phase(self):
+        n_updates = self.n_epoch * (self.buffer_size // self.batch_size)
+        if self.shuffle == "host":
+            self._feeder.prefetch(self._iteration + 1)             # next rollout's permutations, drawn while the GPU works
+        for ep in range(self.n_epoch):
+            if self.shuffle == "host":
+                src = self._feeder.get(self._iteration, ep)
+                self._perm.copy_(src, non_blocking=True)           # H2D from pinned memory
+                self.h2d_bytes += src.numel() * 8
+            else:
+                self._perm.copy_(torch.randperm(self.buffer_size, device=self.device))
+            if self.world_size > 1:
+                self._epoch_distributed()
+            elif self._epoch_graph is not None:
+                self._epoch_graph.replay()
+            else:
+                self._epoch_body()
+        if self.shuffle == "host":
+            self._feeder.mark_consumed(self._iteration)
+        self.learner.iterations += n_updates
+        self._iteration += 1
+
+    # ---------------------------------------------------------------------------------------------- graphs
+    def _capture(self):
+        """Warm up eagerly on a side stream (cuBLAS workspaces, autograd, lazy module state), then capture."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        snap = self._snapshot()
+        with torch.cuda.stream(s):
+            self._rollout()
+            self._perm.copy_(torch.randperm(self.buffer_size, device=self.device))
+            if self.world_size > 1:
+                self._epoch_distributed()
+            else:
+                self._epoch_body()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        self._restore(snap)
+        self._rollout_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._rollout_graph):
+            self._rollout()
+        if self.world_size == 1:
+            self._epoch_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._epoch_graph):
+                self._epoch_body()
+        else:
+            B, lr, mem = self.batch_size, self.learner, self.memory
+            graphs = []
+            for start in range(0, self.buffer_size - B + 1, B):
+                idx = self._perm[start:start + B]
+                ga, gb, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga):
+                    mb = lr.stage_gather(mem, idx)
+                with torch.cuda.graph(gb):
+                    lr.stage_forward_backward(mem, idx, mb)
+                with torch.cuda.graph(gc):
+                    lr.stage_optimizer()
+                graphs.append((ga, gb, gc))
+            self._stage_graphs = graphs
+        torch.cuda.synchronize(self.device)
+        self._restore(snap)   # capture does not execute, but keep the state exactly as before either way
+
+    def _snapshot(self):
+        """Everything a warm-up rollout/update mutates, so that capturing leaves training state untouched."""
+        env, fl = self.envs, self.learner._flat
+        tensors = [env._state, env._rng, env._elapsed, env._ep_score, env.ep_stats, self._ctr, self._x[0], self._x[1],
+                   fl.flat_param, fl.exp_avg, fl.exp_avg_sq, fl.step, fl.lr]
+        return [(t, t.clone()) for t in tensors] + [("cur", self._cur)]
+
+    def _restore(self, snap):
+        for t, c in snap:
+            if isinstance(t, str):
+                self._cur = c
+            else:
+                t.copy_(c)
+
+    # ---------------------------------------------------------------------------------------------- public API
+    def train(self, train_steps):
+        """train_steps vector steps (reference: `for _ in tqdm(range(train_steps))`); a PPO update phase after every
+        n_steps of them.  Returns the log dict of the last update phase (also kept in `self.last_info`)."""
+        if train_steps % self.n_steps != 0:
+            raise ValueError("the device-resident loop advances in whole rollouts: train_steps (%d) must be a "
+                             "multiple of n_steps (%d)" % (train_steps, self.n_steps))
+        with torch.cuda.device(self.device):
+            if self.use_graphs and self._rollout_graph is None:
+                self._capture()
+            for _ in range(train_steps // self.n_steps):
+                if self._rollout_graph is not None:
+                    self._rollout_graph.replay()
+                else:
+                    self._rollout()
+                self.memory.ptr, self.memory.size = 0, self.n_steps
+                self._update_phase()
+                self.memory.clear_fast()
+                self.current_step += self.n_envs * self.n_steps
+                if self.sync_info:
+                    self.last_info = self._collect_info()
+            if not self.sync_info:
+                self.last_info = self._collect_info()
+        return self.last_info
+
+    def _collect_info(self):
+        """One host sync per rollout: learner scalars + episode totals (reference logs at :84,:102-109)."""
+        info = self.learner.info(self.batch_size)
+        st = self.envs.ep_stats.cpu().numpy()
+        self.d2h_bytes += 8 * 8 + 3 * 8 + 4 + 8
+        n_ep = int(st[0]) - self.current_episode
+        info["episodes"] = int(st[0])
+        self.current_episode = int(st[0])
+        info["new_episodes"] = n_ep
+        info["mean_episode_score"] = float(st[1] / st[0]) if st[0] > 0 else float("nan")
+        info["mean_episode_steps"] = float(st[2] / st[0]) if st[0] > 0 else float("nan")
+        return info
+
+    def test(self, env_fn, test_episode):
+        """Evaluation episodes on fresh envs (reference :113-165): stochastic actions, scores of finished episodes."""
+        envs = env_fn()
+        obs, _ = envs.reset()
+        scores = []
+        with torch.no_grad(), torch.cuda.device(self.device):
+            while len(scores) < test_episode:
+                _, dist, _ = self.policy(obs if torch.is_tensor(obs) else torch.as_tensor(obs, device=self.device))
+                acts = dist.stochastic_sample()
+                obs, _, term, trunc, infos = envs.step(acts if envs.native else acts.cpu().numpy())
+                done = (term | trunc)
+                done = done.cpu().numpy() if torch.is_tensor(done) else done
+                for i in np.nonzero(done)[0]:
+                    scores.append(infos[int(i)]["episode_score"])
+                if envs.native:
+                    obs = infos.next_obs
+                else:
+                    for i in np.nonzero(done)[0]:
+                        obs[i] = infos[int(i)]["reset_obs"]
+        envs.close()
+        return scores

@@ -25,6 +25,7 @@ SOURCES = {
     "ppo_loss.cu": [],
     "sample.cu": [],
     "optim.cu": [],
+    "host_utils.cu": [],
 }
 HEADERS = ["common.cuh", "crtrig.cuh", "crtrig_consts.inc", os.path.join("..", "..", "include", "xb200.h")]
 

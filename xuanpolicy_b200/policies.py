@@ -57,7 +57,14 @@ class CategoricalDistribution:
 
     def set_param(self, logits):
         self.logits = logits
-        self._logp = logits - logits.logsumexp(dim=-1, keepdim=True)
+        self._logp_cache = None
+
+    @property
+    def _logp(self):  # normalised log-probabilities, computed only when a torch-side consumer asks for them
+        key = torch.is_grad_enabled()
+        if self._logp_cache is None or self._logp_cache[0] != key:
+            self._logp_cache = (key, self.logits - self.logits.logsumexp(dim=-1, keepdim=True))
+        return self._logp_cache[1]
 
     def get_param(self):
         return self.logits
