@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py — PPO env-steps/s on B200 (BASELINE.json metric), with roofline, CPU baseline and clocks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c5]
+
+A "step" is one PPO iteration of the hot path: a rollout of `horizon` vector steps over the env batch, the
+batched GAE, and n_epoch x n_minibatch fused updates.  Default workload = BASELINE.json configs[1]
+("PPO-Clip Pendulum-v1 Gaussian policy, 4096 envs, horizon 128, on 1 B200"); with N GPUs every rank owns its own
+4096 envs (weak scaling, env-sharded data parallel; the only collectives are the advantage statistics and the
+flat gradient).  For N > 1 launch with torchrun (RANK/LOCAL_RANK/WORLD_SIZE from the env).
+
+Printed keys (one JSON line, rank 0):
+  value  env-steps/s with everything device-resident (index permutations drawn on the GPU)
+  e2e    the same loop through the public API `PPOCLIP_Agent.train` with HOST-drawn minibatch permutations copied
+         H2D from pinned memory every epoch and the log scalars read back D2H every iteration
+  roofline      the kernel of ours with the largest share of the step, timed alone with CUDA events
+  kernels       the same measurement for every hand-written kernel on the path + the GAE micro-benchmark shape
+  cpu_baseline  the reference's algorithm (oracle/ref_port.py: per-env Python loops + torch CPU) on a bounded sample
+`--impl reference` times that CPU path alone (the reference itself is Python and does not travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # BASELINE.json configs[0..4]; hyper-parameters not named there default to the reference yaml
+    "c1": dict(env_id="CartPole-v1", envs=16, horizon=256, hidden=64, gamma=0.99,
+               name="PPO-Clip CartPole-v1, MLP 64x64, 16 envs, horizon 256"),
+    "c2": dict(env_id="Pendulum-v1", envs=4096, horizon=128, hidden=128, gamma=0.98,
+               name="PPO-Clip Pendulum-v1 Gaussian policy, 4096 envs, horizon 128"),
+    "c3": dict(env_id="CartPole-v1", envs=65536, horizon=256, hidden=128, gamma=0.99, strong=True,
+               name="PPO-Clip CartPole-v1, 65536 envs (total, env-sharded), horizon 256, gamma 0.99 lambda 0.95"),
+    "c5": dict(env_id="Pendulum-v1", envs=262144, horizon=128, hidden=256, gamma=0.98, strong=True, minibatch=65536,
+               name="PPO-Clip Pendulum-v1, MLP 256x256, 262144 envs (total), minibatch 65536"),
+}
+HBM_FALLBACK_GBS = 6650.0
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def build_agent(wl, world, shuffle, sync_info, pg=None):
+    from xuanpolicy_b200.configs import build_ppo
+    n_local = wl["envs"] // world if wl.get("strong") else wl["envs"]
+    n_mb = 8
+    if wl.get("minibatch"):
+        n_mb = max(1, (wl["envs"] * wl["horizon"]) // wl["minibatch"])
+    h = [wl["hidden"]]
+    return build_ppo(wl["env_id"], device="cuda", process_group=pg, parallels=n_local, n_steps=wl["horizon"],
+                     gamma=wl["gamma"], gae_lambda=0.95, n_epoch=8, n_minibatch=n_mb, representation_hidden_size=h,
+                     actor_hidden_size=h, critic_hidden_size=h, shuffle=shuffle, sync_info=sync_info,
+                     seed=1 + 1000 * (torch.distributed.get_rank() if world > 1 else 0), running_steps=10 ** 9)
+
+
+def time_agent(agent, steps, warmup, flush, world):
+    """K timed PPO iterations, each bracketed by its own CUDA-event pair; an L2 flush (write of a buffer larger
+    than L2) sits between iterations, outside the pairs.  Returns seconds (max over ranks)."""
+    T = agent.n_steps
+    for _ in range(warmup):
+        agent.train(T)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    pairs = []
+    for _ in range(steps):
+        flush.add_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        agent.train(T)
+        e.record()
+        pairs.append((s, e))
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    total_ms = sum(s.elapsed_time(e) for s, e in pairs)
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item()) / 1e3
+
+
+def count_launches(agent):
+    """Hand-written kernel launches inside one PPO iteration (counted from the calls the agent makes)."""
+    T, E, M = agent.n_steps, agent.n_epoch, agent.buffer_size // agent.batch_size
+    per_rollout = T * 3 + 1 + 1            # sample + env_step + store per step, GAE, counter
+    per_update = 1 + 1 + 2                 # gather_obs, loss, grad-norm + adam
+    return per_rollout + E * M * per_update
+
+
+def time_kernel(fn, flush, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(iters):
+        flush.add_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ms.append(s.elapsed_time(e))
+    return float(np.mean(ms)), float(np.min(ms))
+
+
+def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
+    """Times each hand-written kernel alone, with the arguments it gets inside the step, and derives achieved
+    GB/s from the ALGORITHMIC bytes of DESIGN.md / SURVEY.md §8(d)."""
+    from xuanpolicy_b200 import ops
+    mem, env, lr = agent.memory, agent.envs, agent.learner
+    N, T, B = agent.n_envs, agent.n_steps, agent.batch_size
+    od, gauss = mem.obs_dim, not agent.discrete
+    out = {}
+
+    def add(name, fn, bytes_per_launch, launches):
+        mean_ms, min_ms = time_kernel(fn, flush)
+        gbs = bytes_per_launch / (mean_ms * 1e-3) / 1e9
+        out[name] = {"ms": round(mean_ms, 5), "min_ms": round(min_ms, 5), "launches_per_step": launches,
+                     "bytes_per_launch": int(bytes_per_launch), "achieved_gbs": round(gbs, 2), "frac": round(gbs / peak, 5)}
+
+    with torch.no_grad():
+        dist, v = agent._policy_forward(agent._x[agent._cur])
+    x_cur, x_nxt = agent._x[agent._cur], agent._x[agent._cur ^ 1]
+    snap = agent._snapshot()
+    env_bytes = (78 if gauss else 118) * N
+    add("env_step", lambda: ops.env_step(env._kind, env._state, env._rng, env._elapsed, env._ep_score,
+                                         agent._act.reshape(N), x_nxt[N:], x_nxt[:N], env._rew, env._term, env._trunc,
+                                         env._reset_obs, env._ep_step_out, env._ep_score_out, env.max_episode_length,
+                                         ep_stats=env.ep_stats), env_bytes, T)
+    agent._restore(snap)
+    add("sample_logp", lambda: agent._sample(dist, 0), N * ((4 + 4 + 4) if gauss else (8 + 8 + 4)), T)
+    vN = v[:N].contiguous()
+    add("store", lambda: mem.store_device(x_cur[:N], agent._act, env._rew, vN, env._term, env._trunc, agent._logp, 0),
+        N * 2 * 36, T)
+    add("gae", lambda: mem.finish_rollout(agent._boot_last), (20 + 1) * N * T, 1)
+    idx = agent._perm[:B]
+    agent._perm.copy_(torch.randperm(agent.buffer_size, device="cuda"))
+    add("gather_obs_advstats", lambda: lr.stage_gather(mem, idx), B * (8 + 16 + 4 * od + 4), launches_per_step["updates"])
+    mb = lr.stage_gather(mem, idx)
+    with torch.no_grad():
+        _, a_dist, v_pred = agent.policy(mb["obs"])
+    vp = v_pred.contiguous()
+    dv = torch.empty_like(vp)
+    kw = dict(clip_range=lr.clip_range, vf_coef=lr.vf_coef, ent_coef=lr.ent_coef, inv_batch=1.0 / B, idx=idx, T=T, N=N,
+              adv_stats=mb["stats"], adv_count=B)
+    if gauss:
+        mu, std = a_dist.get_param()
+        mu = mu.contiguous()
+        logstd = std.log().contiguous()
+        dmu = torch.empty_like(mu)
+        dls = torch.empty(mu.shape[1], dtype=torch.float64, device="cuda")
+        add("ppo_loss_fwd_bwd", lambda: ops.ppo_loss_gaussian(mu, logstd, vp, mem._act, mem._ret, mem._adv, mem._logp, dmu,
+                                                              dls, dv, lr._scalars, **kw), B * 40, launches_per_step["updates"])
+    else:
+        logits = a_dist.get_param().contiguous()
+        dl = torch.empty_like(logits)
+        add("ppo_loss_fwd_bwd", lambda: ops.ppo_loss_categorical(logits, vp, mem._act, mem._ret, mem._adv, mem._logp, dl, dv,
+                                                                 lr._scalars, **kw), B * 48, launches_per_step["updates"])
+    snap = agent._snapshot()
+    add("clip_adam", lambda: lr.stage_optimizer(), lr._flat.n * (4 + 16 + 12), launches_per_step["updates"])
+    agent._restore(snap)
+    if with_c4:
+        # BASELINE.json configs[3]: GAE micro-benchmark, T=2048 x N=2^20 fp32 (sharded over ranks), both variants
+        Tc, Nc = 2048, (1 << 20) // world
+        gen = torch.Generator(device="cuda").manual_seed(1234 + (torch.distributed.get_rank() if world > 1 else 0))
+        rew = torch.randn((Tc, Nc), device="cuda", generator=gen)
+        val = torch.randn((Tc, Nc), device="cuda", generator=gen)
+        term = (torch.rand((Tc, Nc), device="cuda", generator=gen) < 1 / 200).float()
+        boot = torch.randn(Nc, device="cuda", generator=gen)
+        adv, ret = torch.empty_like(rew), torch.empty_like(rew)
+        for variant in ("ldg", "tma"):
+            add("gae_c4_" + variant, lambda: ops.gae(rew, val, term, boot, adv, ret, 0.99, 0.95, variant=variant),
+                20 * Tc * Nc, 0)
+        del rew, val, term, adv, ret
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
+    wl = WORKLOADS[args.workload]
+    peak, peak_src = measured_peaks()
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")   # 256 MiB > 126 MB L2
+    sampler = ClockSampler(local) if rank == 0 else None
+
+    # value: device-resident (permutations drawn on the GPU, one host sync at the end of train())
+    agent = build_agent(wl, world, "device", False)
+    secs = time_agent(agent, args.steps, args.warmup, flush, world)
+    env_steps = agent.n_envs * agent.n_steps * args.steps * world
+    value = env_steps / secs
+    launches = count_launches(agent)
+    launches_per_step = {"updates": agent.n_epoch * (agent.buffer_size // agent.batch_size)}
+    kernels = kernel_rooflines(agent, flush, peak, launches_per_step, with_c4=not args.no_c4, world=world) if rank == 0 or world > 1 else {}
+    params = agent.learner._flat.n
+    del agent
+    torch.cuda.empty_cache()
+
+    # e2e: public API with host-drawn permutations (H2D from pinned memory each epoch) and D2H of the log each iteration
+    agent = build_agent(wl, world, "host", True)
+    secs_e2e = time_agent(agent, args.steps, args.warmup, flush, world)
+    iters = args.steps + args.warmup
+    h2d, d2h = agent.h2d_bytes // iters, agent.d2h_bytes // iters
+    e2e = env_steps / secs_e2e
+    info = agent.last_info
+    n_local, horizon, mb = agent.n_envs, agent.n_steps, agent.batch_size
+    del agent
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        return
+    step_share = {k: v["ms"] * v["launches_per_step"] for k, v in kernels.items() if v["launches_per_step"]}
+    dom = max(step_share, key=step_share.get)
+    kd = kernels[dom]
+    cpu = None if args.no_cpu_baseline else cpu_baseline(wl, budget_s=args.cpu_budget if args.cpu_budget else 25.0)
+    line = {
+        "metric": "PPO env-steps/s", "value": round(value, 1), "unit": "env-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(secs / args.steps * 1e3, 4),
+        "higher_is_better": True, "scaling": "strong" if wl.get("strong") else "weak", "vs_baseline": None,
+        "dtype": "f32 (policy MLP, loss, GAE carry f64); f64 (env physics)", "data": "synthetic",
+        "config": {"workload": wl["name"], "envs_per_gpu": n_local, "horizon": horizon, "n_epoch": 8,
+                   "minibatch_per_gpu": mb, "mlp_hidden": wl["hidden"], "params": params, "gamma": wl["gamma"],
+                   "gae_lambda": 0.95, "use_obsnorm": False, "use_rewnorm": False, "parallelism": "env-sharded dp%d" % world,
+                   "l2_flush": "256 MiB buffer written between timed steps (outside the event pairs)",
+                   "allow_tf32": bool(torch.backends.cuda.matmul.allow_tf32)},
+        "e2e": {"value": round(e2e, 1), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": round(secs_e2e / args.steps * 1e3, 4),
+                "what": "PPOCLIP_Agent.train with host-drawn minibatch permutations (pinned H2D per epoch) and log scalars read back"},
+        "gpu_launches": launches * args.steps,
+        "roofline": {"kernel": dom, "bound": "hbm", "achieved": kd["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": kd["frac"], "traffic": None, "peak_source": peak_src,
+                     "note": "largest share of the step among the hand-written kernels; batches this small are "
+                             "launch/latency-bound (working set is L2-resident) — see kernels.gae_c4_* for the HBM-bound shape"},
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "last_info": {k: (float(v) if not isinstance(v, (int, float)) else v) for k, v in info.items()},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------- CPU arms
+def _port_agent(wl, n_envs, threads):
+    from oracle import ref_port
+    from xuanpolicy_b200 import policies
+    torch.set_num_threads(threads)
+    torch.manual_seed(1)
+    np.random.seed(1)
+    envs = ref_port.VecEnvPort(wl["env_id"], n_envs, seed=1, trig="libm")
+    envs.reset()
+    pol = policies.make_policy(envs.observation_space, envs.action_space, hidden=(wl["hidden"],), device="cpu")
+    opt = torch.optim.Adam(pol.parameters(), 4e-4, eps=1e-5)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=10 ** 9)
+    return ref_port.PPOAgentPort(envs, pol, opt, sched, wl["horizon"], 8, 8, wl["gamma"], 0.95)
+
+
+def _time_port(wl, n_envs, threads, iters):
+    agent = _port_agent(wl, n_envs, threads)
+    t0 = time.perf_counter()
+    agent.train(wl["horizon"] * iters)
+    dt = time.perf_counter() - t0
+    return n_envs * wl["horizon"] * iters / dt, dt
+
+
+def _sample_envs(wl, budget_s, iters):
+    """Env count for which `iters` iterations of the reference algorithm take about budget_s on this host."""
+    probe_n = min(32, wl["envs"])
+    rate, _ = _time_port(wl, probe_n, 1, 1)
+    n = int(rate * budget_s / (wl["horizon"] * iters))
+    return max(8, min(wl["envs"], (n // 8) * 8))
+
+
+def cpu_baseline(wl, budget_s):
+    cores = os.cpu_count() or 1
+    n = _sample_envs(wl, budget_s / 2, 1)
+    best = None
+    for threads in sorted({1, cores}):
+        rate, dt = _time_port(wl, n, threads, 1)
+        if best is None or rate > best[0]:
+            best = (rate, threads, dt)
+    return {"value": round(best[0], 1), "unit": "env-steps/s", "cores": best[1], "kind": "port",
+            "host_cores_available": cores,
+            "sample": "%d of %d envs x full horizon %d, 1 PPO iteration (8 epochs x 8 minibatches), %.1f s; "
+                      "oracle/ref_port.py = the reference's per-env Python loops + torch-CPU learner over libm physics"
+                      % (n, wl["envs"], wl["horizon"], best[2])}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    total_iters = args.steps + args.warmup
+    n = _sample_envs(wl, args.cpu_budget if args.cpu_budget else 150.0, total_iters)
+    # small MLPs run faster single-threaded, large minibatches with all cores: pick by a one-iteration trial
+    trial = {th: _time_port(wl, min(n, 64), th, 1)[0] for th in sorted({1, cores})}
+    threads = max(trial, key=trial.get)
+    agent = _port_agent(wl, n, threads)
+    agent.train(wl["horizon"] * args.warmup)
+    t0 = time.perf_counter()
+    agent.train(wl["horizon"] * args.steps)
+    dt = time.perf_counter() - t0
+    value = n * wl["horizon"] * args.steps / dt
+    sample = ("%d of %d envs x full horizon %d per step, %d timed PPO iterations; reference algorithm restated in "
+              "oracle/ref_port.py (the reference is Python at /root/reference and does not travel to the GPU box)"
+              % (n, wl["envs"], wl["horizon"], args.steps))
+    print(json.dumps({
+        "impl": "reference", "metric": "PPO env-steps/s", "value": round(value, 1), "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (torch CPU); f64 physics",
+        "data": "synthetic", "config": {"workload": wl["name"], "sample_envs": n, "horizon": wl["horizon"]},
+        "cpu_baseline": {"value": round(value, 1), "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample,
+                         "host_cores_available": cores},
+        "e2e": {"value": round(value, 1), "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-c4", action="store_true", help="skip the 40 GiB GAE micro-benchmark arrays")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of CPU work for the CPU arms (0 = default)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

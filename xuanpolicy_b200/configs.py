@@ -1,0 +1,43 @@
+"""Default PPO-Clip hyper-parameters for the two classic-control tasks, as a Namespace shaped like the one the
+reference builds from YAML (xuance/common/common_tools.py:32-83).  Values restate
+xuance/configs/ppo/classic_control/CartPole-v1.yaml and Pendulum-v1.yaml (identical except env_id/policy);
+`use_obsnorm` / `use_rewnorm` default to False here because the device-side normaliser is a later row
+ — the yaml default is True."""
+from argparse import Namespace
+
+_COMMON = dict(
+    agent="PPO_Clip", env_name="Classic Control", vectorize="B200_Gym", representation="Basic_MLP", runner="DRL",
+    representation_hidden_size=[128], actor_hidden_size=[128], critic_hidden_size=[128], activation="LeakyReLU",
+    seed=1, parallels=10, running_steps=300000, n_steps=256, n_epoch=8, n_minibatch=8, learning_rate=0.0004,
+    use_grad_clip=True, vf_coef=0.25, ent_coef=0.01, target_kl=0.001, clip_range=0.2, clip_grad_norm=0.5, gamma=0.98,
+    use_gae=True, gae_lambda=0.95, use_advnorm=True, use_obsnorm=False, use_rewnorm=False, obsnorm_range=5,
+    rewnorm_range=5, render=False, device="cuda", model_dir="./models/ppo/", log_dir="./logs/ppo/",
+)
+
+
+def ppo_config(env_id, **overrides):
+    cfg = dict(_COMMON)
+    cfg["env_id"] = env_id
+    cfg["policy"] = "Categorical_AC" if env_id == "CartPole-v1" else "Gaussian_AC"
+    cfg.update(overrides)
+    return Namespace(**cfg)
+
+
+def build_ppo(env_id, device="cuda", process_group=None, **overrides):
+    """Envs + policy + Adam + LinearLR + agent, wired like Runner_DRL.__init__ (xuance/torch/runners/runner_drl.py:15-74)."""
+    import torch
+
+    from .agent import PPOCLIP_Agent
+    from .policies import make_policy
+    from .vec_env import DummyVecEnv_Gym, make_env_fns
+    cfg = ppo_config(env_id, device=device, **overrides)
+    torch.manual_seed(cfg.seed)
+    envs = DummyVecEnv_Gym(make_env_fns(env_id, cfg.seed, cfg.parallels), device=device, native=True)
+    envs.reset()                                                          # runner_basic.py:12
+    policy = make_policy(envs.observation_space, envs.action_space, hidden=tuple(cfg.representation_hidden_size),
+                         device=device)
+    optimizer = torch.optim.Adam(policy.parameters(), cfg.learning_rate, eps=1e-5)      # runner_drl.py:71
+    scheduler = torch.optim.lr_scheduler.LinearLR(optimizer, start_factor=1.0, end_factor=0.0,
+                                                  total_iters=int(cfg.running_steps))    # runner_drl.py:72-73
+    agent = PPOCLIP_Agent(cfg, envs, policy, optimizer, scheduler, device, process_group=process_group)
+    return agent
