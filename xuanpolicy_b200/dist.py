@@ -1,0 +1,67 @@
+"""Env-sharded data parallelism: one process per GPU, NCCL over NVLink.
+
+The reference is single-process; its only collective is the (disabled) mpi4py Allreduce of [sums..., count]
+inside RunningMeanStd (xuance/common/statistic_tools.py:6-32).  The PPO path shards by environment:
+
+  * rank r of W owns envs [r*N/W, (r+1)*N/W): its own env state / RNG, rollout-buffer shard, local index
+    permutation and local minibatch of B/W samples; the policy and the Adam state are replicated;
+  * per update there are exactly two exchanges, both latency-bound:
+      1. all-reduce(sum) of (sum adv, sum adv^2)  -> every rank normalises with the GLOBAL-minibatch mean/std,
+         the sharded equivalent of memory_tools.py:241-242;
+      2. all-reduce(sum) of the flat gradient, each rank having scaled its loss by 1/(B_local*W), so that the
+         sum is the gradient of the global-minibatch mean; clip + Adam then run identically on every rank.
+  Nothing is exchanged during the rollout or the GAE scan.
+
+These helpers are backend-agnostic (NCCL on GPUs, gloo in the CPU tests).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend="nccl"):
+    """Initialise torch.distributed from torchrun's RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* variables."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        return 0, 0, 1
+    rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group(backend)
+    return rank, local, world
+
+
+def shard_envs(total_envs, world, rank):
+    """[lo, hi) of the envs owned by `rank`; shards must be equal for mean-of-means == global mean."""
+    if total_envs % world != 0:
+        raise ValueError("env count %d is not divisible by world size %d" % (total_envs, world))
+    per = total_envs // world
+    return rank * per, (rank + 1) * per
+
+
+def allreduce_adv_stats(stats, group=None):
+    """stats = fp64 [2] (sum, sumsq) of the local minibatch's advantages -> global sums, in place."""
+    dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    return stats
+
+
+def mean_std_from_stats(stats, count):
+    """(mean, population std) exactly as the kernels derive them (csrc/ppo_loss.cu load_adv_norm)."""
+    mean = stats[0] / count
+    var = torch.clamp(stats[1] / count - mean * mean, min=0.0)
+    return mean, torch.sqrt(var)
+
+
+def allreduce_flat_grad(flat_grad, group=None):
+    """Sum of per-rank gradients of loss/(B_local*W) == gradient of the global-minibatch mean loss."""
+    dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return flat_grad
+
+
+def broadcast_parameters(flat_param, src=0, group=None):
+    """Ranks are seeded identically, so this is a safety net rather than a requirement."""
+    dist.broadcast(flat_param, src=src, group=group)
+    return flat_param
