@@ -180,6 +180,16 @@ int xb_clip_adam_step(float* param, const float* grad, float* exp_avg, float* ex
                       double* workspace, float* lr_out, float* gnorm_out, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Non-GEMM half of the MLP backward (the GEMMs stay in torch/cuBLAS): LeakyReLU' fused with the bias gradient.
+ *   dz[b,h] = dy[b,h] * (y[b,h] > 0 ? 1 : slope);   dbias[h] = sum_b dz[b,h]        (dz may alias dy)
+ * Replaces torch autograd's leaky_relu_backward + sum(0) pair in every Linear+LeakyReLU block
+ * (xuance/torch/utils/layers.py:15-21).  H % 4 == 0, H <= 1024.
+ * workspace: fp32 [4 + 592*H], word 0 ZERO-INITIALISED once by the caller.
+ * ---------------------------------------------------------------------------------------------------------- */
+int xb_act_bias_bwd(const float* dy, const float* y, float slope, float* dz, float* dbias, float* workspace,
+                    int64_t B, int H, xb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * HOST helper (host pointers, runs on the calling CPU thread; releases nothing on the device).
  * Uniform random permutation of 0..n-1 into out[n] (a pinned staging buffer): the host side of the minibatch
  * index feed, replacing np.random.shuffle(indexes) in PPOCLIP_Agent.train (ppoclip_agent.py:76-78).

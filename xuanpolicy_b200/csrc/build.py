@@ -26,6 +26,7 @@ SOURCES = {
     "sample.cu": [],
     "optim.cu": [],
     "host_utils.cu": [],
+    "mlp_epilogue.cu": [],
 }
 HEADERS = ["common.cuh", "crtrig.cuh", "crtrig_consts.inc", os.path.join("..", "..", "include", "xb200.h")]
 

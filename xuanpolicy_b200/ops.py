@@ -124,3 +124,9 @@ def clip_adam_step(param, grad, exp_avg, exp_avg_sq, step_dev, lr0, lr_end_facto
               _p(step_dev, I64), float(lr0), float(lr_end_factor), int(lr_total_iters), float(beta1), float(beta2),
               float(eps), float(max_norm), float(grad_scale), _p(workspace, F64), _p(lr_out, F32), _p(gnorm_out, F32),
               _stream())
+
+
+def act_bias_bwd(dy, y, slope, dz, dbias, workspace):
+    B, H = dy.shape
+    _lib.call("xb_act_bias_bwd", _p(dy, F32), _p(y, F32), float(slope), _p(dz, F32), _p(dbias, F32), _p(workspace, F32),
+              B, H, _stream())

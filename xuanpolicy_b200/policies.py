@@ -21,6 +21,66 @@ import torch.nn as nn
 _HALF_LOG_2PI = 0.5 * math.log(2.0 * math.pi)
 
 
+class _LinearLeakyReLU(torch.autograd.Function):
+    """y = leaky_relu(x @ W^T + b).  The two GEMM-shaped pieces stay cuBLAS calls (addmm / mm / bmm); what torch
+    autograd would add around them in the backward — leaky_relu_backward and the strided `sum(0)` bias reduction,
+    ~95 us per layer at B=65536 — is one hand-written pass (csrc/mlp_epilogue.cu), and the weight gradient
+    (M=N=H, K=B: a shape cuBLAS's fp32 heuristics serve with 4 CTAs) is issued as a batched split-K product."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, slope, workspace):
+        y = torch.addmm(bias, x, weight.t())
+        torch.nn.functional.leaky_relu_(y, slope)
+        ctx.save_for_backward(x, weight, y)
+        ctx.slope, ctx.workspace = slope, workspace
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import ops
+        x, weight, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        dz = torch.empty_like(dy)
+        db = torch.empty(dy.shape[1], dtype=dy.dtype, device=dy.device)
+        ops.act_bias_bwd(dy, y, ctx.slope, dz, db, ctx.workspace)
+        dx = dz @ weight if ctx.needs_input_grad[0] else None
+        B, H = dz.shape
+        S = 1
+        while S < 64 and B % (2 * S) == 0 and B // (2 * S) >= 512:
+            S *= 2
+        if S > 1 and x.is_contiguous():
+            dw = torch.bmm(dz.view(S, B // S, H).transpose(1, 2), x.view(S, B // S, x.shape[1])).sum(0)
+        else:
+            dw = dz.t() @ x
+        return dx, dw, db, None, None
+
+
+class _DenseStack(nn.Sequential):
+    """nn.Sequential of [Linear, LeakyReLU, ...] (same parameter names as the reference's Sequential) whose forward
+    routes Linear+LeakyReLU pairs through the fused-epilogue autograd function when gradients are being recorded on
+    a CUDA device; everywhere else it is the plain module chain."""
+
+    def forward(self, x):
+        mods = list(self)
+        fused = x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled()
+        k = 0
+        while k < len(mods):
+            m = mods[k]
+            nxt = mods[k + 1] if k + 1 < len(mods) else None
+            if (fused and isinstance(m, nn.Linear) and isinstance(nxt, nn.LeakyReLU) and m.weight.requires_grad
+                    and m.out_features % 4 == 0 and m.out_features <= 1024 and x.dim() == 2):
+                ws = getattr(self, "_xb_ws", None)
+                if ws is None or ws.device != x.device:
+                    ws = torch.zeros(4 + 592 * 1024, dtype=torch.float32, device=x.device)
+                    object.__setattr__(self, "_xb_ws", ws)
+                x = _LinearLeakyReLU.apply(x, m.weight, m.bias, float(nxt.negative_slope), ws)
+                k += 2
+            else:
+                x = m(x)
+                k += 1
+        return x
+
+
 def _dense_stack(sizes: Sequence[int], act, init, device, last_plain=False, last_init=True):
     """[Linear, act, Linear, act, ...]; with last_plain the final Linear has no activation."""
     mods = []
@@ -33,7 +93,7 @@ def _dense_stack(sizes: Sequence[int], act, init, device, last_plain=False, last
         mods.append(lin)
         if not (final and last_plain):
             mods.append(act())
-    return nn.Sequential(*mods)
+    return _DenseStack(*mods)
 
 
 class MLPRepresentation(nn.Module):
