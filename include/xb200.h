@@ -87,12 +87,13 @@ int xb_sincos_f64(const double* x, double* s, double* c, int64_t n, xb_stream_t 
  * Writes row t of the time-major arrays (the *_row pointers already point at row t).  float4 stores for obs.
  * act: int64 [N] (act_is_i64=1, stored as float32 like the reference, memory_tools.py:173) or float32 [N][act_dim].
  * term/trunc are u8 in, term is stored as float32 0/1 (memory_tools.py:177), trunc as u8 (segment-end flag).
- * rew_scale: nullable device scalar multiplied into rew and clipped to +-rew_clip (reward normalisation hook).
+ * rew_std: nullable device scalar; when given, rewards are stored as clip(rew / *rew_std, +-rew_clip)
+ *          (Agent._process_reward, xuance/torch/agents/agent.py:118-123).
  * ---------------------------------------------------------------------------------------------------------- */
 int xb_store(const float* obs, const void* act, int act_is_i64, int act_dim, const float* rew, const float* val,
              const uint8_t* term, const uint8_t* trunc, const float* logp, float* obs_row, float* act_row,
              float* rew_row, float* val_row, float* term_row, uint8_t* trunc_row, float* logp_row,
-             const float* rew_scale, float rew_clip, int64_t N, xb_stream_t stream);
+             const float* rew_std, float rew_clip, int64_t N, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * (3) GAE / discounted-return reverse scan over T, parallel over envs, + advantage statistics.
@@ -178,6 +179,29 @@ int xb_clip_adam_step(float* param, const float* grad, float* exp_avg, float* ex
                       int64_t* step_dev, float lr0, float lr_end_factor, int64_t lr_total_iters, float beta1,
                       float beta2, float eps, float max_norm /* <=0: no clip */, float grad_scale,
                       double* workspace, float* lr_out, float* gnorm_out, xb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Device-side RunningMeanStd + observation / reward normalisation (per-step path when use_obsnorm / use_rewnorm).
+ * Replaces RunningMeanStd.update/update_from_moments (xuance/common/statistic_tools.py:63-112),
+ * Agent._process_observation/_process_reward (xuance/torch/agents/agent.py:104-123) and the per-env discounted
+ * return tracker (ppoclip_agent.py:87,91-92).
+ *   obs normaliser state: fp64 [9] = mean[4], var[4], count (mean/var hold float32-rounded values)
+ *   xb_moments4      sums fp64 [9] = column sums (4), column sums of squares (4), N of x f32 [N][4]
+ *                    (between the two calls the 9 sums may be all-reduced across ranks: the analogue of mpi_mean :6-17)
+ *   xb_rms_normalize merges `sums` into state_in (Chan), writes the merged state to state_out (!= state_in) and
+ *                    out = clip((x - mean) / (sqrt(var) + 1e-8), +-clip)     f32 [N][4]; lanes >= dim give 0
+ *   xb_returns_track returns[i] = (1-term)*gamma*returns[i] + rew[i]; finished envs add (R, R^2, 1) to sums fp64 [3]
+ *                    and restart at 0
+ *   xb_rms_merge_scalar merges those sums into the return normaliser state fp64 [3] = (mean, var, count) and
+ *                    publishes rew_std = clip(sqrt(var), 0.1, 100), the divisor xb_store applies to rewards
+ * workspace: fp64 [8 + 8*1184], word 0 ZERO-INITIALISED once by the caller (one workspace per call site).
+ * ---------------------------------------------------------------------------------------------------------- */
+int xb_moments4(const float* x, double* sums, double* workspace, int64_t N, xb_stream_t stream);
+int xb_rms_normalize(const float* x, int dim, const double* sums, const double* state_in, double* state_out,
+                     float clip, float* out, int64_t N, xb_stream_t stream);
+int xb_returns_track(float* returns, const float* rew, const uint8_t* term, const uint8_t* trunc, float gamma,
+                     double* sums, double* workspace, int64_t N, xb_stream_t stream);
+int xb_rms_merge_scalar(const double* sums, double* state, float* rew_std, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Non-GEMM half of the MLP backward (the GEMMs stay in torch/cuBLAS): LeakyReLU' fused with the bias gradient.

@@ -110,11 +110,11 @@ class DummyOnPolicyBuffer:
         self.size = min(self.size + 1, self.n_size)
         self._gae_valid = False
 
-    def store_device(self, obs4, act, rew, val, term_u8, trunc_u8, logp, row, rew_scale=None, rew_clip=0.0):
+    def store_device(self, obs4, act, rew, val, term_u8, trunc_u8, logp, row, rew_std=None, rew_clip=0.0):
         """Raw device store of one step into row `row` (graph-capturable; all arguments are CUDA tensors;
         obs4 is [N, 4] float32)."""
         ops.store(obs4, act, rew, val, term_u8, trunc_u8, logp, self._obs[row], self._act[row], self._rew[row],
-                  self._val[row], self._term[row], self._trunc[row], self._logp[row], rew_scale, rew_clip)
+                  self._val[row], self._term[row], self._trunc[row], self._logp[row], rew_std, rew_clip)
 
     # ---------------------------------------------------------------------------------------------- GAE
     def finish_path(self, val, i):

@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(256)
                  float* __restrict__ act_row, float* __restrict__ rew_row, float* __restrict__ val_row,
                  float* __restrict__ term_row, uint8_t* __restrict__ trunc_row, float* __restrict__ logp_row,
                  const float* __restrict__ rew_scale, float rew_clip, int64_t N) {
-    float scale = rew_scale ? *rew_scale : 1.0f;
+    const float std = rew_scale ? *rew_scale : 1.0f;   // rew_scale carries rew_std: rewards are DIVIDED by it
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N; e += (int64_t)gridDim.x * blockDim.x) {
         obs_row[e] = obs[e];
         if (act_is_i64) {
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256)
         }
         float r = rew[e];
         if (rew_scale) {
-            r = r * scale;
+            r = r / std;
             r = fminf(fmaxf(r, -rew_clip), rew_clip);
         }
         rew_row[e] = r;

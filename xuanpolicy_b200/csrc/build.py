@@ -27,6 +27,7 @@ SOURCES = {
     "optim.cu": [],
     "host_utils.cu": [],
     "mlp_epilogue.cu": [],
+    "normalize.cu": [],
 }
 HEADERS = ["common.cuh", "crtrig.cuh", "crtrig_consts.inc", os.path.join("..", "..", "include", "xb200.h")]
 

@@ -1,0 +1,203 @@
+// normalize.cu — device-side RunningMeanStd + observation / reward normalisation.
+//
+// Replaces, on the per-step path of PPOCLIP_Agent.train (ppoclip_agent.py:63-64,68,87-92):
+//     RunningMeanStd.update / update_from_moments      xuance/common/statistic_tools.py:63-112  (Chan merge)
+//     Agent._process_observation / _process_reward     xuance/torch/agents/agent.py:104-123
+//     the per-env discounted-return tracker            ppoclip_agent.py:87,91-92
+// State per normaliser: fp64 [2*D+1] = mean[D], var[D], count, with mean/var rounded to float32 after every
+// merge (the reference keeps them as float32 arrays, statistic_tools.py:46-47).
+//
+// Per step: `moments` (column sums over the env batch, deterministic last-block finish) -> [optional NCCL
+// all-reduce of the 2*D+1 sums across ranks: the analogue of mpi_mean, statistic_tools.py:6-17] ->
+// `rms_normalize` (every thread re-derives the merged statistics — a handful of flops — and normalises its
+// row; one thread publishes the merged state into the OTHER state buffer, so readers never race the writer).
+#include "common.cuh"
+
+namespace xb {
+
+constexpr int kNormBlock = 256;
+constexpr int kNormMaxGrid = kNumSMs * 8;
+
+// Chan et al. merge, in float32 like numpy does with float32 arrays and weak python scalars.
+__device__ __forceinline__ void chan_merge(float mean, float var, double count, float b_mean, float b_var,
+                                           double b_count, float& new_mean, float& new_var, double& new_count) {
+    const double tot = count + b_count;
+    const float fc = (float)count, fb = (float)b_count, ft = (float)tot;
+    const float delta = b_mean - mean;
+    new_mean = mean + delta * fb / ft;
+    const float m_a = var * fc, m_b = b_var * fb;
+    const float m2 = m_a + m_b + delta * delta * fc * fb / ft;
+    new_var = m2 / ft;
+    new_count = tot;
+}
+
+// sums[0..3] = sum x_d, sums[4..7] = sum x_d^2, sums[8] = N
+__global__ void __launch_bounds__(kNormBlock)
+    moments4_kernel(const float4* __restrict__ x, int64_t N, double* __restrict__ sums, double* __restrict__ ws) {
+    __shared__ double smem[8 * 32];
+    __shared__ bool is_last;
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = x[i];
+        a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+        a[4] += (double)v.x * v.x; a[5] += (double)v.y * v.y; a[6] += (double)v.z * v.z; a[7] += (double)v.w * v.w;
+    }
+    block_sum<8>(a, smem);
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
+    double* partials = ws + 8;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) partials[8 * blockIdx.x + k] = a[k];
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] += partials[8 * b + k];
+        }
+        block_sum<8>(t, smem);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sums[k] = t[k];
+            sums[8] = (double)N;
+            *ticket = 0u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kNormBlock)
+    rms_normalize_kernel(const float4* __restrict__ x, int dim, const double* __restrict__ sums,
+                         const double* __restrict__ state_in, double* __restrict__ state_out, float clip,
+                         float4* __restrict__ out, int64_t N) {
+    float mean[4], inv[4];
+    const double b_count = sums[8], count = state_in[8];
+    double new_count = count;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        if (d < dim) {
+            const double bm = sums[d] / b_count;
+            double bv = sums[4 + d] / b_count - bm * bm;   // np.square(np.std(x, axis=0))
+            bv = bv > 0.0 ? bv : 0.0;
+            float nm, nv;
+            chan_merge((float)state_in[d], (float)state_in[4 + d], count, (float)bm, (float)bv, b_count, nm, nv, new_count);
+            mean[d] = nm;
+            inv[d] = 1.0f / (sqrtf(nv) + 1e-8f);
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                state_out[d] = (double)nm;
+                state_out[4 + d] = (double)nv;
+            }
+        } else {
+            mean[d] = 0.0f;
+            inv[d] = 0.0f;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) state_out[8] = new_count;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = x[i];
+        float4 o;
+        o.x = fminf(fmaxf((v.x - mean[0]) * inv[0], -clip), clip);
+        o.y = fminf(fmaxf((v.y - mean[1]) * inv[1], -clip), clip);
+        o.z = fminf(fmaxf((v.z - mean[2]) * inv[2], -clip), clip);
+        o.w = fminf(fmaxf((v.w - mean[3]) * inv[3], -clip), clip);
+        out[i] = o;
+    }
+}
+
+// returns = (1 - term) * gamma * returns + rew ; finished envs contribute (R, R^2, 1) and restart at 0
+__global__ void __launch_bounds__(kNormBlock)
+    returns_track_kernel(float* __restrict__ returns, const float* __restrict__ rew, const uint8_t* __restrict__ term,
+                         const uint8_t* __restrict__ trunc, float gamma, double* __restrict__ sums,
+                         double* __restrict__ ws, int64_t N) {
+    __shared__ double smem[3 * 32];
+    __shared__ bool is_last;
+    double a[3] = {0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool tm = term[i] != 0, tr = trunc[i] != 0;
+        float R = (tm ? 0.0f : 1.0f) * gamma * returns[i] + rew[i];
+        if (tm || tr) {
+            a[0] += (double)R;
+            a[1] += (double)R * (double)R;
+            a[2] += 1.0;
+            R = 0.0f;
+        }
+        returns[i] = R;
+    }
+    block_sum<3>(a, smem);
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
+    double* partials = ws + 8;
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 3; ++k) partials[3 * blockIdx.x + k] = a[k];
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double t[3] = {0, 0, 0};
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+            for (int k = 0; k < 3; ++k) t[k] += partials[3 * b + k];
+        block_sum<3>(t, smem);
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < 3; ++k) sums[k] = t[k];
+            *ticket = 0u;
+        }
+    }
+}
+
+// state = (mean, var, count); sums = (sum R, sum R^2, n finished).  rew_std = clip(sqrt(var), 0.1, 100) (agent.py:120)
+__global__ void rms_merge_scalar_kernel(const double* __restrict__ sums, double* __restrict__ state, float* __restrict__ rew_std) {
+    const double n = sums[2];
+    if (n > 0.0) {
+        const double bm = sums[0] / n;
+        double bv = sums[1] / n - bm * bm;
+        bv = bv > 0.0 ? bv : 0.0;
+        float nm, nv;
+        double nc;
+        chan_merge((float)state[0], (float)state[1], state[2], (float)bm, (float)bv, n, nm, nv, nc);
+        state[0] = (double)nm;
+        state[1] = (double)nv;
+        state[2] = nc;
+    }
+    if (rew_std) *rew_std = fminf(fmaxf(sqrtf((float)state[1]), 0.1f), 100.0f);
+}
+
+}  // namespace xb
+
+using namespace xb;
+
+extern "C" int xb_moments4(const float* x, double* sums, double* workspace, int64_t N, xb_stream_t stream) {
+    if (N <= 0 || !x || !sums || !workspace) return XB_E_BADARG;
+    moments4_kernel<<<grid_for(N, kNormBlock, 2), kNormBlock, 0, (cudaStream_t)stream>>>((const float4*)x, N, sums, workspace);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_rms_normalize(const float* x, int dim, const double* sums, const double* state_in, double* state_out,
+                                float clip, float* out, int64_t N, xb_stream_t stream) {
+    if (N <= 0 || dim < 1 || dim > 4 || !x || !sums || !state_in || !state_out || !out || state_in == state_out)
+        return XB_E_BADARG;
+    rms_normalize_kernel<<<grid_for(N, kNormBlock, 2), kNormBlock, 0, (cudaStream_t)stream>>>(
+        (const float4*)x, dim, sums, state_in, state_out, clip, (float4*)out, N);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_returns_track(float* returns, const float* rew, const uint8_t* term, const uint8_t* trunc, float gamma,
+                                double* sums, double* workspace, int64_t N, xb_stream_t stream) {
+    if (N <= 0 || !returns || !rew || !term || !trunc || !sums || !workspace) return XB_E_BADARG;
+    returns_track_kernel<<<grid_for(N, kNormBlock, 2), kNormBlock, 0, (cudaStream_t)stream>>>(returns, rew, term, trunc, gamma,
+                                                                                              sums, workspace, N);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_rms_merge_scalar(const double* sums, double* state, float* rew_std, xb_stream_t stream) {
+    if (!sums || !state) return XB_E_BADARG;
+    rms_merge_scalar_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sums, state, rew_std);
+    XB_LAUNCH_CHECK();
+    return 0;
+}

@@ -52,13 +52,13 @@ def sincos_f64(x):
 
 
 def store(obs, act, rew, val, term, trunc, logp, obs_row, act_row, rew_row, val_row, term_row, trunc_row, logp_row,
-          rew_scale=None, rew_clip=0.0):
+          rew_std=None, rew_clip=0.0):
     N = rew.numel()
     is_i64 = act.dtype == I64
     act_dim = 1 if is_i64 else act.numel() // N
     _lib.call("xb_store", _p(obs, F32), _p(act), int(is_i64), act_dim, _p(rew, F32), _p(val, F32), _p(term, U8),
               _p(trunc, U8), _p(logp, F32), _p(obs_row, F32), _p(act_row, F32), _p(rew_row, F32), _p(val_row, F32),
-              _p(term_row, F32), _p(trunc_row, U8), _p(logp_row, F32), _p(rew_scale, F32), float(rew_clip), N, _stream())
+              _p(term_row, F32), _p(trunc_row, U8), _p(logp_row, F32), _p(rew_std, F32), float(rew_clip), N, _stream())
 
 
 def gae(rew, val, term, boot_last, adv, ret, gamma, lam, trunc=None, boot=None, stats=None, use_gae=True, variant="auto"):
@@ -130,3 +130,21 @@ def act_bias_bwd(dy, y, slope, dz, dbias, workspace):
     B, H = dy.shape
     _lib.call("xb_act_bias_bwd", _p(dy, F32), _p(y, F32), float(slope), _p(dz, F32), _p(dbias, F32), _p(workspace, F32),
               B, H, _stream())
+
+
+def moments4(x, sums, workspace):
+    _lib.call("xb_moments4", _p(x, F32), _p(sums, F64), _p(workspace, F64), x.shape[0], _stream())
+
+
+def rms_normalize(x, dim, sums, state_in, state_out, clip, out):
+    _lib.call("xb_rms_normalize", _p(x, F32), dim, _p(sums, F64), _p(state_in, F64), _p(state_out, F64), float(clip),
+              _p(out, F32), x.shape[0], _stream())
+
+
+def returns_track(returns, rew, term, trunc, gamma, sums, workspace):
+    _lib.call("xb_returns_track", _p(returns, F32), _p(rew, F32), _p(term, U8), _p(trunc, U8), float(gamma), _p(sums, F64),
+              _p(workspace, F64), returns.numel(), _stream())
+
+
+def rms_merge_scalar(sums, state, rew_std):
+    _lib.call("xb_rms_merge_scalar", _p(sums, F64), _p(state, F64), _p(rew_std, F32), _stream())
