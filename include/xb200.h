@@ -189,7 +189,10 @@ int xb_clip_adam_step(float* param, const float* grad, float* exp_avg, float* ex
  *   xb_moments4      sums fp64 [9] = column sums (4), column sums of squares (4), N of x f32 [N][4]
  *                    (between the two calls the 9 sums may be all-reduced across ranks: the analogue of mpi_mean :6-17)
  *   xb_rms_normalize merges `sums` into state_in (Chan), writes the merged state to state_out (!= state_in) and
- *                    out = clip((x - mean) / (sqrt(var) + 1e-8), +-clip)     f32 [N][4]; lanes >= dim give 0
+ *                    out = clip((x - mean) / (sqrt(var) + 1e-8), +-clip)     f32 [N][4]; lanes >= dim give 0.
+ *                    Rows [0, n_merged_rows) use the merged statistics, rows beyond use state_in unchanged (the
+ *                    previous step's terminal observations, normalised as ppoclip_agent.py:99 saw them);
+ *                    n_merged_rows == 0 normalises without updating (sums may be NULL).
  *   xb_returns_track returns[i] = (1-term)*gamma*returns[i] + rew[i]; finished envs add (R, R^2, 1) to sums fp64 [3]
  *                    and restart at 0
  *   xb_rms_merge_scalar merges those sums into the return normaliser state fp64 [3] = (mean, var, count) and
@@ -198,7 +201,7 @@ int xb_clip_adam_step(float* param, const float* grad, float* exp_avg, float* ex
  * ---------------------------------------------------------------------------------------------------------- */
 int xb_moments4(const float* x, double* sums, double* workspace, int64_t N, xb_stream_t stream);
 int xb_rms_normalize(const float* x, int dim, const double* sums, const double* state_in, double* state_out,
-                     float clip, float* out, int64_t N, xb_stream_t stream);
+                     float clip, float* out, int64_t N, int64_t n_merged_rows, xb_stream_t stream);
 int xb_returns_track(float* returns, const float* rew, const uint8_t* term, const uint8_t* trunc, float gamma,
                      double* sums, double* workspace, int64_t N, xb_stream_t stream);
 int xb_rms_merge_scalar(const double* sums, double* state, float* rew_std, xb_stream_t stream);

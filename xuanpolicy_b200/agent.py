@@ -16,7 +16,8 @@ What changes is the shape of the loop, not its arithmetic:
 Index permutations follow the reference (`np.random.shuffle` of a persistent arange, :76-78) when
 `config.shuffle == "host"` (copied H2D from pinned memory each epoch), or are drawn on device ("device").
 
-Not yet on this path (next rows): use_obsnorm / use_rewnorm — constructing with them raises.
+`use_obsnorm` / `use_rewnorm` run on device too: RunningMeanStd moments + Chan merge + clip in
+csrc/normalize.cu, two extra launches per step each (single-GPU; the sharded variant needs a per-step all-reduce).
 """
 import numpy as np
 import torch
@@ -67,9 +68,10 @@ class HostPermutationFeeder:
 
 class PPOCLIP_Agent:
     def __init__(self, config, envs, policy, optimizer, scheduler=None, device=None, process_group=None):
-        if getattr(config, "use_obsnorm", False) or getattr(config, "use_rewnorm", False):
-            raise NotImplementedError("device-side observation/reward normalisation is not implemented yet "
-                                      "(SURVEY.md §8 f1); run with use_obsnorm=False, use_rewnorm=False")
+        self.use_obsnorm = bool(getattr(config, "use_obsnorm", False))
+        self.use_rewnorm = bool(getattr(config, "use_rewnorm", False))
+        self.obsnorm_range = float(getattr(config, "obsnorm_range", 5))
+        self.rewnorm_range = float(getattr(config, "rewnorm_range", 5))
         self.config, self.envs, self.policy = config, envs, policy
         self.device = torch.device(device if device is not None else "cuda")
         self.n_envs, self.n_steps = envs.num_envs, config.n_steps
@@ -113,6 +115,22 @@ class PPOCLIP_Agent:
         self.sync_info = bool(getattr(config, "sync_info", True))
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        # device-side RunningMeanStd (statistic_tools.py:35-48: mean 0, var 1, count 1e-4), obs state ping-pongs
+        f64 = dict(dtype=torch.float64, device=dev)
+        init = torch.tensor([0, 0, 0, 0, 1, 1, 1, 1, 1e-4], **f64)
+        self._obs_rms = [init.clone(), init.clone()]
+        self._rms_cur = 0
+        self._obs_sums = torch.zeros(9, **f64)
+        self._obs_ws = torch.zeros(8 + 8 * 1184, **f64)
+        self._xn = torch.zeros((2 * N, 4), dtype=torch.float32, device=dev)      # normalised policy input
+        self._ret_rms = torch.tensor([0.0, 1.0, 1e-4], **f64)
+        self._ret_sums = torch.zeros(3, **f64)
+        self._ret_ws = torch.zeros(8 + 8 * 1184, **f64)
+        self._returns = torch.zeros(N, dtype=torch.float32, device=dev)
+        self._rew_std = torch.ones(1, dtype=torch.float32, device=dev)
+        if self.use_obsnorm and self.learner.world_size > 1:
+            raise NotImplementedError("use_obsnorm with env sharding needs the per-step all-reduce of the observation "
+                                      "moments inside the rollout graph; not wired yet")
         self._rollout_graph = None
         self._epoch_graph = None
         self._stage_graphs = None
@@ -148,15 +166,33 @@ class PPOCLIP_Agent:
         """One vector step into buffer row t (reference loop body, ppoclip_agent.py:62-68,88,101)."""
         N, env, mem = self.n_envs, self.envs, self.memory
         x_cur, x_nxt = self._x[self._cur], self._x[self._cur ^ 1]
-        dist, v = self._policy_forward(x_cur)                     # V on [obs_t ; terminal obs of step t-1]
+        x_in = self._normalize_obs(x_cur, update=True)            # obs_rms.update(obs); _process_observation (:63-64)
+        dist, v = self._policy_forward(x_in)                      # V on [obs_t ; terminal obs of step t-1]
         if t > 0:
             mem._boot[t - 1].copy_(v[N:])                         # bootstrap for envs truncated at step t-1 (:99)
         self._sample(dist, t)
         ops.env_step(env._kind, env._state, env._rng, env._elapsed, env._ep_score, self._act.reshape(N),
                      x_nxt[N:], x_nxt[:N], env._rew, env._term, env._trunc, env._reset_obs, env._ep_step_out,
                      env._ep_score_out, env.max_episode_length, ep_stats=env.ep_stats)
-        mem.store_device(x_cur[:N], self._act, env._rew, v[:N].contiguous(), env._term, env._trunc, self._logp, t)
+        mem.store_device(x_in[:N], self._act, env._rew, v[:N].contiguous(), env._term, env._trunc, self._logp, t,
+                         rew_std=self._rew_std if self.use_rewnorm else None, rew_clip=self.rewnorm_range)
+        if self.use_rewnorm:                                      # returns tracker + ret_rms.update (:87,:91-92)
+            ops.returns_track(self._returns, env._rew, env._term, env._trunc, self.gamma, self._ret_sums, self._ret_ws)
+            ops.rms_merge_scalar(self._ret_sums, self._ret_rms, self._rew_std)
         self._cur ^= 1
+
+    def _normalize_obs(self, x, update):
+        """rows [0,N): the observations the agent acts on — merged into obs_rms first when `update`; rows [N,2N): the
+        previous step's terminal observations, normalised with the statistics of that step (agent.py:104-116)."""
+        if not self.use_obsnorm:
+            return x
+        N = self.n_envs
+        s_in, s_out = self._obs_rms[self._rms_cur], self._obs_rms[self._rms_cur ^ 1]
+        if update:
+            ops.moments4(x[:N], self._obs_sums, self._obs_ws)
+        ops.rms_normalize(x, self._obs_dim, self._obs_sums, s_in, s_out, self.obsnorm_range, self._xn, N if update else 0)
+        self._rms_cur ^= 1
+        return self._xn
 
     def _rollout(self):
         """n_steps vector steps, the bootstrap forward (:70) and the batched GAE for every env and segment (:71-75)."""
@@ -164,13 +200,16 @@ class PPOCLIP_Agent:
         with torch.no_grad():
             for t in range(self.n_steps):
                 self._rollout_step(t)
-            _, v = self._policy_forward(self._x[self._cur])
+            _, v = self._policy_forward(self._normalize_obs(self._x[self._cur], update=False))
             self._boot_last.copy_(v[N:])
             self.memory.finish_rollout(self._boot_last)
             ops.counter_add(self._ctr, self.n_steps)
         if self.n_steps % 2:   # keep the ping-pong phase identical for every replay of the captured graph
             self._x[self._cur ^ 1].copy_(self._x[self._cur])
             self._cur ^= 1
+        if self._rms_cur:      # same for the normaliser state (n_steps + 1 publications per rollout)
+            self._obs_rms[0].copy_(self._obs_rms[1])
+            self._rms_cur = 0
 
     # ---------------------------------------------------------------------------------------------- update phase
     def _epoch_body(self):
@@ -271,7 +310,8 @@ class PPOCLIP_Agent:
         """Everything a warm-up rollout/update mutates, so that capturing leaves training state untouched."""
         env, fl = self.envs, self.learner._flat
         tensors = [env._state, env._rng, env._elapsed, env._ep_score, env.ep_stats, self._ctr, self._x[0], self._x[1],
-                   fl.flat_param, fl.exp_avg, fl.exp_avg_sq, fl.step, fl.lr]
+                   fl.flat_param, fl.exp_avg, fl.exp_avg_sq, fl.step, fl.lr, self._obs_rms[0], self._obs_rms[1],
+                   self._ret_rms, self._returns, self._rew_std]
         return [(t, t.clone()) for t in tensors] + [("cur", self._cur)]
 
     def _restore(self, snap):

@@ -72,37 +72,43 @@ __global__ void __launch_bounds__(kNormBlock)
 __global__ void __launch_bounds__(kNormBlock)
     rms_normalize_kernel(const float4* __restrict__ x, int dim, const double* __restrict__ sums,
                          const double* __restrict__ state_in, double* __restrict__ state_out, float clip,
-                         float4* __restrict__ out, int64_t N) {
-    float mean[4], inv[4];
-    const double b_count = sums[8], count = state_in[8];
+                         float4* __restrict__ out, int64_t N, int64_t n_merged_rows) {
+    // rows [0, n_merged_rows) are normalised with the MERGED statistics, the rest with state_in as it is
+    float mean[4], den[4], mean_old[4], den_old[4];
+    const double b_count = n_merged_rows > 0 ? sums[8] : 0.0, count = state_in[8];
     double new_count = count;
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
+        mean[d] = mean_old[d] = 0.0f;
+        den[d] = den_old[d] = 1.0f;
         if (d < dim) {
-            const double bm = sums[d] / b_count;
-            double bv = sums[4 + d] / b_count - bm * bm;   // np.square(np.std(x, axis=0))
-            bv = bv > 0.0 ? bv : 0.0;
-            float nm, nv;
-            chan_merge((float)state_in[d], (float)state_in[4 + d], count, (float)bm, (float)bv, b_count, nm, nv, new_count);
+            float nm = (float)state_in[d], nv = (float)state_in[4 + d];
+            mean_old[d] = nm;
+            den_old[d] = sqrtf(nv) + 1e-8f;
+            if (b_count > 0.0) {
+                const double bm = sums[d] / b_count;
+                double bv = sums[4 + d] / b_count - bm * bm;   // np.square(np.std(x, axis=0))
+                bv = bv > 0.0 ? bv : 0.0;
+                chan_merge((float)state_in[d], (float)state_in[4 + d], count, (float)bm, (float)bv, b_count, nm, nv, new_count);
+            }
             mean[d] = nm;
-            inv[d] = 1.0f / (sqrtf(nv) + 1e-8f);
+            den[d] = sqrtf(nv) + 1e-8f;
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 state_out[d] = (double)nm;
                 state_out[4 + d] = (double)nv;
             }
-        } else {
-            mean[d] = 0.0f;
-            inv[d] = 0.0f;
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) state_out[8] = new_count;
+    const float keep[4] = {dim > 0 ? 1.0f : 0.0f, dim > 1 ? 1.0f : 0.0f, dim > 2 ? 1.0f : 0.0f, dim > 3 ? 1.0f : 0.0f};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 v = x[i];
-        float4 o;
-        o.x = fminf(fmaxf((v.x - mean[0]) * inv[0], -clip), clip);
-        o.y = fminf(fmaxf((v.y - mean[1]) * inv[1], -clip), clip);
-        o.z = fminf(fmaxf((v.z - mean[2]) * inv[2], -clip), clip);
-        o.w = fminf(fmaxf((v.w - mean[3]) * inv[3], -clip), clip);
+        const bool nw = i < n_merged_rows;
+        float4 o;   // (obs - mean) / (std + EPS), clipped  (agent.py:112-113)
+        o.x = keep[0] * fminf(fmaxf((v.x - (nw ? mean[0] : mean_old[0])) / (nw ? den[0] : den_old[0]), -clip), clip);
+        o.y = keep[1] * fminf(fmaxf((v.y - (nw ? mean[1] : mean_old[1])) / (nw ? den[1] : den_old[1]), -clip), clip);
+        o.z = keep[2] * fminf(fmaxf((v.z - (nw ? mean[2] : mean_old[2])) / (nw ? den[2] : den_old[2]), -clip), clip);
+        o.w = keep[3] * fminf(fmaxf((v.w - (nw ? mean[3] : mean_old[3])) / (nw ? den[3] : den_old[3]), -clip), clip);
         out[i] = o;
     }
 }
@@ -177,11 +183,12 @@ extern "C" int xb_moments4(const float* x, double* sums, double* workspace, int6
 }
 
 extern "C" int xb_rms_normalize(const float* x, int dim, const double* sums, const double* state_in, double* state_out,
-                                float clip, float* out, int64_t N, xb_stream_t stream) {
-    if (N <= 0 || dim < 1 || dim > 4 || !x || !sums || !state_in || !state_out || !out || state_in == state_out)
+                                float clip, float* out, int64_t N, int64_t n_merged_rows, xb_stream_t stream) {
+    if (N <= 0 || dim < 1 || dim > 4 || !x || !state_in || !state_out || !out || state_in == state_out ||
+        n_merged_rows < 0 || n_merged_rows > N || (n_merged_rows > 0 && !sums))
         return XB_E_BADARG;
     rms_normalize_kernel<<<grid_for(N, kNormBlock, 2), kNormBlock, 0, (cudaStream_t)stream>>>(
-        (const float4*)x, dim, sums, state_in, state_out, clip, (float4*)out, N);
+        (const float4*)x, dim, sums, state_in, state_out, clip, (float4*)out, N, n_merged_rows);
     XB_LAUNCH_CHECK();
     return 0;
 }

@@ -136,9 +136,9 @@ def moments4(x, sums, workspace):
     _lib.call("xb_moments4", _p(x, F32), _p(sums, F64), _p(workspace, F64), x.shape[0], _stream())
 
 
-def rms_normalize(x, dim, sums, state_in, state_out, clip, out):
+def rms_normalize(x, dim, sums, state_in, state_out, clip, out, n_merged_rows):
     _lib.call("xb_rms_normalize", _p(x, F32), dim, _p(sums, F64), _p(state_in, F64), _p(state_out, F64), float(clip),
-              _p(out, F32), x.shape[0], _stream())
+              _p(out, F32), x.shape[0], int(n_merged_rows), _stream())
 
 
 def returns_track(returns, rew, term, trunc, gamma, sums, workspace):
