@@ -108,7 +108,8 @@ def build_agent(wl, world, shuffle, sync_info, pg=None):
     return build_ppo(wl["env_id"], device="cuda", process_group=pg, parallels=n_local, n_steps=wl["horizon"],
                      gamma=wl["gamma"], gae_lambda=0.95, n_epoch=8, n_minibatch=n_mb, representation_hidden_size=h,
                      actor_hidden_size=h, critic_hidden_size=h, shuffle=shuffle, sync_info=sync_info,
-                     seed=1 + 1000 * (torch.distributed.get_rank() if world > 1 else 0), running_steps=10 ** 9)
+                     seed=1 + 1000 * (torch.distributed.get_rank() if world > 1 else 0), policy_seed=1,
+                     running_steps=10 ** 9)
 
 
 def time_agent(agent, steps, warmup, flush, world):

@@ -51,7 +51,7 @@ def test_returns_tracker_and_reward_normaliser_vs_oracle():
     ret_rms = ref_port.RunningMeanStdPort(())
     returns = np.zeros(N, np.float32)
     f64 = dict(dtype=torch.float64, device="cuda")
-    d_ret, d_state = torch.zeros(N, device="cuda"), torch.tensor([0.0, 1.0, 1e-4], **f64)
+    d_ret, d_state = torch.zeros(N, **f64), torch.tensor([0.0, 1.0, 1e-4], **f64)
     d_sums, d_ws, d_std = torch.zeros(3, **f64), torch.zeros(8 + 8 * 1184, **f64), torch.ones(1, device="cuda")
     for t in range(40):
         rew = (rng.standard_normal(N) * 3 - 1).astype(np.float32)
@@ -65,13 +65,13 @@ def test_returns_tracker_and_reward_normaliser_vs_oracle():
             if term[i] or trunc[i]:
                 ret_rms.update(returns[i:i + 1])
                 returns[i] = 0.0
-        returns = returns.astype(np.float32)
         ops.returns_track(d_ret, torch.from_numpy(rew).cuda(), torch.from_numpy(term.astype(np.uint8)).cuda(),
                           torch.from_numpy(trunc.astype(np.uint8)).cuda(), gamma, d_sums, d_ws)
         ops.rms_merge_scalar(d_sums, d_state, d_std)
-        assert np.allclose(d_ret.cpu().numpy(), returns, rtol=1e-6, atol=1e-6)
+        assert returns.dtype == np.float64            # the reference's tracker is float64 after the first step
+        assert np.allclose(d_ret.cpu().numpy(), returns, rtol=1e-12, atol=1e-12)
         st = d_state.cpu().numpy()
-        assert abs(st[0] - ret_rms.mean) <= 1e-4 * max(1, abs(ret_rms.mean)) and abs(st[1] - ret_rms.var) <= 1e-3 * ret_rms.var
+        assert abs(st[0] - ret_rms.mean) <= 1e-6 * max(1, abs(ret_rms.mean)) and abs(st[1] - ret_rms.var) <= 1e-5 * ret_rms.var
         assert abs(st[2] - ret_rms.count) < 1e-6
 
 
@@ -98,17 +98,21 @@ def test_native_rollout_with_obs_and_reward_normalisation():
             raw = ref.obs.copy()
             obs_rms.update(raw)
             proc = np.clip((raw - obs_rms.mean) / (obs_rms.std + 1e-8), -5, 5)
-            assert np.allclose(obs[t, :, :3], proc, rtol=1e-4, atol=1e-4), (rollout, t, np.abs(obs[t, :, :3] - proc).max())
+            # the reference accumulates the batch mean sequentially in float32 (error ~1e-6 in observation units;
+            # the kernel accumulates in fp64), and while all same-seed envs still share a state std is ~1e-3, so the
+            # tolerance is expressed in observation units and divided by std
+            tol = 1e-4 + 4e-6 / (obs_rms.std + 1e-8)
+            assert np.all(np.abs(obs[t, :, :3] - proc) <= tol), (rollout, t, np.abs(obs[t, :, :3] - proc).max())
             o = ref.step(act[t, :, 0])
             std = np.clip(ret_rms.std, 0.1, 100)
             assert np.allclose(rew[t], np.clip(o["rew"] / std, -5, 5), rtol=1e-4, atol=1e-5), (rollout, t)
-            returns = ((1 - o["term"]) * agent.gamma * returns + o["rew"]).astype(np.float32)
+            returns = (1 - o["term"]) * agent.gamma * returns + o["rew"]
             done = o["term"] | o["trunc"]
             for i in np.nonzero(done)[0]:
                 ret_rms.update(returns[i:i + 1])
                 returns[i] = 0.0
             ref.obs[done] = o["reset_obs"][done]
     st = agent._obs_rms[0].cpu().numpy()
-    assert np.allclose(st[:3], obs_rms.mean, rtol=1e-4, atol=1e-5) and abs(st[8] - obs_rms.count) < 1e-6 * obs_rms.count
+    assert np.allclose(st[:3], obs_rms.mean, rtol=1e-4, atol=2e-5) and abs(st[8] - obs_rms.count) < 1e-6 * obs_rms.count
     info = agent.train(T)
     assert np.isfinite(info["critic-loss"])

@@ -94,6 +94,8 @@ class PPOCLIP_Agent:
                                        value_clip=getattr(config, "value_clip", None))
         self.learner.enable_fused_optimizer(process_group)
         self.world_size = self.learner.world_size
+        if self.world_size > 1:   # replicated policy: every rank starts from rank 0's parameters
+            torch.distributed.broadcast(self.learner._flat.flat_param, src=0, group=process_group)
         N, dev = self.n_envs, self.device
         obs_dim = self.memory.obs_dim
         self._obs_dim = obs_dim
@@ -126,7 +128,7 @@ class PPOCLIP_Agent:
         self._ret_rms = torch.tensor([0.0, 1.0, 1e-4], **f64)
         self._ret_sums = torch.zeros(3, **f64)
         self._ret_ws = torch.zeros(8 + 8 * 1184, **f64)
-        self._returns = torch.zeros(N, dtype=torch.float32, device=dev)
+        self._returns = torch.zeros(N, dtype=torch.float64, device=dev)
         self._rew_std = torch.ones(1, dtype=torch.float32, device=dev)
         if self.use_obsnorm and self.learner.world_size > 1:
             raise NotImplementedError("use_obsnorm with env sharding needs the per-step all-reduce of the observation "

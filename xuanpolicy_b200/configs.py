@@ -23,7 +23,7 @@ def ppo_config(env_id, **overrides):
     return Namespace(**cfg)
 
 
-def build_ppo(env_id, device="cuda", process_group=None, **overrides):
+def build_ppo(env_id, device="cuda", process_group=None, policy_seed=None, **overrides):
     """Envs + policy + Adam + LinearLR + agent, wired like Runner_DRL.__init__ (xuance/torch/runners/runner_drl.py:15-74)."""
     import torch
 
@@ -31,7 +31,7 @@ def build_ppo(env_id, device="cuda", process_group=None, **overrides):
     from .policies import make_policy
     from .vec_env import DummyVecEnv_Gym, make_env_fns
     cfg = ppo_config(env_id, device=device, **overrides)
-    torch.manual_seed(cfg.seed)
+    torch.manual_seed(cfg.seed if policy_seed is None else policy_seed)   # replicated policy: same init on every rank
     envs = DummyVecEnv_Gym(make_env_fns(env_id, cfg.seed, cfg.parallels), device=device, native=True)
     envs.reset()                                                          # runner_basic.py:12
     policy = make_policy(envs.observation_space, envs.action_space, hidden=tuple(cfg.representation_hidden_size),

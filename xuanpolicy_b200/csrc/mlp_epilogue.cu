@@ -15,6 +15,45 @@
 namespace xb {
 
 constexpr int kEpiBlock = 256;
+constexpr int kEpiUnroll = 4;
+
+// y[b,h] = leaky_relu(y[b,h] + bias[h]) in place: the forward epilogue of Linear+LeakyReLU after a bias-free cuBLAS mm
+// (torch's addmm runs a separate 36 us bias kernel plus a 10 us activation kernel at [65536,128]; this is one pass).
+__global__ void __launch_bounds__(kEpiBlock)
+    bias_act_fwd_kernel(float4* __restrict__ y, const float4* __restrict__ bias, float slope, int64_t n4, int H4) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * kEpiUnroll) {
+        float4 v[kEpiUnroll];
+#pragma unroll
+        for (int u = 0; u < kEpiUnroll; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n4) v[u] = y[i];
+        }
+#pragma unroll
+        for (int u = 0; u < kEpiUnroll; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n4) {
+                const float4 b = bias[i % H4];
+                float4 o;
+                o.x = v[u].x + b.x; o.y = v[u].y + b.y; o.z = v[u].z + b.z; o.w = v[u].w + b.w;
+                o.x = o.x > 0.f ? o.x : o.x * slope;
+                o.y = o.y > 0.f ? o.y : o.y * slope;
+                o.z = o.z > 0.f ? o.z : o.z * slope;
+                o.w = o.w > 0.f ? o.w : o.w * slope;
+                y[i] = o;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float4 lrelu_bwd4(const float4 g, const float4 o, float slope) {
+    float4 z;
+    z.x = o.x > 0.f ? g.x : g.x * slope;
+    z.y = o.y > 0.f ? g.y : g.y * slope;
+    z.z = o.z > 0.f ? g.z : g.z * slope;
+    z.w = o.w > 0.f ? g.w : g.w * slope;
+    return z;
+}
 
 __global__ void __launch_bounds__(kEpiBlock)
     act_bias_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ y, float slope,
@@ -29,15 +68,22 @@ __global__ void __launch_bounds__(kEpiBlock)
     const int64_t row1 = row0 + rows_per_cta < B ? row0 + rows_per_cta : B;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < rows_per_pass) {
-        for (int64_t b = row0 + r; b < row1; b += rows_per_pass) {
-            const float4 g = dy[b * H4 + c], o = y[b * H4 + c];
-            float4 z;
-            z.x = o.x > 0.f ? g.x : g.x * slope;
-            z.y = o.y > 0.f ? g.y : g.y * slope;
-            z.z = o.z > 0.f ? g.z : g.z * slope;
-            z.w = o.w > 0.f ? g.w : g.w * slope;
-            dz[b * H4 + c] = z;
-            acc.x += z.x; acc.y += z.y; acc.z += z.z; acc.w += z.w;
+        for (int64_t b0 = row0 + r; b0 < row1; b0 += (int64_t)rows_per_pass * kEpiUnroll) {
+            float4 g[kEpiUnroll], o[kEpiUnroll];
+#pragma unroll
+            for (int u = 0; u < kEpiUnroll; ++u) {       // all loads first: 2*kEpiUnroll 16-byte requests in flight
+                const int64_t b = b0 + (int64_t)u * rows_per_pass;
+                if (b < row1) { g[u] = dy[b * H4 + c]; o[u] = y[b * H4 + c]; }
+            }
+#pragma unroll
+            for (int u = 0; u < kEpiUnroll; ++u) {
+                const int64_t b = b0 + (int64_t)u * rows_per_pass;
+                if (b < row1) {
+                    const float4 z = lrelu_bwd4(g[u], o[u], slope);
+                    dz[b * H4 + c] = z;
+                    acc.x += z.x; acc.y += z.y; acc.z += z.z; acc.w += z.w;
+                }
+            }
         }
         red[r * H4 + c] = acc;
     }
@@ -54,12 +100,24 @@ __global__ void __launch_bounds__(kEpiBlock)
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (is_last) {
+    if (is_last) {   // all threads of the last CTA reduce the per-CTA partials: thread (r, c) takes CTAs r, r+R, ...
         __threadfence();
-        for (int h = threadIdx.x; h < H4 * 4; h += blockDim.x) {
-            float s = 0.f;
-            for (int g = 0; g < (int)gridDim.x; ++g) s += partials[(int64_t)g * H4 * 4 + h];
-            dbias[h] = s;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows_per_pass) {
+            for (int g = r; g < (int)gridDim.x; g += rows_per_pass) {
+                const float4 t = reinterpret_cast<const float4*>(partials)[(int64_t)g * H4 + c];
+                s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+            }
+            red[r * H4 + c] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < H4) {
+            float4 t = red[threadIdx.x];
+            for (int k = 1; k < rows_per_pass; ++k) {
+                const float4 u = red[k * H4 + threadIdx.x];
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            reinterpret_cast<float4*>(dbias)[threadIdx.x] = t;
         }
         if (threadIdx.x == 0) *ticket = 0u;
     }
@@ -69,7 +127,17 @@ __global__ void __launch_bounds__(kEpiBlock)
 
 using namespace xb;
 
-// workspace: fp32 [1 + grid_max * H] with grid_max = 592; word 0 is the ticket (zero-initialised by the caller)
+extern "C" int xb_bias_act_fwd(float* y, const float* bias, float slope, int64_t B, int H, xb_stream_t stream) {
+    if (B <= 0 || !y || !bias) return XB_E_BADARG;
+    if (H % 4 != 0 || H < 4) return XB_E_UNSUPPORTED;
+    const int64_t n4 = B * (H / 4);
+    bias_act_fwd_kernel<<<grid_for((n4 + kEpiUnroll - 1) / kEpiUnroll, kEpiBlock, 8), kEpiBlock, 0, (cudaStream_t)stream>>>(
+        (float4*)y, (const float4*)bias, slope, n4, H / 4);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+// workspace: fp32 [4 + 592 * H]; word 0 is the ticket (zero-initialised by the caller)
 extern "C" int xb_act_bias_bwd(const float* dy, const float* y, float slope, float* dz, float* dbias, float* workspace,
                                int64_t B, int H, xb_stream_t stream) {
     if (B <= 0 || !dy || !y || !dz || !dbias || !workspace) return XB_E_BADARG;
@@ -77,7 +145,7 @@ extern "C" int xb_act_bias_bwd(const float* dy, const float* y, float slope, flo
     const int H4 = H / 4;
     const int rows_per_pass = kEpiBlock / H4;
     int grid = kNumSMs * 4;
-    const int64_t need = (B + rows_per_pass * 8 - 1) / (rows_per_pass * 8);  // at least ~8 passes per CTA
+    const int64_t need = (B + rows_per_pass * kEpiUnroll * 2 - 1) / (rows_per_pass * kEpiUnroll * 2);
     if (need < grid) grid = (int)(need < 1 ? 1 : need);
     const size_t smem = (size_t)rows_per_pass * H4 * sizeof(float4);
     act_bias_bwd_kernel<<<grid, kEpiBlock, smem, (cudaStream_t)stream>>>(

@@ -113,22 +113,24 @@ __global__ void __launch_bounds__(kNormBlock)
     }
 }
 
-// returns = (1 - term) * gamma * returns + rew ; finished envs contribute (R, R^2, 1) and restart at 0
+// returns = (1 - term) * gamma * returns + rew ; finished envs contribute (R, R^2, 1) and restart at 0.
+// fp64 like the reference: `(1 - terminals) * self.gamma * self.returns + rewards` promotes to float64
+// (int64 array x python float), and ret_rms then evolves in float64 (ppoclip_agent.py:87,91).
 __global__ void __launch_bounds__(kNormBlock)
-    returns_track_kernel(float* __restrict__ returns, const float* __restrict__ rew, const uint8_t* __restrict__ term,
-                         const uint8_t* __restrict__ trunc, float gamma, double* __restrict__ sums,
+    returns_track_kernel(double* __restrict__ returns, const float* __restrict__ rew, const uint8_t* __restrict__ term,
+                         const uint8_t* __restrict__ trunc, double gamma, double* __restrict__ sums,
                          double* __restrict__ ws, int64_t N) {
     __shared__ double smem[3 * 32];
     __shared__ bool is_last;
     double a[3] = {0, 0, 0};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
         const bool tm = term[i] != 0, tr = trunc[i] != 0;
-        float R = (tm ? 0.0f : 1.0f) * gamma * returns[i] + rew[i];
+        double R = (tm ? 0.0 : 1.0) * gamma * returns[i] + (double)rew[i];
         if (tm || tr) {
-            a[0] += (double)R;
-            a[1] += (double)R * (double)R;
+            a[0] += R;
+            a[1] += R * R;
             a[2] += 1.0;
-            R = 0.0f;
+            R = 0.0;
         }
         returns[i] = R;
     }
@@ -161,14 +163,13 @@ __global__ void rms_merge_scalar_kernel(const double* __restrict__ sums, double*
         const double bm = sums[0] / n;
         double bv = sums[1] / n - bm * bm;
         bv = bv > 0.0 ? bv : 0.0;
-        float nm, nv;
-        double nc;
-        chan_merge((float)state[0], (float)state[1], state[2], (float)bm, (float)bv, n, nm, nv, nc);
-        state[0] = (double)nm;
-        state[1] = (double)nv;
-        state[2] = nc;
+        const double count = state[2], tot = count + n, delta = bm - state[0];   // Chan merge in fp64
+        const double m2 = state[1] * count + bv * n + delta * delta * count * n / tot;
+        state[0] = state[0] + delta * n / tot;
+        state[1] = m2 / tot;
+        state[2] = tot;
     }
-    if (rew_std) *rew_std = fminf(fmaxf(sqrtf((float)state[1]), 0.1f), 100.0f);
+    if (rew_std) *rew_std = (float)fmin(fmax(sqrt(state[1]), 0.1), 100.0);
 }
 
 }  // namespace xb
@@ -193,7 +194,7 @@ extern "C" int xb_rms_normalize(const float* x, int dim, const double* sums, con
     return 0;
 }
 
-extern "C" int xb_returns_track(float* returns, const float* rew, const uint8_t* term, const uint8_t* trunc, float gamma,
+extern "C" int xb_returns_track(double* returns, const float* rew, const uint8_t* term, const uint8_t* trunc, double gamma,
                                 double* sums, double* workspace, int64_t N, xb_stream_t stream) {
     if (N <= 0 || !returns || !rew || !term || !trunc || !sums || !workspace) return XB_E_BADARG;
     returns_track_kernel<<<grid_for(N, kNormBlock, 2), kNormBlock, 0, (cudaStream_t)stream>>>(returns, rew, term, trunc, gamma,

@@ -123,11 +123,19 @@ class PPOCLIP_Learner:
         else:
             mu = p0.detach().contiguous()
             std = p1
-            logstd = std.detach().log().contiguous()
+            param = getattr(getattr(self.policy, "actor", None), "logstd", None)   # gaussian.py:25
+            direct = param is not None and param.requires_grad and param.numel() == mu.shape[1]
+            logstd = param.detach() if direct else std.detach().log().contiguous()
             dmu = torch.empty_like(mu)
             dls = torch.empty(mu.shape[1], dtype=torch.float64, device=mu.device)
             ops.ppo_loss_gaussian(mu, logstd, v, act, ret, adv, old_logp, dmu, dls, dv, self._scalars, **common)
-            if std.requires_grad:  # d/dstd = d/dlogstd / std ; autograd carries it back to the logstd parameter
+            if direct:             # the kernel's dL/dlogstd goes straight into the parameter's gradient
+                torch.autograd.backward([p0, v_pred], [dmu, dv])
+                if param.grad is None:
+                    param.grad = dls.to(param.dtype)
+                else:
+                    param.grad.add_(dls.to(param.dtype))
+            elif std.requires_grad:  # d/dstd = d/dlogstd / std ; autograd carries it back to the logstd parameter
                 torch.autograd.backward([p0, v_pred, std], [dmu, dv, (dls / std.detach().double()).to(std.dtype)])
             else:
                 torch.autograd.backward([p0, v_pred], [dmu, dv])

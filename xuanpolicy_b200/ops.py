@@ -142,9 +142,14 @@ def rms_normalize(x, dim, sums, state_in, state_out, clip, out, n_merged_rows):
 
 
 def returns_track(returns, rew, term, trunc, gamma, sums, workspace):
-    _lib.call("xb_returns_track", _p(returns, F32), _p(rew, F32), _p(term, U8), _p(trunc, U8), float(gamma), _p(sums, F64),
+    _lib.call("xb_returns_track", _p(returns, F64), _p(rew, F32), _p(term, U8), _p(trunc, U8), float(gamma), _p(sums, F64),
               _p(workspace, F64), returns.numel(), _stream())
 
 
 def rms_merge_scalar(sums, state, rew_std):
     _lib.call("xb_rms_merge_scalar", _p(sums, F64), _p(state, F64), _p(rew_std, F32), _stream())
+
+
+def bias_act_fwd(y, bias, slope):
+    B, H = y.shape
+    _lib.call("xb_bias_act_fwd", _p(y, F32), _p(bias, F32), float(slope), B, H, _stream())

@@ -21,16 +21,42 @@ import torch.nn as nn
 _HALF_LOG_2PI = 0.5 * math.log(2.0 * math.pi)
 
 
+def _split_k(B):
+    S = 1
+    while S < 64 and B % (2 * S) == 0 and B // (2 * S) >= 512:
+        S *= 2
+    return S
+
+
+def _wgrad(dz, x):
+    """dW = dz^T @ x for tall-skinny operands (M = N = H, K = B): cuBLAS's fp32 heuristics serve that shape with a
+    handful of CTAs, so it is issued as a batched split-K product over S slabs of the batch and summed."""
+    B, H = dz.shape
+    S = _split_k(B)
+    if S > 1 and x.is_contiguous():
+        return torch.bmm(dz.view(S, B // S, H).transpose(1, 2), x.view(S, B // S, x.shape[1])).sum(0)
+    return dz.t() @ x
+
+
+def _colsum(dy):
+    """Bias gradient of a narrow head (A or 1 columns): two-stage sum instead of torch's single-CTA reduction."""
+    B = dy.shape[0]
+    if B % 256 == 0 and B >= 4096:
+        return dy.view(256, B // 256, -1).sum(1).sum(0)
+    return dy.sum(0)
+
+
 class _LinearLeakyReLU(torch.autograd.Function):
-    """y = leaky_relu(x @ W^T + b).  The two GEMM-shaped pieces stay cuBLAS calls (addmm / mm / bmm); what torch
-    autograd would add around them in the backward — leaky_relu_backward and the strided `sum(0)` bias reduction,
-    ~95 us per layer at B=65536 — is one hand-written pass (csrc/mlp_epilogue.cu), and the weight gradient
-    (M=N=H, K=B: a shape cuBLAS's fp32 heuristics serve with 4 CTAs) is issued as a batched split-K product."""
+    """y = leaky_relu(x @ W^T + b).  The GEMM-shaped pieces stay cuBLAS calls (mm / bmm); everything torch would run
+    around them is hand-written (csrc/mlp_epilogue.cu): forward bias + activation in one in-place pass (torch's
+    addmm adds a separate 36 us bias kernel + a 10 us activation kernel at [65536,128]) and, in the backward,
+    leaky_relu' fused with the bias-gradient column reduction (torch: 14 us + 82 us)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, slope, workspace):
-        y = torch.addmm(bias, x, weight.t())
-        torch.nn.functional.leaky_relu_(y, slope)
+        from . import ops
+        y = x @ weight.t()
+        ops.bias_act_fwd(y, bias, slope)
         ctx.save_for_backward(x, weight, y)
         ctx.slope, ctx.workspace = slope, workspace
         return y
@@ -44,37 +70,56 @@ class _LinearLeakyReLU(torch.autograd.Function):
         db = torch.empty(dy.shape[1], dtype=dy.dtype, device=dy.device)
         ops.act_bias_bwd(dy, y, ctx.slope, dz, db, ctx.workspace)
         dx = dz @ weight if ctx.needs_input_grad[0] else None
-        B, H = dz.shape
-        S = 1
-        while S < 64 and B % (2 * S) == 0 and B // (2 * S) >= 512:
-            S *= 2
-        if S > 1 and x.is_contiguous():
-            dw = torch.bmm(dz.view(S, B // S, H).transpose(1, 2), x.view(S, B // S, x.shape[1])).sum(0)
-        else:
-            dw = dz.t() @ x
-        return dx, dw, db, None, None
+        return dx, _wgrad(dz, x), db, None, None
+
+
+class _LinearHead(torch.autograd.Function):
+    """Final Linear of a head (no activation): same math as F.linear, cheaper narrow-output gradients."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return torch.addmm(bias, x, weight.t())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dy @ weight if ctx.needs_input_grad[0] else None
+        return dx, _wgrad(dy, x), _colsum(dy)
 
 
 class _DenseStack(nn.Sequential):
-    """nn.Sequential of [Linear, LeakyReLU, ...] (same parameter names as the reference's Sequential) whose forward
-    routes Linear+LeakyReLU pairs through the fused-epilogue autograd function when gradients are being recorded on
-    a CUDA device; everywhere else it is the plain module chain."""
+    """nn.Sequential of [Linear, LeakyReLU, ...] (same parameter names as the reference's Sequential).  On a CUDA
+    device Linear+LeakyReLU pairs run as cuBLAS mm + the hand-written epilogue kernels (with a custom autograd
+    function when gradients are recorded); everywhere else it is the plain module chain."""
+
+    def _workspace(self, device):
+        ws = getattr(self, "_xb_ws", None)
+        if ws is None or ws.device != device:
+            ws = torch.zeros(4 + 592 * 1024, dtype=torch.float32, device=device)
+            object.__setattr__(self, "_xb_ws", ws)
+        return ws
 
     def forward(self, x):
         mods = list(self)
-        fused = x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled()
+        on_gpu = x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
         k = 0
         while k < len(mods):
             m = mods[k]
             nxt = mods[k + 1] if k + 1 < len(mods) else None
-            if (fused and isinstance(m, nn.Linear) and isinstance(nxt, nn.LeakyReLU) and m.weight.requires_grad
-                    and m.out_features % 4 == 0 and m.out_features <= 1024 and x.dim() == 2):
-                ws = getattr(self, "_xb_ws", None)
-                if ws is None or ws.device != x.device:
-                    ws = torch.zeros(4 + 592 * 1024, dtype=torch.float32, device=x.device)
-                    object.__setattr__(self, "_xb_ws", ws)
-                x = _LinearLeakyReLU.apply(x, m.weight, m.bias, float(nxt.negative_slope), ws)
+            if (on_gpu and isinstance(m, nn.Linear) and isinstance(nxt, nn.LeakyReLU) and m.out_features % 4 == 0
+                    and m.out_features <= 1024):
+                if torch.is_grad_enabled() and (m.weight.requires_grad or x.requires_grad):
+                    x = _LinearLeakyReLU.apply(x, m.weight, m.bias, float(nxt.negative_slope), self._workspace(x.device))
+                else:
+                    from . import ops
+                    x = x @ m.weight.t()
+                    ops.bias_act_fwd(x, m.bias, float(nxt.negative_slope))
                 k += 2
+            elif on_gpu and isinstance(m, nn.Linear) and torch.is_grad_enabled() and m.weight.requires_grad:
+                x = _LinearHead.apply(x, m.weight, m.bias)
+                k += 1
             else:
                 x = m(x)
                 k += 1
