@@ -258,7 +258,7 @@ def run_ours(args):
     launches = count_launches(agent)
     launches_per_step = {"updates": agent.n_epoch * (agent.buffer_size // agent.batch_size)}
     kernels = kernel_rooflines(agent, flush, peak, launches_per_step, with_c4=not args.no_c4, world=world) if rank == 0 or world > 1 else {}
-    params = agent.learner._flat.n
+    params = agent.learner._flat.n_params
     del agent
     torch.cuda.empty_cache()
 

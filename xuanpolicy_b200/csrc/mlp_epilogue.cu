@@ -130,6 +130,7 @@ using namespace xb;
 extern "C" int xb_bias_act_fwd(float* y, const float* bias, float slope, int64_t B, int H, xb_stream_t stream) {
     if (B <= 0 || !y || !bias) return XB_E_BADARG;
     if (H % 4 != 0 || H < 4) return XB_E_UNSUPPORTED;
+    if ((((uintptr_t)y) | ((uintptr_t)bias)) & 15u) return XB_E_BADARG;  // float4 accesses
     const int64_t n4 = B * (H / 4);
     bias_act_fwd_kernel<<<grid_for((n4 + kEpiUnroll - 1) / kEpiUnroll, kEpiBlock, 8), kEpiBlock, 0, (cudaStream_t)stream>>>(
         (float4*)y, (const float4*)bias, slope, n4, H / 4);
@@ -142,6 +143,8 @@ extern "C" int xb_act_bias_bwd(const float* dy, const float* y, float slope, flo
                                int64_t B, int H, xb_stream_t stream) {
     if (B <= 0 || !dy || !y || !dz || !dbias || !workspace) return XB_E_BADARG;
     if (H % 4 != 0 || H < 4 || H / 4 > kEpiBlock) return XB_E_UNSUPPORTED;
+    if ((((uintptr_t)dy) | ((uintptr_t)y) | ((uintptr_t)dz) | ((uintptr_t)dbias) | ((uintptr_t)workspace)) & 15u)
+        return XB_E_BADARG;  // float4 accesses
     const int H4 = H / 4;
     const int rows_per_pass = kEpiBlock / H4;
     int grid = kNumSMs * 4;

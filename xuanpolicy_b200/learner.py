@@ -39,9 +39,11 @@ class FlatAdamState:
     def __init__(self, policy, optimizer, scheduler):
         params = [p for p in policy.parameters() if p.requires_grad]
         dev = params[0].device
-        n = sum(p.numel() for p in params)
+        pad4 = lambda k: (k + 3) // 4 * 4          # every tensor starts 16-byte aligned (float4 epilogue kernels)
+        n = sum(pad4(p.numel()) for p in params)
         self.n = n
-        self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
+        self.n_params = sum(p.numel() for p in params)
+        self.flat_param = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
         for p in params:
@@ -49,7 +51,7 @@ class FlatAdamState:
             self.flat_param[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat_param[off:off + k].view_as(p.data)
             p.grad = self.flat_grad[off:off + k].view_as(p.data)
-            off += k
+            off += pad4(k)
         self.params = params
         group = optimizer.param_groups[0]
         if group.get("weight_decay", 0) != 0 or group.get("amsgrad", False) or group.get("maximize", False):
