@@ -221,6 +221,7 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
     add("clip_adam", lambda: lr.stage_optimizer(), lr._flat.n * (4 + 16 + 12), launches_per_step["updates"])
     agent._restore(snap)
     if with_c4:
+        out.update(large_shape_rooflines(flush, peak))
         # BASELINE.json configs[3]: GAE micro-benchmark, T=2048 x N=2^20 fp32 (sharded over ranks), both variants
         Tc, Nc = 2048, (1 << 20) // world
         gen = torch.Generator(device="cuda").manual_seed(1234 + (torch.distributed.get_rank() if world > 1 else 0))
@@ -237,6 +238,48 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
     return out
 
 
+def large_shape_rooflines(flush, peak):
+    """The env-step / store / gather / loss kernels at the C3 shape (CartPole, 65 536 envs x 256 steps, global
+    minibatch 2 097 152): here the working set (738 MB) exceeds L2, so the HBM roofline is meaningful."""
+    import xuanpolicy_b200 as xb
+    from xuanpolicy_b200 import ops
+    N, T, B = 65536, 256, 2097152
+    out = {}
+
+    def add(name, fn, nbytes):
+        mean_ms, min_ms = time_kernel(fn, flush, iters=10)
+        gbs = nbytes / (mean_ms * 1e-3) / 1e9
+        out[name] = {"ms": round(mean_ms, 5), "min_ms": round(min_ms, 5), "launches_per_step": 0, "bytes_per_launch": int(nbytes),
+                     "achieved_gbs": round(gbs, 2), "frac": round(gbs / peak, 5)}
+
+    env = xb.DummyVecEnv_Gym(xb.make_env_fns("CartPole-v1", 1, N), device="cuda", native=True)
+    env.reset()
+    act = torch.randint(0, 2, (N,), device="cuda")
+    add("env_step_c3_65536", lambda: env.step_device(act), 118 * N)
+    obs_space, act_space = xb.make_spaces("CartPole-v1")
+    mem = xb.DummyOnPolicyBuffer(obs_space, act_space, {"old_logp": ()}, N, T, device="cuda", native=True)
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    for t in (mem._obs, mem._rew, mem._val, mem._logp, mem._adv, mem._ret):
+        t.copy_(torch.randn(t.shape, device="cuda", generator=gen))
+    mem._act.copy_(torch.randint(0, 2, mem._act.shape, device="cuda", generator=gen).float())
+    val = torch.randn(N, device="cuda")
+    add("store_c3_65536", lambda: mem.store_device(env._obs, act, env._rew, val, env._term, env._trunc, val, 3), 2 * 36 * N)
+    idx = torch.randperm(N * T, device="cuda")[:B].contiguous()
+    obs_out = torch.empty((B, 4), device="cuda")
+    stats = torch.zeros(2, dtype=torch.float64, device="cuda")
+    add("gather_obs_c3_2M", lambda: ops.gather_obs(idx, T, N, mem._obs, 4, obs_out, b_adv=mem._adv, stats=stats), B * (8 + 16 + 16 + 4))
+    logits = torch.randn((B, 2), device="cuda")
+    vp = torch.randn(B, device="cuda")
+    dl, dv = torch.empty_like(logits), torch.empty_like(vp)
+    scal = torch.zeros(8, dtype=torch.float64, device="cuda")
+    add("ppo_loss_c3_2M", lambda: ops.ppo_loss_categorical(logits, vp, mem._act, mem._ret, mem._adv, mem._logp, dl, dv, scal,
+                                                           0.2, 0.25, 0.01, 1.0 / B, idx=idx, T=T, N=N, adv_stats=stats,
+                                                           adv_count=B), B * 48)
+    del mem, env, obs_out, logits, idx
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -246,6 +289,9 @@ def run_ours(args):
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
     wl = WORKLOADS[args.workload]
+    # strict fp32 GEMMs by default (the parity tolerances are stated for fp32); --tf32 lets cuBLAS use the TF32 tensor
+    # cores for the large-minibatch MLP GEMMs (north_star: "tensor cores only at the large-batch configs")
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
     peak, peak_src = measured_peaks()
     flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")   # 256 MiB > 126 MB L2
     sampler = ClockSampler(local) if rank == 0 else None
@@ -283,7 +329,8 @@ def run_ours(args):
         "metric": "PPO env-steps/s", "value": round(value, 1), "unit": "env-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(secs / args.steps * 1e3, 4),
         "higher_is_better": True, "scaling": "strong" if wl.get("strong") else "weak", "vs_baseline": None,
-        "dtype": "f32 (policy MLP, loss, GAE carry f64); f64 (env physics)", "data": "synthetic",
+        "dtype": ("tf32 MLP GEMMs" if args.tf32 else "f32 MLP GEMMs") + ", f32 loss/optimizer, f64 GAE carry and env physics",
+        "data": "synthetic",
         "config": {"workload": wl["name"], "envs_per_gpu": n_local, "horizon": horizon, "n_epoch": 8,
                    "minibatch_per_gpu": mb, "mlp_hidden": wl["hidden"], "params": params, "gamma": wl["gamma"],
                    "gae_lambda": 0.95, "use_obsnorm": False, "use_rewnorm": False, "parallelism": "env-sharded dp%d" % world,
@@ -390,6 +437,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-c4", action="store_true", help="skip the 40 GiB GAE micro-benchmark arrays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tf32", action="store_true", help="allow TF32 tensor-core GEMMs in the torch MLP (not the headline)")
     ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of CPU work for the CPU arms (0 = default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

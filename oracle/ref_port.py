@@ -209,15 +209,19 @@ class PPOAgentPort:
 
     def __init__(self, envs, policy, optimizer, scheduler, n_steps, n_epoch, n_minibatch, gamma, gae_lam,
                  vf_coef=0.25, ent_coef=0.01, clip_range=0.2, clip_grad_norm=0.5, use_grad_clip=True,
-                 use_gae=True, use_advnorm=True, use_obsnorm=False, use_rewnorm=False, obsnorm_range=5, rewnorm_range=5):
+                 use_gae=True, use_advnorm=True, use_obsnorm=False, use_rewnorm=False, obsnorm_range=5, rewnorm_range=5,
+                 memory=None, update_fn=None):
         self.envs, self.policy, self.optimizer, self.scheduler = envs, policy, optimizer, scheduler
         self.n_envs, self.n_steps, self.n_epoch = envs.num_envs, n_steps, n_epoch
         self.buffer_size = self.n_envs * n_steps
         self.batch_size = self.buffer_size // n_minibatch
         self.gamma = gamma
         act_shape = () if not hasattr(envs.action_space, "low") else envs.action_space.shape
-        self.memory = OnPolicyBufferPort(envs.observation_space.shape, act_shape, self.n_envs, n_steps,
-                                         use_gae, use_advnorm, gamma, gae_lam)
+        # `memory` / `update_fn` let a test drive OTHER implementations of the buffer / learner (the product's
+        # drop-ins) through this restated agent loop, the way the unmodified PPOCLIP_Agent would drive them
+        self.memory = memory if memory is not None else OnPolicyBufferPort(
+            envs.observation_space.shape, act_shape, self.n_envs, n_steps, use_gae, use_advnorm, gamma, gae_lam)
+        self.update_fn = update_fn
         self.hp = dict(vf_coef=vf_coef, ent_coef=ent_coef, clip_range=clip_range, clip_grad_norm=clip_grad_norm,
                        use_grad_clip=use_grad_clip)
         self.use_obsnorm, self.use_rewnorm = use_obsnorm, use_rewnorm
@@ -261,8 +265,11 @@ class PPOAgentPort:
                     np.random.shuffle(indexes)
                     for start in range(0, self.buffer_size, self.batch_size):
                         batch = mem.sample(indexes[start:start + self.batch_size])
-                        self.last_info = ppo_clip_update(self.policy, self.optimizer, self.scheduler,
-                                                         batch[:5] + (batch[5]["old_logp"],), **self.hp)
+                        if self.update_fn is not None:
+                            self.last_info = self.update_fn(*batch[:5], batch[5]["old_logp"])
+                        else:
+                            self.last_info = ppo_clip_update(self.policy, self.optimizer, self.scheduler,
+                                                             batch[:5] + (batch[5]["old_logp"],), **self.hp)
                 mem.clear()
             self.returns = (1 - terminals) * self.gamma * self.returns + rewards
             obs = next_obs

@@ -94,3 +94,34 @@ def test_cartpole_learns(shuffle):
     assert first < 40 and late > 2.5 * first, (first, late)
     if shuffle == "host":
         assert agent.h2d_bytes == 31 * 4 * 256 * 64 * 8
+
+
+@pytest.mark.parametrize("env_id,obsnorm", [("CartPole-v1", True), ("Pendulum-v1", False)])
+def test_compat_dropins_under_the_reference_agent_loop(env_id, obsnorm):
+    """the compat (numpy in/out) drop-ins driven by the reference's own agent loop — here its
+    restatement oracle/ref_port.PPOAgentPort, which calls envs.step / memory.store / finish_path / sample /
+    learner.update exactly like ppoclip_agent.py:59-111 (per-env finish_path calls, host-side obs/reward
+    normalisation, list-of-dict infos)."""
+    import xuanpolicy_b200 as xb
+    from oracle import ref_port
+    torch.manual_seed(0)
+    np.random.seed(0)
+    envs = xb.DummyVecEnv_Gym(xb.make_env_fns(env_id, 1, 12), device="cuda")
+    envs.reset()
+    policy = xb.make_policy(envs.observation_space, envs.action_space, hidden=(32,), device="cuda")
+    opt = torch.optim.Adam(policy.parameters(), 4e-4, eps=1e-5)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=10000)
+    memory = xb.DummyOnPolicyBuffer(envs.observation_space, envs.action_space, {"old_logp": ()}, 12, 24, True, True, 0.98, 0.95)
+    learner = xb.PPOCLIP_Learner(policy, opt, sched, "cuda", "/tmp", vf_coef=0.25, ent_coef=0.01, clip_range=0.2,
+                                 clip_grad_norm=0.5, use_grad_clip=True)
+    agent = ref_port.PPOAgentPort(envs, policy, opt, sched, 24, 2, 4, 0.98, 0.95, use_obsnorm=obsnorm, use_rewnorm=obsnorm,
+                                  memory=memory, update_fn=learner.update)
+    p0 = torch.cat([p.detach().reshape(-1).clone() for p in policy.parameters()])
+    agent.train(24 * 3 + 5)
+    p1 = torch.cat([p.detach().reshape(-1) for p in policy.parameters()])
+    assert learner.iterations == 3 * 2 * 4 and agent.current_step == 12 * 77
+    assert torch.isfinite(p1).all() and not torch.equal(p0, p1)
+    assert set(agent.last_info) == {"actor-loss", "critic-loss", "entropy", "learning_rate", "predict_value", "clip_ratio"}
+    assert memory.size == 5 and memory.ptr == 5 and not memory.full
+    if env_id == "CartPole-v1":
+        assert agent.episodes > 0
