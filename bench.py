@@ -143,8 +143,8 @@ def time_agent(agent, steps, warmup, flush, world):
 def count_launches(agent):
     """Hand-written kernel launches inside one PPO iteration (counted from the calls the agent makes)."""
     T, E, M = agent.n_steps, agent.n_epoch, agent.buffer_size // agent.batch_size
-    per_rollout = T * 3 + 1 + 1            # sample + env_step + store per step, GAE, counter
-    per_update = 1 + 1 + 2                 # gather_obs, loss, grad-norm + adam
+    per_rollout = T * (3 + 3) + 3 + 2 + 1  # sample + env_step + store + 3 fwd MLP epilogues per step, bootstrap fwd, GAE + pack, counter
+    per_update = 1 + 1 + 2 + 6             # gather_obs, loss, grad-norm + adam, 3 fwd + 3 bwd MLP epilogues
     return per_rollout + E * M * per_update
 
 
@@ -193,30 +193,47 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
     vN = v[:N].contiguous()
     add("store", lambda: mem.store_device(x_cur[:N], agent._act, env._rew, vN, env._term, env._trunc, agent._logp, 0),
         N * 2 * 36, T)
-    add("gae", lambda: mem.finish_rollout(agent._boot_last), (20 + 1) * N * T, 1)
+    add("gae_and_pack", lambda: mem.finish_rollout(agent._boot_last), (20 + 1 + (64 if mem._rec is not None else 0)) * N * T, 1)
     idx = agent._perm[:B]
     agent._perm.copy_(torch.randperm(agent.buffer_size, device="cuda"))
-    add("gather_obs_advstats", lambda: lr.stage_gather(mem, idx), B * (8 + 16 + 4 * od + 4), launches_per_step["updates"])
+    add("gather_records" if mem.packed else "gather_obs_advstats", lambda: lr.stage_gather(mem, idx),
+        B * ((8 + 32 + 4 * od + 16) if mem.packed else (8 + 16 + 4 * od + 4)), launches_per_step["updates"])
     mb = lr.stage_gather(mem, idx)
     with torch.no_grad():
         _, a_dist, v_pred = agent.policy(mb["obs"])
     vp = v_pred.contiguous()
     dv = torch.empty_like(vp)
-    kw = dict(clip_range=lr.clip_range, vf_coef=lr.vf_coef, ent_coef=lr.ent_coef, inv_batch=1.0 / B, idx=idx, T=T, N=N,
-              adv_stats=mb["stats"], adv_count=B)
+    kw = dict(clip_range=lr.clip_range, vf_coef=lr.vf_coef, ent_coef=lr.ent_coef, inv_batch=1.0 / B, adv_stats=mb["stats"],
+              adv_count=B)
+    if mem.packed:
+        kw.update(packed=mb["scal"])
+        margs = (None, None, None, None)
+    else:
+        kw.update(idx=idx, T=T, N=N)
+        margs = (mem._act, mem._ret, mem._adv, mem._logp)
     if gauss:
         mu, std = a_dist.get_param()
         mu = mu.contiguous()
         logstd = std.log().contiguous()
         dmu = torch.empty_like(mu)
         dls = torch.empty(mu.shape[1], dtype=torch.float64, device="cuda")
-        add("ppo_loss_fwd_bwd", lambda: ops.ppo_loss_gaussian(mu, logstd, vp, mem._act, mem._ret, mem._adv, mem._logp, dmu,
-                                                              dls, dv, lr._scalars, **kw), B * 40, launches_per_step["updates"])
+        add("ppo_loss_fwd_bwd", lambda: ops.ppo_loss_gaussian(mu, logstd, vp, *margs, dmu, dls, dv, lr._scalars, **kw),
+            B * (32 if mem.packed else 40), launches_per_step["updates"])
     else:
         logits = a_dist.get_param().contiguous()
         dl = torch.empty_like(logits)
-        add("ppo_loss_fwd_bwd", lambda: ops.ppo_loss_categorical(logits, vp, mem._act, mem._ret, mem._adv, mem._logp, dl, dv,
-                                                                 lr._scalars, **kw), B * 48, launches_per_step["updates"])
+        add("ppo_loss_fwd_bwd", lambda: ops.ppo_loss_categorical(logits, vp, *margs, dl, dv, lr._scalars, **kw),
+            B * (40 if mem.packed else 48), launches_per_step["updates"])
+    # the non-GEMM half of the MLP (csrc/mlp_epilogue.cu): per update, one forward and one backward epilogue per
+    # Linear+LeakyReLU block (3 blocks: representation, actor hidden, critic hidden)
+    H = agent.config.representation_hidden_size[-1]
+    yb = torch.randn((B, H), device="cuda")
+    dyb = torch.randn((B, H), device="cuda")
+    dzb, dbb = torch.empty_like(dyb), torch.empty(H, device="cuda")
+    bias = torch.randn(H, device="cuda")
+    ws32 = torch.zeros(4 + 592 * 1024, dtype=torch.float32, device="cuda")
+    add("mlp_bias_act_fwd", lambda: ops.bias_act_fwd(yb, bias, 0.01), B * H * 8, 3 * launches_per_step["updates"])
+    add("mlp_act_bias_bwd", lambda: ops.act_bias_bwd(dyb, yb, 0.01, dzb, dbb, ws32), B * H * 12, 3 * launches_per_step["updates"])
     snap = agent._snapshot()
     add("clip_adam", lambda: lr.stage_optimizer(), lr._flat.n * (4 + 16 + 12), launches_per_step["updates"])
     agent._restore(snap)
@@ -271,11 +288,18 @@ def large_shape_rooflines(flush, peak):
     logits = torch.randn((B, 2), device="cuda")
     vp = torch.randn(B, device="cuda")
     dl, dv = torch.empty_like(logits), torch.empty_like(vp)
-    scal = torch.zeros(8, dtype=torch.float64, device="cuda")
-    add("ppo_loss_c3_2M", lambda: ops.ppo_loss_categorical(logits, vp, mem._act, mem._ret, mem._adv, mem._logp, dl, dv, scal,
+    scal64 = torch.zeros(8, dtype=torch.float64, device="cuda")
+    add("ppo_loss_c3_2M", lambda: ops.ppo_loss_categorical(logits, vp, mem._act, mem._ret, mem._adv, mem._logp, dl, dv, scal64,
                                                            0.2, 0.25, 0.01, 1.0 / B, idx=idx, T=T, N=N, adv_stats=stats,
                                                            adv_count=B), B * 48)
-    del mem, env, obs_out, logits, idx
+    rec = torch.zeros((N * T, 8), device="cuda")
+    add("pack_records_c3", lambda: ops.pack_records(mem._obs, mem._act, mem._logp, mem._adv, mem._ret, rec), N * T * 64)
+    scal = torch.empty((B, 4), device="cuda")
+    add("gather_records_c3_2M", lambda: ops.gather_records(idx, T, N, rec, 4, obs_out, scal, stats=stats), B * (8 + 32 + 16 + 16))
+    add("ppo_loss_packed_c3_2M", lambda: ops.ppo_loss_categorical(logits, vp, None, None, None, None, dl, dv, scal64, 0.2, 0.25,
+                                                                  0.01, 1.0 / B, adv_stats=stats, adv_count=B, packed=scal),
+        B * (16 + 8 + 4 + 8 + 4))
+    del mem, env, obs_out, logits, idx, rec, scal
     torch.cuda.empty_cache()
     return out
 

@@ -124,6 +124,14 @@ int xb_gather_batch(const int64_t* idx, int64_t B, int64_t T, int64_t N, const f
                     const float* b_logp, float* obs_out, float* act_out, float* ret_out, float* val_out,
                     float* adv_out, float* logp_out, double* stats, xb_stream_t stream);
 int xb_normalize_adv(float* adv, const double* stats, int64_t count, int64_t B, xb_stream_t stream);
+/* Packed transition records (act_dim == 1): once per rollout, after xb_gae, xb_pack_records builds one 32-byte,
+ * sector-aligned record {obs[4], act, old_logp, adv, ret} per transition (rec f32 [T*N][8]); xb_gather_records then
+ * reads ONE DRAM sector per sample instead of one per field and emits obs_out [B][obs_dim], scal_out f32 [B][4] =
+ * {act, old_logp, adv, ret} and the minibatch advantage statistics.  Same replaced code as xb_gather_batch. */
+int xb_pack_records(const float* b_obs, const float* b_act, const float* b_logp, const float* b_adv,
+                    const float* b_ret, float* rec, int64_t TN, xb_stream_t stream);
+int xb_gather_records(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* rec, int obs_dim,
+                      float* obs_out, float* scal_out, double* stats, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * (4b) PPO-Clip loss forward + backward, fused with the gather of the per-transition scalars.
@@ -136,7 +144,12 @@ int xb_normalize_adv(float* adv, const double* stats, int64_t count, int64_t B, 
  *             when given, advantages are normalised on the fly (x-mean)/(std+1e-8).
  *   value_clip <= 0 : plain MSE value loss (the reference).  > 0: max((v-R)^2, (v_old+clip(v-v_old,+-c)-R)^2)
  *             (opt-in, formula of xuance/torch/learners/multi_agent_rl/mappo_learner.py:78-87; needs val_old).
+ *   clip_range <= 0 selects the A2C / PG surrogate instead: a_loss = -(adv * log_prob).mean() (old_logp unused, may be
+ *             NULL) — A2C_Learner.update a2c_learner.py:24-35; PG_Learner.update pg_learner.py:19-27 (adv = returns, vf_coef = 0).
  *   inv_batch = 1 / (global minibatch size): the mean() of the reference.
+ *   stride: element stride (in floats) of the dense act/ret/adv/old_logp/val_old arrays when idx == NULL — 1 for
+ *             plain [B] arrays, 4 for the packed float4 {act, old_logp, adv, ret} rows xb_gather_records emits
+ *             (pass base+0, base+3, base+2, base+1); must be 1 with idx, and with act_dim > 1.
  * Outputs: gradients of  L = a_loss - ent_coef*entropy + vf_coef*c_loss  w.r.t. the network outputs, and
  *   scalars fp64 [8] = sums over THIS call's samples of {min-surrogate, value loss term, entropy, v_pred,
  *   clipped-ratio count, 0, 0, 0} (zeroed by the call).
@@ -146,12 +159,12 @@ int xb_ppo_loss_categorical(const int64_t* idx, int64_t B, int64_t T, int64_t N,
                             const float* v_pred, const float* act, const float* ret, const float* adv,
                             const float* old_logp, const float* val_old, const double* adv_stats, int64_t adv_count,
                             float clip_range, float vf_coef, float ent_coef, float value_clip, float inv_batch,
-                            float* dlogits, float* dv, double* scalars, xb_stream_t stream);
+                            int64_t stride, float* dlogits, float* dv, double* scalars, xb_stream_t stream);
 int xb_ppo_loss_gaussian(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* mu, const float* logstd,
                          int A, const float* v_pred, const float* act, const float* ret, const float* adv,
                          const float* old_logp, const float* val_old, const double* adv_stats, int64_t adv_count,
                          float clip_range, float vf_coef, float ent_coef, float value_clip, float inv_batch,
-                         float* dmu, double* dlogstd_acc, float* dv, double* scalars, xb_stream_t stream);
+                         int64_t stride, float* dmu, double* dlogstd_acc, float* dv, double* scalars, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Action sampling fused with log-prob (after the actor GEMM).  Replaces dists.stochastic_sample()+log_prob in

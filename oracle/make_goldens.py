@@ -131,6 +131,52 @@ def gen_loss(name, seed, discrete, hidden, B, hp):
     print("wrote", name)
 
 
+def gen_loss_a2c_pg(name, seed, algo, discrete, hidden, B):
+    """Reference A2C_Learner.update (a2c_learner.py:19-50) / PG_Learner.update (pg_learner.py:17-45): grads + step."""
+    from xuance.torch.learners import A2C_Learner, PG_Learner
+    from xuance.torch.representations import Basic_MLP
+    from xuance.torch.policies import Categorical_Actor_Policy
+    rng = np.random.default_rng(seed)
+    obs_dim = 4 if discrete else 3
+    obs = rng.standard_normal((B, obs_dim)).astype(np.float32)
+    if algo == "a2c":
+        policy = _ref_policy(discrete, hidden, seed)
+    else:
+        torch.manual_seed(seed)
+        rep = Basic_MLP((4,), [hidden], None, torch.nn.init.orthogonal_, torch.nn.LeakyReLU, "cpu")
+        policy = Categorical_Actor_Policy(_spaces().Discrete(2), rep, [hidden], None, torch.nn.init.orthogonal_,
+                                          torch.nn.LeakyReLU, "cpu")
+    with torch.no_grad():
+        for p in policy.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    sd0 = {k: v.detach().clone().numpy() for k, v in policy.state_dict().items()}
+    with torch.no_grad():
+        a_dist = policy(obs)[1]
+        act = a_dist.stochastic_sample().numpy().astype(np.float32)
+    adv = rng.standard_normal(B).astype(np.float32)
+    ret = rng.standard_normal(B).astype(np.float32)
+    out = dict(obs=obs, act=act, ret=ret, adv=adv,
+               meta=np.array(json.dumps(dict(algo=algo, discrete=discrete, hidden=hidden, B=B, vf_coef=0.25, ent_coef=0.01,
+                                             clip_grad=0.5))))
+    for k, v in sd0.items():
+        out["p0/" + k] = v
+    opt = torch.optim.Adam(policy.parameters(), 4e-4, eps=1e-5)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=1000)
+    if algo == "a2c":
+        learner = A2C_Learner(policy, opt, sched, "cpu", "/tmp/xb200_goldens_models", vf_coef=0.25, ent_coef=0.01, clip_grad=0.5)
+        info = learner.update(obs, act, ret, adv)
+    else:
+        learner = PG_Learner(policy, opt, sched, "cpu", "/tmp/xb200_goldens_models", ent_coef=0.01, clip_grad=0.5)
+        info = learner.update(obs, act, ret)
+    for k, v in info.items():
+        out["info/" + k] = np.asarray(float(v))
+    for k, p in policy.named_parameters():
+        out["grad_clipped/" + k] = p.grad.detach().numpy().copy()      # these learners always clip (a2c_learner.py:36)
+        out["p1/" + k] = p.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name)
+
+
 def gen_vecenv(name, env_id, n, steps, seed=1):
     """Reference DummyVecEnv_Gym protocol over the restated physics (libm flavour, as gym would run on a host)."""
     from xuance.environment import DummyVecEnv_Gym, Gym_Env
@@ -194,6 +240,8 @@ def main():
     gen_buffer("buffer_cat_nogae", 103, 4, 32, True, False, True, 0.99, 0.95)
     gen_loss("loss_cat_h64", 201, True, 64, 512, hp)
     gen_loss("loss_gauss_h128", 202, False, 128, 1024, hp)
+    gen_loss_a2c_pg("loss_a2c_gauss_h64", 203, "a2c", False, 64, 640)
+    gen_loss_a2c_pg("loss_pg_cat_h32", 204, "pg", True, 32, 384)
     gen_vecenv("vecenv_cartpole", "CartPole-v1", 6, 700)
     gen_vecenv("vecenv_pendulum", "Pendulum-v1", 4, 450)
     gen_physics("physics_cartpole_cr", "CartPole-v1", 12, 1100)
@@ -201,4 +249,10 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "a2c_pg":      # regenerate only the newer fixtures
+        os.makedirs(OUT, exist_ok=True)
+        ref_loader.load(trig="libm")
+        gen_loss_a2c_pg("loss_a2c_gauss_h64", 203, "a2c", False, 64, 640)
+        gen_loss_a2c_pg("loss_pg_cat_h32", 204, "pg", True, 32, 384)
+    else:
+        main()

@@ -97,12 +97,16 @@ def test_loss_kernel_vs_torch_autograd(discrete, B, A, value_clip):
         full = torch.zeros((T * N, width), device="cuda")
         full[row] = x.reshape(B, width)
         return full.reshape(-1) if width == 1 else full
-    for idx in (None, perm):
+    modes = [None, perm] + (["packed"] if (value_clip == 0 and (discrete or A == 1)) else [])
+    for idx in modes:
         kw = dict(clip_range=clip, vf_coef=vf, ent_coef=ent, inv_batch=1.0 / B, adv_stats=stats, adv_count=B,
                   value_clip=value_clip)
         if idx is None:
             f = lambda x, w=1: x.contiguous()
             kw.update(val_old=val_old)
+        elif isinstance(idx, str):      # compact float4 {act, old_logp, adv, ret} rows, as xb_gather_records emits them
+            f = lambda x, w=1: None
+            kw.update(packed=torch.stack([act.reshape(B), old_logp, adv_raw, ret], dim=1).contiguous())
         else:
             f = scat
             kw.update(idx=idx, T=T, N=N, val_old=scat(val_old))
@@ -182,3 +186,64 @@ def test_fused_clip_adam_matches_torch():
         ok, err = rel_close(p.cpu().numpy(), p_ref.detach().cpu().numpy(), 1e-6)
         assert ok, (it, err)
     assert int(step.item()) == 12
+
+
+@pytest.mark.parametrize("name", ["loss_a2c_gauss_h64", "loss_pg_cat_h32"])
+def test_a2c_and_pg_learners_match_reference_golden(name):
+    """Row f3: A2C_Learner / PG_Learner drop-ins (same fused kernel, A2C surrogate) vs the reference's own updates."""
+    import xuanpolicy_b200 as xb
+    from xuanpolicy_b200 import policies, spaces
+    g = load_golden(name)
+    m = g["meta"]
+    if m["algo"] == "a2c":
+        pol = _policy(g, "cuda")
+    else:
+        rep = policies.MLPRepresentation((4,), [m["hidden"]], device="cuda")
+        pol = policies.CategoricalActor(spaces.Discrete(2), rep, [m["hidden"]], device="cuda")
+        pol.load_state_dict({k[3:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("p0/")})
+    opt = torch.optim.Adam(pol.parameters(), 4e-4, eps=1e-5)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=1000)
+    if m["algo"] == "a2c":
+        learner = xb.A2C_Learner(pol, opt, sched, "cuda", "/tmp", vf_coef=m["vf_coef"], ent_coef=m["ent_coef"], clip_grad=m["clip_grad"])
+        info = learner.update(g["obs"], g["act"], g["ret"], g["adv"])
+    else:
+        learner = xb.PG_Learner(pol, opt, sched, "cuda", "/tmp", ent_coef=m["ent_coef"], clip_grad=m["clip_grad"])
+        info = learner.update(g["obs"], g["act"], g["ret"])
+    keys = [k[5:] for k in g if k.startswith("info/")]
+    assert sorted(info) == sorted(keys)
+    for k in keys:
+        ref = float(g["info/" + k])
+        assert abs(float(info[k]) - ref) <= 1e-4 * max(1.0, abs(ref)), (k, float(info[k]), ref)
+    for k, p in pol.named_parameters():
+        ok, err = rel_close(p.grad.cpu().numpy(), g["grad_clipped/" + k], 1e-4)
+        assert ok, (k, err)
+        ok, err = rel_close(p.detach().cpu().numpy(), g["p1/" + k], 1e-5)
+        assert ok, (k, err)
+
+
+def test_packed_records_gather_bit_exact():
+    """pack_records + gather_records: one 32-byte record per transition; gathered rows equal the SoA gather bit for bit."""
+    from xuanpolicy_b200 import ops
+    T, N, B = 48, 301, 5000
+    rng = np.random.default_rng(8)
+    obs = rng.standard_normal((T, N, 4)).astype(np.float32)
+    act, logp, adv, ret = (rng.standard_normal((T, N)).astype(np.float32) for _ in range(4))
+    d = lambda a: torch.from_numpy(a).cuda()
+    rec = torch.zeros((T * N, 8), device="cuda")
+    ops.pack_records(d(obs), d(act), d(logp), d(adv), d(ret), rec)
+    r = rec.cpu().numpy().reshape(T, N, 8)
+    assert np.array_equal(r[..., :4], obs) and np.array_equal(r[..., 4], act) and np.array_equal(r[..., 5], logp)
+    assert np.array_equal(r[..., 6], adv) and np.array_equal(r[..., 7], ret)
+    idx = rng.permutation(T * N)[:B].astype(np.int64)
+    env, step = np.divmod(idx, T)
+    for obs_dim in (3, 4):
+        obs_out, scal = torch.empty((B, obs_dim), device="cuda"), torch.empty((B, 4), device="cuda")
+        stats = torch.zeros(2, dtype=torch.float64, device="cuda")
+        ops.gather_records(d(idx), T, N, rec, obs_dim, obs_out, scal, stats=stats)
+        assert np.array_equal(obs_out.cpu().numpy(), obs[step, env, :obs_dim])
+        sc = scal.cpu().numpy()
+        assert np.array_equal(sc[:, 0], act[step, env]) and np.array_equal(sc[:, 1], logp[step, env])
+        assert np.array_equal(sc[:, 2], adv[step, env]) and np.array_equal(sc[:, 3], ret[step, env])
+        a = adv[step, env].astype(np.float64)
+        s = stats.cpu().numpy()
+        assert abs(s[0] - a.sum()) < 1e-9 * B and abs(s[1] - (a * a).sum()) < 1e-9 * B

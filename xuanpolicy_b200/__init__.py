@@ -14,8 +14,9 @@ from .spaces import Box, Discrete  # noqa: F401
 from .vec_env import (AlreadySteppingError, DummyVecEnv_Gym, EnvFn, NotSteppingError, make_env_fns,  # noqa: F401
                       make_spaces)
 from .buffer import DummyOnPolicyBuffer  # noqa: F401
-from .learner import PPOCLIP_Learner  # noqa: F401
-from .policies import (CategoricalActorCritic, GaussianActorCritic, MLPRepresentation, make_policy)  # noqa: F401
+from .learner import A2C_Learner, PG_Learner, PPOCLIP_Learner  # noqa: F401
+from .policies import (CategoricalActor, CategoricalActorCritic, GaussianActorCritic, MLPRepresentation,  # noqa: F401
+                       make_policy)
 
 __version__ = "0.1.0"
 

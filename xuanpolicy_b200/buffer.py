@@ -33,8 +33,9 @@ class DummyOnPolicyBuffer:
         obs_shape = tuple(observation_space.shape)
         if len(obs_shape) != 1 or not 1 <= obs_shape[0] <= 4:
             raise NotImplementedError("device buffer supports flat observations of 1..4 floats (classic control)")
-        if auxiliary_shape is not None and set(auxiliary_shape.keys()) != {"old_logp"}:
-            raise NotImplementedError("only the PPO auxiliary {'old_logp': ()} is supported")
+        if auxiliary_shape and set(auxiliary_shape.keys()) != {"old_logp"}:
+            raise NotImplementedError("only the PPO auxiliary {'old_logp': ()} (or none: A2C / PG) is supported")
+        self._has_logp = bool(auxiliary_shape)
         self.obs_dim = obs_shape[0]
         self.discrete = is_discrete(action_space)
         self.act_dim = 1 if self.discrete else int(np.prod(action_space.shape))
@@ -49,6 +50,10 @@ class DummyOnPolicyBuffer:
         self._trunc = torch.zeros((T, N), dtype=torch.uint8, device=dev)
         self._boot = torch.zeros((T, N), **f32)
         self._boot_last = torch.zeros(N, **f32)
+        # packed 32-byte records {obs[4], act, old_logp, adv, ret}: one DRAM sector per transition for the minibatch
+        # gather (csrc/buffer.cu); built by finish_rollout, only for 1-dim actions
+        self._rec = torch.zeros((T * N, 8), **f32) if (native and self.act_dim == 1) else None
+        self._rec_valid = False
         self._stats = torch.zeros(2, dtype=torch.float64, device=dev)        # whole-rollout (sum, sumsq) of adv
         self._mb_stats = torch.zeros(2, dtype=torch.float64, device=dev)     # per-minibatch (sum, sumsq)
         self._zero_u8 = torch.zeros(N, dtype=torch.uint8, device=dev)
@@ -80,6 +85,11 @@ class DummyOnPolicyBuffer:
         self.ptr, self.size = 0, 0
         self._gae_valid = False
 
+    @property
+    def packed(self):
+        """True when the packed-record gather path is available for the current rollout."""
+        return self._rec is not None and self._rec_valid
+
     # ---------------------------------------------------------------------------------------------- store
     def _dev(self, x, dtype):
         if torch.is_tensor(x):
@@ -101,7 +111,7 @@ class DummyOnPolicyBuffer:
                 act_t = act_t.to(torch.int64).reshape(N).contiguous()
             else:
                 act_t = act_t.to(torch.float32).reshape(N, self.act_dim).contiguous()
-            logp = aux_info["old_logp"] if aux_info is not None else torch.zeros(N)
+            logp = aux_info["old_logp"] if (aux_info and "old_logp" in aux_info) else torch.zeros(N)
             trunc = self._zero_u8 if truncations is None else self._dev(truncations, torch.uint8).reshape(N)
             self.store_device(obs_t, act_t, self._dev(rews, torch.float32).reshape(N),
                               self._dev(value, torch.float32).reshape(N), self._dev(terminals, torch.uint8).reshape(N),
@@ -134,6 +144,9 @@ class DummyOnPolicyBuffer:
         ops.gae(self._rew, self._val, self._term, boot_last, self._adv, self._ret, self.gamma, self.gae_lam,
                 trunc=self._trunc, boot=self._boot, stats=self._stats, use_gae=self.use_gae,
                 variant=variant or self.gae_variant)
+        if self._rec is not None:
+            ops.pack_records(self._obs, self._act, self._logp, self._adv, self._ret, self._rec)
+            self._rec_valid = True
         self._gae_valid = True
 
     def _run_gae(self):
@@ -174,9 +187,9 @@ class DummyOnPolicyBuffer:
                 ops.normalize_adv(adv, self._mb_stats, B)
             act = act.reshape((B,) + self._act_shape)
         if self.native:
-            return obs, act, ret, val, adv, {"old_logp": logp}
+            return obs, act, ret, val, adv, ({"old_logp": logp} if self._has_logp else {})
         return (obs.cpu().numpy(), act.cpu().numpy(), ret.cpu().numpy(), val.cpu().numpy(), adv.cpu().numpy(),
-                {"old_logp": logp.cpu().numpy()})
+                ({"old_logp": logp.cpu().numpy()} if self._has_logp else {}))
 
     # ---------------------------------------------------------------------------------------------- views
     def _env_major(self, t, trailing=None):
@@ -220,4 +233,4 @@ class DummyOnPolicyBuffer:
 
     @property
     def auxiliary_infos(self):
-        return {"old_logp": self._env_major(self._logp)}
+        return {"old_logp": self._env_major(self._logp)} if self._has_logp else {}

@@ -145,6 +145,54 @@ __global__ void __launch_bounds__(kGatherBlock)
     if (stats) finish_stats(s, ss, g_partials, &g_ticket, stats, smem);
 }
 
+// ---- packed 32-byte transition records -------------------------------------------------------------------
+// A random minibatch gather over SoA arrays touches one 32 B DRAM sector per FIELD per sample (obs row, act, logp,
+// adv, ret: 5 sectors = 160 B for 32 useful bytes).  Once per rollout, after the GAE scan, the fields a PPO update
+// needs are packed into one sector-sized, sector-aligned record per transition: {obs[4], act, old_logp, adv, ret}.
+// The minibatch gather then reads exactly one sector per sample (100 % sector efficiency) and emits the MLP input
+// and a compact float4 {act, old_logp, adv, ret} per sample, which the loss kernel streams fully coalesced.
+struct __align__(32) Record {
+    float4 obs;
+    float4 s;  // act, old_logp, adv, ret
+};
+
+__global__ void __launch_bounds__(256)
+    pack_records_kernel(const float4* __restrict__ b_obs, const float* __restrict__ b_act,
+                        const float* __restrict__ b_logp, const float* __restrict__ b_adv,
+                        const float* __restrict__ b_ret, Record* __restrict__ rec, int64_t TN) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < TN; i += (int64_t)gridDim.x * blockDim.x) {
+        Record r;
+        r.obs = b_obs[i];
+        r.s = make_float4(b_act[i], b_logp[i], b_adv[i], b_ret[i]);
+        rec[i] = r;
+    }
+}
+
+template <int OBS_DIM>
+__global__ void __launch_bounds__(kGatherBlock)
+    gather_records_kernel(const int64_t* __restrict__ idx, int64_t B, int64_t T, int64_t N,
+                          const Record* __restrict__ rec, float* __restrict__ obs_out, float4* __restrict__ scal_out,
+                          double* __restrict__ stats) {
+    __shared__ double smem[64];
+    double s = 0.0, ss = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+        const Record r = rec[flat_to_row(idx[i], T, N)];
+        if (OBS_DIM == 4) {
+            reinterpret_cast<float4*>(obs_out)[i] = r.obs;
+        } else {
+            float* dst = obs_out + i * OBS_DIM;
+            dst[0] = r.obs.x;
+            if (OBS_DIM > 1) dst[1] = r.obs.y;
+            if (OBS_DIM > 2) dst[2] = r.obs.z;
+        }
+        scal_out[i] = r.s;
+        const double a = (double)r.s.z;
+        s += a;
+        ss += a * a;
+    }
+    if (stats) finish_stats(s, ss, g_partials, &g_ticket, stats, smem);
+}
+
 __global__ void __launch_bounds__(256)
     normalize_adv_kernel(float* __restrict__ adv, const double* __restrict__ stats, double inv_count, int64_t B) {
     double mean = stats[0] * inv_count;
@@ -205,6 +253,35 @@ extern "C" int xb_gather_batch(const int64_t* idx, int64_t B, int64_t T, int64_t
     gather_batch_kernel<<<grid_for(B, kGatherBlock, 8), kGatherBlock, 0, (cudaStream_t)stream>>>(
         idx, B, T, N, (const float4*)b_obs, obs_dim, b_act, act_dim, b_ret, b_val, b_adv, b_logp, obs_out, act_out,
         ret_out, val_out, adv_out, logp_out, stats);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_pack_records(const float* b_obs, const float* b_act, const float* b_logp, const float* b_adv,
+                               const float* b_ret, float* rec, int64_t TN, xb_stream_t stream) {
+    if (TN <= 0 || !b_obs || !b_act || !b_logp || !b_adv || !b_ret || !rec) return XB_E_BADARG;
+    if (((uintptr_t)rec & 31u) || ((uintptr_t)b_obs & 15u)) return XB_E_BADARG;
+    pack_records_kernel<<<grid_for(TN, 256, 8), 256, 0, (cudaStream_t)stream>>>((const float4*)b_obs, b_act, b_logp, b_adv,
+                                                                               b_ret, (Record*)rec, TN);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_gather_records(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* rec, int obs_dim,
+                                 float* obs_out, float* scal_out, double* stats, xb_stream_t stream) {
+    if (B <= 0 || T <= 0 || N <= 0 || !idx || !rec || !obs_out || !scal_out) return XB_E_BADARG;
+    if (obs_dim < 1 || obs_dim > 4) return XB_E_UNSUPPORTED;
+    if (((uintptr_t)rec & 31u) || ((uintptr_t)scal_out & 15u) || (obs_dim == 4 && ((uintptr_t)obs_out & 15u))) return XB_E_BADARG;
+    int grid = grid_for(B, kGatherBlock, 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    const Record* r = (const Record*)rec;
+    float4* so = (float4*)scal_out;
+    switch (obs_dim) {
+        case 4: gather_records_kernel<4><<<grid, kGatherBlock, 0, s>>>(idx, B, T, N, r, obs_out, so, stats); break;
+        case 3: gather_records_kernel<3><<<grid, kGatherBlock, 0, s>>>(idx, B, T, N, r, obs_out, so, stats); break;
+        case 2: gather_records_kernel<2><<<grid, kGatherBlock, 0, s>>>(idx, B, T, N, r, obs_out, so, stats); break;
+        default: gather_records_kernel<1><<<grid, kGatherBlock, 0, s>>>(idx, B, T, N, r, obs_out, so, stats); break;
+    }
     XB_LAUNCH_CHECK();
     return 0;
 }

@@ -21,6 +21,7 @@ namespace xb {
 struct LossCommon {
     const int64_t* idx;  // nullable
     int64_t B, T, N;
+    int64_t stride;      // element stride (floats) of the dense per-sample arrays when idx == NULL (4 = packed float4)
     const float* v_pred;
     const float* act;
     const float* ret;
@@ -35,7 +36,7 @@ struct LossCommon {
 };
 
 __device__ __forceinline__ int64_t sample_row(const LossCommon& c, int64_t i) {
-    if (!c.idx) return i;
+    if (!c.idx) return i * c.stride;
     int64_t k = c.idx[i];
     int64_t env = k / c.T;
     return (k - env * c.T) * c.N + env;
@@ -62,13 +63,19 @@ __device__ __forceinline__ float surrogate_and_value(const LossCommon& c, const 
                                                      float logp, double (&acc)[5]) {
     float A = c.adv[row];
     if (nrm.on) A = (A - nrm.mean) / nrm.denom;
-    const float ratio = expf(logp - c.old_logp[row]);
+    float m, dlogp, ratio = 1.0f;
     const float lo = 1.0f - c.clip_range, hi = 1.0f + c.clip_range;
-    const float s1 = fminf(fmaxf(ratio, lo), hi) * A;
-    const float s2 = A * ratio;
-    const float m = fminf(s1, s2);
-    const bool inactive = (A > 0.0f && ratio > hi) || (A < 0.0f && ratio < lo);
-    const float dlogp = inactive ? 0.0f : -c.inv_batch * A * ratio;
+    if (c.clip_range > 0.0f) {   // PPO-Clip surrogate (ppoclip_learner.py:36-39)
+        ratio = expf(logp - c.old_logp[row]);
+        const float s1 = fminf(fmaxf(ratio, lo), hi) * A;
+        const float s2 = A * ratio;
+        m = fminf(s1, s2);
+        const bool inactive = (A > 0.0f && ratio > hi) || (A < 0.0f && ratio < lo);
+        dlogp = inactive ? 0.0f : -c.inv_batch * A * ratio;
+    } else {                     // A2C / PG surrogate: -(adv * log_prob).mean()  (a2c_learner.py:28, pg_learner.py:24)
+        m = A * logp;
+        dlogp = -c.inv_batch * A;
+    }
 
     const float v = c.v_pred[i], R = c.ret[row];
     float verr = v - R;
@@ -90,7 +97,7 @@ __device__ __forceinline__ float surrogate_and_value(const LossCommon& c, const 
     acc[0] += (double)m;
     acc[1] += (double)vloss;
     acc[3] += (double)v;
-    acc[4] += (ratio < lo || ratio > hi) ? 1.0 : 0.0;
+    acc[4] += (c.clip_range > 0.0f && (ratio < lo || ratio > hi)) ? 1.0 : 0.0;
     return dlogp;
 }
 
@@ -194,8 +201,11 @@ __global__ void __launch_bounds__(kLossBlock)
 
 static int check_common(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* v_pred, const float* act,
                         const float* ret, const float* adv, const float* old_logp, const float* val_old,
-                        const double* adv_stats, int64_t adv_count, float value_clip, float* dv, double* scalars) {
-    if (B <= 0 || !v_pred || !act || !ret || !adv || !old_logp || !dv || !scalars) return XB_E_BADARG;
+                        const double* adv_stats, int64_t adv_count, float value_clip, float* dv, double* scalars,
+                        float clip_range, int64_t stride, int A) {
+    if (clip_range > 0.0f && !old_logp) return XB_E_BADARG;
+    if (stride < 1 || (idx && stride != 1) || (stride > 1 && A > 1)) return XB_E_BADARG;
+    if (B <= 0 || !v_pred || !act || !ret || !adv || !dv || !scalars) return XB_E_BADARG;
     if (idx && (T <= 0 || N <= 0)) return XB_E_BADARG;
     if (adv_stats && adv_count <= 0) return XB_E_BADARG;
     if (value_clip > 0.0f && !val_old) return XB_E_BADARG;
@@ -210,14 +220,14 @@ extern "C" int xb_ppo_loss_categorical(const int64_t* idx, int64_t B, int64_t T,
                                        const float* v_pred, const float* act, const float* ret, const float* adv,
                                        const float* old_logp, const float* val_old, const double* adv_stats,
                                        int64_t adv_count, float clip_range, float vf_coef, float ent_coef,
-                                       float value_clip, float inv_batch, float* dlogits, float* dv, double* scalars,
-                                       xb_stream_t stream) {
-    int rc = check_common(idx, B, T, N, v_pred, act, ret, adv, old_logp, val_old, adv_stats, adv_count, value_clip, dv, scalars);
+                                       float value_clip, float inv_batch, int64_t stride, float* dlogits, float* dv,
+                                       double* scalars, xb_stream_t stream) {
+    int rc = check_common(idx, B, T, N, v_pred, act, ret, adv, old_logp, val_old, adv_stats, adv_count, value_clip, dv, scalars, clip_range, stride, 1);
     if (rc) return rc;
     if (!logits || !dlogits || A < 2) return XB_E_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
     XB_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(double), s));
-    LossCommon c{idx, B, T, N, v_pred, act, ret, adv, old_logp, val_old, adv_stats,
+    LossCommon c{idx, B, T, N, stride, v_pred, act, ret, adv, old_logp, val_old, adv_stats,
                  adv_stats ? 1.0 / (double)adv_count : 0.0, clip_range, vf_coef, ent_coef, value_clip, inv_batch, dv, scalars};
     int grid = grid_for(B, kLossBlock, 8);
     if (A == 2)
@@ -232,16 +242,16 @@ extern "C" int xb_ppo_loss_gaussian(const int64_t* idx, int64_t B, int64_t T, in
                                     const float* logstd, int A, const float* v_pred, const float* act, const float* ret,
                                     const float* adv, const float* old_logp, const float* val_old,
                                     const double* adv_stats, int64_t adv_count, float clip_range, float vf_coef,
-                                    float ent_coef, float value_clip, float inv_batch, float* dmu, double* dlogstd_acc,
-                                    float* dv, double* scalars, xb_stream_t stream) {
-    int rc = check_common(idx, B, T, N, v_pred, act, ret, adv, old_logp, val_old, adv_stats, adv_count, value_clip, dv, scalars);
+                                    float ent_coef, float value_clip, float inv_batch, int64_t stride, float* dmu,
+                                    double* dlogstd_acc, float* dv, double* scalars, xb_stream_t stream) {
+    int rc = check_common(idx, B, T, N, v_pred, act, ret, adv, old_logp, val_old, adv_stats, adv_count, value_clip, dv, scalars, clip_range, stride, A);
     if (rc) return rc;
     if (!mu || !logstd || !dmu || !dlogstd_acc || A < 1) return XB_E_BADARG;
     if (A > kMaxGaussA) return XB_E_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     XB_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(double), s));
     XB_CUDA(cudaMemsetAsync(dlogstd_acc, 0, A * sizeof(double), s));
-    LossCommon c{idx, B, T, N, v_pred, act, ret, adv, old_logp, val_old, adv_stats,
+    LossCommon c{idx, B, T, N, stride, v_pred, act, ret, adv, old_logp, val_old, adv_stats,
                  adv_stats ? 1.0 / (double)adv_count : 0.0, clip_range, vf_coef, ent_coef, value_clip, inv_batch, dv, scalars};
     loss_gaussian_kernel<<<grid_for(B, kLossBlock, 8), kLossBlock, 0, s>>>(c, mu, logstd, A, dmu, dlogstd_acc);
     XB_LAUNCH_CHECK();

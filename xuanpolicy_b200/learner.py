@@ -109,14 +109,14 @@ class PPOCLIP_Learner:
 
     # ---------------------------------------------------------------------------------------------- loss kernel
     def _loss_backward(self, a_dist, v_pred, act, ret, adv, old_logp, val_old, inv_batch, idx=None, T=0, N=0,
-                       adv_stats=None, adv_count=0):
+                       adv_stats=None, adv_count=0, packed=None):
         """Fused loss fwd+bwd on the network outputs, then torch autograd through the MLP."""
         kind, p0, p1 = _dist_params(a_dist)
         v = v_pred.detach().contiguous()
         dv = torch.empty_like(v)
         common = dict(clip_range=self.clip_range, vf_coef=self.vf_coef, ent_coef=self.ent_coef, inv_batch=inv_batch,
                       idx=idx, T=T, N=N, val_old=val_old if self.value_clip > 0 else None, adv_stats=adv_stats,
-                      adv_count=adv_count, value_clip=self.value_clip)
+                      adv_count=adv_count, value_clip=self.value_clip, packed=packed)
         if kind == "categorical":
             logits = p0.detach().contiguous()
             dlogits = torch.empty_like(logits)
@@ -151,10 +151,14 @@ class PPOCLIP_Learner:
             return torch.as_tensor(x, device=dev).to(torch.float32).contiguous()
 
         with torch.cuda.device(dev):
-            act, ret, val, adv, olp = dv_(act_batch), dv_(ret_batch), dv_(value_batch), dv_(adv_batch), dv_(old_logp)
+            act, ret, val, adv = dv_(act_batch), dv_(ret_batch), dv_(value_batch), dv_(adv_batch)
+            olp = dv_(old_logp) if old_logp is not None else None
             obs = torch.as_tensor(obs_batch, device=dev)
             B = ret.shape[0]
-            _, a_dist, v_pred = self.policy(obs)
+            out = self.policy(obs)
+            a_dist = out[1]
+            # actor-only policies (PG) have no critic: a zero value head that receives (and ignores) a zero gradient
+            v_pred = out[2] if len(out) > 2 else torch.zeros(B, device=dev, requires_grad=True)
             self.optimizer.zero_grad()
             self._loss_backward(a_dist, v_pred, act.reshape(B, -1) if act.dim() > 1 else act, ret, adv, olp, val, 1.0 / B)
             if self.use_grad_clip:
@@ -182,14 +186,20 @@ class PPOCLIP_Learner:
         key = (B, obs_dim)
         if key not in self._mb:
             self._mb[key] = dict(obs=torch.empty((B, obs_dim), dtype=torch.float32, device=self.device),
+                                 scal=torch.empty((B, 4), dtype=torch.float32, device=self.device),
                                  stats=torch.zeros(2, dtype=torch.float64, device=self.device))
         return self._mb[key]
 
     def stage_gather(self, memory, idx):
         """Stage 1 of a native update: gather the MLP input rows and the minibatch advantage statistics."""
         mb = self._minibatch_buffers(idx.numel(), memory.obs_dim)
-        ops.gather_obs(idx, memory.n_size, memory.n_envs, memory._obs, memory.obs_dim, mb["obs"],
-                       b_adv=memory._adv if memory.use_advnorm else None, stats=mb["stats"] if memory.use_advnorm else None)
+        if memory.packed and self.value_clip <= 0:   # one 32-byte record per sample: obs + {act, old_logp, adv, ret}
+            ops.gather_records(idx, memory.n_size, memory.n_envs, memory._rec, memory.obs_dim, mb["obs"], mb["scal"],
+                               stats=mb["stats"] if memory.use_advnorm else None)
+        else:
+            ops.gather_obs(idx, memory.n_size, memory.n_envs, memory._obs, memory.obs_dim, mb["obs"],
+                           b_adv=memory._adv if memory.use_advnorm else None,
+                           stats=mb["stats"] if memory.use_advnorm else None)
         return mb
 
     def stage_forward_backward(self, memory, idx, mb):
@@ -197,9 +207,14 @@ class PPOCLIP_Learner:
         B = idx.numel()
         self._flat.flat_grad.zero_()
         _, a_dist, v_pred = self.policy(mb["obs"])
-        self._loss_backward(a_dist, v_pred, memory._act, memory._ret, memory._adv, memory._logp, memory._val,
-                            1.0 / (B * self.world_size), idx=idx, T=memory.n_size, N=memory.n_envs,
-                            adv_stats=mb["stats"] if memory.use_advnorm else None, adv_count=B * self.world_size)
+        stats = mb["stats"] if memory.use_advnorm else None
+        if memory.packed and self.value_clip <= 0:   # scalars already gathered, compact and coalesced
+            self._loss_backward(a_dist, v_pred, None, None, None, None, None, 1.0 / (B * self.world_size),
+                                adv_stats=stats, adv_count=B * self.world_size, packed=mb["scal"])
+        else:                                        # gather fused into the loss kernel
+            self._loss_backward(a_dist, v_pred, memory._act, memory._ret, memory._adv, memory._logp, memory._val,
+                                1.0 / (B * self.world_size), idx=idx, T=memory.n_size, N=memory.n_envs,
+                                adv_stats=stats, adv_count=B * self.world_size)
 
     def stage_optimizer(self):
         """Stage 3: global-norm clip + Adam + LinearLR on the flat buffers (one fused device step)."""
@@ -228,3 +243,34 @@ class PPOCLIP_Learner:
             lr = self._flat.lr0 * (1.0 + (self._flat.end_factor - 1.0) * it / self._flat.total_iters)
         return {"actor-loss": float(-s[0]), "critic-loss": float(s[1]), "entropy": float(s[2]), "learning_rate": lr,
                 "predict_value": float(s[3]), "clip_ratio": torch.tensor(s[4], dtype=torch.float32)}
+
+
+class A2C_Learner(PPOCLIP_Learner):
+    """A2C_Learner drop-in (xuance/torch/learners/policy_gradient/a2c_learner.py:4-50): same constructor and
+    `update(obs_batch, act_batch, ret_batch, adv_batch)`.  Same fused loss kernel with the A2C surrogate
+    (`clip_range <= 0`: a_loss = -(adv * log_prob).mean()); the reference always clips the gradient norm (:36)."""
+
+    def __init__(self, policy, optimizer, scheduler=None, device=None, model_dir="./", vf_coef=0.25, ent_coef=0.005,
+                 clip_grad=None):
+        super().__init__(policy, optimizer, scheduler, device, model_dir, vf_coef=vf_coef, ent_coef=ent_coef,
+                         clip_range=0.0, clip_grad_norm=clip_grad, use_grad_clip=clip_grad is not None)
+        self.clip_grad = clip_grad
+
+    def update(self, obs_batch, act_batch, ret_batch, adv_batch):
+        info = super().update(obs_batch, act_batch, ret_batch, ret_batch, adv_batch, None)
+        info.pop("clip_ratio")
+        return info
+
+
+class PG_Learner(PPOCLIP_Learner):
+    """PG_Learner drop-in (xuance/torch/learners/policy_gradient/pg_learner.py:4-45): actor-only policy
+    (`policy(obs) -> (outputs, dist)`), a_loss = -(returns * log_prob).mean(), no value term."""
+
+    def __init__(self, policy, optimizer, scheduler=None, device=None, model_dir="./", ent_coef=0.005, clip_grad=None):
+        super().__init__(policy, optimizer, scheduler, device, model_dir, vf_coef=0.0, ent_coef=ent_coef, clip_range=0.0,
+                         clip_grad_norm=clip_grad, use_grad_clip=clip_grad is not None)
+        self.clip_grad = clip_grad
+
+    def update(self, obs_batch, act_batch, ret_batch):
+        info = super().update(obs_batch, act_batch, ret_batch, ret_batch, ret_batch, None)
+        return {k: info[k] for k in ("actor-loss", "entropy", "learning_rate")}

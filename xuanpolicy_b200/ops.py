@@ -84,22 +84,44 @@ def normalize_adv(adv, stats, count):
     _lib.call("xb_normalize_adv", _p(adv, F32), _p(stats, F64), count, adv.numel(), _stream())
 
 
+def _scalars(packed, act, ret, adv, old_logp):
+    """Raw pointers + stride of the per-sample scalars: separate arrays (stride 1) or a packed [B, 4] float4 tensor
+    {act, old_logp, adv, ret} as produced by gather_records (stride 4)."""
+    if packed is None:
+        return _p(act, F32), _p(ret, F32), _p(adv, F32), _p(old_logp, F32), 1
+    base = _p(packed, F32)
+    return base, base + 12, base + 8, base + 4, 4
+
+
 def ppo_loss_categorical(logits, v_pred, act, ret, adv, old_logp, dlogits, dv, scalars, clip_range, vf_coef, ent_coef,
-                         inv_batch, idx=None, T=0, N=0, val_old=None, adv_stats=None, adv_count=0, value_clip=0.0):
+                         inv_batch, idx=None, T=0, N=0, val_old=None, adv_stats=None, adv_count=0, value_clip=0.0,
+                         packed=None):
     B, A = logits.shape
-    _lib.call("xb_ppo_loss_categorical", _p(idx, I64), B, T, N, _p(logits, F32), A, _p(v_pred, F32), _p(act, F32),
-              _p(ret, F32), _p(adv, F32), _p(old_logp, F32), _p(val_old, F32), _p(adv_stats, F64), adv_count,
-              float(clip_range), float(vf_coef), float(ent_coef), float(value_clip), float(inv_batch),
-              _p(dlogits, F32), _p(dv, F32), _p(scalars, F64), _stream())
+    pa, pr, pv, pl, stride = _scalars(packed, act, ret, adv, old_logp)
+    _lib.call("xb_ppo_loss_categorical", _p(idx, I64), B, T, N, _p(logits, F32), A, _p(v_pred, F32), pa, pr, pv, pl,
+              _p(val_old, F32), _p(adv_stats, F64), adv_count, float(clip_range), float(vf_coef), float(ent_coef),
+              float(value_clip), float(inv_batch), stride, _p(dlogits, F32), _p(dv, F32), _p(scalars, F64), _stream())
 
 
 def ppo_loss_gaussian(mu, logstd, v_pred, act, ret, adv, old_logp, dmu, dlogstd_acc, dv, scalars, clip_range, vf_coef,
-                      ent_coef, inv_batch, idx=None, T=0, N=0, val_old=None, adv_stats=None, adv_count=0, value_clip=0.0):
+                      ent_coef, inv_batch, idx=None, T=0, N=0, val_old=None, adv_stats=None, adv_count=0, value_clip=0.0,
+                      packed=None):
     B, A = mu.shape
-    _lib.call("xb_ppo_loss_gaussian", _p(idx, I64), B, T, N, _p(mu, F32), _p(logstd, F32), A, _p(v_pred, F32),
-              _p(act, F32), _p(ret, F32), _p(adv, F32), _p(old_logp, F32), _p(val_old, F32), _p(adv_stats, F64),
-              adv_count, float(clip_range), float(vf_coef), float(ent_coef), float(value_clip), float(inv_batch),
-              _p(dmu, F32), _p(dlogstd_acc, F64), _p(dv, F32), _p(scalars, F64), _stream())
+    pa, pr, pv, pl, stride = _scalars(packed, act, ret, adv, old_logp)
+    _lib.call("xb_ppo_loss_gaussian", _p(idx, I64), B, T, N, _p(mu, F32), _p(logstd, F32), A, _p(v_pred, F32), pa, pr, pv,
+              pl, _p(val_old, F32), _p(adv_stats, F64), adv_count, float(clip_range), float(vf_coef), float(ent_coef),
+              float(value_clip), float(inv_batch), stride, _p(dmu, F32), _p(dlogstd_acc, F64), _p(dv, F32),
+              _p(scalars, F64), _stream())
+
+
+def pack_records(b_obs, b_act, b_logp, b_adv, b_ret, rec):
+    _lib.call("xb_pack_records", _p(b_obs, F32), _p(b_act, F32), _p(b_logp, F32), _p(b_adv, F32), _p(b_ret, F32),
+              _p(rec, F32), b_adv.numel(), _stream())
+
+
+def gather_records(idx, T, N, rec, obs_dim, obs_out, scal_out, stats=None):
+    _lib.call("xb_gather_records", _p(idx, I64), idx.numel(), T, N, _p(rec, F32), obs_dim, _p(obs_out, F32),
+              _p(scal_out, F32), _p(stats, F64), _stream())
 
 
 def sample_categorical(logits, seed, counter, offset, act_out, logp_out):

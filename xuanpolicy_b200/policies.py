@@ -275,6 +275,22 @@ class GaussianActorCritic(_ActorCritic):
         self.critic = _Critic(sd, critic_hidden_size, activation, initialize, device, last_init=False)
 
 
+class CategoricalActor(nn.Module):
+    """Actor-only policy (Categorical_Actor_Policy, xuance/torch/policies/categorical.py:88-107), used by PG."""
+
+    def __init__(self, action_space, representation, actor_hidden_size, normalize=None, initialize=nn.init.orthogonal_,
+                 activation=nn.LeakyReLU, device=None):
+        super().__init__()
+        self.action_dim, self.representation = action_space.n, representation
+        self.representation_info_shape = representation.output_shapes
+        self.actor = _CategoricalActor(representation.output_shapes["state"][0], self.action_dim, actor_hidden_size,
+                                       activation, initialize, device)
+
+    def forward(self, observation):
+        outputs = self.representation(observation)
+        return outputs, self.actor(outputs["state"])
+
+
 def make_policy(observation_space, action_space, hidden=(128,), device=None, seed=None):
     """Builds the `representation_hidden_size=actor_hidden_size=critic_hidden_size=hidden` policy of the yaml configs."""
     from .spaces import is_discrete
