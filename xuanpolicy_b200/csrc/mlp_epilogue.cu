@@ -22,6 +22,8 @@ constexpr int kEpiUnroll = 4;
 __global__ void __launch_bounds__(kEpiBlock)
     bias_act_fwd_kernel(float4* __restrict__ y, const float4* __restrict__ bias, float slope, int64_t n4, int H4) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // blockDim.x is a multiple of H4 (checked by the host), so a thread always lands on the same column group
+    const float4 b = bias[threadIdx.x % H4];
     for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * kEpiUnroll) {
         float4 v[kEpiUnroll];
 #pragma unroll
@@ -33,7 +35,6 @@ __global__ void __launch_bounds__(kEpiBlock)
         for (int u = 0; u < kEpiUnroll; ++u) {
             const int64_t i = i0 + u * stride;
             if (i < n4) {
-                const float4 b = bias[i % H4];
                 float4 o;
                 o.x = v[u].x + b.x; o.y = v[u].y + b.y; o.z = v[u].z + b.z; o.w = v[u].w + b.w;
                 o.x = o.x > 0.f ? o.x : o.x * slope;
@@ -104,8 +105,17 @@ __global__ void __launch_bounds__(kEpiBlock)
         __threadfence();
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < rows_per_pass) {
-            for (int g = r; g < (int)gridDim.x; g += rows_per_pass) {
-                const float4 t = reinterpret_cast<const float4*>(partials)[(int64_t)g * H4 + c];
+            const float4* pp = reinterpret_cast<const float4*>(partials);
+            int g = r;
+            for (; g + 7 * rows_per_pass < (int)gridDim.x; g += 8 * rows_per_pass) {   // 8 independent loads in flight
+                float4 t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = pp[(int64_t)(g + u * rows_per_pass) * H4 + c];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { s.x += t[u].x; s.y += t[u].y; s.z += t[u].z; s.w += t[u].w; }
+            }
+            for (; g < (int)gridDim.x; g += rows_per_pass) {
+                const float4 t = pp[(int64_t)g * H4 + c];
                 s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
             }
             red[r * H4 + c] = s;
@@ -129,7 +139,7 @@ using namespace xb;
 
 extern "C" int xb_bias_act_fwd(float* y, const float* bias, float slope, int64_t B, int H, xb_stream_t stream) {
     if (B <= 0 || !y || !bias) return XB_E_BADARG;
-    if (H % 4 != 0 || H < 4) return XB_E_UNSUPPORTED;
+    if (H % 4 != 0 || H < 4 || kEpiBlock % (H / 4) != 0) return XB_E_UNSUPPORTED;
     if ((((uintptr_t)y) | ((uintptr_t)bias)) & 15u) return XB_E_BADARG;  // float4 accesses
     const int64_t n4 = B * (H / 4);
     bias_act_fwd_kernel<<<grid_for((n4 + kEpiUnroll - 1) / kEpiUnroll, kEpiBlock, 8), kEpiBlock, 0, (cudaStream_t)stream>>>(
@@ -147,7 +157,7 @@ extern "C" int xb_act_bias_bwd(const float* dy, const float* y, float slope, flo
         return XB_E_BADARG;  // float4 accesses
     const int H4 = H / 4;
     const int rows_per_pass = kEpiBlock / H4;
-    int grid = kNumSMs * 4;
+    int grid = kNumSMs * 2;
     const int64_t need = (B + rows_per_pass * kEpiUnroll * 2 - 1) / (rows_per_pass * kEpiUnroll * 2);
     if (need < grid) grid = (int)(need < 1 ? 1 : need);
     const size_t smem = (size_t)rows_per_pass * H4 * sizeof(float4);

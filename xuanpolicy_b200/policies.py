@@ -109,7 +109,7 @@ class _DenseStack(nn.Sequential):
             m = mods[k]
             nxt = mods[k + 1] if k + 1 < len(mods) else None
             if (on_gpu and isinstance(m, nn.Linear) and isinstance(nxt, nn.LeakyReLU) and m.out_features % 4 == 0
-                    and m.out_features <= 1024 and m.bias.data_ptr() % 16 == 0):
+                    and m.out_features <= 1024 and 256 % (m.out_features // 4) == 0 and m.bias.data_ptr() % 16 == 0):
                 if torch.is_grad_enabled() and (m.weight.requires_grad or x.requires_grad):
                     x = _LinearLeakyReLU.apply(x, m.weight, m.bias, float(nxt.negative_slope), self._workspace(x.device))
                 else:
