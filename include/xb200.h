@@ -228,6 +228,17 @@ int xb_rms_merge_scalar(const double* sums, double* state, float* rew_std, xb_st
  * ---------------------------------------------------------------------------------------------------------- */
 int xb_act_bias_bwd(const float* dy, const float* y, float slope, float* dz, float* dbias, float* workspace,
                     int64_t B, int H, xb_stream_t stream);
+/* Narrow output heads (A <= 4 columns; bandwidth-bound matrix-vector work): the last Linear of the actor / critic.
+ *   xb_head_fwd      out[b,a] = h[b,:] . W[a,:] + bias[a]                                       h f32 [B][H], W f32 [A][H]
+ *   xb_head_bwd_act  the head's backward fused with the hidden layer's LeakyReLU backward and bias gradient:
+ *                    dz[b,:] = (sum_a dout[b,a] W2[a,:]) * lrelu'(y[b,:]),  db1 = colsum(dz),
+ *                    dW2[a,:] = sum_b dout[b,a] y[b,:],  db2[a] = sum_b dout[b,a]
+ * Replace F.linear + its autograd (outer product, gemv, three reductions) for categorical.py:31,54 / gaussian.py:23,47.
+ * workspace: fp32 [4 + 148*((1+A)*H + 4)], word 0 ZERO-INITIALISED once by the caller. */
+int xb_head_fwd(const float* h, const float* W, const float* bias, float* out, int64_t B, int H, int A,
+                xb_stream_t stream);
+int xb_head_bwd_act(const float* dout, const float* y, const float* W2, float slope, float* dz, float* db1, float* dW2,
+                    float* db2, float* workspace, int64_t B, int H, int A, xb_stream_t stream);
 /* Forward epilogue of the same block: y[b,h] = leaky_relu(y[b,h] + bias[h]) in place, after a bias-free cuBLAS mm. */
 int xb_bias_act_fwd(float* y, const float* bias, float slope, int64_t B, int H, xb_stream_t stream);
 

@@ -247,3 +247,40 @@ def test_packed_records_gather_bit_exact():
         a = adv[step, env].astype(np.float64)
         s = stats.cpu().numpy()
         assert abs(s[0] - a.sum()) < 1e-9 * B and abs(s[1] - (a * a).sum()) < 1e-9 * B
+
+
+@pytest.mark.parametrize("B,H,A", [(4096, 128, 1), (1000, 64, 2), (65536, 128, 1), (3333, 256, 4)])
+def test_mlp_epilogue_and_head_kernels_vs_torch(B, H, A):
+    """csrc/mlp_epilogue.cu against the plain torch ops they replace."""
+    from xuanpolicy_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(B + H)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=gen)
+    y0, bias, slope = rnd(B, H), rnd(H), 0.01
+    y = y0.clone()
+    ops.bias_act_fwd(y, bias, slope)
+    assert torch.equal(y, torch.nn.functional.leaky_relu(y0 + bias, slope))
+    dy = rnd(B, H)
+    dz, db = torch.empty_like(dy), torch.empty(H, device="cuda")
+    ws = torch.zeros(4 + 592 * 1024, device="cuda")
+    ops.act_bias_bwd(dy, y, slope, dz, db, ws)
+    ref_dz = torch.where(y > 0, dy, dy * slope)
+    assert torch.equal(dz, ref_dz)
+    assert torch.allclose(db, ref_dz.double().sum(0).float(), rtol=1e-4, atol=1e-3)
+    w2, b2 = rnd(A, H) * 0.1, rnd(A)
+    out = torch.empty(B, A, device="cuda")
+    ops.head_fwd(y, w2, b2, out)
+    assert torch.allclose(out, torch.addmm(b2, y, w2.t()), rtol=1e-4, atol=1e-4)
+    dout = rnd(B, A)
+    db1, dw2, db2 = torch.empty(H, device="cuda"), torch.empty(A, H, device="cuda"), torch.empty(A, device="cuda")
+    ops.head_bwd_act(dout, y, w2, slope, dz, db1, dw2, db2, ws)
+    dh = dout @ w2
+    ref_dz = torch.where(y > 0, dh, dh * slope)
+    assert torch.allclose(dz, ref_dz, rtol=1e-5, atol=1e-6)
+    scale = lambda t: t.abs().max().item() + 1e-6
+    assert (db1 - ref_dz.double().sum(0).float()).abs().max().item() <= 2e-5 * scale(db1) * 10
+    ref_dw2 = (dout.double().t() @ y.double()).float()
+    assert (dw2 - ref_dw2).abs().max().item() <= 1e-4 * scale(ref_dw2)
+    assert torch.allclose(db2, dout.double().sum(0).float(), rtol=1e-4, atol=1e-3)
+    # second launch reuses the (self-resetting) workspace ticket
+    ops.head_bwd_act(dout, y, w2, slope, dz, db1, dw2, db2, ws)
+    assert (dw2 - ref_dw2).abs().max().item() <= 1e-4 * scale(ref_dw2)

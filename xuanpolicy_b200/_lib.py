@@ -38,6 +38,8 @@ SIGNATURES = {
     "xb_rms_normalize": [_vp, _i32, _vp, _vp, _vp, _f32, _vp, _i64, _i64, _vp],
     "xb_returns_track": [_vp, _vp, _vp, _vp, _f64, _vp, _vp, _i64, _vp],
     "xb_rms_merge_scalar": [_vp, _vp, _vp, _vp],
+    "xb_head_fwd": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
+    "xb_head_bwd_act": [_vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
     "xb_bias_act_fwd": [_vp, _vp, _f32, _i64, _i32, _vp],
     "xb_act_bias_bwd": [_vp, _vp, _f32, _vp, _vp, _vp, _i64, _i32, _vp],
     "xb_clip_adam_step": [_vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _i64, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp],

@@ -133,9 +133,218 @@ __global__ void __launch_bounds__(kEpiBlock)
     }
 }
 
+// ---- narrow output heads (A <= 4 columns): bandwidth-bound matrix-vector work, not a GEMM ---------------------
+// The last Linear of the actor (A = 1..4 outputs) and the critic (1 output) reads a [B, H] activation once and
+// produces A numbers per row.  cuBLAS serves these shapes with gemv-style kernels at ~1.6 TB/s and torch autograd
+// adds an outer-product kernel, a gemv, three reductions and two adds in the backward.  Here:
+//   head_fwd:      out[b,a] = h[b,:] . W[a,:] + bias[a]                                  (one pass over h)
+//   head_bwd_act:  dz[b,:]  = (sum_a dout[b,a] W[a,:]) * lrelu'(y[b,:])   (gradient w.r.t. the hidden pre-activation)
+//                  db1[:]   = sum_b dz[b,:]      dW2[a,:] = sum_b dout[b,a] y[b,:]      db2[a] = sum_b dout[b,a]
+//                  — the head's backward fused with the hidden layer's activation backward: y is read once,
+//                  dz written once, the intermediate dL/dy is never materialised.
+constexpr int kHeadMaxA = 4;
+constexpr int kHeadMaxC = 4;   // float4 column groups per thread in head_fwd (H <= 512)
+constexpr int kHeadBlock = 512;
+
+__global__ void __launch_bounds__(kEpiBlock)
+    head_fwd_kernel(const float4* __restrict__ h, const float4* __restrict__ W, const float* __restrict__ bias,
+                    float* __restrict__ out, int64_t B, int H4, int A, int G) {
+    // a group of G lanes (power of two <= 32, H4 % G == 0) owns a row; lane j covers column groups j, j+G, ...
+    const int lane = threadIdx.x & (G - 1);
+    const int per = H4 / G;
+    float4 w[kHeadMaxA][kHeadMaxC];
+#pragma unroll
+    for (int a = 0; a < kHeadMaxA; ++a)
+#pragma unroll
+        for (int k = 0; k < kHeadMaxC; ++k)
+            w[a][k] = (a < A && k < per) ? W[a * H4 + lane + k * G] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int sub = (threadIdx.x & 31) / G;                 // which row of the warp's 32/G rows
+    // warp-uniform trip count (full-mask shuffles below): iterate on the warp's first row
+    for (int64_t bw = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / G; bw < B; bw += groups) {
+        const int64_t b = bw + sub;
+        const bool live = b < B;
+        const int64_t row = live ? b : B - 1;
+        float acc[kHeadMaxA] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < kHeadMaxC; ++k) {
+            if (k < per) {
+                const float4 v = h[row * H4 + lane + k * G];
+#pragma unroll
+                for (int a = 0; a < kHeadMaxA; ++a)
+                    acc[a] += v.x * w[a][k].x + v.y * w[a][k].y + v.z * w[a][k].z + v.w * w[a][k].w;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < kHeadMaxA; ++a)
+            for (int o = G >> 1; o > 0; o >>= 1) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
+        if (lane == 0 && live) {
+#pragma unroll
+            for (int a = 0; a < kHeadMaxA; ++a)
+                if (a < A) out[b * A + a] = acc[a] + bias[a];
+        }
+    }
+}
+
+__device__ __forceinline__ void add4(float4& s, const float4 t) { s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+__device__ __forceinline__ void fma4(float4& s, float k, const float4 t) { s.x += k * t.x; s.y += k * t.y; s.z += k * t.z; s.w += k * t.w; }
+
+// partial record per CTA (float4 slots): [0, H4) db1 | [H4, (1+A) H4) dW2 rows | slot (1+A) H4: db2 (padded to 4)
+__global__ void __launch_bounds__(kHeadBlock)
+    head_bwd_act_kernel(const float* __restrict__ dout, const float4* __restrict__ y, const float4* __restrict__ W2,
+                        float slope, float4* __restrict__ dz, float* __restrict__ db1, float* __restrict__ dW2,
+                        float* __restrict__ db2, float4* __restrict__ partials, unsigned int* __restrict__ ticket,
+                        int64_t B, int H4, int A) {
+    extern __shared__ float4 red[];  // kHeadBlock float4
+    __shared__ bool is_last;
+    const int R = kHeadBlock / H4;
+    const int c = threadIdx.x % H4, r = threadIdx.x / H4;
+    const int64_t rows_per_cta = (B + gridDim.x - 1) / gridDim.x;
+    const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t row1 = row0 + rows_per_cta < B ? row0 + rows_per_cta : B;
+    const int n4 = (1 + A) * H4 + 1;             // float4 slots per partial record
+    float4 w[kHeadMaxA];
+#pragma unroll
+    for (int a = 0; a < kHeadMaxA; ++a) w[a] = a < A ? W2[a * H4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc_b = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc_w[kHeadMaxA];
+#pragma unroll
+    for (int a = 0; a < kHeadMaxA; ++a) acc_w[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc_d = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t b0 = row0 + r; b0 < row1; b0 += (int64_t)R * kEpiUnroll) {
+        float4 o[kEpiUnroll];
+        float g[kEpiUnroll][kHeadMaxA];
+#pragma unroll
+        for (int u = 0; u < kEpiUnroll; ++u) {
+            const int64_t b = b0 + (int64_t)u * R;
+            if (b < row1) {
+                o[u] = y[b * H4 + c];
+#pragma unroll
+                for (int a = 0; a < kHeadMaxA; ++a) g[u][a] = a < A ? dout[b * A + a] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kEpiUnroll; ++u) {
+            const int64_t b = b0 + (int64_t)u * R;
+            if (b < row1) {
+                float4 dh = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int a = 0; a < kHeadMaxA; ++a) {
+                    fma4(dh, g[u][a], w[a]);
+                    fma4(acc_w[a], g[u][a], o[u]);
+                }
+                if (c == 0) add4(acc_d, make_float4(g[u][0], g[u][1], g[u][2], g[u][3]));
+                const float4 z = lrelu_bwd4(dh, o[u], slope);
+                dz[b * H4 + c] = z;
+                add4(acc_b, z);
+            }
+        }
+    }
+    // block reduction over the R row lanes, field by field; one partial record per CTA
+    float4* my = partials + (int64_t)blockIdx.x * n4;
+#pragma unroll
+    for (int f = 0; f <= kHeadMaxA; ++f) {
+        if (f <= A) {                                 // A is block-uniform, so the barriers are too
+            red[r * H4 + c] = (f == 0) ? acc_b : acc_w[f == 0 ? 0 : f - 1];
+            __syncthreads();
+            if (threadIdx.x < H4) {
+                float4 s = red[threadIdx.x];
+                for (int k = 1; k < R; ++k) add4(s, red[k * H4 + threadIdx.x]);
+                my[f * H4 + threadIdx.x] = s;
+            }
+            __syncthreads();
+        }
+    }
+    if (c == 0) red[r] = acc_d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float4 s = red[0];
+        for (int k = 1; k < R; ++k) add4(s, red[k]);
+        my[(1 + A) * H4] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last) {   // deterministic final reduction: thread (slice, slot) sums CTAs slice, slice+S, ... of one slot
+        __threadfence();
+        for (int base = 0; base < n4; base += kHeadBlock) {
+            const int width = n4 - base < kHeadBlock ? n4 - base : kHeadBlock;   // slots handled this round
+            const int S = kHeadBlock / width;                                      // CTA slices per slot
+            const int slot = base + (int)threadIdx.x % width, slice = (int)threadIdx.x / width;
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (slice < S) {
+                int gi = slice;
+                for (; gi + 3 * S < (int)gridDim.x; gi += 4 * S) {
+                    float4 t[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) t[u] = partials[(int64_t)(gi + u * S) * n4 + slot];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) add4(s, t[u]);
+                }
+                for (; gi < (int)gridDim.x; gi += S) add4(s, partials[(int64_t)gi * n4 + slot]);
+            }
+            __syncthreads();
+            if (slice < S) red[slice * width + (slot - base)] = s;
+            __syncthreads();
+            if ((int)threadIdx.x < width) {
+                float4 t = red[threadIdx.x];
+                for (int k = 1; k < S; ++k) add4(t, red[k * width + threadIdx.x]);
+                const int sl = base + threadIdx.x;
+                if (sl < H4) {
+                    reinterpret_cast<float4*>(db1)[sl] = t;
+                } else if (sl < (1 + A) * H4) {
+                    reinterpret_cast<float4*>(dW2)[sl - H4] = t;
+                } else {
+                    const float v[4] = {t.x, t.y, t.z, t.w};
+                    for (int a = 0; a < A; ++a) db2[a] = v[a];
+                }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+}
+
 }  // namespace xb
 
 using namespace xb;
+
+extern "C" int xb_head_fwd(const float* h, const float* W, const float* bias, float* out, int64_t B, int H, int A,
+                           xb_stream_t stream) {
+    if (B <= 0 || !h || !W || !bias || !out) return XB_E_BADARG;
+    if (H % 4 != 0 || H < 4 || A < 1 || A > kHeadMaxA) return XB_E_UNSUPPORTED;
+    if ((((uintptr_t)h) | ((uintptr_t)W)) & 15u) return XB_E_BADARG;
+    const int H4 = H / 4;
+    int G = 32;
+    while (G > 1 && (H4 % G != 0)) G >>= 1;
+    if (H4 / G > kHeadMaxC) return XB_E_UNSUPPORTED;
+    const int64_t threads = B * G;
+    head_fwd_kernel<<<grid_for(threads, kEpiBlock, 8), kEpiBlock, 0, (cudaStream_t)stream>>>(
+        (const float4*)h, (const float4*)W, bias, out, B, H4, A, G);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+// workspace: fp32 [4 + 148 * ((1 + A) * H + 4)], word 0 = ticket, ZERO-INITIALISED once by the caller
+extern "C" int xb_head_bwd_act(const float* dout, const float* y, const float* W2, float slope, float* dz, float* db1,
+                               float* dW2, float* db2, float* workspace, int64_t B, int H, int A, xb_stream_t stream) {
+    if (B <= 0 || !dout || !y || !W2 || !dz || !db1 || !dW2 || !db2 || !workspace) return XB_E_BADARG;
+    if (H % 4 != 0 || H < 4 || kHeadBlock % (H / 4) != 0 || A < 1 || A > kHeadMaxA) return XB_E_UNSUPPORTED;
+    if ((((uintptr_t)y) | ((uintptr_t)W2) | ((uintptr_t)dz) | ((uintptr_t)db1) | ((uintptr_t)dW2) | ((uintptr_t)workspace)) & 15u)
+        return XB_E_BADARG;
+    const int H4 = H / 4;
+    const int R = kHeadBlock / H4;
+    int grid = kNumSMs;                                  // one 512-thread CTA per SM: 148 partial records
+    const int64_t need = (B + R * kEpiUnroll - 1) / (R * kEpiUnroll);
+    if (need < grid) grid = (int)(need < 1 ? 1 : need);
+    head_bwd_act_kernel<<<grid, kHeadBlock, kHeadBlock * sizeof(float4), (cudaStream_t)stream>>>(
+        dout, (const float4*)y, (const float4*)W2, slope, (float4*)dz, db1, dW2, db2, (float4*)(workspace + 4),
+        (unsigned int*)workspace, B, H4, A);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
 
 extern "C" int xb_bias_act_fwd(float* y, const float* bias, float slope, int64_t B, int H, xb_stream_t stream) {
     if (B <= 0 || !y || !bias) return XB_E_BADARG;

@@ -53,6 +53,7 @@ class FlatAdamState:
             p.grad = self.flat_grad[off:off + k].view_as(p.data)
             off += pad4(k)
         self.params = params
+        self.grad_views = [p.grad for p in params]
         group = optimizer.param_groups[0]
         if group.get("weight_decay", 0) != 0 or group.get("amsgrad", False) or group.get("maximize", False):
             raise NotImplementedError("fused Adam supports plain Adam (no weight decay / amsgrad / maximize)")
@@ -70,6 +71,18 @@ class FlatAdamState:
         self.workspace = torch.zeros(8 + 1024, dtype=torch.float64, device=dev)
         self.lr = torch.full((1,), self.lr0, dtype=torch.float32, device=dev)
         self.gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def backward_into(self, outputs, grad_outputs):
+        """d(loss)/d(params) straight into the flat gradient: `torch.autograd.grad` (fresh gradient tensors, no
+        per-parameter accumulate kernels) followed by one multi-tensor copy.  Parameters that are not reached from
+        `outputs` (e.g. logstd, whose gradient the loss kernel produces directly) get zero."""
+        grads = torch.autograd.grad(outputs, self.params, grad_outputs, allow_unused=True)
+        dst = [v for v, g in zip(self.grad_views, grads) if g is not None]
+        src = [g for g in grads if g is not None]
+        torch._foreach_copy_(dst, src)
+        for v, g in zip(self.grad_views, grads):
+            if g is None:
+                v.zero_()
 
     def apply(self, max_norm, grad_scale=1.0):
         ops.clip_adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step, self.lr0,
@@ -109,8 +122,10 @@ class PPOCLIP_Learner:
 
     # ---------------------------------------------------------------------------------------------- loss kernel
     def _loss_backward(self, a_dist, v_pred, act, ret, adv, old_logp, val_old, inv_batch, idx=None, T=0, N=0,
-                       adv_stats=None, adv_count=0, packed=None):
-        """Fused loss fwd+bwd on the network outputs, then torch autograd through the MLP."""
+                       adv_stats=None, adv_count=0, packed=None, flat=None):
+        """Fused loss fwd+bwd on the network outputs, then torch autograd through the MLP (into `.grad`, or — with
+        `flat` — straight into the flat gradient buffer)."""
+        backward = torch.autograd.backward if flat is None else flat.backward_into
         kind, p0, p1 = _dist_params(a_dist)
         v = v_pred.detach().contiguous()
         dv = torch.empty_like(v)
@@ -121,7 +136,7 @@ class PPOCLIP_Learner:
             logits = p0.detach().contiguous()
             dlogits = torch.empty_like(logits)
             ops.ppo_loss_categorical(logits, v, act, ret, adv, old_logp, dlogits, dv, self._scalars, **common)
-            torch.autograd.backward([p0, v_pred], [dlogits, dv])
+            backward([p0, v_pred], [dlogits, dv])
         else:
             mu = p0.detach().contiguous()
             std = p1
@@ -132,15 +147,17 @@ class PPOCLIP_Learner:
             dls = torch.empty(mu.shape[1], dtype=torch.float64, device=mu.device)
             ops.ppo_loss_gaussian(mu, logstd, v, act, ret, adv, old_logp, dmu, dls, dv, self._scalars, **common)
             if direct:             # the kernel's dL/dlogstd goes straight into the parameter's gradient
-                torch.autograd.backward([p0, v_pred], [dmu, dv])
-                if param.grad is None:
+                backward([p0, v_pred], [dmu, dv])
+                if flat is not None:
+                    flat.grad_views[[id(q) for q in flat.params].index(id(param))].copy_(dls)
+                elif param.grad is None:
                     param.grad = dls.to(param.dtype)
                 else:
                     param.grad.add_(dls.to(param.dtype))
             elif std.requires_grad:  # d/dstd = d/dlogstd / std ; autograd carries it back to the logstd parameter
-                torch.autograd.backward([p0, v_pred, std], [dmu, dv, (dls / std.detach().double()).to(std.dtype)])
+                backward([p0, v_pred, std], [dmu, dv, (dls / std.detach().double()).to(std.dtype)])
             else:
-                torch.autograd.backward([p0, v_pred], [dmu, dv])
+                backward([p0, v_pred], [dmu, dv])
 
     # ---------------------------------------------------------------------------------------------- compat update
     def update(self, obs_batch, act_batch, ret_batch, value_batch, adv_batch, old_logp):
@@ -205,16 +222,15 @@ class PPOCLIP_Learner:
     def stage_forward_backward(self, memory, idx, mb):
         """Stage 2: torch MLP forward, fused gather+loss+backward kernel, torch MLP backward into the flat gradient."""
         B = idx.numel()
-        self._flat.flat_grad.zero_()
         _, a_dist, v_pred = self.policy(mb["obs"])
         stats = mb["stats"] if memory.use_advnorm else None
         if memory.packed and self.value_clip <= 0:   # scalars already gathered, compact and coalesced
             self._loss_backward(a_dist, v_pred, None, None, None, None, None, 1.0 / (B * self.world_size),
-                                adv_stats=stats, adv_count=B * self.world_size, packed=mb["scal"])
+                                adv_stats=stats, adv_count=B * self.world_size, packed=mb["scal"], flat=self._flat)
         else:                                        # gather fused into the loss kernel
             self._loss_backward(a_dist, v_pred, memory._act, memory._ret, memory._adv, memory._logp, memory._val,
                                 1.0 / (B * self.world_size), idx=idx, T=memory.n_size, N=memory.n_envs,
-                                adv_stats=stats, adv_count=B * self.world_size)
+                                adv_stats=stats, adv_count=B * self.world_size, flat=self._flat)
 
     def stage_optimizer(self):
         """Stage 3: global-norm clip + Adam + LinearLR on the flat buffers (one fused device step)."""

@@ -175,3 +175,14 @@ def rms_merge_scalar(sums, state, rew_std):
 def bias_act_fwd(y, bias, slope):
     B, H = y.shape
     _lib.call("xb_bias_act_fwd", _p(y, F32), _p(bias, F32), float(slope), B, H, _stream())
+
+
+def head_fwd(h, weight, bias, out):
+    B, H = h.shape
+    _lib.call("xb_head_fwd", _p(h, F32), _p(weight, F32), _p(bias, F32), _p(out, F32), B, H, weight.shape[0], _stream())
+
+
+def head_bwd_act(dout, y, weight2, slope, dz, db1, dw2, db2, workspace):
+    B, H = y.shape
+    _lib.call("xb_head_bwd_act", _p(dout, F32), _p(y, F32), _p(weight2, F32), float(slope), _p(dz, F32), _p(db1, F32),
+              _p(dw2, F32), _p(db2, F32), _p(workspace, F32), B, H, weight2.shape[0], _stream())

@@ -89,6 +89,43 @@ class _LinearHead(torch.autograd.Function):
         return dx, _wgrad(dy, x), _colsum(dy)
 
 
+class _HiddenThenHead(torch.autograd.Function):
+    """out = (leaky_relu(x @ W1^T + b1)) @ W2^T + b2 with a narrow head (<= 4 outputs): the tail
+    [Linear, LeakyReLU, Linear] of the actor / critic (categorical.py:26-32,48-54; gaussian.py:17-24,41-48) as ONE
+    autograd node.  cuBLAS does the H x H products; the head product (bandwidth-bound matrix-vector work) and the whole
+    non-GEMM backward — head gradients, leaky_relu', both bias gradients — are two hand-written kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, slope, workspace):
+        from . import ops
+        y = x @ w1.t()
+        ops.bias_act_fwd(y, b1, slope)
+        out = torch.empty((x.shape[0], w2.shape[0]), dtype=x.dtype, device=x.device)
+        ops.head_fwd(y, w2, b2, out)
+        ctx.save_for_backward(x, w1, y, w2)
+        ctx.slope, ctx.workspace = slope, workspace
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import ops
+        x, w1, y, w2 = ctx.saved_tensors
+        dout = dout.contiguous()
+        dz = torch.empty_like(y)
+        db1 = torch.empty(y.shape[1], dtype=y.dtype, device=y.device)
+        dw2, db2 = torch.empty_like(w2), torch.empty(w2.shape[0], dtype=y.dtype, device=y.device)
+        ops.head_bwd_act(dout, y, w2, ctx.slope, dz, db1, dw2, db2, ctx.workspace)
+        dx = dz @ w1 if ctx.needs_input_grad[0] else None
+        return dx, _wgrad(dz, x), db1, dw2, db2, None, None
+
+
+def _epilogue_ok(lin):
+    """The float4 epilogue kernels need H % 4 == 0, 256 % (H/4) == 0 and 16-byte aligned parameters."""
+    h = lin.out_features
+    return (h % 4 == 0 and h <= 1024 and 256 % (h // 4) == 0 and lin.bias.data_ptr() % 16 == 0
+            and lin.weight.data_ptr() % 16 == 0)
+
+
 class _DenseStack(nn.Sequential):
     """nn.Sequential of [Linear, LeakyReLU, ...] (same parameter names as the reference's Sequential).  On a CUDA
     device Linear+LeakyReLU pairs run as cuBLAS mm + the hand-written epilogue kernels (with a custom autograd
@@ -102,18 +139,31 @@ class _DenseStack(nn.Sequential):
         return ws
 
     def forward(self, x):
+        from . import ops
         mods = list(self)
         on_gpu = x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
         k = 0
         while k < len(mods):
             m = mods[k]
             nxt = mods[k + 1] if k + 1 < len(mods) else None
-            if (on_gpu and isinstance(m, nn.Linear) and isinstance(nxt, nn.LeakyReLU) and m.out_features % 4 == 0
-                    and m.out_features <= 1024 and 256 % (m.out_features // 4) == 0 and m.bias.data_ptr() % 16 == 0):
+            head = mods[k + 2] if k + 2 == len(mods) - 1 else None
+            fusable = on_gpu and isinstance(m, nn.Linear) and isinstance(nxt, nn.LeakyReLU) and _epilogue_ok(m)
+            if (fusable and isinstance(head, nn.Linear) and head.out_features <= 4 and m.out_features <= 512
+                    and head.weight.data_ptr() % 16 == 0):
+                # tail [Linear, LeakyReLU, Linear(<= 4 outputs)]: one autograd node, hand-written head kernels
+                slope = float(nxt.negative_slope)
+                if torch.is_grad_enabled() and (m.weight.requires_grad or x.requires_grad):
+                    x = _HiddenThenHead.apply(x, m.weight, m.bias, head.weight, head.bias, slope, self._workspace(x.device))
+                else:
+                    y = x @ m.weight.t()
+                    ops.bias_act_fwd(y, m.bias, slope)
+                    x = torch.empty((y.shape[0], head.out_features), dtype=y.dtype, device=y.device)
+                    ops.head_fwd(y, head.weight, head.bias, x)
+                k += 3
+            elif fusable:
                 if torch.is_grad_enabled() and (m.weight.requires_grad or x.requires_grad):
                     x = _LinearLeakyReLU.apply(x, m.weight, m.bias, float(nxt.negative_slope), self._workspace(x.device))
                 else:
-                    from . import ops
                     x = x @ m.weight.t()
                     ops.bias_act_fwd(x, m.bias, float(nxt.negative_slope))
                 k += 2
