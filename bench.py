@@ -140,6 +140,26 @@ def time_agent(agent, steps, warmup, flush, world):
     return float(t.item()) / 1e3
 
 
+def time_phases(agent, flush):
+    """CUDA-event time of one rollout graph replay and one epoch graph replay (single GPU, graphs captured)."""
+    if agent._rollout_graph is None or agent._epoch_graph is None:
+        return None
+    out = {}
+    for name, g in (("rollout_graph_ms", agent._rollout_graph), ("epoch_graph_ms", agent._epoch_graph)):
+        ms = []
+        for _ in range(5):
+            flush.add_(1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            g.replay()
+            e.record()
+            torch.cuda.synchronize()
+            ms.append(s.elapsed_time(e))
+        out[name] = round(float(np.mean(ms)), 4)
+    out["note"] = "one PPO iteration = 1 rollout graph + n_epoch epoch graphs (+ permutation draw/copy per epoch)"
+    return out
+
+
 def count_launches(agent):
     """Hand-written kernel launches inside one PPO iteration (counted from the calls the agent makes)."""
     T, E, M = agent.n_steps, agent.n_epoch, agent.buffer_size // agent.batch_size
@@ -326,6 +346,7 @@ def run_ours(args):
     env_steps = agent.n_envs * agent.n_steps * args.steps * world
     value = env_steps / secs
     launches = count_launches(agent)
+    phases = time_phases(agent, flush) if world == 1 else None
     launches_per_step = {"updates": agent.n_epoch * (agent.buffer_size // agent.batch_size)}
     kernels = kernel_rooflines(agent, flush, peak, launches_per_step, with_c4=not args.no_c4, world=world) if rank == 0 or world > 1 else {}
     params = agent.learner._flat.n_params
@@ -369,6 +390,7 @@ def run_ours(args):
                      "note": "largest share of the step among the hand-written kernels; batches this small are "
                              "launch/latency-bound (working set is L2-resident) — see kernels.gae_c4_* for the HBM-bound shape"},
         "kernels": kernels,
+        "phases": phases,
         "cpu_baseline": cpu,
         "clocks": clocks,
         "last_info": {k: (float(v) if not isinstance(v, (int, float)) else v) for k, v in info.items()},
