@@ -163,8 +163,8 @@ def time_phases(agent, flush):
 def count_launches(agent):
     """Hand-written kernel launches inside one PPO iteration (counted from the calls the agent makes)."""
     T, E, M = agent.n_steps, agent.n_epoch, agent.buffer_size // agent.batch_size
-    per_rollout = T * (3 + 3) + 3 + 2 + 1  # sample + env_step + store + 3 fwd MLP epilogues per step, bootstrap fwd, GAE + pack, counter
-    per_update = 1 + 1 + 2 + 6             # gather_obs, loss, grad-norm + adam, 3 fwd + 3 bwd MLP epilogues
+    per_rollout = T * (3 + 5) + 5 + 2 + 1  # per step: sample, env_step, store, 3 bias+act, 2 head; bootstrap fwd; GAE + pack; counter
+    per_update = 1 + 1 + 2 + 5 + 3         # gather, loss, grad-norm + adam, fwd: 3 bias+act + 2 head, bwd: 2 head+act + 1 act+bias
     return per_rollout + E * M * per_update
 
 
@@ -252,8 +252,15 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
     dzb, dbb = torch.empty_like(dyb), torch.empty(H, device="cuda")
     bias = torch.randn(H, device="cuda")
     ws32 = torch.zeros(4 + 592 * 1024, dtype=torch.float32, device="cuda")
-    add("mlp_bias_act_fwd", lambda: ops.bias_act_fwd(yb, bias, 0.01), B * H * 8, 3 * launches_per_step["updates"])
-    add("mlp_act_bias_bwd", lambda: ops.act_bias_bwd(dyb, yb, 0.01, dzb, dbb, ws32), B * H * 12, 3 * launches_per_step["updates"])
+    A_out = 1 if gauss else 2
+    w2, b2 = torch.randn((A_out, H), device="cuda"), torch.randn(A_out, device="cuda")
+    hout, dout = torch.empty((B, A_out), device="cuda"), torch.randn((B, A_out), device="cuda")
+    dw2, db2 = torch.empty_like(w2), torch.empty_like(b2)
+    upd = launches_per_step["updates"]
+    add("mlp_bias_act_fwd", lambda: ops.bias_act_fwd(yb, bias, 0.01), B * H * 8, 3 * upd)
+    add("mlp_head_fwd", lambda: ops.head_fwd(yb, w2, b2, hout), B * (H + A_out) * 4, 2 * upd)
+    add("mlp_head_bwd_act", lambda: ops.head_bwd_act(dout, yb, w2, 0.01, dzb, dbb, dw2, db2, ws32), B * (2 * H + A_out) * 4, 2 * upd)
+    add("mlp_act_bias_bwd", lambda: ops.act_bias_bwd(dyb, yb, 0.01, dzb, dbb, ws32), B * H * 12, 1 * upd)
     snap = agent._snapshot()
     add("clip_adam", lambda: lr.stage_optimizer(), lr._flat.n * (4 + 16 + 12), launches_per_step["updates"])
     agent._restore(snap)

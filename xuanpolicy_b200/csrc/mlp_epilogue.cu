@@ -146,10 +146,13 @@ constexpr int kHeadMaxA = 4;
 constexpr int kHeadMaxC = 4;   // float4 column groups per thread in head_fwd (H <= 512)
 constexpr int kHeadBlock = 512;
 
+constexpr int kHeadRows = 4;   // rows in flight per lane group
+
 __global__ void __launch_bounds__(kEpiBlock)
     head_fwd_kernel(const float4* __restrict__ h, const float4* __restrict__ W, const float* __restrict__ bias,
                     float* __restrict__ out, int64_t B, int H4, int A, int G) {
-    // a group of G lanes (power of two <= 32, H4 % G == 0) owns a row; lane j covers column groups j, j+G, ...
+    // a group of G lanes (power of two <= 32, H4 % G == 0) owns kHeadRows rows per iteration; lane j covers column
+    // groups j, j+G, ...; all row loads are issued before any arithmetic, then one shuffle tree per (row, output)
     const int lane = threadIdx.x & (G - 1);
     const int per = H4 / G;
     float4 w[kHeadMaxA][kHeadMaxC];
@@ -159,29 +162,32 @@ __global__ void __launch_bounds__(kEpiBlock)
         for (int k = 0; k < kHeadMaxC; ++k)
             w[a][k] = (a < A && k < per) ? W[a * H4 + lane + k * G] : make_float4(0.f, 0.f, 0.f, 0.f);
     const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
-    const int sub = (threadIdx.x & 31) / G;                 // which row of the warp's 32/G rows
-    // warp-uniform trip count (full-mask shuffles below): iterate on the warp's first row
-    for (int64_t bw = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / G; bw < B; bw += groups) {
-        const int64_t b = bw + sub;
-        const bool live = b < B;
-        const int64_t row = live ? b : B - 1;
-        float acc[kHeadMaxA] = {0.f, 0.f, 0.f, 0.f};
+    const int sub = (threadIdx.x & 31) / G;                 // which of the warp's 32/G lane groups
+    // warp-uniform trip count (full-mask shuffles below): iterate on the warp's first lane group
+    for (int64_t bw = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / G; bw < B; bw += groups * kHeadRows) {
+        float4 v[kHeadRows][kHeadMaxC];
 #pragma unroll
-        for (int k = 0; k < kHeadMaxC; ++k) {
-            if (k < per) {
-                const float4 v = h[row * H4 + lane + k * G];
+        for (int u = 0; u < kHeadRows; ++u) {
+            const int64_t b = bw + sub + (int64_t)u * groups;
+            const int64_t row = b < B ? b : B - 1;
 #pragma unroll
-                for (int a = 0; a < kHeadMaxA; ++a)
-                    acc[a] += v.x * w[a][k].x + v.y * w[a][k].y + v.z * w[a][k].z + v.w * w[a][k].w;
-            }
+            for (int k = 0; k < kHeadMaxC; ++k)
+                if (k < per) v[u][k] = h[row * H4 + lane + k * G];
         }
 #pragma unroll
-        for (int a = 0; a < kHeadMaxA; ++a)
-            for (int o = G >> 1; o > 0; o >>= 1) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
-        if (lane == 0 && live) {
+        for (int u = 0; u < kHeadRows; ++u) {
+            const int64_t b = bw + sub + (int64_t)u * groups;
 #pragma unroll
-            for (int a = 0; a < kHeadMaxA; ++a)
-                if (a < A) out[b * A + a] = acc[a] + bias[a];
+            for (int a = 0; a < kHeadMaxA; ++a) {
+                if (a < A) {                                  // A is uniform: no shuffles for unused outputs
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < kHeadMaxC; ++k)
+                        if (k < per) acc += v[u][k].x * w[a][k].x + v[u][k].y * w[a][k].y + v[u][k].z * w[a][k].z + v[u][k].w * w[a][k].w;
+                    for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (lane == 0 && b < B) out[b * A + a] = acc + bias[a];
+                }
+            }
         }
     }
 }
