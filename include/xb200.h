@@ -243,6 +243,44 @@ int xb_head_bwd_act(const float* dout, const float* y, const float* W2, float sl
 int xb_bias_act_fwd(float* y, const float* bias, float slope, int64_t B, int H, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Dense layers of the policy/value MLP at large batch on the tcgen05 tensor cores with fp32-level accuracy
+ * ("3xTF32": x = hi + lo split, three kind::tf32 MMAs per k-step, fp32 accumulation in TMEM; csrc/dense_tc.cu).
+ * Replace the cuBLAS SIMT sgemm calls torch issues for Basic_MLP / ActorNet / CriticNet forward
+ * (xuance/torch/representations/mlp.py:49-51, policies/categorical.py:26-32,48-54, policies/gaussian.py:17-24,41-48)
+ * and for their autograd backward under PPOCLIP_Learner.update (ppoclip_learner.py:47).
+ * All matrices fp32 row-major, 16-byte aligned.  N (layer width) in {64, 128, 256}; K % 32 == 0, 32 <= K <= 256.
+ *   xb_dense_split_weights  W [N][K] -> hi, lo [N][K] (TF32-representable hi, exact remainder lo) and, when thi != NULL,
+ *                           their transposes into thi/tlo [K][ldt] at column offset toff (the dgrad operand; actor and
+ *                           critic layers are concatenated along the reduction dimension).
+ *   xb_dense_fwd            Y[M][N] = leaky_relu(X[M][K] . W^T + bias);  optionally the narrow head that follows it:
+ *                           head_out[M][n_head] = Y . head_w[n_head][N]^T + head_b   (n_head in {0, 1, 2}).
+ *                           b_resident != 0 keeps the whole weight operand in shared memory when it fits.
+ *   xb_dense_dgrad          dZ1[M][N] = ([dz0 | dz1] . [W0 ; W1]) * leaky'(H1)   with the A operand generated on the fly:
+ *                           dz_s[r][k] = (sum_j dout_s[r][j] w2_s[j][k]) * leaky'(Y_s[r][k])   (s = actor, critic),
+ *                           i.e. the backward of  H1 -> {Linear+LeakyReLU -> head}_s  without materialising dz_s.
+ *                           Wthi/Wtlo: [N][K0+K1] from xb_dense_split_weights.  Y1 == NULL drops the second source.
+ * ---------------------------------------------------------------------------------------------------------- */
+int xb_dense_split_weights(const float* W, int N, int K, float* hi, float* lo, float* thi, float* tlo, int ldt,
+                           int toff, xb_stream_t stream);
+int xb_dense_fwd(const float* X, int64_t M, int K, const float* Whi, const float* Wlo, int N, const float* bias,
+                 float slope, float* Y, const float* head_w, const float* head_b, int n_head, float* head_out,
+                 int b_resident, xb_stream_t stream);
+/*   xb_dense_wgrad          weight gradients of {Linear(H_in,H_out)+LeakyReLU -> head}_s for s = actor, critic in one launch:
+ *                           dW_s = dz_s^T X, db_s = colsum(dz_s) (dz_s generated on the fly as in xb_dense_dgrad),
+ *                           dw2_s[j] = sum_b dout_s[b][j] Y_s[b][:], db2_s[j] = sum_b dout_s[b][j].
+ *                           The reduction runs over the batch (MN-major tcgen05 operands straight from the row-major
+ *                           activations); per-CTA partials are summed in a fixed order (deterministic).
+ *                           H_out, H_in in {128, 256}.  workspace: xb_dense_wgrad_workspace_floats(H_in) floats. */
+int xb_dense_wgrad_workspace_floats(int H_in);
+int xb_dense_wgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, const float* Y1, const float* dout1,
+                   const float* w2_1, int nh1, const float* X, int64_t B, int H_out, int H_in, float slope,
+                   float* workspace, float* dW0, float* db0, float* dw2_0, float* db2_0, float* dW1, float* db1,
+                   float* dw2_1, float* db2_1, xb_stream_t stream);
+int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, int K0, const float* Y1,
+                   const float* dout1, const float* w2_1, int nh1, int K1, int64_t M, const float* Wthi,
+                   const float* Wtlo, int N, const float* H1, float slope, float* dZ1, xb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * HOST helper (host pointers, runs on the calling CPU thread; releases nothing on the device).
  * Uniform random permutation of 0..n-1 into out[n] (a pinned staging buffer): the host side of the minibatch
  * index feed, replacing np.random.shuffle(indexes) in PPOCLIP_Agent.train (ppoclip_agent.py:76-78).

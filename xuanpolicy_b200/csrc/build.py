@@ -28,8 +28,9 @@ SOURCES = {
     "host_utils.cu": [],
     "mlp_epilogue.cu": [],
     "normalize.cu": [],
+    "dense_tc.cu": [],
 }
-HEADERS = ["common.cuh", "crtrig.cuh", "crtrig_consts.inc", os.path.join("..", "..", "include", "xb200.h")]
+HEADERS = ["common.cuh", "sm100.cuh", "crtrig.cuh", "crtrig_consts.inc", os.path.join("..", "..", "include", "xb200.h")]
 
 
 def _stale(target, deps):

@@ -1,0 +1,810 @@
+// dense_tc.cu — the policy/value MLP's dense layers at large batch on the 5th-generation tensor cores (tcgen05),
+// with fp32-level accuracy ("3xTF32": x = hi + lo, x*w ~= hi*whi + hi*wlo + lo*whi, fp32 accumulate in TMEM).
+//
+// Replaces, for the large-batch PPO update / rollout forward, the cuBLAS SIMT sgemm calls torch issues for
+//   Basic_MLP.forward                      xuance/torch/representations/mlp.py:49-51
+//   ActorNet/CriticNet.forward             xuance/torch/policies/categorical.py:26-32,48-54; gaussian.py:17-24,41-48
+// and their autograd backward inside PPOCLIP_Learner.update (ppoclip_learner.py:47-48: loss.backward()).
+// The loss tolerance (1e-4 relative in strict fp32) rules out plain TF32; the split keeps ~2^-21 relative error
+// per product while running on the tensor pipe instead of the 74 TFLOP/s fp32 SIMT pipe.
+//
+// Kernel structure (one CTA per SM, persistent over 128-row tiles of the batch, 10 warps):
+//   warp 8      TMA producer   : cp.async.bulk.tensor 2D boxes [rows][32 fp32] (128 B rows, SWIZZLE_128B) into a ring
+//   warps 4-7   operand warps  : turn the raw tile into the MMA's A operand in place (hi) + a second buffer (lo);
+//                                for the backward kernels the raw tile is the saved activation y and the operand is
+//                                dz = (dout . w2) * leaky_relu'(y), generated on the fly (never materialised in HBM)
+//   warp 9      MMA issuer     : one thread issues tcgen05.mma.kind::tf32 (M=128, N<=256, K=8) x3 per k-step,
+//                                tcgen05.commit releases ring slots / publishes the accumulator
+//   warps 0-3   epilogue       : tcgen05.ld the 128 x N fp32 accumulator (double-buffered in TMEM so the next
+//                                tile's MMAs overlap), bias + LeakyReLU (+ fused narrow head) / activation mask, store
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace xb {
+namespace dense {
+
+using namespace sm100;
+
+constexpr int BM = 128;                 // batch rows per tile (UMMA M)
+constexpr int BK = 32;                  // fp32 per k-block = one 128-byte swizzle span
+constexpr int kATile = BM * BK * 4;     // 16 KB
+constexpr int kThreads = 320;
+constexpr int kMiscBytes = 9216;
+constexpr int kMaxSmem = 232448;        // 227 KB opt-in limit per CTA
+
+enum { MODE_FWD = 0, MODE_DGRAD = 1 };
+
+struct KParams {
+    int64_t M;          // rows of the batch
+    int KB;             // number of 32-wide k-blocks
+    int kb_split;       // DGRAD: k-blocks [0, kb_split) read source 0, the rest source 1 (actor | critic)
+    int stages;         // raw ring depth
+    int lo_bufs;        // lo ring depth
+    float slope;
+    // FWD epilogue: Y = leaky(acc + bias); optional head_out[r][j] = Y[r][:] . head_w[j][:] + head_b[j]
+    const float* bias;
+    float* Y;
+    const float* head_w;
+    const float* head_b;
+    int n_head;
+    float* head_out;
+    // DGRAD operand: dz_s[r][k] = (sum_j dout_s[r][j] * w2_s[j][k]) * leaky'(y_s[r][k]);  epilogue: dZ1 = acc * leaky'(H1)
+    const float* dout0;
+    const float* w2_0;
+    int nh0;
+    const float* dout1;
+    const float* w2_1;
+    int nh1;
+    const float* H1;
+    float* dZ1;
+};
+
+// byte offset of logical 16-byte chunk c (0..7) of row r inside a [rows][128 B] SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+// same for the 32-byte-atom flavour (SWIZZLE_128B_ATOM_32B): 32-byte chunk index XOR (row & 3)
+__device__ __forceinline__ uint32_t sw32_off(int r, int c) {
+    return (uint32_t)(r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4)));
+}
+
+template <int N, bool B_RES, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+    dense_kmajor_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                        const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+                        const KParams p) {
+    constexpr int kBTile = N * BK * 4;                  // one k-block of the weight operand, hi or lo
+    constexpr int kTmemCols = 2 * N;                    // double-buffered accumulator (power of two for N in {64,128,256})
+    constexpr uint32_t kIdesc = umma_idesc_tf32(BM, N, 0, 0);
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int S = p.stages, L = p.lo_bufs, KB = p.KB;
+    const uint32_t bres = base;                                              // [2][KB][kBTile] when B_RES
+    const uint32_t ring = base + (B_RES ? 2u * KB * kBTile : 0u);
+    const uint32_t stage_bytes = kATile + (B_RES ? 0 : 2 * kBTile);
+    const uint32_t lo_ring = ring + (uint32_t)S * stage_bytes;
+    const uint32_t misc = lo_ring + (uint32_t)L * kATile;
+    // barriers
+    const uint32_t bar_full = misc, bar_conv = misc + 64, bar_empty = misc + 128, bar_loempty = misc + 192;
+    const uint32_t bar_tfull = misc + 224, bar_tempty = misc + 240, bar_bfull = misc + 256;
+    const uint32_t tmem_slot = misc + 264;
+    unsigned char* misc_ptr = smem_raw + (misc - smem_u32(smem_raw));
+    float* sf = reinterpret_cast<float*>(misc_ptr + 512);                    // per-mode float scratch (<= 7.5 KB)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_tiles = (p.M + BM - 1) / BM;
+
+    // ---------------------------------------------------------------- one-time setup
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_conv + 8 * s, 4);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int j = 0; j < L; ++j) mbar_init(bar_loempty + 8 * j, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 4);
+        }
+        mbar_init(bar_bfull, 1);
+        mbar_fence_init();
+    }
+    if (warp == 9) tmem_alloc<kTmemCols>(tmem_slot);
+    if (MODE == MODE_FWD) {
+        // sf: bias[N] | head_w[2][N]
+        for (int i = threadIdx.x; i < N; i += kThreads) {
+            sf[i] = p.bias ? p.bias[i] : 0.f;
+            sf[N + i] = p.n_head > 0 ? p.head_w[i] : 0.f;
+            sf[2 * N + i] = p.n_head > 1 ? p.head_w[N + i] : 0.f;
+        }
+    } else {
+        // sf: w2[src][head][256] (4 x 256 floats) | dout[2][128][2] staged per tile by the operand warps
+        const int K0 = p.kb_split * BK, K1 = (KB - p.kb_split) * BK;
+        for (int i = threadIdx.x; i < 256; i += kThreads) {
+            sf[i] = (i < K0 && p.nh0 > 0) ? p.w2_0[i] : 0.f;
+            sf[256 + i] = (i < K0 && p.nh0 > 1) ? p.w2_0[K0 + i] : 0.f;
+            sf[512 + i] = (i < K1 && p.nh1 > 0) ? p.w2_1[i] : 0.f;
+            sf[768 + i] = (i < K1 && p.nh1 > 1) ? p.w2_1[K1 + i] : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 8) {
+        // ============================================================ TMA producer
+        if (lane == 0) {
+            tma_prefetch_desc(&map_a0);
+            tma_prefetch_desc(&map_bhi);
+            tma_prefetch_desc(&map_blo);
+            if (MODE == MODE_DGRAD) tma_prefetch_desc(&map_a1);
+            if (B_RES) {
+                mbar_arrive_expect_tx(bar_bfull, 2u * KB * kBTile);
+                for (int kb = 0; kb < KB; ++kb) {
+                    tma_load_2d(bres + kb * kBTile, &map_bhi, kb * BK, 0, bar_bfull);
+                    tma_load_2d(bres + (KB + kb) * kBTile, &map_blo, kb * BK, 0, bar_bfull);
+                }
+            }
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const uint32_t s = it % S, ph = (it / S) & 1;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    const uint32_t st = ring + s * stage_bytes;
+                    mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
+                    const bool src1 = (MODE == MODE_DGRAD) && kb >= p.kb_split;
+                    const int kcol = (src1 ? kb - p.kb_split : kb) * BK;
+                    tma_load_2d(st, src1 ? &map_a1 : &map_a0, kcol, (int)(tile * BM), bar_full + 8 * s);
+                    if (!B_RES) {
+                        tma_load_2d(st + kATile, &map_bhi, kb * BK, 0, bar_full + 8 * s);
+                        tma_load_2d(st + kATile + kBTile, &map_blo, kb * BK, 0, bar_full + 8 * s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ============================================================ MMA issuer
+        if (B_RES) mbar_wait(bar_bfull, 0);
+        uint32_t it = 0, lt = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
+            mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * N;
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const uint32_t s = it % S, ph = (it / S) & 1, j = it % L;
+                mbar_wait(bar_full + 8 * s, ph);
+                mbar_wait(bar_conv + 8 * s, ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t st = ring + s * stage_bytes;
+                    const uint32_t a_hi = st, a_lo = lo_ring + j * kATile;
+                    const uint32_t b_hi = B_RES ? bres + kb * kBTile : st + kATile;
+                    const uint32_t b_lo = B_RES ? bres + (KB + kb) * kBTile : st + kATile + kBTile;
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint64_t da_hi = umma_desc_sw128(a_hi + k * 32, 16, 1024);
+                        const uint64_t da_lo = umma_desc_sw128(a_lo + k * 32, 16, 1024);
+                        const uint64_t db_hi = umma_desc_sw128(b_hi + k * 32, 16, 1024);
+                        const uint64_t db_lo = umma_desc_sw128(b_lo + k * 32, 16, 1024);
+                        mma_tf32_ss(d_tmem, da_lo, db_hi, kIdesc, (kb | k) != 0);
+                        mma_tf32_ss(d_tmem, da_hi, db_lo, kIdesc, 1);
+                        mma_tf32_ss(d_tmem, da_hi, db_hi, kIdesc, 1);
+                    }
+                    mma_commit(bar_empty + 8 * s);
+                    mma_commit(bar_loempty + 8 * j);
+                    if (kb == KB - 1) mma_commit(bar_tfull + 8 * acc);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        // ============================================================ operand warps (128 threads)
+        const int t = threadIdx.x - 128;
+        const int c = t & 7, r0 = t >> 3;                 // logical 16-byte chunk, first row; rows r0 + 16 i
+        float* sdout = sf + 1024;                          // DGRAD: [2 tile parities][128 rows][2 src][2 heads]
+        uint32_t it = 0, lt = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            if (MODE == MODE_DGRAD) {
+                const int64_t row = tile * BM + t;
+                float* d = sdout + (lt & 1) * 512 + t * 4;
+                const bool ok = row < p.M;
+                d[0] = (ok && p.nh0 > 0) ? p.dout0[row * p.nh0] : 0.f;
+                d[1] = (ok && p.nh0 > 1) ? p.dout0[row * p.nh0 + 1] : 0.f;
+                d[2] = (ok && p.nh1 > 0) ? p.dout1[row * p.nh1] : 0.f;
+                d[3] = (ok && p.nh1 > 1) ? p.dout1[row * p.nh1 + 1] : 0.f;
+                bar_sync_named(1, 128);
+            }
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const uint32_t s = it % S, ph = (it / S) & 1, j = it % L;
+                mbar_wait(bar_full + 8 * s, ph);
+                mbar_wait(bar_loempty + 8 * j, ((it / L) & 1) ^ 1);
+                const uint32_t a_raw = ring + s * stage_bytes, a_lo = lo_ring + j * kATile;
+                float w0[4] = {0, 0, 0, 0}, w1[4] = {0, 0, 0, 0};
+                int src = 0;
+                if (MODE == MODE_DGRAD) {
+                    src = kb >= p.kb_split;
+                    const int kcol = (src ? kb - p.kb_split : kb) * BK + 4 * c;
+                    const float* w = sf + src * 512 + kcol;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { w0[q] = w[q]; w1[q] = w[256 + q]; }
+                }
+                float4 xs[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xs[i] = lds128(a_raw + sw128_off(r0 + 16 * i, c));   // 8 loads in flight
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = r0 + 16 * i;
+                    const uint32_t off = sw128_off(r, c);
+                    float4 x = xs[i];
+                    if (MODE == MODE_DGRAD) {
+                        const float* d = sdout + (lt & 1) * 512 + r * 4 + src * 2;
+                        const float d0 = d[0], d1 = d[1];
+                        x.x = (d0 * w0[0] + d1 * w1[0]) * (x.x > 0.f ? 1.f : p.slope);
+                        x.y = (d0 * w0[1] + d1 * w1[1]) * (x.y > 0.f ? 1.f : p.slope);
+                        x.z = (d0 * w0[2] + d1 * w1[2]) * (x.z > 0.f ? 1.f : p.slope);
+                        x.w = (d0 * w0[3] + d1 * w1[3]) * (x.w > 0.f ? 1.f : p.slope);
+                    }
+                    float4 hi, lo;
+                    split_tf32(x.x, hi.x, lo.x);
+                    split_tf32(x.y, hi.y, lo.y);
+                    split_tf32(x.z, hi.z, lo.z);
+                    split_tf32(x.w, hi.w, lo.w);
+                    sts128(a_raw + off, hi);
+                    sts128(a_lo + off, lo);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+            }
+        }
+    } else {
+        // ============================================================ epilogue warps 0-3 (TMEM lanes 32w..32w+31)
+        uint32_t lt = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
+            const int64_t row = tile * BM + warp * 32 + lane;
+            const bool ok = row < p.M;
+            mbar_wait(bar_tfull + 8 * acc, aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * N;
+            float h0 = 0.f, h1 = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < N / 32; ++cc) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + cc * 32, v);
+                float4 m[8];
+                if (MODE == MODE_DGRAD) {
+                    const float4* hp = reinterpret_cast<const float4*>(p.H1 + row * N + cc * 32);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) m[q] = ok ? __ldg(hp + q) : make_float4(0, 0, 0, 0);
+                }
+                tmem_ld_wait();
+                float* out = (MODE == MODE_FWD ? p.Y : p.dZ1) + row * N + cc * 32;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 f = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                           __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                    if (MODE == MODE_FWD) {
+                        const float* b = sf + cc * 32 + 4 * q;
+                        f.x += b[0]; f.y += b[1]; f.z += b[2]; f.w += b[3];
+                        f.x = f.x > 0.f ? f.x : f.x * p.slope;
+                        f.y = f.y > 0.f ? f.y : f.y * p.slope;
+                        f.z = f.z > 0.f ? f.z : f.z * p.slope;
+                        f.w = f.w > 0.f ? f.w : f.w * p.slope;
+                        const float* w = b + N;
+                        h0 += f.x * w[0] + f.y * w[1] + f.z * w[2] + f.w * w[3];
+                        h1 += f.x * w[N] + f.y * w[N + 1] + f.z * w[N + 2] + f.w * w[N + 3];
+                    } else {
+                        f.x *= m[q].x > 0.f ? 1.f : p.slope;
+                        f.y *= m[q].y > 0.f ? 1.f : p.slope;
+                        f.z *= m[q].z > 0.f ? 1.f : p.slope;
+                        f.w *= m[q].w > 0.f ? 1.f : p.slope;
+                    }
+                    if (ok) reinterpret_cast<float4*>(out)[q] = f;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            if (MODE == MODE_FWD && ok) {
+                if (p.n_head > 0) p.head_out[row * p.n_head] = h0 + p.head_b[0];
+                if (p.n_head > 1) p.head_out[row * p.n_head + 1] = h1 + p.head_b[1];
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- weight preparation
+// W [N][K] row-major -> hi/lo [N][K] (forward operand) and, transposed, hi/lo rows of Wt [K][ldt] at column offset
+// `toff` (dgrad operand: dX = dZ . W needs W^T K-major; actor and critic are concatenated along the reduction dim).
+__global__ void split_weights_kernel(const float* __restrict__ W, int N, int K, float* __restrict__ hi,
+                                     float* __restrict__ lo, float* __restrict__ thi, float* __restrict__ tlo, int ldt,
+                                     int toff) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * K) return;
+    const int n = i / K, k = i - n * K;
+    float h, l;
+    split_tf32(W[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
+    if (thi) {
+        thi[(int64_t)k * ldt + toff + n] = h;
+        tlo[(int64_t)k * ldt + toff + n] = l;
+    }
+}
+
+template <int N, bool B_RES, int MODE>
+static int launch_kmajor(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mbhi, const CUtensorMap& mblo,
+                         KParams p, cudaStream_t s) {
+    const int kBTile = N * BK * 4;
+    const int bres = B_RES ? 2 * p.KB * kBTile : 0;
+    const int stage = kATile + (B_RES ? 0 : 2 * kBTile);
+    const int avail = kMaxSmem - 1024 - kMiscBytes - bres;
+    // pick ring depths: at least 2 raw stages + 1 lo buffer; prefer 2 lo buffers, then as many raw stages as fit (<= 6)
+    int L = 2, S = (avail - L * kATile) / stage;
+    if (S < 2) { L = 1; S = (avail - L * kATile) / stage; }
+    if (S < 2) return XB_E_UNSUPPORTED;
+    if (S > 6) S = 6;
+    p.stages = S;
+    p.lo_bufs = L;
+    const int smem = 1024 + bres + S * stage + L * kATile + kMiscBytes;
+    auto kern = dense_kmajor_kernel<N, B_RES, MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        XB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        attr_set = true;
+    }
+    const int64_t tiles = (p.M + BM - 1) / BM;
+    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    kern<<<grid, kThreads, smem, s>>>(ma0, ma1, mbhi, mblo, p);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int MODE>
+static int dispatch_kmajor(int N, bool bres, const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mbhi,
+                           const CUtensorMap& mblo, const KParams& p, cudaStream_t s) {
+    const int kBTile = N * BK * 4;
+    if (bres && (kMaxSmem - 1024 - kMiscBytes - 2 * p.KB * kBTile) < 2 * kATile + kATile) bres = false;
+    switch (N) {
+        case 64:
+            return bres ? launch_kmajor<64, true, MODE>(ma0, ma1, mbhi, mblo, p, s)
+                        : launch_kmajor<64, false, MODE>(ma0, ma1, mbhi, mblo, p, s);
+        case 128:
+            return bres ? launch_kmajor<128, true, MODE>(ma0, ma1, mbhi, mblo, p, s)
+                        : launch_kmajor<128, false, MODE>(ma0, ma1, mbhi, mblo, p, s);
+        case 256:
+            return launch_kmajor<256, false, MODE>(ma0, ma1, mbhi, mblo, p, s);
+        default:
+            return XB_E_UNSUPPORTED;
+    }
+}
+
+// ================================================================================================ weight gradients
+// dW[m][n] = sum_b dz[b][m] * x[b][n],  db[m] = sum_b dz[b][m]   for the hidden layer of the actor and of the critic,
+// plus the narrow head's gradients dw2[j][m] = sum_b dout[b][j] * y[b][m], db2[j] = sum_b dout[b][j].
+// The reduction runs over the BATCH, so both MMA operands are "MN-major": a k-block is 32 batch rows, each a 128-byte
+// row of 32 features, exactly what TMA delivers from the row-major activations (no transpose anywhere).
+// dz is generated on the fly from the saved activation y like in the dgrad kernel; db comes out of the same MMAs
+// through a constant "ones" operand (N = 16 block whose first column is 1).
+// Grid: CTA i works on job (i % n_jobs) = (source, 128-row half of H_out) and on a contiguous slice of the batch;
+// each CTA writes its partial [128][H_in + 4] (column H_in = db) and a deterministic reduce kernel sums the slices.
+struct WParams {
+    int64_t B;
+    int n_jobs;       // sources x (H_out / 128)
+    int halves;       // H_out / 128
+    int H_out;
+    float slope;
+    int stages, lo_bufs;
+    const float* dout[2];
+    const float* w2[2];
+    int nh[2];
+    float* part;       // [grid][128][HIN + 4]
+    float* head_part;  // [grid][2][128]   dw2 partial of this CTA's 128 features
+    float* db2_part;   // [grid][2]
+};
+
+template <int HIN>
+__global__ void __launch_bounds__(kThreads, 1)
+    dense_wgrad_kernel(const __grid_constant__ CUtensorMap map_y0, const __grid_constant__ CUtensorMap map_y1,
+                       const __grid_constant__ CUtensorMap map_x, const WParams p) {
+    constexpr int NBX = HIN / 32;                  // 32-feature boxes of x
+    constexpr int kBox = 32 * 128;                 // one box: 32 batch rows x 128 B
+    constexpr int kStage = 4 * kBox + NBX * kBox;  // dz operand (128 features) | x operand
+    constexpr int kTmemCols = (HIN + 16 <= 256) ? 256 : 512;
+    constexpr uint32_t kIdescMain = umma_idesc_tf32(128, HIN, 1, 1);
+    constexpr uint32_t kIdescBias = umma_idesc_tf32(128, 16, 1, 1);
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int S = p.stages, L = p.lo_bufs;
+    const uint32_t ring = base, lo_ring = ring + (uint32_t)S * kStage, misc = lo_ring + (uint32_t)L * kStage;
+    const uint32_t bar_full = misc, bar_conv = misc + 64, bar_empty = misc + 128, bar_loempty = misc + 192;
+    const uint32_t bar_tfull = misc + 224, tmem_slot = misc + 264;
+    const uint32_t ones = misc + 1024;             // 8 k-rows x 128 B, SWIZZLE_128B_ATOM_32B pattern, column 0 = 1.0
+    unsigned char* misc_ptr = smem_raw + (misc - smem_u32(smem_raw));
+    float* sf = reinterpret_cast<float*>(misc_ptr + 2048);   // head-gradient reduction scratch: [4 warps][2][128] + [4][2]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int job = blockIdx.x % p.n_jobs, q = blockIdx.x / p.n_jobs;
+    const int cj = (gridDim.x - job + p.n_jobs - 1) / p.n_jobs;          // CTAs working on this job
+    const int src = job / p.halves, m0 = (job % p.halves) * 128;
+    const int64_t nblk = (p.B + 31) / 32;
+    const int64_t blk0 = nblk * q / cj, blk1 = nblk * (q + 1) / cj;
+    const int nkb = (int)(blk1 - blk0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_conv + 8 * s, 4);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int j = 0; j < L; ++j) mbar_init(bar_loempty + 8 * j, 1);
+        mbar_init(bar_tfull, 1);
+        mbar_fence_init();
+    }
+    if (warp == 9) tmem_alloc<kTmemCols>(tmem_slot);
+    if (threadIdx.x < 256) {                       // ones block: 8 rows x 32 floats
+        const int r = threadIdx.x >> 5, e = threadIdx.x & 31;
+        float* o = reinterpret_cast<float*>(misc_ptr + 1024);
+        o[r * 32 + e] = (e == ((r & 3) << 3)) ? 1.0f : 0.0f;   // logical element 0 sits in 32-byte chunk (0 ^ (r & 3))
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 8) {
+        // ============================================================ TMA producer
+        if (lane == 0) {
+            const CUtensorMap* my = src ? &map_y1 : &map_y0;
+            tma_prefetch_desc(my);
+            tma_prefetch_desc(&map_x);
+            for (int it = 0; it < nkb; ++it) {
+                const uint32_t s = it % S, ph = (it / S) & 1;
+                mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                const uint32_t st = ring + s * kStage;
+                mbar_arrive_expect_tx(bar_full + 8 * s, kStage);
+                const int row = (int)((blk0 + it) * 32);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) tma_load_2d(st + g * kBox, my, m0 + g * 32, row, bar_full + 8 * s);
+#pragma unroll
+                for (int g = 0; g < NBX; ++g) tma_load_2d(st + (4 + g) * kBox, &map_x, g * 32, row, bar_full + 8 * s);
+            }
+        }
+    } else if (warp == 9) {
+        // ============================================================ MMA issuer
+        for (int it = 0; it < nkb; ++it) {
+            const uint32_t s = it % S, ph = (it / S) & 1, j = it % L;
+            mbar_wait(bar_full + 8 * s, ph);
+            mbar_wait(bar_conv + 8 * s, ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_hi = ring + s * kStage, b_hi = a_hi + 4 * kBox;
+                const uint32_t a_lo = lo_ring + j * kStage, b_lo = a_lo + 4 * kBox;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {         // 8 batch rows per MMA
+                    const uint64_t da_hi = umma_desc_sw128_base32(a_hi + k * 1024, kBox, 512);
+                    const uint64_t da_lo = umma_desc_sw128_base32(a_lo + k * 1024, kBox, 512);
+                    const uint64_t db_hi = umma_desc_sw128_base32(b_hi + k * 1024, kBox, 512);
+                    const uint64_t db_lo = umma_desc_sw128_base32(b_lo + k * 1024, kBox, 512);
+                    const uint64_t d_one = umma_desc_sw128_base32(ones, kBox, 512);
+                    const uint32_t first = (it | k) != 0;
+                    mma_tf32_ss(tmem_base, da_lo, db_hi, kIdescMain, first);
+                    mma_tf32_ss(tmem_base, da_hi, db_lo, kIdescMain, 1);
+                    mma_tf32_ss(tmem_base, da_hi, db_hi, kIdescMain, 1);
+                    mma_tf32_ss(tmem_base + HIN, da_lo, d_one, kIdescBias, first);
+                    mma_tf32_ss(tmem_base + HIN, da_hi, d_one, kIdescBias, 1);
+                }
+                mma_commit(bar_empty + 8 * s);
+                mma_commit(bar_loempty + 8 * j);
+                if (it == nkb - 1) mma_commit(bar_tfull);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        // ============================================================ operand warps
+        const int t = threadIdx.x - 128;
+        const int w = t >> 5;                       // row group: rows 8w .. 8w+7 of the k-block
+        const int g = (t & 31) >> 3, c = t & 7;     // feature box, 16-byte chunk: features m0 + 32g + 4c .. +3
+        const int nh = src ? p.nh[1] : p.nh[0];
+        const float* dout = src ? p.dout[1] : p.dout[0];
+        const float* w2p = src ? p.w2[1] : p.w2[0];
+        float w2a[4], w2b[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int m = m0 + 32 * g + 4 * c + e;
+            w2a[e] = w2p[m];
+            w2b[e] = nh > 1 ? w2p[p.H_out + m] : 0.f;
+        }
+        float ga[4] = {0, 0, 0, 0}, gb[4] = {0, 0, 0, 0}, sa = 0.f, sb = 0.f;   // head-gradient accumulators
+        float d0[8], d1[8];
+        auto load_dout = [&](int it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t b = (blk0 + it) * 32 + 8 * w + i;
+                const bool ok = it < nkb && b < p.B;
+                d0[i] = ok ? __ldg(dout + b * nh) : 0.f;
+                d1[i] = (ok && nh > 1) ? __ldg(dout + b * nh + 1) : 0.f;
+            }
+        };
+        load_dout(0);
+        for (int it = 0; it < nkb; ++it) {
+            const uint32_t s = it % S, ph = (it / S) & 1, j = it % L;
+            float c0[8], c1[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { c0[i] = d0[i]; c1[i] = d1[i]; }
+            load_dout(it + 1);                       // prefetch the next k-block's head gradients
+            mbar_wait(bar_full + 8 * s, ph);
+            mbar_wait(bar_loempty + 8 * j, ((it / L) & 1) ^ 1);
+            const uint32_t raw = ring + s * kStage, lo_b = lo_ring + j * kStage;
+            float4 ys[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ys[i] = lds128(raw + g * kBox + sw32_off(8 * w + i, c));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = 8 * w + i;
+                const uint32_t off = g * kBox + sw32_off(r, c);
+                const float4 y = ys[i];
+                const float e0 = c0[i], e1 = c1[i];
+                ga[0] += e0 * y.x; ga[1] += e0 * y.y; ga[2] += e0 * y.z; ga[3] += e0 * y.w;
+                gb[0] += e1 * y.x; gb[1] += e1 * y.y; gb[2] += e1 * y.z; gb[3] += e1 * y.w;
+                sa += e0; sb += e1;
+                float4 dz;
+                dz.x = (e0 * w2a[0] + e1 * w2b[0]) * (y.x > 0.f ? 1.f : p.slope);
+                dz.y = (e0 * w2a[1] + e1 * w2b[1]) * (y.y > 0.f ? 1.f : p.slope);
+                dz.z = (e0 * w2a[2] + e1 * w2b[2]) * (y.z > 0.f ? 1.f : p.slope);
+                dz.w = (e0 * w2a[3] + e1 * w2b[3]) * (y.w > 0.f ? 1.f : p.slope);
+                float4 hi, lo;
+                split_tf32(dz.x, hi.x, lo.x);
+                split_tf32(dz.y, hi.y, lo.y);
+                split_tf32(dz.z, hi.z, lo.z);
+                split_tf32(dz.w, hi.w, lo.w);
+                sts128(raw + off, hi);
+                sts128(lo_b + off, lo);
+            }
+#pragma unroll
+            for (int gg = 0; gg < NBX / 4; ++gg) {   // x operand: plain split, same thread mapping per group of 4 boxes
+                float4 xs[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xs[i] = lds128(raw + (4 + 4 * gg + g) * kBox + sw32_off(8 * w + i, c));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t off = (4 + 4 * gg + g) * kBox + sw32_off(8 * w + i, c);
+                    const float4 x = xs[i];
+                    float4 hi, lo;
+                    split_tf32(x.x, hi.x, lo.x);
+                    split_tf32(x.y, hi.y, lo.y);
+                    split_tf32(x.z, hi.z, lo.z);
+                    split_tf32(x.w, hi.w, lo.w);
+                    sts128(raw + off, hi);
+                    sts128(lo_b + off, lo);
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+        }
+        // head gradients: sum the 4 row groups (warps) in a fixed order
+        float* hs = sf + w * 256;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            hs[32 * g + 4 * c + e] = ga[e];
+            hs[128 + 32 * g + 4 * c + e] = gb[e];
+        }
+        if ((t & 31) == 0) { sf[1024 + 2 * w] = sa; sf[1024 + 2 * w + 1] = sb; }
+        bar_sync_named(1, 128);
+        for (int i = t; i < 256; i += 128)
+            p.head_part[(int64_t)blockIdx.x * 256 + i] = (sf[i] + sf[256 + i]) + (sf[512 + i] + sf[768 + i]);
+        if (t < 2) p.db2_part[(int64_t)blockIdx.x * 2 + t] = (sf[1024 + t] + sf[1026 + t]) + (sf[1028 + t] + sf[1030 + t]);
+    } else {
+        // ============================================================ epilogue: partial [128][HIN + 4]
+        float* out = p.part + ((int64_t)blockIdx.x * 128 + warp * 32 + lane) * (HIN + 4);
+        if (nkb > 0) {
+            mbar_wait(bar_tfull, 0);
+            tc_fence_after();
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int cc = 0; cc < HIN / 32; ++cc) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + cc * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                reinterpret_cast<float4*>(out + cc * 32)[e] =
+                    nkb > 0 ? make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]),
+                                          __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + HIN - 16, v);      // columns HIN-16 .. HIN+15; element 16 is the bias column
+            tmem_ld_wait();
+            out[HIN] = nkb > 0 ? __uint_as_float(v[16]) : 0.f;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// Sums the per-CTA partials of the wgrad kernel in CTA order (deterministic) and scatters them to the parameter
+// gradients.  One block per (job, output row m); threads over the HIN + 1 columns.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ head_part,
+                                    const float* __restrict__ db2_part, int grid, int n_jobs, int halves, int HIN,
+                                    int H_out, float* dW0, float* db0, float* dw2_0, float* db2_0, int nh0, float* dW1,
+                                    float* db1, float* dw2_1, float* db2_1, int nh1) {
+    const int job = blockIdx.x / 128, r = blockIdx.x % 128;
+    const int src = job / halves, m = (job % halves) * 128 + r;
+    float* dW = src ? dW1 : dW0;
+    float* db = src ? db1 : db0;
+    float* dw2 = src ? dw2_1 : dw2_0;
+    float* db2 = src ? db2_1 : db2_0;
+    const int nh = src ? nh1 : nh0;
+    for (int n = threadIdx.x; n < HIN + 3; n += blockDim.x) {
+        float acc = 0.f;
+        if (n <= HIN) {
+            for (int cta = job; cta < grid; cta += n_jobs) acc += part[((int64_t)cta * 128 + r) * (HIN + 4) + n];
+            if (n < HIN) dW[(int64_t)m * HIN + n] = acc;
+            else db[m] = acc;
+        } else {
+            const int j = n - HIN - 1;               // head index 0 / 1
+            if (j < nh) {
+                for (int cta = job; cta < grid; cta += n_jobs) acc += head_part[(int64_t)cta * 256 + j * 128 + r];
+                dw2[(int64_t)j * H_out + m] = acc;
+                if (m == 0) {                        // db2: any one job of this source carries the full batch slice sum
+                    float s = 0.f;
+                    for (int cta = job; cta < grid; cta += n_jobs) s += db2_part[(int64_t)cta * 2 + j];
+                    db2[j] = s;
+                }
+            }
+        }
+    }
+}
+
+template <int HIN>
+static int launch_wgrad(const CUtensorMap& my0, const CUtensorMap& my1, const CUtensorMap& mx, WParams p, int grid,
+                        cudaStream_t s) {
+    const int stage = (4 + HIN / 32) * 4096;
+    const int avail = kMaxSmem - 1024 - kMiscBytes;
+    int L = 2, S = (avail - L * stage) / stage;
+    if (S < 2) { L = 1; S = (avail - L * stage) / stage; }
+    if (S < 2) return XB_E_UNSUPPORTED;
+    if (S > 6) S = 6;
+    p.stages = S;
+    p.lo_bufs = L;
+    const int smem = 1024 + (S + L) * stage + kMiscBytes;
+    auto kern = dense_wgrad_kernel<HIN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        XB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        attr_set = true;
+    }
+    kern<<<grid, kThreads, smem, s>>>(my0, my1, mx, p);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace dense
+}  // namespace xb
+
+using namespace xb;
+using namespace xb::dense;
+
+static inline bool al16(const void* q) { return ((uintptr_t)q & 15u) == 0; }
+
+extern "C" int xb_dense_split_weights(const float* W, int N, int K, float* hi, float* lo, float* thi, float* tlo,
+                                      int ldt, int toff, xb_stream_t stream) {
+    if (!W || !hi || !lo || N <= 0 || K <= 0 || (thi && !tlo)) return XB_E_BADARG;
+    const int n = N * K;
+    split_weights_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, N, K, hi, lo, thi, tlo, ldt, toff);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_dense_fwd(const float* X, int64_t M, int K, const float* Whi, const float* Wlo, int N,
+                            const float* bias, float slope, float* Y, const float* head_w, const float* head_b,
+                            int n_head, float* head_out, int b_resident, xb_stream_t stream) {
+    if (!X || !Whi || !Wlo || !Y || M <= 0) return XB_E_BADARG;
+    if (K % BK != 0 || K < BK || K > 256 || n_head < 0 || n_head > 2 || (n_head && (!head_w || !head_b || !head_out)))
+        return XB_E_UNSUPPORTED;
+    if (!al16(X) || !al16(Whi) || !al16(Wlo) || !al16(Y)) return XB_E_UNSUPPORTED;
+    CUtensorMap ma, mbhi, mblo;
+    if (!xb_make_map_f32_2d(&ma, X, M, K, K, BM, BK, 1) || !xb_make_map_f32_2d(&mbhi, Whi, N, K, K, N, BK, 1) ||
+        !xb_make_map_f32_2d(&mblo, Wlo, N, K, K, N, BK, 1))
+        return XB_E_DRIVER;
+    KParams p{};
+    p.M = M;
+    p.KB = K / BK;
+    p.kb_split = p.KB;
+    p.slope = slope;
+    p.bias = bias;
+    p.Y = Y;
+    p.head_w = head_w;
+    p.head_b = head_b;
+    p.n_head = n_head;
+    p.head_out = head_out;
+    return dispatch_kmajor<MODE_FWD>(N, b_resident != 0, ma, ma, mbhi, mblo, p, (cudaStream_t)stream);
+}
+
+extern "C" int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, int K0, const float* Y1,
+                              const float* dout1, const float* w2_1, int nh1, int K1, int64_t M, const float* Wthi,
+                              const float* Wtlo, int N, const float* H1, float slope, float* dZ1, xb_stream_t stream) {
+    if (!Y0 || !dout0 || !w2_0 || !Wthi || !Wtlo || !H1 || !dZ1 || M <= 0) return XB_E_BADARG;
+    if (K0 % BK != 0 || K0 < BK || K0 > 256 || nh0 < 1 || nh0 > 2) return XB_E_UNSUPPORTED;
+    if (Y1 && (K1 % BK != 0 || K1 < BK || K1 > 256 || nh1 < 1 || nh1 > 2 || !dout1 || !w2_1)) return XB_E_UNSUPPORTED;
+    if (!Y1) K1 = 0;
+    if (!al16(Y0) || !al16(Wthi) || !al16(Wtlo) || !al16(H1) || !al16(dZ1) || (Y1 && !al16(Y1))) return XB_E_UNSUPPORTED;
+    const int K = K0 + K1;
+    CUtensorMap ma0, ma1, mbhi, mblo;
+    if (!xb_make_map_f32_2d(&ma0, Y0, M, K0, K0, BM, BK, 1) ||
+        !xb_make_map_f32_2d(&ma1, Y1 ? Y1 : Y0, M, Y1 ? K1 : K0, Y1 ? K1 : K0, BM, BK, 1) ||
+        !xb_make_map_f32_2d(&mbhi, Wthi, N, K, K, N, BK, 1) || !xb_make_map_f32_2d(&mblo, Wtlo, N, K, K, N, BK, 1))
+        return XB_E_DRIVER;
+    KParams p{};
+    p.M = M;
+    p.KB = K / BK;
+    p.kb_split = K0 / BK;
+    p.slope = slope;
+    p.dout0 = dout0;
+    p.w2_0 = w2_0;
+    p.nh0 = nh0;
+    p.dout1 = dout1;
+    p.w2_1 = w2_1;
+    p.nh1 = Y1 ? nh1 : 0;
+    p.H1 = H1;
+    p.dZ1 = dZ1;
+    return dispatch_kmajor<MODE_DGRAD>(N, false, ma0, ma1, mbhi, mblo, p, (cudaStream_t)stream);
+}
+
+extern "C" int xb_dense_wgrad_workspace_floats(int H_in) { return kNumSMs * (128 * (H_in + 4) + 256 + 2); }
+
+extern "C" int xb_dense_wgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, const float* Y1,
+                              const float* dout1, const float* w2_1, int nh1, const float* X, int64_t B, int H_out,
+                              int H_in, float slope, float* workspace, float* dW0, float* db0, float* dw2_0,
+                              float* db2_0, float* dW1, float* db1, float* dw2_1, float* db2_1, xb_stream_t stream) {
+    if (!Y0 || !dout0 || !w2_0 || !X || !workspace || !dW0 || !db0 || !dw2_0 || !db2_0 || B <= 0) return XB_E_BADARG;
+    if ((H_out != 128 && H_out != 256) || (H_in != 128 && H_in != 256) || nh0 < 1 || nh0 > 2) return XB_E_UNSUPPORTED;
+    if (Y1 && (!dout1 || !w2_1 || !dW1 || !db1 || !dw2_1 || !db2_1 || nh1 < 1 || nh1 > 2)) return XB_E_BADARG;
+    if (!al16(Y0) || !al16(X) || !al16(workspace) || (Y1 && !al16(Y1))) return XB_E_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUtensorMap my0, my1, mx;
+    if (!xb_make_map_f32_2d(&my0, Y0, B, H_out, H_out, 32, 32, 2) ||
+        !xb_make_map_f32_2d(&my1, Y1 ? Y1 : Y0, B, H_out, H_out, 32, 32, 2) ||
+        !xb_make_map_f32_2d(&mx, X, B, H_in, H_in, 32, 32, 2))
+        return XB_E_DRIVER;
+    WParams p{};
+    p.B = B;
+    p.halves = H_out / 128;
+    p.n_jobs = (Y1 ? 2 : 1) * p.halves;
+    p.H_out = H_out;
+    p.slope = slope;
+    p.dout[0] = dout0; p.w2[0] = w2_0; p.nh[0] = nh0;
+    p.dout[1] = dout1; p.w2[1] = w2_1; p.nh[1] = Y1 ? nh1 : 0;
+    const int grid = kNumSMs;
+    p.part = workspace;
+    p.head_part = workspace + (int64_t)grid * 128 * (H_in + 4);
+    p.db2_part = p.head_part + (int64_t)grid * 256;
+    int rc = H_in == 128 ? launch_wgrad<128>(my0, my1, mx, p, grid, s) : launch_wgrad<256>(my0, my1, mx, p, grid, s);
+    if (rc) return rc;
+    wgrad_reduce_kernel<<<p.n_jobs * 128, 160, 0, s>>>(p.part, p.head_part, p.db2_part, grid, p.n_jobs, p.halves, H_in,
+                                                      H_out, dW0, db0, dw2_0, db2_0, nh0, dW1, db1, dw2_1, db2_1,
+                                                      Y1 ? nh1 : 0);
+    XB_LAUNCH_CHECK();
+    return 0;
+}

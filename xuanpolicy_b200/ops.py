@@ -186,3 +186,40 @@ def head_bwd_act(dout, y, weight2, slope, dz, db1, dw2, db2, workspace):
     B, H = y.shape
     _lib.call("xb_head_bwd_act", _p(dout, F32), _p(y, F32), _p(weight2, F32), float(slope), _p(dz, F32), _p(db1, F32),
               _p(dw2, F32), _p(db2, F32), _p(workspace, F32), B, H, weight2.shape[0], _stream())
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 dense layers
+def dense_split_weights(W, hi, lo, thi=None, tlo=None, toff=0):
+    N, K = W.shape
+    _lib.call("xb_dense_split_weights", _p(W, F32), N, K, _p(hi, F32), _p(lo, F32), _p(thi, F32), _p(tlo, F32),
+              thi.shape[1] if thi is not None else 0, toff, _stream())
+
+
+def dense_fwd(x, w_hi, w_lo, bias, slope, y, head_w=None, head_b=None, head_out=None, b_resident=True):
+    M, K = x.shape
+    N = w_hi.shape[0]
+    _lib.call("xb_dense_fwd", _p(x, F32), M, K, _p(w_hi, F32), _p(w_lo, F32), N, _p(bias, F32), float(slope), _p(y, F32),
+              _p(head_w, F32), _p(head_b, F32), head_w.shape[0] if head_w is not None else 0, _p(head_out, F32),
+              1 if b_resident else 0, _stream())
+
+
+def dense_dgrad(y0, dout0, w2_0, y1, dout1, w2_1, wt_hi, wt_lo, h1, slope, dz1):
+    M, K0 = y0.shape
+    _lib.call("xb_dense_dgrad", _p(y0, F32), _p(dout0, F32), _p(w2_0, F32), w2_0.shape[0], K0, _p(y1, F32),
+              _p(dout1, F32), _p(w2_1, F32), w2_1.shape[0] if w2_1 is not None else 0,
+              y1.shape[1] if y1 is not None else 0, M, _p(wt_hi, F32), _p(wt_lo, F32), wt_hi.shape[0], _p(h1, F32),
+              float(slope), _p(dz1, F32), _stream())
+
+
+def dense_wgrad_workspace(h_in, device):
+    n = _lib.load().xb_dense_wgrad_workspace_floats(int(h_in))
+    return torch.empty(n, dtype=F32, device=device)
+
+
+def dense_wgrad(y0, dout0, w2_0, y1, dout1, w2_1, x, slope, workspace, dW0, db0, dw2_0, db2_0, dW1=None, db1=None,
+                dw2_1=None, db2_1=None):
+    B, H_out = y0.shape
+    _lib.call("xb_dense_wgrad", _p(y0, F32), _p(dout0, F32), _p(w2_0, F32), w2_0.shape[0], _p(y1, F32), _p(dout1, F32),
+              _p(w2_1, F32), w2_1.shape[0] if w2_1 is not None else 0, _p(x, F32), B, H_out, x.shape[1], float(slope),
+              _p(workspace, F32), _p(dW0, F32), _p(db0, F32), _p(dw2_0, F32), _p(db2_0, F32), _p(dW1, F32), _p(db1, F32),
+              _p(dw2_1, F32), _p(db2_1, F32), _stream())
