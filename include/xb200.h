@@ -281,6 +281,19 @@ int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int n
                    const float* Wtlo, int N, const float* H1, float slope, float* dZ1, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * First (narrow-input) layer of the MLP, Linear(obs_dim, H) + LeakyReLU — Basic_MLP
+ * (xuance/torch/representations/mlp.py:40-51) — and its weight gradient; bandwidth-bound SIMT kernels (csrc/mlp_trunk.cu).
+ *   xb_mlp_trunk_fwd    h1[b][n] = leaky_relu(b0[n] + sum_i obs[b*ld + i] W0[n][i])     obs_dim <= 8, H % 4 == 0
+ *   xb_mlp_trunk_wgrad  dW0[n][i] = sum_b dz1[b][n] obs[b*ld + i],  db0[n] = sum_b dz1[b][n]   (deterministic two-stage sum)
+ * workspace: xb_mlp_trunk_wgrad_workspace_floats(obs_dim, H) floats.
+ * ---------------------------------------------------------------------------------------------------------- */
+int xb_mlp_trunk_fwd(const float* obs, int ld, int obs_dim, const float* W0, const float* b0, float slope, float* h1,
+                     int64_t B, int H, xb_stream_t stream);
+int xb_mlp_trunk_wgrad_workspace_floats(int obs_dim, int H);
+int xb_mlp_trunk_wgrad(const float* dz1, const float* obs, int ld, int obs_dim, float* workspace, float* dW0, float* db0,
+                       int64_t B, int H, xb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * HOST helper (host pointers, runs on the calling CPU thread; releases nothing on the device).
  * Uniform random permutation of 0..n-1 into out[n] (a pinned staging buffer): the host side of the minibatch
  * index feed, replacing np.random.shuffle(indexes) in PPOCLIP_Agent.train (ppoclip_agent.py:76-78).

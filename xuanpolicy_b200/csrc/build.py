@@ -16,7 +16,7 @@ OUT = os.path.join(PKG, "libxb200.so")
 OBJ = os.path.join(HERE, "_obj")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("XB_NVCC_EXTRA", "").split()
 SOURCES = {
     "api.cu": [],
     "env_classic.cu": ["-fmad=false"],
@@ -29,6 +29,7 @@ SOURCES = {
     "mlp_epilogue.cu": [],
     "normalize.cu": [],
     "dense_tc.cu": [],
+    "mlp_trunk.cu": [],
 }
 HEADERS = ["common.cuh", "sm100.cuh", "crtrig.cuh", "crtrig_consts.inc", os.path.join("..", "..", "include", "xb200.h")]
 

@@ -25,10 +25,20 @@ namespace dense {
 
 using namespace sm100;
 
+#ifdef XB_DENSE_TS   // debug build only: per-role clock64 timeline of CTA 0 ([4 roles][64 its][8 events])
+static long long* g_xb_ts_host = nullptr;
+#define XB_TS(role, it, ev) do { if (p.ts && blockIdx.x == 0 && (it) < 64) p.ts[((role) * 64 + (it)) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define XB_TS(role, it, ev) do { } while (0)
+#endif
+
 constexpr int BM = 128;                 // batch rows per tile (UMMA M)
 constexpr int BK = 32;                  // fp32 per k-block = one 128-byte swizzle span
 constexpr int kATile = BM * BK * 4;     // 16 KB
-constexpr int kThreads = 320;
+constexpr int kOperandWarps = 8;        // K-major kernels: warps 0-3 epilogue, 4-11 operand, 12 TMA producer, 13 MMA issuer
+constexpr int kProducerWarp = 4 + kOperandWarps, kMmaWarp = kProducerWarp + 1;
+constexpr int kThreads = (kMmaWarp + 1) * 32;
+constexpr int kWThreads = 320;          // wgrad kernel: warps 0-3 epilogue, 4-7 operand, 8 producer, 9 MMA
 constexpr int kMiscBytes = 9216;
 constexpr int kMaxSmem = 232448;        // 227 KB opt-in limit per CTA
 
@@ -40,7 +50,12 @@ struct KParams {
     int kb_split;       // DGRAD: k-blocks [0, kb_split) read source 0, the rest source 1 (actor | critic)
     int stages;         // raw ring depth
     int lo_bufs;        // lo ring depth
+    int out_bufs;       // epilogue staging tiles (1 or 2)
+    int h1_bufs;        // DGRAD mask tiles (1 or 2)
     float slope;
+#ifdef XB_DENSE_TS
+    long long* ts;
+#endif
     // FWD epilogue: Y = leaky(acc + bias); optional head_out[r][j] = Y[r][:] . head_w[j][:] + head_b[j]
     const float* bias;
     float* Y;
@@ -70,24 +85,27 @@ template <int N, bool B_RES, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
     dense_kmajor_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                         const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+                        const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_h1,
                         const KParams p) {
     constexpr int kBTile = N * BK * 4;                  // one k-block of the weight operand, hi or lo
     constexpr int kTmemCols = 2 * N;                    // double-buffered accumulator (power of two for N in {64,128,256})
+    constexpr int kChunks = N / 32;                     // 32-column slices of the output tile
     constexpr uint32_t kIdesc = umma_idesc_tf32(BM, N, 0, 0);
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int S = p.stages, L = p.lo_bufs, KB = p.KB;
+    const int S = p.stages, L = p.lo_bufs, O = p.out_bufs, HB = p.h1_bufs, KB = p.KB;
     const uint32_t bres = base;                                              // [2][KB][kBTile] when B_RES
     const uint32_t ring = base + (B_RES ? 2u * KB * kBTile : 0u);
     const uint32_t stage_bytes = kATile + (B_RES ? 0 : 2 * kBTile);
     const uint32_t lo_ring = ring + (uint32_t)S * stage_bytes;
-    const uint32_t misc = lo_ring + (uint32_t)L * kATile;
-    // barriers
+    const uint32_t out_ring = lo_ring + (uint32_t)L * kATile;                // epilogue staging tiles [128][128 B]
+    const uint32_t h1_ring = out_ring + (uint32_t)O * kATile;                // DGRAD: trunk activation tiles for the mask
+    const uint32_t misc = h1_ring + (MODE == MODE_DGRAD ? (uint32_t)HB * kATile : 0u);
     const uint32_t bar_full = misc, bar_conv = misc + 64, bar_empty = misc + 128, bar_loempty = misc + 192;
     const uint32_t bar_tfull = misc + 224, bar_tempty = misc + 240, bar_bfull = misc + 256;
-    const uint32_t tmem_slot = misc + 264;
+    const uint32_t tmem_slot = misc + 264, bar_h1 = misc + 272;
     unsigned char* misc_ptr = smem_raw + (misc - smem_u32(smem_raw));
-    float* sf = reinterpret_cast<float*>(misc_ptr + 512);                    // per-mode float scratch (<= 7.5 KB)
+    float* sf = reinterpret_cast<float*>(misc_ptr + 512);                    // per-mode float scratch (<= 8 KB)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_tiles = (p.M + BM - 1) / BM;
@@ -96,18 +114,19 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_conv + 8 * s, 4);
+            mbar_init(bar_conv + 8 * s, kOperandWarps);
             mbar_init(bar_empty + 8 * s, 1);
         }
         for (int j = 0; j < L; ++j) mbar_init(bar_loempty + 8 * j, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
             mbar_init(bar_tempty + 8 * a, 4);
+            mbar_init(bar_h1 + 8 * a, 1);
         }
         mbar_init(bar_bfull, 1);
         mbar_fence_init();
     }
-    if (warp == 9) tmem_alloc<kTmemCols>(tmem_slot);
+    if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
     if (MODE == MODE_FWD) {
         // sf: bias[N] | head_w[2][N]
         for (int i = threadIdx.x; i < N; i += kThreads) {
@@ -116,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             sf[2 * N + i] = p.n_head > 1 ? p.head_w[N + i] : 0.f;
         }
     } else {
-        // sf: w2[src][head][256] (4 x 256 floats) | dout[2][128][2] staged per tile by the operand warps
+        // sf: w2[src][head][256] (4 x 256 floats) | dout[2 tile parities][128 rows][2 src][2 heads]
         const int K0 = p.kb_split * BK, K1 = (KB - p.kb_split) * BK;
         for (int i = threadIdx.x; i < 256; i += kThreads) {
             sf[i] = (i < K0 && p.nh0 > 0) ? p.w2_0[i] : 0.f;
@@ -131,8 +150,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    if (warp == 8) {
-        // ============================================================ TMA producer
+    if (warp == kProducerWarp) {
+        // ============================================================ TMA producer (one thread)
         if (lane == 0) {
             tma_prefetch_desc(&map_a0);
             tma_prefetch_desc(&map_bhi);
@@ -145,11 +164,11 @@ __global__ void __launch_bounds__(kThreads, 1)
                     tma_load_2d(bres + (KB + kb) * kBTile, &map_blo, kb * BK, 0, bar_bfull);
                 }
             }
-            uint32_t it = 0;
+            uint32_t s = 0, ph = 0, it = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const uint32_t s = it % S, ph = (it / S) & 1;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    XB_TS(0, it, 0);
                     const uint32_t st = ring + s * stage_bytes;
                     mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
                     const bool src1 = (MODE == MODE_DGRAD) && kb >= p.kb_split;
@@ -159,24 +178,24 @@ __global__ void __launch_bounds__(kThreads, 1)
                         tma_load_2d(st + kATile, &map_bhi, kb * BK, 0, bar_full + 8 * s);
                         tma_load_2d(st + kATile + kBTile, &map_blo, kb * BK, 0, bar_full + 8 * s);
                     }
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                 }
             }
         }
-    } else if (warp == 9) {
-        // ============================================================ MMA issuer
-        if (B_RES) mbar_wait(bar_bfull, 0);
-        uint32_t it = 0, lt = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
-            const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
-            mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * N;
-            for (int kb = 0; kb < KB; ++kb, ++it) {
-                const uint32_t s = it % S, ph = (it / S) & 1, j = it % L;
-                mbar_wait(bar_full + 8 * s, ph);
-                mbar_wait(bar_conv + 8 * s, ph);
-                tc_fence_after();
-                if (lane == 0) {
+    } else if (warp == kMmaWarp) {
+        // ============================================================ MMA issuer (one thread)
+        if (lane == 0) {
+            if (B_RES) mbar_wait(bar_bfull, 0);
+            uint32_t s = 0, ph = 0, j = 0, lt = 0, it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+                const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
+                const uint32_t d_tmem = tmem_base + acc * N;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    XB_TS(1, it, 0);
+                    mbar_wait(bar_conv + 8 * s, ph);          // operand warps arrive after they saw the TMA bytes land
+                    XB_TS(1, it, 1);
+                    tc_fence_after();
                     const uint32_t st = ring + s * stage_bytes;
                     const uint32_t a_hi = st, a_lo = lo_ring + j * kATile;
                     const uint32_t b_hi = B_RES ? bres + kb * kBTile : st + kATile;
@@ -191,34 +210,40 @@ __global__ void __launch_bounds__(kThreads, 1)
                         mma_tf32_ss(d_tmem, da_hi, db_lo, kIdesc, 1);
                         mma_tf32_ss(d_tmem, da_hi, db_hi, kIdesc, 1);
                     }
+                    XB_TS(1, it, 2);
                     mma_commit(bar_empty + 8 * s);
                     mma_commit(bar_loempty + 8 * j);
                     if (kb == KB - 1) mma_commit(bar_tfull + 8 * acc);
+                    XB_TS(1, it, 3);
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                    if (++j == (uint32_t)L) j = 0;
                 }
-                __syncwarp();
             }
         }
     } else if (warp >= 4) {
-        // ============================================================ operand warps (128 threads)
+        // ============================================================ operand warps (256 threads)
         const int t = threadIdx.x - 128;
-        const int c = t & 7, r0 = t >> 3;                 // logical 16-byte chunk, first row; rows r0 + 16 i
+        const int c = t & 7, r0 = t >> 3;                 // logical 16-byte chunk, first row; rows r0 + 32 i
         float* sdout = sf + 1024;                          // DGRAD: [2 tile parities][128 rows][2 src][2 heads]
-        uint32_t it = 0, lt = 0;
+        uint32_t s = 0, ph = 0, j = 0, jph = 0, lt = 0, it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
             if (MODE == MODE_DGRAD) {
-                const int64_t row = tile * BM + t;
-                float* d = sdout + (lt & 1) * 512 + t * 4;
-                const bool ok = row < p.M;
-                d[0] = (ok && p.nh0 > 0) ? p.dout0[row * p.nh0] : 0.f;
-                d[1] = (ok && p.nh0 > 1) ? p.dout0[row * p.nh0 + 1] : 0.f;
-                d[2] = (ok && p.nh1 > 0) ? p.dout1[row * p.nh1] : 0.f;
-                d[3] = (ok && p.nh1 > 1) ? p.dout1[row * p.nh1 + 1] : 0.f;
-                bar_sync_named(1, 128);
+                if (t < BM) {
+                    const int64_t row = tile * BM + t;
+                    float* d = sdout + (lt & 1) * 512 + t * 4;
+                    const bool ok = row < p.M;
+                    d[0] = (ok && p.nh0 > 0) ? p.dout0[row * p.nh0] : 0.f;
+                    d[1] = (ok && p.nh0 > 1) ? p.dout0[row * p.nh0 + 1] : 0.f;
+                    d[2] = (ok && p.nh1 > 0) ? p.dout1[row * p.nh1] : 0.f;
+                    d[3] = (ok && p.nh1 > 1) ? p.dout1[row * p.nh1 + 1] : 0.f;
+                }
+                bar_sync_named(1, kOperandWarps * 32);
             }
             for (int kb = 0; kb < KB; ++kb, ++it) {
-                const uint32_t s = it % S, ph = (it / S) & 1, j = it % L;
                 mbar_wait(bar_full + 8 * s, ph);
-                mbar_wait(bar_loempty + 8 * j, ((it / L) & 1) ^ 1);
+                if (t == 0) XB_TS(2, it, 0);
+                mbar_wait(bar_loempty + 8 * j, jph ^ 1);
+                if (t == 0) XB_TS(2, it, 1);
                 const uint32_t a_raw = ring + s * stage_bytes, a_lo = lo_ring + j * kATile;
                 float w0[4] = {0, 0, 0, 0}, w1[4] = {0, 0, 0, 0};
                 int src = 0;
@@ -229,12 +254,12 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) { w0[q] = w[q]; w1[q] = w[256 + q]; }
                 }
-                float4 xs[8];
+                float4 xs[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) xs[i] = lds128(a_raw + sw128_off(r0 + 16 * i, c));   // 8 loads in flight
+                for (int i = 0; i < 4; ++i) xs[i] = lds128(a_raw + sw128_off(r0 + 32 * i, c));
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = r0 + 16 * i;
+                for (int i = 0; i < 4; ++i) {
+                    const int r = r0 + 32 * i;
                     const uint32_t off = sw128_off(r, c);
                     float4 x = xs[i];
                     if (MODE == MODE_DGRAD) {
@@ -253,34 +278,62 @@ __global__ void __launch_bounds__(kThreads, 1)
                     sts128(a_raw + off, hi);
                     sts128(a_lo + off, lo);
                 }
+                if (t == 0) XB_TS(2, it, 2);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+                if (t == 0) XB_TS(2, it, 3);
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                if (++j == (uint32_t)L) { j = 0; jph ^= 1; }
             }
         }
     } else {
         // ============================================================ epilogue warps 0-3 (TMEM lanes 32w..32w+31)
-        uint32_t lt = 0;
+        // accumulator -> registers -> swizzled staging tile in shared memory -> TMA store (coalesced, off the LSU path)
+        const int r = warp * 32 + lane;                   // row of the tile this thread owns
+        uint32_t lt = 0, g = 0;                            // local tile counter, global chunk counter
+        if (MODE == MODE_DGRAD && threadIdx.x == 0 && (int64_t)blockIdx.x < n_tiles) {
+            mbar_arrive_expect_tx(bar_h1, kATile);
+            tma_load_2d(h1_ring, &map_h1, 0, (int)(blockIdx.x * BM), bar_h1);
+        }
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
             const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
-            const int64_t row = tile * BM + warp * 32 + lane;
-            const bool ok = row < p.M;
+            const int64_t row = tile * BM + r;
             mbar_wait(bar_tfull + 8 * acc, aph);
+            if (threadIdx.x == 0) XB_TS(3, lt, 0);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * N;
             float h0 = 0.f, h1 = 0.f;
 #pragma unroll 1
-            for (int cc = 0; cc < N / 32; ++cc) {
+            for (int cc = 0; cc < kChunks; ++cc, ++g) {
+                if (threadIdx.x == 0) XB_TS(3, lt, 1 + cc);
                 uint32_t v[32];
                 tmem_ld_32x32(taddr + cc * 32, v);
-                float4 m[8];
+                // the staging buffer about to be overwritten must have been read out by its previous TMA store
+                if (threadIdx.x == 0) {
+                    if (O > 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                bar_sync_named(2, 128);
+                const uint32_t obuf = out_ring + (g % (uint32_t)O) * kATile;
+                uint32_t hbuf = 0;
                 if (MODE == MODE_DGRAD) {
-                    const float4* hp = reinterpret_cast<const float4*>(p.H1 + row * N + cc * 32);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) m[q] = ok ? __ldg(hp + q) : make_float4(0, 0, 0, 0);
+                    // prefetch the next chunk's mask tile (double-buffered) or, single-buffered, load this chunk's now
+                    const uint32_t hb = HB > 1 ? (g & 1) : 0, hph = HB > 1 ? ((g >> 1) & 1) : (g & 1);
+                    if (threadIdx.x == 0) {
+                        int ncc = cc + (HB > 1 ? 1 : 0);
+                        int64_t ntile = tile;
+                        if (ncc == kChunks) { ncc = 0; ntile = tile + gridDim.x; }
+                        if (HB > 1 ? ntile < n_tiles : g > 0) {
+                            const uint32_t nb = HB > 1 ? ((g + 1) & 1) : 0;
+                            mbar_arrive_expect_tx(bar_h1 + 8 * nb, kATile);
+                            tma_load_2d(h1_ring + nb * kATile, &map_h1, ncc * 32, (int)(ntile * BM), bar_h1 + 8 * nb);
+                        }
+                    }
+                    hbuf = h1_ring + hb * kATile;
+                    mbar_wait(bar_h1 + 8 * hb, hph);
                 }
                 tmem_ld_wait();
-                float* out = (MODE == MODE_FWD ? p.Y : p.dZ1) + row * N + cc * 32;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     float4 f = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
@@ -296,28 +349,37 @@ __global__ void __launch_bounds__(kThreads, 1)
                         h0 += f.x * w[0] + f.y * w[1] + f.z * w[2] + f.w * w[3];
                         h1 += f.x * w[N] + f.y * w[N + 1] + f.z * w[N + 2] + f.w * w[N + 3];
                     } else {
-                        f.x *= m[q].x > 0.f ? 1.f : p.slope;
-                        f.y *= m[q].y > 0.f ? 1.f : p.slope;
-                        f.z *= m[q].z > 0.f ? 1.f : p.slope;
-                        f.w *= m[q].w > 0.f ? 1.f : p.slope;
+                        const float4 m = lds128(hbuf + sw128_off(r, q));
+                        f.x *= m.x > 0.f ? 1.f : p.slope;
+                        f.y *= m.y > 0.f ? 1.f : p.slope;
+                        f.z *= m.z > 0.f ? 1.f : p.slope;
+                        f.w *= m.w > 0.f ? 1.f : p.slope;
                     }
-                    if (ok) reinterpret_cast<float4*>(out)[q] = f;
+                    sts128(obuf + sw128_off(r, q), f);
+                }
+                fence_proxy_async_smem();
+                bar_sync_named(3, 128);
+                if (threadIdx.x == 0) {
+                    tma_store_2d(&map_out, obuf, cc * 32, (int)(tile * BM));
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-            if (MODE == MODE_FWD && ok) {
+            if (threadIdx.x == 0) XB_TS(3, lt, 7);
+            if (MODE == MODE_FWD && row < p.M) {
                 if (p.n_head > 0) p.head_out[row * p.n_head] = h0 + p.head_b[0];
                 if (p.n_head > 1) p.head_out[row * p.n_head + 1] = h1 + p.head_b[1];
             }
         }
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     // ---------------------------------------------------------------- teardown
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc<kTmemCols>(tmem_base);
     }
@@ -344,19 +406,27 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int N, int K, 
 
 template <int N, bool B_RES, int MODE>
 static int launch_kmajor(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mbhi, const CUtensorMap& mblo,
-                         KParams p, cudaStream_t s) {
+                         const CUtensorMap& mout, const CUtensorMap& mh1, KParams p, cudaStream_t s) {
     const int kBTile = N * BK * 4;
     const int bres = B_RES ? 2 * p.KB * kBTile : 0;
     const int stage = kATile + (B_RES ? 0 : 2 * kBTile);
     const int avail = kMaxSmem - 1024 - kMiscBytes - bres;
-    // pick ring depths: at least 2 raw stages + 1 lo buffer; prefer 2 lo buffers, then as many raw stages as fit (<= 6)
-    int L = 2, S = (avail - L * kATile) / stage;
-    if (S < 2) { L = 1; S = (avail - L * kATile) / stage; }
-    if (S < 2) return XB_E_UNSUPPORTED;
-    if (S > 6) S = 6;
+    // minimum: 2 raw stages, 1 lo buffer, 1 staging tile (+ 1 mask tile); then deepen in order of measured benefit
+    int S = 2, L = 1, O = 1, HB = MODE == MODE_DGRAD ? 1 : 0;
+    auto bytes = [&]() { return S * stage + (L + O + HB) * kATile; };
+    if (bytes() > avail) return XB_E_UNSUPPORTED;
+    ++L; if (bytes() > avail) --L;
+    if (MODE == MODE_DGRAD) { ++HB; if (bytes() > avail) --HB; }
+    ++O; if (bytes() > avail) --O;
+    while (S < 4) { ++S; if (bytes() > avail) { --S; break; } }
     p.stages = S;
     p.lo_bufs = L;
-    const int smem = 1024 + bres + S * stage + L * kATile + kMiscBytes;
+    p.out_bufs = O;
+    p.h1_bufs = HB;
+#ifdef XB_DENSE_TS
+    p.ts = g_xb_ts_host;
+#endif
+    const int smem = 1024 + bres + bytes() + kMiscBytes;
     auto kern = dense_kmajor_kernel<N, B_RES, MODE>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -365,25 +435,26 @@ static int launch_kmajor(const CUtensorMap& ma0, const CUtensorMap& ma1, const C
     }
     const int64_t tiles = (p.M + BM - 1) / BM;
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    kern<<<grid, kThreads, smem, s>>>(ma0, ma1, mbhi, mblo, p);
+    kern<<<grid, kThreads, smem, s>>>(ma0, ma1, mbhi, mblo, mout, mh1, p);
     XB_LAUNCH_CHECK();
     return 0;
 }
 
 template <int MODE>
 static int dispatch_kmajor(int N, bool bres, const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mbhi,
-                           const CUtensorMap& mblo, const KParams& p, cudaStream_t s) {
+                           const CUtensorMap& mblo, const CUtensorMap& mout, const CUtensorMap& mh1, const KParams& p,
+                           cudaStream_t s) {
     const int kBTile = N * BK * 4;
-    if (bres && (kMaxSmem - 1024 - kMiscBytes - 2 * p.KB * kBTile) < 2 * kATile + kATile) bres = false;
+    if (bres && (kMaxSmem - 1024 - kMiscBytes - 2 * p.KB * kBTile) < (2 + 1 + 1 + (MODE == MODE_DGRAD)) * kATile) bres = false;
     switch (N) {
         case 64:
-            return bres ? launch_kmajor<64, true, MODE>(ma0, ma1, mbhi, mblo, p, s)
-                        : launch_kmajor<64, false, MODE>(ma0, ma1, mbhi, mblo, p, s);
+            return bres ? launch_kmajor<64, true, MODE>(ma0, ma1, mbhi, mblo, mout, mh1, p, s)
+                        : launch_kmajor<64, false, MODE>(ma0, ma1, mbhi, mblo, mout, mh1, p, s);
         case 128:
-            return bres ? launch_kmajor<128, true, MODE>(ma0, ma1, mbhi, mblo, p, s)
-                        : launch_kmajor<128, false, MODE>(ma0, ma1, mbhi, mblo, p, s);
+            return bres ? launch_kmajor<128, true, MODE>(ma0, ma1, mbhi, mblo, mout, mh1, p, s)
+                        : launch_kmajor<128, false, MODE>(ma0, ma1, mbhi, mblo, mout, mh1, p, s);
         case 256:
-            return launch_kmajor<256, false, MODE>(ma0, ma1, mbhi, mblo, p, s);
+            return launch_kmajor<256, false, MODE>(ma0, ma1, mbhi, mblo, mout, mh1, p, s);
         default:
             return XB_E_UNSUPPORTED;
     }
@@ -414,7 +485,7 @@ struct WParams {
 };
 
 template <int HIN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kWThreads, 1)
     dense_wgrad_kernel(const __grid_constant__ CUtensorMap map_y0, const __grid_constant__ CUtensorMap map_y1,
                        const __grid_constant__ CUtensorMap map_x, const WParams p) {
     constexpr int NBX = HIN / 32;                  // 32-feature boxes of x
@@ -695,7 +766,7 @@ static int launch_wgrad(const CUtensorMap& my0, const CUtensorMap& my1, const CU
         XB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         attr_set = true;
     }
-    kern<<<grid, kThreads, smem, s>>>(my0, my1, mx, p);
+    kern<<<grid, kWThreads, smem, s>>>(my0, my1, mx, p);
     XB_LAUNCH_CHECK();
     return 0;
 }
@@ -707,6 +778,13 @@ using namespace xb;
 using namespace xb::dense;
 
 static inline bool al16(const void* q) { return ((uintptr_t)q & 15u) == 0; }
+
+#ifdef XB_DENSE_TS
+extern "C" int xb_dense_debug_set_ts(long long* buf) {
+    xb::dense::g_xb_ts_host = buf;
+    return 0;
+}
+#endif
 
 extern "C" int xb_dense_split_weights(const float* W, int N, int K, float* hi, float* lo, float* thi, float* tlo,
                                       int ldt, int toff, xb_stream_t stream) {
@@ -724,9 +802,9 @@ extern "C" int xb_dense_fwd(const float* X, int64_t M, int K, const float* Whi, 
     if (K % BK != 0 || K < BK || K > 256 || n_head < 0 || n_head > 2 || (n_head && (!head_w || !head_b || !head_out)))
         return XB_E_UNSUPPORTED;
     if (!al16(X) || !al16(Whi) || !al16(Wlo) || !al16(Y)) return XB_E_UNSUPPORTED;
-    CUtensorMap ma, mbhi, mblo;
+    CUtensorMap ma, mbhi, mblo, mout;
     if (!xb_make_map_f32_2d(&ma, X, M, K, K, BM, BK, 1) || !xb_make_map_f32_2d(&mbhi, Whi, N, K, K, N, BK, 1) ||
-        !xb_make_map_f32_2d(&mblo, Wlo, N, K, K, N, BK, 1))
+        !xb_make_map_f32_2d(&mblo, Wlo, N, K, K, N, BK, 1) || !xb_make_map_f32_2d(&mout, Y, M, N, N, BM, 32, 1))
         return XB_E_DRIVER;
     KParams p{};
     p.M = M;
@@ -739,7 +817,7 @@ extern "C" int xb_dense_fwd(const float* X, int64_t M, int K, const float* Whi, 
     p.head_b = head_b;
     p.n_head = n_head;
     p.head_out = head_out;
-    return dispatch_kmajor<MODE_FWD>(N, b_resident != 0, ma, ma, mbhi, mblo, p, (cudaStream_t)stream);
+    return dispatch_kmajor<MODE_FWD>(N, b_resident != 0, ma, ma, mbhi, mblo, mout, mout, p, (cudaStream_t)stream);
 }
 
 extern "C" int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, int K0, const float* Y1,
@@ -751,8 +829,9 @@ extern "C" int xb_dense_dgrad(const float* Y0, const float* dout0, const float* 
     if (!Y1) K1 = 0;
     if (!al16(Y0) || !al16(Wthi) || !al16(Wtlo) || !al16(H1) || !al16(dZ1) || (Y1 && !al16(Y1))) return XB_E_UNSUPPORTED;
     const int K = K0 + K1;
-    CUtensorMap ma0, ma1, mbhi, mblo;
-    if (!xb_make_map_f32_2d(&ma0, Y0, M, K0, K0, BM, BK, 1) ||
+    CUtensorMap ma0, ma1, mbhi, mblo, mout, mh1;
+    if (!xb_make_map_f32_2d(&mout, dZ1, M, N, N, BM, 32, 1) || !xb_make_map_f32_2d(&mh1, H1, M, N, N, BM, 32, 1) ||
+        !xb_make_map_f32_2d(&ma0, Y0, M, K0, K0, BM, BK, 1) ||
         !xb_make_map_f32_2d(&ma1, Y1 ? Y1 : Y0, M, Y1 ? K1 : K0, Y1 ? K1 : K0, BM, BK, 1) ||
         !xb_make_map_f32_2d(&mbhi, Wthi, N, K, K, N, BK, 1) || !xb_make_map_f32_2d(&mblo, Wtlo, N, K, K, N, BK, 1))
         return XB_E_DRIVER;
@@ -769,7 +848,7 @@ extern "C" int xb_dense_dgrad(const float* Y0, const float* dout0, const float* 
     p.nh1 = Y1 ? nh1 : 0;
     p.H1 = H1;
     p.dZ1 = dZ1;
-    return dispatch_kmajor<MODE_DGRAD>(N, false, ma0, ma1, mbhi, mblo, p, (cudaStream_t)stream);
+    return dispatch_kmajor<MODE_DGRAD>(N, false, ma0, ma1, mbhi, mblo, mout, mh1, p, (cudaStream_t)stream);
 }
 
 extern "C" int xb_dense_wgrad_workspace_floats(int H_in) { return kNumSMs * (128 * (H_in + 4) + 256 + 2); }

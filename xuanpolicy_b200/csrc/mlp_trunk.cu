@@ -1,0 +1,151 @@
+// mlp_trunk.cu — the first (narrow-input) layer of the policy/value MLP and its weight gradient.
+//
+// Basic_MLP's only layer, Linear(obs_dim, H) + LeakyReLU (xuance/torch/representations/mlp.py:40-51), has a 3- or
+// 4-wide reduction: it is a bandwidth-bound broadcast, not a GEMM, so it runs on the SIMT pipes:
+//   forward   h1[b][n] = leaky(b0[n] + sum_i obs[b][i] W0[n][i])            writes B x H floats, reads B x obs_dim
+//   backward  dW0[n][i] = sum_b dz1[b][n] obs[b][i],  db0[n] = sum_b dz1[b][n]   reads B x H floats once
+// (dz1 comes from the dgrad tensor-core kernel; torch would run a [H x B] x [B x obs_dim] sgemm + a column reduction).
+#include "common.cuh"
+
+namespace xb {
+
+constexpr int kMaxObs = 8;
+
+// one thread = 4 consecutive output features of one row; a group of H/4 threads covers a row
+template <int OBS>
+__global__ void __launch_bounds__(256) trunk_fwd_kernel(const float* __restrict__ obs, int ld, const float* __restrict__ W0,
+                                                        const float* __restrict__ b0, float slope, float4* __restrict__ h1,
+                                                        int64_t B, int H) {
+    const int tpr = H >> 2;                        // threads per row
+    const int rows_per_block = blockDim.x / tpr;
+    const int q = threadIdx.x % tpr, slot = threadIdx.x / tpr;
+    if (slot >= rows_per_block) return;
+    float w[4][OBS], bias[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        bias[e] = b0[4 * q + e];
+#pragma unroll
+        for (int i = 0; i < OBS; ++i) w[e][i] = W0[(4 * q + e) * OBS + i];
+    }
+    for (int64_t b = (int64_t)blockIdx.x * rows_per_block + slot; b < B; b += (int64_t)gridDim.x * rows_per_block) {
+        float x[OBS];
+#pragma unroll
+        for (int i = 0; i < OBS; ++i) x[i] = __ldg(obs + b * ld + i);
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float a = bias[e];
+#pragma unroll
+            for (int i = 0; i < OBS; ++i) a += x[i] * w[e][i];
+            o[e] = a > 0.f ? a : a * slope;
+        }
+        h1[b * tpr + q] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// partial[blockIdx][n][OBS + 1] = sum over this block's rows; a second kernel adds the blocks in order
+template <int OBS>
+__global__ void __launch_bounds__(256) trunk_wgrad_kernel(const float4* __restrict__ dz1, const float* __restrict__ obs,
+                                                          int ld, float* __restrict__ partial, int64_t B, int H) {
+    extern __shared__ float red[];                 // [rows_per_block][H][OBS + 1]
+    const int tpr = H >> 2;
+    const int rows_per_block = blockDim.x / tpr;
+    const int q = threadIdx.x % tpr, slot = threadIdx.x / tpr;
+    float acc[4][OBS + 1];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int i = 0; i <= OBS; ++i) acc[e][i] = 0.f;
+    if (slot < rows_per_block) {
+        for (int64_t b = (int64_t)blockIdx.x * rows_per_block + slot; b < B; b += (int64_t)gridDim.x * rows_per_block) {
+            const float4 d = dz1[b * tpr + q];
+            const float dv[4] = {d.x, d.y, d.z, d.w};
+            float x[OBS];
+#pragma unroll
+            for (int i = 0; i < OBS; ++i) x[i] = __ldg(obs + b * ld + i);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+#pragma unroll
+                for (int i = 0; i < OBS; ++i) acc[e][i] += dv[e] * x[i];
+                acc[e][OBS] += dv[e];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int i = 0; i <= OBS; ++i) red[(slot * H + 4 * q + e) * (OBS + 1) + i] = acc[e][i];
+    }
+    __syncthreads();
+    const int n_out = H * (OBS + 1);
+    for (int k = threadIdx.x; k < n_out; k += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < rows_per_block; ++r) s += red[r * n_out + k];
+        partial[(int64_t)blockIdx.x * n_out + k] = s;
+    }
+}
+
+__global__ void trunk_wgrad_reduce_kernel(const float* __restrict__ partial, int n_blocks, int H, int OBS,
+                                          float* __restrict__ dW0, float* __restrict__ db0) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_out = H * (OBS + 1);
+    if (k >= n_out) return;
+    float s = 0.f;
+    for (int p = 0; p < n_blocks; ++p) s += partial[(int64_t)p * n_out + k];
+    const int n = k / (OBS + 1), i = k % (OBS + 1);
+    if (i < OBS) dW0[n * OBS + i] = s;
+    else db0[n] = s;
+}
+
+constexpr int kTrunkBlocks = 2 * kNumSMs;
+
+}  // namespace xb
+
+using namespace xb;
+
+#define XB_OBS_SWITCH(OBS, CALL)        \
+    switch (OBS) {                      \
+        case 1: { constexpr int O = 1; CALL; } break; \
+        case 2: { constexpr int O = 2; CALL; } break; \
+        case 3: { constexpr int O = 3; CALL; } break; \
+        case 4: { constexpr int O = 4; CALL; } break; \
+        case 5: { constexpr int O = 5; CALL; } break; \
+        case 6: { constexpr int O = 6; CALL; } break; \
+        case 7: { constexpr int O = 7; CALL; } break; \
+        case 8: { constexpr int O = 8; CALL; } break; \
+        default: return XB_E_UNSUPPORTED;             \
+    }
+
+static inline bool trunk_shape_ok(int obs_dim, int H) {
+    return obs_dim >= 1 && obs_dim <= kMaxObs && H % 4 == 0 && H >= 4 && 256 % (H / 4) == 0;
+}
+
+extern "C" int xb_mlp_trunk_fwd(const float* obs, int ld, int obs_dim, const float* W0, const float* b0, float slope,
+                                float* h1, int64_t B, int H, xb_stream_t stream) {
+    if (!obs || !W0 || !b0 || !h1 || B <= 0 || ld < obs_dim) return XB_E_BADARG;
+    if (!trunk_shape_ok(obs_dim, H) || ((uintptr_t)h1 & 15u)) return XB_E_UNSUPPORTED;
+    const int rows_per_block = 256 / (H / 4);
+    const int grid = grid_for((B + rows_per_block - 1) / rows_per_block * 256, 256, 4);
+    XB_OBS_SWITCH(obs_dim, (trunk_fwd_kernel<O><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                               obs, ld, W0, b0, slope, reinterpret_cast<float4*>(h1), B, H)));
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_mlp_trunk_wgrad_workspace_floats(int obs_dim, int H) { return kTrunkBlocks * H * (obs_dim + 1); }
+
+extern "C" int xb_mlp_trunk_wgrad(const float* dz1, const float* obs, int ld, int obs_dim, float* workspace, float* dW0,
+                                  float* db0, int64_t B, int H, xb_stream_t stream) {
+    if (!dz1 || !obs || !workspace || !dW0 || !db0 || B <= 0 || ld < obs_dim) return XB_E_BADARG;
+    if (!trunk_shape_ok(obs_dim, H) || ((uintptr_t)dz1 & 15u)) return XB_E_UNSUPPORTED;
+    const int rows_per_block = 256 / (H / 4);
+    const int smem = rows_per_block * H * (obs_dim + 1) * (int)sizeof(float);
+    if (smem > 48 * 1024) return XB_E_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    XB_OBS_SWITCH(obs_dim, (trunk_wgrad_kernel<O><<<kTrunkBlocks, 256, smem, s>>>(
+                               reinterpret_cast<const float4*>(dz1), obs, ld, workspace, B, H)));
+    XB_LAUNCH_CHECK();
+    const int n_out = H * (obs_dim + 1);
+    trunk_wgrad_reduce_kernel<<<(n_out + 127) / 128, 128, 0, s>>>(workspace, kTrunkBlocks, H, obs_dim, dW0, db0);
+    XB_LAUNCH_CHECK();
+    return 0;
+}

@@ -47,6 +47,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
         ::"r"(smem_dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// shared -> global tile store, tracked by the issuing thread's bulk async-group (commit_group / wait_group)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"((uint64_t)map),
+                 "r"(c0), "r"(c1), "r"(smem_src)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }

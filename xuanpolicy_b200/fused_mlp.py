@@ -1,0 +1,139 @@
+"""The actor-critic MLP of the PPO path on the hand-written dense kernels (csrc/dense_tc.cu, csrc/mlp_trunk.cu).
+
+The torch modules keep owning the parameters (same names / state_dict as the reference's
+Basic_MLP + ActorNet + CriticNet, xuance/torch/representations/mlp.py:21-51, policies/categorical.py:16-85,
+policies/gaussian.py:8-77); this class only *evaluates* them at large batch:
+
+    forward   obs -> h1 = leaky(W0 obs + b0)                         SIMT (3/4-wide reduction)
+              h1  -> ya = leaky(Wa1 h1 + ba1), act_out = Wa2 ya + ba2    tcgen05 3xTF32 GEMM + fused head
+              h1  -> yc = leaky(Wc1 h1 + bc1), v = Wc2 yc + bc2          tcgen05 3xTF32 GEMM + fused head
+    backward  (dL/dact_out, dL/dv) -> every parameter gradient, written straight into the flat gradient buffer:
+              dgrad (dz_a | dz_c generated on the fly) -> dz1; wgrad (dWa1, dba1, dWa2, dba2, dWc1, ...); trunk wgrad.
+
+It replaces torch autograd + cuBLAS SIMT sgemm for the supported shape (one hidden layer per block, width 128 or 256,
+LeakyReLU, action dim <= 2, obs dim <= 8 — every classic-control config of the reference); anything else keeps the
+torch path.  No CPU path: construction requires CUDA parameters.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _stack(seq):
+    return list(seq) if isinstance(seq, nn.Sequential) else None
+
+
+class _OutParams:
+    """What PPOCLIP_Agent._sample / the loss need from a distribution: `get_param()` (distributions.py:47,78)."""
+
+    def __init__(self, logits=None, mu=None, std=None):
+        self._logits, self._mu, self._std = logits, mu, std
+
+    def get_param(self):
+        return self._logits if self._logits is not None else (self._mu, self._std)
+
+
+class FusedActorCritic:
+    MIN_ROWS = 2048          # below this the launch-bound torch path is as good
+
+    @staticmethod
+    def plan(policy):
+        """Returns the layer tuple if `policy` has the supported structure, else None."""
+        try:
+            rep = _stack(policy.representation.model)
+            actor = _stack(getattr(policy.actor, "mu", None) if hasattr(policy.actor, "mu") else policy.actor.model)
+            critic = _stack(policy.critic.model)
+        except AttributeError:
+            return None
+        if rep is None or actor is None or critic is None or len(rep) != 2 or len(actor) != 3 or len(critic) != 3:
+            return None
+        l0, a0 = rep
+        la1, aa, la2 = actor
+        lc1, ac, lc2 = critic
+        lins = (l0, la1, la2, lc1, lc2)
+        if not all(isinstance(m, nn.Linear) and m.bias is not None for m in lins):
+            return None
+        if not all(isinstance(a, nn.LeakyReLU) for a in (a0, aa, ac)):
+            return None
+        if len({float(a.negative_slope) for a in (a0, aa, ac)}) != 1:
+            return None
+        H = l0.out_features
+        if H not in (128, 256) or la1.in_features != H or la1.out_features != H or lc1.in_features != H \
+                or lc1.out_features != H or la2.in_features != H or lc2.in_features != H:
+            return None
+        if l0.in_features > 8 or la2.out_features > 2 or lc2.out_features != 1:
+            return None
+        for m in lins:
+            for t in (m.weight, m.bias):
+                if not t.is_cuda or t.dtype != torch.float32:
+                    return None
+        return dict(l0=l0, la1=la1, la2=la2, lc1=lc1, lc2=lc2, H=H, obs_dim=l0.in_features, A=la2.out_features,
+                    slope=float(a0.negative_slope), gaussian=hasattr(policy.actor, "logstd"))
+
+    def __init__(self, policy):
+        pl = self.plan(policy)
+        if pl is None:
+            raise ValueError("policy structure not supported by the fused dense kernels")
+        self.policy = policy
+        self.__dict__.update(pl)
+        dev = self.l0.weight.device
+        self.device = dev
+        H = self.H
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        # hi/lo splits of the two H x H layers and their transposes concatenated along the reduction dim (dgrad operand)
+        self.wa_hi, self.wa_lo, self.wc_hi, self.wc_lo = z(H, H), z(H, H), z(H, H), z(H, H)
+        self.wt_hi, self.wt_lo = z(H, 2 * H), z(H, 2 * H)
+        self.ws_wgrad = ops.dense_wgrad_workspace(H, dev)
+        self.ws_trunk = ops.mlp_trunk_wgrad_workspace(self.obs_dim, H, dev)
+        self._buf = {}
+        self._last = None
+
+    # every tensor below is read at launch time: parameters may have been re-pointed (FlatAdamState) since __init__
+    def refresh_weights(self):
+        ops.dense_split_weights(self.la1.weight.data, self.wa_hi, self.wa_lo, self.wt_hi, self.wt_lo, 0)
+        ops.dense_split_weights(self.lc1.weight.data, self.wc_hi, self.wc_lo, self.wt_hi, self.wt_lo, self.H)
+
+    def _buffers(self, B):
+        b = self._buf.get(B)
+        if b is None:
+            e = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
+            b = dict(h1=e(B, self.H), ya=e(B, self.H), yc=e(B, self.H), act=e(B, self.A), v=e(B, 1), dz1=None)
+            self._buf[B] = b
+        return b
+
+    def forward(self, obs, refresh=True):
+        """obs: CUDA fp32 [B, obs_dim] with contiguous rows (a column slice of the float4 observation rows is fine).
+        Returns (act_out [B, A], v [B]); the activations stay in per-batch-size buffers for `backward`."""
+        B = obs.shape[0]
+        b = self._buffers(B)
+        if refresh:
+            self.refresh_weights()
+        ops.mlp_trunk_fwd(obs, self.l0.weight.data, self.l0.bias.data, self.slope, b["h1"])
+        ops.dense_fwd(b["h1"], self.wa_hi, self.wa_lo, self.la1.bias.data, self.slope, b["ya"], self.la2.weight.data,
+                      self.la2.bias.data, b["act"])
+        ops.dense_fwd(b["h1"], self.wc_hi, self.wc_lo, self.lc1.bias.data, self.slope, b["yc"], self.lc2.weight.data,
+                      self.lc2.bias.data, b["v"])
+        self._last = (obs, b)
+        return b["act"], b["v"][:, 0]
+
+    def dist_params(self, act_out):
+        if self.gaussian:
+            return _OutParams(mu=act_out, std=None)
+        return _OutParams(logits=act_out)
+
+    def backward(self, dact, dv):
+        """dact [B, A], dv [B] = dL/d(act_out), dL/d(v) for the most recent `forward`; writes .grad of the ten
+        Linear parameters (views of the flat gradient buffer) — plain stores, no accumulation."""
+        obs, b = self._last
+        B = obs.shape[0]
+        if b["dz1"] is None:
+            b["dz1"] = torch.empty(B, self.H, dtype=torch.float32, device=self.device)
+        dv2 = dv.reshape(B, 1)
+        g = lambda p: p.grad
+        ops.dense_dgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, self.wt_hi, self.wt_lo,
+                        b["h1"], self.slope, b["dz1"])
+        ops.dense_wgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, b["h1"], self.slope,
+                        self.ws_wgrad, g(self.la1.weight), g(self.la1.bias), g(self.la2.weight), g(self.la2.bias),
+                        g(self.lc1.weight), g(self.lc1.bias), g(self.lc2.weight), g(self.lc2.bias))
+        ops.mlp_trunk_wgrad(b["dz1"], obs, self.ws_trunk, g(self.l0.weight), g(self.l0.bias))

@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .fused_mlp import FusedActorCritic
 
 
 def _dist_params(a_dist):
@@ -104,6 +105,8 @@ class PPOCLIP_Learner:
         self.value_clip = float(value_clip) if value_clip else 0.0   # opt-in; the reference has none
         self._scalars = torch.zeros(8, dtype=torch.float64, device=self.device)
         self._flat = None
+        self._fused = None          # FusedActorCritic: the MLP on the tcgen05 dense kernels (native path, large batches)
+        self.use_fused_mlp = os.environ.get("XB_FUSED_MLP", "1") != "0"
         self._mb = {}
         self.world_size, self.process_group = 1, None
 
@@ -122,10 +125,12 @@ class PPOCLIP_Learner:
 
     # ---------------------------------------------------------------------------------------------- loss kernel
     def _loss_backward(self, a_dist, v_pred, act, ret, adv, old_logp, val_old, inv_batch, idx=None, T=0, N=0,
-                       adv_stats=None, adv_count=0, packed=None, flat=None):
-        """Fused loss fwd+bwd on the network outputs, then torch autograd through the MLP (into `.grad`, or — with
-        `flat` — straight into the flat gradient buffer)."""
+                       adv_stats=None, adv_count=0, packed=None, flat=None, fused=None):
+        """Fused loss fwd+bwd on the network outputs, then the MLP backward: torch autograd (into `.grad`, or — with
+        `flat` — straight into the flat gradient buffer) or, with `fused`, the hand-written dgrad/wgrad kernels."""
         backward = torch.autograd.backward if flat is None else flat.backward_into
+        if fused is not None:
+            backward = lambda outs, grads: fused.backward(grads[0], grads[1])
         kind, p0, p1 = _dist_params(a_dist)
         v = v_pred.detach().contiguous()
         dv = torch.empty_like(v)
@@ -194,6 +199,8 @@ class PPOCLIP_Learner:
         the constructor is only read for its hyper-parameters from here on."""
         if self._flat is None:
             self._flat = FlatAdamState(self.policy, self.optimizer, self.scheduler)
+            if self.use_fused_mlp and FusedActorCritic.plan(self.policy) is not None:
+                self._fused = FusedActorCritic(self.policy)
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.process_group = process_group
             self.world_size = torch.distributed.get_world_size(process_group)
@@ -222,15 +229,21 @@ class PPOCLIP_Learner:
     def stage_forward_backward(self, memory, idx, mb):
         """Stage 2: torch MLP forward, fused gather+loss+backward kernel, torch MLP backward into the flat gradient."""
         B = idx.numel()
-        _, a_dist, v_pred = self.policy(mb["obs"])
+        fused = self._fused if (self._fused is not None and B >= FusedActorCritic.MIN_ROWS) else None
+        if fused is not None:                        # tcgen05 dense kernels; weights re-split after every Adam step
+            act_out, v_pred = fused.forward(mb["obs"], refresh=True)
+            a_dist = fused.dist_params(act_out)
+        else:
+            _, a_dist, v_pred = self.policy(mb["obs"])
         stats = mb["stats"] if memory.use_advnorm else None
         if memory.packed and self.value_clip <= 0:   # scalars already gathered, compact and coalesced
             self._loss_backward(a_dist, v_pred, None, None, None, None, None, 1.0 / (B * self.world_size),
-                                adv_stats=stats, adv_count=B * self.world_size, packed=mb["scal"], flat=self._flat)
+                                adv_stats=stats, adv_count=B * self.world_size, packed=mb["scal"], flat=self._flat,
+                                fused=fused)
         else:                                        # gather fused into the loss kernel
             self._loss_backward(a_dist, v_pred, memory._act, memory._ret, memory._adv, memory._logp, memory._val,
                                 1.0 / (B * self.world_size), idx=idx, T=memory.n_size, N=memory.n_envs,
-                                adv_stats=stats, adv_count=B * self.world_size, flat=self._flat)
+                                adv_stats=stats, adv_count=B * self.world_size, flat=self._flat, fused=fused)
 
     def stage_optimizer(self):
         """Stage 3: global-norm clip + Adam + LinearLR on the flat buffers (one fused device step)."""

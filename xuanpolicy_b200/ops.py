@@ -223,3 +223,27 @@ def dense_wgrad(y0, dout0, w2_0, y1, dout1, w2_1, x, slope, workspace, dW0, db0,
               _p(w2_1, F32), w2_1.shape[0] if w2_1 is not None else 0, _p(x, F32), B, H_out, x.shape[1], float(slope),
               _p(workspace, F32), _p(dW0, F32), _p(db0, F32), _p(dw2_0, F32), _p(db2_0, F32), _p(dW1, F32), _p(db1, F32),
               _p(dw2_1, F32), _p(db2_1, F32), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ trunk layer (SIMT)
+def _rows_ld(x):
+    """(data pointer, row pitch in floats) of a 2-D fp32 tensor whose rows are contiguous (e.g. a column slice)."""
+    if not x.is_cuda or x.dtype != F32 or x.dim() != 2 or x.stride(1) != 1:
+        raise _lib.XB200Error("expected a CUDA fp32 matrix with contiguous rows")
+    return x.data_ptr(), x.stride(0)
+
+
+def mlp_trunk_fwd(obs, w0, b0, slope, h1):
+    ptr, ld = _rows_ld(obs)
+    _lib.call("xb_mlp_trunk_fwd", ptr, ld, obs.shape[1], _p(w0, F32), _p(b0, F32), float(slope), _p(h1, F32),
+              obs.shape[0], w0.shape[0], _stream())
+
+
+def mlp_trunk_wgrad_workspace(obs_dim, h, device):
+    return torch.empty(_lib.load().xb_mlp_trunk_wgrad_workspace_floats(int(obs_dim), int(h)), dtype=F32, device=device)
+
+
+def mlp_trunk_wgrad(dz1, obs, workspace, dw0, db0):
+    ptr, ld = _rows_ld(obs)
+    _lib.call("xb_mlp_trunk_wgrad", _p(dz1, F32), ptr, ld, obs.shape[1], _p(workspace, F32), _p(dw0, F32), _p(db0, F32),
+              obs.shape[0], dz1.shape[1], _stream())
