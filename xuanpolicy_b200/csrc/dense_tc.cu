@@ -714,12 +714,14 @@ __global__ void __launch_bounds__(kWThreads, 1)
     }
 }
 
-// Sums the per-CTA partials of the wgrad kernel in CTA order (deterministic) and scatters them to the parameter
-// gradients.  One block per (job, output row m); threads over the HIN + 1 columns.
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ head_part,
+// Sums the per-CTA partials of the wgrad kernel in a fixed order (deterministic) and scatters them to the parameter
+// gradients.  One block per (job, output row m): 4 thread groups each add a quarter of the CTAs' partials for their
+// column (loads unrolled so many are in flight), then the groups are combined through shared memory.
+__global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ head_part,
                                     const float* __restrict__ db2_part, int grid, int n_jobs, int halves, int HIN,
                                     int H_out, float* dW0, float* db0, float* dw2_0, float* db2_0, int nh0, float* dW1,
                                     float* db1, float* dw2_1, float* db2_1, int nh1) {
+    __shared__ float red[4][260];
     const int job = blockIdx.x / 128, r = blockIdx.x % 128;
     const int src = job / halves, m = (job % halves) * 128 + r;
     float* dW = src ? dW1 : dW0;
@@ -727,23 +729,41 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, const float*
     float* dw2 = src ? dw2_1 : dw2_0;
     float* db2 = src ? db2_1 : db2_0;
     const int nh = src ? nh1 : nh0;
-    for (int n = threadIdx.x; n < HIN + 3; n += blockDim.x) {
+    const int grp = threadIdx.x >> 7, t = threadIdx.x & 127;
+    const int n_cta = (grid - job + n_jobs - 1) / n_jobs;          // CTAs that worked on this job: job, job + n_jobs, ...
+    const int ncol = HIN + 3;                                       // HIN weights | bias | head 0 | head 1
+    for (int n = t; n < ncol; n += 128) {
         float acc = 0.f;
+        const float* src_ptr;
+        int64_t stride;
         if (n <= HIN) {
-            for (int cta = job; cta < grid; cta += n_jobs) acc += part[((int64_t)cta * 128 + r) * (HIN + 4) + n];
-            if (n < HIN) dW[(int64_t)m * HIN + n] = acc;
-            else db[m] = acc;
+            src_ptr = part + ((int64_t)job * 128 + r) * (HIN + 4) + n;
+            stride = (int64_t)n_jobs * 128 * (HIN + 4);
         } else {
-            const int j = n - HIN - 1;               // head index 0 / 1
-            if (j < nh) {
-                for (int cta = job; cta < grid; cta += n_jobs) acc += head_part[(int64_t)cta * 256 + j * 128 + r];
-                dw2[(int64_t)j * H_out + m] = acc;
-                if (m == 0) {                        // db2: any one job of this source carries the full batch slice sum
-                    float s = 0.f;
-                    for (int cta = job; cta < grid; cta += n_jobs) s += db2_part[(int64_t)cta * 2 + j];
-                    db2[j] = s;
-                }
-            }
+            src_ptr = head_part + (int64_t)job * 256 + (n - HIN - 1) * 128 + r;
+            stride = (int64_t)n_jobs * 256;
+        }
+        int c = grp;
+        for (; c + 12 < n_cta; c += 16) {                           // 4 loads in flight
+            const float a0 = src_ptr[c * stride], a1 = src_ptr[(c + 4) * stride], a2 = src_ptr[(c + 8) * stride],
+                        a3 = src_ptr[(c + 12) * stride];
+            acc += (a0 + a1) + (a2 + a3);
+        }
+        for (; c < n_cta; c += 4) acc += src_ptr[c * stride];
+        red[grp][n] = acc;
+    }
+    __syncthreads();
+    if (grp == 0) {
+        for (int n = t; n < ncol; n += 128) {
+            const float acc = (red[0][n] + red[1][n]) + (red[2][n] + red[3][n]);
+            if (n < HIN) dW[(int64_t)m * HIN + n] = acc;
+            else if (n == HIN) db[m] = acc;
+            else if (n - HIN - 1 < nh) dw2[(int64_t)(n - HIN - 1) * H_out + m] = acc;
+        }
+        if (m == 0 && t < nh) {                                     // db2: this job's CTAs cover the whole batch
+            float s = 0.f;
+            for (int c = 0; c < n_cta; ++c) s += db2_part[(int64_t)(job + c * n_jobs) * 2 + t];
+            db2[t] = s;
         }
     }
 }
@@ -881,7 +901,7 @@ extern "C" int xb_dense_wgrad(const float* Y0, const float* dout0, const float* 
     p.db2_part = p.head_part + (int64_t)grid * 256;
     int rc = H_in == 128 ? launch_wgrad<128>(my0, my1, mx, p, grid, s) : launch_wgrad<256>(my0, my1, mx, p, grid, s);
     if (rc) return rc;
-    wgrad_reduce_kernel<<<p.n_jobs * 128, 160, 0, s>>>(p.part, p.head_part, p.db2_part, grid, p.n_jobs, p.halves, H_in,
+    wgrad_reduce_kernel<<<p.n_jobs * 128, 512, 0, s>>>(p.part, p.head_part, p.db2_part, grid, p.n_jobs, p.halves, H_in,
                                                       H_out, dW0, db0, dw2_0, db2_0, nh0, dW1, db1, dw2_1, db2_1,
                                                       Y1 ? nh1 : 0);
     XB_LAUNCH_CHECK();

@@ -57,17 +57,27 @@ __global__ void __launch_bounds__(256) trunk_wgrad_kernel(const float4* __restri
 #pragma unroll
         for (int i = 0; i <= OBS; ++i) acc[e][i] = 0.f;
     if (slot < rows_per_block) {
-        for (int64_t b = (int64_t)blockIdx.x * rows_per_block + slot; b < B; b += (int64_t)gridDim.x * rows_per_block) {
-            const float4 d = dz1[b * tpr + q];
-            const float dv[4] = {d.x, d.y, d.z, d.w};
-            float x[OBS];
+        const int64_t step = (int64_t)gridDim.x * rows_per_block;
+        for (int64_t b0 = (int64_t)blockIdx.x * rows_per_block + slot; b0 < B; b0 += 4 * step) {
+            float4 d[4];
+            float x[4][OBS];
 #pragma unroll
-            for (int i = 0; i < OBS; ++i) x[i] = __ldg(obs + b * ld + i);
+            for (int u = 0; u < 4; ++u) {           // 4 independent rows in flight per thread
+                const int64_t b = b0 + u * step;
+                const bool ok = b < B;
+                d[u] = ok ? dz1[b * tpr + q] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+                for (int i = 0; i < OBS; ++i) x[u][i] = ok ? __ldg(obs + b * ld + i) : 0.f;
+            }
 #pragma unroll
-                for (int i = 0; i < OBS; ++i) acc[e][i] += dv[e] * x[i];
-                acc[e][OBS] += dv[e];
+            for (int u = 0; u < 4; ++u) {
+                const float dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+#pragma unroll
+                    for (int i = 0; i < OBS; ++i) acc[e][i] += dv[e] * x[u][i];
+                    acc[e][OBS] += dv[e];
+                }
             }
         }
 #pragma unroll
@@ -84,16 +94,21 @@ __global__ void __launch_bounds__(256) trunk_wgrad_kernel(const float4* __restri
     }
 }
 
-__global__ void trunk_wgrad_reduce_kernel(const float* __restrict__ partial, int n_blocks, int H, int OBS,
-                                          float* __restrict__ dW0, float* __restrict__ db0) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per output element: lanes stride over the per-block partials, then a fixed-order shuffle tree (deterministic)
+__global__ void __launch_bounds__(256) trunk_wgrad_reduce_kernel(const float* __restrict__ partial, int n_blocks, int H,
+                                                                 int OBS, float* __restrict__ dW0,
+                                                                 float* __restrict__ db0) {
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int n_out = H * (OBS + 1);
     if (k >= n_out) return;
     float s = 0.f;
-    for (int p = 0; p < n_blocks; ++p) s += partial[(int64_t)p * n_out + k];
-    const int n = k / (OBS + 1), i = k % (OBS + 1);
-    if (i < OBS) dW0[n * OBS + i] = s;
-    else db0[n] = s;
+    for (int p = lane; p < n_blocks; p += 32) s += partial[(int64_t)p * n_out + k];
+    s = warp_sum(s);
+    if (lane == 0) {
+        const int n = k / (OBS + 1), i = k % (OBS + 1);
+        if (i < OBS) dW0[n * OBS + i] = s;
+        else db0[n] = s;
+    }
 }
 
 constexpr int kTrunkBlocks = 2 * kNumSMs;
@@ -145,7 +160,7 @@ extern "C" int xb_mlp_trunk_wgrad(const float* dz1, const float* obs, int ld, in
                                reinterpret_cast<const float4*>(dz1), obs, ld, workspace, B, H)));
     XB_LAUNCH_CHECK();
     const int n_out = H * (obs_dim + 1);
-    trunk_wgrad_reduce_kernel<<<(n_out + 127) / 128, 128, 0, s>>>(workspace, kTrunkBlocks, H, obs_dim, dW0, db0);
+    trunk_wgrad_reduce_kernel<<<(n_out + 7) / 8, 256, 0, s>>>(workspace, kTrunkBlocks, H, obs_dim, dW0, db0);
     XB_LAUNCH_CHECK();
     return 0;
 }

@@ -150,7 +150,9 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    // no "memory" clobber: ordered against the other volatile asm (loads, fences, barriers) but plain C++ loads of
+    // read-only tables (bias, head weights) may be scheduled across it
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
 }
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
