@@ -276,6 +276,12 @@ int xb_dense_wgrad(const float* Y0, const float* dout0, const float* w2_0, int n
                    const float* w2_1, int nh1, const float* X, int64_t B, int H_out, int H_in, float slope,
                    float* workspace, float* dW0, float* db0, float* dw2_0, float* db2_0, float* dW1, float* db1,
                    float* dw2_1, float* db2_1, xb_stream_t stream);
+/*   xb_dense_fwd2           two layers that share the input X in ONE launch (actor and critic hidden layers + their heads):
+ *                           even CTAs evaluate layer 0, odd CTAs layer 1, each with its weights resident in shared memory. */
+int xb_dense_fwd2(const float* X, int64_t M, int K, int N, float slope, const float* Whi0, const float* Wlo0,
+                  const float* bias0, float* Y0, const float* head_w0, const float* head_b0, int n_head0, float* head_out0,
+                  const float* Whi1, const float* Wlo1, const float* bias1, float* Y1, const float* head_w1,
+                  const float* head_b1, int n_head1, float* head_out1, int b_resident, xb_stream_t stream);
 int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, int K0, const float* Y1,
                    const float* dout1, const float* w2_1, int nh1, int K1, int64_t M, const float* Wthi,
                    const float* Wtlo, int N, const float* H1, float slope, float* dZ1, xb_stream_t stream);

@@ -63,6 +63,13 @@ struct KParams {
     const float* head_b;
     int n_head;
     float* head_out;
+    // FWD dual mode: odd CTAs evaluate a second layer on the same input (actor | critic in one launch)
+    int dual;
+    const float* bias1;
+    const float* head_w1;
+    const float* head_b1;
+    int n_head1;
+    float* head_out1;
     // DGRAD operand: dz_s[r][k] = (sum_j dout_s[r][j] * w2_s[j][k]) * leaky'(y_s[r][k]);  epilogue: dZ1 = acc * leaky'(H1)
     const float* dout0;
     const float* w2_0;
@@ -74,6 +81,10 @@ struct KParams {
     float* dZ1;
 };
 
+struct TMaps {          // TMA descriptors: A sources, weight hi/lo, output, DGRAD mask tile; *1 = second layer of FWD dual mode
+    CUtensorMap a0, a1, bhi, blo, out, h1, bhi1, blo1, out1;
+};
+
 // byte offset of logical 16-byte chunk c (0..7) of row r inside a [rows][128 B] SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 // same for the 32-byte-atom flavour (SWIZZLE_128B_ATOM_32B): 32-byte chunk index XOR (row & 3)
@@ -83,10 +94,7 @@ __device__ __forceinline__ uint32_t sw32_off(int r, int c) {
 
 template <int N, bool B_RES, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-    dense_kmajor_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                        const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
-                        const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_h1,
-                        const KParams p) {
+    dense_kmajor_kernel(const __grid_constant__ TMaps maps, const KParams p) {
     constexpr int kBTile = N * BK * 4;                  // one k-block of the weight operand, hi or lo
     constexpr int kTmemCols = 2 * N;                    // double-buffered accumulator (power of two for N in {64,128,256})
     constexpr int kChunks = N / 32;                     // 32-column slices of the output tile
@@ -109,6 +117,21 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_tiles = (p.M + BM - 1) / BM;
+    // FWD dual mode: CTA parity selects the layer; both walk the same tiles
+    const int n_src = (MODE == MODE_FWD && p.dual) ? 2 : 1;
+    const int sel = (MODE == MODE_FWD && p.dual) ? (int)(blockIdx.x & 1) : 0;
+    const int64_t tile0 = blockIdx.x / n_src, tile_step = gridDim.x / n_src;
+    const CUtensorMap* map_a0 = &maps.a0;
+    const CUtensorMap* map_a1 = &maps.a1;
+    const CUtensorMap* map_bhi = sel ? &maps.bhi1 : &maps.bhi;
+    const CUtensorMap* map_blo = sel ? &maps.blo1 : &maps.blo;
+    const CUtensorMap* map_out = sel ? &maps.out1 : &maps.out;
+    const CUtensorMap* map_h1 = &maps.h1;
+    const float* e_bias = sel ? p.bias1 : p.bias;
+    const float* e_head_w = sel ? p.head_w1 : p.head_w;
+    const float* e_head_b = sel ? p.head_b1 : p.head_b;
+    const int e_n_head = sel ? p.n_head1 : p.n_head;
+    float* e_head_out = sel ? p.head_out1 : p.head_out;
 
     // ---------------------------------------------------------------- one-time setup
     if (threadIdx.x == 0) {
@@ -130,9 +153,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (MODE == MODE_FWD) {
         // sf: bias[N] | head_w[2][N]
         for (int i = threadIdx.x; i < N; i += kThreads) {
-            sf[i] = p.bias ? p.bias[i] : 0.f;
-            sf[N + i] = p.n_head > 0 ? p.head_w[i] : 0.f;
-            sf[2 * N + i] = p.n_head > 1 ? p.head_w[N + i] : 0.f;
+            sf[i] = e_bias ? e_bias[i] : 0.f;
+            sf[N + i] = e_n_head > 0 ? e_head_w[i] : 0.f;
+            sf[2 * N + i] = e_n_head > 1 ? e_head_w[N + i] : 0.f;
         }
     } else {
         // sf: w2[src][head][256] (4 x 256 floats) | dout[2 tile parities][128 rows][2 src][2 heads]
@@ -153,19 +176,19 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (warp == kProducerWarp) {
         // ============================================================ TMA producer (one thread)
         if (lane == 0) {
-            tma_prefetch_desc(&map_a0);
-            tma_prefetch_desc(&map_bhi);
-            tma_prefetch_desc(&map_blo);
-            if (MODE == MODE_DGRAD) tma_prefetch_desc(&map_a1);
+            tma_prefetch_desc(map_a0);
+            tma_prefetch_desc(map_bhi);
+            tma_prefetch_desc(map_blo);
+            if (MODE == MODE_DGRAD) tma_prefetch_desc(map_a1);
             if (B_RES) {
                 mbar_arrive_expect_tx(bar_bfull, 2u * KB * kBTile);
                 for (int kb = 0; kb < KB; ++kb) {
-                    tma_load_2d(bres + kb * kBTile, &map_bhi, kb * BK, 0, bar_bfull);
-                    tma_load_2d(bres + (KB + kb) * kBTile, &map_blo, kb * BK, 0, bar_bfull);
+                    tma_load_2d(bres + kb * kBTile, map_bhi, kb * BK, 0, bar_bfull);
+                    tma_load_2d(bres + (KB + kb) * kBTile, map_blo, kb * BK, 0, bar_bfull);
                 }
             }
             uint32_t s = 0, ph = 0, it = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
                     XB_TS(0, it, 0);
@@ -173,10 +196,10 @@ __global__ void __launch_bounds__(kThreads, 1)
                     mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
                     const bool src1 = (MODE == MODE_DGRAD) && kb >= p.kb_split;
                     const int kcol = (src1 ? kb - p.kb_split : kb) * BK;
-                    tma_load_2d(st, src1 ? &map_a1 : &map_a0, kcol, (int)(tile * BM), bar_full + 8 * s);
+                    tma_load_2d(st, src1 ? map_a1 : map_a0, kcol, (int)(tile * BM), bar_full + 8 * s);
                     if (!B_RES) {
-                        tma_load_2d(st + kATile, &map_bhi, kb * BK, 0, bar_full + 8 * s);
-                        tma_load_2d(st + kATile + kBTile, &map_blo, kb * BK, 0, bar_full + 8 * s);
+                        tma_load_2d(st + kATile, map_bhi, kb * BK, 0, bar_full + 8 * s);
+                        tma_load_2d(st + kATile + kBTile, map_blo, kb * BK, 0, bar_full + 8 * s);
                     }
                     if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                 }
@@ -187,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (lane == 0) {
             if (B_RES) mbar_wait(bar_bfull, 0);
             uint32_t s = 0, ph = 0, j = 0, lt = 0, it = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++lt) {
                 const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
                 mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
                 const uint32_t d_tmem = tmem_base + acc * N;
@@ -226,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int c = t & 7, r0 = t >> 3;                 // logical 16-byte chunk, first row; rows r0 + 32 i
         float* sdout = sf + 1024;                          // DGRAD: [2 tile parities][128 rows][2 src][2 heads]
         uint32_t s = 0, ph = 0, j = 0, jph = 0, lt = 0, it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++lt) {
             if (MODE == MODE_DGRAD) {
                 if (t < BM) {
                     const int64_t row = tile * BM + t;
@@ -292,11 +315,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         // accumulator -> registers -> swizzled staging tile in shared memory -> TMA store (coalesced, off the LSU path)
         const int r = warp * 32 + lane;                   // row of the tile this thread owns
         uint32_t lt = 0, g = 0;                            // local tile counter, global chunk counter
-        if (MODE == MODE_DGRAD && threadIdx.x == 0 && (int64_t)blockIdx.x < n_tiles) {
+        if (MODE == MODE_DGRAD && threadIdx.x == 0 && tile0 < n_tiles) {
             mbar_arrive_expect_tx(bar_h1, kATile);
-            tma_load_2d(h1_ring, &map_h1, 0, (int)(blockIdx.x * BM), bar_h1);
+            tma_load_2d(h1_ring, map_h1, 0, (int)(tile0 * BM), bar_h1);
         }
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++lt) {
             const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
             const int64_t row = tile * BM + r;
             mbar_wait(bar_tfull + 8 * acc, aph);
@@ -323,11 +346,11 @@ __global__ void __launch_bounds__(kThreads, 1)
                     if (threadIdx.x == 0) {
                         int ncc = cc + (HB > 1 ? 1 : 0);
                         int64_t ntile = tile;
-                        if (ncc == kChunks) { ncc = 0; ntile = tile + gridDim.x; }
+                        if (ncc == kChunks) { ncc = 0; ntile = tile + tile_step; }
                         if (HB > 1 ? ntile < n_tiles : g > 0) {
                             const uint32_t nb = HB > 1 ? ((g + 1) & 1) : 0;
                             mbar_arrive_expect_tx(bar_h1 + 8 * nb, kATile);
-                            tma_load_2d(h1_ring + nb * kATile, &map_h1, ncc * 32, (int)(ntile * BM), bar_h1 + 8 * nb);
+                            tma_load_2d(h1_ring + nb * kATile, map_h1, ncc * 32, (int)(ntile * BM), bar_h1 + 8 * nb);
                         }
                     }
                     hbuf = h1_ring + hb * kATile;
@@ -360,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 fence_proxy_async_smem();
                 bar_sync_named(3, 128);
                 if (threadIdx.x == 0) {
-                    tma_store_2d(&map_out, obuf, cc * 32, (int)(tile * BM));
+                    tma_store_2d(map_out, obuf, cc * 32, (int)(tile * BM));
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
@@ -369,8 +392,8 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
             if (threadIdx.x == 0) XB_TS(3, lt, 7);
             if (MODE == MODE_FWD && row < p.M) {
-                if (p.n_head > 0) p.head_out[row * p.n_head] = h0 + p.head_b[0];
-                if (p.n_head > 1) p.head_out[row * p.n_head + 1] = h1 + p.head_b[1];
+                if (e_n_head > 0) e_head_out[row * e_n_head] = h0 + e_head_b[0];
+                if (e_n_head > 1) e_head_out[row * e_n_head + 1] = h1 + e_head_b[1];
             }
         }
         if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -405,8 +428,7 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int N, int K, 
 }
 
 template <int N, bool B_RES, int MODE>
-static int launch_kmajor(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mbhi, const CUtensorMap& mblo,
-                         const CUtensorMap& mout, const CUtensorMap& mh1, KParams p, cudaStream_t s) {
+static int launch_kmajor(const TMaps& maps, KParams p, cudaStream_t s) {
     const int kBTile = N * BK * 4;
     const int bres = B_RES ? 2 * p.KB * kBTile : 0;
     const int stage = kATile + (B_RES ? 0 : 2 * kBTile);
@@ -434,27 +456,27 @@ static int launch_kmajor(const CUtensorMap& ma0, const CUtensorMap& ma1, const C
         attr_set = true;
     }
     const int64_t tiles = (p.M + BM - 1) / BM;
-    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    kern<<<grid, kThreads, smem, s>>>(ma0, ma1, mbhi, mblo, mout, mh1, p);
+    const int n_src = (MODE == MODE_FWD && p.dual) ? 2 : 1;
+    const int64_t want = tiles * n_src;
+    const int grid = (int)(want < kNumSMs ? want : (kNumSMs / n_src) * n_src);
+    kern<<<grid, kThreads, smem, s>>>(maps, p);
     XB_LAUNCH_CHECK();
     return 0;
 }
 
 template <int MODE>
-static int dispatch_kmajor(int N, bool bres, const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mbhi,
-                           const CUtensorMap& mblo, const CUtensorMap& mout, const CUtensorMap& mh1, const KParams& p,
-                           cudaStream_t s) {
+static int dispatch_kmajor(int N, bool bres, const TMaps& maps, const KParams& p, cudaStream_t s) {
     const int kBTile = N * BK * 4;
     if (bres && (kMaxSmem - 1024 - kMiscBytes - 2 * p.KB * kBTile) < (2 + 1 + 1 + (MODE == MODE_DGRAD)) * kATile) bres = false;
     switch (N) {
         case 64:
-            return bres ? launch_kmajor<64, true, MODE>(ma0, ma1, mbhi, mblo, mout, mh1, p, s)
-                        : launch_kmajor<64, false, MODE>(ma0, ma1, mbhi, mblo, mout, mh1, p, s);
+            return bres ? launch_kmajor<64, true, MODE>(maps, p, s)
+                        : launch_kmajor<64, false, MODE>(maps, p, s);
         case 128:
-            return bres ? launch_kmajor<128, true, MODE>(ma0, ma1, mbhi, mblo, mout, mh1, p, s)
-                        : launch_kmajor<128, false, MODE>(ma0, ma1, mbhi, mblo, mout, mh1, p, s);
+            return bres ? launch_kmajor<128, true, MODE>(maps, p, s)
+                        : launch_kmajor<128, false, MODE>(maps, p, s);
         case 256:
-            return launch_kmajor<256, false, MODE>(ma0, ma1, mbhi, mblo, mout, mh1, p, s);
+            return launch_kmajor<256, false, MODE>(maps, p, s);
         default:
             return XB_E_UNSUPPORTED;
     }
@@ -815,29 +837,71 @@ extern "C" int xb_dense_split_weights(const float* W, int N, int K, float* hi, f
     return 0;
 }
 
-extern "C" int xb_dense_fwd(const float* X, int64_t M, int K, const float* Whi, const float* Wlo, int N,
-                            const float* bias, float slope, float* Y, const float* head_w, const float* head_b,
-                            int n_head, float* head_out, int b_resident, xb_stream_t stream) {
-    if (!X || !Whi || !Wlo || !Y || M <= 0) return XB_E_BADARG;
-    if (K % BK != 0 || K < BK || K > 256 || n_head < 0 || n_head > 2 || (n_head && (!head_w || !head_b || !head_out)))
-        return XB_E_UNSUPPORTED;
-    if (!al16(X) || !al16(Whi) || !al16(Wlo) || !al16(Y)) return XB_E_UNSUPPORTED;
-    CUtensorMap ma, mbhi, mblo, mout;
-    if (!xb_make_map_f32_2d(&ma, X, M, K, K, BM, BK, 1) || !xb_make_map_f32_2d(&mbhi, Whi, N, K, K, N, BK, 1) ||
-        !xb_make_map_f32_2d(&mblo, Wlo, N, K, K, N, BK, 1) || !xb_make_map_f32_2d(&mout, Y, M, N, N, BM, 32, 1))
-        return XB_E_DRIVER;
+static int dense_fwd_impl(const float* X, int64_t M, int K, int N, float slope, int n_layers, const float* const* Whi,
+                          const float* const* Wlo, const float* const* bias, float* const* Y, const float* const* head_w,
+                          const float* const* head_b, const int* n_head, float* const* head_out, int b_resident,
+                          xb_stream_t stream) {
+    if (!X || M <= 0) return XB_E_BADARG;
+    if (K % BK != 0 || K < BK || K > 256 || !al16(X)) return XB_E_UNSUPPORTED;
+    TMaps maps;
+    if (!xb_make_map_f32_2d(&maps.a0, X, M, K, K, BM, BK, 1)) return XB_E_DRIVER;
+    maps.a1 = maps.a0;
+    for (int l = 0; l < n_layers; ++l) {
+        if (!Whi[l] || !Wlo[l] || !Y[l]) return XB_E_BADARG;
+        if (n_head[l] < 0 || n_head[l] > 2 || (n_head[l] && (!head_w[l] || !head_b[l] || !head_out[l]))) return XB_E_UNSUPPORTED;
+        if (!al16(Whi[l]) || !al16(Wlo[l]) || !al16(Y[l])) return XB_E_UNSUPPORTED;
+        CUtensorMap* mh = l ? &maps.bhi1 : &maps.bhi;
+        CUtensorMap* ml = l ? &maps.blo1 : &maps.blo;
+        CUtensorMap* mo = l ? &maps.out1 : &maps.out;
+        if (!xb_make_map_f32_2d(mh, Whi[l], N, K, K, N, BK, 1) || !xb_make_map_f32_2d(ml, Wlo[l], N, K, K, N, BK, 1) ||
+            !xb_make_map_f32_2d(mo, Y[l], M, N, N, BM, 32, 1))
+            return XB_E_DRIVER;
+    }
+    if (n_layers == 1) { maps.bhi1 = maps.bhi; maps.blo1 = maps.blo; maps.out1 = maps.out; }
+    maps.h1 = maps.out;
     KParams p{};
     p.M = M;
     p.KB = K / BK;
     p.kb_split = p.KB;
     p.slope = slope;
-    p.bias = bias;
-    p.Y = Y;
-    p.head_w = head_w;
-    p.head_b = head_b;
-    p.n_head = n_head;
-    p.head_out = head_out;
-    return dispatch_kmajor<MODE_FWD>(N, b_resident != 0, ma, ma, mbhi, mblo, mout, mout, p, (cudaStream_t)stream);
+    p.bias = bias[0];
+    p.Y = Y[0];
+    p.head_w = head_w[0];
+    p.head_b = head_b[0];
+    p.n_head = n_head[0];
+    p.head_out = head_out[0];
+    p.dual = n_layers == 2;
+    if (p.dual) {
+        p.bias1 = bias[1];
+        p.head_w1 = head_w[1];
+        p.head_b1 = head_b[1];
+        p.n_head1 = n_head[1];
+        p.head_out1 = head_out[1];
+    }
+    return dispatch_kmajor<MODE_FWD>(N, b_resident != 0, maps, p, (cudaStream_t)stream);
+}
+
+extern "C" int xb_dense_fwd(const float* X, int64_t M, int K, const float* Whi, const float* Wlo, int N,
+                            const float* bias, float slope, float* Y, const float* head_w, const float* head_b,
+                            int n_head, float* head_out, int b_resident, xb_stream_t stream) {
+    return dense_fwd_impl(X, M, K, N, slope, 1, &Whi, &Wlo, &bias, &Y, &head_w, &head_b, &n_head, &head_out, b_resident,
+                          stream);
+}
+
+extern "C" int xb_dense_fwd2(const float* X, int64_t M, int K, int N, float slope, const float* Whi0, const float* Wlo0,
+                             const float* bias0, float* Y0, const float* head_w0, const float* head_b0, int n_head0,
+                             float* head_out0, const float* Whi1, const float* Wlo1, const float* bias1, float* Y1,
+                             const float* head_w1, const float* head_b1, int n_head1, float* head_out1, int b_resident,
+                             xb_stream_t stream) {
+    const float* Whi[2] = {Whi0, Whi1};
+    const float* Wlo[2] = {Wlo0, Wlo1};
+    const float* bias[2] = {bias0, bias1};
+    float* Y[2] = {Y0, Y1};
+    const float* hw[2] = {head_w0, head_w1};
+    const float* hb[2] = {head_b0, head_b1};
+    const int nh[2] = {n_head0, n_head1};
+    float* ho[2] = {head_out0, head_out1};
+    return dense_fwd_impl(X, M, K, N, slope, 2, Whi, Wlo, bias, Y, hw, hb, nh, ho, b_resident, stream);
 }
 
 extern "C" int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, int K0, const float* Y1,
@@ -849,12 +913,13 @@ extern "C" int xb_dense_dgrad(const float* Y0, const float* dout0, const float* 
     if (!Y1) K1 = 0;
     if (!al16(Y0) || !al16(Wthi) || !al16(Wtlo) || !al16(H1) || !al16(dZ1) || (Y1 && !al16(Y1))) return XB_E_UNSUPPORTED;
     const int K = K0 + K1;
-    CUtensorMap ma0, ma1, mbhi, mblo, mout, mh1;
-    if (!xb_make_map_f32_2d(&mout, dZ1, M, N, N, BM, 32, 1) || !xb_make_map_f32_2d(&mh1, H1, M, N, N, BM, 32, 1) ||
-        !xb_make_map_f32_2d(&ma0, Y0, M, K0, K0, BM, BK, 1) ||
-        !xb_make_map_f32_2d(&ma1, Y1 ? Y1 : Y0, M, Y1 ? K1 : K0, Y1 ? K1 : K0, BM, BK, 1) ||
-        !xb_make_map_f32_2d(&mbhi, Wthi, N, K, K, N, BK, 1) || !xb_make_map_f32_2d(&mblo, Wtlo, N, K, K, N, BK, 1))
+    TMaps maps;
+    if (!xb_make_map_f32_2d(&maps.out, dZ1, M, N, N, BM, 32, 1) || !xb_make_map_f32_2d(&maps.h1, H1, M, N, N, BM, 32, 1) ||
+        !xb_make_map_f32_2d(&maps.a0, Y0, M, K0, K0, BM, BK, 1) ||
+        !xb_make_map_f32_2d(&maps.a1, Y1 ? Y1 : Y0, M, Y1 ? K1 : K0, Y1 ? K1 : K0, BM, BK, 1) ||
+        !xb_make_map_f32_2d(&maps.bhi, Wthi, N, K, K, N, BK, 1) || !xb_make_map_f32_2d(&maps.blo, Wtlo, N, K, K, N, BK, 1))
         return XB_E_DRIVER;
+    maps.bhi1 = maps.bhi; maps.blo1 = maps.blo; maps.out1 = maps.out;
     KParams p{};
     p.M = M;
     p.KB = K / BK;
@@ -868,7 +933,7 @@ extern "C" int xb_dense_dgrad(const float* Y0, const float* dout0, const float* 
     p.nh1 = Y1 ? nh1 : 0;
     p.H1 = H1;
     p.dZ1 = dZ1;
-    return dispatch_kmajor<MODE_DGRAD>(N, false, ma0, ma1, mbhi, mblo, mout, mh1, p, (cudaStream_t)stream);
+    return dispatch_kmajor<MODE_DGRAD>(N, false, maps, p, (cudaStream_t)stream);
 }
 
 extern "C" int xb_dense_wgrad_workspace_floats(int H_in) { return kNumSMs * (128 * (H_in + 4) + 256 + 2); }

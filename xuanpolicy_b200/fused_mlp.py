@@ -110,10 +110,9 @@ class FusedActorCritic:
         if refresh:
             self.refresh_weights()
         ops.mlp_trunk_fwd(obs, self.l0.weight.data, self.l0.bias.data, self.slope, b["h1"])
-        ops.dense_fwd(b["h1"], self.wa_hi, self.wa_lo, self.la1.bias.data, self.slope, b["ya"], self.la2.weight.data,
-                      self.la2.bias.data, b["act"])
-        ops.dense_fwd(b["h1"], self.wc_hi, self.wc_lo, self.lc1.bias.data, self.slope, b["yc"], self.lc2.weight.data,
-                      self.lc2.bias.data, b["v"])
+        ops.dense_fwd2(b["h1"], self.slope,
+                       (self.wa_hi, self.wa_lo, self.la1.bias.data, b["ya"], self.la2.weight.data, self.la2.bias.data, b["act"]),
+                       (self.wc_hi, self.wc_lo, self.lc1.bias.data, b["yc"], self.lc2.weight.data, self.lc2.bias.data, b["v"]))
         self._last = (obs, b)
         return b["act"], b["v"][:, 0]
 

@@ -203,6 +203,17 @@ def dense_fwd(x, w_hi, w_lo, bias, slope, y, head_w=None, head_b=None, head_out=
               1 if b_resident else 0, _stream())
 
 
+def dense_fwd2(x, slope, layer0, layer1, b_resident=True):
+    """layerK = (w_hi, w_lo, bias, y, head_w, head_b, head_out): two layers on the same input in one launch."""
+    M, K = x.shape
+    N = layer0[0].shape[0]
+    args = []
+    for w_hi, w_lo, bias, y, head_w, head_b, head_out in (layer0, layer1):
+        args += [_p(w_hi, F32), _p(w_lo, F32), _p(bias, F32), _p(y, F32), _p(head_w, F32), _p(head_b, F32),
+                 head_w.shape[0] if head_w is not None else 0, _p(head_out, F32)]
+    _lib.call("xb_dense_fwd2", _p(x, F32), M, K, N, float(slope), *args, 1 if b_resident else 0, _stream())
+
+
 def dense_dgrad(y0, dout0, w2_0, y1, dout1, w2_1, wt_hi, wt_lo, h1, slope, dz1):
     M, K0 = y0.shape
     _lib.call("xb_dense_dgrad", _p(y0, F32), _p(dout0, F32), _p(w2_0, F32), w2_0.shape[0], K0, _p(y1, F32),
