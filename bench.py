@@ -46,6 +46,15 @@ WORKLOADS = {
 HBM_FALLBACK_GBS = 6650.0
 
 
+def measured_tf32_peak():
+    """Dense TF32 tensor-pipe ceiling in TFLOP/s: half the measured cuBLAS bf16 burst throughput (same pipe, K per
+    instruction halves), else half the fallback."""
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["bf16_tflops"]) / 2
+    return 1590.0 / 2
+
+
 def measured_peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -163,8 +172,15 @@ def time_phases(agent, flush):
 def count_launches(agent):
     """Hand-written kernel launches inside one PPO iteration (counted from the calls the agent makes)."""
     T, E, M = agent.n_steps, agent.n_epoch, agent.buffer_size // agent.batch_size
-    per_rollout = T * (3 + 5) + 5 + 2 + 1  # per step: sample, env_step, store, 3 bias+act, 2 head; bootstrap fwd; GAE + pack; counter
-    per_update = 1 + 1 + 2 + 5 + 3         # gather, loss, grad-norm + adam, fwd: 3 bias+act + 2 head, bwd: 2 head+act + 1 act+bias
+    if agent.learner._fused is not None:
+        # rollout: weight split (2); per step trunk, hidden x2 (one launch), sample, env_step, store; bootstrap forward (2);
+        # GAE + record packing (2); counter (1)
+        per_rollout = 2 + T * 5 + 2 + 2 + 1
+        # update: gather, weight split (2), trunk, hidden, loss, dgrad, wgrad + reduce, trunk wgrad + reduce, grad-norm, adam
+        per_update = 1 + 2 + 1 + 1 + 1 + 1 + 2 + 2 + 2
+    else:
+        per_rollout = T * (3 + 5) + 5 + 2 + 1  # per step: sample, env_step, store, 3 bias+act, 2 head; bootstrap fwd; GAE + pack; counter
+        per_update = 1 + 1 + 2 + 5 + 3         # gather, loss, grad-norm + adam, fwd: 3 bias+act + 2 head, bwd: 2 head+act + 1 act+bias
     return per_rollout + E * M * per_update
 
 
@@ -192,12 +208,17 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
     N, T, B = agent.n_envs, agent.n_steps, agent.batch_size
     od, gauss = mem.obs_dim, not agent.discrete
     out = {}
+    tf32_peak = measured_tf32_peak()
 
-    def add(name, fn, bytes_per_launch, launches):
+    def add(name, fn, bytes_per_launch, launches, flops=None):
         mean_ms, min_ms = time_kernel(fn, flush)
         gbs = bytes_per_launch / (mean_ms * 1e-3) / 1e9
         out[name] = {"ms": round(mean_ms, 5), "min_ms": round(min_ms, 5), "launches_per_step": launches,
                      "bytes_per_launch": int(bytes_per_launch), "achieved_gbs": round(gbs, 2), "frac": round(gbs / peak, 5)}
+        if flops:   # tensor-core kernels: fp32-equivalent GEMM flops (2MNK); the 3xTF32 split issues 3x that on the tensor pipe
+            tf = flops / (mean_ms * 1e-3) / 1e12
+            out[name].update({"gemm_tflops": round(tf, 2), "tensor_pipe_tflops_tf32": round(3 * tf, 2),
+                              "tensor_frac_of_tf32_peak": round(3 * tf / tf32_peak, 4)})
 
     with torch.no_grad():
         dist, v = agent._policy_forward(agent._x[agent._cur])
@@ -219,8 +240,13 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
     add("gather_records" if mem.packed else "gather_obs_advstats", lambda: lr.stage_gather(mem, idx),
         B * ((8 + 32 + 4 * od + 16) if mem.packed else (8 + 16 + 4 * od + 4)), launches_per_step["updates"])
     mb = lr.stage_gather(mem, idx)
+    fused = lr._fused if (lr._fused is not None and B >= lr._fused.MIN_ROWS) else None
     with torch.no_grad():
-        _, a_dist, v_pred = agent.policy(mb["obs"])
+        if fused is not None:
+            act_out, v_pred = fused.forward(mb["obs"])
+            a_dist = fused.dist_params(act_out)
+        else:
+            _, a_dist, v_pred = agent.policy(mb["obs"])
     vp = v_pred.contiguous()
     dv = torch.empty_like(vp)
     kw = dict(clip_range=lr.clip_range, vf_coef=lr.vf_coef, ent_coef=lr.ent_coef, inv_batch=1.0 / B, adv_stats=mb["stats"],
@@ -234,7 +260,7 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
     if gauss:
         mu, std = a_dist.get_param()
         mu = mu.contiguous()
-        logstd = std.log().contiguous()
+        logstd = agent.policy.actor.logstd.detach() if std is None else std.log().contiguous()
         dmu = torch.empty_like(mu)
         dls = torch.empty(mu.shape[1], dtype=torch.float64, device="cuda")
         add("ppo_loss_fwd_bwd", lambda: ops.ppo_loss_gaussian(mu, logstd, vp, *margs, dmu, dls, dv, lr._scalars, **kw),
@@ -244,23 +270,45 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
         dl = torch.empty_like(logits)
         add("ppo_loss_fwd_bwd", lambda: ops.ppo_loss_categorical(logits, vp, *margs, dl, dv, lr._scalars, **kw),
             B * (40 if mem.packed else 48), launches_per_step["updates"])
-    # the non-GEMM half of the MLP (csrc/mlp_epilogue.cu): per update, one forward and one backward epilogue per
-    # Linear+LeakyReLU block (3 blocks: representation, actor hidden, critic hidden)
     H = agent.config.representation_hidden_size[-1]
-    yb = torch.randn((B, H), device="cuda")
-    dyb = torch.randn((B, H), device="cuda")
-    dzb, dbb = torch.empty_like(dyb), torch.empty(H, device="cuda")
-    bias = torch.randn(H, device="cuda")
-    ws32 = torch.zeros(4 + 592 * 1024, dtype=torch.float32, device="cuda")
-    A_out = 1 if gauss else 2
-    w2, b2 = torch.randn((A_out, H), device="cuda"), torch.randn(A_out, device="cuda")
-    hout, dout = torch.empty((B, A_out), device="cuda"), torch.randn((B, A_out), device="cuda")
-    dw2, db2 = torch.empty_like(w2), torch.empty_like(b2)
     upd = launches_per_step["updates"]
-    add("mlp_bias_act_fwd", lambda: ops.bias_act_fwd(yb, bias, 0.01), B * H * 8, 3 * upd)
-    add("mlp_head_fwd", lambda: ops.head_fwd(yb, w2, b2, hout), B * (H + A_out) * 4, 2 * upd)
-    add("mlp_head_bwd_act", lambda: ops.head_bwd_act(dout, yb, w2, 0.01, dzb, dbb, dw2, db2, ws32), B * (2 * H + A_out) * 4, 2 * upd)
-    add("mlp_act_bias_bwd", lambda: ops.act_bias_bwd(dyb, yb, 0.01, dzb, dbb, ws32), B * H * 12, 1 * upd)
+    A_out = 1 if gauss else 2
+    if fused is not None:
+        # the MLP on the tcgen05 dense kernels (csrc/dense_tc.cu) + the SIMT trunk layer (csrc/mlp_trunk.cu), update shape
+        obs_u = mb["obs"]
+        bu = fused._buffers(B)
+        if bu["dz1"] is None:
+            bu["dz1"] = torch.empty(B, H, dtype=torch.float32, device="cuda")
+        dact = torch.randn((B, A_out), device="cuda") / B
+        dv2 = torch.randn((B, 1), device="cuda") / B
+        f4 = 4 * B * H
+        add("mlp_split_weights", lambda: fused.refresh_weights(), 2 * H * H * 4 * 5, upd + 1)
+        add("mlp_trunk_fwd", lambda: fused.stage_trunk(obs_u, bu), B * od * 4 + f4, upd)
+        add("dense_fwd2_tc", lambda: fused.stage_hidden(bu), 3 * f4 + B * (A_out + 1) * 4, upd, flops=2 * 2.0 * B * H * H)
+        add("dense_dgrad_tc", lambda: fused.stage_dgrad(bu, dact, dv2), 4 * f4 + B * (A_out + 1) * 4, upd, flops=2.0 * B * 2 * H * H)
+        add("dense_wgrad_tc", lambda: fused.stage_wgrad(bu, dact, dv2), 3 * f4 + B * (A_out + 1) * 4, upd,
+            flops=2 * 2.0 * B * H * (H + 1))
+        add("mlp_trunk_wgrad", lambda: fused.stage_trunk_wgrad(obs_u, bu), f4 + B * od * 4, upd)
+        # rollout shape: 2N rows (the obs to act on + the previous step's terminal obs)
+        x_r = agent._x[agent._cur][:, :od]
+        br = fused._buffers(2 * N)
+        add("mlp_trunk_fwd_rollout", lambda: fused.stage_trunk(x_r, br), 2 * N * (od * 4 + H * 4), T + 1)
+        add("dense_fwd2_tc_rollout", lambda: fused.stage_hidden(br), 3 * 4 * 2 * N * H, T + 1, flops=2 * 2.0 * 2 * N * H * H)
+    else:
+        # torch/cuBLAS GEMMs + the non-GEMM half of the MLP (csrc/mlp_epilogue.cu): per update, one forward and one
+        # backward epilogue per Linear+LeakyReLU block (3 blocks: representation, actor hidden, critic hidden)
+        yb = torch.randn((B, H), device="cuda")
+        dyb = torch.randn((B, H), device="cuda")
+        dzb, dbb = torch.empty_like(dyb), torch.empty(H, device="cuda")
+        bias = torch.randn(H, device="cuda")
+        ws32 = torch.zeros(4 + 592 * 1024, dtype=torch.float32, device="cuda")
+        w2, b2 = torch.randn((A_out, H), device="cuda"), torch.randn(A_out, device="cuda")
+        hout, dout = torch.empty((B, A_out), device="cuda"), torch.randn((B, A_out), device="cuda")
+        dw2, db2 = torch.empty_like(w2), torch.empty_like(b2)
+        add("mlp_bias_act_fwd", lambda: ops.bias_act_fwd(yb, bias, 0.01), B * H * 8, 3 * upd)
+        add("mlp_head_fwd", lambda: ops.head_fwd(yb, w2, b2, hout), B * (H + A_out) * 4, 2 * upd)
+        add("mlp_head_bwd_act", lambda: ops.head_bwd_act(dout, yb, w2, 0.01, dzb, dbb, dw2, db2, ws32), B * (2 * H + A_out) * 4, 2 * upd)
+        add("mlp_act_bias_bwd", lambda: ops.act_bias_bwd(dyb, yb, 0.01, dzb, dbb, ws32), B * H * 12, 1 * upd)
     snap = agent._snapshot()
     add("clip_adam", lambda: lr.stage_optimizer(), lr._flat.n * (4 + 16 + 12), launches_per_step["updates"])
     agent._restore(snap)
@@ -357,6 +405,7 @@ def run_ours(args):
     launches_per_step = {"updates": agent.n_epoch * (agent.buffer_size // agent.batch_size)}
     kernels = kernel_rooflines(agent, flush, peak, launches_per_step, with_c4=not args.no_c4, world=world) if rank == 0 or world > 1 else {}
     params = agent.learner._flat.n_params
+    fused_on = agent.learner._fused is not None and agent.batch_size >= agent.learner._fused.MIN_ROWS
     del agent
     torch.cuda.empty_cache()
 
@@ -381,7 +430,8 @@ def run_ours(args):
         "metric": "PPO env-steps/s", "value": round(value, 1), "unit": "env-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(secs / args.steps * 1e3, 4),
         "higher_is_better": True, "scaling": "strong" if wl.get("strong") else "weak", "vs_baseline": None,
-        "dtype": ("tf32 MLP GEMMs" if args.tf32 else "f32 MLP GEMMs") + ", f32 loss/optimizer, f64 GAE carry and env physics",
+        "dtype": ("f32-accurate MLP GEMMs (3xTF32 split on the tcgen05 tensor cores, fp32 accumulate)" if fused_on else
+                  ("tf32 MLP GEMMs" if args.tf32 else "f32 MLP GEMMs (cuBLAS SIMT)")) + ", f32 loss/optimizer, f64 GAE carry and env physics",
         "data": "synthetic",
         "config": {"workload": wl["name"], "envs_per_gpu": n_local, "horizon": horizon, "n_epoch": 8,
                    "minibatch_per_gpu": mb, "mlp_hidden": wl["hidden"], "params": params, "gamma": wl["gamma"],
@@ -394,8 +444,10 @@ def run_ours(args):
         "gpu_launches": launches * args.steps,
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": kd["achieved_gbs"], "peak": peak, "unit": "GB/s",
                      "frac": kd["frac"], "traffic": None, "peak_source": peak_src,
-                     "note": "largest share of the step among the hand-written kernels; batches this small are "
-                             "launch/latency-bound (working set is L2-resident) — see kernels.gae_c4_* for the HBM-bound shape"},
+                     "tensor": {k: kd[k] for k in ("gemm_tflops", "tensor_pipe_tflops_tf32", "tensor_frac_of_tf32_peak") if k in kd},
+                     "note": "kernel with the largest share of the step (CUDA-event time x launches per step); achieved = "
+                             "algorithmic bytes / time.  Dense kernels: HBM time and 3xTF32 tensor-pipe time are about equal "
+                             "at this shape, both fractions are given.  See kernels.gae_c4_* for the pure HBM-bound shape"},
         "kernels": kernels,
         "phases": phases,
         "cpu_baseline": cpu,

@@ -17,6 +17,8 @@
 //                                tcgen05.commit releases ring slots / publishes the accumulator
 //   warps 0-3   epilogue       : tcgen05.ld the 128 x N fp32 accumulator (double-buffered in TMEM so the next
 //                                tile's MMAs overlap), bias + LeakyReLU (+ fused narrow head) / activation mask, store
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -92,12 +94,128 @@ __device__ __forceinline__ uint32_t sw32_off(int r, int c) {
     return (uint32_t)(r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4)));
 }
 
+// ------------------------------------------------------------------------------------------------ epilogue (warps 0-3)
+// Each warp owns TMEM lanes 32w..32w+31 = 32 rows of the tile and is fully autonomous: accumulator chunk -> registers
+// (tcgen05.ld) -> bias/activation/head or activation mask -> its own swizzled 4 KB staging sub-tile -> its own TMA
+// store of a [32 rows][32 cols] box (coalesced, off the LSU store path; rows beyond M are clipped by the tensor map).
+// DGRAD: the trunk-activation sub-tile for the mask is TMA-loaded per warp, one chunk ahead (double-buffered).
+struct EpiCtx {
+    uint32_t tmem_base, bar_tfull, bar_tempty, bar_h1w, out_ring, h1_ring;
+    int O, HB;
+    int64_t tile0, tile_step, n_tiles, M;
+    const CUtensorMap* map_out;
+    const CUtensorMap* map_h1;
+    const float* sf;
+    float slope;
+    int n_head;
+    const float* head_b;
+    float* head_out;
+#ifdef XB_DENSE_TS
+    long long* ts;
+#endif
+};
+
+template <int N, int MODE>
+__device__ __forceinline__ void epilogue_warp(const EpiCtx& c, int warp, int lane) {
+    constexpr int kChunks = N / 32;
+    constexpr uint32_t kSub = 32 * 128;                               // one warp's sub-tile: 32 rows x 128 B
+    const uint32_t bar_h1 = c.bar_h1w + warp * 16;                    // 2 barriers per warp
+    uint32_t lt = 0, g = 0;
+    if (MODE == MODE_DGRAD && lane == 0 && c.tile0 < c.n_tiles) {
+        mbar_arrive_expect_tx(bar_h1, kSub);
+        tma_load_2d(c.h1_ring + warp * kSub, c.map_h1, 0, (int)(c.tile0 * BM + warp * 32), bar_h1);
+    }
+    for (int64_t tile = c.tile0; tile < c.n_tiles; tile += c.tile_step, ++lt) {
+        const uint32_t acc = lt & 1, tph = (lt >> 1) & 1;
+        const int64_t row = tile * BM + warp * 32 + lane;
+        mbar_wait(c.bar_tfull + 8 * acc, tph);
+#ifdef XB_DENSE_TS
+        if (threadIdx.x == 0 && c.ts && blockIdx.x == 0 && lt < 64) c.ts[(3 * 64 + lt) * 8 + 0] = clock64();
+#endif
+        tc_fence_after();
+        const uint32_t taddr = c.tmem_base + ((uint32_t)(warp * 32) << 16) + acc * N;
+        float h0 = 0.f, h1 = 0.f;
+#pragma unroll 1
+        for (int cc = 0; cc < kChunks; ++cc, ++g) {
+#ifdef XB_DENSE_TS
+            if (threadIdx.x == 0 && c.ts && blockIdx.x == 0 && lt < 64) c.ts[(3 * 64 + lt) * 8 + 1 + cc] = clock64();
+#endif
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + cc * 32, v);
+            // the staging sub-tile about to be overwritten must have been read out by its previous TMA store
+            if (lane == 0) {
+                if (c.O > 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            __syncwarp();
+            const uint32_t obuf = c.out_ring + (g % (uint32_t)c.O) * kATile + warp * kSub;
+            uint32_t hbuf = 0;
+            if (MODE == MODE_DGRAD) {
+                const uint32_t hb = c.HB > 1 ? (g & 1) : 0, hph = c.HB > 1 ? ((g >> 1) & 1) : (g & 1);
+                if (lane == 0) {       // prefetch the next chunk's mask sub-tile (or, single-buffered, load this chunk's now)
+                    int ncc = cc + (c.HB > 1 ? 1 : 0);
+                    int64_t ntile = tile;
+                    if (ncc == kChunks) { ncc = 0; ntile = tile + c.tile_step; }
+                    if (c.HB > 1 ? ntile < c.n_tiles : g > 0) {
+                        const uint32_t nb = c.HB > 1 ? ((g + 1) & 1) : 0;
+                        mbar_arrive_expect_tx(bar_h1 + 8 * nb, kSub);
+                        tma_load_2d(c.h1_ring + nb * kATile + warp * kSub, c.map_h1, ncc * 32,
+                                    (int)(ntile * BM + warp * 32), bar_h1 + 8 * nb);
+                    }
+                }
+                hbuf = c.h1_ring + hb * kATile + warp * kSub;
+                mbar_wait(bar_h1 + 8 * hb, hph);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 f = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                if (MODE == MODE_FWD) {
+                    const float* b = c.sf + cc * 32 + 4 * q;
+                    f.x += b[0]; f.y += b[1]; f.z += b[2]; f.w += b[3];
+                    f.x = f.x > 0.f ? f.x : f.x * c.slope;
+                    f.y = f.y > 0.f ? f.y : f.y * c.slope;
+                    f.z = f.z > 0.f ? f.z : f.z * c.slope;
+                    f.w = f.w > 0.f ? f.w : f.w * c.slope;
+                    const float* w = b + N;
+                    h0 += f.x * w[0] + f.y * w[1] + f.z * w[2] + f.w * w[3];
+                    h1 += f.x * w[N] + f.y * w[N + 1] + f.z * w[N + 2] + f.w * w[N + 3];
+                } else {
+                    const float4 m = lds128(hbuf + sw128_off(lane, q));
+                    f.x *= m.x > 0.f ? 1.f : c.slope;
+                    f.y *= m.y > 0.f ? 1.f : c.slope;
+                    f.z *= m.z > 0.f ? 1.f : c.slope;
+                    f.w *= m.w > 0.f ? 1.f : c.slope;
+                }
+                sts128(obuf + sw128_off(lane, q), f);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(c.map_out, obuf, cc * 32, (int)(tile * BM + warp * 32));
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(c.bar_tempty + 8 * acc);
+#ifdef XB_DENSE_TS
+        if (threadIdx.x == 0 && c.ts && blockIdx.x == 0 && lt < 64) c.ts[(3 * 64 + lt) * 8 + 7] = clock64();
+#endif
+        if (MODE == MODE_FWD && row < c.M) {
+            if (c.n_head > 0) c.head_out[row * c.n_head] = h0 + c.head_b[0];
+            if (c.n_head > 1) c.head_out[row * c.n_head + 1] = h1 + c.head_b[1];
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <int N, bool B_RES, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
     dense_kmajor_kernel(const __grid_constant__ TMaps maps, const KParams p) {
     constexpr int kBTile = N * BK * 4;                  // one k-block of the weight operand, hi or lo
     constexpr int kTmemCols = 2 * N;                    // double-buffered accumulator (power of two for N in {64,128,256})
-    constexpr int kChunks = N / 32;                     // 32-column slices of the output tile
     constexpr uint32_t kIdesc = umma_idesc_tf32(BM, N, 0, 0);
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -111,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t misc = h1_ring + (MODE == MODE_DGRAD ? (uint32_t)HB * kATile : 0u);
     const uint32_t bar_full = misc, bar_conv = misc + 64, bar_empty = misc + 128, bar_loempty = misc + 192;
     const uint32_t bar_tfull = misc + 224, bar_tempty = misc + 240, bar_bfull = misc + 256;
-    const uint32_t tmem_slot = misc + 264, bar_h1 = misc + 272;
+    const uint32_t tmem_slot = misc + 264, bar_h1w = misc + 352;
     unsigned char* misc_ptr = smem_raw + (misc - smem_u32(smem_raw));
     float* sf = reinterpret_cast<float*>(misc_ptr + 512);                    // per-mode float scratch (<= 8 KB)
 
@@ -144,8 +262,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int a = 0; a < 2; ++a) {
             mbar_init(bar_tfull + 8 * a, 1);
             mbar_init(bar_tempty + 8 * a, 4);
-            mbar_init(bar_h1 + 8 * a, 1);
         }
+        for (int a = 0; a < 8; ++a) mbar_init(bar_h1w + 8 * a, 1);
         mbar_init(bar_bfull, 1);
         mbar_fence_init();
     }
@@ -311,92 +429,17 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
         }
     } else {
-        // ============================================================ epilogue warps 0-3 (TMEM lanes 32w..32w+31)
-        // accumulator -> registers -> swizzled staging tile in shared memory -> TMA store (coalesced, off the LSU path)
-        const int r = warp * 32 + lane;                   // row of the tile this thread owns
-        uint32_t lt = 0, g = 0;                            // local tile counter, global chunk counter
-        if (MODE == MODE_DGRAD && threadIdx.x == 0 && tile0 < n_tiles) {
-            mbar_arrive_expect_tx(bar_h1, kATile);
-            tma_load_2d(h1_ring, map_h1, 0, (int)(tile0 * BM), bar_h1);
-        }
-        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++lt) {
-            const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
-            const int64_t row = tile * BM + r;
-            mbar_wait(bar_tfull + 8 * acc, aph);
-            if (threadIdx.x == 0) XB_TS(3, lt, 0);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * N;
-            float h0 = 0.f, h1 = 0.f;
-#pragma unroll 1
-            for (int cc = 0; cc < kChunks; ++cc, ++g) {
-                if (threadIdx.x == 0) XB_TS(3, lt, 1 + cc);
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + cc * 32, v);
-                // the staging buffer about to be overwritten must have been read out by its previous TMA store
-                if (threadIdx.x == 0) {
-                    if (O > 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                }
-                bar_sync_named(2, 128);
-                const uint32_t obuf = out_ring + (g % (uint32_t)O) * kATile;
-                uint32_t hbuf = 0;
-                if (MODE == MODE_DGRAD) {
-                    // prefetch the next chunk's mask tile (double-buffered) or, single-buffered, load this chunk's now
-                    const uint32_t hb = HB > 1 ? (g & 1) : 0, hph = HB > 1 ? ((g >> 1) & 1) : (g & 1);
-                    if (threadIdx.x == 0) {
-                        int ncc = cc + (HB > 1 ? 1 : 0);
-                        int64_t ntile = tile;
-                        if (ncc == kChunks) { ncc = 0; ntile = tile + tile_step; }
-                        if (HB > 1 ? ntile < n_tiles : g > 0) {
-                            const uint32_t nb = HB > 1 ? ((g + 1) & 1) : 0;
-                            mbar_arrive_expect_tx(bar_h1 + 8 * nb, kATile);
-                            tma_load_2d(h1_ring + nb * kATile, map_h1, ncc * 32, (int)(ntile * BM), bar_h1 + 8 * nb);
-                        }
-                    }
-                    hbuf = h1_ring + hb * kATile;
-                    mbar_wait(bar_h1 + 8 * hb, hph);
-                }
-                tmem_ld_wait();
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float4 f = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                           __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-                    if (MODE == MODE_FWD) {
-                        const float* b = sf + cc * 32 + 4 * q;
-                        f.x += b[0]; f.y += b[1]; f.z += b[2]; f.w += b[3];
-                        f.x = f.x > 0.f ? f.x : f.x * p.slope;
-                        f.y = f.y > 0.f ? f.y : f.y * p.slope;
-                        f.z = f.z > 0.f ? f.z : f.z * p.slope;
-                        f.w = f.w > 0.f ? f.w : f.w * p.slope;
-                        const float* w = b + N;
-                        h0 += f.x * w[0] + f.y * w[1] + f.z * w[2] + f.w * w[3];
-                        h1 += f.x * w[N] + f.y * w[N + 1] + f.z * w[N + 2] + f.w * w[N + 3];
-                    } else {
-                        const float4 m = lds128(hbuf + sw128_off(r, q));
-                        f.x *= m.x > 0.f ? 1.f : p.slope;
-                        f.y *= m.y > 0.f ? 1.f : p.slope;
-                        f.z *= m.z > 0.f ? 1.f : p.slope;
-                        f.w *= m.w > 0.f ? 1.f : p.slope;
-                    }
-                    sts128(obuf + sw128_off(r, q), f);
-                }
-                fence_proxy_async_smem();
-                bar_sync_named(3, 128);
-                if (threadIdx.x == 0) {
-                    tma_store_2d(map_out, obuf, cc * 32, (int)(tile * BM));
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-            if (threadIdx.x == 0) XB_TS(3, lt, 7);
-            if (MODE == MODE_FWD && row < p.M) {
-                if (e_n_head > 0) e_head_out[row * e_n_head] = h0 + e_head_b[0];
-                if (e_n_head > 1) e_head_out[row * e_n_head + 1] = h1 + e_head_b[1];
-            }
-        }
-        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        // ============================================================ epilogue warps 0-3
+        EpiCtx c;
+        c.tmem_base = tmem_base; c.bar_tfull = bar_tfull; c.bar_tempty = bar_tempty; c.bar_h1w = bar_h1w;
+        c.out_ring = out_ring; c.h1_ring = h1_ring; c.O = O; c.HB = HB;
+        c.tile0 = tile0; c.tile_step = tile_step; c.n_tiles = n_tiles; c.M = p.M;
+        c.map_out = map_out; c.map_h1 = map_h1; c.sf = sf; c.slope = p.slope;
+        c.n_head = e_n_head; c.head_b = e_head_b; c.head_out = e_head_out;
+#ifdef XB_DENSE_TS
+        c.ts = p.ts;
+#endif
+        epilogue_warp<N, MODE>(c, warp, lane);
     }
 
     // ---------------------------------------------------------------- teardown
@@ -464,17 +507,372 @@ static int launch_kmajor(const TMaps& maps, KParams p, cudaStream_t s) {
     return 0;
 }
 
+// ================================================================================================ TS variant
+// Same kernels with the A operand in TENSOR MEMORY (tcgen05.mma "TS" form) for N <= 128.  The SS form above is bound
+// by shared-memory bandwidth: every M=128 x N=128 x K=8 MMA streams 4 KB of A and 4 KB of B out of shared memory in
+// its 64 cycles (the full 128 B/clk), on top of the operand warps' own hi/lo traffic.  Here the operand warps read the
+// raw tile once (row per thread, un-swizzling as they go), split it in registers and tcgen05.st the hi/lo halves into
+// a 4-deep ring of TMEM columns; the MMAs then read only B from shared memory, the raw stage is released as soon as it
+// has been read (not when the MMAs retire), and the lo ring disappears from shared memory.
+// TMEM budget (512 columns): accumulator 2 x N | A ring 4 x (32 hi + 32 lo).
+constexpr int kTA = 4;                    // TMEM A-operand stages
+constexpr int kTsTmemCols = 512;
+
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// One k-block of the TS main loop issued by the MMA thread as a single instruction stream: the phase checks of the
+// NEXT k-block's barriers are issued first and only consumed after the 12 MMAs and the commits, so their ~300-cycle
+// latency (measured: passing an already-complete mbarrier) overlaps MMA issue instead of idling the tensor pipe.
+// Returns a bit mask: 1 = next A stage ready, 2 = next B stage ready.
+__device__ __forceinline__ uint32_t ts_kblock(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t db_hi,
+                                              uint64_t db_lo, uint32_t idesc, uint32_t accumulate_first,
+                                              uint32_t next_bar_a, uint32_t next_par_a, uint32_t next_bar_b,
+                                              uint32_t next_par_b, uint32_t commit0, uint32_t commit1, uint32_t commit2) {
+    uint32_t ready;
+    asm volatile(
+        "{\n"
+        ".reg .pred pa, pb, p0, p1, c1, c2;\n"
+        ".reg .b32 ah, al, r;\n"
+        ".reg .b64 bh, bl;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 pa, [%8], %9;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 pb, [%10], %11;\n"
+        "setp.ne.b32 p0, %7, 0;\n"
+        "setp.ne.b32 p1, 1, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%3], %4, %6, p0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %5, %6, p1;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %4, %6, p1;\n"
+        "add.u32 ah, %2, 8;  add.u32 al, %3, 8;  add.u64 bh, %4, 2;  add.u64 bl, %5, 2;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al], bh, %6, p1;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bl, %6, p1;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bh, %6, p1;\n"
+        "add.u32 ah, %2, 16; add.u32 al, %3, 16; add.u64 bh, %4, 4;  add.u64 bl, %5, 4;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al], bh, %6, p1;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bl, %6, p1;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bh, %6, p1;\n"
+        "add.u32 ah, %2, 24; add.u32 al, %3, 24; add.u64 bh, %4, 6;  add.u64 bl, %5, 6;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al], bh, %6, p1;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bl, %6, p1;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bh, %6, p1;\n"
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n"
+        "setp.ne.b32 c1, %13, 0;\n"
+        "setp.ne.b32 c2, %14, 0;\n"
+        "@c1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%13];\n"
+        "@c2 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%14];\n"
+        "selp.u32 %0, 1, 0, pa;\n"
+        "selp.u32 r, 2, 0, pb;\n"
+        "or.b32 %0, %0, r;\n"
+        "}\n"
+        : "=r"(ready)
+        : "r"(d_tmem), "r"(a_hi), "r"(a_lo), "l"(db_hi), "l"(db_lo), "r"(idesc), "r"(accumulate_first), "r"(next_bar_a),
+          "r"(next_par_a), "r"(next_bar_b), "r"(next_par_b), "r"(commit0), "r"(commit1), "r"(commit2)
+        : "memory");
+    return ready;
+}
+
+template <int N, bool B_RES, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+    dense_kmajor_ts_kernel(const __grid_constant__ TMaps maps, const KParams p) {
+    static_assert(N <= 128, "TS variant: accumulators (2N) + A ring (256) must fit the 512 TMEM columns");
+    constexpr int kBTile = N * BK * 4;
+    constexpr uint32_t kIdesc = umma_idesc_tf32(BM, N, 0, 0);
+    constexpr uint32_t kACol = 2 * N;                   // first TMEM column of the A ring
+    extern __shared__ unsigned char smem_raw[];
+    if (threadIdx.x == 0) XB_TS(0, 62, 0);
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int S = p.stages, SB = p.lo_bufs, O = p.out_bufs, HB = p.h1_bufs, KB = p.KB;   // lo_bufs doubles as B-ring depth
+    const uint32_t bres = base;                                              // [2][KB][kBTile] when B_RES
+    const uint32_t ring = base + (B_RES ? 2u * KB * kBTile : 0u);            // raw A tiles
+    const uint32_t b_ring = ring + (uint32_t)S * kATile;                     // streamed weight k-blocks (hi | lo)
+    const uint32_t out_ring = b_ring + (B_RES ? 0u : (uint32_t)SB * 2 * kBTile);
+    const uint32_t h1_ring = out_ring + (uint32_t)O * kATile;
+    const uint32_t misc = h1_ring + (MODE == MODE_DGRAD ? (uint32_t)HB * kATile : 0u);
+    const uint32_t bar_full = misc, bar_conv = misc + 64, bar_empty = misc + 128, bar_aempty = misc + 192;
+    const uint32_t bar_tfull = misc + 224, bar_tempty = misc + 240, bar_bfull = misc + 256;
+    const uint32_t tmem_slot = misc + 264, bar_h1w = misc + 352, bar_bfull_r = misc + 288, bar_bempty = misc + 320;
+    unsigned char* misc_ptr = smem_raw + (misc - smem_u32(smem_raw));
+    float* sf = reinterpret_cast<float*>(misc_ptr + 512);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_tiles = (p.M + BM - 1) / BM;
+    const int n_src = (MODE == MODE_FWD && p.dual) ? 2 : 1;
+    const int sel = (MODE == MODE_FWD && p.dual) ? (int)(blockIdx.x & 1) : 0;
+    const int64_t tile0 = blockIdx.x / n_src, tile_step = gridDim.x / n_src;
+    const CUtensorMap* map_a0 = &maps.a0;
+    const CUtensorMap* map_a1 = &maps.a1;
+    const CUtensorMap* map_bhi = sel ? &maps.bhi1 : &maps.bhi;
+    const CUtensorMap* map_blo = sel ? &maps.blo1 : &maps.blo;
+    const CUtensorMap* map_out = sel ? &maps.out1 : &maps.out;
+    const CUtensorMap* map_h1 = &maps.h1;
+    const float* e_bias = sel ? p.bias1 : p.bias;
+    const float* e_head_w = sel ? p.head_w1 : p.head_w;
+    const float* e_head_b = sel ? p.head_b1 : p.head_b;
+    const int e_n_head = sel ? p.n_head1 : p.n_head;
+    float* e_head_out = sel ? p.head_out1 : p.head_out;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, kOperandWarps);          // released by the operand warps once they have read it
+        }
+        for (int a = 0; a < kTA; ++a) {
+            mbar_init(bar_conv + 8 * a, kOperandWarps);
+            mbar_init(bar_aempty + 8 * a, 1);
+        }
+        for (int b = 0; b < 3; ++b) {
+            mbar_init(bar_bfull_r + 8 * b, 1);
+            mbar_init(bar_bempty + 8 * b, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 4);
+        }
+        for (int a = 0; a < 8; ++a) mbar_init(bar_h1w + 8 * a, 1);
+        mbar_init(bar_bfull, 1);
+        mbar_fence_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc<kTsTmemCols>(tmem_slot);
+    if (MODE == MODE_FWD) {
+        for (int i = threadIdx.x; i < N; i += kThreads) {
+            sf[i] = e_bias ? e_bias[i] : 0.f;
+            sf[N + i] = e_n_head > 0 ? e_head_w[i] : 0.f;
+            sf[2 * N + i] = e_n_head > 1 ? e_head_w[N + i] : 0.f;
+        }
+    } else {
+        const int K0 = p.kb_split * BK, K1 = (KB - p.kb_split) * BK;
+        for (int i = threadIdx.x; i < 256; i += kThreads) {
+            sf[i] = (i < K0 && p.nh0 > 0) ? p.w2_0[i] : 0.f;
+            sf[256 + i] = (i < K0 && p.nh0 > 1) ? p.w2_0[K0 + i] : 0.f;
+            sf[512 + i] = (i < K1 && p.nh1 > 0) ? p.w2_1[i] : 0.f;
+            sf[768 + i] = (i < K1 && p.nh1 > 1) ? p.w2_1[K1 + i] : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (threadIdx.x == 0) XB_TS(0, 62, 1);
+
+    if (warp == kProducerWarp) {
+        // ============================================================ TMA producer (one thread)
+        if (lane == 0) {
+            tma_prefetch_desc(map_a0);
+            tma_prefetch_desc(map_bhi);
+            tma_prefetch_desc(map_blo);
+            if (MODE == MODE_DGRAD) tma_prefetch_desc(map_a1);
+            if (B_RES) {
+                mbar_arrive_expect_tx(bar_bfull, 2u * KB * kBTile);
+                for (int kb = 0; kb < KB; ++kb) {
+                    tma_load_2d(bres + kb * kBTile, map_bhi, kb * BK, 0, bar_bfull);
+                    tma_load_2d(bres + (KB + kb) * kBTile, map_blo, kb * BK, 0, bar_bfull);
+                }
+            }
+            uint32_t s = 0, ph = 0, sb = 0, bph = 0, it = 0;
+            for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    XB_TS(0, it, 0);
+                    mbar_arrive_expect_tx(bar_full + 8 * s, kATile);
+                    const bool src1 = (MODE == MODE_DGRAD) && kb >= p.kb_split;
+                    const int kcol = (src1 ? kb - p.kb_split : kb) * BK;
+                    tma_load_2d(ring + s * kATile, src1 ? map_a1 : map_a0, kcol, (int)(tile * BM), bar_full + 8 * s);
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                    if (!B_RES) {
+                        mbar_wait(bar_bempty + 8 * sb, bph ^ 1);
+                        const uint32_t bs = b_ring + sb * 2 * kBTile;
+                        mbar_arrive_expect_tx(bar_bfull_r + 8 * sb, 2 * kBTile);
+                        tma_load_2d(bs, map_bhi, kb * BK, 0, bar_bfull_r + 8 * sb);
+                        tma_load_2d(bs + kBTile, map_blo, kb * BK, 0, bar_bfull_r + 8 * sb);
+                        if (++sb == (uint32_t)SB) { sb = 0; bph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ============================================================ MMA issuer (one thread)
+        if (lane == 0) {
+            if (B_RES) mbar_wait(bar_bfull, 0);
+            // a barrier/parity pair that always tests complete, for the unused prefetch slot
+            const uint32_t dummy_bar = bar_bfull, dummy_par = B_RES ? 0u : 1u;
+            uint32_t ta = 0, aph = 0, sb = 0, bph = 0, lt = 0, it = 0;
+            uint32_t ready = 0;                             // bit 0: A stage `ta` known ready, bit 1: B stage `sb`
+            for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++lt) {
+                const uint32_t acc = lt & 1, tph = (lt >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, tph ^ 1);
+                const uint32_t d_tmem = tmem_base + acc * N;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    XB_TS(1, it, 0);
+                    if (!(ready & 1)) mbar_wait(bar_conv + 8 * ta, aph);
+                    if (!B_RES && !(ready & 2)) mbar_wait(bar_bfull_r + 8 * sb, bph);
+                    XB_TS(1, it, 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = tmem_base + kACol + ta * 64, a_lo = a_hi + 32;
+                    const uint32_t b_hi = B_RES ? bres + kb * kBTile : b_ring + sb * 2 * kBTile;
+                    const uint32_t b_lo = B_RES ? bres + (KB + kb) * kBTile : b_hi + kBTile;
+                    // next k-block's stages (the tile boundary does not matter: the rings run continuously)
+                    const uint32_t nta = ta + 1 == kTA ? 0 : ta + 1, naph = ta + 1 == kTA ? aph ^ 1 : aph;
+                    const uint32_t nsb = sb + 1 == (uint32_t)SB ? 0 : sb + 1, nbph = sb + 1 == (uint32_t)SB ? bph ^ 1 : bph;
+                    ready = ts_kblock(d_tmem, a_hi, a_lo, umma_desc_sw128(b_hi, 16, 1024), umma_desc_sw128(b_lo, 16, 1024),
+                                      kIdesc, kb != 0, bar_conv + 8 * nta, naph, B_RES ? dummy_bar : bar_bfull_r + 8 * nsb,
+                                      B_RES ? dummy_par : nbph, bar_aempty + 8 * ta, B_RES ? 0u : bar_bempty + 8 * sb,
+                                      kb == KB - 1 ? bar_tfull + 8 * acc : 0u);
+                    XB_TS(1, it, 3);
+                    ta = nta; aph = naph;
+                    if (!B_RES) { sb = nsb; bph = nbph; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ============================================================ operand warps (256 threads): raw tile -> TMEM
+        const int lq = warp & 3, ch = (warp - 4) >> 2;    // TMEM lane quarter (warp % 4), half of the 32 k-columns
+        const int r = 32 * lq + lane;                     // row of the tile = TMEM lane
+        const uint32_t lane_base = (uint32_t)(32 * lq) << 16;
+        uint32_t s = 0, ph = 0, ta = 0, aph = 0, it = 0;
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
+            float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;   // DGRAD: dL/d(head outputs) of this row
+            if (MODE == MODE_DGRAD) {
+                const int64_t row = tile * BM + r;
+                if (row < p.M) {
+                    d00 = p.nh0 > 0 ? __ldg(p.dout0 + row * p.nh0) : 0.f;
+                    d01 = p.nh0 > 1 ? __ldg(p.dout0 + row * p.nh0 + 1) : 0.f;
+                    d10 = p.nh1 > 0 ? __ldg(p.dout1 + row * p.nh1) : 0.f;
+                    d11 = p.nh1 > 1 ? __ldg(p.dout1 + row * p.nh1 + 1) : 0.f;
+                }
+            }
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                mbar_wait(bar_full + 8 * s, ph);
+                if (threadIdx.x == 128) XB_TS(2, it, 0);
+                const uint32_t a_raw = ring + s * kATile;
+                float4 xs[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xs[i] = lds128(a_raw + sw128_off(r, 4 * ch + i));
+                float x[16] = {xs[0].x, xs[0].y, xs[0].z, xs[0].w, xs[1].x, xs[1].y, xs[1].z, xs[1].w,
+                               xs[2].x, xs[2].y, xs[2].z, xs[2].w, xs[3].x, xs[3].y, xs[3].z, xs[3].w};
+                if (MODE == MODE_DGRAD) {
+                    const int src = kb >= p.kb_split;
+                    const float* w = sf + src * 512 + (src ? kb - p.kb_split : kb) * BK + 16 * ch;
+                    const float e0 = src ? d10 : d00, e1 = src ? d11 : d01;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) x[q] = (e0 * w[q] + e1 * w[256 + q]) * (x[q] > 0.f ? 1.f : p.slope);
+                }
+                float hi[16], lo[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) split_tf32(x[q], hi[q], lo[q]);
+                if (threadIdx.x == 128) XB_TS(2, it, 1);
+                mbar_wait(bar_aempty + 8 * ta, aph ^ 1);
+                if (threadIdx.x == 128) XB_TS(2, it, 2);
+                tc_fence_after();
+                const uint32_t acol = tmem_base + lane_base + kACol + ta * 64 + 16 * ch;
+                tmem_st_32x16(acol, hi);
+                tmem_st_32x16(acol + 32, lo);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8 * s);      // the raw tile has been consumed: hand the slot back
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_conv + 8 * ta);
+                if (threadIdx.x == 128) XB_TS(2, it, 3);
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                if (++ta == kTA) { ta = 0; aph ^= 1; }
+            }
+        }
+    } else {
+        // ============================================================ epilogue warps 0-3
+        EpiCtx c;
+        c.tmem_base = tmem_base; c.bar_tfull = bar_tfull; c.bar_tempty = bar_tempty; c.bar_h1w = bar_h1w;
+        c.out_ring = out_ring; c.h1_ring = h1_ring; c.O = O; c.HB = HB;
+        c.tile0 = tile0; c.tile_step = tile_step; c.n_tiles = n_tiles; c.M = p.M;
+        c.map_out = map_out; c.map_h1 = map_h1; c.sf = sf; c.slope = p.slope;
+        c.n_head = e_n_head; c.head_b = e_head_b; c.head_out = e_head_out;
+#ifdef XB_DENSE_TS
+        c.ts = p.ts;
+#endif
+        epilogue_warp<N, MODE>(c, warp, lane);
+    }
+
+    if (threadIdx.x == 0) XB_TS(0, 63, 0);
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) XB_TS(0, 63, 1);
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc<kTsTmemCols>(tmem_base);
+    }
+}
+
+template <int N, bool B_RES, int MODE>
+static int launch_kmajor_ts(const TMaps& maps, KParams p, cudaStream_t s) {
+    const int kBTile = N * BK * 4;
+    const int bres = B_RES ? 2 * p.KB * kBTile : 0;
+    const int avail = kMaxSmem - 1024 - kMiscBytes - bres;
+    // minimum: 2 raw stages, (2 weight stages), 1 staging tile (+ 1 mask tile); then deepen
+    int S = 2, SB = B_RES ? 0 : 2, O = 1, HB = MODE == MODE_DGRAD ? 1 : 0;
+    auto bytes = [&]() { return (S + O + HB) * kATile + SB * 2 * kBTile; };
+    if (bytes() > avail) return XB_E_UNSUPPORTED;
+    ++O; if (bytes() > avail) --O;
+    if (MODE == MODE_DGRAD) { ++HB; if (bytes() > avail) --HB; }
+    while (S < 4) { ++S; if (bytes() > avail) { --S; break; } }
+    if (!B_RES) { ++SB; if (bytes() > avail) --SB; }
+    p.stages = S;
+    p.lo_bufs = SB;
+    p.out_bufs = O;
+    p.h1_bufs = HB;
+#ifdef XB_DENSE_TS
+    p.ts = g_xb_ts_host;
+#endif
+    const int smem = 1024 + bres + bytes() + kMiscBytes;
+    auto kern = dense_kmajor_ts_kernel<N, B_RES, MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        XB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        attr_set = true;
+    }
+    const int64_t tiles = (p.M + BM - 1) / BM;
+    const int n_src = (MODE == MODE_FWD && p.dual) ? 2 : 1;
+    const int64_t want = tiles * n_src;
+    const int grid = (int)(want < kNumSMs ? want : (kNumSMs / n_src) * n_src);
+    kern<<<grid, kThreads, smem, s>>>(maps, p);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int MODE>
 static int dispatch_kmajor(int N, bool bres, const TMaps& maps, const KParams& p, cudaStream_t s) {
     const int kBTile = N * BK * 4;
+    static const bool use_ts = []() { const char* e = getenv("XB_DENSE_SS"); return !(e && e[0] == '1'); }();
+    if (use_ts && N <= 128) {            // A operand in tensor memory
+        if (bres && (kMaxSmem - 1024 - kMiscBytes - 2 * p.KB * kBTile) < (2 + 1 + (MODE == MODE_DGRAD)) * kATile) bres = false;
+        if (N == 64)
+            return bres ? launch_kmajor_ts<64, true, MODE>(maps, p, s) : launch_kmajor_ts<64, false, MODE>(maps, p, s);
+        if (N == 128)
+            return bres ? launch_kmajor_ts<128, true, MODE>(maps, p, s) : launch_kmajor_ts<128, false, MODE>(maps, p, s);
+        return XB_E_UNSUPPORTED;
+    }
     if (bres && (kMaxSmem - 1024 - kMiscBytes - 2 * p.KB * kBTile) < (2 + 1 + 1 + (MODE == MODE_DGRAD)) * kATile) bres = false;
     switch (N) {
         case 64:
-            return bres ? launch_kmajor<64, true, MODE>(maps, p, s)
-                        : launch_kmajor<64, false, MODE>(maps, p, s);
+            return bres ? launch_kmajor<64, true, MODE>(maps, p, s) : launch_kmajor<64, false, MODE>(maps, p, s);
         case 128:
-            return bres ? launch_kmajor<128, true, MODE>(maps, p, s)
-                        : launch_kmajor<128, false, MODE>(maps, p, s);
+            return bres ? launch_kmajor<128, true, MODE>(maps, p, s) : launch_kmajor<128, false, MODE>(maps, p, s);
         case 256:
             return launch_kmajor<256, false, MODE>(maps, p, s);
         default:
@@ -854,7 +1252,7 @@ static int dense_fwd_impl(const float* X, int64_t M, int K, int N, float slope, 
         CUtensorMap* ml = l ? &maps.blo1 : &maps.blo;
         CUtensorMap* mo = l ? &maps.out1 : &maps.out;
         if (!xb_make_map_f32_2d(mh, Whi[l], N, K, K, N, BK, 1) || !xb_make_map_f32_2d(ml, Wlo[l], N, K, K, N, BK, 1) ||
-            !xb_make_map_f32_2d(mo, Y[l], M, N, N, BM, 32, 1))
+            !xb_make_map_f32_2d(mo, Y[l], M, N, N, 32, 32, 1))
             return XB_E_DRIVER;
     }
     if (n_layers == 1) { maps.bhi1 = maps.bhi; maps.blo1 = maps.blo; maps.out1 = maps.out; }
@@ -914,7 +1312,7 @@ extern "C" int xb_dense_dgrad(const float* Y0, const float* dout0, const float* 
     if (!al16(Y0) || !al16(Wthi) || !al16(Wtlo) || !al16(H1) || !al16(dZ1) || (Y1 && !al16(Y1))) return XB_E_UNSUPPORTED;
     const int K = K0 + K1;
     TMaps maps;
-    if (!xb_make_map_f32_2d(&maps.out, dZ1, M, N, N, BM, 32, 1) || !xb_make_map_f32_2d(&maps.h1, H1, M, N, N, BM, 32, 1) ||
+    if (!xb_make_map_f32_2d(&maps.out, dZ1, M, N, N, 32, 32, 1) || !xb_make_map_f32_2d(&maps.h1, H1, M, N, N, 32, 32, 1) ||
         !xb_make_map_f32_2d(&maps.a0, Y0, M, K0, K0, BM, BK, 1) ||
         !xb_make_map_f32_2d(&maps.a1, Y1 ? Y1 : Y0, M, Y1 ? K1 : K0, Y1 ? K1 : K0, BM, BK, 1) ||
         !xb_make_map_f32_2d(&maps.bhi, Wthi, N, K, K, N, BK, 1) || !xb_make_map_f32_2d(&maps.blo, Wtlo, N, K, K, N, BK, 1))

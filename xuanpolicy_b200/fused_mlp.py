@@ -102,6 +102,29 @@ class FusedActorCritic:
             self._buf[B] = b
         return b
 
+    # ---------------------------------------------------------------------------------------------- stages (one launch each)
+    def stage_trunk(self, obs, b):
+        ops.mlp_trunk_fwd(obs, self.l0.weight.data, self.l0.bias.data, self.slope, b["h1"])
+
+    def stage_hidden(self, b):
+        ops.dense_fwd2(b["h1"], self.slope,
+                       (self.wa_hi, self.wa_lo, self.la1.bias.data, b["ya"], self.la2.weight.data, self.la2.bias.data, b["act"]),
+                       (self.wc_hi, self.wc_lo, self.lc1.bias.data, b["yc"], self.lc2.weight.data, self.lc2.bias.data, b["v"]))
+
+    def stage_dgrad(self, b, dact, dv2):
+        ops.dense_dgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, self.wt_hi, self.wt_lo,
+                        b["h1"], self.slope, b["dz1"])
+
+    def stage_wgrad(self, b, dact, dv2):
+        g = lambda p: p.grad
+        ops.dense_wgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, b["h1"], self.slope,
+                        self.ws_wgrad, g(self.la1.weight), g(self.la1.bias), g(self.la2.weight), g(self.la2.bias),
+                        g(self.lc1.weight), g(self.lc1.bias), g(self.lc2.weight), g(self.lc2.bias))
+
+    def stage_trunk_wgrad(self, obs, b):
+        ops.mlp_trunk_wgrad(b["dz1"], obs, self.ws_trunk, self.l0.weight.grad, self.l0.bias.grad)
+
+    # ---------------------------------------------------------------------------------------------- forward / backward
     def forward(self, obs, refresh=True):
         """obs: CUDA fp32 [B, obs_dim] with contiguous rows (a column slice of the float4 observation rows is fine).
         Returns (act_out [B, A], v [B]); the activations stay in per-batch-size buffers for `backward`."""
@@ -109,10 +132,8 @@ class FusedActorCritic:
         b = self._buffers(B)
         if refresh:
             self.refresh_weights()
-        ops.mlp_trunk_fwd(obs, self.l0.weight.data, self.l0.bias.data, self.slope, b["h1"])
-        ops.dense_fwd2(b["h1"], self.slope,
-                       (self.wa_hi, self.wa_lo, self.la1.bias.data, b["ya"], self.la2.weight.data, self.la2.bias.data, b["act"]),
-                       (self.wc_hi, self.wc_lo, self.lc1.bias.data, b["yc"], self.lc2.weight.data, self.lc2.bias.data, b["v"]))
+        self.stage_trunk(obs, b)
+        self.stage_hidden(b)
         self._last = (obs, b)
         return b["act"], b["v"][:, 0]
 
@@ -129,10 +150,6 @@ class FusedActorCritic:
         if b["dz1"] is None:
             b["dz1"] = torch.empty(B, self.H, dtype=torch.float32, device=self.device)
         dv2 = dv.reshape(B, 1)
-        g = lambda p: p.grad
-        ops.dense_dgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, self.wt_hi, self.wt_lo,
-                        b["h1"], self.slope, b["dz1"])
-        ops.dense_wgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, b["h1"], self.slope,
-                        self.ws_wgrad, g(self.la1.weight), g(self.la1.bias), g(self.la2.weight), g(self.la2.bias),
-                        g(self.lc1.weight), g(self.lc1.bias), g(self.lc2.weight), g(self.lc2.bias))
-        ops.mlp_trunk_wgrad(b["dz1"], obs, self.ws_trunk, g(self.l0.weight), g(self.l0.bias))
+        self.stage_dgrad(b, dact, dv2)
+        self.stage_wgrad(b, dact, dv2)
+        self.stage_trunk_wgrad(obs, b)
