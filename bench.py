@@ -425,6 +425,10 @@ def run_ours(args):
     step_share = {k: v["ms"] * v["launches_per_step"] for k, v in kernels.items() if v["launches_per_step"]}
     dom = max(step_share, key=step_share.get)
     kd = kernels[dom]
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and args.workload == "c2":      # ncu DRAM bytes per launch of the same kernel at this shape
+        traffic = json.load(open(tpath)).get(dom)
     cpu = None if args.no_cpu_baseline else cpu_baseline(wl, budget_s=args.cpu_budget if args.cpu_budget else 25.0)
     line = {
         "metric": "PPO env-steps/s", "value": round(value, 1), "unit": "env-steps/s", "n_gpus": world,
@@ -443,7 +447,7 @@ def run_ours(args):
                 "what": "PPOCLIP_Agent.train with host-drawn minibatch permutations (pinned H2D per epoch) and log scalars read back"},
         "gpu_launches": launches * args.steps,
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": kd["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": kd["frac"], "traffic": None, "peak_source": peak_src,
+                     "frac": kd["frac"], "traffic": traffic, "peak_source": peak_src,
                      "tensor": {k: kd[k] for k in ("gemm_tflops", "tensor_pipe_tflops_tf32", "tensor_frac_of_tf32_peak") if k in kd},
                      "note": "kernel with the largest share of the step (CUDA-event time x launches per step); achieved = "
                              "algorithmic bytes / time.  Dense kernels: HBM time and 3xTF32 tensor-pipe time are about equal "

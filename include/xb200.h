@@ -255,6 +255,7 @@ int xb_bias_act_fwd(float* y, const float* bias, float slope, int64_t B, int H, 
  *   xb_dense_fwd            Y[M][N] = leaky_relu(X[M][K] . W^T + bias);  optionally the narrow head that follows it:
  *                           head_out[M][n_head] = Y . head_w[n_head][N]^T + head_b   (n_head in {0, 1, 2}).
  *                           b_resident != 0 keeps the whole weight operand in shared memory when it fits.
+ *                           Y == NULL (with n_head > 0): only the head outputs are produced (no activation store).
  *   xb_dense_dgrad          dZ1[M][N] = ([dz0 | dz1] . [W0 ; W1]) * leaky'(H1)   with the A operand generated on the fly:
  *                           dz_s[r][k] = (sum_j dout_s[r][j] w2_s[j][k]) * leaky'(Y_s[r][k])   (s = actor, critic),
  *                           i.e. the backward of  H1 -> {Linear+LeakyReLU -> head}_s  without materialising dz_s.
@@ -262,6 +263,10 @@ int xb_bias_act_fwd(float* y, const float* bias, float slope, int64_t B, int H, 
  * ---------------------------------------------------------------------------------------------------------- */
 int xb_dense_split_weights(const float* W, int N, int K, float* hi, float* lo, float* thi, float* tlo, int ldt,
                            int toff, xb_stream_t stream);
+/*   xb_dense_split_weights2 both hidden layers (actor W0, critic W1, each [N][K]) in one launch; thi/tlo [K][2N] receive the
+ *                           transposes side by side (W0^T | W1^T). */
+int xb_dense_split_weights2(const float* W0, float* hi0, float* lo0, const float* W1, float* hi1, float* lo1, int N, int K,
+                            float* thi, float* tlo, xb_stream_t stream);
 int xb_dense_fwd(const float* X, int64_t M, int K, const float* Whi, const float* Wlo, int N, const float* bias,
                  float slope, float* Y, const float* head_w, const float* head_b, int n_head, float* head_out,
                  int b_resident, xb_stream_t stream);
@@ -282,6 +287,15 @@ int xb_dense_fwd2(const float* X, int64_t M, int K, int N, float slope, const fl
                   const float* bias0, float* Y0, const float* head_w0, const float* head_b0, int n_head0, float* head_out0,
                   const float* Whi1, const float* Wlo1, const float* bias1, float* Y1, const float* head_w1,
                   const float* head_b1, int n_head1, float* head_out1, int b_resident, xb_stream_t stream);
+/*   xb_mlp_fwd_from_obs     the whole actor-critic forward in ONE launch (rollout / inference): the trunk layer
+ *                           h1 = leaky_relu(W0 obs + b0) is generated by the operand warps straight into tensor memory
+ *                           (obs_dim <= 4, H in {64, 128}), then both hidden layers + heads as in xb_dense_fwd2.
+ *                           Y0 / Y1 may both be NULL: only the head outputs are produced. */
+int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const float* W0, const float* b0, int64_t M, int H,
+                        float slope, const float* Whi0, const float* Wlo0, const float* bias0, float* Y0,
+                        const float* head_w0, const float* head_b0, int n_head0, float* head_out0, const float* Whi1,
+                        const float* Wlo1, const float* bias1, float* Y1, const float* head_w1, const float* head_b1,
+                        int n_head1, float* head_out1, xb_stream_t stream);
 int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, int K0, const float* Y1,
                    const float* dout1, const float* w2_1, int nh1, int K1, int64_t M, const float* Wthi,
                    const float* Wtlo, int N, const float* H1, float slope, float* dZ1, xb_stream_t stream);

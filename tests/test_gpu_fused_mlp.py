@@ -102,3 +102,24 @@ def test_fused_update_matches_torch_update_one_step():
     # parameters after the clipped Adam step: the first Adam step is lr * g / (|g| + eps), i.e. sign-like, so a
     # flipped unit can move a near-zero-gradient parameter by a visible fraction of lr; bound the step difference by 5% of lr
     assert float((p1 - p0).abs().max()) < 0.05 * 4e-4
+
+
+@pytest.mark.parametrize("env_id,B", [("Pendulum-v1", 8192), ("CartPole-v1", 4096 + 33)])
+def test_rollout_forward_from_observations_matches_training_forward(env_id, B):
+    """xb_mlp_fwd_from_obs (trunk generated inside the tensor-core kernel, heads only) == trunk kernel + dense_fwd2."""
+    import xuanpolicy_b200 as xb
+    from xuanpolicy_b200.fused_mlp import FusedActorCritic
+    from xuanpolicy_b200.policies import make_policy
+    obs_space, act_space = xb.make_spaces(env_id)
+    policy = make_policy(obs_space, act_space, hidden=(128,), device="cuda", seed=4)
+    with torch.no_grad():
+        for p in policy.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    fused = FusedActorCritic(policy)
+    obs = torch.randn(B, 4, device="cuda")[:, :obs_space.shape[0]]
+    a1, v1 = fused.forward(obs)
+    a1, v1 = a1.clone(), v1.clone()
+    a2, v2 = fused.forward_inference(obs)
+    torch.cuda.synchronize()
+    assert _rel(a2, a1) < 2e-5 and _rel(v2, v1) < 2e-5

@@ -15,6 +15,9 @@ WANT = [
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "gpu_dram_pct"),
     ("lts__t_sector_hit_rate.pct", "l2_hit_pct"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_active_pct"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem_lsu_wavefronts_pct"),
+    ("sm__cycles_elapsed.max", "sm_cycles"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy_pct"),
     ("launch__registers_per_thread", "regs"),
     ("launch__occupancy_limit_registers", "occ_lim_regs"),

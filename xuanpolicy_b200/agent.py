@@ -152,7 +152,7 @@ class PPOCLIP_Agent:
     def _policy_forward(self, x):
         fused = self.learner._fused
         if fused is not None and x.shape[0] >= fused.MIN_ROWS:     # weights were split at the start of the rollout
-            act_out, v = fused.forward(x[:, :self._obs_dim], refresh=False)
+            act_out, v = fused.forward_inference(x[:, :self._obs_dim])
             return fused.dist_params(act_out), v
         _, dist, v = self.policy(x[:, :self._obs_dim])
         return dist, v

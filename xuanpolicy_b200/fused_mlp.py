@@ -91,8 +91,8 @@ class FusedActorCritic:
 
     # every tensor below is read at launch time: parameters may have been re-pointed (FlatAdamState) since __init__
     def refresh_weights(self):
-        ops.dense_split_weights(self.la1.weight.data, self.wa_hi, self.wa_lo, self.wt_hi, self.wt_lo, 0)
-        ops.dense_split_weights(self.lc1.weight.data, self.wc_hi, self.wc_lo, self.wt_hi, self.wt_lo, self.H)
+        ops.dense_split_weights2(self.la1.weight.data, self.wa_hi, self.wa_lo, self.lc1.weight.data, self.wc_hi, self.wc_lo,
+                                 self.wt_hi, self.wt_lo)
 
     def _buffers(self, B):
         b = self._buf.get(B)
@@ -123,6 +123,18 @@ class FusedActorCritic:
 
     def stage_trunk_wgrad(self, obs, b):
         ops.mlp_trunk_wgrad(b["dz1"], obs, self.ws_trunk, self.l0.weight.grad, self.l0.bias.grad)
+
+    def forward_inference(self, obs):
+        """Rollout forward (no activations kept): trunk + both hidden layers + heads in ONE launch for obs_dim <= 4,
+        H <= 128 (the trunk layer is generated inside the kernel); otherwise the training forward without refresh."""
+        if self.obs_dim > 4 or self.H > 128:
+            return self.forward(obs, refresh=False)
+        B = obs.shape[0]
+        b = self._buffers(B)
+        ops.mlp_fwd_from_obs(obs, self.l0.weight.data, self.l0.bias.data, self.slope,
+                             (self.wa_hi, self.wa_lo, self.la1.bias.data, None, self.la2.weight.data, self.la2.bias.data, b["act"]),
+                             (self.wc_hi, self.wc_lo, self.lc1.bias.data, None, self.lc2.weight.data, self.lc2.bias.data, b["v"]))
+        return b["act"], b["v"][:, 0]
 
     # ---------------------------------------------------------------------------------------------- forward / backward
     def forward(self, obs, refresh=True):

@@ -189,10 +189,23 @@ def head_bwd_act(dout, y, weight2, slope, dz, db1, dw2, db2, workspace):
 
 
 # ------------------------------------------------------------------------------------------------ tcgen05 dense layers
+def _rows_ld(x):
+    """(data pointer, row pitch in floats) of a 2-D fp32 tensor whose rows are contiguous (e.g. a column slice)."""
+    if not x.is_cuda or x.dtype != F32 or x.dim() != 2 or x.stride(1) != 1:
+        raise _lib.XB200Error("expected a CUDA fp32 matrix with contiguous rows")
+    return x.data_ptr(), x.stride(0)
+
+
 def dense_split_weights(W, hi, lo, thi=None, tlo=None, toff=0):
     N, K = W.shape
     _lib.call("xb_dense_split_weights", _p(W, F32), N, K, _p(hi, F32), _p(lo, F32), _p(thi, F32), _p(tlo, F32),
               thi.shape[1] if thi is not None else 0, toff, _stream())
+
+
+def dense_split_weights2(w0, hi0, lo0, w1, hi1, lo1, thi, tlo):
+    N, K = w0.shape
+    _lib.call("xb_dense_split_weights2", _p(w0, F32), _p(hi0, F32), _p(lo0, F32), _p(w1, F32), _p(hi1, F32), _p(lo1, F32),
+              N, K, _p(thi, F32), _p(tlo, F32), _stream())
 
 
 def dense_fwd(x, w_hi, w_lo, bias, slope, y, head_w=None, head_b=None, head_out=None, b_resident=True):
@@ -212,6 +225,17 @@ def dense_fwd2(x, slope, layer0, layer1, b_resident=True):
         args += [_p(w_hi, F32), _p(w_lo, F32), _p(bias, F32), _p(y, F32), _p(head_w, F32), _p(head_b, F32),
                  head_w.shape[0] if head_w is not None else 0, _p(head_out, F32)]
     _lib.call("xb_dense_fwd2", _p(x, F32), M, K, N, float(slope), *args, 1 if b_resident else 0, _stream())
+
+
+def mlp_fwd_from_obs(obs, w0, b0, slope, layer0, layer1):
+    """Whole actor-critic forward in one launch; layerK = (w_hi, w_lo, bias, y or None, head_w, head_b, head_out)."""
+    ptr, ld = _rows_ld(obs)
+    args = []
+    for w_hi, w_lo, bias, y, head_w, head_b, head_out in (layer0, layer1):
+        args += [_p(w_hi, F32), _p(w_lo, F32), _p(bias, F32), _p(y, F32), _p(head_w, F32), _p(head_b, F32),
+                 head_w.shape[0], _p(head_out, F32)]
+    _lib.call("xb_mlp_fwd_from_obs", ptr, ld, obs.shape[1], _p(w0, F32), _p(b0, F32), obs.shape[0], w0.shape[0],
+              float(slope), *args, _stream())
 
 
 def dense_dgrad(y0, dout0, w2_0, y1, dout1, w2_1, wt_hi, wt_lo, h1, slope, dz1):
@@ -237,13 +261,6 @@ def dense_wgrad(y0, dout0, w2_0, y1, dout1, w2_1, x, slope, workspace, dW0, db0,
 
 
 # ------------------------------------------------------------------------------------------------ trunk layer (SIMT)
-def _rows_ld(x):
-    """(data pointer, row pitch in floats) of a 2-D fp32 tensor whose rows are contiguous (e.g. a column slice)."""
-    if not x.is_cuda or x.dtype != F32 or x.dim() != 2 or x.stride(1) != 1:
-        raise _lib.XB200Error("expected a CUDA fp32 matrix with contiguous rows")
-    return x.data_ptr(), x.stride(0)
-
-
 def mlp_trunk_fwd(obs, w0, b0, slope, h1):
     ptr, ld = _rows_ld(obs)
     _lib.call("xb_mlp_trunk_fwd", ptr, ld, obs.shape[1], _p(w0, F32), _p(b0, F32), float(slope), _p(h1, F32),
