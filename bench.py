@@ -173,11 +173,11 @@ def count_launches(agent):
     """Hand-written kernel launches inside one PPO iteration (counted from the calls the agent makes)."""
     T, E, M = agent.n_steps, agent.n_epoch, agent.buffer_size // agent.batch_size
     if agent.learner._fused is not None:
-        # rollout: weight split (2); per step trunk, hidden x2 (one launch), sample, env_step, store; bootstrap forward (2);
+        # rollout: weight split (1); per step the one-launch forward + the fused sample/env/store step; bootstrap forward (1);
         # GAE + record packing (2); counter (1)
-        per_rollout = 2 + T * 5 + 2 + 2 + 1
-        # update: gather, weight split (2), trunk, hidden, loss, dgrad, wgrad + reduce, trunk wgrad + reduce, grad-norm, adam
-        per_update = 1 + 2 + 1 + 1 + 1 + 1 + 2 + 2 + 2
+        per_rollout = 1 + T * (2 if agent._fused_step else 4) + 1 + 2 + 1   # split; per step forward + fused step; bootstrap fwd
+        # update: gather, weight split, trunk, hidden, loss, dgrad, wgrad + reduce, trunk wgrad + reduce, grad-norm, adam
+        per_update = 1 + 1 + 1 + 1 + 1 + 1 + 2 + 2 + 2
     else:
         per_rollout = T * (3 + 5) + 5 + 2 + 1  # per step: sample, env_step, store, 3 bias+act, 2 head; bootstrap fwd; GAE + pack; counter
         per_update = 1 + 1 + 2 + 5 + 3         # gather, loss, grad-norm + adam, fwd: 3 bias+act + 2 head, bwd: 2 head+act + 1 act+bias
@@ -225,15 +225,35 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
     x_cur, x_nxt = agent._x[agent._cur], agent._x[agent._cur ^ 1]
     snap = agent._snapshot()
     env_bytes = (78 if gauss else 118) * N
+    sep = 0 if agent._fused_step else T      # the three per-step kernels are fused into one launch on the rollout path
     add("env_step", lambda: ops.env_step(env._kind, env._state, env._rng, env._elapsed, env._ep_score,
                                          agent._act.reshape(N), x_nxt[N:], x_nxt[:N], env._rew, env._term, env._trunc,
                                          env._reset_obs, env._ep_step_out, env._ep_score_out, env.max_episode_length,
-                                         ep_stats=env.ep_stats), env_bytes, T)
+                                         ep_stats=env.ep_stats), env_bytes, sep)
     agent._restore(snap)
-    add("sample_logp", lambda: agent._sample(dist, 0), N * ((4 + 4 + 4) if gauss else (8 + 8 + 4)), T)
+    add("sample_logp", lambda: agent._sample(dist, 0), N * ((4 + 4 + 4) if gauss else (8 + 8 + 4)), sep)
     vN = v[:N].contiguous()
     add("store", lambda: mem.store_device(x_cur[:N], agent._act, env._rew, vN, env._term, env._trunc, agent._logp, 0),
-        N * 2 * 36, T)
+        N * 2 * 36, sep)
+    if agent._fused_step:
+        snap = agent._snapshot()
+        cur = agent._cur
+
+        def one_step():
+            agent._rollout_step(0)
+        with torch.no_grad():
+            dist0, v0 = dist, v
+            prm = dist0.get_param()
+            act_param = prm[:N] if not gauss else prm[0][:N]
+            logstd = None if not gauss else agent.policy.actor.logstd.detach()
+            add("rollout_step_fused", lambda: ops.rollout_step(
+                env._kind, act_param, logstd, v0[:N], agent.seed, agent._ctr, 0, env._state, env._rng, env._elapsed,
+                env._ep_score, x_nxt[N:], x_nxt[:N], env._rew, env._term, env._trunc, env._reset_obs, env._ep_step_out,
+                env._ep_score_out, env.ep_stats, env.max_episode_length, x_cur[:N], agent._act, agent._logp, mem._obs[0],
+                mem._act[0], mem._rew[0], mem._val[0], mem._term[0], mem._trunc[0], mem._logp[0]),
+                env_bytes + N * ((4 + 4 + 4) if gauss else (8 + 8 + 4)) + N * 36, T)
+        agent._restore(snap)
+        agent._cur = cur
     add("gae_and_pack", lambda: mem.finish_rollout(agent._boot_last), (20 + 1 + (64 if mem._rec is not None else 0)) * N * T, 1)
     idx = agent._perm[:B]
     agent._perm.copy_(torch.randperm(agent.buffer_size, device="cuda"))

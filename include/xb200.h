@@ -243,6 +243,23 @@ int xb_head_bwd_act(const float* dout, const float* y, const float* W2, float sl
 int xb_bias_act_fwd(float* y, const float* bias, float slope, int64_t B, int H, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * One vector step of the device-resident rollout in ONE launch: xb_sample_* + xb_env_step + xb_store fused per env
+ * (PPOCLIP_Agent._action ppoclip_agent.py:50-57; DummyVecEnv_Gym.step_wait gym_vec_env.py:200-212;
+ * DummyOnPolicyBuffer.store memory_tools.py:196-204).  CartPole-v1: act_param = logits [N][2], act_out int64 [N];
+ * Pendulum-v1: act_param = mu [N][1], logstd [1], act_out f32 [N].  x_in = the observations the action was computed
+ * from (stored as the transition's obs); all other arguments as in xb_env_step / xb_store.  Physics and store are
+ * bit-identical to the three separate calls; the sampled action may differ from xb_sample_* in the last ulp of the
+ * transcendental functions (this translation unit is built without FMA contraction).
+ * ---------------------------------------------------------------------------------------------------------- */
+int xb_rollout_step(int env_kind, const float* act_param, const float* logstd, const float* val, uint64_t seed,
+                    const uint64_t* counter_dev, uint64_t offset, double* state, uint64_t* rng, int32_t* elapsed,
+                    double* ep_score, float* obs, float* next_obs, float* rew, uint8_t* term, uint8_t* trunc,
+                    float* reset_obs, int32_t* ep_step_out, double* ep_score_out, double* ep_stats,
+                    int max_episode_steps, const float* x_in, void* act_out, float* logp_out, float* obs_row,
+                    float* act_row, float* rew_row, float* val_row, float* term_row, uint8_t* trunc_row, float* logp_row,
+                    const float* rew_scale, float rew_clip, int64_t N, xb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Dense layers of the policy/value MLP at large batch on the tcgen05 tensor cores with fp32-level accuracy
  * ("3xTF32": x = hi + lo split, three kind::tf32 MMAs per k-step, fp32 accumulation in TMEM; csrc/dense_tc.cu).
  * Replace the cuBLAS SIMT sgemm calls torch issues for Basic_MLP / ActorNet / CriticNet forward

@@ -133,6 +133,11 @@ class PPOCLIP_Agent:
         if self.use_obsnorm and self.learner.world_size > 1:
             raise NotImplementedError("use_obsnorm with env sharding needs the per-step all-reduce of the observation "
                                       "moments inside the rollout graph; not wired yet")
+        # one launch per vector step (sample + env step + store) for the two classic-control action shapes
+        import os as _os
+        self._fused_step = (_os.environ.get("XB_FUSED_STEP", "1") != "0" and
+                            ((self.discrete and int(self.action_space.n) == 2) or
+                             (not self.discrete and self.memory.act_dim == 1)))
         self._rollout_graph = None
         self._epoch_graph = None
         self._stage_graphs = None
@@ -176,12 +181,28 @@ class PPOCLIP_Agent:
         dist, v = self._policy_forward(x_in)                      # V on [obs_t ; terminal obs of step t-1]
         if t > 0:
             mem._boot[t - 1].copy_(v[N:])                         # bootstrap for envs truncated at step t-1 (:99)
-        self._sample(dist, t)
-        ops.env_step(env._kind, env._state, env._rng, env._elapsed, env._ep_score, self._act.reshape(N),
-                     x_nxt[N:], x_nxt[:N], env._rew, env._term, env._trunc, env._reset_obs, env._ep_step_out,
-                     env._ep_score_out, env.max_episode_length, ep_stats=env.ep_stats)
-        mem.store_device(x_in[:N], self._act, env._rew, v[:N].contiguous(), env._term, env._trunc, self._logp, t,
-                         rew_std=self._rew_std if self.use_rewnorm else None, rew_clip=self.rewnorm_range)
+        if self._fused_step:
+            # sample + env step + store in one launch (csrc/env_classic.cu: rollout_step_kernel)
+            prm = dist.get_param()
+            if self.discrete:
+                act_param, logstd = prm[:N], None
+            else:
+                act_param = prm[0][:N]
+                logstd = getattr(getattr(self.policy, "actor", None), "logstd", None)
+                logstd = logstd.detach() if logstd is not None else prm[1].log().contiguous()
+            ops.rollout_step(env._kind, act_param, logstd, v[:N], self.seed, self._ctr, t, env._state, env._rng,
+                             env._elapsed, env._ep_score, x_nxt[N:], x_nxt[:N], env._rew, env._term, env._trunc,
+                             env._reset_obs, env._ep_step_out, env._ep_score_out, env.ep_stats, env.max_episode_length,
+                             x_in[:N], self._act, self._logp, mem._obs[t], mem._act[t], mem._rew[t], mem._val[t],
+                             mem._term[t], mem._trunc[t], mem._logp[t],
+                             rew_std=self._rew_std if self.use_rewnorm else None, rew_clip=self.rewnorm_range)
+        else:
+            self._sample(dist, t)
+            ops.env_step(env._kind, env._state, env._rng, env._elapsed, env._ep_score, self._act.reshape(N),
+                         x_nxt[N:], x_nxt[:N], env._rew, env._term, env._trunc, env._reset_obs, env._ep_step_out,
+                         env._ep_score_out, env.max_episode_length, ep_stats=env.ep_stats)
+            mem.store_device(x_in[:N], self._act, env._rew, v[:N].contiguous(), env._term, env._trunc, self._logp, t,
+                             rew_std=self._rew_std if self.use_rewnorm else None, rew_clip=self.rewnorm_range)
         if self.use_rewnorm:                                      # returns tracker + ret_rms.update (:87,:91-92)
             ops.returns_track(self._returns, env._rew, env._term, env._trunc, self.gamma, self._ret_sums, self._ret_ws)
             ops.rms_merge_scalar(self._ret_sums, self._ret_rms, self._rew_std)

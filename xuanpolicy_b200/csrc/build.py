@@ -31,7 +31,7 @@ SOURCES = {
     "dense_tc.cu": [],
     "mlp_trunk.cu": [],
 }
-HEADERS = ["common.cuh", "sm100.cuh", "crtrig.cuh", "crtrig_consts.inc", os.path.join("..", "..", "include", "xb200.h")]
+HEADERS = ["common.cuh", "sm100.cuh", "sample.cuh", "crtrig.cuh", "crtrig_consts.inc", os.path.join("..", "..", "include", "xb200.h")]
 
 
 def _stale(target, deps):

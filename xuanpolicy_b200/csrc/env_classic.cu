@@ -13,6 +13,7 @@
 // 16 obs (+16 next_obs), 4 rew, 2 flags, 4+8 episode outputs; all accesses are SoA and fully coalesced,
 // observations are one float4 per env.
 #include "common.cuh"
+#include "sample.cuh"
 #include "crtrig.cuh"
 
 namespace xb {
@@ -47,6 +48,7 @@ constexpr double kPi = 3.141592653589793;
 struct CartPole {
     static constexpr int S = 4;
     typedef int64_t action_t;
+    static constexpr bool kDiscrete = true;
     __device__ static void draw(double (&st)[4], Pcg64& g) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) st[k] = pcg64_uniform(g, -0.05, 0.05 - (-0.05));
@@ -82,6 +84,7 @@ struct CartPole {
 struct Pendulum {
     static constexpr int S = 2;
     typedef float action_t;
+    static constexpr bool kDiscrete = false;
     __device__ static void draw(double (&st)[2], Pcg64& g) {
         st[0] = pcg64_uniform(g, -kPi, kPi - (-kPi));
         st[1] = pcg64_uniform(g, -1.0, 1.0 - (-1.0));
@@ -199,6 +202,125 @@ __global__ void __launch_bounds__(128)
     ep_score[e] = score;
 }
 
+// ------------------------------------------------------------------------------------------------ fused rollout step
+// One launch per vector step of the device-resident rollout: sample the action + its log-prob from the policy outputs
+// (PPOCLIP_Agent._action, ppoclip_agent.py:50-57), step the env (DummyVecEnv_Gym.step_wait, gym_vec_env.py:200-212) and
+// store the transition into rollout row t (DummyOnPolicyBuffer.store, memory_tools.py:196-204) — the three per-env
+// kernels sample_* / env_step / store back to back in one thread, the action never leaves registers.
+struct RolloutStepArgs {
+    // policy outputs for rows [0, N): logits [N][2] (Discrete(2)) or mu [N][1] + logstd [1]; value [N]
+    const float* act_param;
+    const float* logstd;
+    const float* val;
+    uint64_t seed;
+    const uint64_t* counter_dev;
+    uint64_t offset;
+    // env state (SoA) and per-step outputs, as in env_step_kernel
+    double* state;
+    uint64_t* rng;
+    int32_t* elapsed;
+    double* ep_score;
+    float4* obs;          // terminal-inclusive observation of this step
+    float4* next_obs;     // reset-substituted observation the policy acts on next
+    float* rew;
+    uint8_t* term;
+    uint8_t* trunc;
+    float4* reset_obs;
+    int32_t* ep_step_out;
+    double* ep_score_out;
+    double* ep_stats;
+    int max_steps;
+    // the observation the action was computed from, and the action / log-prob scratch the agent exposes
+    const float4* x_in;
+    void* act_out;
+    float* logp_out;
+    // rollout buffer row t
+    float4* obs_row;
+    float* act_row;
+    float* rew_row;
+    float* val_row;
+    float* term_row;
+    uint8_t* trunc_row;
+    float* logp_row;
+    const float* rew_scale;   // nullable: rewards are divided by *rew_scale and clipped to +-rew_clip (use_rewnorm)
+    float rew_clip;
+    int64_t N;
+};
+
+template <class Env>
+__global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs a) {
+    const int64_t N = a.N;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    // ---- sample (sample.cuh)
+    const Philox ph = philox_setup(a.seed, a.counter_dev, a.offset);
+    typename Env::action_t act;
+    float logp;
+    if (Env::kDiscrete) {
+        act = (typename Env::action_t)sample_categorical_one(a.act_param + e * 2, 2, e, ph, &logp);
+        ((int64_t*)a.act_out)[e] = (int64_t)act;
+        a.act_row[e] = (float)act;
+    } else {
+        float x;
+        logp = sample_gaussian_one(a.act_param + e, a.logstd, 1, e, ph, &x);
+        act = (typename Env::action_t)x;
+        ((float*)a.act_out)[e] = x;
+        a.act_row[e] = x;
+    }
+    a.logp_out[e] = logp;
+    a.logp_row[e] = logp;
+    a.obs_row[e] = a.x_in[e];
+    a.val_row[e] = a.val[e];
+    // ---- env step (identical arithmetic to env_step_kernel)
+    double st[Env::S];
+#pragma unroll
+    for (int k = 0; k < Env::S; ++k) st[k] = a.state[k * N + e];
+    int32_t el = a.elapsed[e];
+    double score = a.ep_score[e];
+    bool terminated;
+    const double reward = Env::step(st, act, terminated);
+    el += 1;
+    const bool truncated = el >= a.max_steps;
+    score = __dadd_rn(score, reward);
+    float4 o = Env::observe(st);
+    a.obs[e] = o;
+    const float r32 = (float)reward;
+    a.rew[e] = r32;
+    a.term[e] = terminated ? 1 : 0;
+    a.trunc[e] = truncated ? 1 : 0;
+    a.ep_step_out[e] = el;
+    a.ep_score_out[e] = score;
+    if (terminated || truncated) {
+        if (a.ep_stats) {
+            atomicAdd(&a.ep_stats[0], 1.0);
+            atomicAdd(&a.ep_stats[1], score);
+            atomicAdd(&a.ep_stats[2], (double)el);
+        }
+        Pcg64 g = load_rng<Env>(a.rng, N, e);
+        Env::draw(st, g);
+        a.rng[e] = g.hi;
+        a.rng[N + e] = g.lo;
+        el = 0;
+        score = 0.0;
+        o = Env::observe(st);
+        a.reset_obs[e] = o;
+    }
+    if (a.next_obs) a.next_obs[e] = o;
+#pragma unroll
+    for (int k = 0; k < Env::S; ++k) a.state[k * N + e] = st[k];
+    a.elapsed[e] = el;
+    a.ep_score[e] = score;
+    // ---- store the rest of the transition (store_kernel)
+    float r = r32;
+    if (a.rew_scale) {
+        r = r / *a.rew_scale;
+        r = fminf(fmaxf(r, -a.rew_clip), a.rew_clip);
+    }
+    a.rew_row[e] = r;
+    a.term_row[e] = terminated ? 1.0f : 0.0f;
+    if (a.trunc_row) a.trunc_row[e] = truncated ? 1 : 0;
+}
+
 __global__ void sincos_kernel(const double* __restrict__ x, double* __restrict__ s, double* __restrict__ c, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) sincos_cr(x[i], &s[i], &c[i]);
@@ -258,6 +380,32 @@ extern "C" int xb_env_step(int env_kind, double* state, uint64_t* rng, int32_t* 
 extern "C" int xb_sincos_f64(const double* x, double* s, double* c, int64_t n, xb_stream_t stream) {
     if (n <= 0 || !x || !s || !c) return XB_E_BADARG;
     sincos_kernel<<<ceil_div_i64(n, 128), 128, 0, (cudaStream_t)stream>>>(x, s, c, n);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_rollout_step(int env_kind, const float* act_param, const float* logstd, const float* val, uint64_t seed,
+                               const uint64_t* counter_dev, uint64_t offset, double* state, uint64_t* rng,
+                               int32_t* elapsed, double* ep_score, float* obs, float* next_obs, float* rew, uint8_t* term,
+                               uint8_t* trunc, float* reset_obs, int32_t* ep_step_out, double* ep_score_out,
+                               double* ep_stats, int max_episode_steps, const float* x_in, void* act_out, float* logp_out,
+                               float* obs_row, float* act_row, float* rew_row, float* val_row, float* term_row,
+                               uint8_t* trunc_row, float* logp_row, const float* rew_scale, float rew_clip, int64_t N,
+                               xb_stream_t stream) {
+    if (N <= 0 || !act_param || !val || !state || !rng || !elapsed || !ep_score || !obs || !rew || !term || !trunc ||
+        !reset_obs || !ep_step_out || !ep_score_out || !x_in || !act_out || !logp_out || !obs_row || !act_row ||
+        !rew_row || !val_row || !term_row || !logp_row)
+        return XB_E_BADARG;
+    if (env_kind == XB_ENV_PENDULUM && !logstd) return XB_E_BADARG;
+    RolloutStepArgs a{act_param, logstd, val, seed, counter_dev, offset, state, rng, elapsed, ep_score, (float4*)obs,
+                      (float4*)next_obs, rew, term, trunc, (float4*)reset_obs, ep_step_out, ep_score_out, ep_stats,
+                      max_episode_steps, (const float4*)x_in, act_out, logp_out, (float4*)obs_row, act_row, rew_row,
+                      val_row, term_row, trunc_row, logp_row, rew_scale, rew_clip, N};
+    cudaStream_t s = (cudaStream_t)stream;
+    int block = env_block(N), grid = ceil_div_i64(N, block);
+    if (env_kind == XB_ENV_CARTPOLE) rollout_step_kernel<CartPole><<<grid, block, 0, s>>>(a);
+    else if (env_kind == XB_ENV_PENDULUM) rollout_step_kernel<Pendulum><<<grid, block, 0, s>>>(a);
+    else return XB_E_UNSUPPORTED;
     XB_LAUNCH_CHECK();
     return 0;
 }

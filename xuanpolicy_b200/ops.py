@@ -45,6 +45,19 @@ def env_step(kind, state, rng, elapsed, ep_score, actions, obs, next_obs, rew, t
               N, _stream())
 
 
+def rollout_step(kind, act_param, logstd, val, seed, counter, offset, state, rng, elapsed, ep_score, obs, next_obs, rew,
+                 term, trunc, reset_obs, ep_step_out, ep_score_out, ep_stats, max_steps, x_in, act_out, logp_out, obs_row,
+                 act_row, rew_row, val_row, term_row, trunc_row, logp_row, rew_std=None, rew_clip=0.0):
+    """sample + env step + store of one vector step in one launch (see xb_rollout_step in include/xb200.h)."""
+    N = elapsed.numel()
+    _lib.call("xb_rollout_step", kind, _p(act_param, F32), _p(logstd, F32), _p(val, F32), int(seed), _p(counter, I64),
+              int(offset), _p(state, F64), _p(rng, I64), _p(elapsed, I32), _p(ep_score, F64), _p(obs, F32),
+              _p(next_obs, F32), _p(rew, F32), _p(term, U8), _p(trunc, U8), _p(reset_obs, F32), _p(ep_step_out, I32),
+              _p(ep_score_out, F64), _p(ep_stats, F64), max_steps, _p(x_in, F32), _p(act_out, I64 if kind == 0 else F32),
+              _p(logp_out, F32), _p(obs_row, F32), _p(act_row, F32), _p(rew_row, F32), _p(val_row, F32),
+              _p(term_row, F32), _p(trunc_row, U8), _p(logp_row, F32), _p(rew_std, F32), float(rew_clip), N, _stream())
+
+
 def sincos_f64(x):
     s, c = torch.empty_like(x), torch.empty_like(x)
     _lib.call("xb_sincos_f64", _p(x, F64), _p(s, F64), _p(c, F64), x.numel(), _stream())
