@@ -312,8 +312,12 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
         # rollout shape: 2N rows (the obs to act on + the previous step's terminal obs)
         x_r = agent._x[agent._cur][:, :od]
         br = fused._buffers(2 * N)
-        add("mlp_trunk_fwd_rollout", lambda: fused.stage_trunk(x_r, br), 2 * N * (od * 4 + H * 4), T + 1)
-        add("dense_fwd2_tc_rollout", lambda: fused.stage_hidden(br), 3 * 4 * 2 * N * H, T + 1, flops=2 * 2.0 * 2 * N * H * H)
+        if od <= 4 and H <= 128:   # the whole forward in one launch: trunk generated in-kernel, heads only
+            add("mlp_fwd_from_obs_rollout", lambda: fused.forward_inference(x_r), 2 * N * (od * 4 + (A_out + 1) * 4), T + 1,
+                flops=2 * 2.0 * 2 * N * H * H)
+        else:
+            add("mlp_trunk_fwd_rollout", lambda: fused.stage_trunk(x_r, br), 2 * N * (od * 4 + H * 4), T + 1)
+            add("dense_fwd2_tc_rollout", lambda: fused.stage_hidden(br), 3 * 4 * 2 * N * H, T + 1, flops=2 * 2.0 * 2 * N * H * H)
     else:
         # torch/cuBLAS GEMMs + the non-GEMM half of the MLP (csrc/mlp_epilogue.cu): per update, one forward and one
         # backward epilogue per Linear+LeakyReLU block (3 blocks: representation, actor hidden, critic hidden)

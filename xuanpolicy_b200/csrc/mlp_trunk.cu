@@ -58,11 +58,12 @@ __global__ void __launch_bounds__(256) trunk_wgrad_kernel(const float4* __restri
         for (int i = 0; i <= OBS; ++i) acc[e][i] = 0.f;
     if (slot < rows_per_block) {
         const int64_t step = (int64_t)gridDim.x * rows_per_block;
-        for (int64_t b0 = (int64_t)blockIdx.x * rows_per_block + slot; b0 < B; b0 += 4 * step) {
-            float4 d[4];
-            float x[4][OBS];
+        constexpr int U = 8;                        // independent rows in flight per thread
+        for (int64_t b0 = (int64_t)blockIdx.x * rows_per_block + slot; b0 < B; b0 += U * step) {
+            float4 d[U];
+            float x[U][OBS];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {           // 4 independent rows in flight per thread
+            for (int u = 0; u < U; ++u) {
                 const int64_t b = b0 + u * step;
                 const bool ok = b < B;
                 d[u] = ok ? dz1[b * tpr + q] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256) trunk_wgrad_kernel(const float4* __restri
                 for (int i = 0; i < OBS; ++i) x[u][i] = ok ? __ldg(obs + b * ld + i) : 0.f;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const float dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256) trunk_wgrad_reduce_kernel(const float* __
     }
 }
 
-constexpr int kTrunkBlocks = 2 * kNumSMs;
+constexpr int kTrunkBlocks = 3 * kNumSMs;
 
 }  // namespace xb
 
