@@ -123,3 +123,43 @@ def test_rollout_forward_from_observations_matches_training_forward(env_id, B):
     a2, v2 = fused.forward_inference(obs)
     torch.cuda.synchronize()
     assert _rel(a2, a1) < 2e-5 and _rel(v2, v1) < 2e-5
+
+
+def test_tensor_core_update_matches_reference_golden():
+    """The whole native update with the MLP on the tcgen05 kernels (forward, loss kernel, dgrad/wgrad, clip + Adam)
+    against the REFERENCE's own `PPOCLIP_Learner.update` output (tests/golden/loss_gauss_h128.npz, generated by running
+    the unmodified reference): info scalars, every param.grad before clipping (1e-4), parameters after the step (1e-5)."""
+    import xuanpolicy_b200 as xb
+    from tests.helpers import load_golden, rel_close
+    from xuanpolicy_b200 import policies, spaces
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = load_golden("loss_gauss_h128")
+    m = g["meta"]
+    dev = "cuda"
+    for tag, clip in (("noclip", False), ("clip", True)):
+        pol = policies.make_policy(spaces.Box(-1, 1, (3,)), spaces.Box(-2.0, 2.0, (1,)), hidden=(m["hidden"],), device=dev)
+        pol.load_state_dict({k[3:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("p0/")})
+        opt = torch.optim.Adam(pol.parameters(), 4e-4, eps=1e-5)
+        sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=1000)
+        learner = xb.PPOCLIP_Learner(pol, opt, sched, dev, "/tmp", vf_coef=m["vf_coef"], ent_coef=m["ent_coef"],
+                                     clip_range=m["clip_range"], clip_grad_norm=m["clip_grad_norm"], use_grad_clip=clip)
+        flat = learner.enable_fused_optimizer()
+        fused = learner._fused
+        assert fused is not None
+        t = lambda k: torch.as_tensor(g[k], device=dev).float().contiguous()
+        B = g["ret"].shape[0]
+        act_out, v = fused.forward(t("obs"))
+        learner._loss_backward(fused.dist_params(act_out), v, t("act").reshape(B, -1), t("ret"), t("adv"), t("old_logp"),
+                               t("val"), 1.0 / B, flat=flat, fused=fused)
+        torch.cuda.synchronize()
+        for k, p in pol.named_parameters():
+            ok, err = rel_close(p.grad.cpu().numpy(), g["grad_noclip/%s" % k], 1e-4)
+            assert ok, (tag, k, err)
+        learner.stage_optimizer()
+        info = learner.info(B)
+        for k in ("actor-loss", "critic-loss", "entropy", "predict_value"):
+            ref = float(g["info_%s/%s" % (tag, k)])
+            assert abs(float(info[k]) - ref) <= 1e-4 * max(1.0, abs(ref)), (k, float(info[k]), ref)
+        for k, p in pol.named_parameters():
+            ok, err = rel_close(p.detach().cpu().numpy(), g["p1_%s/%s" % (tag, k)], 1e-5)
+            assert ok, (tag, k, err)
