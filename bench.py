@@ -176,8 +176,8 @@ def count_launches(agent):
         # rollout: weight split (1); per step the one-launch forward + the fused sample/env/store step; bootstrap forward (1);
         # GAE + record packing (2); counter (1)
         per_rollout = 1 + T * (2 if agent._fused_step else 4) + 1 + 2 + 1   # split; per step forward + fused step; bootstrap fwd
-        # update: gather, weight split, trunk, hidden, loss, dgrad, wgrad + reduce, trunk wgrad + reduce, grad-norm, adam
-        per_update = 1 + 1 + 1 + 1 + 1 + 1 + 2 + 2 + 2
+        # update: gather, weight split, trunk, hidden, loss, dgrad, wgrad, trunk wgrad, tail (all reduces), grad-norm, adam
+        per_update = 1 + 1 + 1 + 1 + 1 + 1 + 1 + 1 + 1 + 2
     else:
         per_rollout = T * (3 + 5) + 5 + 2 + 1  # per step: sample, env_step, store, 3 bias+act, 2 head; bootstrap fwd; GAE + pack; counter
         per_update = 1 + 1 + 2 + 5 + 3         # gather, loss, grad-norm + adam, fwd: 3 bias+act + 2 head, bwd: 2 head+act + 1 act+bias
@@ -309,6 +309,7 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
         add("dense_wgrad_tc", lambda: fused.stage_wgrad(bu, dact, dv2), 3 * f4 + B * (A_out + 1) * 4, upd,
             flops=2 * 2.0 * B * H * (H + 1))
         add("mlp_trunk_wgrad", lambda: fused.stage_trunk_wgrad(obs_u, bu), f4 + B * od * 4, upd)
+        add("mlp_backward_tail", lambda: fused.stage_tail(), fused.ws_wgrad.numel() * 4 + fused.ws_trunk.numel() * 4, upd)
         # rollout shape: 2N rows (the obs to act on + the previous step's terminal obs)
         x_r = agent._x[agent._cur][:, :od]
         br = fused._buffers(2 * N)

@@ -294,6 +294,14 @@ int xb_dense_fwd(const float* X, int64_t M, int K, const float* Whi, const float
  *                           activations); per-CTA partials are summed in a fixed order (deterministic).
  *                           H_out, H_in in {128, 256}.  workspace: xb_dense_wgrad_workspace_floats(H_in) floats. */
 int xb_dense_wgrad_workspace_floats(int H_in);
+/*   xb_mlp_backward_tail    ONE launch that finishes a backward pass: sums xb_dense_wgrad's partials (called with dW0 == NULL)
+ *                           into the eight hidden/head gradients, xb_mlp_trunk_wgrad's partials (called with dW0 == NULL)
+ *                           into dWt/dbt, and converts the loss kernel's fp64 log-std gradient to the fp32 parameter
+ *                           gradient (dls64 / trunk_ws may be NULL). */
+int xb_mlp_backward_tail(const float* wgrad_ws, int H_out, int H_in, int n_sources, int nh0, int nh1, float* dW0, float* db0,
+                         float* dw2_0, float* db2_0, float* dW1, float* db1, float* dw2_1, float* db2_1,
+                         const float* trunk_ws, int trunk_parts, int obs_dim, float* dWt, float* dbt, const double* dls64,
+                         float* dls32, int A, xb_stream_t stream);
 int xb_dense_wgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, const float* Y1, const float* dout1,
                    const float* w2_1, int nh1, const float* X, int64_t B, int H_out, int H_in, float slope,
                    float* workspace, float* dW0, float* db0, float* dw2_0, float* db2_0, float* dW1, float* db1,
@@ -322,11 +330,13 @@ int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int n
  * (xuance/torch/representations/mlp.py:40-51) — and its weight gradient; bandwidth-bound SIMT kernels (csrc/mlp_trunk.cu).
  *   xb_mlp_trunk_fwd    h1[b][n] = leaky_relu(b0[n] + sum_i obs[b*ld + i] W0[n][i])     obs_dim <= 8, H % 4 == 0
  *   xb_mlp_trunk_wgrad  dW0[n][i] = sum_b dz1[b][n] obs[b*ld + i],  db0[n] = sum_b dz1[b][n]   (deterministic two-stage sum)
- * workspace: xb_mlp_trunk_wgrad_workspace_floats(obs_dim, H) floats.
+ * workspace: xb_mlp_trunk_wgrad_workspace_floats(obs_dim, H) floats.  dW0 == NULL: leave the partial sums in the
+ * workspace (xb_mlp_backward_tail finishes them together with the hidden layers' partials in one launch).
  * ---------------------------------------------------------------------------------------------------------- */
 int xb_mlp_trunk_fwd(const float* obs, int ld, int obs_dim, const float* W0, const float* b0, float slope, float* h1,
                      int64_t B, int H, xb_stream_t stream);
 int xb_mlp_trunk_wgrad_workspace_floats(int obs_dim, int H);
+int xb_mlp_trunk_wgrad_parts(void);     /* number of partial sums per output in the workspace */
 int xb_mlp_trunk_wgrad(const float* dz1, const float* obs, int ld, int obs_dim, float* workspace, float* dW0, float* db0,
                        int64_t B, int H, xb_stream_t stream);
 

@@ -57,6 +57,9 @@ SIGNATURES = {
                        _vp, _vp, _vp, _vp],
     "xb_mlp_trunk_fwd": [_vp, _i32, _i32, _vp, _vp, _f32, _vp, _i64, _i32, _vp],
     "xb_mlp_trunk_wgrad_workspace_floats": [_i32, _i32],
+    "xb_mlp_trunk_wgrad_parts": [],
+    "xb_mlp_backward_tail": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp,
+                             _vp, _vp, _vp, _i32, _vp],
     "xb_mlp_trunk_wgrad": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _i32, _vp],
     "xb_clip_adam_step": [_vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _i64, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp],
 }

@@ -148,10 +148,11 @@ extern "C" int xb_mlp_trunk_fwd(const float* obs, int ld, int obs_dim, const flo
 }
 
 extern "C" int xb_mlp_trunk_wgrad_workspace_floats(int obs_dim, int H) { return kTrunkBlocks * H * (obs_dim + 1); }
+extern "C" int xb_mlp_trunk_wgrad_parts(void) { return kTrunkBlocks; }
 
 extern "C" int xb_mlp_trunk_wgrad(const float* dz1, const float* obs, int ld, int obs_dim, float* workspace, float* dW0,
                                   float* db0, int64_t B, int H, xb_stream_t stream) {
-    if (!dz1 || !obs || !workspace || !dW0 || !db0 || B <= 0 || ld < obs_dim) return XB_E_BADARG;
+    if (!dz1 || !obs || !workspace || (dW0 && !db0) || B <= 0 || ld < obs_dim) return XB_E_BADARG;
     if (!trunk_shape_ok(obs_dim, H) || ((uintptr_t)dz1 & 15u)) return XB_E_UNSUPPORTED;
     const int rows_per_block = 256 / (H / 4);
     const int smem = rows_per_block * H * (obs_dim + 1) * (int)sizeof(float);
@@ -160,6 +161,7 @@ extern "C" int xb_mlp_trunk_wgrad(const float* dz1, const float* obs, int ld, in
     XB_OBS_SWITCH(obs_dim, (trunk_wgrad_kernel<O><<<kTrunkBlocks, 256, smem, s>>>(
                                reinterpret_cast<const float4*>(dz1), obs, ld, workspace, B, H)));
     XB_LAUNCH_CHECK();
+    if (!dW0) return 0;                      // partials only: the caller finishes with xb_mlp_backward_tail
     const int n_out = H * (obs_dim + 1);
     trunk_wgrad_reduce_kernel<<<(n_out + 7) / 8, 256, 0, s>>>(workspace, kTrunkBlocks, H, obs_dim, dW0, db0);
     XB_LAUNCH_CHECK();

@@ -116,13 +116,21 @@ class FusedActorCritic:
                         b["h1"], self.slope, b["dz1"])
 
     def stage_wgrad(self, b, dact, dv2):
-        g = lambda p: p.grad
+        """Per-CTA partial sums only (into ws_wgrad); `stage_tail` finishes them."""
         ops.dense_wgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, b["h1"], self.slope,
-                        self.ws_wgrad, g(self.la1.weight), g(self.la1.bias), g(self.la2.weight), g(self.la2.bias),
-                        g(self.lc1.weight), g(self.lc1.bias), g(self.lc2.weight), g(self.lc2.bias))
+                        self.ws_wgrad, None, None, None, None)
 
     def stage_trunk_wgrad(self, obs, b):
-        ops.mlp_trunk_wgrad(b["dz1"], obs, self.ws_trunk, self.l0.weight.grad, self.l0.bias.grad)
+        """Per-block partial sums only (into ws_trunk); `stage_tail` finishes them."""
+        ops.mlp_trunk_wgrad(b["dz1"], obs, self.ws_trunk, None, None)
+
+    def stage_tail(self, dls64=None, dls32=None):
+        """One launch: all partial sums -> the ten Linear gradients (+ the loss kernel's fp64 log-std gradient -> fp32)."""
+        g = lambda p: p.grad
+        ops.mlp_backward_tail(self.ws_wgrad, self.H, self.H, self.la2.weight.shape[0], 1,
+                              (g(self.la1.weight), g(self.la1.bias), g(self.la2.weight), g(self.la2.bias)),
+                              (g(self.lc1.weight), g(self.lc1.bias), g(self.lc2.weight), g(self.lc2.bias)),
+                              self.ws_trunk, self.obs_dim, g(self.l0.weight), g(self.l0.bias), dls64, dls32)
 
     def forward_inference(self, obs):
         """Rollout forward (no activations kept): trunk + both hidden layers + heads in ONE launch for obs_dim <= 4,
@@ -154,9 +162,10 @@ class FusedActorCritic:
             return _OutParams(mu=act_out, std=None)
         return _OutParams(logits=act_out)
 
-    def backward(self, dact, dv):
+    def backward(self, dact, dv, dls64=None, dls32=None):
         """dact [B, A], dv [B] = dL/d(act_out), dL/d(v) for the most recent `forward`; writes .grad of the ten
-        Linear parameters (views of the flat gradient buffer) — plain stores, no accumulation."""
+        Linear parameters (views of the flat gradient buffer) — plain stores, no accumulation.  dls64 -> dls32: the
+        loss kernel's fp64 log-std gradient, converted in the same tail launch."""
         obs, b = self._last
         B = obs.shape[0]
         if b["dz1"] is None:
@@ -165,3 +174,4 @@ class FusedActorCritic:
         self.stage_dgrad(b, dact, dv2)
         self.stage_wgrad(b, dact, dv2)
         self.stage_trunk_wgrad(obs, b)
+        self.stage_tail(dls64, dls32)

@@ -151,7 +151,9 @@ class PPOCLIP_Learner:
             dmu = torch.empty_like(mu)
             dls = torch.empty(mu.shape[1], dtype=torch.float64, device=mu.device)
             ops.ppo_loss_gaussian(mu, logstd, v, act, ret, adv, old_logp, dmu, dls, dv, self._scalars, **common)
-            if direct:             # the kernel's dL/dlogstd goes straight into the parameter's gradient
+            if direct and fused is not None and flat is not None:   # fp64 -> fp32 log-std gradient inside the tail launch
+                fused.backward(dmu, dv, dls, flat.grad_views[[id(q) for q in flat.params].index(id(param))])
+            elif direct:           # the kernel's dL/dlogstd goes straight into the parameter's gradient
                 backward([p0, v_pred], [dmu, dv])
                 if flat is not None:
                     flat.grad_views[[id(q) for q in flat.params].index(id(param))].copy_(dls)

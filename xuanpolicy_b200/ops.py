@@ -288,3 +288,12 @@ def mlp_trunk_wgrad(dz1, obs, workspace, dw0, db0):
     ptr, ld = _rows_ld(obs)
     _lib.call("xb_mlp_trunk_wgrad", _p(dz1, F32), ptr, ld, obs.shape[1], _p(workspace, F32), _p(dw0, F32), _p(db0, F32),
               obs.shape[0], dz1.shape[1], _stream())
+
+
+def mlp_backward_tail(wgrad_ws, h_out, h_in, nh0, nh1, grads0, grads1, trunk_ws, obs_dim, dwt, dbt, dls64=None, dls32=None):
+    """grads0/grads1 = (dW, db, dw2, db2) of the actor / critic; finishes xb_dense_wgrad + xb_mlp_trunk_wgrad partials."""
+    parts = _lib.load().xb_mlp_trunk_wgrad_parts()
+    _lib.call("xb_mlp_backward_tail", _p(wgrad_ws, F32), h_out, h_in, 2 if grads1 is not None else 1, nh0, nh1,
+              *[_p(g, F32) for g in grads0], *([_p(g, F32) for g in grads1] if grads1 is not None else [None] * 4),
+              _p(trunk_ws, F32), parts, obs_dim, _p(dwt, F32), _p(dbt, F32), _p(dls64, F64), _p(dls32, F32),
+              dls64.numel() if dls64 is not None else 0, _stream())
