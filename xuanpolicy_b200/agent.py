@@ -284,10 +284,10 @@ class PPOCLIP_Agent:
                 self.h2d_bytes += src.numel() * 8
             else:
                 self._perm.copy_(torch.randperm(self.buffer_size, device=self.device))
-            if self.world_size > 1:
-                self._epoch_distributed()
-            elif self._epoch_graph is not None:
+            if self._epoch_graph is not None:
                 self._epoch_graph.replay()
+            elif self.world_size > 1:
+                self._epoch_distributed()
             else:
                 self._epoch_body()
         if self.shuffle == "host":
@@ -318,6 +318,8 @@ class PPOCLIP_Agent:
             self._epoch_graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._epoch_graph):
                 self._epoch_body()
+        elif self._capture_distributed_epoch():
+            pass          # one graph per epoch with the NCCL all-reduces inside it
         else:
             B, lr, mem = self.batch_size, self.learner, self.memory
             graphs = []
@@ -334,6 +336,39 @@ class PPOCLIP_Agent:
             self._stage_graphs = graphs
         torch.cuda.synchronize(self.device)
         self._restore(snap)   # capture does not execute, but keep the state exactly as before either way
+
+    def _capture_distributed_epoch(self):
+        """Env-sharded epoch as ONE CUDA graph: NCCL collectives are graph-capturable, so the two all-reduces of every
+        update are recorded between the kernels instead of being launched from the host (5 host launches per update
+        otherwise).  Returns False (and leaves the per-stage graphs to be captured) if the capture is refused."""
+        import os
+        # opt-in: +3 % at 2 GPUs (65.2 M vs 63.1 M env-steps/s at C2), but the small-batch 2-rank test hung once with the
+        # collectives inside the graph, so the per-stage graphs with host-launched all-reduces stay the default
+        if os.environ.get("XB_DIST_EPOCH_GRAPH", "0") != "1":
+            return False
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._epoch_distributed_eager()
+            self._epoch_graph = g
+            return True
+        except Exception as e:        # pragma: no cover - depends on the NCCL / driver combination
+            import warnings
+            warnings.warn("distributed epoch graph capture failed (%s); using per-stage graphs" % (e,))
+            self._epoch_graph = None
+            torch.cuda.synchronize(self.device)
+            return False
+
+    def _epoch_distributed_eager(self):
+        B, lr, mem = self.batch_size, self.learner, self.memory
+        for start in range(0, self.buffer_size - B + 1, B):
+            idx = self._perm[start:start + B]
+            mb = lr.stage_gather(mem, idx)
+            if mem.use_advnorm:
+                torch.distributed.all_reduce(mb["stats"], group=lr.process_group)
+            lr.stage_forward_backward(mem, idx, mb)
+            torch.distributed.all_reduce(lr._flat.flat_grad, group=lr.process_group)
+            lr.stage_optimizer()
 
     def _snapshot(self):
         """Everything a warm-up rollout/update mutates, so that capturing leaves training state untouched."""
