@@ -30,6 +30,7 @@ extern "C" {
 
 #define XB_ENV_CARTPOLE 0 /* CartPole-v1: state (x, x_dot, theta, theta_dot), action int64 {0,1}, limit 500 */
 #define XB_ENV_PENDULUM 1 /* Pendulum-v1: state (theta, theta_dot), action float32 torque, limit 200 */
+#define XB_ENV_MOUNTAINCAR 2 /* MountainCar-v0: state (position, velocity), action int64 {0,1,2}, limit 200 */
 
 #define XB_E_BADARG (-1)
 #define XB_E_UNSUPPORTED (-2)
@@ -245,7 +246,7 @@ int xb_bias_act_fwd(float* y, const float* bias, float slope, int64_t B, int H, 
 /* ------------------------------------------------------------------------------------------------------------
  * One vector step of the device-resident rollout in ONE launch: xb_sample_* + xb_env_step + xb_store fused per env
  * (PPOCLIP_Agent._action ppoclip_agent.py:50-57; DummyVecEnv_Gym.step_wait gym_vec_env.py:200-212;
- * DummyOnPolicyBuffer.store memory_tools.py:196-204).  CartPole-v1: act_param = logits [N][2], act_out int64 [N];
+ * DummyOnPolicyBuffer.store memory_tools.py:196-204).  CartPole-v1 / MountainCar-v0: act_param = logits [N][2] / [N][3], act_out int64 [N];
  * Pendulum-v1: act_param = mu [N][1], logstd [1], act_out f32 [N].  x_in = the observations the action was computed
  * from (stored as the transition's obs); all other arguments as in xb_env_step / xb_store.  Physics and store are
  * bit-identical to the three separate calls; the sampled action may differ from xb_sample_* in the last ulp of the

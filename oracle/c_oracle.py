@@ -58,7 +58,8 @@ class VecEnvC:
     """N independent copies of one classic-control env, stepped by the C oracle (AoS fp64 state)."""
 
     SPEC = {"CartPole-v1": dict(sdim=4, odim=4, max_steps=500, act=np.int64),
-            "Pendulum-v1": dict(sdim=2, odim=3, max_steps=200, act=np.float32)}
+            "Pendulum-v1": dict(sdim=2, odim=3, max_steps=200, act=np.float32),
+            "MountainCar-v0": dict(sdim=2, odim=2, max_steps=200, act=np.int64)}
 
     def __init__(self, env_id, n, seed=1, flavour="cr", n_warm_resets=2, seeds=None):
         sp = self.SPEC[env_id]
@@ -80,6 +81,9 @@ class VecEnvC:
         if self.env_id == "CartPole-v1":
             L.oc_cartpole_reset(_p(self.state), _p(self.rng), _p(self.elapsed), _p(self.ep_score), _p(self.obs),
                                 C.c_int(n_draws), C.c_long(self.n))
+        elif self.env_id == "MountainCar-v0":
+            L.oc_mountaincar_reset(_p(self.state), _p(self.rng), _p(self.elapsed), _p(self.ep_score), _p(self.obs),
+                                   C.c_int(n_draws), C.c_long(self.n))
         else:
             L.oc_pendulum_reset(_p(self.state), _p(self.rng), _p(self.elapsed), _p(self.ep_score), _p(self.obs),
                                 C.c_int(n_draws), C.c_long(self.n), C.c_int(self.flavour))
@@ -94,7 +98,8 @@ class VecEnvC:
         reset_obs = np.zeros((n, self.odim), np.float32)
         ep_step = np.empty(n, np.int32)
         ep_score = np.empty(n, np.float64)
-        fn = lib().oc_cartpole_step if self.env_id == "CartPole-v1" else lib().oc_pendulum_step
+        fn = {"CartPole-v1": lib().oc_cartpole_step, "Pendulum-v1": lib().oc_pendulum_step,
+              "MountainCar-v0": lib().oc_mountaincar_step}[self.env_id]
         fn(_p(self.state), _p(self.rng), _p(self.elapsed), _p(self.ep_score), _p(a), _p(self.obs), _p(rew), _p(term),
            _p(trunc), _p(reset_obs), _p(ep_step), _p(ep_score), C.c_int(self.max_steps), C.c_long(n), C.c_int(self.flavour))
         return dict(obs=self.obs.copy(), rew=rew, term=term.astype(bool), trunc=trunc.astype(bool),

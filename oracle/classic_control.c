@@ -5,7 +5,7 @@
  * --impl reference legs may load this.  The product (xuanpolicy_b200/) never links or calls it.
  *
  * What it restates (citations relative to /root/reference unless noted):
- *   - gym 0.26.2 CartPoleEnv.step/reset, PendulumEnv.step/reset/_get_obs/angle_normalize,
+ *   - gym 0.26.2 CartPoleEnv.step/reset, PendulumEnv.step/reset/_get_obs/angle_normalize, MountainCarEnv.step/reset,
  *     TimeLimit.step/reset (third party, pinned setup.py:51, NOT vendored -> published algorithm,
  *     SURVEY.md App. A), driven the way xuance drives it:
  *       Gym_Env.step/reset bookkeeping   xuance/environment/gym/gym_env.py:36-49
@@ -107,6 +107,54 @@ void oc_cartpole_step(double* state, uint64_t* rng, int32_t* elapsed, double* ep
             cartpole_draw(st, rng + 4 * e);
             elapsed[e] = 0; ep_score[e] = 0.0;
             for (int k = 0; k < 4; ++k) reset_obs[4 * e + k] = (float)st[k];
+        }
+    }
+}
+
+
+/* ---------------------------------------------------------------- MountainCar-v0 ------------------------ */
+/* gym 0.26.2 MountainCarEnv (gym/envs/classic_control/mountain_car.py), restated from the published algorithm:
+ *   velocity += (action - 1) * force + math.cos(3 * position) * (-gravity); clip; position += velocity; clip;
+ *   left-wall inelastic stop; terminated = position >= 0.5 and velocity >= 0; reward -1; reset position U(-0.6, -0.4). */
+static void mountaincar_draw(double* st, uint64_t* rng) {
+    st[0] = pcg64_uniform(rng, -0.6, -0.4 - (-0.6));
+    st[1] = 0.0;
+}
+
+void oc_mountaincar_reset(double* state /*[n][2]*/, uint64_t* rng, int32_t* elapsed, double* ep_score, float* obs /*[n][2]*/,
+                          int n_draws, long n) {
+    for (long e = 0; e < n; ++e) {
+        for (int d = 0; d < n_draws; ++d) mountaincar_draw(state + 2 * e, rng + 4 * e);
+        elapsed[e] = 0; ep_score[e] = 0.0;
+        obs[2 * e] = (float)state[2 * e]; obs[2 * e + 1] = (float)state[2 * e + 1];
+    }
+}
+
+void oc_mountaincar_step(double* state, uint64_t* rng, int32_t* elapsed, double* ep_score,
+                         const int64_t* actions, float* obs, float* rew, uint8_t* term, uint8_t* trunc,
+                         float* reset_obs, int32_t* ep_step_out, double* ep_score_out,
+                         int max_steps, long n, int flavour) {
+    const double force = 0.001, gravity = 0.0025, max_speed = 0.07, min_pos = -1.2, max_pos = 0.6, goal_pos = 0.5;
+    for (long e = 0; e < n; ++e) {
+        double* st = state + 2 * e;
+        double position = st[0], velocity = st[1];
+        velocity = velocity + ((double)(actions[e] - 1) * force + cos_f(3.0 * position, flavour) * (-gravity));
+        velocity = velocity < -max_speed ? -max_speed : (velocity > max_speed ? max_speed : velocity);
+        position = position + velocity;
+        position = position < min_pos ? min_pos : (position > max_pos ? max_pos : position);
+        if (position == min_pos && velocity < 0.0) velocity = 0.0;
+        st[0] = position; st[1] = velocity;
+        int terminated = position >= goal_pos && velocity >= 0.0;
+        elapsed[e] += 1;
+        int truncated = elapsed[e] >= max_steps;
+        ep_score[e] += -1.0;
+        obs[2 * e] = (float)st[0]; obs[2 * e + 1] = (float)st[1];
+        rew[e] = -1.0f; term[e] = (uint8_t)terminated; trunc[e] = (uint8_t)truncated;
+        ep_step_out[e] = elapsed[e]; ep_score_out[e] = ep_score[e];
+        if (terminated || truncated) {
+            mountaincar_draw(st, rng + 4 * e);
+            elapsed[e] = 0; ep_score[e] = 0.0;
+            reset_obs[2 * e] = (float)st[0]; reset_obs[2 * e + 1] = (float)st[1];
         }
     }
 }

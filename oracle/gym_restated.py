@@ -1,4 +1,4 @@
-"""CPU restatement of gym 0.26.2 classic-control physics (CartPole-v1, Pendulum-v1).
+"""CPU restatement of gym 0.26.2 classic-control physics (CartPole-v1, Pendulum-v1, MountainCar-v0).
 
 ORACLE / TEST INFRASTRUCTURE — never imported by the product (xuanpolicy_b200/).
 
@@ -215,6 +215,53 @@ class PendulumRestated:
         return None
 
 
+class MountainCarRestated:
+    """gym 0.26.2 MountainCarEnv (gym/envs/classic_control/mountain_car.py), goal_velocity = 0."""
+    min_position = -1.2
+    max_position = 0.6
+    max_speed = 0.07
+    goal_position = 0.5
+    goal_velocity = 0
+    force = 0.001
+    gravity = 0.0025
+    metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 30}
+    reward_range = (-float("inf"), float("inf"))
+
+    def __init__(self, trig="libm", with_spaces=True):
+        self.m = _Math(trig)
+        self.np_random = None
+        self.state = None
+        if with_spaces:
+            low = np.array([self.min_position, -self.max_speed], dtype=np.float32)
+            high = np.array([self.max_position, self.max_speed], dtype=np.float32)
+            self.observation_space = _Spaces.box(low, high)
+            self.action_space = _Spaces.discrete(3)
+
+    def reset(self, seed=None):
+        if seed is not None or self.np_random is None:
+            self.np_random = new_rng(seed)
+        self.state = (float(self.np_random.uniform(low=-0.6, high=-0.4)), 0.0)
+        return np.array(self.state, dtype=np.float32), {}
+
+    def step(self, action):
+        position, velocity = self.state
+        velocity = velocity + ((int(action) - 1) * self.force + self.m.cos(3 * position) * (-self.gravity))
+        velocity = min(max(velocity, -self.max_speed), self.max_speed)
+        position = position + velocity
+        position = min(max(position, self.min_position), self.max_position)
+        if position == self.min_position and velocity < 0:
+            velocity = 0.0
+        terminated = bool(position >= self.goal_position and velocity >= self.goal_velocity)
+        self.state = (position, velocity)
+        return np.array(self.state, dtype=np.float32), -1.0, terminated, False, {}
+
+    def close(self):
+        pass
+
+    def render(self):
+        return None
+
+
 class TimeLimitRestated:
     """gym 0.26.2 wrappers.TimeLimit (outermost wrapper returned by gym.make)."""
 
@@ -255,7 +302,8 @@ class TimeLimitRestated:
         return self.env.render()
 
 
-SPECS = {"CartPole-v1": (CartPoleRestated, 500), "Pendulum-v1": (PendulumRestated, 200)}
+SPECS = {"CartPole-v1": (CartPoleRestated, 500), "Pendulum-v1": (PendulumRestated, 200),
+         "MountainCar-v0": (MountainCarRestated, 200)}
 DEFAULT_TRIG = "libm"
 
 

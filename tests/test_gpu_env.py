@@ -1,4 +1,4 @@
-"""GPU parity: batched CartPole/Pendulum kernels vs the oracle (bit-exact, Tier 1) through the drop-in API."""
+"""GPU parity: batched CartPole/Pendulum/MountainCar kernels vs the oracle (bit-exact, Tier 1) through the drop-in API."""
 import numpy as np
 import pytest
 import torch
@@ -53,7 +53,8 @@ def test_env_tape_bit_exact_vs_golden(name):
     assert np.array_equal(envs.buf_obs, g["obs"][-1])
 
 
-@pytest.mark.parametrize("env_id,n,steps", [("CartPole-v1", 4099, 520), ("Pendulum-v1", 4096, 410)])
+@pytest.mark.parametrize("env_id,n,steps", [("CartPole-v1", 4099, 520), ("Pendulum-v1", 4096, 410),
+                                            ("MountainCar-v0", 2051, 430)])
 def test_env_large_batch_bit_exact_vs_c_oracle(env_id, n, steps):
     """Ragged batch size, per-env divergent random actions, many resets: still bit-exact with the C oracle."""
     from oracle import c_oracle
@@ -67,6 +68,9 @@ def test_env_large_batch_bit_exact_vs_c_oracle(env_id, n, steps):
         if env_id == "CartPole-v1":
             heur = (obs[:, 2] + 0.5 * obs[:, 3] > 0).astype(np.int64)
             a = np.where(rng.random(n) < 0.8, heur, rng.integers(0, 2, n))
+        elif env_id == "MountainCar-v0":        # energy-pumping heuristic so that some cars reach the goal (terminated)
+            heur = np.where(obs[:, 1] > 0, 2, 0).astype(np.int64)
+            a = np.where(rng.random(n) < 0.9, heur, rng.integers(0, 3, n))
         else:
             a = (1.5 * rng.standard_normal((n, 1))).astype(np.float32)
         obs, rew, term, trunc, infos = envs.step(a)

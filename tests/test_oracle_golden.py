@@ -169,3 +169,34 @@ def test_learner_port_matches_reference_golden(name):
             assert ok, (k, err)
             ok, err = rel_close(p.detach().numpy(), g["p1_%s/%s" % (tag, k)], 1e-5)
             assert ok, (k, err)
+
+
+def test_mountaincar_c_and_python_restatements_agree_and_kat():
+    """MountainCar-v0: the C oracle and the Python restatement of gym 0.26.2's MountainCarEnv agree bit for
+    bit (libm flavour) over random action tapes with resets, and on a hand-computable known answer: from
+    (position, velocity) = (-0.5, 0) with action 2: velocity = 0.001 + cos(-1.5) * -0.0025, position = -0.5 + velocity."""
+    import math
+    from oracle import c_oracle, gym_restated
+    n = 6
+    ref = c_oracle.VecEnvC("MountainCar-v0", n, seed=3, flavour="libm", n_warm_resets=1)
+    envs = [gym_restated.make("MountainCar-v0", trig="libm") for _ in range(n)]
+    obs = np.stack([e.reset(seed=3)[0] for e in envs])
+    assert np.array_equal(obs, ref.obs)
+    rng = np.random.default_rng(0)
+    episodes = 0
+    for t in range(450):
+        a = rng.integers(0, 3, n)
+        o = ref.step(a)
+        for i, e in enumerate(envs):
+            ob, r, term, trunc, _ = e.step(a[i])
+            assert np.array_equal(ob, o["obs"][i]) and r == o["rew"][i] and term == o["term"][i] and trunc == o["trunc"][i]
+            if term or trunc:
+                assert np.array_equal(e.reset()[0], o["reset_obs"][i])
+                episodes += 1
+    assert episodes >= n
+    e = gym_restated.MountainCarRestated("cr", with_spaces=False)
+    e.state = (-0.5, 0.0)
+    ob, r, term, trunc, _ = e.step(2)
+    v = 0.001 + math.cos(-1.5) * -0.0025
+    assert e.state == (-0.5 + v, v) and r == -1.0 and not term
+    assert ob.dtype == np.float32 and ob[0] == np.float32(-0.5 + v)

@@ -18,7 +18,7 @@ _COMMON = dict(
 def ppo_config(env_id, **overrides):
     cfg = dict(_COMMON)
     cfg["env_id"] = env_id
-    cfg["policy"] = "Categorical_AC" if env_id == "CartPole-v1" else "Gaussian_AC"
+    cfg["policy"] = "Gaussian_AC" if env_id == "Pendulum-v1" else "Categorical_AC"
     cfg.update(overrides)
     return Namespace(**cfg)
 

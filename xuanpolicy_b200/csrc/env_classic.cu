@@ -1,4 +1,4 @@
-// env_classic.cu — batched CartPole-v1 / Pendulum-v1 step + auto-reset, one thread per environment.
+// env_classic.cu — batched CartPole-v1 / Pendulum-v1 / MountainCar-v0 step + auto-reset, one thread per environment.
 //
 // Replaces the per-env Python loop of DummyVecEnv_Gym.step_wait (xuance/environment/gym/gym_vec_env.py:201-212)
 // over Gym_Env.step (xuance/environment/gym/gym_env.py:43-49) over gym 0.26.2's CartPoleEnv / PendulumEnv /
@@ -49,6 +49,7 @@ struct CartPole {
     static constexpr int S = 4;
     typedef int64_t action_t;
     static constexpr bool kDiscrete = true;
+    static constexpr int kActions = 2;
     __device__ static void draw(double (&st)[4], Pcg64& g) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) st[k] = pcg64_uniform(g, -0.05, 0.05 - (-0.05));
@@ -85,6 +86,7 @@ struct Pendulum {
     static constexpr int S = 2;
     typedef float action_t;
     static constexpr bool kDiscrete = false;
+    static constexpr int kActions = 1;
     __device__ static void draw(double (&st)[2], Pcg64& g) {
         st[0] = pcg64_uniform(g, -kPi, kPi - (-kPi));
         st[1] = pcg64_uniform(g, -1.0, 1.0 - (-1.0));
@@ -120,6 +122,41 @@ struct Pendulum {
         st[0] = newth; st[1] = newthdot;
         terminated = false;
         return -costs;
+    }
+};
+
+
+// gym 0.26.2 MountainCarEnv (gym/envs/classic_control/mountain_car.py; xuance config
+// xuance/configs/ppo/classic_control/MountainCar-v0.yaml), TimeLimit 200.  Operation order of step():
+//   velocity += (action - 1) * force + math.cos(3 * position) * (-gravity)
+//   velocity = clip(velocity, -max_speed, max_speed); position += velocity; position = clip(position, min, max)
+//   if position == min_position and velocity < 0: velocity = 0
+//   terminated = position >= goal_position and velocity >= goal_velocity; reward = -1.0
+// reset(): state = [uniform(-0.6, -0.4), 0].
+struct MountainCar {
+    static constexpr int S = 2;
+    typedef int64_t action_t;
+    static constexpr bool kDiscrete = true;
+    static constexpr int kActions = 3;
+    __device__ static void draw(double (&st)[2], Pcg64& g) {
+        st[0] = pcg64_uniform(g, -0.6, -0.4 - (-0.6));
+        st[1] = 0.0;
+    }
+    __device__ static float4 observe(const double (&st)[2]) { return make_float4((float)st[0], (float)st[1], 0.0f, 0.0f); }
+    __device__ static double step(double (&st)[2], action_t action, bool& terminated) {
+        const double force = 0.001, gravity = 0.0025, max_speed = 0.07, min_pos = -1.2, max_pos = 0.6, goal_pos = 0.5;
+        double position = st[0], velocity = st[1];
+        double s, c;
+        sincos_cr(__dmul_rn(3.0, position), &s, &c);
+        const double push = __dmul_rn((double)(action - 1), force);
+        velocity = __dadd_rn(velocity, __dadd_rn(push, __dmul_rn(c, -gravity)));
+        velocity = velocity < -max_speed ? -max_speed : (velocity > max_speed ? max_speed : velocity);
+        position = __dadd_rn(position, velocity);
+        position = position < min_pos ? min_pos : (position > max_pos ? max_pos : position);
+        if (position == min_pos && velocity < 0.0) velocity = 0.0;
+        st[0] = position; st[1] = velocity;
+        terminated = position >= goal_pos && velocity >= 0.0;
+        return -1.0;
     }
 };
 
@@ -257,7 +294,7 @@ __global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs
     typename Env::action_t act;
     float logp;
     if (Env::kDiscrete) {
-        act = (typename Env::action_t)sample_categorical_one(a.act_param + e * 2, 2, e, ph, &logp);
+        act = (typename Env::action_t)sample_categorical_one(a.act_param + e * Env::kActions, Env::kActions, e, ph, &logp);
         ((int64_t*)a.act_out)[e] = (int64_t)act;
         a.act_row[e] = (float)act;
     } else {
@@ -346,6 +383,8 @@ extern "C" int xb_env_reset(int env_kind, double* state, uint64_t* rng, int32_t*
         env_reset_kernel<CartPole><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (float4*)obs, n_draws, N);
     else if (env_kind == XB_ENV_PENDULUM)
         env_reset_kernel<Pendulum><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (float4*)obs, n_draws, N);
+    else if (env_kind == XB_ENV_MOUNTAINCAR)
+        env_reset_kernel<MountainCar><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (float4*)obs, n_draws, N);
     else
         return XB_E_UNSUPPORTED;
     XB_LAUNCH_CHECK();
@@ -371,6 +410,11 @@ extern "C" int xb_env_step(int env_kind, double* state, uint64_t* rng, int32_t* 
                                                          (float4*)obs, (float4*)next_obs, rew, term, trunc,
                                                          (float4*)reset_obs, ep_step_out, ep_score_out, ep_stats,
                                                          max_episode_steps, N);
+    else if (env_kind == XB_ENV_MOUNTAINCAR)
+        env_step_kernel<MountainCar><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (const int64_t*)actions,
+                                                            (float4*)obs, (float4*)next_obs, rew, term, trunc,
+                                                            (float4*)reset_obs, ep_step_out, ep_score_out, ep_stats,
+                                                            max_episode_steps, N);
     else
         return XB_E_UNSUPPORTED;
     XB_LAUNCH_CHECK();
@@ -405,6 +449,7 @@ extern "C" int xb_rollout_step(int env_kind, const float* act_param, const float
     int block = env_block(N), grid = ceil_div_i64(N, block);
     if (env_kind == XB_ENV_CARTPOLE) rollout_step_kernel<CartPole><<<grid, block, 0, s>>>(a);
     else if (env_kind == XB_ENV_PENDULUM) rollout_step_kernel<Pendulum><<<grid, block, 0, s>>>(a);
+    else if (env_kind == XB_ENV_MOUNTAINCAR) rollout_step_kernel<MountainCar><<<grid, block, 0, s>>>(a);
     else return XB_E_UNSUPPORTED;
     XB_LAUNCH_CHECK();
     return 0;

@@ -7,7 +7,7 @@ import torch
 
 from . import _lib
 
-ENV_KINDS = {"CartPole-v1": 0, "Pendulum-v1": 1}
+ENV_KINDS = {"CartPole-v1": 0, "Pendulum-v1": 1, "MountainCar-v0": 2}
 GAE_VARIANTS = {"auto": 0, "ldg": 1, "tma": 2}
 
 
@@ -40,7 +40,7 @@ def env_step(kind, state, rng, elapsed, ep_score, actions, obs, next_obs, rew, t
              ep_score_out, max_steps, ep_stats=None):
     N = elapsed.numel()
     _lib.call("xb_env_step", kind, _p(state, F64), _p(rng, I64), _p(elapsed, I32), _p(ep_score, F64),
-              _p(actions, I64 if kind == 0 else F32), _p(obs, F32), _p(next_obs, F32), _p(rew, F32), _p(term, U8),
+              _p(actions, F32 if kind == 1 else I64), _p(obs, F32), _p(next_obs, F32), _p(rew, F32), _p(term, U8),
               _p(trunc, U8), _p(reset_obs, F32), _p(ep_step_out, I32), _p(ep_score_out, F64), _p(ep_stats, F64), max_steps,
               N, _stream())
 
@@ -53,7 +53,7 @@ def rollout_step(kind, act_param, logstd, val, seed, counter, offset, state, rng
     _lib.call("xb_rollout_step", kind, _p(act_param, F32), _p(logstd, F32), _p(val, F32), int(seed), _p(counter, I64),
               int(offset), _p(state, F64), _p(rng, I64), _p(elapsed, I32), _p(ep_score, F64), _p(obs, F32),
               _p(next_obs, F32), _p(rew, F32), _p(term, U8), _p(trunc, U8), _p(reset_obs, F32), _p(ep_step_out, I32),
-              _p(ep_score_out, F64), _p(ep_stats, F64), max_steps, _p(x_in, F32), _p(act_out, I64 if kind == 0 else F32),
+              _p(ep_score_out, F64), _p(ep_stats, F64), max_steps, _p(x_in, F32), _p(act_out, F32 if kind == 1 else I64),
               _p(logp_out, F32), _p(obs_row, F32), _p(act_row, F32), _p(rew_row, F32), _p(val_row, F32),
               _p(term_row, F32), _p(trunc_row, U8), _p(logp_row, F32), _p(rew_std, F32), float(rew_clip), N, _stream())
 

@@ -23,6 +23,7 @@ from .spaces import Box, Discrete
 SPECS = {
     "CartPole-v1": dict(kind=0, state_dim=4, obs_dim=4, max_steps=500),
     "Pendulum-v1": dict(kind=1, state_dim=2, obs_dim=3, max_steps=200),
+    "MountainCar-v0": dict(kind=2, state_dim=2, obs_dim=2, max_steps=200),
 }
 
 
@@ -43,7 +44,9 @@ def make_spaces(env_id):
     if env_id == "Pendulum-v1":
         high = np.array([1.0, 1.0, 8.0], np.float32)
         return Box(-high, high), Box(-2.0, 2.0, shape=(1,))
-    raise NotImplementedError("only CartPole-v1 and Pendulum-v1 have device kernels (got %r)" % (env_id,))
+    if env_id == "MountainCar-v0":
+        return Box(np.array([-1.2, -0.07], np.float32), np.array([0.6, 0.07], np.float32)), Discrete(3)
+    raise NotImplementedError("only CartPole-v1, Pendulum-v1 and MountainCar-v0 have device kernels (got %r)" % (env_id,))
 
 
 class EnvFn:
@@ -138,7 +141,7 @@ class DummyVecEnv_Gym:
             self._ep_step_out = torch.zeros(N, dtype=torch.int32, device=dev)
             self._ep_score_out = torch.zeros(N, dtype=torch.float64, device=dev)
             self.ep_stats = torch.zeros(3, dtype=torch.float64, device=dev)  # finished episodes, sum score, sum length
-            act_dtype = torch.int64 if self._kind == 0 else torch.float32
+            act_dtype = torch.float32 if self._kind == 1 else torch.int64
             self._act = torch.zeros(N, dtype=act_dtype, device=dev)
             ops.env_reset(self._kind, self._state, self._rng, self._elapsed, self._ep_score, self._obs, 1)
         self.buf_obs = np.zeros((N,) + self.obs_shape, dtype=np.float32)
