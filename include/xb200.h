@@ -168,6 +168,39 @@ int xb_ppo_loss_gaussian(const int64_t* idx, int64_t B, int64_t T, int64_t N, co
                          int64_t stride, float* dmu, double* dlogstd_acc, float* dv, double* scalars, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * (4b) Losses that carry the OLD ACTION DISTRIBUTION (PPO-KL, PPG).  Forward + backward
+ * w.r.t. the network outputs of
+ *     L = surr_coef*a_loss + kl_w*mean KL(new||old) - ent_coef*mean H + vf_coef*mean (v-R)^2
+ *         + aux_coef*mean (aux_v - stopgrad(v))^2
+ * with  ratio = exp(log_prob(act) - old_dist.log_prob(act)),  a_loss = -mean(ratio*adv) (clip_range <= 0) or the
+ * clipped surrogate (clip_range > 0), kl_w = kl_coef * (*kl_coef_dev if given).  Replaces
+ *   PPOKL_Learner.update          xuance/torch/learners/policy_gradient/ppokl_learner.py:26-37
+ *   PPG_Learner.update_policy     xuance/torch/learners/policy_gradient/ppg_learner.py:27-39   (surr 1, ent)
+ *   PPG_Learner.update_critic     ppg_learner.py:58-60                                        (vf 1 only)
+ *   PPG_Learner.update_auxiliary  ppg_learner.py:75-80                                        (kl_beta, vf 1, aux 1)
+ *   CategoricalDistribution / DiagGaussianDistribution.kl_divergence   xuance/torch/utils/distributions.py:63-66,97-100
+ *   merge_distributions           xuance/torch/utils/operations.py:75-92 (the caller passes the merged parameters)
+ * All per-sample inputs are dense [B] minibatch arrays.  aux_v / daux are nullable (required when aux_coef != 0).
+ * Gaussian: KL is averaged over B*A elements like the reference's `.mean()` of the element-wise Normal KL;
+ *   old_std is [B][A] (old_std_per_sample = 1) or one shared row [A] (0).
+ * scalars fp64 [8] (zeroed by the call) = sums of {surrogate, (v-R)^2, entropy, v_pred, clipped-ratio count,
+ *   KL (summed over A), (aux_v-v)^2, 0}.
+ * xb_kl_coef_adapt: the adaptive coefficient of ppokl_learner.py:39-43 on the device, from scalars[5]/count
+ *   (count = B for Categorical, B*A for Gaussian): > 1.5*target -> x2, < 0.5*target -> /2, clip to [0.1, 20].
+ * ---------------------------------------------------------------------------------------------------------- */
+int xb_dist_loss_categorical(int64_t B, const float* logits, const float* old_logits, int A, const float* v_pred,
+                             const float* aux_v, const float* act, const float* ret, const float* adv,
+                             float clip_range, float surr_coef, float kl_coef, const float* kl_coef_dev, float vf_coef,
+                             float ent_coef, float aux_coef, float inv_batch, float* dlogits, float* dv, float* daux,
+                             double* scalars, xb_stream_t stream);
+int xb_dist_loss_gaussian(int64_t B, const float* mu, const float* logstd, const float* old_mu, const float* old_std,
+                          int old_std_per_sample, int A, const float* v_pred, const float* aux_v, const float* act,
+                          const float* ret, const float* adv, float clip_range, float surr_coef, float kl_coef,
+                          const float* kl_coef_dev, float vf_coef, float ent_coef, float aux_coef, float inv_batch,
+                          float* dmu, double* dlogstd_acc, float* dv, float* daux, double* scalars, xb_stream_t stream);
+int xb_kl_coef_adapt(const double* scalars, float* kl_coef_dev, float target_kl, int64_t count, xb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Action sampling fused with log-prob (after the actor GEMM).  Replaces dists.stochastic_sample()+log_prob in
  * PPOCLIP_Agent._action (ppoclip_agent.py:50-57; distributions.py:57-58,89-90).  Philox4x32-10, counter-based:
  * stream position = (*counter_dev + offset, env index), so a captured graph replays with fresh numbers once

@@ -8,6 +8,8 @@ own classes behind stub gym/gymnasium/mpi4py modules (oracle/ref_loader.py):
                    driven with the exact call protocol of PPOCLIP_Agent.train (ppoclip_agent.py:68-100)
     loss_*.npz     PPOCLIP_Learner.update                          xuance/torch/learners/policy_gradient/ppoclip_learner.py:24-65
                    with the reference's own policy modules (policies/categorical.py, policies/gaussian.py)
+    loss_ppokl_*   PPOKL_Learner.update                            .../ppokl_learner.py:21-61 (two updates: adaptive kl_coef)
+    loss_ppg_*     PPG_Learner.update_policy/_critic/_auxiliary    .../ppg_learner.py:23-88
     vecenv_*.npz   DummyVecEnv_Gym.reset/step                      xuance/environment/gym/gym_vec_env.py:155-212
                    over the RESTATED physics (gym itself is absent: "parity unpinned" for the physics)
     physics_*.npz  action tapes through the C oracle, flavour "cr" (self-derived KATs, Tier-1 target)
@@ -177,6 +179,114 @@ def gen_loss_a2c_pg(name, seed, algo, discrete, hidden, B):
     print("wrote", name)
 
 
+def _old_dist_inputs(policy, obs, rng, ppg):
+    """Actions + the OLD distribution (a perturbed copy of the policy) as the reference's per-sample object array."""
+    from xuance.torch.utils.operations import split_distributions
+    with torch.no_grad():
+        out = policy(obs)
+        act = out[1].stochastic_sample().numpy().astype(np.float32)
+        saved = [p.detach().clone() for p in policy.parameters()]
+        for p in policy.parameters():
+            p.add_(0.03 * torch.randn_like(p))
+        old = policy(obs)[1]
+        old_dists = split_distributions(old)
+        if hasattr(old, "logits"):
+            old_params = dict(old_logits=old.logits.numpy().copy())
+        else:
+            old_params = dict(old_mu=old.mu.numpy().copy(), old_std=old.std.numpy().copy())
+        for p, q in zip(policy.parameters(), saved):
+            p.copy_(q)
+    return act, old_dists, old_params
+
+
+def gen_loss_ppokl(name, seed, discrete, hidden, B, target_kl):
+    """Reference PPOKL_Learner.update (ppokl_learner.py:21-61), two consecutive updates (the second one runs with the
+    adapted kl_coef): info, grads and parameters after each, kl_coef after each."""
+    from xuance.torch.learners import PPOKL_Learner
+    rng = np.random.default_rng(seed)
+    obs = rng.standard_normal((B, 4 if discrete else 3)).astype(np.float32)
+    policy = _ref_policy(discrete, hidden, seed)
+    with torch.no_grad():
+        for p in policy.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    sd0 = {k: v.detach().clone().numpy() for k, v in policy.state_dict().items()}
+    act, old_dists, old_params = _old_dist_inputs(policy, obs, rng, False)
+    adv = rng.standard_normal(B).astype(np.float32)
+    with torch.no_grad():
+        ret = (policy(obs)[2].numpy() + rng.standard_normal(B)).astype(np.float32)
+    out = dict(obs=obs, act=act, ret=ret, adv=adv, **old_params,
+               meta=np.array(json.dumps(dict(algo="ppokl", discrete=discrete, hidden=hidden, B=B, vf_coef=0.25,
+                                             ent_coef=0.01, target_kl=target_kl))))
+    for k, v in sd0.items():
+        out["p0/" + k] = v
+    opt = torch.optim.Adam(policy.parameters(), 4e-4, eps=1e-5)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=1000)
+    learner = PPOKL_Learner(policy, opt, sched, "cpu", "/tmp/xb200_goldens_models", vf_coef=0.25, ent_coef=0.01,
+                            target_kl=target_kl)
+    for it in (1, 2):
+        info = learner.update(obs, act, ret, adv, old_dists)
+        for k, v in info.items():
+            out["info%d/%s" % (it, k)] = np.asarray(float(v))
+        out["kl_coef%d" % it] = np.asarray(float(learner.kl_coef))
+        for k, p in policy.named_parameters():
+            out["grad%d/%s" % (it, k)] = p.grad.detach().numpy().copy()
+            out["p%d/%s" % (it, k)] = p.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, "kl_coef", float(out["kl_coef1"]), float(out["kl_coef2"]))
+
+
+def gen_loss_ppg(name, seed, discrete, hidden, B):
+    """Reference PPG_Learner.update_policy / update_critic / update_auxiliary (ppg_learner.py:23-88), run in that order
+    on one policy (Categorical_PPG_Policy / Gaussian_PPG_Policy): info, grads (None -> absent) and parameters per phase."""
+    from xuance.torch.learners import PPG_Learner
+    from xuance.torch.representations import Basic_MLP
+    from xuance.torch.policies import Categorical_PPG_Policy, Gaussian_PPG_Policy
+    S = _spaces()
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    act_fn, init = torch.nn.LeakyReLU, torch.nn.init.orthogonal_
+    obs_dim = 4 if discrete else 3
+    rep = Basic_MLP((obs_dim,), [hidden], None, init, act_fn, "cpu")
+    if discrete:
+        policy = Categorical_PPG_Policy(S.Discrete(2), rep, [hidden], [hidden], None, init, act_fn, "cpu")
+    else:
+        policy = Gaussian_PPG_Policy(S.Box(-2.0, 2.0, shape=(1,)), rep, [hidden], [hidden], None, init, act_fn, "cpu")
+    with torch.no_grad():
+        for p in policy.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    sd0 = {k: v.detach().clone().numpy() for k, v in policy.state_dict().items()}
+    obs = rng.standard_normal((B, obs_dim)).astype(np.float32)
+    act, old_dists, old_params = _old_dist_inputs(policy, obs, rng, True)
+    adv = rng.standard_normal(B).astype(np.float32)
+    with torch.no_grad():
+        ret = (policy(obs)[2].numpy() + rng.standard_normal(B)).astype(np.float32)
+    out = dict(obs=obs, act=act, ret=ret, adv=adv, **old_params,
+               meta=np.array(json.dumps(dict(algo="ppg", discrete=discrete, hidden=hidden, B=B, ent_coef=0.01,
+                                             clip_range=0.2, kl_beta=1.5))))
+    for k, v in sd0.items():
+        out["p0/" + k] = v
+    opt = torch.optim.Adam(policy.parameters(), 4e-4, eps=1e-5)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=1000)
+    learner = PPG_Learner(policy, opt, sched, "cpu", "/tmp/xb200_goldens_models", ent_coef=0.01, clip_range=0.2, kl_beta=1.5)
+    for phase in ("policy", "critic", "auxiliary"):
+        info = getattr(learner, "update_" + phase)(obs, act, ret, adv, old_dists)
+        for k, v in info.items():
+            out["info_%s/%s" % (phase, k)] = np.asarray(float(v))
+        for k, p in policy.named_parameters():
+            if p.grad is not None:
+                out["grad_%s/%s" % (phase, k)] = p.grad.detach().numpy().copy()
+            out["p_%s/%s" % (phase, k)] = p.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name)
+
+
+def gen_f3_dist():
+    gen_loss_ppokl("loss_ppokl_cat_h64", 205, True, 64, 512, target_kl=0.01)
+    gen_loss_ppokl("loss_ppokl_gauss_h64", 206, False, 64, 768, target_kl=1e-4)
+    gen_loss_ppg("loss_ppg_cat_h32", 207, True, 32, 384)
+    gen_loss_ppg("loss_ppg_gauss_h64", 208, False, 64, 640)
+
+
 def gen_vecenv(name, env_id, n, steps, seed=1):
     """Reference DummyVecEnv_Gym protocol over the restated physics (libm flavour, as gym would run on a host)."""
     from xuance.environment import DummyVecEnv_Gym, Gym_Env
@@ -242,6 +352,7 @@ def main():
     gen_loss("loss_gauss_h128", 202, False, 128, 1024, hp)
     gen_loss_a2c_pg("loss_a2c_gauss_h64", 203, "a2c", False, 64, 640)
     gen_loss_a2c_pg("loss_pg_cat_h32", 204, "pg", True, 32, 384)
+    gen_f3_dist()
     gen_vecenv("vecenv_cartpole", "CartPole-v1", 6, 700)
     gen_vecenv("vecenv_pendulum", "Pendulum-v1", 4, 450)
     gen_physics("physics_cartpole_cr", "CartPole-v1", 12, 1100)
@@ -254,5 +365,9 @@ if __name__ == "__main__":
         ref_loader.load(trig="libm")
         gen_loss_a2c_pg("loss_a2c_gauss_h64", 203, "a2c", False, 64, 640)
         gen_loss_a2c_pg("loss_pg_cat_h32", 204, "pg", True, 32, 384)
+    elif len(sys.argv) > 1 and sys.argv[1] == "f3_dist":
+        os.makedirs(OUT, exist_ok=True)
+        ref_loader.load(trig="libm")
+        gen_f3_dist()
     else:
         main()

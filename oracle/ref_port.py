@@ -187,6 +187,85 @@ def ppo_clip_update(policy, optimizer, scheduler, batch, vf_coef=0.25, ent_coef=
             "predict_value": v_pred.mean().item(), "clip_ratio": n_clipped / ratio.shape[0]}
 
 
+def _kl(new, old):
+    """kl_divergence(new, old) of two reference-shaped wrappers (distributions.py:63-66,97-100) from their parameters."""
+    pn, po = new.get_param(), old
+    if isinstance(pn, (tuple, list)):
+        mu, std = pn
+        omu, ostd = po
+        var_ratio = (std / ostd) ** 2
+        t1 = ((mu - omu) / ostd) ** 2
+        return 0.5 * (var_ratio + t1 - 1 - var_ratio.log())            # element-wise [B, A]
+    lp = pn - pn.logsumexp(-1, keepdim=True)
+    lq = po - po.logsumexp(-1, keepdim=True)
+    return (lp.exp() * (lp - lq)).sum(-1)
+
+
+def _old_logp(old, act):
+    if isinstance(old, (tuple, list)):
+        omu, ostd = old
+        return (-((act - omu) ** 2) / (2 * ostd ** 2) - ostd.log() - 0.5 * np.log(2 * np.pi)).sum(-1)
+    lq = old - old.logsumexp(-1, keepdim=True)
+    return lq.gather(-1, act.long().unsqueeze(-1)).squeeze(-1)
+
+
+def ppokl_update(policy, optimizer, scheduler, batch, old, state, vf_coef=0.25, ent_coef=0.005, target_kl=0.25):
+    """One PPOKL_Learner.update step (ppokl_learner.py:21-61).  `old` = old logits, or (old_mu, old_std);
+    `state` = {"kl_coef": float} carried between updates."""
+    obs, act, ret, adv = batch
+    act, ret, adv = (torch.as_tensor(a) for a in (act, ret, adv))
+    old = tuple(torch.as_tensor(o) for o in old) if isinstance(old, (tuple, list)) else torch.as_tensor(old)
+    _, dist, v_pred = policy(obs)
+    logp = dist.log_prob(act)
+    kl = _kl(dist, old).mean()
+    ratio = (logp - _old_logp(old, act)).exp().float()
+    a_loss = -(ratio * adv).mean() + state["kl_coef"] * kl
+    c_loss = torch.nn.functional.mse_loss(v_pred, ret)
+    e_loss = dist.entropy().mean()
+    loss = a_loss - ent_coef * e_loss + vf_coef * c_loss
+    if kl > target_kl * 1.5:
+        state["kl_coef"] = state["kl_coef"] * 2.0
+    elif kl < target_kl * 0.5:
+        state["kl_coef"] = state["kl_coef"] / 2.0
+    state["kl_coef"] = float(np.clip(state["kl_coef"], 0.1, 20))
+    optimizer.zero_grad()
+    loss.backward()
+    optimizer.step()
+    if scheduler is not None:
+        scheduler.step()
+    return {"actor-loss": a_loss.item(), "critic-loss": c_loss.item(), "entropy": e_loss.item(),
+            "learning_rate": optimizer.state_dict()["param_groups"][0]["lr"], "kl": kl.item(),
+            "predict_value": v_pred.mean().item()}
+
+
+def ppg_update(phase, policy, optimizer, scheduler, batch, old, ent_coef=0.005, clip_range=0.25, kl_beta=1.0):
+    """PPG_Learner.update_policy / update_critic / update_auxiliary (ppg_learner.py:23-88)."""
+    obs, act, ret, adv = batch
+    act, ret, adv = (torch.as_tensor(a) for a in (act, ret, adv))
+    old = tuple(torch.as_tensor(o) for o in old) if isinstance(old, (tuple, list)) else torch.as_tensor(old)
+    _, dist, v, aux_v = policy(obs)
+    mse = torch.nn.functional.mse_loss
+    if phase == "policy":
+        ratio = (dist.log_prob(act) - _old_logp(old, act)).exp().float()
+        a_loss = -torch.minimum(ratio.clamp(1.0 - clip_range, 1.0 + clip_range) * adv, adv * ratio).mean()
+        e_loss = dist.entropy().mean()
+        loss = a_loss - ent_coef * e_loss
+    elif phase == "critic":
+        loss = mse(v, ret)
+    else:
+        loss = mse(v.detach(), aux_v) + kl_beta * _kl(dist, old).mean() + mse(v, ret)
+    optimizer.zero_grad()
+    loss.backward()
+    optimizer.step()
+    if phase == "policy":
+        if scheduler is not None:
+            scheduler.step()
+        cr = ((ratio < 1 - clip_range).sum() + (ratio > 1 + clip_range).sum()) / ratio.shape[0]
+        return {"actor-loss": a_loss.item(), "entropy": e_loss.item(),
+                "learning_rate": optimizer.state_dict()["param_groups"][0]["lr"], "clip_ratio": cr}
+    return {"critic-loss": loss.item()} if phase == "critic" else {"kl-loss": loss.item()}
+
+
 # ------------------------------------------------------------------------------------------------ normaliser
 class RunningMeanStdPort:
     def __init__(self, shape, epsilon=1e-4):

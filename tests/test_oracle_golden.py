@@ -171,6 +171,68 @@ def test_learner_port_matches_reference_golden(name):
             assert ok, (k, err)
 
 
+def _old_from_golden(g):
+    return g["old_logits"] if "old_logits" in g else (g["old_mu"], g["old_std"])
+
+
+@pytest.mark.parametrize("name", ["loss_ppokl_cat_h64", "loss_ppokl_gauss_h64"])
+def test_ppokl_port_matches_reference_golden(name):
+    """Row f3: the PPO-KL restatement (two updates, adaptive kl_coef) vs the reference's own PPOKL_Learner."""
+    g = load_golden(name)
+    m = g["meta"]
+    pol = _policy_from_golden(g)
+    opt = torch.optim.Adam(pol.parameters(), 4e-4, eps=1e-5)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=1000)
+    state = {"kl_coef": 1.0}
+    for it in (1, 2):
+        info = ref_port.ppokl_update(pol, opt, sched, (g["obs"], g["act"], g["ret"], g["adv"]), _old_from_golden(g), state,
+                                     vf_coef=m["vf_coef"], ent_coef=m["ent_coef"], target_kl=m["target_kl"])
+        assert state["kl_coef"] == float(g["kl_coef%d" % it])
+        for k, v in info.items():
+            ref = float(g["info%d/%s" % (it, k)])
+            assert abs(float(v) - ref) <= 1e-5 * max(1.0, abs(ref)), (it, k)
+        for k, p in pol.named_parameters():
+            ok, err = rel_close(p.grad.numpy(), g["grad%d/%s" % (it, k)], 1e-4)
+            assert ok, (it, k, err)
+            ok, err = rel_close(p.detach().numpy(), g["p%d/%s" % (it, k)], 1e-5)
+            assert ok, (it, k, err)
+
+
+def _ppg_policy_from_golden(g, device="cpu"):
+    m = g["meta"]
+    rep = policies.MLPRepresentation((4 if m["discrete"] else 3,), [m["hidden"]], device=device)
+    if m["discrete"]:
+        pol = policies.CategoricalPPGActorCritic(spaces.Discrete(2), rep, [m["hidden"]], [m["hidden"]], device=device)
+    else:
+        pol = policies.GaussianPPGActorCritic(spaces.Box(-2.0, 2.0, (1,)), rep, [m["hidden"]], [m["hidden"]], device=device)
+    pol.load_state_dict({k[3:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("p0/")}, strict=True)
+    return pol
+
+
+@pytest.mark.parametrize("name", ["loss_ppg_cat_h32", "loss_ppg_gauss_h64"])
+def test_ppg_port_matches_reference_golden(name):
+    """Row f3: the three PPG phase updates restated vs the reference's own PPG_Learner (run in sequence)."""
+    g = load_golden(name)
+    m = g["meta"]
+    pol = _ppg_policy_from_golden(g)
+    opt = torch.optim.Adam(pol.parameters(), 4e-4, eps=1e-5)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=1000)
+    for phase in ("policy", "critic", "auxiliary"):
+        info = ref_port.ppg_update(phase, pol, opt, sched, (g["obs"], g["act"], g["ret"], g["adv"]), _old_from_golden(g),
+                                   ent_coef=m["ent_coef"], clip_range=m["clip_range"], kl_beta=m["kl_beta"])
+        for k, v in info.items():
+            ref = float(g["info_%s/%s" % (phase, k)])
+            assert abs(float(v) - ref) <= 1e-5 * max(1.0, abs(ref)), (phase, k)
+        for k, p in pol.named_parameters():
+            key = "grad_%s/%s" % (phase, k)
+            assert (p.grad is None) == (key not in g), (phase, k)
+            if p.grad is not None:
+                ok, err = rel_close(p.grad.numpy(), g[key], 1e-4)
+                assert ok, (phase, k, err)
+            ok, err = rel_close(p.detach().numpy(), g["p_%s/%s" % (phase, k)], 1e-5)
+            assert ok, (phase, k, err)
+
+
 def test_mountaincar_c_and_python_restatements_agree_and_kat():
     """MountainCar-v0: the C oracle and the Python restatement of gym 0.26.2's MountainCarEnv agree bit for
     bit (libm flavour) over random action tapes with resets, and on a hand-computable known answer: from

@@ -30,6 +30,11 @@ SIGNATURES = {
                                 _f32, _f32, _f32, _i64, _vp, _vp, _vp, _vp],
     "xb_ppo_loss_gaussian": [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32,
                              _f32, _f32, _f32, _i64, _vp, _vp, _vp, _vp, _vp],
+    "xb_dist_loss_categorical": [_i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _vp, _f32, _f32, _f32, _f32,
+                                 _vp, _vp, _vp, _vp, _vp],
+    "xb_dist_loss_gaussian": [_i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _vp, _f32, _f32,
+                              _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp],
+    "xb_kl_coef_adapt": [_vp, _vp, _f32, _i64, _vp],
     "xb_pack_records": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "xb_gather_records": [_vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp],
     "xb_sample_categorical": [_vp, _i32, _u64, _vp, _u64, _vp, _vp, _i64, _vp],

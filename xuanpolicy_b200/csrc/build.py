@@ -23,6 +23,7 @@ SOURCES = {
     "buffer.cu": [],
     "gae.cu": [],
     "ppo_loss.cu": [],
+    "dist_loss.cu": [],
     "sample.cu": [],
     "optim.cu": [],
     "host_utils.cu": [],

@@ -305,3 +305,198 @@ class PG_Learner(PPOCLIP_Learner):
     def update(self, obs_batch, act_batch, ret_batch):
         info = super().update(obs_batch, act_batch, ret_batch, ret_batch, ret_batch, None)
         return {k: info[k] for k in ("actor-loss", "entropy", "learning_rate")}
+
+
+# ---------------------------------------------------------------------------------------------------- PPO-KL / PPG
+def old_dist_params(old_dists, device):
+    """Parameters of the OLD action distribution of a minibatch as CUDA tensors: ('categorical', logits [B, A], None)
+    or ('gaussian', mu [B, A], std [B, A] | [A]).
+
+    Accepts what the reference hands its learners — a numpy object array of per-sample distribution wrappers
+    (`split_distributions` / `merge_distributions`, xuance/torch/utils/operations.py:53-92) — as well as one batched
+    wrapper (anything with `get_param()`), which is what the device buffer returns from `sample`."""
+    f32 = lambda t: torch.as_tensor(t, device=device).detach().to(torch.float32).contiguous()
+    if hasattr(old_dists, "get_param"):
+        p = old_dists.get_param()
+        if isinstance(p, (tuple, list)):
+            return "gaussian", f32(p[0]), f32(p[1])
+        return "categorical", f32(p), None
+    flat = np.asarray(old_dists, dtype=object).reshape(-1)
+    first = flat[0].get_param()
+    if isinstance(first, (tuple, list)):
+        mu = torch.stack([torch.as_tensor(d.get_param()[0]).reshape(-1) for d in flat])
+        std = torch.stack([torch.as_tensor(d.get_param()[1]).reshape(-1) for d in flat])
+        return "gaussian", f32(mu), f32(std)
+    logits = torch.cat([torch.as_tensor(d.get_param()).reshape(1, -1) for d in flat], dim=0)
+    return "categorical", f32(logits), None
+
+
+class _DistLossLearner(PPOCLIP_Learner):
+    """Shared machinery of the learners whose loss needs the old action distribution (csrc/dist_loss.cu)."""
+
+    def _dist_loss_backward(self, a_dist, v_pred, aux_v, act, ret, adv, old_dists, *, clip_range, surr_coef, kl_coef,
+                            vf_coef, ent_coef, aux_coef=0.0, kl_coef_dev=None):
+        """Runs the fused loss kernel on the network outputs and back-propagates through the torch MLP.  Only the
+        outputs that carry a non-zero coefficient are back-propagated, so untouched sub-networks keep `grad = None`
+        and the torch optimizer skips them exactly like the reference's `loss.backward()` does."""
+        dev = self.device
+        kind, p0, p1 = _dist_params(a_dist)
+        okind, o0, o1 = old_dist_params(old_dists, dev)
+        if okind != kind:
+            raise TypeError("KL divergence needs two distributions of the same type")   # distributions.py:64-65
+        B = ret.shape[0]
+        v = v_pred.detach().contiguous()
+        dv = torch.empty_like(v)
+        aux = aux_v.detach().contiguous() if aux_v is not None else None
+        daux = torch.empty_like(aux) if (aux is not None and aux_coef != 0.0) else None
+        kw = dict(clip_range=clip_range, surr_coef=surr_coef, kl_coef=kl_coef, vf_coef=vf_coef, ent_coef=ent_coef,
+                  inv_batch=1.0 / B, kl_coef_dev=kl_coef_dev, aux_v=aux, aux_coef=aux_coef, daux=daux)
+        actor_live = surr_coef != 0.0 or kl_coef != 0.0 or ent_coef != 0.0
+        outs, grads = [], []
+        if vf_coef != 0.0:
+            outs.append(v_pred)
+            grads.append(dv)
+        if daux is not None:
+            outs.append(aux_v)
+            grads.append(daux)
+        if kind == "categorical":
+            logits = p0.detach().contiguous()
+            dlogits = torch.empty_like(logits)
+            ops.dist_loss_categorical(logits, o0.reshape(B, -1), v, act.reshape(B), ret, adv, dlogits, dv, self._scalars, **kw)
+            if actor_live:
+                outs.append(p0)
+                grads.append(dlogits)
+            torch.autograd.backward(outs, grads)
+            return B
+        mu = p0.detach().contiguous()
+        A = mu.shape[1]
+        std = p1
+        param = getattr(getattr(self.policy, "actor", None), "logstd", None)   # gaussian.py:25
+        direct = param is not None and param.requires_grad and param.numel() == A
+        logstd = param.detach() if direct else std.detach().log().contiguous()
+        dmu = torch.empty_like(mu)
+        dls = torch.empty(A, dtype=torch.float64, device=dev)
+        old_std = o1.reshape(B, A) if o1.numel() == B * A else o1.reshape(A)
+        ops.dist_loss_gaussian(mu, logstd, o0.reshape(B, A), old_std, v, act.reshape(B, A), ret, adv, dmu, dls, dv,
+                               self._scalars, **kw)
+        if actor_live:
+            outs.append(p0)
+            grads.append(dmu)
+            if not direct and std.requires_grad:
+                outs.append(std)
+                grads.append((dls / std.detach().double()).to(std.dtype))
+        torch.autograd.backward(outs, grads)
+        if actor_live and direct:
+            g = dls.to(param.dtype)
+            param.grad = g if param.grad is None else param.grad.add_(g)
+        return B * A
+
+    def _prep(self, *arrays):
+        return [torch.as_tensor(x, device=self.device).to(torch.float32).contiguous() for x in arrays]
+
+    def _step(self, scheduler=True):
+        self.optimizer.step()
+        if scheduler and self.scheduler is not None:
+            self.scheduler.step()
+        return self.optimizer.state_dict()["param_groups"][0]["lr"]
+
+
+class PPOKL_Learner(_DistLossLearner):
+    """PPOKL_Learner drop-in (xuance/torch/learners/policy_gradient/ppokl_learner.py:5-61): same constructor and
+    `update(obs_batch, act_batch, ret_batch, adv_batch, old_dists)`.  Loss + backward w.r.t. the network outputs
+    in one kernel; the adaptive KL coefficient (:39-43) lives on the device (`kl_coef` reads it back).  No gradient
+    clipping, like the reference."""
+
+    def __init__(self, policy, optimizer, scheduler=None, device=None, model_dir="./", vf_coef=0.25, ent_coef=0.005,
+                 target_kl=0.25):
+        super().__init__(policy, optimizer, scheduler, device, model_dir, vf_coef=vf_coef, ent_coef=ent_coef,
+                         clip_range=0.0, clip_grad_norm=None, use_grad_clip=False)
+        self.target_kl = target_kl
+        self._kl_coef_dev = torch.ones(1, dtype=torch.float32, device=self.device)
+
+    @property
+    def kl_coef(self):
+        return float(self._kl_coef_dev.item())
+
+    @kl_coef.setter
+    def kl_coef(self, value):
+        self._kl_coef_dev.fill_(float(value))
+
+    def update(self, obs_batch, act_batch, ret_batch, adv_batch, old_dists):
+        self.iterations += 1
+        with torch.cuda.device(self.device):
+            act, ret, adv = self._prep(act_batch, ret_batch, adv_batch)
+            B = ret.shape[0]
+            _, a_dist, v_pred = self.policy(torch.as_tensor(obs_batch, device=self.device))
+            kl_used = self._kl_coef_dev.clone()
+            self.optimizer.zero_grad()
+            kl_count = self._dist_loss_backward(a_dist, v_pred, None, act, ret, adv, old_dists, clip_range=0.0,
+                                                surr_coef=1.0, kl_coef=1.0, vf_coef=self.vf_coef, ent_coef=self.ent_coef,
+                                                kl_coef_dev=self._kl_coef_dev)
+            ops.kl_coef_adapt(self._scalars, self._kl_coef_dev, self.target_kl, kl_count)   # takes effect next update
+            lr = self._step()
+            s = self._scalars.cpu().numpy()
+            kl = float(s[5]) / kl_count
+            a_loss = -float(s[0]) / B + float(kl_used.item()) * kl
+        return {"actor-loss": a_loss, "critic-loss": float(s[1]) / B, "entropy": float(s[2]) / B, "learning_rate": lr,
+                "kl": kl, "predict_value": float(s[3]) / B}
+
+
+class PPG_Learner(_DistLossLearner):
+    """PPG_Learner drop-in (xuance/torch/learners/policy_gradient/ppg_learner.py:5-91): same constructor and the
+    three phase updates `update_policy / update_critic / update_auxiliary(obs, act, ret, adv, old_dists)` over a
+    policy returning `(outputs, a_dist, v, aux_v)`.  Each phase is one launch of the generic kernel of
+    csrc/dist_loss.cu with that phase's coefficients."""
+
+    def __init__(self, policy, optimizer, scheduler=None, device=None, model_dir="./", ent_coef=0.005, clip_range=0.25,
+                 kl_beta=1.0):
+        super().__init__(policy, optimizer, scheduler, device, model_dir, vf_coef=0.0, ent_coef=ent_coef,
+                         clip_range=clip_range, clip_grad_norm=None, use_grad_clip=False)
+        self.kl_beta = kl_beta
+        self.policy_iterations = 0
+        self.value_iterations = 0
+
+    def _forward(self, obs_batch):
+        return self.policy(torch.as_tensor(obs_batch, device=self.device))
+
+    def update_policy(self, obs_batch, act_batch, ret_batch, adv_batch, old_dists):
+        with torch.cuda.device(self.device):
+            act, ret, adv = self._prep(act_batch, ret_batch, adv_batch)
+            B = ret.shape[0]
+            _, a_dist, v, _ = self._forward(obs_batch)
+            self.optimizer.zero_grad()
+            self._dist_loss_backward(a_dist, v, None, act, ret, adv, old_dists, clip_range=self.clip_range, surr_coef=1.0,
+                                     kl_coef=0.0, vf_coef=0.0, ent_coef=self.ent_coef)
+            lr = self._step()
+            s = self._scalars.cpu().numpy() / B
+        self.policy_iterations += 1
+        return {"actor-loss": float(-s[0]), "entropy": float(s[2]), "learning_rate": lr,
+                "clip_ratio": torch.tensor(s[4], dtype=torch.float32)}
+
+    def update_critic(self, obs_batch, act_batch, ret_batch, adv_batch, old_dists):
+        with torch.cuda.device(self.device):
+            act, ret, adv = self._prep(act_batch, ret_batch, adv_batch)
+            B = ret.shape[0]
+            _, a_dist, v, _ = self._forward(obs_batch)
+            self.optimizer.zero_grad()
+            self._dist_loss_backward(a_dist, v, None, act, ret, adv, old_dists, clip_range=0.0, surr_coef=0.0, kl_coef=0.0,
+                                     vf_coef=1.0, ent_coef=0.0)
+            self._step(scheduler=False)                       # the reference steps no scheduler here (:63)
+            s = self._scalars.cpu().numpy() / B
+        self.value_iterations += 1
+        return {"critic-loss": float(s[1])}
+
+    def update_auxiliary(self, obs_batch, act_batch, ret_batch, adv_batch, old_dists):
+        with torch.cuda.device(self.device):
+            act, ret, adv = self._prep(act_batch, ret_batch, adv_batch)
+            B = ret.shape[0]
+            _, a_dist, v, aux_v = self._forward(obs_batch)
+            self.optimizer.zero_grad()
+            kl_count = self._dist_loss_backward(a_dist, v, aux_v, act, ret, adv, old_dists, clip_range=0.0, surr_coef=0.0,
+                                                kl_coef=self.kl_beta, vf_coef=1.0, ent_coef=0.0, aux_coef=1.0)
+            self._step(scheduler=False)                       # (:84)
+            s = self._scalars.cpu().numpy()
+        return {"kl-loss": float(s[6]) / B + self.kl_beta * float(s[5]) / kl_count + float(s[1]) / B}
+
+    def update(self):
+        pass

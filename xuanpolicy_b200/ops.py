@@ -127,6 +127,32 @@ def ppo_loss_gaussian(mu, logstd, v_pred, act, ret, adv, old_logp, dmu, dlogstd_
               _p(scalars, F64), _stream())
 
 
+def dist_loss_categorical(logits, old_logits, v_pred, act, ret, adv, dlogits, dv, scalars, clip_range, surr_coef, kl_coef,
+                          vf_coef, ent_coef, inv_batch, kl_coef_dev=None, aux_v=None, aux_coef=0.0, daux=None):
+    """PPO-KL / PPG losses on Categorical outputs with the old logits (see xb_dist_loss_categorical)."""
+    B, A = logits.shape
+    _lib.call("xb_dist_loss_categorical", B, _p(logits, F32), _p(old_logits, F32), A, _p(v_pred, F32), _p(aux_v, F32),
+              _p(act, F32), _p(ret, F32), _p(adv, F32), float(clip_range), float(surr_coef), float(kl_coef),
+              _p(kl_coef_dev, F32), float(vf_coef), float(ent_coef), float(aux_coef), float(inv_batch), _p(dlogits, F32),
+              _p(dv, F32), _p(daux, F32), _p(scalars, F64), _stream())
+
+
+def dist_loss_gaussian(mu, logstd, old_mu, old_std, v_pred, act, ret, adv, dmu, dlogstd_acc, dv, scalars, clip_range,
+                       surr_coef, kl_coef, vf_coef, ent_coef, inv_batch, kl_coef_dev=None, aux_v=None, aux_coef=0.0,
+                       daux=None):
+    """PPO-KL / PPG losses on diagonal-Gaussian outputs; old_std is [B, A] or one shared row [A]."""
+    B, A = mu.shape
+    _lib.call("xb_dist_loss_gaussian", B, _p(mu, F32), _p(logstd, F32), _p(old_mu, F32), _p(old_std, F32),
+              1 if old_std.dim() == 2 else 0, A, _p(v_pred, F32), _p(aux_v, F32), _p(act, F32), _p(ret, F32), _p(adv, F32),
+              float(clip_range), float(surr_coef), float(kl_coef), _p(kl_coef_dev, F32), float(vf_coef), float(ent_coef),
+              float(aux_coef), float(inv_batch), _p(dmu, F32), _p(dlogstd_acc, F64), _p(dv, F32), _p(daux, F32),
+              _p(scalars, F64), _stream())
+
+
+def kl_coef_adapt(scalars, kl_coef_dev, target_kl, count):
+    _lib.call("xb_kl_coef_adapt", _p(scalars, F64), _p(kl_coef_dev, F32), float(target_kl), int(count), _stream())
+
+
 def pack_records(b_obs, b_act, b_logp, b_adv, b_ret, rec):
     _lib.call("xb_pack_records", _p(b_obs, F32), _p(b_act, F32), _p(b_logp, F32), _p(b_adv, F32), _p(b_ret, F32),
               _p(rec, F32), b_adv.numel(), _stream())

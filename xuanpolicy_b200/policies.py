@@ -7,10 +7,12 @@ the two unchanged and `PPOCLIP_Learner.update` can drive either:
     CategoricalActorCritic <-> Categorical_AC_Policy   xuance/torch/policies/categorical.py:16-85
     GaussianActorCritic    <-> Gaussian_AC_Policy      xuance/torch/policies/gaussian.py:8-77
     distributions          <-> xuance/torch/utils/distributions.py:39-101
+    Categorical/GaussianPPGActorCritic <-> PPGActorCritic   categorical.py:110-141 / gaussian.py:103-131
 
 `forward(obs)` returns `(outputs_dict, dist, value)` exactly like the reference.  When the drop-in classes are
 used behind the reference's own runner, the reference's modules are used instead and these are not needed.
 """
+import copy
 import math
 from typing import Sequence
 
@@ -339,6 +341,54 @@ class CategoricalActor(nn.Module):
     def forward(self, observation):
         outputs = self.representation(observation)
         return outputs, self.actor(outputs["state"])
+
+
+class CategoricalPPGActorCritic(nn.Module):
+    """PPGActorCritic for Discrete actions (xuance/torch/policies/categorical.py:110-141): three copies of the
+    representation (actor / critic / auxiliary critic) and `forward -> (policy_outputs, a_dist, v, aux_v)`."""
+
+    def __init__(self, action_space, representation, actor_hidden_size, critic_hidden_size, normalize=None,
+                 initialize=nn.init.orthogonal_, activation=nn.LeakyReLU, device=None):
+        super().__init__()
+        self.action_dim = action_space.n
+        self.actor_representation = representation
+        self.critic_representation = copy.deepcopy(representation)
+        self.aux_critic_representation = copy.deepcopy(representation)
+        self.representation_info_shape = representation.output_shapes
+        sd = representation.output_shapes["state"][0]
+        self.actor = _CategoricalActor(sd, self.action_dim, actor_hidden_size, activation, initialize, device)
+        self.critic = _Critic(sd, critic_hidden_size, activation, initialize, device)
+        self.aux_critic = _Critic(sd, critic_hidden_size, activation, initialize, device)
+
+    def forward(self, observation):
+        policy_outputs = self.actor_representation(observation)
+        critic_outputs = self.critic_representation(observation)
+        aux_outputs = self.aux_critic_representation(observation)
+        return (policy_outputs, self.actor(policy_outputs["state"]), self.critic(critic_outputs["state"]),
+                self.aux_critic(aux_outputs["state"]))
+
+
+class GaussianPPGActorCritic(nn.Module):
+    """PPGActorCritic for Box actions (xuance/torch/policies/gaussian.py:103-131): the auxiliary critic reads the
+    ACTOR's representation (:130), the critic has its own copy."""
+
+    def __init__(self, action_space, representation, actor_hidden_size, critic_hidden_size, normalize=None,
+                 initialize=nn.init.orthogonal_, activation=nn.LeakyReLU, device=None):
+        super().__init__()
+        self.action_dim = action_space.shape[0]
+        self.actor_representation = representation
+        self.critic_representation = copy.deepcopy(representation)
+        self.representation_info_shape = representation.output_shapes
+        sd = representation.output_shapes["state"][0]
+        self.actor = _GaussianActor(sd, self.action_dim, actor_hidden_size, activation, initialize, device)
+        self.critic = _Critic(sd, critic_hidden_size, activation, initialize, device, last_init=False)
+        self.aux_critic = _Critic(sd, critic_hidden_size, activation, initialize, device, last_init=False)
+
+    def forward(self, observation):
+        policy_outputs = self.actor_representation(observation)
+        critic_outputs = self.critic_representation(observation)
+        return (policy_outputs, self.actor(policy_outputs["state"]), self.critic(critic_outputs["state"]),
+                self.aux_critic(policy_outputs["state"]))
 
 
 def make_policy(observation_space, action_space, hidden=(128,), device=None, seed=None):
