@@ -256,7 +256,7 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
         agent._cur = cur
     add("gae_and_pack", lambda: mem.finish_rollout(agent._boot_last), (20 + 1 + (64 if mem._rec is not None else 0)) * N * T, 1)
     idx = agent._perm[:B]
-    agent._perm.copy_(torch.randperm(agent.buffer_size, device="cuda"))
+    agent._device_permutation()
     add("gather_records" if mem.packed else "gather_obs_advstats", lambda: lr.stage_gather(mem, idx),
         B * ((8 + 32 + 4 * od + 16) if mem.packed else (8 + 16 + 4 * od + 4)), launches_per_step["updates"])
     mb = lr.stage_gather(mem, idx)

@@ -284,6 +284,9 @@ int xb_bias_act_fwd(float* y, const float* bias, float slope, int64_t B, int H, 
  * from (stored as the transition's obs); all other arguments as in xb_env_step / xb_store.  Physics and store are
  * bit-identical to the three separate calls; the sampled action may differ from xb_sample_* in the last ulp of the
  * transcendental functions (this translation unit is built without FMA contraction).
+ * boot_src / boot_row (nullable pair, f32 [N]): V(terminal observation of the PREVIOUS step) copied into the previous
+ * rollout row's bootstrap values — the value the reference obtains with a full-batch forward per finished env
+ * (ppoclip_agent.py:98-100) — so the step needs no separate copy launch.
  * ---------------------------------------------------------------------------------------------------------- */
 int xb_rollout_step(int env_kind, const float* act_param, const float* logstd, const float* val, uint64_t seed,
                     const uint64_t* counter_dev, uint64_t offset, double* state, uint64_t* rng, int32_t* elapsed,
@@ -291,7 +294,8 @@ int xb_rollout_step(int env_kind, const float* act_param, const float* logstd, c
                     float* reset_obs, int32_t* ep_step_out, double* ep_score_out, double* ep_stats,
                     int max_episode_steps, const float* x_in, void* act_out, float* logp_out, float* obs_row,
                     float* act_row, float* rew_row, float* val_row, float* term_row, uint8_t* trunc_row, float* logp_row,
-                    const float* rew_scale, float rew_clip, int64_t N, xb_stream_t stream);
+                    const float* rew_scale, float rew_clip, const float* boot_src, float* boot_row, int64_t N,
+                    xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Dense layers of the policy/value MLP at large batch on the tcgen05 tensor cores with fp32-level accuracy
@@ -373,6 +377,17 @@ int xb_mlp_trunk_wgrad_workspace_floats(int obs_dim, int H);
 int xb_mlp_trunk_wgrad_parts(void);     /* number of partial sums per output in the workspace */
 int xb_mlp_trunk_wgrad(const float* dz1, const float* obs, int ld, int obs_dim, float* workspace, float* dW0, float* db0,
                        int64_t B, int H, xb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Device-side minibatch permutation: out[i] = P(i), a keyed pseudo-random bijection of [0, n) (swap-free Feistel
+ * network on ceil(log2 n) bits + cycle walking), evaluated independently per index: one launch, no sort, no scratch.
+ * Replaces np.random.shuffle(indexes) in PPOCLIP_Agent.train (ppoclip_agent.py:76-78).  The key is derived from
+ * (seed, *counter_dev + offset), so a captured graph draws a fresh permutation on every replay once xb_counter_add
+ * has advanced the device counter (counter_dev may be NULL).  The permutation itself is not a parity target (the
+ * reference uses numpy's global MT19937 stream); being a permutation, and varying with the key, are tested.
+ * ---------------------------------------------------------------------------------------------------------- */
+int xb_random_permutation(int64_t* out, int64_t n, uint64_t seed, const uint64_t* counter_dev, uint64_t offset,
+                          xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * HOST helper (host pointers, runs on the calling CPU thread; releases nothing on the device).

@@ -280,11 +280,68 @@ def gen_loss_ppg(name, seed, discrete, hidden, B):
     print("wrote", name)
 
 
+def gen_buffer_olddist(name, seed, n_envs, n_size, discrete):
+    """Reference DummyOnPolicyBuffer with the PPO-KL / PPG auxiliary {"old_dist": None} (object arrays of per-sample
+    distribution wrappers, memory_tools.py:28-30): store -> finish_path -> sample, then the whole-buffer reassignment
+    PPG_Agent.train performs (ppg_agent.py:90-93) and a second sample."""
+    from xuance.common import DummyOnPolicyBuffer
+    from xuance.torch.utils.distributions import CategoricalDistribution, DiagGaussianDistribution
+    from xuance.torch.utils.operations import split_distributions, merge_distributions
+    S = _spaces()
+    rng = np.random.default_rng(seed)
+    T, N, A = n_size, n_envs, (3 if discrete else 2)
+    obs_dim = 4 if discrete else 3
+    obs_space = S.Box(-np.ones(obs_dim, np.float32), np.ones(obs_dim, np.float32))
+    act_space = S.Discrete(A) if discrete else S.Box(-2.0, 2.0, shape=(A,))
+    buf = DummyOnPolicyBuffer(obs_space, act_space, {"old_dist": None}, N, T, True, True, 0.99, 0.95)
+
+    def batched(p0, std=None):
+        if discrete:
+            d = CategoricalDistribution(A)
+            d.set_param(torch.as_tensor(p0))
+        else:
+            d = DiagGaussianDistribution(A)
+            d.set_param(torch.as_tensor(p0), torch.as_tensor(std))
+        return d
+
+    def params(objs):
+        m = merge_distributions(objs)
+        return (m.logits.numpy().copy(),) if discrete else (m.mu.numpy().copy(), m.std.numpy().copy())
+
+    obs = rng.standard_normal((T, N, obs_dim)).astype(np.float32)
+    act = rng.integers(0, A, (T, N)).astype(np.int64) if discrete else rng.standard_normal((T, N, A)).astype(np.float32)
+    rew, val = rng.standard_normal((T, N)).astype(np.float32), rng.standard_normal((T, N)).astype(np.float32)
+    p0 = rng.standard_normal((T, N, A)).astype(np.float32)
+    std = np.exp(0.3 * rng.standard_normal((T, A))).astype(np.float32)       # one std row per step (policy of that step)
+    boot = rng.standard_normal(N).astype(np.float32)
+    for t in range(T):
+        buf.store(obs[t], act[t], rew[t], val[t], np.zeros(N, bool), {"old_dist": split_distributions(batched(p0[t], std[t]))})
+    for i in range(N):
+        buf.finish_path(boot[i], i)
+    idx = rng.permutation(N * T).astype(np.int64)[:(N * T) // 2]
+    b1 = buf.sample(idx)
+    out = dict(obs=obs, act=act, rew=rew, val=val, p0=p0, std=std, boot=boot, idx=idx, s1_adv=b1[4], s1_ret=b1[2])
+    for k, v in enumerate(params(b1[5]["old_dist"])):
+        out["s1_old%d" % k] = v
+    new_p0 = rng.standard_normal((N, T, A)).astype(np.float32)               # env-major, like memory.observations
+    new_std = np.exp(0.3 * rng.standard_normal(A)).astype(np.float32)
+    buf.auxiliary_infos["old_dist"] = split_distributions(batched(new_p0, new_std))
+    b2 = buf.sample(idx)
+    out.update(new_p0=new_p0, new_std=new_std)
+    for k, v in enumerate(params(b2[5]["old_dist"])):
+        out["s2_old%d" % k] = v
+    out["meta"] = np.array(json.dumps(dict(n_envs=N, n_size=T, discrete=discrete, A=A)))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name)
+
+
 def gen_f3_dist():
     gen_loss_ppokl("loss_ppokl_cat_h64", 205, True, 64, 512, target_kl=0.01)
     gen_loss_ppokl("loss_ppokl_gauss_h64", 206, False, 64, 768, target_kl=1e-4)
     gen_loss_ppg("loss_ppg_cat_h32", 207, True, 32, 384)
     gen_loss_ppg("loss_ppg_gauss_h64", 208, False, 64, 640)
+    gen_buffer_olddist("buffer_cat_olddist", 209, 5, 24, True)
+    gen_buffer_olddist("buffer_box_olddist", 210, 4, 20, False)
 
 
 def gen_vecenv(name, env_id, n, steps, seed=1):

@@ -125,3 +125,55 @@ def test_gather_indices_bit_exact_and_stats():
         a = adv[step, env].astype(np.float64)
         s = stats.cpu().numpy()
         assert abs(s[0] - a.sum()) < 1e-9 * B and abs(s[1] - (a * a).sum()) < 1e-9 * B
+
+
+@pytest.mark.parametrize("name", ["buffer_cat_olddist", "buffer_box_olddist"])
+@pytest.mark.parametrize("per_sample_objects", [False, True])
+def test_buffer_old_dist_auxiliary_matches_reference_golden(name, per_sample_objects):
+    """Row f3 (PPO-KL / PPG): the {"old_dist": None} auxiliary.  The reference stores numpy arrays of Python distribution
+    objects (memory_tools.py:28-30); the drop-in keeps their parameters on the device.  store -> sample, then the
+    whole-buffer reassignment of PPG_Agent.train (ppg_agent.py:90-93) -> sample: gathered parameters bit-exact."""
+    import xuanpolicy_b200 as xb
+    from xuanpolicy_b200 import policies, spaces
+    g = load_golden(name)
+    m = g["meta"]
+    T, N, A = m["n_size"], m["n_envs"], m["A"]
+    if m["discrete"]:
+        obs_space, act_space = spaces.Box(-1, 1, (4,)), spaces.Discrete(A)
+    else:
+        obs_space, act_space = spaces.Box(-1, 1, (3,)), spaces.Box(-2.0, 2.0, (A,))
+
+    def wrap(p0, std=None):
+        if m["discrete"]:
+            d = policies.CategoricalDistribution(A)
+            d.set_param(torch.as_tensor(p0))
+        else:
+            d = policies.DiagGaussianDistribution(A)
+            d.set_param(torch.as_tensor(p0), torch.as_tensor(std))
+        return d
+
+    def split(p0, std=None):          # the shape split_distributions (operations.py:53-72) produces
+        flat = p0.reshape(-1, A)
+        objs = [wrap(row[None] if m["discrete"] else row, std) for row in flat]
+        return np.array(objs, dtype=object).reshape(p0.shape[:-1])
+
+    make = split if per_sample_objects else wrap
+    buf = xb.DummyOnPolicyBuffer(obs_space, act_space, {"old_dist": None}, N, T, True, True, 0.99, 0.95)
+    for t in range(T):
+        buf.store(g["obs"][t], g["act"][t], g["rew"][t], g["val"][t], np.zeros(N, bool),
+                  {"old_dist": make(g["p0"][t], None if m["discrete"] else g["std"][t])})
+    for i in range(N):
+        buf.finish_path(g["boot"][i], i)
+    b1 = buf.sample(g["idx"])
+    ok, err = gae_close(b1[4], g["s1_adv"], 2e-5)
+    assert ok, err
+    old = b1[5]["old_dist"].get_param()
+    old = (old,) if m["discrete"] else old
+    for k, t in enumerate(old):
+        assert np.array_equal(t.cpu().numpy(), g["s1_old%d" % k])
+    buf.auxiliary_infos["old_dist"] = make(g["new_p0"], None if m["discrete"] else g["new_std"])
+    old = buf.sample(g["idx"])[5]["old_dist"].get_param()
+    old = (old,) if m["discrete"] else old
+    for k, t in enumerate(old):
+        assert np.array_equal(t.cpu().numpy(), g["s2_old%d" % k])
+    assert buf.auxiliary_infos["old_dist"].shape == (N, T)

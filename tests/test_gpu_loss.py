@@ -284,3 +284,50 @@ def test_mlp_epilogue_and_head_kernels_vs_torch(B, H, A):
     # second launch reuses the (self-resetting) workspace ticket
     ops.head_bwd_act(dout, y, w2, slope, dz, db1, dw2, db2, ws)
     assert (dw2 - ref_dw2).abs().max().item() <= 1e-4 * scale(ref_dw2)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 64, 1000, 4096, 65536, 524288, 1000003])
+def test_device_permutation_is_a_bijection(n):
+    """xb_random_permutation (np.random.shuffle stand-in, ppoclip_agent.py:76-78): exactly the values 0..n-1, each once;
+    a different key (seed or device counter) gives a different permutation; the same key reproduces it."""
+    from xuanpolicy_b200 import ops
+    ctr = torch.zeros(1, dtype=torch.int64, device="cuda")
+    out = torch.empty(n, dtype=torch.int64, device="cuda")
+    ops.random_permutation(out, 123, ctr, 0)
+    assert torch.equal(torch.sort(out).values, torch.arange(n, device="cuda"))
+    again = torch.empty_like(out)
+    ops.random_permutation(again, 123, ctr, 0)
+    assert torch.equal(out, again)
+    if n >= 64:
+        ops.counter_add(ctr, 1)
+        ops.random_permutation(again, 123, ctr, 0)
+        assert torch.equal(torch.sort(again).values, torch.arange(n, device="cuda")) and not torch.equal(out, again)
+        ops.random_permutation(again, 124, None, 0)
+        assert not torch.equal(out, again)
+        assert (out == torch.arange(n, device="cuda")).float().mean().item() < 0.05     # not the identity
+
+
+def test_device_permutation_statistics():
+    """Uniformity checks a shuffle must pass for minibatch SGD: over 400 keys, where element 0 lands and which element
+    lands first are uniform over 64 buckets (chi-square, 63 dof, p ~ 1e-4 bound 113), minibatch membership of neighbours
+    is independent, and the mean displacement matches n/3."""
+    from xuanpolicy_b200 import ops
+    n, K = 8192, 400
+    ctr = torch.zeros(1, dtype=torch.int64, device="cuda")
+    out = torch.empty(n, dtype=torch.int64, device="cuda")
+    first, pos0, same_mb, disp = [], [], [], []
+    for k in range(K):
+        ops.random_permutation(out, 99, ctr, k)
+        p = out.cpu().numpy()
+        first.append(p[0])
+        pos0.append(int(np.nonzero(p == 0)[0][0]))
+        mb = np.empty(n, np.int64)
+        mb[p] = np.arange(n) // (n // 8)          # minibatch each element falls in
+        same_mb.append(np.mean(mb[:-1] == mb[1:]))
+        disp.append(np.mean(np.abs(p - np.arange(n))))
+    for v in (first, pos0):
+        counts = np.bincount(np.asarray(v) // (n // 64), minlength=64)
+        chi2 = float(np.sum((counts - K / 64) ** 2 / (K / 64)))
+        assert chi2 < 113.0, chi2
+    assert abs(np.mean(same_mb) - 1 / 8) < 0.003, np.mean(same_mb)
+    assert abs(np.mean(disp) / n - 1 / 3) < 0.005, np.mean(disp) / n

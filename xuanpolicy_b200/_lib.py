@@ -18,7 +18,7 @@ SIGNATURES = {
     "xb_env_reset": [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp],
     "xb_env_step": [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp],
     "xb_rollout_step": [_i32, _vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                        _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _vp],
+                        _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _i64, _vp],
     "xb_sincos_f64": [_vp, _vp, _vp, _i64, _vp],
     "xb_store": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _vp],
     "xb_gae": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f64, _f64, _i32, _i32, _vp],
@@ -41,6 +41,7 @@ SIGNATURES = {
     "xb_sample_gaussian": [_vp, _vp, _i32, _u64, _vp, _u64, _vp, _vp, _i64, _vp],
     "xb_counter_add": [_vp, _u64, _vp],
     "xb_host_permutation": [_vp, _i64, _u64],
+    "xb_random_permutation": [_vp, _i64, _u64, _vp, _u64, _vp],
     "xb_moments4": [_vp, _vp, _vp, _i64, _vp],
     "xb_rms_normalize": [_vp, _i32, _vp, _vp, _vp, _f32, _vp, _i64, _i64, _vp],
     "xb_returns_track": [_vp, _vp, _vp, _vp, _f64, _vp, _vp, _i64, _vp],

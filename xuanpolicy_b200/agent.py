@@ -108,6 +108,8 @@ class PPOCLIP_Agent:
         self._boot_last = torch.zeros(N, dtype=torch.float32, device=dev)
         self._ctr = torch.zeros(1, dtype=torch.int64, device=dev)
         self._perm = torch.zeros(self.buffer_size, dtype=torch.int64, device=dev)
+        self._perm_ctr = torch.zeros(1, dtype=torch.int64, device=dev)      # one tick per drawn device permutation
+        self._perm_seed = self.seed * 2654435761 + 7919 * self._rank() + 1
         self._feeder = None
         if self.shuffle == "host":
             self._feeder = HostPermutationFeeder(self.buffer_size, self.n_epoch, self.seed + 7919 * self._rank(),
@@ -179,7 +181,7 @@ class PPOCLIP_Agent:
         x_cur, x_nxt = self._x[self._cur], self._x[self._cur ^ 1]
         x_in = self._normalize_obs(x_cur, update=True)            # obs_rms.update(obs); _process_observation (:63-64)
         dist, v = self._policy_forward(x_in)                      # V on [obs_t ; terminal obs of step t-1]
-        if t > 0:
+        if t > 0 and not self._fused_step:
             mem._boot[t - 1].copy_(v[N:])                         # bootstrap for envs truncated at step t-1 (:99)
         if self._fused_step:
             # sample + env step + store in one launch (csrc/env_classic.cu: rollout_step_kernel)
@@ -195,7 +197,8 @@ class PPOCLIP_Agent:
                              env._reset_obs, env._ep_step_out, env._ep_score_out, env.ep_stats, env.max_episode_length,
                              x_in[:N], self._act, self._logp, mem._obs[t], mem._act[t], mem._rew[t], mem._val[t],
                              mem._term[t], mem._trunc[t], mem._logp[t],
-                             rew_std=self._rew_std if self.use_rewnorm else None, rew_clip=self.rewnorm_range)
+                             rew_std=self._rew_std if self.use_rewnorm else None, rew_clip=self.rewnorm_range,
+                             boot_src=v[N:] if t > 0 else None, boot_row=mem._boot[t - 1] if t > 0 else None)
         else:
             self._sample(dist, t)
             ops.env_step(env._kind, env._state, env._rng, env._elapsed, env._ep_score, self._act.reshape(N),
@@ -241,8 +244,16 @@ class PPOCLIP_Agent:
             self._rms_cur = 0
 
     # ---------------------------------------------------------------------------------------------- update phase
+    def _device_permutation(self):
+        """np.random.shuffle(indexes) (ppoclip_agent.py:76-78) as one launch: a keyed bijection of [0, buffer_size)
+        (csrc/sample.cu: random_permutation_kernel); the device counter makes every graph replay draw a new one."""
+        ops.random_permutation(self._perm, self._perm_seed, self._perm_ctr, 0)
+        ops.counter_add(self._perm_ctr, 1)
+
     def _epoch_body(self):
         B = self.batch_size
+        if self.shuffle != "host":
+            self._device_permutation()
         for start in range(0, self.buffer_size - B + 1, B):
             idx = self._perm[start:start + B]
             mb = self.learner.stage_gather(self.memory, idx)
@@ -282,8 +293,8 @@ class PPOCLIP_Agent:
                 src = self._feeder.get(self._iteration, ep)
                 self._perm.copy_(src, non_blocking=True)           # H2D from pinned memory
                 self.h2d_bytes += src.numel() * 8
-            else:
-                self._perm.copy_(torch.randperm(self.buffer_size, device=self.device))
+            elif self.world_size > 1:                              # single rank: drawn inside the epoch graph
+                self._device_permutation()
             if self._epoch_graph is not None:
                 self._epoch_graph.replay()
             elif self.world_size > 1:
@@ -303,7 +314,7 @@ class PPOCLIP_Agent:
         snap = self._snapshot()
         with torch.cuda.stream(s):
             self._rollout()
-            self._perm.copy_(torch.randperm(self.buffer_size, device=self.device))
+            self._device_permutation()
             if self.world_size > 1:
                 self._epoch_distributed()
             else:
@@ -373,7 +384,7 @@ class PPOCLIP_Agent:
     def _snapshot(self):
         """Everything a warm-up rollout/update mutates, so that capturing leaves training state untouched."""
         env, fl = self.envs, self.learner._flat
-        tensors = [env._state, env._rng, env._elapsed, env._ep_score, env.ep_stats, self._ctr, self._x[0], self._x[1],
+        tensors = [env._state, env._rng, env._elapsed, env._ep_score, env.ep_stats, self._ctr, self._perm_ctr, self._x[0], self._x[1],
                    fl.flat_param, fl.exp_avg, fl.exp_avg_sq, fl.step, fl.lr, self._obs_rms[0], self._obs_rms[1],
                    self._ret_rms, self._returns, self._rew_std]
         return [(t, t.clone()) for t in tensors] + [("cur", self._cur)]

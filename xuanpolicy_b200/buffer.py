@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .policies import OldDistBatch, old_dist_params
 from .spaces import is_discrete
 
 
@@ -33,9 +34,15 @@ class DummyOnPolicyBuffer:
         obs_shape = tuple(observation_space.shape)
         if len(obs_shape) != 1 or not 1 <= obs_shape[0] <= 4:
             raise NotImplementedError("device buffer supports flat observations of 1..4 floats (classic control)")
-        if auxiliary_shape and set(auxiliary_shape.keys()) != {"old_logp"}:
-            raise NotImplementedError("only the PPO auxiliary {'old_logp': ()} (or none: A2C / PG) is supported")
-        self._has_logp = bool(auxiliary_shape)
+        if auxiliary_shape and set(auxiliary_shape.keys()) not in ({"old_logp"}, {"old_dist"}):
+            raise NotImplementedError("supported auxiliaries: {'old_logp': ()} (PPO-Clip), {'old_dist': None} "
+                                      "(PPO-KL / PPG), or none (A2C / PG)")
+        self._has_logp = bool(auxiliary_shape) and "old_logp" in auxiliary_shape
+        # {"old_dist": None}: the reference keeps an [n_envs, n_size] numpy array of Python distribution objects
+        # (memory_tools.py:28-30); here their parameters live in one device array [T, N, W] (W = A logits, or
+        # A means + A stds), allocated at the first store
+        self._has_dist = bool(auxiliary_shape) and "old_dist" in auxiliary_shape
+        self._dist, self._dist_kind = None, None
         self.obs_dim = obs_shape[0]
         self.discrete = is_discrete(action_space)
         self.act_dim = 1 if self.discrete else int(np.prod(action_space.shape))
@@ -73,7 +80,7 @@ class DummyOnPolicyBuffer:
         """Reference re-allocates zeroed arrays (memory_tools.py:185-194); here the same storage is zeroed."""
         self.ptr, self.size = 0, 0
         for t in (self._obs, self._act, self._rew, self._val, self._term, self._logp, self._adv, self._ret,
-                  self._trunc, self._boot):
+                  self._trunc, self._boot) + ((self._dist,) if self._dist is not None else ()):
             t.zero_()
         self._h_segend[...] = 0
         self._h_boot[...] = 0
@@ -112,6 +119,8 @@ class DummyOnPolicyBuffer:
             else:
                 act_t = act_t.to(torch.float32).reshape(N, self.act_dim).contiguous()
             logp = aux_info["old_logp"] if (aux_info and "old_logp" in aux_info) else torch.zeros(N)
+            if self._has_dist:
+                self._store_old_dist(aux_info["old_dist"], p)
             trunc = self._zero_u8 if truncations is None else self._dev(truncations, torch.uint8).reshape(N)
             self.store_device(obs_t, act_t, self._dev(rews, torch.float32).reshape(N),
                               self._dev(value, torch.float32).reshape(N), self._dev(terminals, torch.uint8).reshape(N),
@@ -125,6 +134,34 @@ class DummyOnPolicyBuffer:
         obs4 is [N, 4] float32)."""
         ops.store(obs4, act, rew, val, term_u8, trunc_u8, logp, self._obs[row], self._act[row], self._rew[row],
                   self._val[row], self._term[row], self._trunc[row], self._logp[row], rew_std, rew_clip)
+
+    # ---------------------------------------------------------------------------------------------- old_dist
+    def _dist_rows(self, dists, rows):
+        """[rows, W] device rows (logits, or means | stds) of `rows` old distributions."""
+        kind, p0, p1 = old_dist_params(dists, self.device)
+        p0 = p0.reshape(rows, -1)
+        w = p0 if kind == "categorical" else torch.cat([p0, p1.reshape(-1, p0.shape[1]).expand(rows, -1)], dim=1)
+        if self._dist is None:
+            self._dist_kind = kind
+            self._dist = torch.zeros((self.n_size, self.n_envs, w.shape[1]), dtype=torch.float32, device=self.device)
+        return w
+
+    def _store_old_dist(self, dists, row):
+        rows = self._dist_rows(dists, self.n_envs)      # allocates the device array at the first store
+        self._dist[row].copy_(rows)
+
+    def _old_dist_batch(self, w):
+        if self._dist_kind == "categorical":
+            return OldDistBatch("categorical", w)
+        A = w.shape[-1] // 2
+        return OldDistBatch("gaussian", w[..., :A].contiguous(), w[..., A:].contiguous())
+
+    def set_old_dist(self, dists):
+        """`memory.auxiliary_infos['old_dist'] = split_distributions(new_dist)` of PPG_Agent.train (ppg_agent.py:90-93):
+        replaces the stored old distributions of the WHOLE buffer; `dists` is env-major [n_envs, n_size] like
+        `memory.observations`."""
+        rows = self._dist_rows(dists, self.n_envs * self.n_size).reshape(self.n_envs, self.n_size, -1)
+        self._dist.copy_(rows.transpose(0, 1))
 
     # ---------------------------------------------------------------------------------------------- GAE
     def finish_path(self, val, i):
@@ -186,10 +223,14 @@ class DummyOnPolicyBuffer:
             if self.use_advnorm:
                 ops.normalize_adv(adv, self._mb_stats, B)
             act = act.reshape((B,) + self._act_shape)
+            aux = {"old_logp": logp if self.native else logp.cpu().numpy()} if self._has_logp else {}
+            if self._has_dist:       # stays on the device in both modes: the learner is its only consumer
+                w = torch.empty((B, self._dist.shape[2]), **f32)
+                ops.gather_rows(idx, self.n_size, self.n_envs, self._dist, w)
+                aux["old_dist"] = self._old_dist_batch(w)
         if self.native:
-            return obs, act, ret, val, adv, ({"old_logp": logp} if self._has_logp else {})
-        return (obs.cpu().numpy(), act.cpu().numpy(), ret.cpu().numpy(), val.cpu().numpy(), adv.cpu().numpy(),
-                ({"old_logp": logp.cpu().numpy()} if self._has_logp else {}))
+            return obs, act, ret, val, adv, aux
+        return obs.cpu().numpy(), act.cpu().numpy(), ret.cpu().numpy(), val.cpu().numpy(), adv.cpu().numpy(), aux
 
     # ---------------------------------------------------------------------------------------------- views
     def _env_major(self, t, trailing=None):
@@ -233,4 +274,23 @@ class DummyOnPolicyBuffer:
 
     @property
     def auxiliary_infos(self):
+        if self._has_dist:
+            return _AuxInfos(self)
         return {"old_logp": self._env_major(self._logp)} if self._has_logp else {}
+
+
+class _AuxInfos(dict):
+    """`memory.auxiliary_infos` for the "old_dist" auxiliary: reading gives the env-major [n_envs, n_size] batch,
+    assigning replaces the stored distributions (the one write PPG_Agent.train performs, ppg_agent.py:93)."""
+
+    def __init__(self, memory):
+        super().__init__()
+        self._memory = memory
+        if memory._dist is not None:
+            dict.__setitem__(self, "old_dist", memory._old_dist_batch(memory._dist.transpose(0, 1)))
+
+    def __setitem__(self, key, value):
+        if key != "old_dist":
+            raise KeyError(key)
+        self._memory.set_old_dist(value)
+        dict.__setitem__(self, key, self._memory._old_dist_batch(self._memory._dist.transpose(0, 1)))

@@ -281,6 +281,9 @@ struct RolloutStepArgs {
     float* logp_row;
     const float* rew_scale;   // nullable: rewards are divided by *rew_scale and clipped to +-rew_clip (use_rewnorm)
     float rew_clip;
+    // nullable pair: V(terminal obs of the previous step) [N] -> the previous rollout row's bootstrap values
+    const float* boot_src;
+    float* boot_row;
     int64_t N;
 };
 
@@ -308,6 +311,7 @@ __global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs
     a.logp_row[e] = logp;
     a.obs_row[e] = a.x_in[e];
     a.val_row[e] = a.val[e];
+    if (a.boot_row) a.boot_row[e] = a.boot_src[e];   // V(terminal obs) for envs truncated at step t-1 (ppoclip_agent.py:99)
     // ---- env step (identical arithmetic to env_step_kernel)
     double st[Env::S];
 #pragma unroll
@@ -434,17 +438,18 @@ extern "C" int xb_rollout_step(int env_kind, const float* act_param, const float
                                uint8_t* trunc, float* reset_obs, int32_t* ep_step_out, double* ep_score_out,
                                double* ep_stats, int max_episode_steps, const float* x_in, void* act_out, float* logp_out,
                                float* obs_row, float* act_row, float* rew_row, float* val_row, float* term_row,
-                               uint8_t* trunc_row, float* logp_row, const float* rew_scale, float rew_clip, int64_t N,
-                               xb_stream_t stream) {
+                               uint8_t* trunc_row, float* logp_row, const float* rew_scale, float rew_clip,
+                               const float* boot_src, float* boot_row, int64_t N, xb_stream_t stream) {
     if (N <= 0 || !act_param || !val || !state || !rng || !elapsed || !ep_score || !obs || !rew || !term || !trunc ||
         !reset_obs || !ep_step_out || !ep_score_out || !x_in || !act_out || !logp_out || !obs_row || !act_row ||
         !rew_row || !val_row || !term_row || !logp_row)
         return XB_E_BADARG;
     if (env_kind == XB_ENV_PENDULUM && !logstd) return XB_E_BADARG;
+    if ((boot_row != nullptr) != (boot_src != nullptr)) return XB_E_BADARG;
     RolloutStepArgs a{act_param, logstd, val, seed, counter_dev, offset, state, rng, elapsed, ep_score, (float4*)obs,
                       (float4*)next_obs, rew, term, trunc, (float4*)reset_obs, ep_step_out, ep_score_out, ep_stats,
                       max_episode_steps, (const float4*)x_in, act_out, logp_out, (float4*)obs_row, act_row, rew_row,
-                      val_row, term_row, trunc_row, logp_row, rew_scale, rew_clip, N};
+                      val_row, term_row, trunc_row, logp_row, rew_scale, rew_clip, boot_src, boot_row, N};
     cudaStream_t s = (cudaStream_t)stream;
     int block = env_block(N), grid = ceil_div_i64(N, block);
     if (env_kind == XB_ENV_CARTPOLE) rollout_step_kernel<CartPole><<<grid, block, 0, s>>>(a);

@@ -36,6 +36,47 @@ __global__ void __launch_bounds__(128)
 
 __global__ void counter_add_kernel(uint64_t* counter, uint64_t inc) { *counter += inc; }
 
+// ---------------------------------------------------------------------------------------------- device permutation
+// A keyed pseudo-random BIJECTION of [0, n) evaluated per index — no sort, no scratch, one 8-byte store per index
+// (np.random.shuffle(indexes) of ppoclip_agent.py:76-78; torch.randperm costs 7 launches incl. a radix sort).
+// Construction: k = ceil(log2 n) bits split into a high part (a = k/2 bits) and a low part (b = k-a bits); eight
+// swap-free Feistel rounds alternately xor one part with a keyed 64-bit mix of the other (each round is a bijection
+// of [0, 2^k) whatever a and b are); values that land in [n, 2^k) are walked along their cycle until they fall back
+// into [0, n) (cycle walking keeps the map a bijection of [0, n); 2^k < 2n, so < 2 evaluations on average).
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+constexpr int kPermRounds = 8;
+
+__device__ __forceinline__ uint64_t feistel_bijection(uint64_t x, int a, int b, const uint64_t (&key)[kPermRounds]) {
+    const uint64_t mask_a = (1ULL << a) - 1ULL, mask_b = (1ULL << b) - 1ULL;
+    uint64_t hi = x >> b, lo = x & mask_b;
+#pragma unroll
+    for (int r = 0; r < kPermRounds; r += 2) {
+        hi ^= mix64(lo + key[r]) & mask_a;
+        lo ^= mix64(hi + key[r + 1]) & mask_b;
+    }
+    return (hi << b) | lo;
+}
+
+__global__ void __launch_bounds__(256)
+    random_permutation_kernel(int64_t* __restrict__ out, int64_t n, int bits, uint64_t seed,
+                              const uint64_t* __restrict__ counter_dev, uint64_t offset) {
+    const int a = bits / 2, b = bits - a;
+    uint64_t key[kPermRounds];
+    const uint64_t base = mix64(seed ^ 0x9E3779B97F4A7C15ULL) + (counter_dev ? *counter_dev : 0ULL) + offset;
+#pragma unroll
+    for (int r = 0; r < kPermRounds; ++r) key[r] = mix64(base * 0xD1342543DE82EF95ULL + (uint64_t)(r + 1) * 0x9E3779B97F4A7C15ULL);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t j = feistel_bijection((uint64_t)i, a, b, key);
+        while (j >= (uint64_t)n) j = feistel_bijection(j, a, b, key);
+        out[i] = (int64_t)j;
+    }
+}
+
 }  // namespace xb
 
 using namespace xb;
@@ -61,6 +102,16 @@ extern "C" int xb_sample_gaussian(const float* mu, const float* logstd, int A, u
 extern "C" int xb_counter_add(uint64_t* counter_dev, uint64_t inc, xb_stream_t stream) {
     if (!counter_dev) return XB_E_BADARG;
     counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter_dev, inc);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_random_permutation(int64_t* out, int64_t n, uint64_t seed, const uint64_t* counter_dev, uint64_t offset,
+                                     xb_stream_t stream) {
+    if (!out || n <= 0 || n > (1LL << 40)) return XB_E_BADARG;
+    int bits = 2;                                   // at least one bit per Feistel half
+    while ((1LL << bits) < n) ++bits;
+    random_permutation_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(out, n, bits, seed, counter_dev, offset);
     XB_LAUNCH_CHECK();
     return 0;
 }

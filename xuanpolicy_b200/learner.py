@@ -18,6 +18,7 @@ import torch
 
 from . import ops
 from .fused_mlp import FusedActorCritic
+from .policies import old_dist_params
 
 
 def _dist_params(a_dist):
@@ -308,29 +309,6 @@ class PG_Learner(PPOCLIP_Learner):
 
 
 # ---------------------------------------------------------------------------------------------------- PPO-KL / PPG
-def old_dist_params(old_dists, device):
-    """Parameters of the OLD action distribution of a minibatch as CUDA tensors: ('categorical', logits [B, A], None)
-    or ('gaussian', mu [B, A], std [B, A] | [A]).
-
-    Accepts what the reference hands its learners — a numpy object array of per-sample distribution wrappers
-    (`split_distributions` / `merge_distributions`, xuance/torch/utils/operations.py:53-92) — as well as one batched
-    wrapper (anything with `get_param()`), which is what the device buffer returns from `sample`."""
-    f32 = lambda t: torch.as_tensor(t, device=device).detach().to(torch.float32).contiguous()
-    if hasattr(old_dists, "get_param"):
-        p = old_dists.get_param()
-        if isinstance(p, (tuple, list)):
-            return "gaussian", f32(p[0]), f32(p[1])
-        return "categorical", f32(p), None
-    flat = np.asarray(old_dists, dtype=object).reshape(-1)
-    first = flat[0].get_param()
-    if isinstance(first, (tuple, list)):
-        mu = torch.stack([torch.as_tensor(d.get_param()[0]).reshape(-1) for d in flat])
-        std = torch.stack([torch.as_tensor(d.get_param()[1]).reshape(-1) for d in flat])
-        return "gaussian", f32(mu), f32(std)
-    logits = torch.cat([torch.as_tensor(d.get_param()).reshape(1, -1) for d in flat], dim=0)
-    return "categorical", f32(logits), None
-
-
 class _DistLossLearner(PPOCLIP_Learner):
     """Shared machinery of the learners whose loss needs the old action distribution (csrc/dist_loss.cu)."""
 

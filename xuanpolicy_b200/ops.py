@@ -47,7 +47,8 @@ def env_step(kind, state, rng, elapsed, ep_score, actions, obs, next_obs, rew, t
 
 def rollout_step(kind, act_param, logstd, val, seed, counter, offset, state, rng, elapsed, ep_score, obs, next_obs, rew,
                  term, trunc, reset_obs, ep_step_out, ep_score_out, ep_stats, max_steps, x_in, act_out, logp_out, obs_row,
-                 act_row, rew_row, val_row, term_row, trunc_row, logp_row, rew_std=None, rew_clip=0.0):
+                 act_row, rew_row, val_row, term_row, trunc_row, logp_row, rew_std=None, rew_clip=0.0, boot_src=None,
+                 boot_row=None):
     """sample + env step + store of one vector step in one launch (see xb_rollout_step in include/xb200.h)."""
     N = elapsed.numel()
     _lib.call("xb_rollout_step", kind, _p(act_param, F32), _p(logstd, F32), _p(val, F32), int(seed), _p(counter, I64),
@@ -55,7 +56,8 @@ def rollout_step(kind, act_param, logstd, val, seed, counter, offset, state, rng
               _p(next_obs, F32), _p(rew, F32), _p(term, U8), _p(trunc, U8), _p(reset_obs, F32), _p(ep_step_out, I32),
               _p(ep_score_out, F64), _p(ep_stats, F64), max_steps, _p(x_in, F32), _p(act_out, F32 if kind == 1 else I64),
               _p(logp_out, F32), _p(obs_row, F32), _p(act_row, F32), _p(rew_row, F32), _p(val_row, F32),
-              _p(term_row, F32), _p(trunc_row, U8), _p(logp_row, F32), _p(rew_std, F32), float(rew_clip), N, _stream())
+              _p(term_row, F32), _p(trunc_row, U8), _p(logp_row, F32), _p(rew_std, F32), float(rew_clip), _p(boot_src, F32),
+              _p(boot_row, F32), N, _stream())
 
 
 def sincos_f64(x):
@@ -91,6 +93,14 @@ def gather_batch(idx, T, N, b_obs, obs_dim, b_act, act_dim, b_ret, b_val, b_adv,
     _lib.call("xb_gather_batch", _p(idx, I64), idx.numel(), T, N, _p(b_obs, F32), obs_dim, _p(b_act, F32), act_dim,
               _p(b_ret, F32), _p(b_val, F32), _p(b_adv, F32), _p(b_logp, F32), _p(obs_out, F32), _p(act_out, F32),
               _p(ret_out, F32), _p(val_out, F32), _p(adv_out, F32), _p(logp_out, F32), _p(stats, F64), _stream())
+
+
+def gather_rows(idx, T, N, src, out):
+    """out[i, :] = src[step, env, :] for the reference's flat index k -> (env = k // T, step = k % T): any per-transition
+    [T, N, W] array through the generic row slot of xb_gather_batch."""
+    W = src.shape[2]
+    _lib.call("xb_gather_batch", _p(idx, I64), idx.numel(), T, N, None, 1, _p(src, F32), W, None, None, None, None, None,
+              _p(out, F32), None, None, None, None, None, _stream())
 
 
 def normalize_adv(adv, stats, count):
@@ -173,6 +183,11 @@ def sample_gaussian(mu, logstd, seed, counter, offset, act_out, logp_out):
     N, A = mu.shape
     _lib.call("xb_sample_gaussian", _p(mu, F32), _p(logstd, F32), A, seed, _p(counter, I64), offset, _p(act_out, F32),
               _p(logp_out, F32), N, _stream())
+
+
+def random_permutation(out, seed, counter=None, offset=0):
+    """out[i] = P(i): a keyed pseudo-random permutation of 0..n-1 written in one launch (xb_random_permutation)."""
+    _lib.call("xb_random_permutation", _p(out, I64), out.numel(), int(seed), _p(counter, I64), int(offset), _stream())
 
 
 def counter_add(counter, inc=1):

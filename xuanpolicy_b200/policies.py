@@ -265,6 +265,48 @@ class DiagGaussianDistribution:
         return self.mu
 
 
+def old_dist_params(old_dists, device):
+    """Parameters of the OLD action distribution of a minibatch as CUDA tensors: ('categorical', logits [B, A], None)
+    or ('gaussian', mu [B, A], std [B, A] | [A]).
+
+    Accepts what the reference hands its learners — a numpy object array of per-sample distribution wrappers
+    (`split_distributions` / `merge_distributions`, xuance/torch/utils/operations.py:53-92) — as well as one batched
+    wrapper (anything with `get_param()`), which is what the device buffer returns from `sample`."""
+    f32 = lambda t: torch.as_tensor(t, device=device).detach().to(torch.float32).contiguous()
+    if hasattr(old_dists, "get_param"):
+        p = old_dists.get_param()
+        if isinstance(p, (tuple, list)):
+            return "gaussian", f32(p[0]), f32(p[1])
+        return "categorical", f32(p), None
+    flat = np.asarray(old_dists, dtype=object).reshape(-1)
+    first = flat[0].get_param()
+    if isinstance(first, (tuple, list)):
+        mu = torch.stack([torch.as_tensor(d.get_param()[0]).reshape(-1) for d in flat])
+        std = torch.stack([torch.as_tensor(d.get_param()[1]).reshape(-1) for d in flat])
+        return "gaussian", f32(mu), f32(std)
+    logits = torch.cat([torch.as_tensor(d.get_param()).reshape(1, -1) for d in flat], dim=0)
+    return "categorical", f32(logits), None
+
+
+class OldDistBatch:
+    """The old action distributions of a batch of transitions as two device tensors — what the device buffer keeps
+    and returns for the auxiliary key "old_dist" instead of the reference's numpy array of per-sample Python objects
+    (memory_tools.py:28-30, operations.py:53-72).  `get_param()` has the wrappers' meaning: logits, or (mu, std)."""
+
+    def __init__(self, kind, p0, p1=None):
+        self.kind, self.p0, self.p1 = kind, p0, p1
+
+    def get_param(self):
+        return self.p0 if self.kind == "categorical" else (self.p0, self.p1)
+
+    @property
+    def shape(self):
+        return tuple(self.p0.shape[:-1])
+
+    def __len__(self):
+        return self.p0.shape[0]
+
+
 class _CategoricalActor(nn.Module):
     def __init__(self, state_dim, action_dim, hidden, act, init, device):
         super().__init__()
