@@ -151,10 +151,11 @@ def time_agent(agent, steps, warmup, flush, world):
 
 def time_phases(agent, flush):
     """CUDA-event time of one rollout graph replay and one epoch graph replay (single GPU, graphs captured)."""
-    if agent._rollout_graph is None or agent._epoch_graph is None:
+    epoch_graph = agent._epoch_graph if agent._epoch_graph is not None else (agent._epoch_graphs or [None])[0]
+    if agent._rollout_graph is None or epoch_graph is None:
         return None
     out = {}
-    for name, g in (("rollout_graph_ms", agent._rollout_graph), ("epoch_graph_ms", agent._epoch_graph)):
+    for name, g in (("rollout_graph_ms", agent._rollout_graph), ("epoch_graph_ms", epoch_graph)):
         ms = []
         for _ in range(5):
             flush.add_(1)
@@ -181,7 +182,8 @@ def count_launches(agent):
     else:
         per_rollout = T * (3 + 5) + 5 + 2 + 1  # per step: sample, env_step, store, 3 bias+act, 2 head; bootstrap fwd; GAE + pack; counter
         per_update = 1 + 1 + 2 + 5 + 3         # gather, loss, grad-norm + adam, fwd: 3 bias+act + 2 head, bwd: 2 head+act + 1 act+bias
-    return per_rollout + E * M * per_update
+    per_epoch = 2 if agent.shuffle != "host" else 0     # device permutation + its counter tick
+    return per_rollout + E * (M * per_update + per_epoch)
 
 
 def time_kernel(fn, flush, iters=20, warm=3):

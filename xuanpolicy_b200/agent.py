@@ -109,6 +109,10 @@ class PPOCLIP_Agent:
         self._ctr = torch.zeros(1, dtype=torch.int64, device=dev)
         self._perm = torch.zeros(self.buffer_size, dtype=torch.int64, device=dev)
         self._perm_ctr = torch.zeros(1, dtype=torch.int64, device=dev)      # one tick per drawn device permutation
+        self._perm_bufs = [self._perm, torch.zeros_like(self._perm)]        # host shuffle: double-buffered H2D target
+        self._perm_ready, self._perm_free, self._perm_staged = [None, None], [None, None], False
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._epoch_graphs = None
         self._perm_seed = self.seed * 2654435761 + 7919 * self._rank() + 1
         self._feeder = None
         if self.shuffle == "host":
@@ -250,12 +254,13 @@ class PPOCLIP_Agent:
         ops.random_permutation(self._perm, self._perm_seed, self._perm_ctr, 0)
         ops.counter_add(self._perm_ctr, 1)
 
-    def _epoch_body(self):
+    def _epoch_body(self, perm=None):
         B = self.batch_size
         if self.shuffle != "host":
             self._device_permutation()
+        perm = self._perm if perm is None else perm
         for start in range(0, self.buffer_size - B + 1, B):
-            idx = self._perm[start:start + B]
+            idx = perm[start:start + B]
             mb = self.learner.stage_gather(self.memory, idx)
             self.learner.stage_forward_backward(self.memory, idx, mb)
             self.learner.stage_optimizer()
@@ -284,7 +289,44 @@ class PPOCLIP_Agent:
             else:
                 lr.stage_optimizer()
 
+    def _stage_host_perm(self, ep):
+        """H2D copy of epoch `ep`'s host-drawn permutation into device buffer ep & 1 on the copy stream, so it overlaps
+        the previous epoch's graph (which reads the other buffer)."""
+        k = ep & 1
+        src = self._feeder.get(self._iteration, ep)
+        cs = self._copy_stream
+        if self._perm_free[k] is not None:
+            cs.wait_event(self._perm_free[k])                      # the epoch that last read this buffer has finished
+        with torch.cuda.stream(cs):
+            self._perm_bufs[k].copy_(src, non_blocking=True)       # from pinned memory
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        self._perm_ready[k] = ev
+        self.h2d_bytes += src.numel() * 8
+
+    def _update_phase_overlapped(self):
+        """Host-shuffle update phase with double-buffered permutations: two captured epoch graphs, one per buffer."""
+        main = torch.cuda.current_stream(self.device)
+        if not self._perm_staged:
+            self._stage_host_perm(0)
+        self._perm_staged = False
+        self._feeder.prefetch(self._iteration + 1)
+        for ep in range(self.n_epoch):
+            if ep + 1 < self.n_epoch:
+                self._stage_host_perm(ep + 1)
+            k = ep & 1
+            main.wait_event(self._perm_ready[k])
+            self._epoch_graphs[k].replay()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self._perm_free[k] = ev
+        self._feeder.mark_consumed(self._iteration)
+        self.learner.iterations += self.n_epoch * (self.buffer_size // self.batch_size)
+        self._iteration += 1
+
     def _update_phase(self):
+        if self._epoch_graphs is not None:
+            return self._update_phase_overlapped()
         n_updates = self.n_epoch * (self.buffer_size // self.batch_size)
         if self.shuffle == "host":
             self._feeder.prefetch(self._iteration + 1)             # next rollout's permutations, drawn while the GPU works
@@ -325,7 +367,15 @@ class PPOCLIP_Agent:
         self._rollout_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._rollout_graph):
             self._rollout()
-        if self.world_size == 1:
+        if self.world_size == 1 and self.shuffle == "host":
+            # one epoch graph per permutation buffer: the H2D copy of the next permutation overlaps the running epoch
+            self._epoch_graphs = []
+            for k in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._epoch_body(self._perm_bufs[k])
+                self._epoch_graphs.append(g)
+        elif self.world_size == 1:
             self._epoch_graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._epoch_graph):
                 self._epoch_body()
@@ -407,6 +457,9 @@ class PPOCLIP_Agent:
             if self.use_graphs and self._rollout_graph is None:
                 self._capture()
             for _ in range(train_steps // self.n_steps):
+                if self._epoch_graphs is not None and not self._perm_staged:
+                    self._stage_host_perm(0)                       # first permutation travels while the rollout runs
+                    self._perm_staged = True
                 if self._rollout_graph is not None:
                     self._rollout_graph.replay()
                 else:
