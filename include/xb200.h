@@ -379,6 +379,48 @@ int xb_mlp_trunk_wgrad(const float* dz1, const float* obs, int ld, int obs_dim, 
                        int64_t B, int H, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * (5b) Env-sharded data parallelism over NVLink / NVSwitch PEER MEMORY: the two exchanges of an
+ * update — the (sum adv, sum adv^2) behind the global-minibatch advantage normalisation (memory_tools.py:241-242)
+ * and the flat-gradient sum in front of clip_grad_norm_ + Adam (ppoclip_learner.py:47-49) — as kernels that read the
+ * peers' buffers directly, fused with the computation that consumes the result.  The reference is single-process
+ * (its only collective is the disabled mpi4py Allreduce of xuance/common/statistic_tools.py:6-32).
+ *
+ * Every rank owns one "comm block" (xb_peer_alloc: cudaMalloc, zeroed) of xb_peer_block_bytes(n) bytes, laid out
+ *   [ barrier flags | stats fp64 [xb_peer_stats_max()] at xb_peer_stats_offset() | gradient fp32 [n] at xb_peer_grad_offset() ]
+ * exported / imported through CUDA IPC (xb_peer_export -> 64-byte handle -> xb_peer_import in the peer process).
+ * peer_bases is a HOST array of the W device pointers (index = rank; own block at [rank]).
+ * tickets: u32 [64] device, zero-initialised once, private to the rank (per-CTA barrier counters; never reset).
+ * Every rank must issue the same sequence of xb_peer_* launches with the same n.
+ *
+ * xb_peer_allreduce_grad_norm: barrier; grad_out[i] = sum_r gradient_r[i] in rank order (bit-identical on every rank);
+ *   squared norm of grad_out * grad_scale; barrier; then exactly the scalars xb_clip_adam_step's first kernel derives
+ *   (workspace layout identical), so xb_adam_apply can follow.  n must be a multiple of 4.
+ * xb_adam_apply: the second kernel of xb_clip_adam_step alone (clip + Adam from the scalars in workspace).
+ * xb_peer_allreduce_f64: out[j] = sum_r stats_r[j], j < n <= xb_peer_stats_max().
+ * xb_adv_stats_minibatches: stats[m] = (sum, sumsq) of adv over minibatch m = idx[m*B, (m+1)*B) for every minibatch
+ *   of an epoch in one launch (adv element stride `stride` floats per transition row; zeroes stats first).
+ * ---------------------------------------------------------------------------------------------------------- */
+int64_t xb_peer_block_bytes(int64_t n_grad_floats);
+int64_t xb_peer_stats_offset(void);
+int64_t xb_peer_grad_offset(void);
+int xb_peer_stats_max(void);
+int xb_peer_alloc(void** ptr_out /* host */, int64_t bytes);
+int xb_peer_free(void* ptr);
+int xb_peer_export(void* ptr, void* handle_out /* host, 64 bytes */);
+int xb_peer_import(const void* handle /* host, 64 bytes */, void** ptr_out /* host */);
+int xb_peer_close(void* ptr);
+int xb_peer_allreduce_grad_norm(const void* const* peer_bases /* host [W] */, int rank, int W, int64_t n, float* grad_out,
+                                uint32_t* tickets, int64_t* step_dev, float lr0, float lr_end_factor,
+                                int64_t lr_total_iters, float beta1, float beta2, float eps, float max_norm,
+                                float grad_scale, double* workspace, float* lr_out, float* gnorm_out, xb_stream_t stream);
+int xb_adam_apply(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float beta1, float beta2,
+                  float eps, float grad_scale, const double* workspace, xb_stream_t stream);
+int xb_peer_allreduce_f64(const void* const* peer_bases /* host [W] */, int rank, int W, int n, double* out,
+                          uint32_t* tickets, xb_stream_t stream);
+int xb_adv_stats_minibatches(const int64_t* idx, int64_t n_minibatches, int64_t B, int64_t T, int64_t N, const float* adv,
+                             int64_t stride, double* stats, xb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Device-side minibatch permutation: out[i] = P(i), a keyed pseudo-random bijection of [0, n) (swap-free Feistel
  * network on ceil(log2 n) bits + cycle walking), evaluated independently per index: one launch, no sort, no scratch.
  * Replaces np.random.shuffle(indexes) in PPOCLIP_Agent.train (ppoclip_agent.py:76-78).  The key is derived from

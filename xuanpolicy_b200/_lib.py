@@ -67,6 +67,17 @@ SIGNATURES = {
     "xb_mlp_backward_tail": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp,
                              _vp, _vp, _vp, _i32, _vp],
     "xb_mlp_trunk_wgrad": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _i32, _vp],
+    "xb_peer_stats_max": [],
+    "xb_peer_alloc": [_vp, _i64],
+    "xb_peer_free": [_vp],
+    "xb_peer_export": [_vp, _vp],
+    "xb_peer_import": [_vp, _vp],
+    "xb_peer_close": [_vp],
+    "xb_peer_allreduce_grad_norm": [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _f32, _f32, _i64, _f32, _f32, _f32, _f32, _f32, _vp,
+                                    _vp, _vp, _vp],
+    "xb_adam_apply": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp],
+    "xb_peer_allreduce_f64": [_vp, _i32, _i32, _i32, _vp, _vp, _vp],
+    "xb_adv_stats_minibatches": [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp],
     "xb_clip_adam_step": [_vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _i64, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp],
 }
 
@@ -91,6 +102,10 @@ def load():
         fn = getattr(lib, name)  # AttributeError here means header and library are out of sync
         fn.argtypes = argtypes
         fn.restype = C.c_int
+    for name in ("xb_peer_block_bytes", "xb_peer_stats_offset", "xb_peer_grad_offset"):
+        fn = getattr(lib, name)
+        fn.argtypes = [C.c_int64] if name == "xb_peer_block_bytes" else []
+        fn.restype = C.c_int64
     lib.xb_error_string.argtypes = [C.c_int]
     lib.xb_error_string.restype = C.c_char_p
     if lib.xb_version() != 100:

@@ -109,6 +109,7 @@ class PPOCLIP_Agent:
         self._ctr = torch.zeros(1, dtype=torch.int64, device=dev)
         self._perm = torch.zeros(self.buffer_size, dtype=torch.int64, device=dev)
         self._perm_ctr = torch.zeros(1, dtype=torch.int64, device=dev)      # one tick per drawn device permutation
+        self._mb_stats_all = torch.zeros(2 * max(1, self.buffer_size // self.batch_size), dtype=torch.float64, device=dev)
         self._perm_bufs = [self._perm, torch.zeros_like(self._perm)]        # host shuffle: double-buffered H2D target
         self._perm_ready, self._perm_free, self._perm_staged = [None, None], [None, None], False
         self._copy_stream = torch.cuda.Stream(device=dev)
@@ -265,9 +266,31 @@ class PPOCLIP_Agent:
             self.learner.stage_forward_backward(self.memory, idx, mb)
             self.learner.stage_optimizer()
 
+    def _epoch_peer(self):
+        """Env-sharded epoch over NVLink peer memory — no NCCL call, so the whole epoch is ONE captured graph:
+        the (sum adv, sum adv^2) of all minibatches of the epoch are computed in one pass and exchanged once
+        (global-minibatch advantage normalisation, memory_tools.py:241-242), and every update's gradient exchange is
+        fused into the first optimiser kernel (csrc/peer_comm.cu)."""
+        B, lr, mem, peer = self.batch_size, self.learner, self.memory, self.learner._peer
+        M = self.buffer_size // B
+        if mem.use_advnorm:
+            if mem.packed and lr.value_clip <= 0:
+                adv, stride = mem._rec.view(-1)[6:], 8          # adv lane of the packed 32-byte records
+            else:
+                adv, stride = mem._adv, 1
+            ops.adv_stats_minibatches(self._perm, M, B, mem.n_size, mem.n_envs, adv, stride, peer.stats)
+            ops.peer_allreduce_f64(peer, 2 * M, self._mb_stats_all)
+        for k, start in enumerate(range(0, self.buffer_size - B + 1, B)):
+            idx = self._perm[start:start + B]
+            mb = lr.stage_gather(mem, idx, compute_stats=False)
+            lr.stage_forward_backward(mem, idx, mb, stats=self._mb_stats_all[2 * k:2 * k + 2])
+            lr.stage_optimizer()
+
     def _epoch_distributed(self):
         """Env-sharded data parallel epoch: every rank updates on its local minibatch; the only exchanges are the
         two-scalar advantage statistics and the flat gradient, between (graph) stages."""
+        if self.learner._peer is not None:
+            return self._epoch_peer()
         B, lr, mem = self.batch_size, self.learner, self.memory
         for k, start in enumerate(range(0, self.buffer_size - B + 1, B)):
             idx = self._perm[start:start + B]
@@ -379,6 +402,10 @@ class PPOCLIP_Agent:
             self._epoch_graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._epoch_graph):
                 self._epoch_body()
+        elif self.learner._peer is not None:
+            self._epoch_graph = torch.cuda.CUDAGraph()      # peer-memory exchange: plain kernels, one graph per epoch
+            with torch.cuda.graph(self._epoch_graph):
+                self._epoch_peer()
         elif self._capture_distributed_epoch():
             pass          # one graph per epoch with the NCCL all-reduces inside it
         else:

@@ -26,6 +26,7 @@ SOURCES = {
     "dist_loss.cu": [],
     "sample.cu": [],
     "optim.cu": [],
+    "peer_comm.cu": [],
     "host_utils.cu": [],
     "mlp_epilogue.cu": [],
     "normalize.cu": [],

@@ -111,3 +111,14 @@ extern "C" int xb_clip_adam_step(float* param, const float* grad, float* exp_avg
     XB_LAUNCH_CHECK();
     return 0;
 }
+
+extern "C" int xb_adam_apply(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float beta1,
+                             float beta2, float eps, float grad_scale, const double* workspace, xb_stream_t stream) {
+    if (n <= 0 || !param || !grad || !exp_avg || !exp_avg_sq || !workspace) return XB_E_BADARG;
+    AdamHyper h{0.0f, 0.0f, beta1, beta2, eps, 0.0f, grad_scale, 0};
+    int grid = grid_for(n, kOptBlock, 4);
+    if (grid > kOptMaxGrid) grid = kOptMaxGrid;
+    adam_apply_kernel<<<grid, kOptBlock, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, h, workspace);
+    XB_LAUNCH_CHECK();
+    return 0;
+}

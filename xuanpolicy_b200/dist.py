@@ -14,6 +14,7 @@ inside RunningMeanStd (xuance/common/statistic_tools.py:6-32).  The PPO path sha
 
 These helpers are backend-agnostic (NCCL on GPUs, gloo in the CPU tests).
 """
+import ctypes as C
 import os
 
 import torch
@@ -65,3 +66,66 @@ def broadcast_parameters(flat_param, src=0, group=None):
     """Ranks are seeded identically, so this is a safety net rather than a requirement."""
     dist.broadcast(flat_param, src=src, group=group)
     return flat_param
+
+
+class _DeviceMemory:
+    """Zero-copy torch view of a raw device allocation (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class PeerComm:
+    """One rank's side of the NVLink peer-memory exchange (csrc/peer_comm.cu, include/xb200.h section 5b).
+
+    Allocates this rank's comm block [barrier flags | minibatch statistics | flat gradient], exchanges CUDA IPC
+    handles through the process group and maps every peer's block.  `grad` (fp32 [n]) and `stats` (fp64) are torch
+    views INTO the block: the backward kernels write the gradient there, the peers read it with P2P loads inside
+    xb_peer_allreduce_grad_norm.  Single node only (IPC), world size <= 8."""
+
+    def __init__(self, n_grad_floats, device, group=None):
+        from . import _lib
+        lib = _lib.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError("peer-memory exchange supports up to 8 ranks of one node")
+        self.n = (int(n_grad_floats) + 3) // 4 * 4
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            ptr = C.c_void_p()
+            _lib.call("xb_peer_alloc", C.byref(ptr), lib.xb_peer_block_bytes(self.n))
+            self._own = ptr.value
+            handle = C.create_string_buffer(64)
+            _lib.call("xb_peer_export", ptr, handle)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self._imported = []
+            self.bases = (C.c_void_p * self.world)()
+            for r in range(self.world):
+                if r == self.rank:
+                    self.bases[r] = self._own
+                else:
+                    p = C.c_void_p()
+                    _lib.call("xb_peer_import", C.create_string_buffer(handles[r], 64), C.byref(p))
+                    self._imported.append(p.value)
+                    self.bases[r] = p.value
+            self._keep = (_DeviceMemory(self._own + lib.xb_peer_grad_offset(), self.n, "<f4"),
+                          _DeviceMemory(self._own + lib.xb_peer_stats_offset(), lib.xb_peer_stats_max(), "<f8"))
+            self.grad = torch.as_tensor(self._keep[0], device=self.device)
+            self.stats = torch.as_tensor(self._keep[1], device=self.device)
+            self.tickets = torch.zeros(64, dtype=torch.int32, device=self.device)
+            torch.cuda.synchronize(self.device)
+        dist.barrier(group)          # every rank has mapped every block before the first kernel touches one
+
+    def close(self):
+        from . import _lib
+        if self._own is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+        for p in self._imported:
+            _lib.call("xb_peer_close", C.c_void_p(p))
+        _lib.call("xb_peer_free", C.c_void_p(self._own))
+        self._own, self._imported = None, []

@@ -38,7 +38,7 @@ class FlatAdamState:
     Hyper-parameters are read from the torch optimizer / LinearLR scheduler the caller built
     (xuance/torch/runners/runner_drl.py:71-73)."""
 
-    def __init__(self, policy, optimizer, scheduler):
+    def __init__(self, policy, optimizer, scheduler, grad_alloc=None):
         params = [p for p in policy.parameters() if p.requires_grad]
         dev = params[0].device
         pad4 = lambda k: (k + 3) // 4 * 4          # every tensor starts 16-byte aligned (float4 epilogue kernels)
@@ -46,7 +46,9 @@ class FlatAdamState:
         self.n = n
         self.n_params = sum(p.numel() for p in params)
         self.flat_param = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        # grad_alloc(n) -> fp32 [n]: lets the gradient live in peer-visible memory (dist.PeerComm) when env-sharded
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev) if grad_alloc is None else grad_alloc(n)
+        self.grad_sum = None                        # peer mode: the cross-rank sum lands here (local memory)
         off = 0
         for p in params:
             k = p.numel()
@@ -86,6 +88,17 @@ class FlatAdamState:
             if g is None:
                 v.zero_()
 
+    def apply_peer(self, peer, max_norm, grad_scale=1.0):
+        """Env-sharded step: ONE kernel sums the W ranks' gradients over NVLink peer memory and takes the norm of the sum
+        (csrc/peer_comm.cu), then the Adam kernel consumes the local copy of the sum."""
+        if self.grad_sum is None:
+            self.grad_sum = torch.zeros_like(self.flat_param)
+        ops.peer_allreduce_grad_norm(peer, self.grad_sum, peer.tickets, self.step, self.lr0, self.end_factor,
+                                     self.total_iters, self.beta1, self.beta2, self.eps, max_norm, grad_scale,
+                                     self.workspace, lr_out=self.lr, gnorm_out=self.gnorm)
+        ops.adam_apply(self.flat_param, self.grad_sum, self.exp_avg, self.exp_avg_sq, self.beta1, self.beta2, self.eps,
+                       grad_scale, self.workspace)
+
     def apply(self, max_norm, grad_scale=1.0):
         ops.clip_adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step, self.lr0,
                            self.end_factor, self.total_iters, self.beta1, self.beta2, self.eps, max_norm, grad_scale,
@@ -110,6 +123,7 @@ class PPOCLIP_Learner:
         self.use_fused_mlp = os.environ.get("XB_FUSED_MLP", "1") != "0"
         self._mb = {}
         self.world_size, self.process_group = 1, None
+        self._peer = None           # dist.PeerComm when env-sharded over NVLink peer memory
 
     # ---------------------------------------------------------------------------------------------- checkpoints
     def save_model(self, model_path):
@@ -200,14 +214,30 @@ class PPOCLIP_Learner:
     def enable_fused_optimizer(self, process_group=None):
         """Switch to the flat-buffer fused clip+Adam+LinearLR step (native path).  The torch optimizer handed to
         the constructor is only read for its hyper-parameters from here on."""
-        if self._flat is None:
-            self._flat = FlatAdamState(self.policy, self.optimizer, self.scheduler)
-            if self.use_fused_mlp and FusedActorCritic.plan(self.policy) is not None:
-                self._fused = FusedActorCritic(self.policy)
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.process_group = process_group
             self.world_size = torch.distributed.get_world_size(process_group)
+        if self._flat is None:
+            grad_alloc = None
+            if self.world_size > 1 and os.environ.get("XB_PEER_COMM", "1") != "0":
+                grad_alloc = self._peer_grad_alloc
+            self._flat = FlatAdamState(self.policy, self.optimizer, self.scheduler, grad_alloc)
+            if self.use_fused_mlp and FusedActorCritic.plan(self.policy) is not None:
+                self._fused = FusedActorCritic(self.policy)
         return self._flat
+
+    def _peer_grad_alloc(self, n):
+        """The flat gradient inside this rank's NVLink-visible comm block (dist.PeerComm), so the peers sum it with P2P
+        loads.  Falls back to the NCCL all-reduce path (with a warning) when CUDA IPC is unavailable."""
+        from .dist import PeerComm
+        try:
+            self._peer = PeerComm(n, self.device, self.process_group)
+        except Exception as e:            # pragma: no cover - depends on the container's IPC permissions
+            import warnings
+            warnings.warn("peer-memory exchange unavailable (%s); using NCCL all-reduces" % (e,))
+            self._peer = None
+            return torch.zeros(n, dtype=torch.float32, device=self.device)
+        return self._peer.grad[:n]
 
     def _minibatch_buffers(self, B, obs_dim):
         key = (B, obs_dim)
@@ -217,20 +247,22 @@ class PPOCLIP_Learner:
                                  stats=torch.zeros(2, dtype=torch.float64, device=self.device))
         return self._mb[key]
 
-    def stage_gather(self, memory, idx):
-        """Stage 1 of a native update: gather the MLP input rows and the minibatch advantage statistics."""
+    def stage_gather(self, memory, idx, compute_stats=True):
+        """Stage 1 of a native update: gather the MLP input rows and (unless the caller already has the global ones)
+        the minibatch advantage statistics."""
         mb = self._minibatch_buffers(idx.numel(), memory.obs_dim)
+        want = memory.use_advnorm and compute_stats
         if memory.packed and self.value_clip <= 0:   # one 32-byte record per sample: obs + {act, old_logp, adv, ret}
             ops.gather_records(idx, memory.n_size, memory.n_envs, memory._rec, memory.obs_dim, mb["obs"], mb["scal"],
-                               stats=mb["stats"] if memory.use_advnorm else None)
+                               stats=mb["stats"] if want else None)
         else:
             ops.gather_obs(idx, memory.n_size, memory.n_envs, memory._obs, memory.obs_dim, mb["obs"],
-                           b_adv=memory._adv if memory.use_advnorm else None,
-                           stats=mb["stats"] if memory.use_advnorm else None)
+                           b_adv=memory._adv if want else None, stats=mb["stats"] if want else None)
         return mb
 
-    def stage_forward_backward(self, memory, idx, mb):
-        """Stage 2: torch MLP forward, fused gather+loss+backward kernel, torch MLP backward into the flat gradient."""
+    def stage_forward_backward(self, memory, idx, mb, stats=None):
+        """Stage 2: torch MLP forward, fused gather+loss+backward kernel, torch MLP backward into the flat gradient.
+        `stats` (fp64 [2], optional): the GLOBAL-minibatch (sum adv, sum adv^2) when the caller exchanged them itself."""
         B = idx.numel()
         fused = self._fused if (self._fused is not None and B >= FusedActorCritic.MIN_ROWS) else None
         if fused is not None:                        # tcgen05 dense kernels; weights re-split after every Adam step
@@ -238,7 +270,7 @@ class PPOCLIP_Learner:
             a_dist = fused.dist_params(act_out)
         else:
             _, a_dist, v_pred = self.policy(mb["obs"])
-        stats = mb["stats"] if memory.use_advnorm else None
+        stats = (stats if stats is not None else mb["stats"]) if memory.use_advnorm else None
         if memory.packed and self.value_clip <= 0:   # scalars already gathered, compact and coalesced
             self._loss_backward(a_dist, v_pred, None, None, None, None, None, 1.0 / (B * self.world_size),
                                 adv_stats=stats, adv_count=B * self.world_size, packed=mb["scal"], flat=self._flat,
@@ -249,8 +281,13 @@ class PPOCLIP_Learner:
                                 adv_stats=stats, adv_count=B * self.world_size, flat=self._flat, fused=fused)
 
     def stage_optimizer(self):
-        """Stage 3: global-norm clip + Adam + LinearLR on the flat buffers (one fused device step)."""
-        self._flat.apply(self.clip_grad_norm if self.use_grad_clip else 0.0, 1.0)
+        """Stage 3: global-norm clip + Adam + LinearLR on the flat buffers (one fused device step).  Env-sharded over peer
+        memory, the gradient exchange happens INSIDE this stage (fused with the norm pass)."""
+        max_norm = self.clip_grad_norm if self.use_grad_clip else 0.0
+        if self._peer is not None:
+            self._flat.apply_peer(self._peer, max_norm, 1.0)
+        else:
+            self._flat.apply(max_norm, 1.0)
 
     def update_from_buffer(self, memory, idx):
         """One PPO-Clip SGD step on the minibatch `idx` (CUDA int64 flat indices) of a native buffer.
@@ -262,7 +299,7 @@ class PPOCLIP_Learner:
         if self.world_size > 1 and memory.use_advnorm:
             torch.distributed.all_reduce(mb["stats"], group=self.process_group)
         self.stage_forward_backward(memory, idx, mb)
-        if self.world_size > 1:
+        if self.world_size > 1 and self._peer is None:
             torch.distributed.all_reduce(self._flat.flat_grad, group=self.process_group)
         self.stage_optimizer()
 

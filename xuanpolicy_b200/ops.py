@@ -202,6 +202,31 @@ def clip_adam_step(param, grad, exp_avg, exp_avg_sq, step_dev, lr0, lr_end_facto
               _stream())
 
 
+def peer_allreduce_grad_norm(peer, grad_out, tickets, step_dev, lr0, lr_end_factor, lr_total_iters, beta1, beta2, eps,
+                             max_norm, grad_scale, workspace, lr_out=None, gnorm_out=None):
+    """Cross-GPU gradient sum over peer memory fused with the gradient-norm pass (xb_peer_allreduce_grad_norm)."""
+    _lib.call("xb_peer_allreduce_grad_norm", peer.bases, peer.rank, peer.world, peer.n, _p(grad_out, F32), _p(tickets, I32),
+              _p(step_dev, I64), float(lr0), float(lr_end_factor), int(lr_total_iters), float(beta1), float(beta2),
+              float(eps), float(max_norm), float(grad_scale), _p(workspace, F64), _p(lr_out, F32), _p(gnorm_out, F32),
+              _stream())
+
+
+def adam_apply(param, grad, exp_avg, exp_avg_sq, beta1, beta2, eps, grad_scale, workspace):
+    _lib.call("xb_adam_apply", _p(param, F32), _p(grad, F32), _p(exp_avg, F32), _p(exp_avg_sq, F32), param.numel(),
+              float(beta1), float(beta2), float(eps), float(grad_scale), _p(workspace, F64), _stream())
+
+
+def peer_allreduce_f64(peer, n, out):
+    """out[:n] = sum over ranks of the first n doubles of each rank's comm-block statistics."""
+    _lib.call("xb_peer_allreduce_f64", peer.bases, peer.rank, peer.world, int(n), _p(out, F64), _p(peer.tickets, I32),
+              _stream())
+
+
+def adv_stats_minibatches(idx, n_minibatches, B, T, N, adv, stride, stats):
+    _lib.call("xb_adv_stats_minibatches", _p(idx, I64), int(n_minibatches), int(B), int(T), int(N), _p(adv, F32), int(stride),
+              _p(stats, F64), _stream())
+
+
 def act_bias_bwd(dy, y, slope, dz, dbias, workspace):
     B, H = dy.shape
     _lib.call("xb_act_bias_bwd", _p(dy, F32), _p(y, F32), float(slope), _p(dz, F32), _p(dbias, F32), _p(workspace, F32),
