@@ -386,15 +386,16 @@ int xb_mlp_trunk_wgrad(const float* dz1, const float* obs, int ld, int obs_dim, 
  * (its only collective is the disabled mpi4py Allreduce of xuance/common/statistic_tools.py:6-32).
  *
  * Every rank owns one "comm block" (xb_peer_alloc: cudaMalloc, zeroed) of xb_peer_block_bytes(n) bytes, laid out
- *   [ barrier flags | stats fp64 [xb_peer_stats_max()] at xb_peer_stats_offset() | gradient fp32 [n] at xb_peer_grad_offset() ]
+ *   [ barrier flags | stats fp64 [xb_peer_stats_max()] at xb_peer_stats_offset() | gradient inbox fp32 [2][8][n] at xb_peer_grad_offset() ]
  * exported / imported through CUDA IPC (xb_peer_export -> 64-byte handle -> xb_peer_import in the peer process).
  * peer_bases is a HOST array of the W device pointers (index = rank; own block at [rank]).
  * tickets: u32 [64] device, zero-initialised once, private to the rank (per-CTA barrier counters; never reset).
  * Every rank must issue the same sequence of xb_peer_* launches with the same n.
  *
- * xb_peer_allreduce_grad_norm: barrier; grad_out[i] = sum_r gradient_r[i] in rank order (bit-identical on every rank);
- *   squared norm of grad_out * grad_scale; barrier; then exactly the scalars xb_clip_adam_step's first kernel derives
- *   (workspace layout identical), so xb_adam_apply can follow.  n must be a multiple of 4.
+ * xb_peer_allreduce_grad_norm: every CTA pushes its slice of grad_in (local, fp32 [n]) into inbox[launch parity][rank] of
+ *   every peer with P2P stores; ONE barrier; grad_out[i] = sum_r inbox[parity][r][i] in rank order (bit-identical on every
+ *   rank) read from local memory; squared norm of grad_out * grad_scale; then exactly the scalars xb_clip_adam_step's
+ *   first kernel derives (workspace layout identical), so xb_adam_apply can follow.  n must be a multiple of 4.
  * xb_adam_apply: the second kernel of xb_clip_adam_step alone (clip + Adam from the scalars in workspace).
  * xb_peer_allreduce_f64: out[j] = sum_r stats_r[j], j < n <= xb_peer_stats_max().
  * xb_adv_stats_minibatches: stats[m] = (sum, sumsq) of adv over minibatch m = idx[m*B, (m+1)*B) for every minibatch
@@ -409,8 +410,8 @@ int xb_peer_free(void* ptr);
 int xb_peer_export(void* ptr, void* handle_out /* host, 64 bytes */);
 int xb_peer_import(const void* handle /* host, 64 bytes */, void** ptr_out /* host */);
 int xb_peer_close(void* ptr);
-int xb_peer_allreduce_grad_norm(const void* const* peer_bases /* host [W] */, int rank, int W, int64_t n, float* grad_out,
-                                uint32_t* tickets, int64_t* step_dev, float lr0, float lr_end_factor,
+int xb_peer_allreduce_grad_norm(const void* const* peer_bases /* host [W] */, int rank, int W, int64_t n,
+                                const float* grad_in, float* grad_out, uint32_t* tickets, int64_t* step_dev, float lr0, float lr_end_factor,
                                 int64_t lr_total_iters, float beta1, float beta2, float eps, float max_norm,
                                 float grad_scale, double* workspace, float* lr_out, float* gnorm_out, xb_stream_t stream);
 int xb_adam_apply(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float beta1, float beta2,

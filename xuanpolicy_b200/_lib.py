@@ -73,7 +73,7 @@ SIGNATURES = {
     "xb_peer_export": [_vp, _vp],
     "xb_peer_import": [_vp, _vp],
     "xb_peer_close": [_vp],
-    "xb_peer_allreduce_grad_norm": [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _f32, _f32, _i64, _f32, _f32, _f32, _f32, _f32, _vp,
+    "xb_peer_allreduce_grad_norm": [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _f32, _f32, _i64, _f32, _f32, _f32, _f32, _f32, _vp,
                                     _vp, _vp, _vp],
     "xb_adam_apply": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp],
     "xb_peer_allreduce_f64": [_vp, _i32, _i32, _i32, _vp, _vp, _vp],

@@ -266,22 +266,25 @@ class PPOCLIP_Agent:
             self.learner.stage_forward_backward(self.memory, idx, mb)
             self.learner.stage_optimizer()
 
-    def _epoch_peer(self):
+    def _epoch_peer(self, perm=None):
         """Env-sharded epoch over NVLink peer memory — no NCCL call, so the whole epoch is ONE captured graph:
         the (sum adv, sum adv^2) of all minibatches of the epoch are computed in one pass and exchanged once
         (global-minibatch advantage normalisation, memory_tools.py:241-242), and every update's gradient exchange is
         fused into the first optimiser kernel (csrc/peer_comm.cu)."""
         B, lr, mem, peer = self.batch_size, self.learner, self.memory, self.learner._peer
         M = self.buffer_size // B
+        if self.shuffle != "host":
+            self._device_permutation()
+        perm = self._perm if perm is None else perm
         if mem.use_advnorm:
             if mem.packed and lr.value_clip <= 0:
                 adv, stride = mem._rec.view(-1)[6:], 8          # adv lane of the packed 32-byte records
             else:
                 adv, stride = mem._adv, 1
-            ops.adv_stats_minibatches(self._perm, M, B, mem.n_size, mem.n_envs, adv, stride, peer.stats)
+            ops.adv_stats_minibatches(perm, M, B, mem.n_size, mem.n_envs, adv, stride, peer.stats)
             ops.peer_allreduce_f64(peer, 2 * M, self._mb_stats_all)
         for k, start in enumerate(range(0, self.buffer_size - B + 1, B)):
-            idx = self._perm[start:start + B]
+            idx = perm[start:start + B]
             mb = lr.stage_gather(mem, idx, compute_stats=False)
             lr.stage_forward_backward(mem, idx, mb, stats=self._mb_stats_all[2 * k:2 * k + 2])
             lr.stage_optimizer()
@@ -358,7 +361,7 @@ class PPOCLIP_Agent:
                 src = self._feeder.get(self._iteration, ep)
                 self._perm.copy_(src, non_blocking=True)           # H2D from pinned memory
                 self.h2d_bytes += src.numel() * 8
-            elif self.world_size > 1:                              # single rank: drawn inside the epoch graph
+            elif self.world_size > 1 and self.learner._peer is None:   # otherwise drawn inside the epoch graph
                 self._device_permutation()
             if self._epoch_graph is not None:
                 self._epoch_graph.replay()
@@ -379,7 +382,8 @@ class PPOCLIP_Agent:
         snap = self._snapshot()
         with torch.cuda.stream(s):
             self._rollout()
-            self._device_permutation()
+            if self.shuffle == "host" or (self.world_size > 1 and self.learner._peer is None):
+                self._device_permutation()                 # a valid permutation for the warm-up epoch
             if self.world_size > 1:
                 self._epoch_distributed()
             else:
@@ -390,13 +394,15 @@ class PPOCLIP_Agent:
         self._rollout_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._rollout_graph):
             self._rollout()
-        if self.world_size == 1 and self.shuffle == "host":
+        peer = self.learner._peer is not None
+        epoch = self._epoch_peer if peer else self._epoch_body
+        if (self.world_size == 1 or peer) and self.shuffle == "host":
             # one epoch graph per permutation buffer: the H2D copy of the next permutation overlaps the running epoch
             self._epoch_graphs = []
             for k in range(2):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._epoch_body(self._perm_bufs[k])
+                    epoch(self._perm_bufs[k])
                 self._epoch_graphs.append(g)
         elif self.world_size == 1:
             self._epoch_graph = torch.cuda.CUDAGraph()

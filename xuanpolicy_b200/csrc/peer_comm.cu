@@ -3,23 +3,23 @@
 //
 // One process per GPU.  Every rank owns one cudaMalloc'd "comm block" that its peers map through CUDA IPC:
 //
-//     [ flags  u32 [kPeerSlots][kPeerMaxRanks] | stats fp64 [kPeerStatsMax] | gradient fp32 [n] ]
+//     [ flags u32 [kPeerSlots][kPeerMaxRanks] | stats fp64 [kPeerStatsMax] | inbox fp32 [2][kPeerMaxRanks][n] ]
 //
-// The rank's backward kernels write the flat gradient straight into its own comm block.  Then
-//   * xb_peer_allreduce_grad_norm — ONE kernel: cross-GPU barrier, every rank loads all W gradients with P2P loads
-//     and sums them in rank order 0..W-1 (bit-identical sums on every rank, so the replicated Adam step stays
-//     bit-identical), writes the reduced gradient locally, accumulates its squared norm and, in the last block,
-//     derives the clip coefficient / learning rate / bias corrections (what grad_norm_kernel does for one GPU).
-//     It replaces  all_reduce(flat_grad) + clip_grad_norm_'s norm pass  (the sharded form of
-//     ppoclip_learner.py:47-49) — the collective IS the first pass of the optimiser.
+//   * xb_peer_allreduce_grad_norm — ONE kernel, ONE cross-GPU barrier per update: every CTA PUSHES its slice of the
+//     local flat gradient into inbox[parity][my rank] of every peer with posted P2P stores, signals, waits for the
+//     same slice from every rank, then sums the W inbox rows in rank order 0..W-1 out of LOCAL memory (bit-identical
+//     sums on every rank, so the replicated Adam step stays bit-identical), writes the reduced gradient, accumulates
+//     its squared norm and, in the last CTA, derives the clip coefficient / learning rate / bias corrections (what
+//     grad_norm_kernel does on one GPU).  It replaces  all_reduce(flat_grad) + the norm pass of clip_grad_norm_
+//     (the sharded form of ppoclip_learner.py:47-49): the collective IS the first pass of the optimiser.
+//     The inbox is double-buffered by launch parity, so no second barrier is needed: a peer can only overwrite
+//     inbox[p] two launches later, after a barrier that this rank enters only once it has finished reading inbox[p].
 //   * xb_peer_allreduce_f64 — the (sum adv, sum adv^2) of every minibatch of an epoch in one exchange
-//     (the sharded form of memory_tools.py:241-242), fed by xb_adv_stats_minibatches.
+//     (the sharded form of memory_tools.py:241-242), fed by xb_adv_stats_minibatches.  Pull-based, two barriers.
 //
 // Cross-GPU barrier (per CTA, no grid-wide sync): CTA b of rank r release-stores a monotonically increasing ticket
 // into flags[b][r] of every peer, then acquire-spins until its own flags[b][*] have reached the ticket.  Tickets
-// come from a per-CTA device counter, so a captured CUDA graph replays correctly.  A start barrier orders "all
-// ranks' gradients are complete" before the loads; an end barrier orders "all peers have read my gradient" before
-// the kernel (and with it the stream) lets the next backward overwrite it.
+// come from a per-CTA device counter, so a captured CUDA graph replays correctly.
 #include <cstring>
 
 #include "common.cuh"
@@ -78,22 +78,32 @@ struct AdamHyperP {  // same fields as optim.cu's AdamHyper
 constexpr int kPeerBlock = 512;
 
 // ws layout = optim.cu: [0] norm [1] clip [2] lr [3] bc1 [4] sqrt(bc2) [5] ticket bits, [8..) per-CTA partials.
-// tickets: u32 [kPeerSlots] local per-CTA barrier counters.
+// tickets: u32 [kPeerSlots] local per-CTA barrier counters (one tick per launch; its parity selects the inbox half).
 __global__ void __launch_bounds__(kPeerBlock)
-    peer_allreduce_grad_norm_kernel(PeerTable t, int rank, int W, int64_t n4, float* __restrict__ grad_out,
-                                    uint32_t* __restrict__ tickets, int64_t* __restrict__ step_dev, AdamHyperP h,
-                                    double* __restrict__ ws, float* __restrict__ lr_out, float* __restrict__ gnorm_out) {
+    peer_allreduce_grad_norm_kernel(PeerTable t, int rank, int W, int64_t n4, const float* __restrict__ grad_in,
+                                    float* __restrict__ grad_out, uint32_t* __restrict__ tickets,
+                                    int64_t* __restrict__ step_dev, AdamHyperP h, double* __restrict__ ws,
+                                    float* __restrict__ lr_out, float* __restrict__ gnorm_out) {
     __shared__ double smem[32];
     __shared__ bool is_last;
     const int slot = blockIdx.x;
     const uint32_t base_ticket = tickets[slot];          // read by every thread before thread 0 advances it below
-    peer_barrier(t, rank, W, slot, base_ticket + 1);     // every rank's gradient is complete and visible
+    const int64_t half = (int64_t)(base_ticket & 1u) * kPeerMaxRanks * n4;   // float4 offset of this launch's inbox half
+    const float4* in4 = reinterpret_cast<const float4*>(grad_in);
+    // push my slice into every rank's inbox row [rank] (own row included: a plain local store)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 g = in4[i];
+        for (int r = 0; r < W; ++r) reinterpret_cast<float4*>(t.base[r] + kPeerGradOff)[half + (int64_t)rank * n4 + i] = g;
+    }
+    peer_barrier(t, rank, W, slot, base_ticket + 1);     // every rank's slice has landed in my inbox
+    if (threadIdx.x == 0) tickets[slot] = base_ticket + 1;
+    const float4* box = reinterpret_cast<const float4*>(t.base[rank] + kPeerGradOff) + half;
     double acc[1] = {0.0};
     float4* out4 = reinterpret_cast<float4*>(grad_out);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        float4 s = ld_peer_f4(reinterpret_cast<const float4*>(t.base[0] + kPeerGradOff) + i);
+        float4 s = ld_peer_f4(box + i);                  // written by remote stores: bypass any stale L1 line
         for (int r = 1; r < W; ++r) {
-            const float4 g = ld_peer_f4(reinterpret_cast<const float4*>(t.base[r] + kPeerGradOff) + i);
+            const float4 g = ld_peer_f4(box + (int64_t)r * n4 + i);
             s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
         }
         out4[i] = s;
@@ -101,8 +111,6 @@ __global__ void __launch_bounds__(kPeerBlock)
         const double gz = (double)(s.z * h.grad_scale), gw = (double)(s.w * h.grad_scale);
         acc[0] += gx * gx + gy * gy + gz * gz + gw * gw;
     }
-    peer_barrier(t, rank, W, slot, base_ticket + 2);     // all peers have read my gradient: it may be overwritten
-    if (threadIdx.x == 0) tickets[slot] = base_ticket + 2;
     block_sum<1>(acc, smem);
     unsigned int* ticket = reinterpret_cast<unsigned int*>(ws + 5);
     if (threadIdx.x == 0) {
@@ -192,7 +200,7 @@ static int make_table(const void* const* bases, int rank, int W, PeerTable* t) {
 using namespace xb;
 
 extern "C" int64_t xb_peer_block_bytes(int64_t n_grad_floats) {
-    return kPeerGradOff + ((n_grad_floats + 3) / 4 * 4) * (int64_t)sizeof(float);
+    return kPeerGradOff + 2 * kPeerMaxRanks * ((n_grad_floats + 3) / 4 * 4) * (int64_t)sizeof(float);
 }
 extern "C" int64_t xb_peer_stats_offset(void) { return kPeerStatsOff; }
 extern "C" int64_t xb_peer_grad_offset(void) { return kPeerGradOff; }
@@ -228,19 +236,19 @@ extern "C" int xb_peer_close(void* ptr) {
 }
 
 extern "C" int xb_peer_allreduce_grad_norm(const void* const* peer_bases /* host [W] */, int rank, int W, int64_t n,
-                                           float* grad_out, uint32_t* tickets, int64_t* step_dev, float lr0,
+                                           const float* grad_in, float* grad_out, uint32_t* tickets, int64_t* step_dev, float lr0,
                                            float lr_end_factor, int64_t lr_total_iters, float beta1, float beta2,
                                            float eps, float max_norm, float grad_scale, double* workspace,
                                            float* lr_out, float* gnorm_out, xb_stream_t stream) {
     PeerTable t;
     int rc = make_table(peer_bases, rank, W, &t);
     if (rc) return rc;
-    if (n <= 0 || (n & 3) || !grad_out || !tickets || !step_dev || !workspace) return XB_E_BADARG;
+    if (n <= 0 || (n & 3) || !grad_in || !grad_out || !tickets || !step_dev || !workspace) return XB_E_BADARG;
     AdamHyperP h{lr0, lr_end_factor, beta1, beta2, eps, max_norm, grad_scale, lr_total_iters};
     const int64_t n4 = n / 4;
     int grid = (int)((n4 + kPeerBlock - 1) / kPeerBlock);
     if (grid > kPeerSlots - 1) grid = kPeerSlots - 1;
-    peer_allreduce_grad_norm_kernel<<<grid, kPeerBlock, 0, (cudaStream_t)stream>>>(t, rank, W, n4, grad_out, tickets, step_dev,
+    peer_allreduce_grad_norm_kernel<<<grid, kPeerBlock, 0, (cudaStream_t)stream>>>(t, rank, W, n4, grad_in, grad_out, tickets, step_dev,
                                                                                   h, workspace, lr_out, gnorm_out);
     XB_LAUNCH_CHECK();
     return 0;

@@ -79,10 +79,10 @@ class _DeviceMemory:
 class PeerComm:
     """One rank's side of the NVLink peer-memory exchange (csrc/peer_comm.cu, include/xb200.h section 5b).
 
-    Allocates this rank's comm block [barrier flags | minibatch statistics | flat gradient], exchanges CUDA IPC
-    handles through the process group and maps every peer's block.  `grad` (fp32 [n]) and `stats` (fp64) are torch
-    views INTO the block: the backward kernels write the gradient there, the peers read it with P2P loads inside
-    xb_peer_allreduce_grad_norm.  Single node only (IPC), world size <= 8."""
+    Allocates this rank's comm block [barrier flags | minibatch statistics | gradient inbox [2][8][n]], exchanges CUDA
+    IPC handles through the process group and maps every peer's block.  `stats` (fp64) is a torch view INTO the block;
+    the gradient inbox is only touched by xb_peer_allreduce_grad_norm (peers push their slices into it with P2P
+    stores).  Single node only (IPC), world size <= 8."""
 
     def __init__(self, n_grad_floats, device, group=None):
         from . import _lib
@@ -111,10 +111,8 @@ class PeerComm:
                     _lib.call("xb_peer_import", C.create_string_buffer(handles[r], 64), C.byref(p))
                     self._imported.append(p.value)
                     self.bases[r] = p.value
-            self._keep = (_DeviceMemory(self._own + lib.xb_peer_grad_offset(), self.n, "<f4"),
-                          _DeviceMemory(self._own + lib.xb_peer_stats_offset(), lib.xb_peer_stats_max(), "<f8"))
-            self.grad = torch.as_tensor(self._keep[0], device=self.device)
-            self.stats = torch.as_tensor(self._keep[1], device=self.device)
+            self._keep = _DeviceMemory(self._own + lib.xb_peer_stats_offset(), lib.xb_peer_stats_max(), "<f8")
+            self.stats = torch.as_tensor(self._keep, device=self.device)
             self.tickets = torch.zeros(64, dtype=torch.int32, device=self.device)
             torch.cuda.synchronize(self.device)
         dist.barrier(group)          # every rank has mapped every block before the first kernel touches one

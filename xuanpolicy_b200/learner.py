@@ -38,7 +38,7 @@ class FlatAdamState:
     Hyper-parameters are read from the torch optimizer / LinearLR scheduler the caller built
     (xuance/torch/runners/runner_drl.py:71-73)."""
 
-    def __init__(self, policy, optimizer, scheduler, grad_alloc=None):
+    def __init__(self, policy, optimizer, scheduler):
         params = [p for p in policy.parameters() if p.requires_grad]
         dev = params[0].device
         pad4 = lambda k: (k + 3) // 4 * 4          # every tensor starts 16-byte aligned (float4 epilogue kernels)
@@ -46,8 +46,7 @@ class FlatAdamState:
         self.n = n
         self.n_params = sum(p.numel() for p in params)
         self.flat_param = torch.zeros(n, dtype=torch.float32, device=dev)
-        # grad_alloc(n) -> fp32 [n]: lets the gradient live in peer-visible memory (dist.PeerComm) when env-sharded
-        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev) if grad_alloc is None else grad_alloc(n)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad_sum = None                        # peer mode: the cross-rank sum lands here (local memory)
         off = 0
         for p in params:
@@ -89,11 +88,11 @@ class FlatAdamState:
                 v.zero_()
 
     def apply_peer(self, peer, max_norm, grad_scale=1.0):
-        """Env-sharded step: ONE kernel sums the W ranks' gradients over NVLink peer memory and takes the norm of the sum
-        (csrc/peer_comm.cu), then the Adam kernel consumes the local copy of the sum."""
+        """Env-sharded step: ONE kernel pushes this rank's gradient to every peer over NVLink, sums the W gradients in rank
+        order and takes the norm of the sum (csrc/peer_comm.cu); the Adam kernel then consumes the sum."""
         if self.grad_sum is None:
             self.grad_sum = torch.zeros_like(self.flat_param)
-        ops.peer_allreduce_grad_norm(peer, self.grad_sum, peer.tickets, self.step, self.lr0, self.end_factor,
+        ops.peer_allreduce_grad_norm(peer, self.flat_grad, self.grad_sum, peer.tickets, self.step, self.lr0, self.end_factor,
                                      self.total_iters, self.beta1, self.beta2, self.eps, max_norm, grad_scale,
                                      self.workspace, lr_out=self.lr, gnorm_out=self.gnorm)
         ops.adam_apply(self.flat_param, self.grad_sum, self.exp_avg, self.exp_avg_sq, self.beta1, self.beta2, self.eps,
@@ -218,17 +217,16 @@ class PPOCLIP_Learner:
             self.process_group = process_group
             self.world_size = torch.distributed.get_world_size(process_group)
         if self._flat is None:
-            grad_alloc = None
+            self._flat = FlatAdamState(self.policy, self.optimizer, self.scheduler)
             if self.world_size > 1 and os.environ.get("XB_PEER_COMM", "1") != "0":
-                grad_alloc = self._peer_grad_alloc
-            self._flat = FlatAdamState(self.policy, self.optimizer, self.scheduler, grad_alloc)
+                self._open_peer_comm(self._flat.n)
             if self.use_fused_mlp and FusedActorCritic.plan(self.policy) is not None:
                 self._fused = FusedActorCritic(self.policy)
         return self._flat
 
-    def _peer_grad_alloc(self, n):
-        """The flat gradient inside this rank's NVLink-visible comm block (dist.PeerComm), so the peers sum it with P2P
-        loads.  Falls back to the NCCL all-reduce path (with a warning) when CUDA IPC is unavailable."""
+    def _open_peer_comm(self, n):
+        """This rank's NVLink-visible comm block (dist.PeerComm).  Falls back to the NCCL all-reduce path (with a
+        warning) when CUDA IPC is unavailable."""
         from .dist import PeerComm
         try:
             self._peer = PeerComm(n, self.device, self.process_group)
@@ -236,8 +234,6 @@ class PPOCLIP_Learner:
             import warnings
             warnings.warn("peer-memory exchange unavailable (%s); using NCCL all-reduces" % (e,))
             self._peer = None
-            return torch.zeros(n, dtype=torch.float32, device=self.device)
-        return self._peer.grad[:n]
 
     def _minibatch_buffers(self, B, obs_dim):
         key = (B, obs_dim)

@@ -202,10 +202,11 @@ def clip_adam_step(param, grad, exp_avg, exp_avg_sq, step_dev, lr0, lr_end_facto
               _stream())
 
 
-def peer_allreduce_grad_norm(peer, grad_out, tickets, step_dev, lr0, lr_end_factor, lr_total_iters, beta1, beta2, eps,
+def peer_allreduce_grad_norm(peer, grad_in, grad_out, tickets, step_dev, lr0, lr_end_factor, lr_total_iters, beta1, beta2, eps,
                              max_norm, grad_scale, workspace, lr_out=None, gnorm_out=None):
     """Cross-GPU gradient sum over peer memory fused with the gradient-norm pass (xb_peer_allreduce_grad_norm)."""
-    _lib.call("xb_peer_allreduce_grad_norm", peer.bases, peer.rank, peer.world, peer.n, _p(grad_out, F32), _p(tickets, I32),
+    _lib.call("xb_peer_allreduce_grad_norm", peer.bases, peer.rank, peer.world, peer.n, _p(grad_in, F32), _p(grad_out, F32),
+              _p(tickets, I32),
               _p(step_dev, I64), float(lr0), float(lr_end_factor), int(lr_total_iters), float(beta1), float(beta2),
               float(eps), float(max_norm), float(grad_scale), _p(workspace, F64), _p(lr_out, F32), _p(gnorm_out, F32),
               _stream())
