@@ -340,6 +340,16 @@ int xb_mlp_backward_tail(const float* wgrad_ws, int H_out, int H_in, int n_sourc
                          float* dw2_0, float* db2_0, float* dW1, float* db1, float* dw2_1, float* db2_1,
                          const float* trunk_ws, int trunk_parts, int obs_dim, float* dWt, float* dbt, const double* dls64,
                          float* dls32, int A, xb_stream_t stream);
+/* The same launch, additionally taking the global norm of the gradients it finishes (it finishes EVERY gradient of the
+ * policy, so trunk_ws is required) and deriving the clipped-Adam step scalars into norm_workspace exactly like the first
+ * kernel of xb_clip_adam_step (clip_grad_norm_ + LinearLR + bias corrections, ppoclip_learner.py:48-51): follow it with
+ * xb_adam_apply.  Saves the separate gradient-norm launch of every update. */
+int xb_mlp_backward_tail_norm(const float* wgrad_ws, int H_out, int H_in, int n_sources, int nh0, int nh1, float* dW0,
+                              float* db0, float* dw2_0, float* db2_0, float* dW1, float* db1, float* dw2_1, float* db2_1,
+                              const float* trunk_ws, int trunk_parts, int obs_dim, float* dWt, float* dbt,
+                              const double* dls64, float* dls32, int A, double* norm_workspace, int64_t* step_dev,
+                              float lr0, float lr_end_factor, int64_t lr_total_iters, float beta1, float beta2,
+                              float max_norm, float grad_scale, float* lr_out, float* gnorm_out, xb_stream_t stream);
 int xb_dense_wgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, const float* Y1, const float* dout1,
                    const float* w2_1, int nh1, const float* X, int64_t B, int H_out, int H_in, float slope,
                    float* workspace, float* dW0, float* db0, float* dw2_0, float* db2_0, float* dW1, float* db1,

@@ -10,67 +10,23 @@
 // Kernel 1 reduces sum((grad*grad_scale)^2) (per-block partials, last block finishes deterministically) and
 // derives the step scalars; kernel 2 applies clip + Adam element-wise.  Traffic: 4 B/param read in pass 1,
 // 16 B read + 12 B written per param in pass 2 (params are 9-133 K floats here: launch-latency bound).
-#include "common.cuh"
+#include "optim.cuh"
 
 namespace xb {
 
 constexpr int kOptBlock = 256;
-constexpr int kOptMaxGrid = 1024;
-
-// workspace layout (doubles): [0] grad norm, [1] clip coefficient, [2] lr, [3] bias_correction1,
-// [4] sqrt(bias_correction2), [5] ticket (as bits), [8 .. 8+kOptMaxGrid) partials
-struct AdamHyper {
-    float lr0, lr_end_factor, beta1, beta2, eps, max_norm, grad_scale;
-    int64_t lr_total_iters;
-};
 
 __global__ void __launch_bounds__(kOptBlock)
     grad_norm_kernel(const float* __restrict__ grad, int64_t n, int64_t* __restrict__ step_dev, AdamHyper h,
                      double* __restrict__ ws, float* __restrict__ lr_out, float* __restrict__ gnorm_out) {
     __shared__ double smem[32];
     __shared__ bool is_last;
-    double acc[1] = {0.0};
+    double sq = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double g = (double)(grad[i] * h.grad_scale);
-        acc[0] += g * g;
+        sq += g * g;
     }
-    block_sum<1>(acc, smem);
-    unsigned int* ticket = reinterpret_cast<unsigned int*>(ws + 5);
-    if (threadIdx.x == 0) {
-        ws[8 + blockIdx.x] = acc[0];
-        __threadfence();
-        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        double tot[1] = {0.0};
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) tot[0] += ws[8 + b];
-        block_sum<1>(tot, smem);
-        if (threadIdx.x == 0) {
-            const double norm = sqrt(tot[0]);
-            double clip = 1.0;
-            if (h.max_norm > 0.0f) {
-                clip = (double)h.max_norm / (norm + 1e-6);
-                if (clip > 1.0) clip = 1.0;
-            }
-            const int64_t it = *step_dev;  // updates done so far
-            const int64_t capped = it < h.lr_total_iters ? it : h.lr_total_iters;
-            double factor = 1.0;
-            if (h.lr_total_iters > 0) factor = 1.0 + ((double)h.lr_end_factor - 1.0) * (double)capped / (double)h.lr_total_iters;
-            const double lr = (double)h.lr0 * factor;
-            const double t = (double)(it + 1);
-            ws[0] = norm;
-            ws[1] = clip;
-            ws[2] = lr;
-            ws[3] = 1.0 - pow((double)h.beta1, t);
-            ws[4] = sqrt(1.0 - pow((double)h.beta2, t));
-            *step_dev = it + 1;
-            *ticket = 0u;
-            if (lr_out) *lr_out = (float)lr;
-            if (gnorm_out) *gnorm_out = (float)norm;
-        }
-    }
+    grad_norm_finish(sq, step_dev, h, ws, lr_out, gnorm_out, smem, &is_last);
 }
 
 __global__ void __launch_bounds__(kOptBlock)

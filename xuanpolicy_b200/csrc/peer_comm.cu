@@ -22,7 +22,7 @@
 // come from a per-CTA device counter, so a captured CUDA graph replays correctly.
 #include <cstring>
 
-#include "common.cuh"
+#include "optim.cuh"
 
 namespace xb {
 
@@ -70,11 +70,6 @@ __device__ __forceinline__ void peer_barrier(const PeerTable& t, int rank, int W
     __syncthreads();
 }
 
-struct AdamHyperP {  // same fields as optim.cu's AdamHyper
-    float lr0, lr_end_factor, beta1, beta2, eps, max_norm, grad_scale;
-    int64_t lr_total_iters;
-};
-
 constexpr int kPeerBlock = 512;
 
 // ws layout = optim.cu: [0] norm [1] clip [2] lr [3] bc1 [4] sqrt(bc2) [5] ticket bits, [8..) per-CTA partials.
@@ -82,7 +77,7 @@ constexpr int kPeerBlock = 512;
 __global__ void __launch_bounds__(kPeerBlock)
     peer_allreduce_grad_norm_kernel(PeerTable t, int rank, int W, int64_t n4, const float* __restrict__ grad_in,
                                     float* __restrict__ grad_out, uint32_t* __restrict__ tickets,
-                                    int64_t* __restrict__ step_dev, AdamHyperP h, double* __restrict__ ws,
+                                    int64_t* __restrict__ step_dev, AdamHyper h, double* __restrict__ ws,
                                     float* __restrict__ lr_out, float* __restrict__ gnorm_out) {
     __shared__ double smem[32];
     __shared__ bool is_last;
@@ -111,43 +106,7 @@ __global__ void __launch_bounds__(kPeerBlock)
         const double gz = (double)(s.z * h.grad_scale), gw = (double)(s.w * h.grad_scale);
         acc[0] += gx * gx + gy * gy + gz * gz + gw * gw;
     }
-    block_sum<1>(acc, smem);
-    unsigned int* ticket = reinterpret_cast<unsigned int*>(ws + 5);
-    if (threadIdx.x == 0) {
-        ws[8 + blockIdx.x] = acc[0];
-        __threadfence();
-        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        double tot[1] = {0.0};
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) tot[0] += ws[8 + b];
-        block_sum<1>(tot, smem);
-        if (threadIdx.x == 0) {
-            const double norm = sqrt(tot[0]);
-            double clip = 1.0;
-            if (h.max_norm > 0.0f) {
-                clip = (double)h.max_norm / (norm + 1e-6);
-                if (clip > 1.0) clip = 1.0;
-            }
-            const int64_t it = *step_dev;
-            const int64_t capped = it < h.lr_total_iters ? it : h.lr_total_iters;
-            double factor = 1.0;
-            if (h.lr_total_iters > 0) factor = 1.0 + ((double)h.lr_end_factor - 1.0) * (double)capped / (double)h.lr_total_iters;
-            const double lr = (double)h.lr0 * factor;
-            const double tt = (double)(it + 1);
-            ws[0] = norm;
-            ws[1] = clip;
-            ws[2] = lr;
-            ws[3] = 1.0 - pow((double)h.beta1, tt);
-            ws[4] = sqrt(1.0 - pow((double)h.beta2, tt));
-            *step_dev = it + 1;
-            *ticket = 0u;
-            if (lr_out) *lr_out = (float)lr;
-            if (gnorm_out) *gnorm_out = (float)norm;
-        }
-    }
+    grad_norm_finish(acc[0], step_dev, h, ws, lr_out, gnorm_out, smem, &is_last);
 }
 
 // out[j] = sum over ranks (rank order) of the peers' stats[j], j < n <= kPeerStatsMax.  One CTA, the last flag slot.
@@ -244,7 +203,7 @@ extern "C" int xb_peer_allreduce_grad_norm(const void* const* peer_bases /* host
     int rc = make_table(peer_bases, rank, W, &t);
     if (rc) return rc;
     if (n <= 0 || (n & 3) || !grad_in || !grad_out || !tickets || !step_dev || !workspace) return XB_E_BADARG;
-    AdamHyperP h{lr0, lr_end_factor, beta1, beta2, eps, max_norm, grad_scale, lr_total_iters};
+    AdamHyper h{lr0, lr_end_factor, beta1, beta2, eps, max_norm, grad_scale, lr_total_iters};
     const int64_t n4 = n / 4;
     int grid = (int)((n4 + kPeerBlock - 1) / kPeerBlock);
     if (grid > kPeerSlots - 1) grid = kPeerSlots - 1;

@@ -88,6 +88,8 @@ class FusedActorCritic:
         self.ws_trunk = ops.mlp_trunk_wgrad_workspace(self.obs_dim, H, dev)
         self._buf = {}
         self._last = None
+        # (FlatAdamState, max_norm) when the learner wants the gradient norm + Adam scalars out of the tail launch
+        self.norm_sink, self.norm_done = None, False
 
     # every tensor below is read at launch time: parameters may have been re-pointed (FlatAdamState) since __init__
     def refresh_weights(self):
@@ -125,12 +127,19 @@ class FusedActorCritic:
         ops.mlp_trunk_wgrad(b["dz1"], obs, self.ws_trunk, None, None)
 
     def stage_tail(self, dls64=None, dls32=None):
-        """One launch: all partial sums -> the ten Linear gradients (+ the loss kernel's fp64 log-std gradient -> fp32)."""
+        """One launch: all partial sums -> the ten Linear gradients (+ the loss kernel's fp64 log-std gradient -> fp32)
+        and, when `norm_sink` is armed, their global norm + the clipped-Adam step scalars (optim workspace)."""
         g = lambda p: p.grad
+        norm, self.norm_done = None, False
+        if self.norm_sink is not None and (not self.gaussian or dls64 is not None):   # every gradient passes through here
+            fl, max_norm = self.norm_sink
+            norm = (fl.workspace, fl.step, fl.lr0, fl.end_factor, fl.total_iters, fl.beta1, fl.beta2, max_norm, 1.0, fl.lr,
+                    fl.gnorm)
+            self.norm_done = True
         ops.mlp_backward_tail(self.ws_wgrad, self.H, self.H, self.la2.weight.shape[0], 1,
                               (g(self.la1.weight), g(self.la1.bias), g(self.la2.weight), g(self.la2.bias)),
                               (g(self.lc1.weight), g(self.lc1.bias), g(self.lc2.weight), g(self.lc2.bias)),
-                              self.ws_trunk, self.obs_dim, g(self.l0.weight), g(self.l0.bias), dls64, dls32)
+                              self.ws_trunk, self.obs_dim, g(self.l0.weight), g(self.l0.bias), dls64, dls32, norm=norm)
 
     def forward_inference(self, obs):
         """Rollout forward (no activations kept): trunk + both hidden layers + heads in ONE launch for obs_dim <= 4,

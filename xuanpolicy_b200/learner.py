@@ -261,6 +261,12 @@ class PPOCLIP_Learner:
         `stats` (fp64 [2], optional): the GLOBAL-minibatch (sum adv, sum adv^2) when the caller exchanged them itself."""
         B = idx.numel()
         fused = self._fused if (self._fused is not None and B >= FusedActorCritic.MIN_ROWS) else None
+        if self._fused is not None:
+            # single rank: the tail launch of the fused backward also takes the gradient norm (stage_optimizer then only
+            # applies Adam); env-sharded, the norm belongs to the cross-rank sum and is taken by the peer kernel instead
+            single = self.world_size == 1 and os.environ.get("XB_TAIL_NORM", "1") != "0"
+            self._fused.norm_sink = (self._flat, self.clip_grad_norm if self.use_grad_clip else 0.0) if (fused is not None and single) else None
+            self._fused.norm_done = False
         if fused is not None:                        # tcgen05 dense kernels; weights re-split after every Adam step
             act_out, v_pred = fused.forward(mb["obs"], refresh=True)
             a_dist = fused.dist_params(act_out)
@@ -282,6 +288,10 @@ class PPOCLIP_Learner:
         max_norm = self.clip_grad_norm if self.use_grad_clip else 0.0
         if self._peer is not None:
             self._flat.apply_peer(self._peer, max_norm, 1.0)
+        elif self._fused is not None and self._fused.norm_done:     # norm + step scalars came out of the backward tail launch
+            fl = self._flat
+            ops.adam_apply(fl.flat_param, fl.flat_grad, fl.exp_avg, fl.exp_avg_sq, fl.beta1, fl.beta2, fl.eps, 1.0, fl.workspace)
+            self._fused.norm_done = False
         else:
             self._flat.apply(max_norm, 1.0)
 

@@ -357,10 +357,20 @@ def mlp_trunk_wgrad(dz1, obs, workspace, dw0, db0):
               obs.shape[0], dz1.shape[1], _stream())
 
 
-def mlp_backward_tail(wgrad_ws, h_out, h_in, nh0, nh1, grads0, grads1, trunk_ws, obs_dim, dwt, dbt, dls64=None, dls32=None):
-    """grads0/grads1 = (dW, db, dw2, db2) of the actor / critic; finishes xb_dense_wgrad + xb_mlp_trunk_wgrad partials."""
+def mlp_backward_tail(wgrad_ws, h_out, h_in, nh0, nh1, grads0, grads1, trunk_ws, obs_dim, dwt, dbt, dls64=None, dls32=None,
+                      norm=None):
+    """grads0/grads1 = (dW, db, dw2, db2) of the actor / critic; finishes xb_dense_wgrad + xb_mlp_trunk_wgrad partials.
+    norm = (workspace, step_dev, lr0, lr_end_factor, lr_total_iters, beta1, beta2, max_norm, grad_scale, lr_out, gnorm_out):
+    also take the global gradient norm and derive the clipped-Adam scalars in the same launch."""
     parts = _lib.load().xb_mlp_trunk_wgrad_parts()
-    _lib.call("xb_mlp_backward_tail", _p(wgrad_ws, F32), h_out, h_in, 2 if grads1 is not None else 1, nh0, nh1,
-              *[_p(g, F32) for g in grads0], *([_p(g, F32) for g in grads1] if grads1 is not None else [None] * 4),
-              _p(trunk_ws, F32), parts, obs_dim, _p(dwt, F32), _p(dbt, F32), _p(dls64, F64), _p(dls32, F32),
-              dls64.numel() if dls64 is not None else 0, _stream())
+    args = [_p(wgrad_ws, F32), h_out, h_in, 2 if grads1 is not None else 1, nh0, nh1,
+            *[_p(g, F32) for g in grads0], *([_p(g, F32) for g in grads1] if grads1 is not None else [None] * 4),
+            _p(trunk_ws, F32), parts, obs_dim, _p(dwt, F32), _p(dbt, F32), _p(dls64, F64), _p(dls32, F32),
+            dls64.numel() if dls64 is not None else 0]
+    if norm is None:
+        _lib.call("xb_mlp_backward_tail", *args, _stream())
+    else:
+        ws, step_dev, lr0, end_factor, total_iters, beta1, beta2, max_norm, grad_scale, lr_out, gnorm_out = norm
+        _lib.call("xb_mlp_backward_tail_norm", *args, _p(ws, F64), _p(step_dev, I64), float(lr0), float(end_factor),
+                  int(total_iters), float(beta1), float(beta2), float(max_norm), float(grad_scale), _p(lr_out, F32),
+                  _p(gnorm_out, F32), _stream())
