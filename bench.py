@@ -179,7 +179,8 @@ def count_launches(agent):
         per_rollout = 1 + T * (2 if agent._fused_step else 4) + 1 + 2 + 1   # split; per step forward + fused step; bootstrap fwd
         # update: gather, weight split, trunk, hidden, loss, dgrad, wgrad, trunk wgrad, tail (all reduces), grad-norm, adam
         tail_norm = agent.world_size == 1 and os.environ.get("XB_TAIL_NORM", "1") != "0"   # norm taken by the tail launch
-        per_update = 1 + 1 + 1 + 1 + 1 + 1 + 1 + 1 + 1 + (1 if tail_norm else 2)
+        adam_split = os.environ.get("XB_ADAM_SPLIT", "1") != "0"                          # weight split done by the Adam launch
+        per_update = 1 + (0 if adam_split else 1) + 1 + 1 + 1 + 1 + 1 + 1 + 1 + (1 if tail_norm else 2)
     else:
         per_rollout = T * (3 + 5) + 5 + 2 + 1  # per step: sample, env_step, store, 3 bias+act, 2 head; bootstrap fwd; GAE + pack; counter
         per_update = 1 + 1 + 2 + 5 + 3         # gather, loss, grad-norm + adam, fwd: 3 bias+act + 2 head, bwd: 2 head+act + 1 act+bias

@@ -426,6 +426,13 @@ int xb_peer_allreduce_grad_norm(const void* const* peer_bases /* host [W] */, in
                                 float grad_scale, double* workspace, float* lr_out, float* gnorm_out, xb_stream_t stream);
 int xb_adam_apply(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float beta1, float beta2,
                   float eps, float grad_scale, const double* workspace, xb_stream_t stream);
+/* xb_adam_apply fused with xb_dense_split_weights2: the two H x H hidden-layer weights W_s = param + w_off_s ([N][K]) get
+ * their tf32 hi/lo operand copies (and the transposed, concatenated dgrad operand thi/tlo [K][2N]) rewritten by the same
+ * threads that update them, so no separate split launch is needed before the next forward. */
+int xb_adam_apply_split(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float beta1,
+                        float beta2, float eps, float grad_scale, const double* workspace, int64_t w_off0, float* hi0,
+                        float* lo0, int64_t w_off1, float* hi1, float* lo1, int N, int K, float* thi, float* tlo,
+                        xb_stream_t stream);
 int xb_peer_allreduce_f64(const void* const* peer_bases /* host [W] */, int rank, int W, int n, double* out,
                           uint32_t* tickets, xb_stream_t stream);
 int xb_adv_stats_minibatches(const int64_t* idx, int64_t n_minibatches, int64_t B, int64_t T, int64_t N, const float* adv,

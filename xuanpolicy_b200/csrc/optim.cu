@@ -48,6 +48,60 @@ __global__ void __launch_bounds__(kOptBlock)
     }
 }
 
+// adam_apply + the tf32 hi/lo operand split of the two H x H hidden-layer weights (dense_tc.cu split_weights_kernel) in one
+// launch: the split of an updated weight is written right where the weight is updated, so the next forward / dgrad find
+// their 3xTF32 operands ready and the per-update split launch disappears.
+struct AdamSplit {
+    int64_t off[2];   // element offset of W_s [N][K] inside the flat parameter buffer
+    float* hi[2];
+    float* lo[2];
+    int toff[2];      // column offset inside the transposed, concatenated operand
+    float* thi;
+    float* tlo;
+    int N, K, ldt;
+};
+
+__device__ __forceinline__ void split_tf32_opt(float x, float& hi, float& lo) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    lo = x - hi;
+}
+
+__global__ void __launch_bounds__(kOptBlock)
+    adam_apply_split_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ exp_avg,
+                            float* __restrict__ exp_avg_sq, int64_t n, AdamHyper h, const double* __restrict__ ws, AdamSplit sp) {
+    const float gscale = h.grad_scale * (float)ws[1];
+    const float step_size = (float)(ws[2] / ws[3]);
+    const float bc2_sqrt = (float)ws[4];
+    const float b1 = h.beta1, b2 = h.beta2, eps = h.eps;
+    const int64_t nk = (int64_t)sp.N * sp.K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float g = grad[i] * gscale;
+        float m = exp_avg[i], v = exp_avg_sq[i];
+        m = m + (g - m) * (1.0f - b1);
+        v = v * b2 + (1.0f - b2) * g * g;
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        const float p = param[i] - step_size * (m / denom);
+        param[i] = p;
+        exp_avg[i] = m;
+        exp_avg_sq[i] = v;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int64_t j = i - sp.off[s];
+            if (j >= 0 && j < nk) {
+                float hi, lo;
+                split_tf32_opt(p, hi, lo);
+                sp.hi[s][j] = hi;
+                sp.lo[s][j] = lo;
+                const int row = (int)(j / sp.K), k = (int)(j - (int64_t)row * sp.K);
+                sp.thi[(int64_t)k * sp.ldt + sp.toff[s] + row] = hi;
+                sp.tlo[(int64_t)k * sp.ldt + sp.toff[s] + row] = lo;
+            }
+        }
+    }
+}
+
 }  // namespace xb
 
 using namespace xb;
@@ -75,6 +129,22 @@ extern "C" int xb_adam_apply(float* param, const float* grad, float* exp_avg, fl
     int grid = grid_for(n, kOptBlock, 4);
     if (grid > kOptMaxGrid) grid = kOptMaxGrid;
     adam_apply_kernel<<<grid, kOptBlock, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, h, workspace);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_adam_apply_split(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float beta1,
+                                   float beta2, float eps, float grad_scale, const double* workspace, int64_t w_off0,
+                                   float* hi0, float* lo0, int64_t w_off1, float* hi1, float* lo1, int N, int K, float* thi,
+                                   float* tlo, xb_stream_t stream) {
+    if (n <= 0 || !param || !grad || !exp_avg || !exp_avg_sq || !workspace) return XB_E_BADARG;
+    if (!hi0 || !lo0 || !hi1 || !lo1 || !thi || !tlo || N <= 0 || K <= 0) return XB_E_BADARG;
+    if (w_off0 < 0 || w_off1 < 0 || w_off0 + (int64_t)N * K > n || w_off1 + (int64_t)N * K > n) return XB_E_BADARG;
+    AdamHyper h{0.0f, 0.0f, beta1, beta2, eps, 0.0f, grad_scale, 0};
+    AdamSplit sp{{w_off0, w_off1}, {hi0, hi1}, {lo0, lo1}, {0, N}, thi, tlo, N, K, 2 * N};
+    int grid = grid_for(n, kOptBlock, 4);
+    if (grid > kOptMaxGrid) grid = kOptMaxGrid;
+    adam_apply_split_kernel<<<grid, kOptBlock, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, h, workspace, sp);
     XB_LAUNCH_CHECK();
     return 0;
 }

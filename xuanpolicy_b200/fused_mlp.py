@@ -90,9 +90,12 @@ class FusedActorCritic:
         self._last = None
         # (FlatAdamState, max_norm) when the learner wants the gradient norm + Adam scalars out of the tail launch
         self.norm_sink, self.norm_done = None, False
+        # True while the hi/lo operand copies are known to match the weights (the Adam launch rewrote them)
+        self.splits_fresh = False
 
     # every tensor below is read at launch time: parameters may have been re-pointed (FlatAdamState) since __init__
     def refresh_weights(self):
+        self.splits_fresh = True
         ops.dense_split_weights2(self.la1.weight.data, self.wa_hi, self.wa_lo, self.lc1.weight.data, self.wc_hi, self.wc_lo,
                                  self.wt_hi, self.wt_lo)
 

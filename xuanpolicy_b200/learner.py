@@ -87,7 +87,20 @@ class FlatAdamState:
             if g is None:
                 v.zero_()
 
-    def apply_peer(self, peer, max_norm, grad_scale=1.0):
+    def adam(self, grad, fused=None, grad_scale=1.0):
+        """Second pass of the step (scalars already in `workspace`).  With the tensor-core MLP active the same launch
+        rewrites the tf32 hi/lo operand copies of the two hidden-layer weights (`fused.splits_fresh` tells the next
+        forward that no separate split launch is needed)."""
+        if fused is not None and fused.la1.weight.data_ptr() >= self.flat_param.data_ptr():
+            ops.adam_apply_split(self.flat_param, grad, self.exp_avg, self.exp_avg_sq, self.beta1, self.beta2, self.eps,
+                                 grad_scale, self.workspace, fused.la1.weight.data, fused.wa_hi, fused.wa_lo,
+                                 fused.lc1.weight.data, fused.wc_hi, fused.wc_lo, fused.wt_hi, fused.wt_lo)
+            fused.splits_fresh = True
+        else:
+            ops.adam_apply(self.flat_param, grad, self.exp_avg, self.exp_avg_sq, self.beta1, self.beta2, self.eps,
+                           grad_scale, self.workspace)
+
+    def apply_peer(self, peer, max_norm, grad_scale=1.0, fused=None):
         """Env-sharded step: ONE kernel pushes this rank's gradient to every peer over NVLink, sums the W gradients in rank
         order and takes the norm of the sum (csrc/peer_comm.cu); the Adam kernel then consumes the sum."""
         if self.grad_sum is None:
@@ -95,8 +108,7 @@ class FlatAdamState:
         ops.peer_allreduce_grad_norm(peer, self.flat_grad, self.grad_sum, peer.tickets, self.step, self.lr0, self.end_factor,
                                      self.total_iters, self.beta1, self.beta2, self.eps, max_norm, grad_scale,
                                      self.workspace, lr_out=self.lr, gnorm_out=self.gnorm)
-        ops.adam_apply(self.flat_param, self.grad_sum, self.exp_avg, self.exp_avg_sq, self.beta1, self.beta2, self.eps,
-                       grad_scale, self.workspace)
+        self.adam(self.grad_sum, fused, grad_scale)
 
     def apply(self, max_norm, grad_scale=1.0):
         ops.clip_adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step, self.lr0,
@@ -136,6 +148,8 @@ class PPOCLIP_Learner:
         names = sorted(n for n in os.listdir(path) if n != "obs_rms.npy")
         state = torch.load(os.path.join(path, names[-1]), map_location=self.device)
         self.policy.load_state_dict(state)
+        if self._fused is not None:
+            self._fused.splits_fresh = False      # the tf32 operand copies no longer match the weights
 
     # ---------------------------------------------------------------------------------------------- loss kernel
     def _loss_backward(self, a_dist, v_pred, act, ret, adv, old_logp, val_old, inv_batch, idx=None, T=0, N=0,
@@ -268,7 +282,7 @@ class PPOCLIP_Learner:
             self._fused.norm_sink = (self._flat, self.clip_grad_norm if self.use_grad_clip else 0.0) if (fused is not None and single) else None
             self._fused.norm_done = False
         if fused is not None:                        # tcgen05 dense kernels; weights re-split after every Adam step
-            act_out, v_pred = fused.forward(mb["obs"], refresh=True)
+            act_out, v_pred = fused.forward(mb["obs"], refresh=not fused.splits_fresh)
             a_dist = fused.dist_params(act_out)
         else:
             _, a_dist, v_pred = self.policy(mb["obs"])
@@ -286,14 +300,16 @@ class PPOCLIP_Learner:
         """Stage 3: global-norm clip + Adam + LinearLR on the flat buffers (one fused device step).  Env-sharded over peer
         memory, the gradient exchange happens INSIDE this stage (fused with the norm pass)."""
         max_norm = self.clip_grad_norm if self.use_grad_clip else 0.0
+        fused = self._fused if (self._fused is not None and os.environ.get("XB_ADAM_SPLIT", "1") != "0") else None
         if self._peer is not None:
-            self._flat.apply_peer(self._peer, max_norm, 1.0)
+            self._flat.apply_peer(self._peer, max_norm, 1.0, fused)
         elif self._fused is not None and self._fused.norm_done:     # norm + step scalars came out of the backward tail launch
-            fl = self._flat
-            ops.adam_apply(fl.flat_param, fl.flat_grad, fl.exp_avg, fl.exp_avg_sq, fl.beta1, fl.beta2, fl.eps, 1.0, fl.workspace)
+            self._flat.adam(self._flat.flat_grad, fused, 1.0)
             self._fused.norm_done = False
         else:
             self._flat.apply(max_norm, 1.0)
+            if self._fused is not None:
+                self._fused.splits_fresh = False
 
     def update_from_buffer(self, memory, idx):
         """One PPO-Clip SGD step on the minibatch `idx` (CUDA int64 flat indices) of a native buffer.

@@ -217,6 +217,16 @@ def adam_apply(param, grad, exp_avg, exp_avg_sq, beta1, beta2, eps, grad_scale, 
               float(beta1), float(beta2), float(eps), float(grad_scale), _p(workspace, F64), _stream())
 
 
+def adam_apply_split(param, grad, exp_avg, exp_avg_sq, beta1, beta2, eps, grad_scale, workspace, w0, hi0, lo0, w1, hi1, lo1,
+                     thi, tlo):
+    """Adam step + the tf32 operand split of the hidden-layer weights w0 / w1 (views INTO `param`) in one launch."""
+    N, K = w0.shape
+    off = lambda w: (w.data_ptr() - param.data_ptr()) // 4
+    _lib.call("xb_adam_apply_split", _p(param, F32), _p(grad, F32), _p(exp_avg, F32), _p(exp_avg_sq, F32), param.numel(),
+              float(beta1), float(beta2), float(eps), float(grad_scale), _p(workspace, F64), off(w0), _p(hi0, F32),
+              _p(lo0, F32), off(w1), _p(hi1, F32), _p(lo1, F32), N, K, _p(thi, F32), _p(tlo, F32), _stream())
+
+
 def peer_allreduce_f64(peer, n, out):
     """out[:n] = sum over ranks of the first n doubles of each rank's comm-block statistics."""
     _lib.call("xb_peer_allreduce_f64", peer.bases, peer.rank, peer.world, int(n), _p(out, F64), _p(peer.tickets, I32),
