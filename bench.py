@@ -254,7 +254,8 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
                 env._kind, act_param, logstd, v0[:N], agent.seed, agent._ctr, 0, env._state, env._rng, env._elapsed,
                 env._ep_score, x_nxt[N:], x_nxt[:N], env._rew, env._term, env._trunc, env._reset_obs, env._ep_step_out,
                 env._ep_score_out, env.ep_stats, env.max_episode_length, x_cur[:N], agent._act, agent._logp, mem._obs[0],
-                mem._act[0], mem._rew[0], mem._val[0], mem._term[0], mem._trunc[0], mem._logp[0]),
+                mem._act[0], mem._rew[0], mem._val[0], mem._term[0], mem._trunc[0], mem._logp[0],
+                boot_src=v0[N:], boot_row=mem._boot[0], trig_cache=agent._trig_cache),
                 env_bytes + N * ((4 + 4 + 4) if gauss else (8 + 8 + 4)) + N * 36, T)
         agent._restore(snap)
         agent._cur = cur

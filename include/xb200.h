@@ -287,6 +287,9 @@ int xb_bias_act_fwd(float* y, const float* bias, float slope, int64_t B, int H, 
  * boot_src / boot_row (nullable pair, f32 [N]): V(terminal observation of the PREVIOUS step) copied into the previous
  * rollout row's bootstrap values — the value the reference obtains with a full-batch forward per finished env
  * (ppoclip_agent.py:98-100) — so the step needs no separate copy launch.
+ * trig_cache (nullable, fp64 [3][N], initialise the first row to NaN): Pendulum's observation (cos, sin of the new theta)
+ * is the next step's dynamics input; the row (theta, sin, cos) is reused when its key equals the current theta bit for
+ * bit, recomputed otherwise — the values are identical either way (correctly-rounded pure functions of theta).
  * ---------------------------------------------------------------------------------------------------------- */
 int xb_rollout_step(int env_kind, const float* act_param, const float* logstd, const float* val, uint64_t seed,
                     const uint64_t* counter_dev, uint64_t offset, double* state, uint64_t* rng, int32_t* elapsed,
@@ -294,8 +297,8 @@ int xb_rollout_step(int env_kind, const float* act_param, const float* logstd, c
                     float* reset_obs, int32_t* ep_step_out, double* ep_score_out, double* ep_stats,
                     int max_episode_steps, const float* x_in, void* act_out, float* logp_out, float* obs_row,
                     float* act_row, float* rew_row, float* val_row, float* term_row, uint8_t* trunc_row, float* logp_row,
-                    const float* rew_scale, float rew_clip, const float* boot_src, float* boot_row, int64_t N,
-                    xb_stream_t stream);
+                    const float* rew_scale, float rew_clip, const float* boot_src, float* boot_row, double* trig_cache,
+                    int64_t N, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Dense layers of the policy/value MLP at large batch on the tcgen05 tensor cores with fp32-level accuracy

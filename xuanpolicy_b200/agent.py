@@ -106,6 +106,8 @@ class PPOCLIP_Agent:
                                 dtype=torch.int64 if self.discrete else torch.float32, device=dev)
         self._logp = torch.zeros(N, dtype=torch.float32, device=dev)
         self._boot_last = torch.zeros(N, dtype=torch.float32, device=dev)
+        # (theta, sin, cos) of the last observation per env, keyed by theta (NaN = empty): see xb_rollout_step
+        self._trig_cache = torch.full((3, N), float("nan"), dtype=torch.float64, device=dev)
         self._ctr = torch.zeros(1, dtype=torch.int64, device=dev)
         self._perm = torch.zeros(self.buffer_size, dtype=torch.int64, device=dev)
         self._perm_ctr = torch.zeros(1, dtype=torch.int64, device=dev)      # one tick per drawn device permutation
@@ -203,7 +205,8 @@ class PPOCLIP_Agent:
                              x_in[:N], self._act, self._logp, mem._obs[t], mem._act[t], mem._rew[t], mem._val[t],
                              mem._term[t], mem._trunc[t], mem._logp[t],
                              rew_std=self._rew_std if self.use_rewnorm else None, rew_clip=self.rewnorm_range,
-                             boot_src=v[N:] if t > 0 else None, boot_row=mem._boot[t - 1] if t > 0 else None)
+                             boot_src=v[N:] if t > 0 else None, boot_row=mem._boot[t - 1] if t > 0 else None,
+                             trig_cache=self._trig_cache)
         else:
             self._sample(dist, t)
             ops.env_step(env._kind, env._state, env._rng, env._elapsed, env._ep_score, self._act.reshape(N),

@@ -46,6 +46,7 @@ constexpr double kPi = 3.141592653589793;
 
 // ---------------------------------------------------------------- per-env dynamics ---------------------------
 struct CartPole {
+    static constexpr bool kTrigCache = false;
     static constexpr int S = 4;
     typedef int64_t action_t;
     static constexpr bool kDiscrete = true;
@@ -83,6 +84,7 @@ struct CartPole {
 };
 
 struct Pendulum {
+    static constexpr bool kTrigCache = true;   // sin/cos(theta) of the observation are the next step's dynamics inputs
     static constexpr int S = 2;
     typedef float action_t;
     static constexpr bool kDiscrete = false;
@@ -91,10 +93,13 @@ struct Pendulum {
         st[0] = pcg64_uniform(g, -kPi, kPi - (-kPi));
         st[1] = pcg64_uniform(g, -1.0, 1.0 - (-1.0));
     }
+    __device__ static float4 observe_sc(const double (&st)[2], double s, double c) {   // s, c = sin, cos of st[0]
+        return make_float4((float)c, (float)s, (float)st[1], 0.0f);
+    }
     __device__ static float4 observe(const double (&st)[2]) {
         double s, c;
         sincos_cr(st[0], &s, &c);
-        return make_float4((float)c, (float)s, (float)st[1], 0.0f);
+        return observe_sc(st, s, c);
     }
     __device__ static double angle_normalize(double x) {
         const double two_pi = 2 * kPi;
@@ -107,6 +112,12 @@ struct Pendulum {
         return __dsub_rn(r, kPi);
     }
     __device__ static double step(double (&st)[2], action_t action, bool& terminated) {
+        double s, c;
+        sincos_cr(st[0], &s, &c);
+        return step_sc(st, action, terminated, s);
+    }
+    // the same step with sin(theta) supplied by the caller (the previous step's observation already evaluated it)
+    __device__ static double step_sc(double (&st)[2], action_t action, bool& terminated, double s) {
         const double dt = 0.05;
         double th = st[0], thdot = st[1];
         float u32 = action < -2.0f ? -2.0f : (action > 2.0f ? 2.0f : action);
@@ -114,8 +125,6 @@ struct Pendulum {
         double an = angle_normalize(th);
         double costs = __dadd_rn(__dadd_rn(__dmul_rn(an, an), __dmul_rn(0.1, __dmul_rn(thdot, thdot))),
                                  __dmul_rn(0.001, __dmul_rn(u, u)));
-        double s, c;
-        sincos_cr(th, &s, &c);
         double newthdot = __dadd_rn(thdot, __dmul_rn(__dadd_rn(__dmul_rn(15.0, s), __dmul_rn(3.0, u)), dt));
         newthdot = newthdot < -8.0 ? -8.0 : (newthdot > 8.0 ? 8.0 : newthdot);
         double newth = __dadd_rn(th, __dmul_rn(newthdot, dt));
@@ -134,6 +143,7 @@ struct Pendulum {
 //   terminated = position >= goal_position and velocity >= goal_velocity; reward = -1.0
 // reset(): state = [uniform(-0.6, -0.4), 0].
 struct MountainCar {
+    static constexpr bool kTrigCache = false;
     static constexpr int S = 2;
     typedef int64_t action_t;
     static constexpr bool kDiscrete = true;
@@ -284,6 +294,10 @@ struct RolloutStepArgs {
     // nullable pair: V(terminal obs of the previous step) [N] -> the previous rollout row's bootstrap values
     const float* boot_src;
     float* boot_row;
+    // nullable, fp64 [3][N]: (theta, sin theta, cos theta) of the last observation this kernel produced.  sin/cos are pure
+    // functions of theta, so a row is used only when its key equals the current theta bit for bit — a stale or
+    // never-written row (key NaN) just means the values are recomputed.  Halves the correctly-rounded trig work of Pendulum.
+    double* trig_cache;
     int64_t N;
 };
 
@@ -319,11 +333,26 @@ __global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs
     int32_t el = a.elapsed[e];
     double score = a.ep_score[e];
     bool terminated;
-    const double reward = Env::step(st, act, terminated);
+    double reward;
+    float4 o;
+    double sc_s = 0.0, sc_c = 0.0;
+    if constexpr (Env::kTrigCache) {
+        bool hit = false;
+        if (a.trig_cache && a.trig_cache[e] == st[0]) {
+            sc_s = a.trig_cache[N + e];
+            hit = true;
+        }
+        if (!hit) sincos_cr(st[0], &sc_s, &sc_c);
+        reward = Env::step_sc(st, act, terminated, sc_s);
+        sincos_cr(st[0], &sc_s, &sc_c);            // of the NEW theta: this step's observation, the next step's dynamics
+        o = Env::observe_sc(st, sc_s, sc_c);
+    } else {
+        reward = Env::step(st, act, terminated);
+        o = Env::observe(st);
+    }
     el += 1;
     const bool truncated = el >= a.max_steps;
     score = __dadd_rn(score, reward);
-    float4 o = Env::observe(st);
     a.obs[e] = o;
     const float r32 = (float)reward;
     a.rew[e] = r32;
@@ -343,10 +372,22 @@ __global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs
         a.rng[N + e] = g.lo;
         el = 0;
         score = 0.0;
-        o = Env::observe(st);
+        if constexpr (Env::kTrigCache) {
+            sincos_cr(st[0], &sc_s, &sc_c);
+            o = Env::observe_sc(st, sc_s, sc_c);
+        } else {
+            o = Env::observe(st);
+        }
         a.reset_obs[e] = o;
     }
     if (a.next_obs) a.next_obs[e] = o;
+    if constexpr (Env::kTrigCache) {
+        if (a.trig_cache) {
+            a.trig_cache[e] = st[0];
+            a.trig_cache[N + e] = sc_s;
+            a.trig_cache[2 * N + e] = sc_c;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < Env::S; ++k) a.state[k * N + e] = st[k];
     a.elapsed[e] = el;
@@ -439,7 +480,7 @@ extern "C" int xb_rollout_step(int env_kind, const float* act_param, const float
                                double* ep_stats, int max_episode_steps, const float* x_in, void* act_out, float* logp_out,
                                float* obs_row, float* act_row, float* rew_row, float* val_row, float* term_row,
                                uint8_t* trunc_row, float* logp_row, const float* rew_scale, float rew_clip,
-                               const float* boot_src, float* boot_row, int64_t N, xb_stream_t stream) {
+                               const float* boot_src, float* boot_row, double* trig_cache, int64_t N, xb_stream_t stream) {
     if (N <= 0 || !act_param || !val || !state || !rng || !elapsed || !ep_score || !obs || !rew || !term || !trunc ||
         !reset_obs || !ep_step_out || !ep_score_out || !x_in || !act_out || !logp_out || !obs_row || !act_row ||
         !rew_row || !val_row || !term_row || !logp_row)
@@ -449,7 +490,7 @@ extern "C" int xb_rollout_step(int env_kind, const float* act_param, const float
     RolloutStepArgs a{act_param, logstd, val, seed, counter_dev, offset, state, rng, elapsed, ep_score, (float4*)obs,
                       (float4*)next_obs, rew, term, trunc, (float4*)reset_obs, ep_step_out, ep_score_out, ep_stats,
                       max_episode_steps, (const float4*)x_in, act_out, logp_out, (float4*)obs_row, act_row, rew_row,
-                      val_row, term_row, trunc_row, logp_row, rew_scale, rew_clip, boot_src, boot_row, N};
+                      val_row, term_row, trunc_row, logp_row, rew_scale, rew_clip, boot_src, boot_row, trig_cache, N};
     cudaStream_t s = (cudaStream_t)stream;
     int block = env_block(N), grid = ceil_div_i64(N, block);
     if (env_kind == XB_ENV_CARTPOLE) rollout_step_kernel<CartPole><<<grid, block, 0, s>>>(a);

@@ -48,7 +48,7 @@ def env_step(kind, state, rng, elapsed, ep_score, actions, obs, next_obs, rew, t
 def rollout_step(kind, act_param, logstd, val, seed, counter, offset, state, rng, elapsed, ep_score, obs, next_obs, rew,
                  term, trunc, reset_obs, ep_step_out, ep_score_out, ep_stats, max_steps, x_in, act_out, logp_out, obs_row,
                  act_row, rew_row, val_row, term_row, trunc_row, logp_row, rew_std=None, rew_clip=0.0, boot_src=None,
-                 boot_row=None):
+                 boot_row=None, trig_cache=None):
     """sample + env step + store of one vector step in one launch (see xb_rollout_step in include/xb200.h)."""
     N = elapsed.numel()
     _lib.call("xb_rollout_step", kind, _p(act_param, F32), _p(logstd, F32), _p(val, F32), int(seed), _p(counter, I64),
@@ -57,7 +57,7 @@ def rollout_step(kind, act_param, logstd, val, seed, counter, offset, state, rng
               _p(ep_score_out, F64), _p(ep_stats, F64), max_steps, _p(x_in, F32), _p(act_out, F32 if kind == 1 else I64),
               _p(logp_out, F32), _p(obs_row, F32), _p(act_row, F32), _p(rew_row, F32), _p(val_row, F32),
               _p(term_row, F32), _p(trunc_row, U8), _p(logp_row, F32), _p(rew_std, F32), float(rew_clip), _p(boot_src, F32),
-              _p(boot_row, F32), N, _stream())
+              _p(boot_row, F32), _p(trig_cache, F64), N, _stream())
 
 
 def sincos_f64(x):
