@@ -153,8 +153,8 @@ int xb_gather_records(const int64_t* idx, int64_t B, int64_t T, int64_t N, const
  *             (pass base+0, base+3, base+2, base+1); must be 1 with idx, and with act_dim > 1.
  * Outputs: gradients of  L = a_loss - ent_coef*entropy + vf_coef*c_loss  w.r.t. the network outputs, and
  *   scalars fp64 [8] = sums over THIS call's samples of {min-surrogate, value loss term, entropy, v_pred,
- *   clipped-ratio count, 0, 0, 0} (zeroed by the call).
- * Gaussian: logstd f32 [A] is shared by the batch; dlogstd_acc fp64 [A] (zeroed by the call) receives its gradient.
+ *   clipped-ratio count, 0, 0, 0} (overwritten; summed in a fixed order, so bit-reproducible run to run).
+ * Gaussian: logstd f32 [A] is shared by the batch; dlogstd_acc fp64 [A] (overwritten) receives its gradient.
  * ---------------------------------------------------------------------------------------------------------- */
 int xb_ppo_loss_categorical(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* logits, int A,
                             const float* v_pred, const float* act, const float* ret, const float* adv,

@@ -12,8 +12,9 @@
 // (xuance/common/memory_tools.py:236-243).  Closed-form gradients: SURVEY.md App. C.
 //
 // One thread per sample.  HBM traffic per sample (Categorical, A=2): 8 B index + 4x4 B gathered scalars +
-// 8 B logits + 4 B v read, 8 B dlogits + 4 B dv written = 48 B.  The scalar reductions (loss terms for the
-// log) are warp-shuffle + one fp64 atomic per block.
+// 8 B logits + 4 B v read, 8 B dlogits + 4 B dv written = 48 B.  The scalar reductions (loss terms for the log, the
+// log-std gradient) are warp-shuffle -> per-CTA partial -> fixed-order sum in the last CTA: deterministic, no atomics on
+// the results, nothing to zero beforehand.
 #include "common.cuh"
 
 namespace xb {
@@ -101,15 +102,43 @@ __device__ __forceinline__ float surrogate_and_value(const LossCommon& c, const 
     return dlogp;
 }
 
-__device__ __forceinline__ void flush_scalars(double (&acc)[5], double* scalars, double* smem) {
-    block_sum<5>(acc, smem);
+constexpr int kLossBlock = 256;
+constexpr int kLossMaxGrid = kNumSMs * 8;
+constexpr int kLossSlots = 16;   // doubles per CTA partial: 5 log scalars + up to 8 log-std gradient sums
+
+// Per-CTA partial sums -> ticket -> the last CTA adds them in CTA order: deterministic, no atomics on the results and no
+// zeroing launch in front of the kernel (the outputs are overwritten).  One loss kernel runs at a time per device.
+__device__ double g_loss_partials[kLossMaxGrid * kLossSlots];
+__device__ unsigned int g_loss_ticket;
+
+// v[0..4] -> scalars[0..4] (scalars[5..7] = 0); v[5..5+A) -> dlogstd[0..A) when dlogstd != NULL.
+template <int K>
+__device__ __forceinline__ void finish_sums(double (&v)[K], double* smem, double* __restrict__ scalars,
+                                            double* __restrict__ dlogstd, int A) {
+    __shared__ bool is_last;
+    block_sum<K>(v, smem);
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) atomicAdd(&scalars[k], acc[k]);
+        for (int k = 0; k < K; ++k) g_loss_partials[blockIdx.x * kLossSlots + k] = v[k];
+        __threadfence();
+        is_last = (atomicAdd(&g_loss_ticket, 1u) == gridDim.x - 1);
     }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = warp; k < K; k += kLossBlock / 32) {   // one warp per output, CTA partials added in a fixed order
+        double s = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) s += g_loss_partials[b * kLossSlots + k];
+        s = warp_sum(s);
+        if (lane == 0) {
+            if (k < 5) scalars[k] = s;
+            else if (dlogstd && k - 5 < A) dlogstd[k - 5] = s;
+        }
+    }
+    if (threadIdx.x < 3) scalars[5 + threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) g_loss_ticket = 0u;
 }
-
-constexpr int kLossBlock = 256;
 
 // ------------------------------------------------------------------------------------------------ Categorical
 template <int A_STATIC>
@@ -144,7 +173,7 @@ __global__ void __launch_bounds__(kLossBlock)
             dz[j] = dlogp * ((j == a ? 1.0f : 0.0f) - pj) + ge * pj * (lp + H);
         }
     }
-    flush_scalars(acc, c.scalars, smem);
+    finish_sums<5>(acc, smem, c.scalars, nullptr, 0);
 }
 
 // ------------------------------------------------------------------------------------------------ Gaussian
@@ -154,7 +183,7 @@ constexpr float kHalfLog2Pi = 0.9189385332046727f;
 __global__ void __launch_bounds__(kLossBlock)
     loss_gaussian_kernel(LossCommon c, const float* __restrict__ mu, const float* __restrict__ logstd, int A,
                          float* __restrict__ dmu, double* __restrict__ dlogstd_acc) {
-    __shared__ double smem[kMaxGaussA * 32];
+    __shared__ double smem[(5 + kMaxGaussA) * 32];
     const AdvNorm nrm = load_adv_norm(c);
     float ls[kMaxGaussA], inv_var[kMaxGaussA];
     float H = 0.0f;
@@ -191,12 +220,12 @@ __global__ void __launch_bounds__(kLossBlock)
             }
         }
     }
-    block_sum<kMaxGaussA>(gls, smem);
-    if (threadIdx.x == 0) {
-        for (int k = 0; k < A; ++k) atomicAdd(&dlogstd_acc[k], gls[k]);
-    }
-    __syncthreads();
-    flush_scalars(acc, c.scalars, smem);
+    double all[5 + kMaxGaussA];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) all[k] = acc[k];
+#pragma unroll
+    for (int k = 0; k < kMaxGaussA; ++k) all[5 + k] = gls[k];
+    finish_sums<5 + kMaxGaussA>(all, smem, c.scalars, dlogstd_acc, A);
 }
 
 static int check_common(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* v_pred, const float* act,
@@ -226,7 +255,6 @@ extern "C" int xb_ppo_loss_categorical(const int64_t* idx, int64_t B, int64_t T,
     if (rc) return rc;
     if (!logits || !dlogits || A < 2) return XB_E_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
-    XB_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(double), s));
     LossCommon c{idx, B, T, N, stride, v_pred, act, ret, adv, old_logp, val_old, adv_stats,
                  adv_stats ? 1.0 / (double)adv_count : 0.0, clip_range, vf_coef, ent_coef, value_clip, inv_batch, dv, scalars};
     int grid = grid_for(B, kLossBlock, 8);
@@ -249,8 +277,6 @@ extern "C" int xb_ppo_loss_gaussian(const int64_t* idx, int64_t B, int64_t T, in
     if (!mu || !logstd || !dmu || !dlogstd_acc || A < 1) return XB_E_BADARG;
     if (A > kMaxGaussA) return XB_E_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
-    XB_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(double), s));
-    XB_CUDA(cudaMemsetAsync(dlogstd_acc, 0, A * sizeof(double), s));
     LossCommon c{idx, B, T, N, stride, v_pred, act, ret, adv, old_logp, val_old, adv_stats,
                  adv_stats ? 1.0 / (double)adv_count : 0.0, clip_range, vf_coef, ent_coef, value_clip, inv_batch, dv, scalars};
     loss_gaussian_kernel<<<grid_for(B, kLossBlock, 8), kLossBlock, 0, s>>>(c, mu, logstd, A, dmu, dlogstd_acc);
