@@ -513,6 +513,8 @@ class PPOCLIP_Agent:
     def _collect_info(self):
         """One host sync per rollout: learner scalars + episode totals (reference logs at :84,:102-109)."""
         info = self.learner.info(self.batch_size)
+        if self.learner._peer is not None:
+            self.learner._peer.check()
         st = self.envs.ep_stats.cpu().numpy()
         self.d2h_bytes += 8 * 8 + 3 * 8 + 4 + 8
         n_ep = int(st[0]) - self.current_episode

@@ -27,7 +27,7 @@
 namespace xb {
 
 constexpr int kPeerMaxRanks = 8;
-constexpr int kPeerSlots = 64;       // CTA slots: [0, kPeerSlots-1) gradient all-reduce, last slot the stats exchange
+constexpr int kPeerSlots = 64;       // CTA slots: [0, kPeerSlots-2) gradient all-reduce, [62] error flag (tickets only), [63] the stats exchange
 constexpr int kPeerStatsMax = 2048;  // doubles (two per minibatch of an epoch)
 constexpr int64_t kPeerFlagsBytes = (int64_t)kPeerSlots * kPeerMaxRanks * sizeof(uint32_t);
 constexpr int64_t kPeerStatsOff = kPeerFlagsBytes;
@@ -56,15 +56,36 @@ __device__ __forceinline__ double ld_peer_f64(const double* p) {
     return v;
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+constexpr unsigned long long kPeerTimeoutNs = 20ULL * 1000 * 1000 * 1000;   // a peer that is 20 s late is gone
+constexpr int kPeerErrSlot = kPeerSlots - 2;                                // tickets[kPeerErrSlot] != 0: a barrier timed out
+
 // All threads of the CTA call it; `ticket` must be the same in every rank for the same barrier instance.
-__device__ __forceinline__ void peer_barrier(const PeerTable& t, int rank, int W, int slot, uint32_t ticket) {
+// A wait that exceeds kPeerTimeoutNs gives up and raises the rank-local error flag (the host turns it into an exception)
+// instead of spinning forever when a peer process has died.
+__device__ __forceinline__ void peer_barrier(const PeerTable& t, int rank, int W, int slot, uint32_t ticket, uint32_t* tickets) {
     __syncthreads();  // every thread's earlier accesses are ordered before the release below
     if ((int)threadIdx.x < W) {
         const int peer = threadIdx.x;
         uint32_t* theirs = reinterpret_cast<uint32_t*>(t.base[peer]) + slot * kPeerMaxRanks + rank;
         st_release_sys(theirs, ticket);
         const uint32_t* mine = reinterpret_cast<const uint32_t*>(t.base[rank]) + slot * kPeerMaxRanks + peer;
+        unsigned long long t0 = 0;
+        unsigned int spins = 0;
         while ((int32_t)(ld_acquire_sys(mine) - ticket) < 0) {
+            if ((++spins & 0x3ffu) == 0) {           // look at the clock every 1024 polls
+                const unsigned long long now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > kPeerTimeoutNs) {
+                    tickets[kPeerErrSlot] = 1u;
+                    break;
+                }
+            }
         }
     }
     __syncthreads();
@@ -90,7 +111,7 @@ __global__ void __launch_bounds__(kPeerBlock)
         const float4 g = in4[i];
         for (int r = 0; r < W; ++r) reinterpret_cast<float4*>(t.base[r] + kPeerGradOff)[half + (int64_t)rank * n4 + i] = g;
     }
-    peer_barrier(t, rank, W, slot, base_ticket + 1);     // every rank's slice has landed in my inbox
+    peer_barrier(t, rank, W, slot, base_ticket + 1, tickets);     // every rank's slice has landed in my inbox
     if (threadIdx.x == 0) tickets[slot] = base_ticket + 1;
     const float4* box = reinterpret_cast<const float4*>(t.base[rank] + kPeerGradOff) + half;
     double acc[1] = {0.0};
@@ -114,13 +135,13 @@ __global__ void __launch_bounds__(256)
     peer_allreduce_f64_kernel(PeerTable t, int rank, int W, int n, double* __restrict__ out, uint32_t* __restrict__ tickets) {
     const int slot = kPeerSlots - 1;
     const uint32_t base_ticket = tickets[slot];
-    peer_barrier(t, rank, W, slot, base_ticket + 1);
+    peer_barrier(t, rank, W, slot, base_ticket + 1, tickets);
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
         double s = 0.0;
         for (int r = 0; r < W; ++r) s += ld_peer_f64(reinterpret_cast<const double*>(t.base[r] + kPeerStatsOff) + j);
         out[j] = s;
     }
-    peer_barrier(t, rank, W, slot, base_ticket + 2);
+    peer_barrier(t, rank, W, slot, base_ticket + 2, tickets);
     if (threadIdx.x == 0) tickets[slot] = base_ticket + 2;
 }
 
@@ -206,7 +227,7 @@ extern "C" int xb_peer_allreduce_grad_norm(const void* const* peer_bases /* host
     AdamHyper h{lr0, lr_end_factor, beta1, beta2, eps, max_norm, grad_scale, lr_total_iters};
     const int64_t n4 = n / 4;
     int grid = (int)((n4 + kPeerBlock - 1) / kPeerBlock);
-    if (grid > kPeerSlots - 1) grid = kPeerSlots - 1;
+    if (grid > kPeerSlots - 2) grid = kPeerSlots - 2;
     peer_allreduce_grad_norm_kernel<<<grid, kPeerBlock, 0, (cudaStream_t)stream>>>(t, rank, W, n4, grad_in, grad_out, tickets, step_dev,
                                                                                   h, workspace, lr_out, gnorm_out);
     XB_LAUNCH_CHECK();
