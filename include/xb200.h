@@ -31,6 +31,7 @@ extern "C" {
 #define XB_ENV_CARTPOLE 0 /* CartPole-v1: state (x, x_dot, theta, theta_dot), action int64 {0,1}, limit 500 */
 #define XB_ENV_PENDULUM 1 /* Pendulum-v1: state (theta, theta_dot), action float32 torque, limit 200 */
 #define XB_ENV_MOUNTAINCAR 2 /* MountainCar-v0: state (position, velocity), action int64 {0,1,2}, limit 200 */
+#define XB_ENV_ACROBOT 3 /* Acrobot-v1: state (theta1, theta2, dtheta1, dtheta2), action int64 {0,1,2}, limit 500; obs 6 floats = TWO float4 per row */
 
 #define XB_E_BADARG (-1)
 #define XB_E_UNSUPPORTED (-2)
@@ -53,7 +54,8 @@ const char* xb_error_string(int code);
  *           Gym_Env.reset / step                xuance/environment/gym/gym_env.py:36-49
  *           gym 0.26.2 CartPoleEnv / PendulumEnv / TimeLimit / np_random (third party, restated: SURVEY.md App. A/B)
  *
- * state     fp64 [S][N] (SoA; S = 4 CartPole, 2 Pendulum)
+ * state     fp64 [S][N] (SoA; S = 4 CartPole / Acrobot, 2 Pendulum / MountainCar)
+ * obs       f32 [N][4] rows (one float4 per env); Acrobot-v1: [N][8] (two float4: cos t1, sin t1, cos t2, sin t2 | dt1, dt2, 0, 0)
  * rng       u64  [4][N] (SoA) numpy PCG64: state_hi, state_lo, inc_hi, inc_lo
  * elapsed   i32  [N]    TimeLimit._elapsed_steps == Gym_Env._episode_step
  * ep_score  fp64 [N]    Gym_Env._episode_score
@@ -90,11 +92,13 @@ int xb_sincos_f64(const double* x, double* s, double* c, int64_t n, xb_stream_t 
  * term/trunc are u8 in, term is stored as float32 0/1 (memory_tools.py:177), trunc as u8 (segment-end flag).
  * rew_std: nullable device scalar; when given, rewards are stored as clip(rew / *rew_std, +-rew_clip)
  *          (Agent._process_reward, xuance/torch/agents/agent.py:118-123).
+ * obs_vec: float4s per observation row: 1 (obs_dim <= 4, XB_OBS_STRIDE floats) or 2 (wide rows of 8 floats for
+ *          obs_dim 5..8, e.g. Acrobot-v1's 6); the gathers below infer the same width from obs_dim.
  * ---------------------------------------------------------------------------------------------------------- */
 int xb_store(const float* obs, const void* act, int act_is_i64, int act_dim, const float* rew, const float* val,
              const uint8_t* term, const uint8_t* trunc, const float* logp, float* obs_row, float* act_row,
              float* rew_row, float* val_row, float* term_row, uint8_t* trunc_row, float* logp_row,
-             const float* rew_std, float rew_clip, int64_t N, xb_stream_t stream);
+             const float* rew_std, float rew_clip, int obs_vec, int64_t N, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * (3) GAE / discounted-return reverse scan over T, parallel over envs, + advantage statistics.

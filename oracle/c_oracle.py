@@ -59,7 +59,8 @@ class VecEnvC:
 
     SPEC = {"CartPole-v1": dict(sdim=4, odim=4, max_steps=500, act=np.int64),
             "Pendulum-v1": dict(sdim=2, odim=3, max_steps=200, act=np.float32),
-            "MountainCar-v0": dict(sdim=2, odim=2, max_steps=200, act=np.int64)}
+            "MountainCar-v0": dict(sdim=2, odim=2, max_steps=200, act=np.int64),
+            "Acrobot-v1": dict(sdim=4, odim=6, max_steps=500, act=np.int64)}
 
     def __init__(self, env_id, n, seed=1, flavour="cr", n_warm_resets=2, seeds=None):
         sp = self.SPEC[env_id]
@@ -84,6 +85,9 @@ class VecEnvC:
         elif self.env_id == "MountainCar-v0":
             L.oc_mountaincar_reset(_p(self.state), _p(self.rng), _p(self.elapsed), _p(self.ep_score), _p(self.obs),
                                    C.c_int(n_draws), C.c_long(self.n))
+        elif self.env_id == "Acrobot-v1":
+            L.oc_acrobot_reset(_p(self.state), _p(self.rng), _p(self.elapsed), _p(self.ep_score), _p(self.obs),
+                               C.c_int(n_draws), C.c_long(self.n), C.c_int(self.flavour))
         else:
             L.oc_pendulum_reset(_p(self.state), _p(self.rng), _p(self.elapsed), _p(self.ep_score), _p(self.obs),
                                 C.c_int(n_draws), C.c_long(self.n), C.c_int(self.flavour))
@@ -99,7 +103,7 @@ class VecEnvC:
         ep_step = np.empty(n, np.int32)
         ep_score = np.empty(n, np.float64)
         fn = {"CartPole-v1": lib().oc_cartpole_step, "Pendulum-v1": lib().oc_pendulum_step,
-              "MountainCar-v0": lib().oc_mountaincar_step}[self.env_id]
+              "MountainCar-v0": lib().oc_mountaincar_step, "Acrobot-v1": lib().oc_acrobot_step}[self.env_id]
         fn(_p(self.state), _p(self.rng), _p(self.elapsed), _p(self.ep_score), _p(a), _p(self.obs), _p(rew), _p(term),
            _p(trunc), _p(reset_obs), _p(ep_step), _p(ep_score), C.c_int(self.max_steps), C.c_long(n), C.c_int(self.flavour))
         return dict(obs=self.obs.copy(), rew=rew, term=term.astype(bool), trunc=trunc.astype(bool),

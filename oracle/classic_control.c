@@ -6,6 +6,7 @@
  *
  * What it restates (citations relative to /root/reference unless noted):
  *   - gym 0.26.2 CartPoleEnv.step/reset, PendulumEnv.step/reset/_get_obs/angle_normalize, MountainCarEnv.step/reset,
+ *     AcrobotEnv.step/reset/_dsdt/rk4/wrap/bound,
  *     TimeLimit.step/reset (third party, pinned setup.py:51, NOT vendored -> published algorithm,
  *     SURVEY.md App. A), driven the way xuance drives it:
  *       Gym_Env.step/reset bookkeeping   xuance/environment/gym/gym_env.py:36-49
@@ -155,6 +156,91 @@ void oc_mountaincar_step(double* state, uint64_t* rng, int32_t* elapsed, double*
             mountaincar_draw(st, rng + 4 * e);
             elapsed[e] = 0; ep_score[e] = 0.0;
             reset_obs[2 * e] = (float)st[0]; reset_obs[2 * e + 1] = (float)st[1];
+        }
+    }
+}
+
+/* ---------------------------------------------------------------- Acrobot-v1 ---------------------------- */
+/* gym 0.26.2 AcrobotEnv (gym/envs/classic_control/acrobot.py), "book" dynamics, restated from the published algorithm:
+ *   s_augmented = np.append(state, AVAIL_TORQUE[a]); ns = rk4(_dsdt, s_augmented, [0, dt=0.2]) (one RK4 step);
+ *   ns[0:2] = wrap(., -pi, pi); ns[2] = bound(., +-4pi); ns[3] = bound(., +-9pi);
+ *   terminated = -cos(s0) - cos(s1 + s0) > 1.0; reward = -1.0 (0.0 when terminated);
+ *   obs = float32([cos s0, sin s0, cos s1, sin s1, s2, s3]); reset: uniform(-0.1, 0.1, 4).astype(float32).
+ * Every expression keeps Python's left-to-right order; products with the unit constants (m = l = I = 1, lc = 0.5) are
+ * exact and folded.  Deviation (documented): right after reset gym's state is a float32 array and numpy evaluates the
+ * observation's cos/sin in FLOAT32; here it is float32(double cos), like after every step. */
+static void acrobot_draw(double* st, uint64_t* rng) {
+    for (int k = 0; k < 4; ++k) st[k] = (double)(float)pcg64_uniform(rng, -0.1, 0.1 - (-0.1));
+}
+static void acrobot_obs(const double* st, float* o, int flavour) {
+    o[0] = (float)cos_f(st[0], flavour); o[1] = (float)sin_f(st[0], flavour);
+    o[2] = (float)cos_f(st[1], flavour); o[3] = (float)sin_f(st[1], flavour);
+    o[4] = (float)st[2]; o[5] = (float)st[3];
+}
+static void acrobot_dsdt(const double* y, double a, double* k, int flavour) {
+    const double theta1 = y[0], theta2 = y[1], dtheta1 = y[2], dtheta2 = y[3];
+    const double c2 = cos_f(theta2, flavour), s2 = sin_f(theta2, flavour);
+    const double d1 = ((0.25 + (1.25 + c2)) + 1.0) + 1.0;
+    const double d2 = (0.25 + 0.5 * c2) + 1.0;
+    const double phi2 = (0.5 * 9.8) * cos_f((theta1 + theta2) - OC_PI / 2.0, flavour);
+    const double phi1 = (((-0.5 * sq_f(dtheta2, flavour)) * s2 - (dtheta2 * dtheta1) * s2)
+                         + (1.5 * 9.8) * cos_f(theta1 - OC_PI / 2.0, flavour)) + phi2;
+    const double ddtheta2 = (((a + (d2 / d1) * phi1) - (0.5 * sq_f(dtheta1, flavour)) * s2) - phi2)
+                            / (1.25 - sq_f(d2, flavour) / d1);
+    const double ddtheta1 = -(d2 * ddtheta2 + phi1) / d1;
+    k[0] = dtheta1; k[1] = dtheta2; k[2] = ddtheta1; k[3] = ddtheta2;
+}
+static double acrobot_wrap(double x, double m, double M) {
+    const double diff = M - m;
+    while (x > M) x = x - diff;
+    while (x < m) x = x + diff;
+    return x;
+}
+
+void oc_acrobot_reset(double* state /*[n][4]*/, uint64_t* rng, int32_t* elapsed, double* ep_score, float* obs /*[n][6]*/,
+                      int n_draws, long n, int flavour) {
+    for (long e = 0; e < n; ++e) {
+        for (int d = 0; d < n_draws; ++d) acrobot_draw(state + 4 * e, rng + 4 * e);
+        elapsed[e] = 0; ep_score[e] = 0.0;
+        acrobot_obs(state + 4 * e, obs + 6 * e, flavour);
+    }
+}
+
+void oc_acrobot_step(double* state, uint64_t* rng, int32_t* elapsed, double* ep_score,
+                     const int64_t* actions, float* obs, float* rew, uint8_t* term, uint8_t* trunc,
+                     float* reset_obs, int32_t* ep_step_out, double* ep_score_out,
+                     int max_steps, long n, int flavour) {
+    const double dt = 0.2, dt2 = 0.2 / 2.0, dt6 = 0.2 / 6.0;
+    for (long e = 0; e < n; ++e) {
+        double* st = state + 4 * e;
+        const double a = (double)(actions[e] - 1);
+        double k1[4], k2[4], k3[4], k4[4], y[4];
+        acrobot_dsdt(st, a, k1, flavour);
+        for (int i = 0; i < 4; ++i) y[i] = st[i] + dt2 * k1[i];
+        acrobot_dsdt(y, a, k2, flavour);
+        for (int i = 0; i < 4; ++i) y[i] = st[i] + dt2 * k2[i];
+        acrobot_dsdt(y, a, k3, flavour);
+        for (int i = 0; i < 4; ++i) y[i] = st[i] + dt * k3[i];
+        acrobot_dsdt(y, a, k4, flavour);
+        for (int i = 0; i < 4; ++i) y[i] = st[i] + dt6 * (((k1[i] + 2.0 * k2[i]) + 2.0 * k3[i]) + k4[i]);
+        y[0] = acrobot_wrap(y[0], -OC_PI, OC_PI);
+        y[1] = acrobot_wrap(y[1], -OC_PI, OC_PI);
+        const double v1 = 4 * OC_PI, v2 = 9 * OC_PI;
+        y[2] = fmin(fmax(y[2], -v1), v1);
+        y[3] = fmin(fmax(y[3], -v2), v2);
+        for (int i = 0; i < 4; ++i) st[i] = y[i];
+        int terminated = (-cos_f(st[0], flavour) - cos_f(st[1] + st[0], flavour)) > 1.0;
+        double reward = terminated ? 0.0 : -1.0;
+        elapsed[e] += 1;
+        int truncated = elapsed[e] >= max_steps;
+        ep_score[e] += reward;
+        acrobot_obs(st, obs + 6 * e, flavour);
+        rew[e] = (float)reward; term[e] = (uint8_t)terminated; trunc[e] = (uint8_t)truncated;
+        ep_step_out[e] = elapsed[e]; ep_score_out[e] = ep_score[e];
+        if (terminated || truncated) {
+            acrobot_draw(st, rng + 4 * e);
+            elapsed[e] = 0; ep_score[e] = 0.0;
+            acrobot_obs(st, reset_obs + 6 * e, flavour);
         }
     }
 }

@@ -262,6 +262,105 @@ class MountainCarRestated:
         return None
 
 
+class AcrobotRestated:
+    """gym 0.26.2 AcrobotEnv (gym/envs/classic_control/acrobot.py), book_or_nips = "book", torque_noise_max = 0.
+    Written expression by expression like the original (`_dsdt`, `rk4`, `wrap`, `bound`); `v**2` goes through `self.m.sq`
+    and cos/sin through `self.m` so the two oracle flavours share every other line.  Deviation (documented): right after
+    reset gym's state is a float32 array and numpy evaluates the observation's cos/sin in float32; here the observation is
+    float32(double cos), like after every step."""
+    dt = 0.2
+    LINK_LENGTH_1 = 1.0
+    LINK_LENGTH_2 = 1.0
+    LINK_MASS_1 = 1.0
+    LINK_MASS_2 = 1.0
+    LINK_COM_POS_1 = 0.5
+    LINK_COM_POS_2 = 0.5
+    LINK_MOI = 1.0
+    MAX_VEL_1 = 4 * math.pi
+    MAX_VEL_2 = 9 * math.pi
+    AVAIL_TORQUE = [-1.0, 0.0, +1]
+    metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 15}
+    reward_range = (-float("inf"), float("inf"))
+
+    def __init__(self, trig="libm", with_spaces=True):
+        self.m = _Math(trig)
+        self.np_random = None
+        self.state = None
+        if with_spaces:
+            high = np.array([1.0, 1.0, 1.0, 1.0, self.MAX_VEL_1, self.MAX_VEL_2], dtype=np.float32)
+            self.observation_space = _Spaces.box(-high, high)
+            self.action_space = _Spaces.discrete(3)
+
+    def _get_ob(self):
+        s = self.state
+        c, sn = self.m.cos, self.m.sin
+        return np.array([c(float(s[0])), sn(float(s[0])), c(float(s[1])), sn(float(s[1])), s[2], s[3]], dtype=np.float32)
+
+    def reset(self, seed=None):
+        if seed is not None or self.np_random is None:
+            self.np_random = new_rng(seed)
+        self.state = self.np_random.uniform(low=-0.1, high=0.1, size=(4,)).astype(np.float32)
+        return self._get_ob(), {}
+
+    def _dsdt(self, s_augmented):
+        cos, sin, sq, pi = self.m.cos, self.m.sin, self.m.sq, math.pi
+        m1, m2, l1 = self.LINK_MASS_1, self.LINK_MASS_2, self.LINK_LENGTH_1
+        lc1, lc2 = self.LINK_COM_POS_1, self.LINK_COM_POS_2
+        I1 = I2 = self.LINK_MOI
+        g = 9.8
+        a = s_augmented[-1]
+        theta1, theta2, dtheta1, dtheta2 = s_augmented[:4]
+        d1 = m1 * lc1 ** 2 + m2 * (l1 ** 2 + lc2 ** 2 + 2 * l1 * lc2 * cos(theta2)) + I1 + I2
+        d2 = m2 * (lc2 ** 2 + l1 * lc2 * cos(theta2)) + I2
+        phi2 = m2 * lc2 * g * cos(theta1 + theta2 - pi / 2.0)
+        phi1 = (-m2 * l1 * lc2 * sq(dtheta2) * sin(theta2)
+                - 2 * m2 * l1 * lc2 * dtheta2 * dtheta1 * sin(theta2)
+                + (m1 * lc1 + m2 * l1) * g * cos(theta1 - pi / 2)
+                + phi2)
+        ddtheta2 = (a + d2 / d1 * phi1 - m2 * l1 * lc2 * sq(dtheta1) * sin(theta2) - phi2) / (m2 * lc2 ** 2 + I2 - sq(d2) / d1)
+        ddtheta1 = -(d2 * ddtheta2 + phi1) / d1
+        return [dtheta1, dtheta2, ddtheta1, ddtheta2, 0.0]
+
+    def _rk4(self, y0):
+        dt = self.dt - 0
+        dt2 = dt / 2.0
+        ax = lambda y, c, k: [yi + c * ki for yi, ki in zip(y, k)]          # y0 + c * k, element by element
+        k1 = self._dsdt(y0)
+        k2 = self._dsdt(ax(y0, dt2, k1))
+        k3 = self._dsdt(ax(y0, dt2, k2))
+        k4 = self._dsdt(ax(y0, dt, k3))
+        c6 = dt / 6.0
+        return [y + c6 * (((a + 2 * b) + 2 * c) + d) for y, a, b, c, d in zip(y0, k1, k2, k3, k4)][:4]
+
+    @staticmethod
+    def _wrap(x, m, M):
+        diff = M - m
+        while x > M:
+            x = x - diff
+        while x < m:
+            x = x + diff
+        return x
+
+    def step(self, a):
+        torque = float(self.AVAIL_TORQUE[int(a)])
+        s_augmented = [float(v) for v in self.state] + [torque]            # np.append(float32 state, torque) -> float64
+        ns = self._rk4(s_augmented)
+        ns[0] = self._wrap(ns[0], -math.pi, math.pi)
+        ns[1] = self._wrap(ns[1], -math.pi, math.pi)
+        ns[2] = min(max(ns[2], -self.MAX_VEL_1), self.MAX_VEL_1)
+        ns[3] = min(max(ns[3], -self.MAX_VEL_2), self.MAX_VEL_2)
+        self.state = np.array(ns, dtype=np.float64)
+        terminated = bool(-self.m.cos(ns[0]) - self.m.cos(ns[1] + ns[0]) > 1.0)
+        reward = -1.0 if not terminated else 0.0
+        return self._get_ob(), reward, terminated, False, {}
+
+    def close(self):
+        pass
+
+    def render(self):
+        return None
+
+
 class TimeLimitRestated:
     """gym 0.26.2 wrappers.TimeLimit (outermost wrapper returned by gym.make)."""
 
@@ -303,7 +402,7 @@ class TimeLimitRestated:
 
 
 SPECS = {"CartPole-v1": (CartPoleRestated, 500), "Pendulum-v1": (PendulumRestated, 200),
-         "MountainCar-v0": (MountainCarRestated, 200)}
+         "MountainCar-v0": (MountainCarRestated, 200), "Acrobot-v1": (AcrobotRestated, 500)}
 DEFAULT_TRIG = "libm"
 
 

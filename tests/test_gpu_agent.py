@@ -13,7 +13,8 @@ def _build(env_id, **kw):
     return build_ppo(env_id, **kw)
 
 
-@pytest.mark.parametrize("env_id,n,T", [("CartPole-v1", 64, 40), ("Pendulum-v1", 48, 230), ("MountainCar-v0", 40, 210)])
+@pytest.mark.parametrize("env_id,n,T", [("CartPole-v1", 64, 40), ("Pendulum-v1", 48, 230), ("MountainCar-v0", 40, 210),
+                                       ("Acrobot-v1", 24, 520)])
 @pytest.mark.parametrize("graphs", [True, False])
 def test_native_rollout_replays_bit_exact_through_the_oracle(env_id, n, T, graphs):
     """Take the actions the device loop drew, replay them through the C oracle from the same seed: the buffer's
@@ -47,7 +48,7 @@ def test_native_rollout_replays_bit_exact_through_the_oracle(env_id, n, T, graph
             assert trunc_seen > 0
         # values stored are the critic's output on the stored observations
         with torch.no_grad():
-            _, _, v = agent.policy(mem._obs.reshape(T * n, 4)[:, :od])
+            _, _, v = agent.policy(mem._obs.reshape(T * n, mem.obs_row)[:, :od])
         assert torch.allclose(v.reshape(T, n), mem._val, atol=1e-5, rtol=1e-5)
         adv64, ret64 = c_oracle.gae(mem._rew.cpu().numpy(), mem._val.cpu().numpy(), mem._term.cpu().numpy(),
                                     agent._boot_last.cpu().numpy(), agent.gamma, agent.gae_lam,
@@ -55,7 +56,7 @@ def test_native_rollout_replays_bit_exact_through_the_oracle(env_id, n, T, graph
         assert gae_close(mem._adv.cpu().numpy(), adv64)[0] and gae_close(mem._ret.cpu().numpy(), ret64)[0]
         # old_logp stored == log-prob of the stored action under the rollout policy
         with torch.no_grad():
-            _, dist, _ = agent.policy(mem._obs.reshape(T * n, 4)[:, :od])
+            _, dist, _ = agent.policy(mem._obs.reshape(T * n, mem.obs_row)[:, :od])
             a_t = mem._act.reshape(T * n, -1)
             lp = dist.log_prob(a_t if env_id == "Pendulum-v1" else a_t[:, 0])
         assert torch.allclose(lp.reshape(T, n), mem._logp, atol=2e-5, rtol=1e-5)

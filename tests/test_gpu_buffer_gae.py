@@ -177,3 +177,31 @@ def test_buffer_old_dist_auxiliary_matches_reference_golden(name, per_sample_obj
     for k, t in enumerate(old):
         assert np.array_equal(t.cpu().numpy(), g["s2_old%d" % k])
     assert buf.auxiliary_infos["old_dist"].shape == (N, T)
+
+
+@pytest.mark.parametrize("obs_dim", [5, 6, 8])
+def test_wide_observation_rows_store_and_gather_bit_exact(obs_dim):
+    """Observations of 5..8 floats (Acrobot-v1: 6) occupy two float4 per transition: store -> sample / gather_obs return
+    exactly the stored rows under the reference's flat index k -> (env = k // T, step = k % T) (memory_tools.py:234)."""
+    import xuanpolicy_b200 as xb
+    from xuanpolicy_b200 import ops, spaces
+    T, N = 12, 37
+    rng = np.random.default_rng(obs_dim)
+    obs_space = spaces.Box(-np.ones(obs_dim, np.float32), np.ones(obs_dim, np.float32))
+    buf = xb.DummyOnPolicyBuffer(obs_space, spaces.Discrete(3), {"old_logp": ()}, N, T, True, False, 0.99, 0.95)
+    obs = rng.standard_normal((T, N, obs_dim)).astype(np.float32)
+    act = rng.integers(0, 3, (T, N)).astype(np.int64)
+    rew, val, logp = (rng.standard_normal((T, N)).astype(np.float32) for _ in range(3))
+    for t in range(T):
+        buf.store(obs[t], act[t], rew[t], val[t], np.zeros(N, bool), {"old_logp": logp[t]})
+    for i in range(N):
+        buf.finish_path(0.0, i)
+    assert np.array_equal(buf.observations, obs.transpose(1, 0, 2))
+    idx = rng.permutation(T * N)[:200].astype(np.int64)
+    env, step = np.divmod(idx, T)
+    s_obs, s_act, _, s_val, _, aux = buf.sample(idx)
+    assert np.array_equal(s_obs, obs[step, env]) and np.array_equal(s_act, act[step, env].astype(np.float32))
+    assert np.array_equal(s_val, val[step, env]) and np.array_equal(aux["old_logp"], logp[step, env])
+    out = torch.empty((200, obs_dim), device="cuda")
+    ops.gather_obs(torch.from_numpy(idx).cuda(), T, N, buf._obs, obs_dim, out)
+    assert np.array_equal(out.cpu().numpy(), obs[step, env])

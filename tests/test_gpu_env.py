@@ -54,7 +54,7 @@ def test_env_tape_bit_exact_vs_golden(name):
 
 
 @pytest.mark.parametrize("env_id,n,steps", [("CartPole-v1", 4099, 520), ("Pendulum-v1", 4096, 410),
-                                            ("MountainCar-v0", 2051, 430)])
+                                            ("MountainCar-v0", 2051, 430), ("Acrobot-v1", 1027, 560)])
 def test_env_large_batch_bit_exact_vs_c_oracle(env_id, n, steps):
     """Ragged batch size, per-env divergent random actions, many resets: still bit-exact with the C oracle."""
     from oracle import c_oracle
@@ -70,6 +70,9 @@ def test_env_large_batch_bit_exact_vs_c_oracle(env_id, n, steps):
             a = np.where(rng.random(n) < 0.8, heur, rng.integers(0, 2, n))
         elif env_id == "MountainCar-v0":        # energy-pumping heuristic so that some cars reach the goal (terminated)
             heur = np.where(obs[:, 1] > 0, 2, 0).astype(np.int64)
+            a = np.where(rng.random(n) < 0.9, heur, rng.integers(0, 3, n))
+        elif env_id == "Acrobot-v1":            # torque along the second joint's velocity: swings up (terminated) in ~70 steps
+            heur = np.where(obs[:, 5] > 0, 2, 0).astype(np.int64)
             a = np.where(rng.random(n) < 0.9, heur, rng.integers(0, 3, n))
         else:
             a = (1.5 * rng.standard_normal((n, 1))).astype(np.float32)

@@ -262,3 +262,47 @@ def test_mountaincar_c_and_python_restatements_agree_and_kat():
     v = 0.001 + math.cos(-1.5) * -0.0025
     assert e.state == (-0.5 + v, v) and r == -1.0 and not term
     assert ob.dtype == np.float32 and ob[0] == np.float32(-0.5 + v)
+
+
+ACROBOT_KAT = ["-0x1.171879311533ap-5", "0x1.ca4ce60785caap-7", "-0x1.e3f658adeead0p-6", "0x1.39e01fea84742p-2"]
+
+
+def test_acrobot_c_and_python_restatements_agree_and_kat():
+    """Acrobot-v1: the C oracle and the Python restatement (written expression by expression like gym
+    0.26.2's AcrobotEnv: _dsdt, rk4, wrap, bound) agree bit for bit in both flavours over episodes that terminate and
+    truncate; known-answer values (self-derived from the published equations, like the survey's other KATs)."""
+    from oracle import c_oracle, gym_restated
+    for fl in ("cr", "libm"):
+        n = 5
+        env = c_oracle.VecEnvC("Acrobot-v1", n, seed=1, flavour=fl, n_warm_resets=2)
+        pys = []
+        for e in range(n):
+            p = gym_restated.make("Acrobot-v1", trig=fl)
+            p.reset(seed=1)
+            o, _ = p.reset()
+            pys.append(p)
+            assert np.array_equal(o, env.obs[e])
+        rng = np.random.default_rng(3)
+        n_term = n_trunc = 0
+        for t in range(620):
+            a = rng.integers(0, 3, n)
+            a[:3] = np.where(env.state[:3, 3] > 0, 2, 0)          # torque along the second joint's velocity: swings up, terminates
+            o = env.step(a)
+            for e in range(n):
+                ob, r, term, trunc, _ = pys[e].step(a[e])
+                assert np.array_equal(ob, o["obs"][e]) and r == o["rew"][e], (fl, t, e)
+                assert term == o["term"][e] and trunc == o["trunc"][e], (fl, t, e)
+                n_term, n_trunc = n_term + int(term), n_trunc + int(trunc)
+                if term or trunc:
+                    ro, _ = pys[e].reset()
+                    assert np.array_equal(ro, o["reset_obs"][e])
+                assert np.array_equal(np.asarray(pys[e].env.state, np.float64), o["state"][e]), (fl, t, e)
+        assert n_term > 0 and n_trunc > 0
+    # KAT: PCG64(SeedSequence(1)), second reset draw (the first observation the agent sees), then action 2 ("cr" flavour)
+    env = c_oracle.VecEnvC("Acrobot-v1", 1, seed=1, flavour="cr", n_warm_resets=2)
+    draw = np.random.Generator(np.random.PCG64(np.random.SeedSequence(1)))
+    draw.uniform(-0.1, 0.1, 4)
+    assert np.array_equal(env.state[0], draw.uniform(-0.1, 0.1, 4).astype(np.float32).astype(np.float64))
+    o = env.step(np.array([2]))
+    assert o["rew"][0] == -1.0 and not o["term"][0]
+    assert [float.hex(float(v)) for v in o["state"][0]] == ACROBOT_KAT

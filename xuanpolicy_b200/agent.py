@@ -100,7 +100,7 @@ class PPOCLIP_Agent:
         obs_dim = self.memory.obs_dim
         self._obs_dim = obs_dim
         # ping-pong policy-input buffers: rows [0,N) = obs the policy acts on, rows [N,2N) = terminal obs of the last step
-        self._x = [torch.zeros((2 * N, 4), dtype=torch.float32, device=dev) for _ in range(2)]
+        self._x = [torch.zeros((2 * N, self.memory.obs_row), dtype=torch.float32, device=dev) for _ in range(2)]
         self._cur = 0
         self._act = torch.zeros(N if self.discrete else (N, self.memory.act_dim),
                                 dtype=torch.int64 if self.discrete else torch.float32, device=dev)
@@ -133,6 +133,8 @@ class PPOCLIP_Agent:
         self._rms_cur = 0
         self._obs_sums = torch.zeros(9, **f64)
         self._obs_ws = torch.zeros(8 + 8 * 1184, **f64)
+        if self.use_obsnorm and self.memory.obs_row != 4:
+            raise NotImplementedError("device observation normalisation covers observations of up to 4 floats")
         self._xn = torch.zeros((2 * N, 4), dtype=torch.float32, device=dev)      # normalised policy input
         self._ret_rms = torch.tensor([0.0, 1.0, 1e-4], **f64)
         self._ret_sums = torch.zeros(3, **f64)

@@ -32,8 +32,8 @@ class DummyOnPolicyBuffer:
         if self.device.type != "cuda":
             raise RuntimeError("xuanpolicy_b200 buffers live on a CUDA device only (no CPU fallback)")
         obs_shape = tuple(observation_space.shape)
-        if len(obs_shape) != 1 or not 1 <= obs_shape[0] <= 4:
-            raise NotImplementedError("device buffer supports flat observations of 1..4 floats (classic control)")
+        if len(obs_shape) != 1 or not 1 <= obs_shape[0] <= 8:
+            raise NotImplementedError("device buffer supports flat observations of 1..8 floats (classic control)")
         if auxiliary_shape and set(auxiliary_shape.keys()) not in ({"old_logp"}, {"old_dist"}):
             raise NotImplementedError("supported auxiliaries: {'old_logp': ()} (PPO-Clip), {'old_dist': None} "
                                       "(PPO-KL / PPG), or none (A2C / PG)")
@@ -50,7 +50,8 @@ class DummyOnPolicyBuffer:
         self.start_ids = np.zeros(n_envs, np.int64)
         T, N, dev = n_size, n_envs, self.device
         f32 = dict(dtype=torch.float32, device=dev)
-        self._obs = torch.zeros((T, N, 4), **f32)
+        self.obs_row = 4 if self.obs_dim <= 4 else 8      # floats per stored observation row (one or two float4)
+        self._obs = torch.zeros((T, N, self.obs_row), **f32)
         self._act = torch.zeros((T, N, self.act_dim), **f32)
         self._rew, self._val, self._term = torch.zeros((T, N), **f32), torch.zeros((T, N), **f32), torch.zeros((T, N), **f32)
         self._logp, self._adv, self._ret = torch.zeros((T, N), **f32), torch.zeros((T, N), **f32), torch.zeros((T, N), **f32)
@@ -59,7 +60,7 @@ class DummyOnPolicyBuffer:
         self._boot_last = torch.zeros(N, **f32)
         # packed 32-byte records {obs[4], act, old_logp, adv, ret}: one DRAM sector per transition for the minibatch
         # gather (csrc/buffer.cu); built by finish_rollout, only for 1-dim actions
-        self._rec = torch.zeros((T * N, 8), **f32) if (native and self.act_dim == 1) else None
+        self._rec = torch.zeros((T * N, 8), **f32) if (native and self.act_dim == 1 and self.obs_row == 4) else None
         self._rec_valid = False
         self._stats = torch.zeros(2, dtype=torch.float64, device=dev)        # whole-rollout (sum, sumsq) of adv
         self._mb_stats = torch.zeros(2, dtype=torch.float64, device=dev)     # per-minibatch (sum, sumsq)
@@ -109,8 +110,8 @@ class DummyOnPolicyBuffer:
         N, p = self.n_envs, self.ptr
         with torch.cuda.device(self.device):
             obs_t = self._dev(obs, torch.float32).reshape(N, self.obs_dim)
-            if self.obs_dim != 4:
-                padded = torch.zeros((N, 4), dtype=torch.float32, device=self.device)
+            if self.obs_dim != self.obs_row:
+                padded = torch.zeros((N, self.obs_row), dtype=torch.float32, device=self.device)
                 padded[:, :self.obs_dim] = obs_t
                 obs_t = padded
             act_t = acts if (torch.is_tensor(acts) and acts.is_cuda) else torch.as_tensor(np.ascontiguousarray(acts)).to(self.device)
@@ -131,7 +132,7 @@ class DummyOnPolicyBuffer:
 
     def store_device(self, obs4, act, rew, val, term_u8, trunc_u8, logp, row, rew_std=None, rew_clip=0.0):
         """Raw device store of one step into row `row` (graph-capturable; all arguments are CUDA tensors;
-        obs4 is [N, 4] float32)."""
+        obs4 is [N, obs_row] float32)."""
         ops.store(obs4, act, rew, val, term_u8, trunc_u8, logp, self._obs[row], self._act[row], self._rew[row],
                   self._val[row], self._term[row], self._trunc[row], self._logp[row], rew_std, rew_clip)
 

@@ -21,10 +21,11 @@ __global__ void __launch_bounds__(256)
                  const uint8_t* __restrict__ trunc, const float* __restrict__ logp, float4* __restrict__ obs_row,
                  float* __restrict__ act_row, float* __restrict__ rew_row, float* __restrict__ val_row,
                  float* __restrict__ term_row, uint8_t* __restrict__ trunc_row, float* __restrict__ logp_row,
-                 const float* __restrict__ rew_scale, float rew_clip, int64_t N) {
+                 const float* __restrict__ rew_scale, float rew_clip, int obs_vec, int64_t N) {
     const float std = rew_scale ? *rew_scale : 1.0f;   // rew_scale carries rew_std: rewards are DIVIDED by it
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N; e += (int64_t)gridDim.x * blockDim.x) {
-        obs_row[e] = obs[e];
+        obs_row[e * obs_vec] = obs[e * obs_vec];
+        if (obs_vec == 2) obs_row[e * 2 + 1] = obs[e * 2 + 1];   // wide observations (5..8 floats): two float4 per row
         if (act_is_i64) {
             act_row[e] = (float)((const int64_t*)act)[e];
         } else {
@@ -86,6 +87,27 @@ constexpr int kGatherMaxGrid = kNumSMs * 8;
 __device__ double g_partials[2 * kGatherMaxGrid];
 __device__ unsigned int g_ticket = 0;
 
+// wide observation rows (obs_dim 5..8): two float4 per transition
+__global__ void __launch_bounds__(kGatherBlock)
+    gather_obs_wide_kernel(const int64_t* __restrict__ idx, int64_t B, int64_t T, int64_t N, const float4* __restrict__ b_obs,
+                           int obs_dim, const float* __restrict__ b_adv, float* __restrict__ obs_out,
+                           double* __restrict__ stats) {
+    __shared__ double smem[64];
+    double s = 0.0, ss = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = flat_to_row(idx[i], T, N);
+        const float4 a = b_obs[2 * row], b = b_obs[2 * row + 1];
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        for (int k = 0; k < obs_dim; ++k) obs_out[i * obs_dim + k] = v[k];
+        if (stats) {
+            const double adv = (double)b_adv[row];
+            s += adv;
+            ss += adv * adv;
+        }
+    }
+    if (stats) finish_stats(s, ss, g_partials, &g_ticket, stats, smem);
+}
+
 template <int OBS_DIM>
 __global__ void __launch_bounds__(kGatherBlock)
     gather_obs_kernel(const int64_t* __restrict__ idx, int64_t B, int64_t T, int64_t N,
@@ -126,9 +148,15 @@ __global__ void __launch_bounds__(kGatherBlock)
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t row = flat_to_row(idx[i], T, N);
         if (obs_out) {
-            float4 o = b_obs[row];
-            float v[4] = {o.x, o.y, o.z, o.w};
-            for (int k = 0; k < obs_dim; ++k) obs_out[i * obs_dim + k] = v[k];
+            if (obs_dim <= 4) {
+                float4 o = b_obs[row];
+                float v[4] = {o.x, o.y, o.z, o.w};
+                for (int k = 0; k < obs_dim; ++k) obs_out[i * obs_dim + k] = v[k];
+            } else {   // wide rows: two float4 per transition
+                const float4 a = b_obs[2 * row], b = b_obs[2 * row + 1];
+                const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                for (int k = 0; k < obs_dim; ++k) obs_out[i * obs_dim + k] = v[k];
+            }
         }
         if (act_out)
             for (int k = 0; k < act_dim; ++k) act_out[i * act_dim + k] = b_act[row * act_dim + k];
@@ -211,14 +239,15 @@ using namespace xb;
 extern "C" int xb_store(const float* obs, const void* act, int act_is_i64, int act_dim, const float* rew,
                         const float* val, const uint8_t* term, const uint8_t* trunc, const float* logp,
                         float* obs_row, float* act_row, float* rew_row, float* val_row, float* term_row,
-                        uint8_t* trunc_row, float* logp_row, const float* rew_scale, float rew_clip, int64_t N,
-                        xb_stream_t stream) {
+                        uint8_t* trunc_row, float* logp_row, const float* rew_scale, float rew_clip, int obs_vec,
+                        int64_t N, xb_stream_t stream) {
     if (N <= 0 || act_dim < 1 || !obs || !act || !rew || !val || !term || !logp || !obs_row || !act_row ||
         !rew_row || !val_row || !term_row || !logp_row)
         return XB_E_BADARG;
+    if (obs_vec != 1 && obs_vec != 2) return XB_E_UNSUPPORTED;
     store_kernel<<<grid_for(N, 256, 4), 256, 0, (cudaStream_t)stream>>>(
         (const float4*)obs, act, act_is_i64, act_dim, rew, val, term, trunc, logp, (float4*)obs_row, act_row, rew_row,
-        val_row, term_row, trunc_row, logp_row, rew_scale, rew_clip, N);
+        val_row, term_row, trunc_row, logp_row, rew_scale, rew_clip, obs_vec, N);
     XB_LAUNCH_CHECK();
     return 0;
 }
@@ -226,10 +255,15 @@ extern "C" int xb_store(const float* obs, const void* act, int act_is_i64, int a
 extern "C" int xb_gather_obs(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* b_obs, int obs_dim,
                              const float* b_adv, float* obs_out, double* stats, xb_stream_t stream) {
     if (B <= 0 || T <= 0 || N <= 0 || !idx || !b_obs || !obs_out || (stats && !b_adv)) return XB_E_BADARG;
-    if (obs_dim < 1 || obs_dim > 4) return XB_E_UNSUPPORTED;
+    if (obs_dim < 1 || obs_dim > 8) return XB_E_UNSUPPORTED;
     int grid = grid_for(B, kGatherBlock, 8);
     cudaStream_t s = (cudaStream_t)stream;
     const float4* o = (const float4*)b_obs;
+    if (obs_dim > 4) {
+        gather_obs_wide_kernel<<<grid, kGatherBlock, 0, s>>>(idx, B, T, N, o, obs_dim, b_adv, obs_out, stats);
+        XB_LAUNCH_CHECK();
+        return 0;
+    }
     switch (obs_dim) {
         case 4: gather_obs_kernel<4><<<grid, kGatherBlock, 0, s>>>(idx, B, T, N, o, b_adv, obs_out, stats); break;
         case 3: gather_obs_kernel<3><<<grid, kGatherBlock, 0, s>>>(idx, B, T, N, o, b_adv, obs_out, stats); break;
@@ -246,7 +280,7 @@ extern "C" int xb_gather_batch(const int64_t* idx, int64_t B, int64_t T, int64_t
                                float* ret_out, float* val_out, float* adv_out, float* logp_out, double* stats,
                                xb_stream_t stream) {
     if (B <= 0 || T <= 0 || N <= 0 || !idx) return XB_E_BADARG;
-    if (obs_dim < 1 || obs_dim > 4 || act_dim < 1) return XB_E_UNSUPPORTED;
+    if (obs_dim < 1 || obs_dim > 8 || act_dim < 1) return XB_E_UNSUPPORTED;
     if ((obs_out && !b_obs) || (act_out && !b_act) || (ret_out && !b_ret) || (val_out && !b_val) ||
         ((adv_out || stats) && !b_adv) || (logp_out && !b_logp))
         return XB_E_BADARG;

@@ -1,4 +1,4 @@
-// env_classic.cu — batched CartPole-v1 / Pendulum-v1 / MountainCar-v0 step + auto-reset, one thread per environment.
+// env_classic.cu — batched CartPole-v1 / Pendulum-v1 / MountainCar-v0 / Acrobot-v1 step + auto-reset, one thread per environment.
 //
 // Replaces the per-env Python loop of DummyVecEnv_Gym.step_wait (xuance/environment/gym/gym_vec_env.py:201-212)
 // over Gym_Env.step (xuance/environment/gym/gym_env.py:43-49) over gym 0.26.2's CartPoleEnv / PendulumEnv /
@@ -46,6 +46,7 @@ constexpr double kPi = 3.141592653589793;
 
 // ---------------------------------------------------------------- per-env dynamics ---------------------------
 struct CartPole {
+    static constexpr int kObsVec = 1;   // float4s per observation row
     static constexpr bool kTrigCache = false;
     static constexpr int S = 4;
     typedef int64_t action_t;
@@ -84,6 +85,7 @@ struct CartPole {
 };
 
 struct Pendulum {
+    static constexpr int kObsVec = 1;   // float4s per observation row
     static constexpr bool kTrigCache = true;   // sin/cos(theta) of the observation are the next step's dynamics inputs
     static constexpr int S = 2;
     typedef float action_t;
@@ -143,6 +145,7 @@ struct Pendulum {
 //   terminated = position >= goal_position and velocity >= goal_velocity; reward = -1.0
 // reset(): state = [uniform(-0.6, -0.4), 0].
 struct MountainCar {
+    static constexpr int kObsVec = 1;   // float4s per observation row
     static constexpr bool kTrigCache = false;
     static constexpr int S = 2;
     typedef int64_t action_t;
@@ -170,6 +173,110 @@ struct MountainCar {
     }
 };
 
+// gym 0.26.2 AcrobotEnv (gym/envs/classic_control/acrobot.py; xuance config xuance/configs/ppo/classic_control/Acrobot-v1.yaml),
+// "book" dynamics, TimeLimit 500, restated from the published algorithm (operation order = Python's left-to-right):
+//   s_augmented = append(state, AVAIL_TORQUE[a]);  ns = rk4(_dsdt, s_augmented, [0, 0.2])   (one RK4 step, dt = 0.2)
+//   ns[0], ns[1] = wrap(., -pi, pi);  ns[2] = bound(., -4pi, 4pi);  ns[3] = bound(., -9pi, 9pi)
+//   terminated = -cos(s0) - cos(s1 + s0) > 1.0;  reward = -1.0 (0.0 on termination)
+//   obs = float32([cos s0, sin s0, cos s1, sin s1, s2, s3]);  reset: uniform(-0.1, 0.1, 4).astype(float32)
+// With m1 = m2 = l1 = I1 = I2 = 1, lc1 = lc2 = 0.5, g = 9.8 the constant sub-products of _dsdt fold exactly
+// (x*1.0, x*0.5 and 0.5*9.8 are exact), which leaves the roundings written out below.
+struct Acrobot {
+    static constexpr int kObsVec = 2;
+    static constexpr bool kTrigCache = false;
+    static constexpr int S = 4;
+    typedef int64_t action_t;
+    static constexpr bool kDiscrete = true;
+    static constexpr int kActions = 3;
+    __device__ static void draw(double (&st)[4], Pcg64& g) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) st[k] = (double)(float)pcg64_uniform(g, -0.1, 0.1 - (-0.1));   // .astype(np.float32)
+    }
+    __device__ static void observe(const double (&st)[4], float4 (&o)[2]) {
+        double s0, c0, s1, c1;
+        sincos_cr(st[0], &s0, &c0);
+        sincos_cr(st[1], &s1, &c1);
+        o[0] = make_float4((float)c0, (float)s0, (float)c1, (float)s1);
+        o[1] = make_float4((float)st[2], (float)st[3], 0.0f, 0.0f);
+    }
+    // _dsdt: (theta1, theta2, dtheta1, dtheta2, a) -> (dtheta1, dtheta2, ddtheta1, ddtheta2)
+    __device__ static void dsdt(const double (&y)[4], double a, double (&k)[4]) {
+        const double theta1 = y[0], theta2 = y[1], dtheta1 = y[2], dtheta2 = y[3];
+        const double half_pi = kPi / 2.0;
+        double s2, c2, sn, cphi2, cphi1;
+        sincos_cr(theta2, &s2, &c2);
+        sincos_cr(__dsub_rn(__dadd_rn(theta1, theta2), half_pi), &sn, &cphi2);
+        sincos_cr(__dsub_rn(theta1, half_pi), &sn, &cphi1);
+        // d1 = m1*lc1**2 + m2*(l1**2 + lc2**2 + 2*l1*lc2*cos(theta2)) + I1 + I2
+        const double d1 = __dadd_rn(__dadd_rn(__dadd_rn(0.25, __dadd_rn(1.25, c2)), 1.0), 1.0);
+        // d2 = m2*(lc2**2 + l1*lc2*cos(theta2)) + I2
+        const double d2 = __dadd_rn(__dadd_rn(0.25, __dmul_rn(0.5, c2)), 1.0);
+        const double phi2 = __dmul_rn(0.5 * 9.8, cphi2);                       // m2*lc2*g*cos(theta1 + theta2 - pi/2)
+        // phi1 = -m2*l1*lc2*dtheta2**2*sin(theta2) - 2*m2*l1*lc2*dtheta2*dtheta1*sin(theta2) + (m1*lc1 + m2*l1)*g*cos(theta1 - pi/2) + phi2
+        const double tA = __dmul_rn(__dmul_rn(-0.5, __dmul_rn(dtheta2, dtheta2)), s2);
+        const double tB = __dmul_rn(__dmul_rn(dtheta2, dtheta1), s2);
+        const double tC = __dmul_rn(1.5 * 9.8, cphi1);
+        const double phi1 = __dadd_rn(__dadd_rn(__dsub_rn(tA, tB), tC), phi2);
+        // book: ddtheta2 = (a + d2/d1*phi1 - m2*l1*lc2*dtheta1**2*sin(theta2) - phi2) / (m2*lc2**2 + I2 - d2**2/d1)
+        const double num = __dsub_rn(__dsub_rn(__dadd_rn(a, __dmul_rn(__ddiv_rn(d2, d1), phi1)),
+                                               __dmul_rn(__dmul_rn(0.5, __dmul_rn(dtheta1, dtheta1)), s2)), phi2);
+        const double den = __dsub_rn(1.25, __ddiv_rn(__dmul_rn(d2, d2), d1));
+        const double ddtheta2 = __ddiv_rn(num, den);
+        const double ddtheta1 = __ddiv_rn(-__dadd_rn(__dmul_rn(d2, ddtheta2), phi1), d1);
+        k[0] = dtheta1; k[1] = dtheta2; k[2] = ddtheta1; k[3] = ddtheta2;
+    }
+    __device__ static double wrap(double x, double m, double M) {
+        const double diff = __dsub_rn(M, m);
+        while (x > M) x = __dsub_rn(x, diff);
+        while (x < m) x = __dadd_rn(x, diff);
+        return x;
+    }
+    __device__ static double step(double (&st)[4], action_t action, bool& terminated) {
+        const double a = (double)(action - 1);                                  // AVAIL_TORQUE = [-1.0, 0.0, +1]
+        const double dt = 0.2, dt2 = 0.2 / 2.0, dt6 = 0.2 / 6.0;
+        double k1[4], k2[4], k3[4], k4[4], y[4];
+        dsdt(st, a, k1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = __dadd_rn(st[i], __dmul_rn(dt2, k1[i]));
+        dsdt(y, a, k2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = __dadd_rn(st[i], __dmul_rn(dt2, k2[i]));
+        dsdt(y, a, k3);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = __dadd_rn(st[i], __dmul_rn(dt, k3[i]));
+        dsdt(y, a, k4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {   // y0 + dt / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4)
+            const double sum = __dadd_rn(__dadd_rn(__dadd_rn(k1[i], __dmul_rn(2.0, k2[i])), __dmul_rn(2.0, k3[i])), k4[i]);
+            y[i] = __dadd_rn(st[i], __dmul_rn(dt6, sum));
+        }
+        y[0] = wrap(y[0], -kPi, kPi);
+        y[1] = wrap(y[1], -kPi, kPi);
+        const double v1 = 4 * kPi, v2 = 9 * kPi;
+        y[2] = fmin(fmax(y[2], -v1), v1);
+        y[3] = fmin(fmax(y[3], -v2), v2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st[i] = y[i];
+        double s0, c0, s10, c10;
+        sincos_cr(st[0], &s0, &c0);
+        sincos_cr(__dadd_rn(st[1], st[0]), &s10, &c10);
+        terminated = __dsub_rn(-c0, c10) > 1.0;
+        return terminated ? 0.0 : -1.0;
+    }
+};
+
+// one-float4 observation rows: array form of observe() for the kernels below
+template <class Env>
+__device__ __forceinline__ void observe_row(const double (&st)[Env::S], float4 (&o)[Env::kObsVec]) {
+    if constexpr (Env::kObsVec == 1) o[0] = Env::observe(st);
+    else Env::observe(st, o);
+}
+template <class Env>
+__device__ __forceinline__ void put_row(float4* dst, int64_t e, const float4 (&o)[Env::kObsVec]) {
+#pragma unroll
+    for (int v = 0; v < Env::kObsVec; ++v) dst[e * Env::kObsVec + v] = o[v];
+}
+
 // ---------------------------------------------------------------- kernels ------------------------------------
 template <class Env>
 __device__ __forceinline__ Pcg64 load_rng(const uint64_t* rng, int64_t N, int64_t e) {
@@ -193,7 +300,9 @@ __global__ void __launch_bounds__(128) env_reset_kernel(double* __restrict__ sta
     rng[N + e] = g.lo;
     elapsed[e] = 0;
     ep_score[e] = 0.0;
-    obs[e] = Env::observe(st);
+    float4 o[Env::kObsVec];
+    observe_row<Env>(st, o);
+    put_row<Env>(obs, e, o);
 }
 
 template <class Env>
@@ -219,8 +328,9 @@ __global__ void __launch_bounds__(128)
     bool truncated = el >= max_steps;
     score = __dadd_rn(score, reward);          // Gym_Env._episode_score += reward (fp64)
 
-    float4 o = Env::observe(st);
-    obs[e] = o;
+    float4 o[Env::kObsVec];
+    observe_row<Env>(st, o);
+    put_row<Env>(obs, e, o);
     rew[e] = (float)reward;
     term[e] = terminated ? 1 : 0;
     trunc[e] = truncated ? 1 : 0;
@@ -239,10 +349,10 @@ __global__ void __launch_bounds__(128)
         rng[N + e] = g.lo;
         el = 0;
         score = 0.0;
-        o = Env::observe(st);
-        reset_obs[e] = o;
+        observe_row<Env>(st, o);
+        put_row<Env>(reset_obs, e, o);
     }
-    if (next_obs) next_obs[e] = o;
+    if (next_obs) put_row<Env>(next_obs, e, o);
 #pragma unroll
     for (int k = 0; k < Env::S; ++k) state[k * N + e] = st[k];
     elapsed[e] = el;
@@ -430,6 +540,8 @@ extern "C" int xb_env_reset(int env_kind, double* state, uint64_t* rng, int32_t*
         env_reset_kernel<Pendulum><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (float4*)obs, n_draws, N);
     else if (env_kind == XB_ENV_MOUNTAINCAR)
         env_reset_kernel<MountainCar><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (float4*)obs, n_draws, N);
+    else if (env_kind == XB_ENV_ACROBOT)
+        env_reset_kernel<Acrobot><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (float4*)obs, n_draws, N);
     else
         return XB_E_UNSUPPORTED;
     XB_LAUNCH_CHECK();
@@ -460,6 +572,11 @@ extern "C" int xb_env_step(int env_kind, double* state, uint64_t* rng, int32_t* 
                                                             (float4*)obs, (float4*)next_obs, rew, term, trunc,
                                                             (float4*)reset_obs, ep_step_out, ep_score_out, ep_stats,
                                                             max_episode_steps, N);
+    else if (env_kind == XB_ENV_ACROBOT)
+        env_step_kernel<Acrobot><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (const int64_t*)actions,
+                                                        (float4*)obs, (float4*)next_obs, rew, term, trunc,
+                                                        (float4*)reset_obs, ep_step_out, ep_score_out, ep_stats,
+                                                        max_episode_steps, N);
     else
         return XB_E_UNSUPPORTED;
     XB_LAUNCH_CHECK();

@@ -7,7 +7,7 @@ import torch
 
 from . import _lib
 
-ENV_KINDS = {"CartPole-v1": 0, "Pendulum-v1": 1, "MountainCar-v0": 2}
+ENV_KINDS = {"CartPole-v1": 0, "Pendulum-v1": 1, "MountainCar-v0": 2, "Acrobot-v1": 3}
 GAE_VARIANTS = {"auto": 0, "ldg": 1, "tma": 2}
 
 
@@ -73,7 +73,8 @@ def store(obs, act, rew, val, term, trunc, logp, obs_row, act_row, rew_row, val_
     act_dim = 1 if is_i64 else act.numel() // N
     _lib.call("xb_store", _p(obs, F32), _p(act), int(is_i64), act_dim, _p(rew, F32), _p(val, F32), _p(term, U8),
               _p(trunc, U8), _p(logp, F32), _p(obs_row, F32), _p(act_row, F32), _p(rew_row, F32), _p(val_row, F32),
-              _p(term_row, F32), _p(trunc_row, U8), _p(logp_row, F32), _p(rew_std, F32), float(rew_clip), N, _stream())
+              _p(term_row, F32), _p(trunc_row, U8), _p(logp_row, F32), _p(rew_std, F32), float(rew_clip),
+              obs.shape[-1] // 4, N, _stream())
 
 
 def gae(rew, val, term, boot_last, adv, ret, gamma, lam, trunc=None, boot=None, stats=None, use_gae=True, variant="auto"):

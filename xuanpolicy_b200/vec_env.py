@@ -24,6 +24,7 @@ SPECS = {
     "CartPole-v1": dict(kind=0, state_dim=4, obs_dim=4, max_steps=500),
     "Pendulum-v1": dict(kind=1, state_dim=2, obs_dim=3, max_steps=200),
     "MountainCar-v0": dict(kind=2, state_dim=2, obs_dim=2, max_steps=200),
+    "Acrobot-v1": dict(kind=3, state_dim=4, obs_dim=6, max_steps=500),
 }
 
 
@@ -46,7 +47,11 @@ def make_spaces(env_id):
         return Box(-high, high), Box(-2.0, 2.0, shape=(1,))
     if env_id == "MountainCar-v0":
         return Box(np.array([-1.2, -0.07], np.float32), np.array([0.6, 0.07], np.float32)), Discrete(3)
-    raise NotImplementedError("only CartPole-v1, Pendulum-v1 and MountainCar-v0 have device kernels (got %r)" % (env_id,))
+    if env_id == "Acrobot-v1":
+        high = np.array([1.0, 1.0, 1.0, 1.0, 4 * np.pi, 9 * np.pi], np.float32)
+        return Box(-high, high), Discrete(3)
+    raise NotImplementedError("only CartPole-v1, Pendulum-v1, MountainCar-v0 and Acrobot-v1 have device kernels (got %r)"
+                              % (env_id,))
 
 
 class EnvFn:
@@ -132,9 +137,11 @@ class DummyVecEnv_Gym:
             self._state = torch.zeros((self._state_dim, N), dtype=torch.float64, device=dev)
             self._elapsed = torch.zeros(N, dtype=torch.int32, device=dev)
             self._ep_score = torch.zeros(N, dtype=torch.float64, device=dev)
-            self._obs = torch.zeros((N, 4), dtype=torch.float32, device=dev)
-            self._next_obs = torch.zeros((N, 4), dtype=torch.float32, device=dev)
-            self._reset_obs = torch.zeros((N, 4), dtype=torch.float32, device=dev)
+            # observation rows are whole float4s: 4 floats (obs_dim <= 4) or 8 (wide rows, Acrobot-v1's 6)
+            self._obs_row = 4 if self._obs_dim <= 4 else 8
+            self._obs = torch.zeros((N, self._obs_row), dtype=torch.float32, device=dev)
+            self._next_obs = torch.zeros((N, self._obs_row), dtype=torch.float32, device=dev)
+            self._reset_obs = torch.zeros((N, self._obs_row), dtype=torch.float32, device=dev)
             self._rew = torch.zeros(N, dtype=torch.float32, device=dev)
             self._term = torch.zeros(N, dtype=torch.uint8, device=dev)
             self._trunc = torch.zeros(N, dtype=torch.uint8, device=dev)
