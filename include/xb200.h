@@ -137,6 +137,13 @@ int xb_pack_records(const float* b_obs, const float* b_act, const float* b_logp,
                     const float* b_ret, float* rec, int64_t TN, xb_stream_t stream);
 int xb_gather_records(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* rec, int obs_dim,
                       float* obs_out, float* scal_out, double* stats, xb_stream_t stream);
+/* xb_gather_records fused with the MLP's first layer (Basic_MLP: Linear(obs_dim, H) + LeakyReLU,
+ * xuance/torch/representations/mlp.py:40-51; same arithmetic as xb_mlp_trunk_fwd, bit-identical output):
+ * additionally writes h1 f32 [B][H] = leaky_relu(obs W0^T + b0), so the gathered rows feed the layer from registers and the
+ * latency-bound gather hides behind the store-bound layer — one launch instead of two per update. */
+int xb_gather_trunk_fwd(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* rec, int obs_dim, const float* W0,
+                        const float* b0, float slope, int H, float* obs_out, float* scal_out, double* stats, float* h1,
+                        xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * (4b) PPO-Clip loss forward + backward, fused with the gather of the per-transition scalars.

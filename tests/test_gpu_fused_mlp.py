@@ -163,3 +163,24 @@ def test_tensor_core_update_matches_reference_golden():
         for k, p in pol.named_parameters():
             ok, err = rel_close(p.detach().cpu().numpy(), g["p1_%s/%s" % (tag, k)], 1e-5)
             assert ok, (tag, k, err)
+
+
+@pytest.mark.parametrize("obs_dim,H,B", [(3, 128, 65536), (4, 128, 5000), (3, 256, 4097), (2, 128, 2048)])
+def test_gather_trunk_fwd_equals_gather_then_trunk(obs_dim, H, B):
+    """xb_gather_trunk_fwd (gather + first MLP layer in one launch) is bit-identical to xb_gather_records followed by
+    xb_mlp_trunk_fwd: gathered observations, packed scalars, advantage statistics and h1."""
+    from xuanpolicy_b200 import ops
+    T, N = 64, 1031
+    gen = torch.Generator(device="cuda").manual_seed(obs_dim * 1000 + H)
+    rec = torch.randn((T * N, 8), device="cuda", generator=gen)
+    idx = torch.randperm(T * N, device="cuda", generator=gen)[:B].contiguous()
+    w0, b0 = torch.randn((H, obs_dim), device="cuda", generator=gen), torch.randn(H, device="cuda", generator=gen)
+    obs_a, scal_a = torch.empty((B, obs_dim), device="cuda"), torch.empty((B, 4), device="cuda")
+    st_a, h_a = torch.zeros(2, dtype=torch.float64, device="cuda"), torch.empty((B, H), device="cuda")
+    ops.gather_records(idx, T, N, rec, obs_dim, obs_a, scal_a, stats=st_a)
+    ops.mlp_trunk_fwd(obs_a, w0, b0, 0.01, h_a)
+    obs_b, scal_b = torch.empty_like(obs_a), torch.empty_like(scal_a)
+    st_b, h_b = torch.zeros_like(st_a), torch.empty_like(h_a)
+    ops.gather_trunk_fwd(idx, T, N, rec, obs_dim, w0, b0, 0.01, obs_b, scal_b, h_b, stats=st_b)
+    assert torch.equal(obs_a, obs_b) and torch.equal(scal_a, scal_b) and torch.equal(h_a, h_b)
+    assert torch.allclose(st_a, st_b, rtol=1e-12, atol=1e-9)

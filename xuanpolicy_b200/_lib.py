@@ -37,6 +37,7 @@ SIGNATURES = {
     "xb_kl_coef_adapt": [_vp, _vp, _f32, _i64, _vp],
     "xb_pack_records": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "xb_gather_records": [_vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp],
+    "xb_gather_trunk_fwd": [_vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp],
     "xb_sample_categorical": [_vp, _i32, _u64, _vp, _u64, _vp, _vp, _i64, _vp],
     "xb_sample_gaussian": [_vp, _vp, _i32, _u64, _vp, _u64, _vp, _vp, _i64, _vp],
     "xb_counter_add": [_vp, _u64, _vp],

@@ -157,14 +157,15 @@ class FusedActorCritic:
         return b["act"], b["v"][:, 0]
 
     # ---------------------------------------------------------------------------------------------- forward / backward
-    def forward(self, obs, refresh=True):
+    def forward(self, obs, refresh=True, trunk_done=False):
         """obs: CUDA fp32 [B, obs_dim] with contiguous rows (a column slice of the float4 observation rows is fine).
         Returns (act_out [B, A], v [B]); the activations stay in per-batch-size buffers for `backward`."""
         B = obs.shape[0]
         b = self._buffers(B)
         if refresh:
             self.refresh_weights()
-        self.stage_trunk(obs, b)
+        if not trunk_done:              # the gather kernel already produced h1 for these rows (xb_gather_trunk_fwd)
+            self.stage_trunk(obs, b)
         self.stage_hidden(b)
         self._last = (obs, b)
         return b["act"], b["v"][:, 0]

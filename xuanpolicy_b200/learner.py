@@ -262,7 +262,17 @@ class PPOCLIP_Learner:
         the minibatch advantage statistics."""
         mb = self._minibatch_buffers(idx.numel(), memory.obs_dim)
         want = memory.use_advnorm and compute_stats
-        if memory.packed and self.value_clip <= 0:   # one 32-byte record per sample: obs + {act, old_logp, adv, ret}
+        fused = self._fused if (self._fused is not None and idx.numel() >= FusedActorCritic.MIN_ROWS) else None
+        mb["trunk_done"] = False
+        if (fused is not None and memory.packed and self.value_clip <= 0 and fused.obs_dim <= 4
+                and os.environ.get("XB_GATHER_TRUNK", "1") != "0"):
+            # gather + the MLP's first layer in one launch: the gathered rows feed the layer from registers
+            b = fused._buffers(idx.numel())
+            ops.gather_trunk_fwd(idx, memory.n_size, memory.n_envs, memory._rec, memory.obs_dim, fused.l0.weight.data,
+                                 fused.l0.bias.data, fused.slope, mb["obs"], mb["scal"], b["h1"],
+                                 stats=mb["stats"] if want else None)
+            mb["trunk_done"] = True
+        elif memory.packed and self.value_clip <= 0:   # one 32-byte record per sample: obs + {act, old_logp, adv, ret}
             ops.gather_records(idx, memory.n_size, memory.n_envs, memory._rec, memory.obs_dim, mb["obs"], mb["scal"],
                                stats=mb["stats"] if want else None)
         else:
@@ -282,7 +292,7 @@ class PPOCLIP_Learner:
             self._fused.norm_sink = (self._flat, self.clip_grad_norm if self.use_grad_clip else 0.0) if (fused is not None and single) else None
             self._fused.norm_done = False
         if fused is not None:                        # tcgen05 dense kernels; weights re-split after every Adam step
-            act_out, v_pred = fused.forward(mb["obs"], refresh=not fused.splits_fresh)
+            act_out, v_pred = fused.forward(mb["obs"], refresh=not fused.splits_fresh, trunk_done=mb.get("trunk_done", False))
             a_dist = fused.dist_params(act_out)
         else:
             _, a_dist, v_pred = self.policy(mb["obs"])

@@ -174,6 +174,12 @@ def gather_records(idx, T, N, rec, obs_dim, obs_out, scal_out, stats=None):
               _p(scal_out, F32), _p(stats, F64), _stream())
 
 
+def gather_trunk_fwd(idx, T, N, rec, obs_dim, w0, b0, slope, obs_out, scal_out, h1, stats=None):
+    """gather_records + the MLP's first layer in one launch (xb_gather_trunk_fwd)."""
+    _lib.call("xb_gather_trunk_fwd", _p(idx, I64), idx.numel(), T, N, _p(rec, F32), obs_dim, _p(w0, F32), _p(b0, F32),
+              float(slope), w0.shape[0], _p(obs_out, F32), _p(scal_out, F32), _p(stats, F64), _p(h1, F32), _stream())
+
+
 def sample_categorical(logits, seed, counter, offset, act_out, logp_out):
     N, A = logits.shape
     _lib.call("xb_sample_categorical", _p(logits, F32), A, seed, _p(counter, I64), offset, _p(act_out, I64),
