@@ -263,10 +263,14 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
     add("gae_and_pack", lambda: mem.finish_rollout(agent._boot_last), (20 + 1 + (64 if mem._rec is not None else 0)) * N * T, 1)
     idx = agent._perm[:B]
     agent._device_permutation()
-    add("gather_records" if mem.packed else "gather_obs_advstats", lambda: lr.stage_gather(mem, idx),
-        B * ((8 + 32 + 4 * od + 16) if mem.packed else (8 + 16 + 4 * od + 4)), launches_per_step["updates"])
-    mb = lr.stage_gather(mem, idx)
     fused = lr._fused if (lr._fused is not None and B >= lr._fused.MIN_ROWS) else None
+    Hh = agent.config.representation_hidden_size[-1]
+    mb = lr.stage_gather(mem, idx)
+    if mb.get("trunk_done"):     # gather fused with the MLP's first layer: + the B x H activations it writes
+        add("gather_trunk_fwd", lambda: lr.stage_gather(mem, idx), B * (8 + 32 + 4 * od + 16 + 4 * Hh), launches_per_step["updates"])
+    else:
+        add("gather_records" if mem.packed else "gather_obs_advstats", lambda: lr.stage_gather(mem, idx),
+            B * ((8 + 32 + 4 * od + 16) if mem.packed else (8 + 16 + 4 * od + 4)), launches_per_step["updates"])
     with torch.no_grad():
         if fused is not None:
             act_out, v_pred = fused.forward(mb["obs"])
@@ -308,8 +312,9 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
         dact = torch.randn((B, A_out), device="cuda") / B
         dv2 = torch.randn((B, 1), device="cuda") / B
         f4 = 4 * B * H
-        add("mlp_split_weights", lambda: fused.refresh_weights(), 2 * H * H * 4 * 5, upd + 1)
-        add("mlp_trunk_fwd", lambda: fused.stage_trunk(obs_u, bu), B * od * 4 + f4, upd)
+        adam_split = os.environ.get("XB_ADAM_SPLIT", "1") != "0"
+        add("mlp_split_weights", lambda: fused.refresh_weights(), 2 * H * H * 4 * 5, 1 if adam_split else upd + 1)
+        add("mlp_trunk_fwd", lambda: fused.stage_trunk(obs_u, bu), B * od * 4 + f4, 0 if mb.get("trunk_done") else upd)
         add("dense_fwd2_tc", lambda: fused.stage_hidden(bu), 3 * f4 + B * (A_out + 1) * 4, upd, flops=2 * 2.0 * B * H * H)
         add("dense_dgrad_tc", lambda: fused.stage_dgrad(bu, dact, dv2), 4 * f4 + B * (A_out + 1) * 4, upd, flops=2.0 * B * 2 * H * H)
         add("dense_wgrad_tc", lambda: fused.stage_wgrad(bu, dact, dv2), 3 * f4 + B * (A_out + 1) * 4, upd,
@@ -341,7 +346,11 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
         add("mlp_head_bwd_act", lambda: ops.head_bwd_act(dout, yb, w2, 0.01, dzb, dbb, dw2, db2, ws32), B * (2 * H + A_out) * 4, 2 * upd)
         add("mlp_act_bias_bwd", lambda: ops.act_bias_bwd(dyb, yb, 0.01, dzb, dbb, ws32), B * H * 12, 1 * upd)
     snap = agent._snapshot()
-    add("clip_adam", lambda: lr.stage_optimizer(), lr._flat.n * (4 + 16 + 12), launches_per_step["updates"])
+    def optimizer_stage():     # what the update graph runs after the backward tail: Adam (+ operand split); norm alone otherwise
+        if fused is not None:
+            fused.norm_done = agent.world_size == 1 and os.environ.get("XB_TAIL_NORM", "1") != "0"
+        lr.stage_optimizer()
+    add("adam_step", optimizer_stage, lr._flat.n * (16 + 12), launches_per_step["updates"])
     agent._restore(snap)
     if with_c4:
         out.update(large_shape_rooflines(flush, peak))
