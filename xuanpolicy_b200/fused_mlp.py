@@ -14,6 +14,8 @@ It replaces torch autograd + cuBLAS SIMT sgemm for the supported shape (one hidd
 LeakyReLU, action dim <= 2, obs dim <= 8 — every classic-control config of the reference); anything else keeps the
 torch path.  No CPU path: construction requires CUDA parameters.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -92,6 +94,8 @@ class FusedActorCritic:
         self.norm_sink, self.norm_done = None, False
         # True while the hi/lo operand copies are known to match the weights (the Adam launch rewrote them)
         self.splits_fresh = False
+        self.fork_wgrad = os.environ.get("XB_FORK_WGRAD", "0") == "1"
+        self._side = None
 
     # every tensor below is read at launch time: parameters may have been re-pointed (FlatAdamState) since __init__
     def refresh_weights(self):
@@ -184,7 +188,22 @@ class FusedActorCritic:
         if b["dz1"] is None:
             b["dz1"] = torch.empty(B, self.H, dtype=torch.float32, device=self.device)
         dv2 = dv.reshape(B, 1)
-        self.stage_dgrad(b, dact, dv2)
-        self.stage_wgrad(b, dact, dv2)
-        self.stage_trunk_wgrad(obs, b)
+        if self.fork_wgrad:
+            # opt-in experiment (XB_FORK_WGRAD=1): dgrad -> trunk wgrad and the (independent) hidden-layer wgrad as two graph
+            # branches, so that wgrad CTAs could fill the SMs dgrad's last, partially filled round of tiles leaves idle.
+            # Measured: no gain (epoch graph 1.2255 vs 1.2235 ms) — both kernels are one-CTA-per-SM persistent loops with
+            # static work shares, so the branch that starts late still ends late.
+            cur = torch.cuda.current_stream(self.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            self._side.wait_stream(cur)
+            self.stage_dgrad(b, dact, dv2)
+            with torch.cuda.stream(self._side):
+                self.stage_wgrad(b, dact, dv2)
+            self.stage_trunk_wgrad(obs, b)
+            cur.wait_stream(self._side)
+        else:
+            self.stage_dgrad(b, dact, dv2)
+            self.stage_wgrad(b, dact, dv2)
+            self.stage_trunk_wgrad(obs, b)
         self.stage_tail(dls64, dls32)
