@@ -232,6 +232,80 @@ __global__ void __launch_bounds__(256)
         adv[i] = (adv[i] - m) / denom;
 }
 
+// ------------------------------------------------------------------------------------------------ gather + trunk layer
+// xb_gather_records fused with the MLP's first layer (mlp_trunk.cu trunk_fwd_kernel: Linear(obs_dim, H) + LeakyReLU,
+// xuance/torch/representations/mlp.py:40-51): the gathered observation never makes a round trip through HBM before the
+// layer that consumes it, and the launch-latency-bound gather hides behind the store-bound layer (B x H floats written).
+// Warp-centric: a warp first gathers 32 rows (lane l loads the index and the 32-byte record of row base + l: 32
+// independent sector reads in flight, emits obs_out / scal_out and carries the advantage statistics), then walks those 32
+// rows, broadcasting each row's observation with shuffles while every lane computes its 4 output features with exactly
+// trunk_fwd_kernel's arithmetic and the warp stores one coalesced 512-byte piece of h1 per row.  H = 128: one warp covers a
+// row; H = 256: two warps (feature halves) walk the same rows, only the first emits the gathered outputs.
+template <int OBS_DIM>
+__global__ void __launch_bounds__(256)
+    gather_trunk_fwd_kernel(const int64_t* __restrict__ idx, int64_t B, int64_t T, int64_t N, const Record* __restrict__ rec,
+                            const float* __restrict__ W0, const float* __restrict__ b0, float slope, int H,
+                            float* __restrict__ obs_out, float4* __restrict__ scal_out, double* __restrict__ stats,
+                            float4* __restrict__ h1) {
+    __shared__ double smem[64];
+    const int tpr = H >> 2;                     // float4 outputs per row
+    const int wpr = tpr >> 5;                   // warps per row (1 or 2)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = warp % wpr;                // which 128-feature slice of the row this warp computes
+    const int q = half * 32 + lane;
+    float w[4][OBS_DIM], bias[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        bias[e] = b0[4 * q + e];
+#pragma unroll
+        for (int i = 0; i < OBS_DIM; ++i) w[e][i] = W0[(4 * q + e) * OBS_DIM + i];
+    }
+    double s = 0.0, ss = 0.0;
+    const int64_t n_chunks = (B + 31) >> 5;
+    const int64_t streams = (int64_t)gridDim.x * (blockDim.x >> 5) / wpr;
+    for (int64_t c = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) / wpr; c < n_chunks; c += streams) {
+        const int64_t b = c * 32 + lane;
+        Record r;
+        r.obs = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < B) {
+            r = rec[flat_to_row(idx[b], T, N)];
+            if (half == 0) {
+                if (OBS_DIM == 4) {
+                    reinterpret_cast<float4*>(obs_out)[b] = r.obs;
+                } else {
+                    float* dst = obs_out + b * OBS_DIM;
+                    dst[0] = r.obs.x;
+                    if (OBS_DIM > 1) dst[1] = r.obs.y;
+                    if (OBS_DIM > 2) dst[2] = r.obs.z;
+                }
+                scal_out[b] = r.s;
+                const double a = (double)r.s.z;
+                s += a;
+                ss += a * a;
+            }
+        }
+        const int rows = (int)((B - c * 32) < 32 ? (B - c * 32) : 32);
+#pragma unroll 4
+        for (int j = 0; j < rows; ++j) {
+            float x[4];
+            x[0] = __shfl_sync(0xffffffffu, r.obs.x, j);
+            if (OBS_DIM > 1) x[1] = __shfl_sync(0xffffffffu, r.obs.y, j);
+            if (OBS_DIM > 2) x[2] = __shfl_sync(0xffffffffu, r.obs.z, j);
+            if (OBS_DIM > 3) x[3] = __shfl_sync(0xffffffffu, r.obs.w, j);
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float a = bias[e];
+#pragma unroll
+                for (int i = 0; i < OBS_DIM; ++i) a += x[i] * w[e][i];
+                o[e] = a > 0.f ? a : a * slope;
+            }
+            h1[(c * 32 + j) * tpr + q] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    if (stats) finish_stats(s, ss, g_partials, &g_ticket, stats, smem);
+}
+
 }  // namespace xb
 
 using namespace xb;
@@ -318,80 +392,6 @@ extern "C" int xb_gather_records(const int64_t* idx, int64_t B, int64_t T, int64
     }
     XB_LAUNCH_CHECK();
     return 0;
-}
-
-// ------------------------------------------------------------------------------------------------ gather + trunk layer
-// xb_gather_records fused with the MLP's first layer (mlp_trunk.cu trunk_fwd_kernel: Linear(obs_dim, H) + LeakyReLU,
-// xuance/torch/representations/mlp.py:40-51): the gathered observation never makes a round trip through HBM before the
-// layer that consumes it, and the launch-latency-bound gather hides behind the store-bound layer (B x H floats written).
-// Warp-centric: a warp first gathers 32 rows (lane l loads the index and the 32-byte record of row base + l: 32
-// independent sector reads in flight, emits obs_out / scal_out and carries the advantage statistics), then walks those 32
-// rows, broadcasting each row's observation with shuffles while every lane computes its 4 output features with exactly
-// trunk_fwd_kernel's arithmetic and the warp stores one coalesced 512-byte piece of h1 per row.  H = 128: one warp covers a
-// row; H = 256: two warps (feature halves) walk the same rows, only the first emits the gathered outputs.
-template <int OBS_DIM>
-__global__ void __launch_bounds__(256)
-    gather_trunk_fwd_kernel(const int64_t* __restrict__ idx, int64_t B, int64_t T, int64_t N, const Record* __restrict__ rec,
-                            const float* __restrict__ W0, const float* __restrict__ b0, float slope, int H,
-                            float* __restrict__ obs_out, float4* __restrict__ scal_out, double* __restrict__ stats,
-                            float4* __restrict__ h1) {
-    __shared__ double smem[64];
-    const int tpr = H >> 2;                     // float4 outputs per row
-    const int wpr = tpr >> 5;                   // warps per row (1 or 2)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int half = warp % wpr;                // which 128-feature slice of the row this warp computes
-    const int q = half * 32 + lane;
-    float w[4][OBS_DIM], bias[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        bias[e] = b0[4 * q + e];
-#pragma unroll
-        for (int i = 0; i < OBS_DIM; ++i) w[e][i] = W0[(4 * q + e) * OBS_DIM + i];
-    }
-    double s = 0.0, ss = 0.0;
-    const int64_t n_chunks = (B + 31) >> 5;
-    const int64_t streams = (int64_t)gridDim.x * (blockDim.x >> 5) / wpr;
-    for (int64_t c = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) / wpr; c < n_chunks; c += streams) {
-        const int64_t b = c * 32 + lane;
-        Record r;
-        r.obs = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (b < B) {
-            r = rec[flat_to_row(idx[b], T, N)];
-            if (half == 0) {
-                if (OBS_DIM == 4) {
-                    reinterpret_cast<float4*>(obs_out)[b] = r.obs;
-                } else {
-                    float* dst = obs_out + b * OBS_DIM;
-                    dst[0] = r.obs.x;
-                    if (OBS_DIM > 1) dst[1] = r.obs.y;
-                    if (OBS_DIM > 2) dst[2] = r.obs.z;
-                }
-                scal_out[b] = r.s;
-                const double a = (double)r.s.z;
-                s += a;
-                ss += a * a;
-            }
-        }
-        const int rows = (int)((B - c * 32) < 32 ? (B - c * 32) : 32);
-#pragma unroll 4
-        for (int j = 0; j < rows; ++j) {
-            float x[4];
-            x[0] = __shfl_sync(0xffffffffu, r.obs.x, j);
-            if (OBS_DIM > 1) x[1] = __shfl_sync(0xffffffffu, r.obs.y, j);
-            if (OBS_DIM > 2) x[2] = __shfl_sync(0xffffffffu, r.obs.z, j);
-            if (OBS_DIM > 3) x[3] = __shfl_sync(0xffffffffu, r.obs.w, j);
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float a = bias[e];
-#pragma unroll
-                for (int i = 0; i < OBS_DIM; ++i) a += x[i] * w[e][i];
-                o[e] = a > 0.f ? a : a * slope;
-            }
-            h1[(c * 32 + j) * tpr + q] = make_float4(o[0], o[1], o[2], o[3]);
-        }
-    }
-    if (stats) finish_stats(s, ss, g_partials, &g_ticket, stats, smem);
 }
 
 extern "C" int xb_gather_trunk_fwd(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* rec, int obs_dim,
