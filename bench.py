@@ -181,7 +181,10 @@ def count_launches(agent):
         tail_norm = agent.world_size == 1 and os.environ.get("XB_TAIL_NORM", "1") != "0"   # norm taken by the tail launch
         adam_split = os.environ.get("XB_ADAM_SPLIT", "1") != "0"                          # weight split done by the Adam launch
         gather_trunk = os.environ.get("XB_GATHER_TRUNK", "1") != "0"                     # gather + first layer in one launch
-        per_update = 1 + (0 if adam_split else 1) + (0 if gather_trunk else 1) + 1 + 1 + 1 + 1 + 1 + 1 + (1 if tail_norm else 2)
+        fused_loss = agent.learner._fused_loss_ok(agent.memory, agent.learner._fused)      # loss in the forward epilogue
+        # gather(+trunk), [split], [trunk], hidden(+loss), [loss], dgrad, wgrad, trunk wgrad, tail(+norm), [norm], adam(+split)
+        per_update = (1 + (0 if adam_split else 1) + (0 if gather_trunk else 1) + 1 + (0 if fused_loss else 1) + 1 + 1 + 1 + 1
+                      + (1 if tail_norm else 2))
     else:
         per_rollout = T * (3 + 5) + 5 + 2 + 1  # per step: sample, env_step, store, 3 bias+act, 2 head; bootstrap fwd; GAE + pack; counter
         per_update = 1 + 1 + 2 + 5 + 3         # gather, loss, grad-norm + adam, fwd: 3 bias+act + 2 head, bwd: 2 head+act + 1 act+bias

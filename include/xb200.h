@@ -378,6 +378,22 @@ int xb_dense_fwd2(const float* X, int64_t M, int K, int N, float slope, const fl
  *                           h1 = leaky_relu(W0 obs + b0) is generated by the operand warps straight into tensor memory
  *                           (obs_dim <= 4, H in {64, 128}), then both hidden layers + heads as in xb_dense_fwd2.
  *                           Y0 / Y1 may both be NULL: only the head outputs are produced. */
+/* xb_dense_fwd2 (actor | critic hidden layers + heads) with xb_ppo_loss_* fused into its epilogue: the epilogue thread that
+ * holds a row's head outputs turns them straight into dL/d(mu | logits) (actor CTA) and dL/dv (critic CTA) with the formulas of
+ * ppoclip_learner.py:33-44 — no loss launch, no round trip of the head outputs.
+ *   scal        f32 [M][4] = {act, old_logp, adv, ret} per row (xb_gather_records / xb_gather_trunk_fwd); 16-byte aligned
+ *   adv_stats   nullable (sum, sumsq) over adv_count samples -> on-the-fly advantage normalisation
+ *   logstd      Gaussian actor (n_head0 = 1): f32 [1] shared log-std, dlogstd fp64 [1] receives its gradient;
+ *               NULL: Categorical actor with n_head0 = 2 logits.  clip_range <= 0 selects the A2C / PG surrogate.
+ *   dact f32 [M][n_head0], dv f32 [M]: gradients w.r.t. the head outputs (inputs of xb_dense_dgrad / xb_dense_wgrad)
+ *   loss_partials fp64 [148 * 8], loss_ticket u32 [1] (zero once): scratch; scalars fp64 [8] as xb_ppo_loss_* (deterministic). */
+int xb_dense_fwd2_loss(const float* X, int64_t M, int K, int N, float slope, const float* Whi0, const float* Wlo0,
+                       const float* bias0, float* Y0, const float* head_w0, const float* head_b0, int n_head0,
+                       float* head_out0, const float* Whi1, const float* Wlo1, const float* bias1, float* Y1,
+                       const float* head_w1, const float* head_b1, int n_head1, float* head_out1, int b_resident,
+                       const float* scal, const double* adv_stats, int64_t adv_count, float clip_range, float vf_coef,
+                       float ent_coef, float inv_batch, const float* logstd, float* dact, float* dv, double* loss_partials,
+                       uint32_t* loss_ticket, double* scalars, double* dlogstd, xb_stream_t stream);
 int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const float* W0, const float* b0, int64_t M, int H,
                         float slope, const float* Whi0, const float* Wlo0, const float* bias0, float* Y0,
                         const float* head_w0, const float* head_b0, int n_head0, float* head_out0, const float* Whi1,

@@ -184,3 +184,65 @@ def test_gather_trunk_fwd_equals_gather_then_trunk(obs_dim, H, B):
     ops.gather_trunk_fwd(idx, T, N, rec, obs_dim, w0, b0, 0.01, obs_b, scal_b, h_b, stats=st_b)
     assert torch.equal(obs_a, obs_b) and torch.equal(scal_a, scal_b) and torch.equal(h_a, h_b)
     assert torch.allclose(st_a, st_b, rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("env_id,hidden,B,clip,advnorm", [("Pendulum-v1", 128, 65536, 0.2, True), ("CartPole-v1", 128, 5000, 0.2, True),
+                                                          ("Pendulum-v1", 256, 4096, 0.2, False), ("CartPole-v1", 128, 2048, 0.0, True)])
+def test_loss_fused_into_the_forward_epilogue_equals_the_loss_kernel(env_id, hidden, B, clip, advnorm):
+    """xb_dense_fwd2_loss: the PPO loss forward + backward computed in the epilogue of the hidden-layer launch gives the same
+    dL/d(head outputs), log scalars and log-std gradient as xb_dense_fwd2 followed by xb_ppo_loss_* on its outputs."""
+    import xuanpolicy_b200 as xb
+    from xuanpolicy_b200 import ops
+    from xuanpolicy_b200.fused_mlp import FusedActorCritic
+    from xuanpolicy_b200.learner import FlatAdamState
+    from xuanpolicy_b200.policies import make_policy
+    obs_space, act_space = xb.make_spaces(env_id)
+    policy = make_policy(obs_space, act_space, hidden=(hidden,), device="cuda", seed=4)
+    with torch.no_grad():
+        for p in policy.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    FlatAdamState(policy, torch.optim.Adam(policy.parameters(), 1e-3), None)
+    fused = FusedActorCritic(policy)
+    g = torch.Generator(device="cuda").manual_seed(B + 1)
+    obs = torch.randn(B, 4, device="cuda", generator=g)[:, :obs_space.shape[0]]
+    act_out, v = fused.forward(obs)
+    act_out, v = act_out.clone(), v.clone().contiguous()
+    gauss = fused.gaussian
+    scal = torch.empty(B, 4, device="cuda")                        # {act, old_logp, adv, ret}
+    if gauss:
+        logstd = policy.actor.logstd.detach()
+        scal[:, 0] = act_out[:, 0] + logstd.exp() * torch.randn(B, device="cuda", generator=g)
+        logp = -((scal[:, 0] - act_out[:, 0]) ** 2) / (2 * (2 * logstd).exp()) - logstd - 0.9189385332046727
+    else:
+        logstd = None
+        scal[:, 0] = torch.randint(0, 2, (B,), device="cuda", generator=g).float()
+        logp = torch.log_softmax(act_out, -1).gather(1, scal[:, :1].long())[:, 0]
+    scal[:, 1] = logp + 0.1 * torch.randn(B, device="cuda", generator=g)
+    scal[:, 2] = torch.randn(B, device="cuda", generator=g) * 2 + 0.3
+    scal[:, 3] = v + torch.randn(B, device="cuda", generator=g)
+    stats = torch.stack([scal[:, 2].double().sum(), (scal[:, 2].double() ** 2).sum()]) if advnorm else None
+    kw = dict(clip_range=clip, vf_coef=0.25, ent_coef=0.01, inv_batch=1.0 / B, adv_stats=stats, adv_count=B, packed=scal)
+    s_ref = torch.zeros(8, dtype=torch.float64, device="cuda")
+    dv_ref = torch.empty(B, device="cuda")
+    dact_ref = torch.empty_like(act_out)
+    if gauss:
+        dls_ref = torch.zeros(1, dtype=torch.float64, device="cuda")
+        ops.ppo_loss_gaussian(act_out, logstd, v, None, None, None, None, dact_ref, dls_ref, dv_ref, s_ref, **kw)
+    else:
+        ops.ppo_loss_categorical(act_out, v, None, None, None, None, dact_ref, dv_ref, s_ref, **kw)
+    s_new = torch.full((8,), 7.0, dtype=torch.float64, device="cuda")
+    dls_new = torch.zeros(1, dtype=torch.float64, device="cuda")
+    loss = dict(scal=scal, adv_stats=stats, adv_count=B, clip_range=clip, vf_coef=0.25, ent_coef=0.01, inv_batch=1.0 / B,
+                logstd=logstd, scalars=s_new, dlogstd=dls_new if gauss else None)
+    for _ in range(2):                                             # twice: the ticket re-arms itself
+        fused.forward(obs, loss=loss)
+    b = fused._last[1]
+    torch.cuda.synchronize()
+    assert torch.equal(b["act"], act_out) and torch.equal(b["v"][:, 0], v)
+    assert torch.allclose(b["dact"], dact_ref, rtol=1e-6, atol=1e-12) and torch.allclose(b["dv"][:, 0], dv_ref, rtol=1e-6, atol=1e-12)
+    # sums of B float terms whose last bits may differ between the two translation units (FMA contraction): 1e-6 of the scale
+    scale = float(s_ref.abs().max())
+    assert torch.allclose(s_new, s_ref, rtol=1e-6, atol=1e-6 * scale), (s_new, s_ref)
+    if gauss:
+        assert torch.allclose(dls_new, dls_ref, rtol=1e-6, atol=1e-9)

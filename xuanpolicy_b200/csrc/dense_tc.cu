@@ -43,12 +43,34 @@ constexpr int kOperandWarps = 8;        // K-major kernels: warps 0-3 epilogue, 
 constexpr int kProducerWarp = 4 + kOperandWarps, kMmaWarp = kProducerWarp + 1;
 constexpr int kThreads = (kMmaWarp + 1) * 32;
 constexpr int kMiscBytes = 9216;
+constexpr int kLossRedOff = 8704;        // last 512 B of the misc area: per-warp loss sums (4 x 8 doubles) + a flag
 constexpr int kWMiscBytes = 15360;      // wgrad kernel: barriers, [8 warps][3][128] head/bias-gradient scratch
 constexpr int kMaxSmem = 232448;        // 227 KB opt-in limit per CTA
 
 enum { MODE_FWD = 0, MODE_DGRAD = 1 };
 
+// Optional fusion of the PPO-Clip loss forward + backward (ppo_loss.cu, same formulas: SURVEY.md App. C) into the FWD
+// epilogue of the dual (actor | critic) launch: the epilogue thread of a row holds the head outputs in registers, so the
+// actor CTA turns (mu | logits) straight into dL/dmu | dL/dlogits and the critic CTA v into dL/dv — no separate loss launch,
+// no round trip of the head outputs.  Log scalars and the log-std gradient are reduced per CTA and summed in CTA order by the
+// last CTA (deterministic).  scal == NULL disables it.
+struct FusedLoss {
+    const float4* scal;        // packed minibatch scalars [M] = {act, old_logp, adv, ret} (xb_gather_records / _trunk_fwd)
+    const double* adv_stats;   // nullable (sum, sumsq) of the global minibatch's advantages -> on-the-fly normalisation
+    double inv_adv_count;
+    float clip_range, vf_coef, ent_coef, inv_batch;
+    int gaussian;              // 1: actor head = mu (A = 1) with a shared log-std; 0: Categorical with 2 logits
+    const float* logstd;       // gaussian: [1]
+    float* dact;               // out [M][n_head of the actor]
+    float* dv;                 // out [M]
+    double* partials;          // scratch [gridDim][8]
+    unsigned int* ticket;      // scratch, self-resetting
+    double* scalars;           // out fp64 [8] = sums of {surrogate, (v-R)^2, entropy, v, clipped count, 0, 0, 0}
+    double* dlogstd;           // out fp64 [1] (gaussian)
+};
+
 struct KParams {
+    FusedLoss loss;
     int64_t M;          // rows of the batch
     int KB;             // number of 32-wide k-blocks
     int kb_split;       // DGRAD: k-blocks [0, kb_split) read source 0, the rest source 1 (actor | critic)
@@ -122,6 +144,9 @@ struct EpiCtx {
     float* head_out;
     int n_off;         // first output column of this CTA (DGRAD n_split)
     bool store_y;      // FWD: false = only the fused head outputs are wanted (rollout / inference)
+    FusedLoss loss;    // FWD: fused PPO loss (loss.scal != NULL)
+    int sel;           // FWD dual: 0 = actor CTA, 1 = critic CTA
+    double* red;       // shared memory [4 warps][8] for the per-CTA loss sums
 #ifdef XB_DENSE_TS
     long long* ts;
 #endif
@@ -133,6 +158,25 @@ __device__ __forceinline__ void epilogue_warp(const EpiCtx& c, int warp, int lan
     constexpr uint32_t kSub = 32 * 128;                               // one warp's sub-tile: 32 rows x 128 B
     const uint32_t bar_h1 = c.bar_h1w + warp * 16;                    // 2 barriers per warp
     uint32_t lt = 0, g = 0;
+    // fused loss state (FWD only): advantage normalisation, Gaussian constants, this thread's partial sums
+    const bool with_loss = MODE == MODE_FWD && c.loss.scal != nullptr;
+    float l_mean = 0.f, l_denom = 1.f, l_ls = 0.f, l_inv_var = 1.f;
+    bool l_norm = false;
+    double lacc[6] = {0, 0, 0, 0, 0, 0};   // surrogate, value loss, entropy, v, clipped count, dlogstd
+    if (with_loss) {
+        if (c.loss.adv_stats) {
+            const double mean = c.loss.adv_stats[0] * c.loss.inv_adv_count;
+            const double var = c.loss.adv_stats[1] * c.loss.inv_adv_count - mean * mean;
+            l_mean = (float)mean;
+            l_denom = (float)sqrt(var > 0.0 ? var : 0.0) + 1e-8f;
+            l_norm = true;
+        }
+        if (c.loss.gaussian) {
+            l_ls = c.loss.logstd[0];
+            const float sd = expf(l_ls);
+            l_inv_var = 1.0f / (sd * sd);
+        }
+    }
     if (MODE == MODE_DGRAD && lane == 0 && c.tile0 < c.n_tiles) {
         mbar_arrive_expect_tx(bar_h1, kSub);
         tma_load_2d(c.h1_ring + warp * kSub, c.map_h1, c.n_off, (int)(c.tile0 * BM + warp * 32), bar_h1);
@@ -221,9 +265,98 @@ __device__ __forceinline__ void epilogue_warp(const EpiCtx& c, int warp, int lan
         if (MODE == MODE_FWD && row < c.M) {
             if (c.n_head > 0) c.head_out[row * c.n_head] = h0 + c.head_b[0];
             if (c.n_head > 1) c.head_out[row * c.n_head + 1] = h1 + c.head_b[1];
+            if (with_loss) {
+                const float4 sc = c.loss.scal[row];                 // {act, old_logp, adv, ret}
+                const float ib = c.loss.inv_batch;
+                if (c.sel == 1) {                                   // critic CTA: value loss (ppoclip_learner.py:41)
+                    const float v = h0 + c.head_b[0];
+                    const float verr = v - sc.w;
+                    c.loss.dv[row] = c.loss.vf_coef * ib * (2.0f * verr);
+                    lacc[1] += (double)(verr * verr);
+                    lacc[3] += (double)v;
+                } else {                                            // actor CTA: clipped surrogate + entropy (:33-39,:43)
+                    float A = sc.z;
+                    if (l_norm) A = (A - l_mean) / l_denom;
+                    const float lo = 1.0f - c.loss.clip_range, hi = 1.0f + c.loss.clip_range;
+                    const float ge = c.loss.ent_coef * ib;
+                    float logp, H, z0 = h0 + c.head_b[0], z1 = 0.f, lse = 0.f, diff = 0.f;
+                    int a = 0;
+                    if (c.loss.gaussian) {
+                        diff = sc.x - z0;
+                        logp = -(diff * diff) * (0.5f * l_inv_var) - l_ls - 0.9189385332046727f;
+                        H = 0.5f + 0.9189385332046727f + l_ls;
+                    } else {
+                        z1 = h1 + c.head_b[1];
+                        a = (int)sc.x;
+                        const float zmax = fmaxf(z0, z1);
+                        lse = zmax + logf(expf(z0 - zmax) + expf(z1 - zmax));
+                        const float lp0 = z0 - lse, lp1 = z1 - lse;
+                        H = -(expf(lp0) * lp0) - expf(lp1) * lp1;
+                        logp = a ? lp1 : lp0;
+                    }
+                    float m, dlogp, ratio = 1.0f;
+                    if (c.loss.clip_range > 0.0f) {
+                        ratio = expf(logp - sc.y);
+                        const float s1 = fminf(fmaxf(ratio, lo), hi) * A;
+                        const float s2 = A * ratio;
+                        m = fminf(s1, s2);
+                        const bool inactive = (A > 0.0f && ratio > hi) || (A < 0.0f && ratio < lo);
+                        dlogp = inactive ? 0.0f : -ib * A * ratio;
+                    } else {
+                        m = A * logp;
+                        dlogp = -ib * A;
+                    }
+                    if (c.loss.gaussian) {
+                        c.loss.dact[row] = dlogp * diff * l_inv_var;
+                        lacc[5] += (double)(dlogp * (diff * diff * l_inv_var - 1.0f)) - (double)ge;
+                    } else {
+                        const float lp0 = z0 - lse, lp1 = z1 - lse;
+                        const float p0 = expf(lp0), p1 = expf(lp1);
+                        c.loss.dact[row * 2] = dlogp * ((a == 0 ? 1.0f : 0.0f) - p0) + ge * p0 * (lp0 + H);
+                        c.loss.dact[row * 2 + 1] = dlogp * ((a == 1 ? 1.0f : 0.0f) - p1) + ge * p1 * (lp1 + H);
+                    }
+                    lacc[0] += (double)m;
+                    lacc[2] += (double)H;
+                    lacc[4] += (c.loss.clip_range > 0.0f && (ratio < lo || ratio > hi)) ? 1.0 : 0.0;
+                }
+            }
         }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (with_loss) {                                                // this warp's sums -> shared memory (finished by the CTA)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double v = warp_sum(lacc[k]);
+            if (lane == 0) c.red[warp * 8 + k] = v;
+        }
+    }
+}
+
+// After the CTA-wide barrier that follows the epilogue: CTA sums -> global partials -> the last CTA adds all CTAs' partials
+// in CTA order and writes the loss scalars / log-std gradient.  Called by every thread of the CTA.
+__device__ __forceinline__ void fused_loss_finish(const FusedLoss& L, const double* red, bool* flag_smem) {
+    if (!L.scal) return;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) L.partials[blockIdx.x * 8 + k] = (red[k] + red[8 + k]) + (red[16 + k] + red[24 + k]);
+        __threadfence();
+        *flag_smem = (atomicAdd(L.ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!*flag_smem) return;
+    __threadfence();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < 6) {
+        double s = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) s += L.partials[b * 8 + warp];
+        s = warp_sum(s);
+        if (lane == 0) {
+            if (warp < 5) L.scalars[warp] = s;
+            else if (L.gaussian && L.dlogstd) L.dlogstd[0] = s;
+        }
+    }
+    if (threadIdx.x < 3) L.scalars[5 + threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) *L.ticket = 0u;
 }
 
 template <int N, bool B_RES, int MODE>
@@ -453,6 +586,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         c.n_head = e_n_head; c.head_b = e_head_b; c.head_out = e_head_out;
         c.store_y = MODE != MODE_FWD || p.Y != nullptr;
         c.n_off = 0;
+        c.loss = p.loss; c.sel = sel; c.red = reinterpret_cast<double*>(misc_ptr + kLossRedOff);
 #ifdef XB_DENSE_TS
         c.ts = p.ts;
 #endif
@@ -466,6 +600,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         tc_fence_after();
         tmem_dealloc<kTmemCols>(tmem_base);
     }
+    if (MODE == MODE_FWD)
+        fused_loss_finish(p.loss, reinterpret_cast<const double*>(misc_ptr + kLossRedOff),
+                          reinterpret_cast<bool*>(misc_ptr + kLossRedOff + 256));
 }
 
 // ---------------------------------------------------------------------------------------------- weight preparation
@@ -888,6 +1025,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         c.n_head = e_n_head; c.head_b = e_head_b; c.head_out = e_head_out;
         c.store_y = MODE != MODE_FWD || p.Y != nullptr;
         c.n_off = n_off;
+        c.loss = p.loss; c.sel = sel; c.red = reinterpret_cast<double*>(misc_ptr + kLossRedOff);
 #ifdef XB_DENSE_TS
         c.ts = p.ts;
 #endif
@@ -902,6 +1040,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         tc_fence_after();
         tmem_dealloc<kTsTmemCols>(tmem_base);
     }
+    if (MODE == MODE_FWD)
+        fused_loss_finish(p.loss, reinterpret_cast<const double*>(misc_ptr + kLossRedOff),
+                          reinterpret_cast<bool*>(misc_ptr + kLossRedOff + 256));
 }
 
 template <int N, bool B_RES, int MODE>
@@ -1448,7 +1589,7 @@ struct TrunkArgs {
 static int dense_fwd_impl(const float* X, const TrunkArgs* trunk, int64_t M, int K, int N, float slope, int n_layers, const float* const* Whi,
                           const float* const* Wlo, const float* const* bias, float* const* Y, const float* const* head_w,
                           const float* const* head_b, const int* n_head, float* const* head_out, int b_resident,
-                          xb_stream_t stream) {
+                          xb_stream_t stream, const FusedLoss* loss = nullptr) {
     if ((!X && !trunk) || M <= 0) return XB_E_BADARG;
     if (K % BK != 0 || K < BK || K > 256 || (X && !al16(X))) return XB_E_UNSUPPORTED;
     if (trunk && (!trunk->obs || !trunk->W0 || !trunk->b0 || trunk->obs_dim < 1 || trunk->obs_dim > 4 ||
@@ -1502,6 +1643,10 @@ static int dense_fwd_impl(const float* X, const TrunkArgs* trunk, int64_t M, int
         p.n_head1 = n_head[1];
         p.head_out1 = head_out[1];
     }
+    if (loss) {
+        if (n_layers != 2 || n_head[1] != 1 || n_head[0] != (loss->gaussian ? 1 : 2)) return XB_E_UNSUPPORTED;
+        p.loss = *loss;
+    }
     return dispatch_kmajor<MODE_FWD>(N, b_resident != 0, maps, p, (cudaStream_t)stream);
 }
 
@@ -1526,6 +1671,31 @@ extern "C" int xb_dense_fwd2(const float* X, int64_t M, int K, int N, float slop
     const int nh[2] = {n_head0, n_head1};
     float* ho[2] = {head_out0, head_out1};
     return dense_fwd_impl(X, nullptr, M, K, N, slope, 2, Whi, Wlo, bias, Y, hw, hb, nh, ho, b_resident, stream);
+}
+
+extern "C" int xb_dense_fwd2_loss(const float* X, int64_t M, int K, int N, float slope, const float* Whi0, const float* Wlo0,
+                                  const float* bias0, float* Y0, const float* head_w0, const float* head_b0, int n_head0,
+                                  float* head_out0, const float* Whi1, const float* Wlo1, const float* bias1, float* Y1,
+                                  const float* head_w1, const float* head_b1, int n_head1, float* head_out1, int b_resident,
+                                  const float* scal, const double* adv_stats, int64_t adv_count, float clip_range,
+                                  float vf_coef, float ent_coef, float inv_batch, const float* logstd, float* dact, float* dv,
+                                  double* loss_partials, uint32_t* loss_ticket, double* scalars, double* dlogstd,
+                                  xb_stream_t stream) {
+    if (!scal || !dact || !dv || !loss_partials || !loss_ticket || !scalars) return XB_E_BADARG;
+    if (adv_stats && adv_count <= 0) return XB_E_BADARG;
+    if (logstd && !dlogstd) return XB_E_BADARG;
+    if (((uintptr_t)scal & 15u)) return XB_E_BADARG;
+    const float* Whi[2] = {Whi0, Whi1};
+    const float* Wlo[2] = {Wlo0, Wlo1};
+    const float* bias[2] = {bias0, bias1};
+    float* Y[2] = {Y0, Y1};
+    const float* hw[2] = {head_w0, head_w1};
+    const float* hb[2] = {head_b0, head_b1};
+    const int nh[2] = {n_head0, n_head1};
+    float* ho[2] = {head_out0, head_out1};
+    FusedLoss L{(const float4*)scal, adv_stats, adv_stats ? 1.0 / (double)adv_count : 0.0, clip_range, vf_coef, ent_coef,
+                inv_batch, logstd ? 1 : 0, logstd, dact, dv, loss_partials, loss_ticket, scalars, dlogstd};
+    return dense_fwd_impl(X, nullptr, M, K, N, slope, 2, Whi, Wlo, bias, Y, hw, hb, nh, ho, b_resident, stream, &L);
 }
 
 extern "C" int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const float* W0, const float* b0, int64_t M, int H,

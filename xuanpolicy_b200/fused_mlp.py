@@ -94,6 +94,8 @@ class FusedActorCritic:
         self.norm_sink, self.norm_done = None, False
         # True while the hi/lo operand copies are known to match the weights (the Adam launch rewrote them)
         self.splits_fresh = False
+        self._loss_partials = torch.zeros(148 * 8, dtype=torch.float64, device=dev)     # scratch of the fused loss epilogue
+        self._loss_ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         self.fork_wgrad = os.environ.get("XB_FORK_WGRAD", "0") == "1"
         self._side = None
 
@@ -115,10 +117,22 @@ class FusedActorCritic:
     def stage_trunk(self, obs, b):
         ops.mlp_trunk_fwd(obs, self.l0.weight.data, self.l0.bias.data, self.slope, b["h1"])
 
-    def stage_hidden(self, b):
-        ops.dense_fwd2(b["h1"], self.slope,
-                       (self.wa_hi, self.wa_lo, self.la1.bias.data, b["ya"], self.la2.weight.data, self.la2.bias.data, b["act"]),
-                       (self.wc_hi, self.wc_lo, self.lc1.bias.data, b["yc"], self.lc2.weight.data, self.lc2.bias.data, b["v"]))
+    def stage_hidden(self, b, loss=None):
+        """Actor + critic hidden layers and heads in one launch.  `loss` (dict: scal, adv_stats, adv_count, clip_range,
+        vf_coef, ent_coef, inv_batch, logstd, scalars, dlogstd): also the PPO loss forward + backward, fused into the
+        kernel's epilogue — dL/d(act_out) lands in b["dact"], dL/dv in b["dv"]."""
+        l0 = (self.wa_hi, self.wa_lo, self.la1.bias.data, b["ya"], self.la2.weight.data, self.la2.bias.data, b["act"])
+        l1 = (self.wc_hi, self.wc_lo, self.lc1.bias.data, b["yc"], self.lc2.weight.data, self.lc2.bias.data, b["v"])
+        if loss is None:
+            ops.dense_fwd2(b["h1"], self.slope, l0, l1)
+            return
+        if "dact" not in b:
+            B = b["h1"].shape[0]
+            b["dact"] = torch.empty(B, self.A, dtype=torch.float32, device=self.device)
+            b["dv"] = torch.empty(B, 1, dtype=torch.float32, device=self.device)
+        ops.dense_fwd2_loss(b["h1"], self.slope, l0, l1, loss["scal"], loss["adv_stats"], loss["adv_count"],
+                            loss["clip_range"], loss["vf_coef"], loss["ent_coef"], loss["inv_batch"], loss["logstd"],
+                            b["dact"], b["dv"], self._loss_partials, self._loss_ticket, loss["scalars"], loss["dlogstd"])
 
     def stage_dgrad(self, b, dact, dv2):
         ops.dense_dgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, self.wt_hi, self.wt_lo,
@@ -161,7 +175,7 @@ class FusedActorCritic:
         return b["act"], b["v"][:, 0]
 
     # ---------------------------------------------------------------------------------------------- forward / backward
-    def forward(self, obs, refresh=True, trunk_done=False):
+    def forward(self, obs, refresh=True, trunk_done=False, loss=None):
         """obs: CUDA fp32 [B, obs_dim] with contiguous rows (a column slice of the float4 observation rows is fine).
         Returns (act_out [B, A], v [B]); the activations stay in per-batch-size buffers for `backward`."""
         B = obs.shape[0]
@@ -170,7 +184,7 @@ class FusedActorCritic:
             self.refresh_weights()
         if not trunk_done:              # the gather kernel already produced h1 for these rows (xb_gather_trunk_fwd)
             self.stage_trunk(obs, b)
-        self.stage_hidden(b)
+        self.stage_hidden(b, loss)
         self._last = (obs, b)
         return b["act"], b["v"][:, 0]
 

@@ -135,6 +135,7 @@ class PPOCLIP_Learner:
         self._mb = {}
         self.world_size, self.process_group = 1, None
         self._peer = None           # dist.PeerComm when env-sharded over NVLink peer memory
+        self._dls64 = None          # fp64 log-std gradient written by the fused loss epilogue
 
     # ---------------------------------------------------------------------------------------------- checkpoints
     def save_model(self, model_path):
@@ -291,12 +292,29 @@ class PPOCLIP_Learner:
             single = self.world_size == 1 and os.environ.get("XB_TAIL_NORM", "1") != "0"
             self._fused.norm_sink = (self._flat, self.clip_grad_norm if self.use_grad_clip else 0.0) if (fused is not None and single) else None
             self._fused.norm_done = False
+        stats = (stats if stats is not None else mb["stats"]) if memory.use_advnorm else None
+        if fused is not None and self._fused_loss_ok(memory, fused):
+            # the loss forward + backward ride in the epilogue of the hidden-layer launch (csrc/dense_tc.cu FusedLoss)
+            logstd = fused.policy.actor.logstd.detach() if fused.gaussian else None
+            if fused.gaussian and self._dls64 is None:
+                self._dls64 = torch.zeros(1, dtype=torch.float64, device=self.device)
+            loss = dict(scal=mb["scal"], adv_stats=stats, adv_count=B * self.world_size, clip_range=self.clip_range,
+                        vf_coef=self.vf_coef, ent_coef=self.ent_coef, inv_batch=1.0 / (B * self.world_size), logstd=logstd,
+                        scalars=self._scalars, dlogstd=self._dls64 if fused.gaussian else None)
+            fused.forward(mb["obs"], refresh=not fused.splits_fresh, trunk_done=mb.get("trunk_done", False), loss=loss)
+            b = fused._last[1]
+            if fused.gaussian:
+                flat = self._flat
+                dls32 = flat.grad_views[[id(q) for q in flat.params].index(id(fused.policy.actor.logstd))]
+                fused.backward(b["dact"], b["dv"], self._dls64, dls32)
+            else:
+                fused.backward(b["dact"], b["dv"])
+            return
         if fused is not None:                        # tcgen05 dense kernels; weights re-split after every Adam step
             act_out, v_pred = fused.forward(mb["obs"], refresh=not fused.splits_fresh, trunk_done=mb.get("trunk_done", False))
             a_dist = fused.dist_params(act_out)
         else:
             _, a_dist, v_pred = self.policy(mb["obs"])
-        stats = (stats if stats is not None else mb["stats"]) if memory.use_advnorm else None
         if memory.packed and self.value_clip <= 0:   # scalars already gathered, compact and coalesced
             self._loss_backward(a_dist, v_pred, None, None, None, None, None, 1.0 / (B * self.world_size),
                                 adv_stats=stats, adv_count=B * self.world_size, packed=mb["scal"], flat=self._flat,
@@ -305,6 +323,16 @@ class PPOCLIP_Learner:
             self._loss_backward(a_dist, v_pred, memory._act, memory._ret, memory._adv, memory._logp, memory._val,
                                 1.0 / (B * self.world_size), idx=idx, T=memory.n_size, N=memory.n_envs,
                                 adv_stats=stats, adv_count=B * self.world_size, flat=self._flat, fused=fused)
+
+    def _fused_loss_ok(self, memory, fused):
+        """The loss can ride in the forward kernel's epilogue when the minibatch scalars are the packed float4 rows, there is
+        no value clipping, and the actor head is Gaussian with one action dim and a directly-held log-std, or 2 logits."""
+        if os.environ.get("XB_FUSED_LOSS", "1") == "0" or not (memory.packed and self.value_clip <= 0 and self._flat is not None):
+            return False
+        if fused.gaussian:
+            p = getattr(fused.policy.actor, "logstd", None)
+            return fused.A == 1 and p is not None and p.requires_grad and p.numel() == 1
+        return fused.A == 2
 
     def stage_optimizer(self):
         """Stage 3: global-norm clip + Adam + LinearLR on the flat buffers (one fused device step).  Env-sharded over peer

@@ -324,6 +324,21 @@ def dense_fwd2(x, slope, layer0, layer1, b_resident=True):
     _lib.call("xb_dense_fwd2", _p(x, F32), M, K, N, float(slope), *args, 1 if b_resident else 0, _stream())
 
 
+def dense_fwd2_loss(x, slope, layer0, layer1, scal, adv_stats, adv_count, clip_range, vf_coef, ent_coef, inv_batch, logstd,
+                    dact, dv, partials, ticket, scalars, dlogstd, b_resident=True):
+    """dense_fwd2 with the PPO loss forward + backward fused into its epilogue (xb_dense_fwd2_loss)."""
+    M, K = x.shape
+    N = layer0[0].shape[0]
+    args = []
+    for w_hi, w_lo, bias, y, head_w, head_b, head_out in (layer0, layer1):
+        args += [_p(w_hi, F32), _p(w_lo, F32), _p(bias, F32), _p(y, F32), _p(head_w, F32), _p(head_b, F32),
+                 head_w.shape[0], _p(head_out, F32)]
+    _lib.call("xb_dense_fwd2_loss", _p(x, F32), M, K, N, float(slope), *args, 1 if b_resident else 0, _p(scal, F32),
+              _p(adv_stats, F64), int(adv_count), float(clip_range), float(vf_coef), float(ent_coef), float(inv_batch),
+              _p(logstd, F32), _p(dact, F32), _p(dv, F32), _p(partials, F64), _p(ticket, I32), _p(scalars, F64),
+              _p(dlogstd, F64), _stream())
+
+
 def mlp_fwd_from_obs(obs, w0, b0, slope, layer0, layer1):
     """Whole actor-critic forward in one launch; layerK = (w_hi, w_lo, bias, y or None, head_w, head_b, head_out)."""
     ptr, ld = _rows_ld(obs)
