@@ -477,8 +477,9 @@ def run_ours(args):
         "metric": "PPO env-steps/s", "value": round(value, 1), "unit": "env-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(secs / args.steps * 1e3, 4),
         "higher_is_better": True, "scaling": "strong" if wl.get("strong") else "weak", "vs_baseline": None,
-        "dtype": ("f32-accurate MLP GEMMs (3xTF32 split on the tcgen05 tensor cores, fp32 accumulate)" if fused_on else
-                  ("tf32 MLP GEMMs" if args.tf32 else "f32 MLP GEMMs (cuBLAS SIMT)")) + ", f32 loss/optimizer, f64 GAE carry and env physics",
+        "dtype": "tf32" if (args.tf32 and not fused_on) else "f32",
+        "dtype_detail": ("f32-accurate MLP GEMMs (3xTF32 split on the tcgen05 tensor cores, fp32 accumulate)" if fused_on else
+                         ("tf32 MLP GEMMs" if args.tf32 else "f32 MLP GEMMs (cuBLAS SIMT)")) + ", f32 loss/optimizer, f64 GAE carry and env physics",
         "data": "synthetic",
         "config": {"workload": wl["name"], "envs_per_gpu": n_local, "horizon": horizon, "n_epoch": 8,
                    "minibatch_per_gpu": mb, "mlp_hidden": wl["hidden"], "params": params, "gamma": wl["gamma"],
@@ -573,7 +574,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": "PPO env-steps/s", "value": round(value, 1), "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (torch CPU); f64 physics",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "dtype_detail": "f32 torch CPU learner, f64 physics",
         "data": "synthetic", "config": {"workload": wl["name"], "sample_envs": n, "horizon": wl["horizon"]},
         "cpu_baseline": {"value": round(value, 1), "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample,
                          "host_cores_available": cores},
