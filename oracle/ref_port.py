@@ -364,3 +364,61 @@ class PPOAgentPort:
                     obs[i] = infos[i]["reset_obs"]
                     self.episodes += 1
             self.current_step += self.n_envs
+
+
+class PPGAgentPort:
+    """PPG_Agent.train restated (xuance/torch/agents/policy_gradient/ppg_agent.py:55-109; logging removed): rollout with
+    the old action distributions stored per transition, then the policy phase, the critic phase, the refresh of every
+    stored old distribution from the current policy (:90-93) and the auxiliary phase.  `memory` and the three `update_*`
+    callables let a test drive OTHER implementations (the product's drop-in buffer and PPG_Learner) through this loop.
+    The reference wraps the distributions with split_distributions (one Python object per sample); the batched wrapper is
+    passed as is here — the drop-in buffer accepts both."""
+
+    def __init__(self, envs, policy, memory, update_policy, update_critic, update_auxiliary, n_steps, n_minibatch=4,
+                 policy_nepoch=1, value_nepoch=1, aux_nepoch=1):
+        self.envs, self.policy, self.memory = envs, policy, memory
+        self.update_policy, self.update_critic, self.update_auxiliary = update_policy, update_critic, update_auxiliary
+        self.n_envs, self.n_steps = envs.num_envs, n_steps
+        self.buffer_size = self.n_envs * n_steps
+        self.batch_size = self.buffer_size // n_minibatch
+        self.policy_nepoch, self.value_nepoch, self.aux_nepoch = policy_nepoch, value_nepoch, aux_nepoch
+        self.current_step, self.episodes, self.infos = 0, 0, {}
+
+    def _action(self, obs):
+        _, dists, vs, _ = self.policy(obs)
+        acts = dists.stochastic_sample()
+        return acts.detach().cpu().numpy(), vs.detach().cpu().numpy(), dists
+
+    def _phase(self, n_epoch, update, indexes):
+        for _ in range(n_epoch):
+            np.random.shuffle(indexes)
+            for start in range(0, self.buffer_size, self.batch_size):
+                obs_b, act_b, ret_b, _, adv_b, aux_b = self.memory.sample(indexes[start:start + self.batch_size])
+                self.infos.update(update(obs_b, act_b, ret_b, adv_b, aux_b["old_dist"]))
+
+    def train(self, train_steps):
+        obs = self.envs.buf_obs
+        mem = self.memory
+        for _ in range(train_steps):
+            acts, rets, dists = self._action(obs)
+            next_obs, rewards, terminals, truncations, infos = self.envs.step(acts)
+            mem.store(obs, acts, rewards, rets, terminals, {"old_dist": dists})
+            if mem.full:
+                _, vals, _ = self._action(next_obs)
+                for i in range(self.n_envs):
+                    mem.finish_path(vals[i], i)
+                indexes = np.arange(self.buffer_size)
+                self._phase(self.policy_nepoch, self.update_policy, indexes)
+                self._phase(self.value_nepoch, self.update_critic, indexes)
+                buffer_obs = mem.observations                                     # [n_envs, n_size, obs_dim]
+                _, new_dist, _, _ = self.policy(np.asarray(buffer_obs).reshape(self.buffer_size, -1))
+                mem.auxiliary_infos["old_dist"] = new_dist                         # ppg_agent.py:93
+                self._phase(self.aux_nepoch, self.update_auxiliary, indexes)
+                mem.clear()
+            obs = next_obs
+            for i in range(self.n_envs):
+                if terminals[i] or truncations[i]:
+                    obs[i] = infos[i]["reset_obs"]
+                    mem.finish_path(0, i)
+                    self.episodes += 1
+            self.current_step += self.n_envs

@@ -126,3 +126,36 @@ def test_compat_dropins_under_the_reference_agent_loop(env_id, obsnorm):
     assert memory.size == 5 and memory.ptr == 5 and not memory.full
     if env_id == "CartPole-v1":
         assert agent.episodes > 0
+
+
+@pytest.mark.parametrize("env_id", ["CartPole-v1", "Pendulum-v1"])
+def test_ppg_dropins_under_the_reference_agent_loop(env_id):
+    """Row f3 end to end: the reference's PPG_Agent.train (restated in oracle/ref_port.PPGAgentPort: rollout with stored
+    old distributions, policy / critic phases, whole-buffer old-distribution refresh, auxiliary phase, ppg_agent.py:55-109)
+    driving the drop-in env, buffer ({"old_dist": None} auxiliary on the device) and PPG_Learner."""
+    import xuanpolicy_b200 as xb
+    from oracle import ref_port
+    from xuanpolicy_b200 import policies
+    torch.manual_seed(0)
+    np.random.seed(0)
+    n, T = 10, 16
+    envs = xb.DummyVecEnv_Gym(xb.make_env_fns(env_id, 1, n), device="cuda")
+    envs.reset()
+    rep = policies.MLPRepresentation(envs.observation_space.shape, [32], device="cuda")
+    cls = policies.CategoricalPPGActorCritic if env_id == "CartPole-v1" else policies.GaussianPPGActorCritic
+    policy = cls(envs.action_space, rep, [32], [32], device="cuda").cuda()
+    opt = torch.optim.Adam(policy.parameters(), 4e-4, eps=1e-5)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=10000)
+    memory = xb.DummyOnPolicyBuffer(envs.observation_space, envs.action_space, {"old_dist": None}, n, T, True, True, 0.98, 0.95)
+    learner = xb.PPG_Learner(policy, opt, sched, "cuda", "/tmp", ent_coef=0.01, clip_range=0.2, kl_beta=1.0)
+    agent = ref_port.PPGAgentPort(envs, policy, memory, learner.update_policy, learner.update_critic, learner.update_auxiliary,
+                                  n_steps=T, n_minibatch=4, policy_nepoch=2, value_nepoch=1, aux_nepoch=1)
+    p0 = {k: v.detach().clone() for k, v in policy.named_parameters()}
+    agent.train(2 * T + 3)
+    assert learner.policy_iterations == 2 * 2 * 4 and learner.value_iterations == 2 * 1 * 4
+    assert set(agent.infos) == {"actor-loss", "entropy", "learning_rate", "clip_ratio", "critic-loss", "kl-loss"}
+    assert all(np.isfinite(float(v)) for v in agent.infos.values())
+    for k, v in policy.named_parameters():
+        assert torch.isfinite(v).all() and not torch.equal(v, p0[k]), k      # every sub-network was trained by some phase
+    assert memory.size == 3 and not memory.full
+    assert agent.current_step == n * (2 * T + 3)
