@@ -438,7 +438,9 @@ int xb_mlp_trunk_wgrad(const float* dz1, const float* obs, int ld, int obs_dim, 
  *   rank) read from local memory; squared norm of grad_out * grad_scale; then exactly the scalars xb_clip_adam_step's
  *   first kernel derives (workspace layout identical), so xb_adam_apply can follow.  n must be a multiple of 4.
  * xb_adam_apply: the second kernel of xb_clip_adam_step alone (clip + Adam from the scalars in workspace).
- * xb_peer_allreduce_f64: out[j] = sum_r stats_r[j], j < n <= xb_peer_stats_max().
+ * xb_peer_allreduce_f64: out[j] = sum_r stats_r[offset + j], j < n, offset + n <= xb_peer_stats_max().  Used once per epoch for
+ *   the minibatch advantage statistics and, with use_obsnorm / use_rewnorm, once per vector step for the observation /
+ *   return moments (the analogue of mpi_moments, xuance/common/statistic_tools.py:6-32).
  * xb_adv_stats_minibatches: stats[m] = (sum, sumsq) of adv over minibatch m = idx[m*B, (m+1)*B) for every minibatch
  *   of an epoch in one launch (adv element stride `stride` floats per transition row; zeroes stats first).
  * ---------------------------------------------------------------------------------------------------------- */
@@ -464,7 +466,7 @@ int xb_adam_apply_split(float* param, const float* grad, float* exp_avg, float* 
                         float beta2, float eps, float grad_scale, const double* workspace, int64_t w_off0, float* hi0,
                         float* lo0, int64_t w_off1, float* hi1, float* lo1, int N, int K, float* thi, float* tlo,
                         xb_stream_t stream);
-int xb_peer_allreduce_f64(const void* const* peer_bases /* host [W] */, int rank, int W, int n, double* out,
+int xb_peer_allreduce_f64(const void* const* peer_bases /* host [W] */, int rank, int W, int offset, int n, double* out,
                           uint32_t* tickets, xb_stream_t stream);
 int xb_adv_stats_minibatches(const int64_t* idx, int64_t n_minibatches, int64_t B, int64_t T, int64_t N, const float* adv,
                              int64_t stride, double* stats, xb_stream_t stream);

@@ -57,6 +57,25 @@ if peer is not None:
     torch.cuda.synchronize()
     stats_ok = torch.equal(out, torch.arange(6, dtype=torch.float64, device="cuda") * sum(range(1, world + 1)))
     peer_ok = "ok" if (bitwise and close and norm_ok and moved and stats_ok) else "BAD(%%s,%%s,%%s,%%s,%%s)" %% (bitwise, close, norm_ok, moved, stats_ok)
+# sharded observation / reward normalisation: every rank must hold the same GLOBAL running statistics
+norm_ok = "off"
+if peer is not None:
+    a2 = build_ppo("Pendulum-v1", device="cuda", parallels=96, n_steps=24, n_epoch=1, n_minibatch=2, shuffle="device",
+                   seed=7 + 100 * rank, use_obsnorm=True, use_rewnorm=True)
+    a2.train(2 * 24)
+    torch.cuda.synchronize()
+    st = torch.cat([a2._obs_rms[a2._rms_cur], a2._ret_rms, a2._rew_std.double()])
+    allst = [torch.empty_like(st) for _ in range(world)]
+    torch.distributed.all_gather(allst, st)
+    same_stats = all(torch.equal(allst[0], x) for x in allst)
+    count_ok = abs(float(st[8]) - (1e-4 + 2 * 24 * 96 * world)) < 1e-6       # every env of every rank merged every step
+    flat2 = a2.learner._flat.flat_param
+    g2 = [torch.empty_like(flat2) for _ in range(world)]
+    torch.distributed.all_gather(g2, flat2)
+    norm_ok = "ok" if (same_stats and count_ok and all(torch.equal(g2[0], x) for x in g2) and bool(torch.isfinite(st).all())) \
+        else "BAD(%%s,%%s,%%s)" %% (same_stats, count_ok, float(st[8]))
+if rank == 0:
+    print("NORM %%s" %% norm_ok)
 if rank == 0:
     print("RESULT same_params=%%s envs_differ=%%s critic=%%.4f steps=%%d peer=%%s" %% (same, envs_differ, info["critic-loss"], steps, peer_ok))
 torch.distributed.destroy_process_group()
@@ -78,3 +97,5 @@ def test_two_rank_training_stays_in_sync(tmp_path, peer):
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][-1]
     assert "same_params=True" in line and "envs_differ=True" in line and "steps=24" in line, line
     assert ("peer=ok" if peer == "1" else "peer=off") in line, line
+    norm = [l for l in out.stdout.splitlines() if l.startswith("NORM")][-1]
+    assert norm == ("NORM ok" if peer == "1" else "NORM off"), norm

@@ -141,9 +141,18 @@ class PPOCLIP_Agent:
         self._ret_ws = torch.zeros(8 + 8 * 1184, **f64)
         self._returns = torch.zeros(N, dtype=torch.float64, device=dev)
         self._rew_std = torch.ones(1, dtype=torch.float32, device=dev)
-        if self.use_obsnorm and self.learner.world_size > 1:
-            raise NotImplementedError("use_obsnorm with env sharding needs the per-step all-reduce of the observation "
-                                      "moments inside the rollout graph; not wired yet")
+        # env-sharded normalisers: the per-step observation moments [9] and finished-episode return sums [3] are exchanged
+        # over peer memory (the analogue of mpi_moments, statistic_tools.py:6-32) so every rank keeps the GLOBAL statistics;
+        # they live at the end of the comm block's statistics region (its start carries the per-epoch advantage sums)
+        self._norm_peer = self.learner._peer if (self.use_obsnorm or self.use_rewnorm) else None
+        if (self.use_obsnorm or self.use_rewnorm) and self.learner.world_size > 1 and self._norm_peer is None:
+            raise NotImplementedError("use_obsnorm / use_rewnorm with env sharding need the peer-memory exchange "
+                                      "(XB_PEER_COMM=1 and CUDA IPC available)")
+        if self._norm_peer is not None:
+            self._norm_off = self._norm_peer.stats.numel() - 12
+            self._norm_local = self._norm_peer.stats[self._norm_off:]
+            self._norm_local.zero_()
+            self._norm_global = torch.zeros(12, **f64)
         # one launch per vector step (sample + env step + store) for the two classic-control action shapes
         import os as _os
         self._fused_step = (_os.environ.get("XB_FUSED_STEP", "1") != "0" and
@@ -188,6 +197,14 @@ class PPOCLIP_Agent:
         """One vector step into buffer row t (reference loop body, ppoclip_agent.py:62-68,88,101)."""
         N, env, mem = self.n_envs, self.envs, self.memory
         x_cur, x_nxt = self._x[self._cur], self._x[self._cur ^ 1]
+        if self._norm_peer is not None:
+            # sharded: this step's observation moments + the previous step's return sums in ONE exchange, then the global
+            # return normaliser is merged before this step's rewards are scaled (same order as the reference, :87-92)
+            if self.use_obsnorm:
+                ops.moments4(x_cur[:N], self._norm_local[:9], self._obs_ws)
+            ops.peer_allreduce_f64(self._norm_peer, 12, self._norm_global, offset=self._norm_off)
+            if self.use_rewnorm:
+                ops.rms_merge_scalar(self._norm_global[9:], self._ret_rms, self._rew_std)
         x_in = self._normalize_obs(x_cur, update=True)            # obs_rms.update(obs); _process_observation (:63-64)
         dist, v = self._policy_forward(x_in)                      # V on [obs_t ; terminal obs of step t-1]
         if t > 0 and not self._fused_step:
@@ -217,8 +234,11 @@ class PPOCLIP_Agent:
             mem.store_device(x_in[:N], self._act, env._rew, v[:N].contiguous(), env._term, env._trunc, self._logp, t,
                              rew_std=self._rew_std if self.use_rewnorm else None, rew_clip=self.rewnorm_range)
         if self.use_rewnorm:                                      # returns tracker + ret_rms.update (:87,:91-92)
-            ops.returns_track(self._returns, env._rew, env._term, env._trunc, self.gamma, self._ret_sums, self._ret_ws)
-            ops.rms_merge_scalar(self._ret_sums, self._ret_rms, self._rew_std)
+            if self._norm_peer is not None:      # merged globally at the start of the next step (see above)
+                ops.returns_track(self._returns, env._rew, env._term, env._trunc, self.gamma, self._norm_local[9:], self._ret_ws)
+            else:
+                ops.returns_track(self._returns, env._rew, env._term, env._trunc, self.gamma, self._ret_sums, self._ret_ws)
+                ops.rms_merge_scalar(self._ret_sums, self._ret_rms, self._rew_std)
         self._cur ^= 1
 
     def _normalize_obs(self, x, update):
@@ -228,9 +248,12 @@ class PPOCLIP_Agent:
             return x
         N = self.n_envs
         s_in, s_out = self._obs_rms[self._rms_cur], self._obs_rms[self._rms_cur ^ 1]
-        if update:
+        sums = self._obs_sums
+        if update and self._norm_peer is not None:
+            sums = self._norm_global[:9]            # global moments, exchanged by _rollout_step
+        elif update:
             ops.moments4(x[:N], self._obs_sums, self._obs_ws)
-        ops.rms_normalize(x, self._obs_dim, self._obs_sums, s_in, s_out, self.obsnorm_range, self._xn, N if update else 0)
+        ops.rms_normalize(x, self._obs_dim, sums, s_in, s_out, self.obsnorm_range, self._xn, N if update else 0)
         self._rms_cur ^= 1
         return self._xn
 
@@ -475,6 +498,8 @@ class PPOCLIP_Agent:
         tensors = [env._state, env._rng, env._elapsed, env._ep_score, env.ep_stats, self._ctr, self._perm_ctr, self._x[0], self._x[1],
                    fl.flat_param, fl.exp_avg, fl.exp_avg_sq, fl.step, fl.lr, self._obs_rms[0], self._obs_rms[1],
                    self._ret_rms, self._returns, self._rew_std]
+        if self._norm_peer is not None:
+            tensors.append(self._norm_local)      # pending return sums of the last step (merged at the next step)
         return [(t, t.clone()) for t in tensors] + [("cur", self._cur)]
 
     def _restore(self, snap):

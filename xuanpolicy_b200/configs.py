@@ -1,8 +1,9 @@
 """Default PPO-Clip hyper-parameters for the two classic-control tasks, as a Namespace shaped like the one the
 reference builds from YAML (xuance/common/common_tools.py:32-83).  Values restate
 xuance/configs/ppo/classic_control/CartPole-v1.yaml and Pendulum-v1.yaml (identical except env_id/policy);
-`use_obsnorm` / `use_rewnorm` default to False here because the device-side normaliser is a later row
- — the yaml default is True."""
+`use_obsnorm` / `use_rewnorm` default to False here because the BASELINE configs are measured without them (the yaml
+default is True); the device-side normalisers (csrc/normalize.cu) run when they are switched on,
+single GPU and env-sharded."""
 from argparse import Namespace
 
 _COMMON = dict(

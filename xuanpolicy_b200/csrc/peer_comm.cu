@@ -132,13 +132,14 @@ __global__ void __launch_bounds__(kPeerBlock)
 
 // out[j] = sum over ranks (rank order) of the peers' stats[j], j < n <= kPeerStatsMax.  One CTA, the last flag slot.
 __global__ void __launch_bounds__(256)
-    peer_allreduce_f64_kernel(PeerTable t, int rank, int W, int n, double* __restrict__ out, uint32_t* __restrict__ tickets) {
+    peer_allreduce_f64_kernel(PeerTable t, int rank, int W, int offset, int n, double* __restrict__ out,
+                              uint32_t* __restrict__ tickets) {
     const int slot = kPeerSlots - 1;
     const uint32_t base_ticket = tickets[slot];
     peer_barrier(t, rank, W, slot, base_ticket + 1, tickets);
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
         double s = 0.0;
-        for (int r = 0; r < W; ++r) s += ld_peer_f64(reinterpret_cast<const double*>(t.base[r] + kPeerStatsOff) + j);
+        for (int r = 0; r < W; ++r) s += ld_peer_f64(reinterpret_cast<const double*>(t.base[r] + kPeerStatsOff) + offset + j);
         out[j] = s;
     }
     peer_barrier(t, rank, W, slot, base_ticket + 2, tickets);
@@ -234,13 +235,13 @@ extern "C" int xb_peer_allreduce_grad_norm(const void* const* peer_bases /* host
     return 0;
 }
 
-extern "C" int xb_peer_allreduce_f64(const void* const* peer_bases /* host [W] */, int rank, int W, int n, double* out,
-                                     uint32_t* tickets, xb_stream_t stream) {
+extern "C" int xb_peer_allreduce_f64(const void* const* peer_bases /* host [W] */, int rank, int W, int offset, int n,
+                                     double* out, uint32_t* tickets, xb_stream_t stream) {
     PeerTable t;
     int rc = make_table(peer_bases, rank, W, &t);
     if (rc) return rc;
-    if (n <= 0 || n > kPeerStatsMax || !out || !tickets) return XB_E_BADARG;
-    peer_allreduce_f64_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(t, rank, W, n, out, tickets);
+    if (n <= 0 || offset < 0 || offset + n > kPeerStatsMax || !out || !tickets) return XB_E_BADARG;
+    peer_allreduce_f64_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(t, rank, W, offset, n, out, tickets);
     XB_LAUNCH_CHECK();
     return 0;
 }

@@ -234,10 +234,10 @@ def adam_apply_split(param, grad, exp_avg, exp_avg_sq, beta1, beta2, eps, grad_s
               _p(lo0, F32), off(w1), _p(hi1, F32), _p(lo1, F32), N, K, _p(thi, F32), _p(tlo, F32), _stream())
 
 
-def peer_allreduce_f64(peer, n, out):
-    """out[:n] = sum over ranks of the first n doubles of each rank's comm-block statistics."""
-    _lib.call("xb_peer_allreduce_f64", peer.bases, peer.rank, peer.world, int(n), _p(out, F64), _p(peer.tickets, I32),
-              _stream())
+def peer_allreduce_f64(peer, n, out, offset=0):
+    """out[:n] = sum over ranks of doubles [offset, offset + n) of each rank's comm-block statistics."""
+    _lib.call("xb_peer_allreduce_f64", peer.bases, peer.rank, peer.world, int(offset), int(n), _p(out, F64),
+              _p(peer.tickets, I32), _stream())
 
 
 def adv_stats_minibatches(idx, n_minibatches, B, T, N, adv, stride, stats):
