@@ -251,7 +251,8 @@ int xb_clip_adam_step(float* param, const float* grad, float* exp_avg, float* ex
  *                    Rows [0, n_merged_rows) use the merged statistics, rows beyond use state_in unchanged (the
  *                    previous step's terminal observations, normalised as ppoclip_agent.py:99 saw them);
  *                    n_merged_rows == 0 normalises without updating (sums may be NULL).
- *   xb_returns_track returns[i] = (1-term)*gamma*returns[i] + rew[i] (fp64 [N]); finished envs add (R, R^2, 1) to sums fp64 [3]
+ *   xb_returns_track returns[i] = (1-term)*gamma*returns[i] + rew[i] (fp64 [N]; mask_terminal = 0 drops the (1-term) factor:
+ *                    the A2C agent's tracker, a2c_agent.py:85); finished envs add (R, R^2, 1) to sums fp64 [3]
  *                    and restart at 0
  *   xb_rms_merge_scalar merges those sums into the return normaliser state fp64 [3] = (mean, var, count) and
  *                    publishes rew_std = clip(sqrt(var), 0.1, 100), the divisor xb_store applies to rewards
@@ -260,7 +261,7 @@ int xb_clip_adam_step(float* param, const float* grad, float* exp_avg, float* ex
 int xb_moments4(const float* x, double* sums, double* workspace, int64_t N, xb_stream_t stream);
 int xb_rms_normalize(const float* x, int dim, const double* sums, const double* state_in, double* state_out,
                      float clip, float* out, int64_t N, int64_t n_merged_rows, xb_stream_t stream);
-int xb_returns_track(double* returns, const float* rew, const uint8_t* term, const uint8_t* trunc, double gamma,
+int xb_returns_track(double* returns, const float* rew, const uint8_t* term, const uint8_t* trunc, double gamma, int mask_terminal,
                      double* sums, double* workspace, int64_t N, xb_stream_t stream);
 int xb_rms_merge_scalar(const double* sums, double* state, float* rew_std, xb_stream_t stream);
 

@@ -159,3 +159,25 @@ def test_ppg_dropins_under_the_reference_agent_loop(env_id):
         assert torch.isfinite(v).all() and not torch.equal(v, p0[k]), k      # every sub-network was trained by some phase
     assert memory.size == 3 and not memory.full
     assert agent.current_step == n * (2 * T + 3)
+
+
+@pytest.mark.parametrize("env_id,n,T", [("Pendulum-v1", 256, 16), ("CartPole-v1", 48, 16)])
+def test_native_a2c_agent_uses_the_a2c_surrogate(env_id, n, T):
+    """Row f3: A2C_Agent (a2c_agent.py:57-100) on the device-resident loop.  With one epoch of one minibatch the policy at
+    update time is the rollout policy, so the logged actor loss must equal -(adv_normalised * stored log-prob).mean()
+    (a2c_learner.py:28) computed from the buffer — at 4096 samples through the tensor-core MLP with the loss in its epilogue,
+    at 768 through the torch MLP and the stand-alone loss kernel."""
+    import xuanpolicy_b200 as xb
+    agent = _build(env_id, parallels=n, n_steps=T, n_epoch=1, n_minibatch=1, shuffle="device", seed=3, agent_class=xb.A2C_Agent,
+                   clip_grad=0.5)
+    info = agent.train(T)
+    assert "clip_ratio" not in info and agent.learner.clip_range == 0.0
+    mem = agent.memory
+    adv = mem._adv.double().reshape(-1)
+    adv_n = (adv.float() - adv.mean().float()) / (adv.std(unbiased=False).float() + 1e-8)
+    expect = float(-(adv_n.double() * mem._logp.double().reshape(-1)).mean())
+    assert abs(info["actor-loss"] - expect) <= 1e-4 * max(1.0, abs(expect)), (info["actor-loss"], expect)
+    expect_c = float(((mem._val - mem._ret).double() ** 2).mean())
+    assert abs(info["critic-loss"] - expect_c) <= 1e-4 * max(1.0, abs(expect_c))
+    info2 = agent.train(2 * T)
+    assert np.isfinite(info2["actor-loss"]) and int(agent.learner._flat.step.item()) == 3

@@ -6,6 +6,7 @@ Drop-in classes (same names / signatures as the reference, see each module's doc
     PPOCLIP_Learner      learner.py   <- xuance/torch/learners/policy_gradient/ppoclip_learner.py:4-65
     A2C / PG / PPOKL / PPG_Learner   learner.py <- xuance/torch/learners/policy_gradient/{a2c,pg,ppokl,ppg}_learner.py
     PPOCLIP_Agent        agent.py     <- xuance/torch/agents/policy_gradient/ppoclip_agent.py:4-165 (vectorised loop)
+    A2C_Agent            agent.py     <- xuance/torch/agents/policy_gradient/a2c_agent.py:6-100 (same loop, A2C surrogate)
 All arithmetic on the path runs in hand-written CUDA kernels reached through the C ABI of include/xb200.h
 (libxb200.so, bound with ctypes in _lib.py).  There is no CPU fallback: importing works anywhere, but
 constructing any of the classes without the library or without a CUDA device raises.
@@ -23,7 +24,7 @@ __version__ = "0.1.0"
 
 
 def __getattr__(name):
-    if name == "PPOCLIP_Agent":
-        from .agent import PPOCLIP_Agent
-        return PPOCLIP_Agent
+    if name in ("PPOCLIP_Agent", "A2C_Agent"):
+        from . import agent
+        return getattr(agent, name)
     raise AttributeError(name)

@@ -45,7 +45,7 @@ SIGNATURES = {
     "xb_random_permutation": [_vp, _i64, _u64, _vp, _u64, _vp],
     "xb_moments4": [_vp, _vp, _vp, _i64, _vp],
     "xb_rms_normalize": [_vp, _i32, _vp, _vp, _vp, _f32, _vp, _i64, _i64, _vp],
-    "xb_returns_track": [_vp, _vp, _vp, _vp, _f64, _vp, _vp, _i64, _vp],
+    "xb_returns_track": [_vp, _vp, _vp, _vp, _f64, _i32, _vp, _vp, _i64, _vp],
     "xb_rms_merge_scalar": [_vp, _vp, _vp, _vp],
     "xb_head_fwd": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
     "xb_head_bwd_act": [_vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],

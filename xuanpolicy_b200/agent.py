@@ -67,6 +67,8 @@ class HostPermutationFeeder:
 
 
 class PPOCLIP_Agent:
+    _mask_terminal_returns = True      # the reward normaliser's return tracker drops the running return on a terminal (:87)
+
     def __init__(self, config, envs, policy, optimizer, scheduler=None, device=None, process_group=None):
         self.use_obsnorm = bool(getattr(config, "use_obsnorm", False))
         self.use_rewnorm = bool(getattr(config, "use_rewnorm", False))
@@ -235,9 +237,11 @@ class PPOCLIP_Agent:
                              rew_std=self._rew_std if self.use_rewnorm else None, rew_clip=self.rewnorm_range)
         if self.use_rewnorm:                                      # returns tracker + ret_rms.update (:87,:91-92)
             if self._norm_peer is not None:      # merged globally at the start of the next step (see above)
-                ops.returns_track(self._returns, env._rew, env._term, env._trunc, self.gamma, self._norm_local[9:], self._ret_ws)
+                ops.returns_track(self._returns, env._rew, env._term, env._trunc, self.gamma, self._norm_local[9:], self._ret_ws,
+                                  mask_terminal=self._mask_terminal_returns)
             else:
-                ops.returns_track(self._returns, env._rew, env._term, env._trunc, self.gamma, self._ret_sums, self._ret_ws)
+                ops.returns_track(self._returns, env._rew, env._term, env._trunc, self.gamma, self._ret_sums, self._ret_ws,
+                                  mask_terminal=self._mask_terminal_returns)
                 ops.rms_merge_scalar(self._ret_sums, self._ret_rms, self._rew_std)
         self._cur ^= 1
 
@@ -573,3 +577,26 @@ class PPOCLIP_Agent:
                         obs[i] = infos[int(i)]["reset_obs"]
         envs.close()
         return scores
+
+
+class A2C_Agent(PPOCLIP_Agent):
+    """A2C_Agent drop-in (xuance/torch/agents/policy_gradient/a2c_agent.py:6-100), vectorised like PPOCLIP_Agent: the same
+    device-resident rollout / GAE / minibatch loop — the reference's two `train` bodies differ only in the learner
+    (A2C surrogate -(adv * log_prob).mean(), a2c_learner.py:24-35, always gradient-clipped with `config.clip_grad`, :36),
+    the absent old_logp auxiliary, and the reward normaliser's return tracker, which does not mask terminals (:85).
+    The fused kernels select the A2C surrogate with clip_range = 0."""
+
+    _mask_terminal_returns = False
+
+    def __init__(self, config, envs, policy, optimizer, scheduler=None, device=None, process_group=None):
+        from argparse import Namespace
+        cfg = Namespace(**vars(config))
+        cfg.clip_range = 0.0                                   # A2C surrogate in the loss kernels
+        cfg.clip_grad_norm = getattr(config, "clip_grad", getattr(config, "clip_grad_norm", 0.5))
+        cfg.use_grad_clip = True
+        super().__init__(cfg, envs, policy, optimizer, scheduler, device, process_group)
+
+    def _collect_info(self):
+        info = super()._collect_info()
+        info.pop("clip_ratio", None)                           # a2c_learner.py:42-48 logs no clip ratio
+        return info

@@ -24,8 +24,9 @@ def ppo_config(env_id, **overrides):
     return Namespace(**cfg)
 
 
-def build_ppo(env_id, device="cuda", process_group=None, policy_seed=None, **overrides):
-    """Envs + policy + Adam + LinearLR + agent, wired like Runner_DRL.__init__ (xuance/torch/runners/runner_drl.py:15-74)."""
+def build_ppo(env_id, device="cuda", process_group=None, policy_seed=None, agent_class=None, **overrides):
+    """Envs + policy + Adam + LinearLR + agent, wired like Runner_DRL.__init__ (xuance/torch/runners/runner_drl.py:15-74).
+    `agent_class`: PPOCLIP_Agent (default) or A2C_Agent."""
     import torch
 
     from .agent import PPOCLIP_Agent
@@ -40,5 +41,5 @@ def build_ppo(env_id, device="cuda", process_group=None, policy_seed=None, **ove
     optimizer = torch.optim.Adam(policy.parameters(), cfg.learning_rate, eps=1e-5)      # runner_drl.py:71
     scheduler = torch.optim.lr_scheduler.LinearLR(optimizer, start_factor=1.0, end_factor=0.0,
                                                   total_iters=int(cfg.running_steps))    # runner_drl.py:72-73
-    agent = PPOCLIP_Agent(cfg, envs, policy, optimizer, scheduler, device, process_group=process_group)
+    agent = (agent_class or PPOCLIP_Agent)(cfg, envs, policy, optimizer, scheduler, device, process_group=process_group)
     return agent

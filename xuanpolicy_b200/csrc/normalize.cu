@@ -118,14 +118,15 @@ __global__ void __launch_bounds__(kNormBlock)
 // (int64 array x python float), and ret_rms then evolves in float64 (ppoclip_agent.py:87,91).
 __global__ void __launch_bounds__(kNormBlock)
     returns_track_kernel(double* __restrict__ returns, const float* __restrict__ rew, const uint8_t* __restrict__ term,
-                         const uint8_t* __restrict__ trunc, double gamma, double* __restrict__ sums,
+                         const uint8_t* __restrict__ trunc, double gamma, int mask_terminal, double* __restrict__ sums,
                          double* __restrict__ ws, int64_t N) {
     __shared__ double smem[3 * 32];
     __shared__ bool is_last;
     double a[3] = {0, 0, 0};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
         const bool tm = term[i] != 0, tr = trunc[i] != 0;
-        double R = (tm ? 0.0 : 1.0) * gamma * returns[i] + (double)rew[i];
+        // PPO: (1 - terminals) * gamma * returns + rewards (ppoclip_agent.py:87); A2C: gamma * returns + rewards (a2c_agent.py:85)
+        double R = ((tm && mask_terminal) ? 0.0 : 1.0) * gamma * returns[i] + (double)rew[i];
         if (tm || tr) {
             a[0] += R;
             a[1] += R * R;
@@ -195,10 +196,10 @@ extern "C" int xb_rms_normalize(const float* x, int dim, const double* sums, con
 }
 
 extern "C" int xb_returns_track(double* returns, const float* rew, const uint8_t* term, const uint8_t* trunc, double gamma,
-                                double* sums, double* workspace, int64_t N, xb_stream_t stream) {
+                                int mask_terminal, double* sums, double* workspace, int64_t N, xb_stream_t stream) {
     if (N <= 0 || !returns || !rew || !term || !trunc || !sums || !workspace) return XB_E_BADARG;
     returns_track_kernel<<<grid_for(N, kNormBlock, 2), kNormBlock, 0, (cudaStream_t)stream>>>(returns, rew, term, trunc, gamma,
-                                                                                              sums, workspace, N);
+                                                                                              mask_terminal, sums, workspace, N);
     XB_LAUNCH_CHECK();
     return 0;
 }

@@ -260,9 +260,9 @@ def rms_normalize(x, dim, sums, state_in, state_out, clip, out, n_merged_rows):
               _p(out, F32), x.shape[0], int(n_merged_rows), _stream())
 
 
-def returns_track(returns, rew, term, trunc, gamma, sums, workspace):
-    _lib.call("xb_returns_track", _p(returns, F64), _p(rew, F32), _p(term, U8), _p(trunc, U8), float(gamma), _p(sums, F64),
-              _p(workspace, F64), returns.numel(), _stream())
+def returns_track(returns, rew, term, trunc, gamma, sums, workspace, mask_terminal=True):
+    _lib.call("xb_returns_track", _p(returns, F64), _p(rew, F32), _p(term, U8), _p(trunc, U8), float(gamma),
+              1 if mask_terminal else 0, _p(sums, F64), _p(workspace, F64), returns.numel(), _stream())
 
 
 def rms_merge_scalar(sums, state, rew_std):
