@@ -246,3 +246,57 @@ def test_loss_fused_into_the_forward_epilogue_equals_the_loss_kernel(env_id, hid
     assert torch.allclose(s_new, s_ref, rtol=1e-6, atol=1e-6 * scale), (s_new, s_ref)
     if gauss:
         assert torch.allclose(dls_new, dls_ref, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["loss_gauss_h128"])
+def test_fused_loss_epilogue_update_matches_reference_golden(name):
+    """The native update with the loss INSIDE the forward kernel's epilogue (xb_dense_fwd2_loss), the norm inside the
+    backward tail launch and the operand split inside the Adam launch, against the REFERENCE's own PPOCLIP_Learner.update
+    (golden generated by running the unmodified reference): info scalars, every param.grad before clipping (1e-4),
+    parameters after the clipped Adam step (1e-5)."""
+    import xuanpolicy_b200 as xb
+    from tests.helpers import load_golden, rel_close
+    from xuanpolicy_b200 import policies, spaces
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = load_golden(name)
+    m = g["meta"]
+    dev = "cuda"
+    t = lambda k: torch.as_tensor(g[k], device=dev).float().contiguous()
+    B = g["ret"].shape[0]
+    scal = torch.stack([t("act").reshape(B), t("old_logp"), t("adv"), t("ret")], dim=1).contiguous()   # packed minibatch rows
+    for tag, clip in (("noclip", False), ("clip", True)):
+        pol = policies.make_policy(spaces.Box(-1, 1, (3,)), spaces.Box(-2.0, 2.0, (1,)), hidden=(m["hidden"],), device=dev)
+        pol.load_state_dict({k[3:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("p0/")})
+        opt = torch.optim.Adam(pol.parameters(), 4e-4, eps=1e-5)
+        sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=1000)
+        learner = xb.PPOCLIP_Learner(pol, opt, sched, dev, "/tmp", vf_coef=m["vf_coef"], ent_coef=m["ent_coef"],
+                                     clip_range=m["clip_range"], clip_grad_norm=m["clip_grad_norm"], use_grad_clip=clip)
+        flat = learner.enable_fused_optimizer()
+        fused = learner._fused
+        dls64 = torch.zeros(1, dtype=torch.float64, device=dev)
+        loss = dict(scal=scal, adv_stats=None, adv_count=B, clip_range=m["clip_range"], vf_coef=m["vf_coef"],
+                    ent_coef=m["ent_coef"], inv_batch=1.0 / B, logstd=pol.actor.logstd.detach(), scalars=learner._scalars,
+                    dlogstd=dls64)
+        fused.norm_sink = (flat, m["clip_grad_norm"] if clip else 0.0)
+        fused.forward(t("obs"), loss=loss)
+        b = fused._last[1]
+        dls32 = flat.grad_views[[id(q) for q in flat.params].index(id(pol.actor.logstd))]
+        fused.backward(b["dact"], b["dv"], dls64, dls32)
+        assert fused.norm_done
+        torch.cuda.synchronize()
+        for k, p in pol.named_parameters():
+            ok, err = rel_close(p.grad.cpu().numpy(), g["grad_noclip/%s" % k], 1e-4)
+            assert ok, (tag, k, err)
+        learner.stage_optimizer()                    # Adam (+ operand split) from the scalars the tail launch derived
+        assert fused.splits_fresh
+        info = learner.info(B)
+        for k in ("actor-loss", "critic-loss", "entropy", "predict_value", "clip_ratio"):
+            ref = float(g["info_%s/%s" % (tag, k)])
+            assert abs(float(info[k]) - ref) <= 1e-4 * max(1.0, abs(ref)), (k, float(info[k]), ref)
+        for k, p in pol.named_parameters():
+            ok, err = rel_close(p.detach().cpu().numpy(), g["p1_%s/%s" % (tag, k)], 1e-5)
+            assert ok, (tag, k, err)
+        # the operand copies the Adam launch wrote equal a fresh split of the updated weights
+        hi, lo = fused.wa_hi.clone(), fused.wa_lo.clone()
+        fused.refresh_weights()
+        assert torch.equal(hi, fused.wa_hi) and torch.equal(lo, fused.wa_lo)
