@@ -407,6 +407,7 @@ def main():
     gen_buffer("buffer_cat_nogae", 103, 4, 32, True, False, True, 0.99, 0.95)
     gen_loss("loss_cat_h64", 201, True, 64, 512, hp)
     gen_loss("loss_gauss_h128", 202, False, 128, 1024, hp)
+    gen_loss("loss_cat_h128", 211, True, 128, 1024, hp)          # width the tensor-core MLP path supports, Categorical head
     gen_loss_a2c_pg("loss_a2c_gauss_h64", 203, "a2c", False, 64, 640)
     gen_loss_a2c_pg("loss_pg_cat_h32", 204, "pg", True, 32, 384)
     gen_f3_dist()

@@ -248,7 +248,7 @@ def test_loss_fused_into_the_forward_epilogue_equals_the_loss_kernel(env_id, hid
         assert torch.allclose(dls_new, dls_ref, rtol=1e-6, atol=1e-9)
 
 
-@pytest.mark.parametrize("name", ["loss_gauss_h128"])
+@pytest.mark.parametrize("name", ["loss_gauss_h128", "loss_cat_h128"])
 def test_fused_loss_epilogue_update_matches_reference_golden(name):
     """The native update with the loss INSIDE the forward kernel's epilogue (xb_dense_fwd2_loss), the norm inside the
     backward tail launch and the operand split inside the Adam launch, against the REFERENCE's own PPOCLIP_Learner.update
@@ -265,7 +265,10 @@ def test_fused_loss_epilogue_update_matches_reference_golden(name):
     B = g["ret"].shape[0]
     scal = torch.stack([t("act").reshape(B), t("old_logp"), t("adv"), t("ret")], dim=1).contiguous()   # packed minibatch rows
     for tag, clip in (("noclip", False), ("clip", True)):
-        pol = policies.make_policy(spaces.Box(-1, 1, (3,)), spaces.Box(-2.0, 2.0, (1,)), hidden=(m["hidden"],), device=dev)
+        if m["discrete"]:
+            pol = policies.make_policy(spaces.Box(-1, 1, (4,)), spaces.Discrete(2), hidden=(m["hidden"],), device=dev)
+        else:
+            pol = policies.make_policy(spaces.Box(-1, 1, (3,)), spaces.Box(-2.0, 2.0, (1,)), hidden=(m["hidden"],), device=dev)
         pol.load_state_dict({k[3:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("p0/")})
         opt = torch.optim.Adam(pol.parameters(), 4e-4, eps=1e-5)
         sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=1000)
@@ -273,15 +276,19 @@ def test_fused_loss_epilogue_update_matches_reference_golden(name):
                                      clip_range=m["clip_range"], clip_grad_norm=m["clip_grad_norm"], use_grad_clip=clip)
         flat = learner.enable_fused_optimizer()
         fused = learner._fused
-        dls64 = torch.zeros(1, dtype=torch.float64, device=dev)
+        gauss = not m["discrete"]
+        dls64 = torch.zeros(1, dtype=torch.float64, device=dev) if gauss else None
         loss = dict(scal=scal, adv_stats=None, adv_count=B, clip_range=m["clip_range"], vf_coef=m["vf_coef"],
-                    ent_coef=m["ent_coef"], inv_batch=1.0 / B, logstd=pol.actor.logstd.detach(), scalars=learner._scalars,
-                    dlogstd=dls64)
+                    ent_coef=m["ent_coef"], inv_batch=1.0 / B, logstd=pol.actor.logstd.detach() if gauss else None,
+                    scalars=learner._scalars, dlogstd=dls64)
         fused.norm_sink = (flat, m["clip_grad_norm"] if clip else 0.0)
         fused.forward(t("obs"), loss=loss)
         b = fused._last[1]
-        dls32 = flat.grad_views[[id(q) for q in flat.params].index(id(pol.actor.logstd))]
-        fused.backward(b["dact"], b["dv"], dls64, dls32)
+        if gauss:
+            dls32 = flat.grad_views[[id(q) for q in flat.params].index(id(pol.actor.logstd))]
+            fused.backward(b["dact"], b["dv"], dls64, dls32)
+        else:
+            fused.backward(b["dact"], b["dv"])
         assert fused.norm_done
         torch.cuda.synchronize()
         for k, p in pol.named_parameters():

@@ -151,7 +151,7 @@ def _policy_from_golden(g):
     return pol
 
 
-@pytest.mark.parametrize("name", ["loss_cat_h64", "loss_gauss_h128"])
+@pytest.mark.parametrize("name", ["loss_cat_h64", "loss_gauss_h128", "loss_cat_h128"])
 def test_learner_port_matches_reference_golden(name):
     g = load_golden(name)
     m = g["meta"]
