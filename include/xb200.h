@@ -431,7 +431,7 @@ int xb_mlp_trunk_wgrad(const float* dz1, const float* obs, int ld, int obs_dim, 
  * exported / imported through CUDA IPC (xb_peer_export -> 64-byte handle -> xb_peer_import in the peer process).
  * peer_bases is a HOST array of the W device pointers (index = rank; own block at [rank]).
  * tickets: u32 [64] device, zero-initialised once, private to the rank (per-CTA barrier counters; never reset).
- * Every rank must issue the same sequence of xb_peer_* launches with the same n.  A barrier wait that exceeds 20 s gives up
+ * Every rank must issue the same sequence of xb_peer_* launches with the same n.  A barrier wait that exceeds 60 s gives up
  * and sets tickets[62] (the host checks it) instead of spinning forever when a peer process has died.
  *
  * xb_peer_allreduce_grad_norm: every CTA pushes its slice of grad_in (local, fp32 [n]) into inbox[launch parity][rank] of

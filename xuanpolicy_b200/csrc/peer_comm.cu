@@ -62,7 +62,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-constexpr unsigned long long kPeerTimeoutNs = 20ULL * 1000 * 1000 * 1000;   // a peer that is 20 s late is gone
+constexpr unsigned long long kPeerTimeoutNs = 60ULL * 1000 * 1000 * 1000;   // a peer that is 60 s late is gone
 constexpr int kPeerErrSlot = kPeerSlots - 2;                                // tickets[kPeerErrSlot] != 0: a barrier timed out
 
 // All threads of the CTA call it; `ticket` must be the same in every rank for the same barrier instance.

@@ -118,7 +118,7 @@ class PeerComm:
         dist.barrier(group)          # every rank has mapped every block before the first kernel touches one
 
     def check(self):
-        """Raises if a cross-GPU barrier timed out on this rank (a peer process died or fell > 20 s behind).
+        """Raises if a cross-GPU barrier timed out on this rank (a peer process died or fell > 60 s behind).
         Costs one 4-byte D2H read: call it where the host synchronises anyway."""
         if int(self.tickets[62].item()) != 0:
             raise RuntimeError("xb200 peer-memory barrier timed out on rank %d: a peer rank is gone or stalled" % self.rank)
