@@ -181,3 +181,45 @@ def test_native_a2c_agent_uses_the_a2c_surrogate(env_id, n, T):
     assert abs(info["critic-loss"] - expect_c) <= 1e-4 * max(1.0, abs(expect_c))
     info2 = agent.train(2 * T)
     assert np.isfinite(info2["actor-loss"]) and int(agent.learner._flat.step.item()) == 3
+
+
+@pytest.mark.parametrize("env", [{"XB_ADAM_SPLIT": "0"}, {"XB_TAIL_NORM": "0"}, {}])
+def test_graph_replay_resplits_weights_on_every_optimizer_path(env, monkeypatch):
+    """the first minibatch of every captured epoch must see tf32 operand copies that match the weights, also
+    when the optimiser launch does not rewrite them (XB_ADAM_SPLIT=0, XB_TAIL_NORM=0 = the path the NCCL fallback uses).
+    Graph replay over several epochs and rollouts must equal the eager loop on the same path (tensor-core MLP active:
+    minibatch 2048 rows)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    out = []
+    for graphs in (True, False):
+        agent = _build("CartPole-v1", parallels=64, n_steps=64, n_epoch=3, n_minibatch=2, use_cuda_graphs=graphs,
+                       shuffle="device", seed=3)
+        assert agent.learner._fused is not None and agent.batch_size >= agent.learner._fused.MIN_ROWS
+        assert agent.learner.adam_resplits() == (not env)
+        agent.train(2 * 64)
+        out.append(agent.learner._flat.flat_param.clone())
+    assert torch.allclose(out[0], out[1], atol=2e-5, rtol=1e-4), (out[0] - out[1]).abs().max()
+
+
+def test_train_accepts_any_step_count_and_ragged_minibatches():
+    """ppoclip_agent.py:59-61,79-83: `train(k)` for any k (the buffer position carries across calls) and a short last
+    minibatch when n_envs * n_steps is not a multiple of n_minibatch."""
+    agent = _build("CartPole-v1", parallels=30, n_steps=20, n_epoch=2, n_minibatch=7, shuffle="device", seed=2)
+    assert agent.batch_size == 85 and agent.n_updates_per_epoch == 8           # 7 x 85 + one minibatch of 5
+    agent.train(7)
+    assert agent.memory.ptr == 7 and agent.learner.iterations == 0 and agent.current_step == 0
+    agent.train(13 + 20 + 4)                                                   # finishes rollout 1 (eager), rollout 2 (graph), 4 into rollout 3
+    assert agent.learner.iterations == 2 * 2 * 8 and agent.memory.ptr == 4
+    assert int(agent.learner._flat.step.item()) == 32
+    info = agent.train(16)
+    assert agent.learner.iterations == 3 * 2 * 8 and agent.memory.ptr == 0 and agent.current_step == 3 * 30 * 20
+    assert np.isfinite(info["actor-loss"]) and np.isfinite(info["critic-loss"])
+    # the partial-rollout path is the graph's launches issued eagerly: same rollout either way
+    a = _build("Pendulum-v1", parallels=16, n_steps=12, n_epoch=1, n_minibatch=2, shuffle="device", seed=4)
+    b = _build("Pendulum-v1", parallels=16, n_steps=12, n_epoch=1, n_minibatch=2, shuffle="device", seed=4)
+    a.train(12)
+    b.train(5)
+    b.train(7)
+    assert torch.equal(a.envs._state, b.envs._state) and torch.equal(a.memory._adv, b.memory._adv)
+    assert torch.allclose(a.learner._flat.flat_param, b.learner._flat.flat_param, atol=1e-6)

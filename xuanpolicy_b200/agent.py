@@ -5,24 +5,34 @@ Mirrors PPOCLIP_Agent (xuance/torch/agents/policy_gradient/ppoclip_agent.py:4-16
 steps; one PPO update phase of n_epoch x n_minibatch SGD steps every n_steps), same hyper-parameter names.
 
 What changes is the shape of the loop, not its arithmetic:
-  * one rollout of n_steps vector steps is ONE CUDA graph: policy forward (torch) -> fused sample+log-prob kernel
-    -> env step kernel -> rollout store kernel, per step, then the bootstrap forward and the batched GAE scan;
-    the reference's O(N) Python loops (:71-75, :89-109), per-step D2H copies (:54-56) and list-of-dict infos are gone;
+  * one rollout of n_steps vector steps is ONE CUDA graph: per step the whole actor-critic forward in one launch
+    (csrc/dense_tc.cu xb_mlp_fwd_from_obs; the torch modules only below FusedActorCritic.MIN_ROWS rows or for
+    unsupported policy shapes) and one fused sample + env step + store launch (csrc/env_classic.cu
+    rollout_step_kernel), then the bootstrap forward and the batched GAE scan; the reference's O(N) Python loops
+    (:71-75, :89-109), per-step D2H copies (:54-56) and list-of-dict infos are gone;
   * truncation bootstraps: the reference runs a full-batch forward per finished env (:99); here every step's
     forward also evaluates V(terminal obs of the previous step) on rows [N, 2N) of the same batch, so the
     values are there for whichever envs were truncated;
-  * the update phase is n_epoch graph launches (n_minibatch fused updates each); with env-sharded data
-    parallelism the two NCCL all-reduces per update sit between graph stages.
+  * the update phase is n_epoch graph launches (n_minibatch fused updates each, every kernel hand-written); with
+    env-sharded data parallelism the exchanges are kernels of ours over NVLink peer memory inside the same graph
+    (csrc/peer_comm.cu); NCCL all-reduces between per-stage graphs are the fallback when CUDA IPC is unavailable.
+Env-sharded runs: every rank may be given the SAME config seed — the action-sampling key and the permutation seeds
+fold the rank in, so the ranks' rollouts are decorrelated (the envs themselves are all seeded alike, like the
+reference's, gym_env.py:18-19, and diverge through their actions).
 Index permutations follow the reference (`np.random.shuffle` of a persistent arange, :76-78) when
 `config.shuffle == "host"` (copied H2D from pinned memory each epoch), or are drawn on device ("device").
 
 `use_obsnorm` / `use_rewnorm` run on device too: RunningMeanStd moments + Chan merge + clip in
-csrc/normalize.cu, two extra launches per step each (single-GPU; the sharded variant needs a per-step all-reduce).
+csrc/normalize.cu, two extra launches per step each; env-sharded, the per-step moments are exchanged over peer memory so
+every rank holds the global statistics.
+`train(train_steps)` accepts any step count (ppoclip_agent.py:59-61): whole rollouts replay the captured graph, a
+partial rollout runs the same launches eagerly and the buffer position carries over to the next call.
 """
 import numpy as np
 import torch
 
 from . import _lib, ops
+from . import dist as xdist
 from .buffer import DummyOnPolicyBuffer
 from .learner import PPOCLIP_Learner
 from .spaces import is_discrete
@@ -83,9 +93,13 @@ class PPOCLIP_Agent:
         self.discrete = is_discrete(self.action_space)
         self.buffer_size = self.n_envs * self.n_steps
         self.batch_size = self.buffer_size // self.n_minibatch
+        self.n_updates_per_epoch = -(-self.buffer_size // self.batch_size)      # incl. the short last minibatch, if any
         self.use_graphs = bool(getattr(config, "use_cuda_graphs", True))
         self.shuffle = getattr(config, "shuffle", "host")
         self.seed = int(getattr(config, "seed", 1))
+        # Philox key of the action sampler: the rank is folded in so that ranks given the same config seed draw
+        # different actions (otherwise W ranks would compute W bit-identical rollouts)
+        self._sample_seed = self.seed + 1000003 * self._rank()
         self.memory = DummyOnPolicyBuffer(self.observation_space, self.action_space, {"old_logp": ()}, self.n_envs,
                                           self.n_steps, config.use_gae, config.use_advnorm, self.gamma, self.gae_lam,
                                           device=self.device, native=True,
@@ -97,7 +111,10 @@ class PPOCLIP_Agent:
         self.learner.enable_fused_optimizer(process_group)
         self.world_size = self.learner.world_size
         if self.world_size > 1:   # replicated policy: every rank starts from rank 0's parameters
-            torch.distributed.broadcast(self.learner._flat.flat_param, src=0, group=process_group)
+            xdist.broadcast_parameters(self.learner._flat.flat_param, 0, process_group)
+            if self.buffer_size % self.batch_size:
+                raise ValueError("env-sharded training needs n_envs * n_steps (%d) divisible by n_minibatch (%d): the ranks' "
+                                 "minibatches must be equal for the global-minibatch statistics" % (self.buffer_size, self.n_minibatch))
         N, dev = self.n_envs, self.device
         obs_dim = self.memory.obs_dim
         self._obs_dim = obs_dim
@@ -125,6 +142,7 @@ class PPOCLIP_Agent:
                                                  workers=int(getattr(config, "feeder_threads", 4)))
             self._feeder.prefetch(0)
         self._iteration = 0
+        self._t = 0                        # vector steps already taken in the current (unfinished) rollout
         self.sync_info = bool(getattr(config, "sync_info", True))
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -188,12 +206,12 @@ class PPOCLIP_Agent:
         N = self.n_envs
         if self.discrete:
             logits = dist.get_param()
-            ops.sample_categorical(logits[:N].contiguous(), self.seed, self._ctr, offset, self._act, self._logp)
+            ops.sample_categorical(logits[:N].contiguous(), self._sample_seed, self._ctr, offset, self._act, self._logp)
         else:
             mu, std = dist.get_param()
             logstd = getattr(getattr(self.policy, "actor", None), "logstd", None)   # gaussian.py:25
             logstd = logstd.detach() if logstd is not None else std.log().contiguous()
-            ops.sample_gaussian(mu[:N].contiguous(), logstd, self.seed, self._ctr, offset, self._act, self._logp)
+            ops.sample_gaussian(mu[:N].contiguous(), logstd, self._sample_seed, self._ctr, offset, self._act, self._logp)
 
     def _rollout_step(self, t):
         """One vector step into buffer row t (reference loop body, ppoclip_agent.py:62-68,88,101)."""
@@ -220,7 +238,7 @@ class PPOCLIP_Agent:
                 act_param = prm[0][:N]
                 logstd = getattr(getattr(self.policy, "actor", None), "logstd", None)
                 logstd = logstd.detach() if logstd is not None else prm[1].log().contiguous()
-            ops.rollout_step(env._kind, act_param, logstd, v[:N], self.seed, self._ctr, t, env._state, env._rng,
+            ops.rollout_step(env._kind, act_param, logstd, v[:N], self._sample_seed, self._ctr, t, env._state, env._rng,
                              env._elapsed, env._ep_score, x_nxt[N:], x_nxt[:N], env._rew, env._term, env._trunc,
                              env._reset_obs, env._ep_step_out, env._ep_score_out, env.ep_stats, env.max_episode_length,
                              x_in[:N], self._act, self._logp, mem._obs[t], mem._act[t], mem._rew[t], mem._val[t],
@@ -261,24 +279,31 @@ class PPOCLIP_Agent:
         self._rms_cur ^= 1
         return self._xn
 
-    def _rollout(self):
-        """n_steps vector steps, the bootstrap forward (:70) and the batched GAE for every env and segment (:71-75)."""
+    def _rollout_begin(self):
+        if self.learner._fused is not None:
+            self.learner._fused.refresh_weights()
+
+    def _rollout_end(self):
+        """The bootstrap forward (:70), the batched GAE for every env and segment (:71-75), counter / ping-pong upkeep."""
         N = self.n_envs
-        with torch.no_grad():
-            if self.learner._fused is not None:
-                self.learner._fused.refresh_weights()
-            for t in range(self.n_steps):
-                self._rollout_step(t)
-            _, v = self._policy_forward(self._normalize_obs(self._x[self._cur], update=False))
-            self._boot_last.copy_(v[N:])
-            self.memory.finish_rollout(self._boot_last)
-            ops.counter_add(self._ctr, self.n_steps)
+        _, v = self._policy_forward(self._normalize_obs(self._x[self._cur], update=False))
+        self._boot_last.copy_(v[N:])
+        self.memory.finish_rollout(self._boot_last)
+        ops.counter_add(self._ctr, self.n_steps)
         if self.n_steps % 2:   # keep the ping-pong phase identical for every replay of the captured graph
             self._x[self._cur ^ 1].copy_(self._x[self._cur])
             self._cur ^= 1
         if self._rms_cur:      # same for the normaliser state (n_steps + 1 publications per rollout)
             self._obs_rms[0].copy_(self._obs_rms[1])
             self._rms_cur = 0
+
+    def _rollout(self):
+        """n_steps vector steps, the bootstrap forward and the GAE scan: the body of the captured rollout graph."""
+        with torch.no_grad():
+            self._rollout_begin()
+            for t in range(self.n_steps):
+                self._rollout_step(t)
+            self._rollout_end()
 
     # ---------------------------------------------------------------------------------------------- update phase
     def _device_permutation(self):
@@ -287,12 +312,24 @@ class PPOCLIP_Agent:
         ops.random_permutation(self._perm, self._perm_seed, self._perm_ctr, 0)
         ops.counter_add(self._perm_ctr, 1)
 
+    def _epoch_start(self):
+        """Called at the top of every (captured) epoch / first-minibatch stage.  The tf32 hi/lo operand copies of the
+        hidden-layer weights are only known to be current if the optimiser launch re-splits them (adam_apply_split);
+        on every other path the first minibatch of the epoch re-splits unconditionally — the `splits_fresh` flag is
+        Python state evaluated at capture time and must not leak from the capture of the rollout graph."""
+        fused = self.learner._fused
+        if fused is not None and not self.learner.adam_resplits():
+            fused.splits_fresh = False
+
     def _epoch_body(self, perm=None):
         B = self.batch_size
+        self._epoch_start()
         if self.shuffle != "host":
             self._device_permutation()
         perm = self._perm if perm is None else perm
-        for start in range(0, self.buffer_size - B + 1, B):
+        # like the reference (`range(0, buffer_size, batch_size)`, ppoclip_agent.py:79-83): when buffer_size is not a
+        # multiple of n_minibatch the last, short minibatch is trained on too
+        for start in range(0, self.buffer_size, B):
             idx = perm[start:start + B]
             mb = self.learner.stage_gather(self.memory, idx)
             self.learner.stage_forward_backward(self.memory, idx, mb)
@@ -305,6 +342,7 @@ class PPOCLIP_Agent:
         fused into the first optimiser kernel (csrc/peer_comm.cu)."""
         B, lr, mem, peer = self.batch_size, self.learner, self.memory, self.learner._peer
         M = self.buffer_size // B
+        self._epoch_start()
         if self.shuffle != "host":
             self._device_permutation()
         perm = self._perm if perm is None else perm
@@ -327,6 +365,8 @@ class PPOCLIP_Agent:
         if self.learner._peer is not None:
             return self._epoch_peer()
         B, lr, mem = self.batch_size, self.learner, self.memory
+        if self._stage_graphs is None:
+            self._epoch_start()
         for k, start in enumerate(range(0, self.buffer_size - B + 1, B)):
             idx = self._perm[start:start + B]
             g = self._stage_graphs[k] if self._stage_graphs is not None else None
@@ -336,12 +376,12 @@ class PPOCLIP_Agent:
             else:
                 mb = lr.stage_gather(mem, idx)
             if mem.use_advnorm:
-                torch.distributed.all_reduce(mb["stats"], group=lr.process_group)
+                xdist.allreduce_adv_stats(mb["stats"], lr.process_group)
             if g is not None:
                 g[1].replay()
             else:
                 lr.stage_forward_backward(mem, idx, mb)
-            torch.distributed.all_reduce(lr._flat.flat_grad, group=lr.process_group)
+            xdist.allreduce_flat_grad(lr._flat.flat_grad, lr.process_group)
             if g is not None:
                 g[2].replay()
             else:
@@ -379,13 +419,13 @@ class PPOCLIP_Agent:
             ev.record(main)
             self._perm_free[k] = ev
         self._feeder.mark_consumed(self._iteration)
-        self.learner.iterations += self.n_epoch * (self.buffer_size // self.batch_size)
+        self.learner.iterations += self.n_epoch * self.n_updates_per_epoch
         self._iteration += 1
 
     def _update_phase(self):
         if self._epoch_graphs is not None:
             return self._update_phase_overlapped()
-        n_updates = self.n_epoch * (self.buffer_size // self.batch_size)
+        n_updates = self.n_epoch * self.n_updates_per_epoch
         if self.shuffle == "host":
             self._feeder.prefetch(self._iteration + 1)             # next rollout's permutations, drawn while the GPU works
         for ep in range(self.n_epoch):
@@ -451,6 +491,8 @@ class PPOCLIP_Agent:
             graphs = []
             for start in range(0, self.buffer_size - B + 1, B):
                 idx = self._perm[start:start + B]
+                if start == 0:
+                    self._epoch_start()
                 ga, gb, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
                 with torch.cuda.graph(ga):
                     mb = lr.stage_gather(mem, idx)
@@ -487,13 +529,14 @@ class PPOCLIP_Agent:
 
     def _epoch_distributed_eager(self):
         B, lr, mem = self.batch_size, self.learner, self.memory
+        self._epoch_start()
         for start in range(0, self.buffer_size - B + 1, B):
             idx = self._perm[start:start + B]
             mb = lr.stage_gather(mem, idx)
             if mem.use_advnorm:
-                torch.distributed.all_reduce(mb["stats"], group=lr.process_group)
+                xdist.allreduce_adv_stats(mb["stats"], lr.process_group)
             lr.stage_forward_backward(mem, idx, mb)
-            torch.distributed.all_reduce(lr._flat.flat_grad, group=lr.process_group)
+            xdist.allreduce_flat_grad(lr._flat.flat_grad, lr.process_group)
             lr.stage_optimizer()
 
     def _snapshot(self):
@@ -515,22 +558,39 @@ class PPOCLIP_Agent:
 
     # ---------------------------------------------------------------------------------------------- public API
     def train(self, train_steps):
-        """train_steps vector steps (reference: `for _ in tqdm(range(train_steps))`); a PPO update phase after every
-        n_steps of them.  Returns the log dict of the last update phase (also kept in `self.last_info`)."""
-        if train_steps % self.n_steps != 0:
-            raise ValueError("the device-resident loop advances in whole rollouts: train_steps (%d) must be a "
-                             "multiple of n_steps (%d)" % (train_steps, self.n_steps))
+        """train_steps vector steps (reference: `for _ in tqdm(range(train_steps))`, ppoclip_agent.py:59-61); a PPO update
+        phase every time the buffer fills (every n_steps of them, counted across calls like the reference's `memory.ptr`).
+        Whole rollouts replay the captured graph; a partial rollout (train_steps not a multiple of n_steps, or a call that
+        starts mid-rollout) issues the same launches eagerly.  Returns the log dict of the last update phase (also kept in
+        `self.last_info`)."""
+        remaining = int(train_steps)
         with torch.cuda.device(self.device):
-            if self.use_graphs and self._rollout_graph is None:
-                self._capture()
-            for _ in range(train_steps // self.n_steps):
-                if self._epoch_graphs is not None and not self._perm_staged:
-                    self._stage_host_perm(0)                       # first permutation travels while the rollout runs
-                    self._perm_staged = True
-                if self._rollout_graph is not None:
-                    self._rollout_graph.replay()
-                else:
-                    self._rollout()
+            while remaining > 0:
+                if self._t == 0 and remaining >= self.n_steps:
+                    if self.use_graphs and self._rollout_graph is None:
+                        self._capture()            # only ever at a rollout boundary: the warm-up rollout overwrites the buffer
+                    if self._epoch_graphs is not None and not self._perm_staged:
+                        self._stage_host_perm(0)                   # first permutation travels while the rollout runs
+                        self._perm_staged = True
+                    if self._rollout_graph is not None:
+                        self._rollout_graph.replay()
+                    else:
+                        self._rollout()
+                    remaining -= self.n_steps
+                else:                                              # partial rollout: the same launches, eagerly
+                    k = min(remaining, self.n_steps - self._t)
+                    with torch.no_grad():
+                        if self._t == 0:
+                            self._rollout_begin()
+                        for t in range(self._t, self._t + k):
+                            self._rollout_step(t)
+                        self._t += k
+                        remaining -= k
+                        self.memory.ptr = self.memory.size = self._t
+                        if self._t < self.n_steps:
+                            break
+                        self._rollout_end()
+                self._t = 0
                 self.memory.ptr, self.memory.size = 0, self.n_steps
                 self._update_phase()
                 self.memory.clear_fast()
@@ -543,7 +603,8 @@ class PPOCLIP_Agent:
 
     def _collect_info(self):
         """One host sync per rollout: learner scalars + episode totals (reference logs at :84,:102-109)."""
-        info = self.learner.info(self.batch_size)
+        last_mb = self.buffer_size - (self.n_updates_per_epoch - 1) * self.batch_size   # size of the last minibatch trained on
+        info = self.learner.info(last_mb)
         if self.learner._peer is not None:
             self.learner._peer.check()
         st = self.envs.ep_stats.cpu().numpy()

@@ -33,7 +33,7 @@ SOURCES = {
     "dense_tc.cu": [],
     "mlp_trunk.cu": [],
 }
-HEADERS = ["common.cuh", "sm100.cuh", "sample.cuh", "crtrig.cuh", "crtrig_consts.inc", os.path.join("..", "..", "include", "xb200.h")]
+HEADERS = ["common.cuh", "sm100.cuh", "sample.cuh", "optim.cuh", "crtrig.cuh", "crtrig_consts.inc", os.path.join("..", "..", "include", "xb200.h")]
 
 
 def _stale(target, deps):

@@ -653,11 +653,7 @@ static int launch_kmajor(const TMaps& maps, KParams p, cudaStream_t s) {
 #endif
     const int smem = 1024 + bres + bytes() + kMiscBytes;
     auto kern = dense_kmajor_kernel<N, B_RES, MODE>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        XB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        attr_set = true;
-    }
+    XB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));   // per device, cheap: set on every launch
     const int64_t tiles = (p.M + BM - 1) / BM;
     const int n_src = MODE == MODE_FWD ? (p.dual ? 2 : 1) : (p.n_split > 1 ? p.n_split : 1);
     const int64_t want = tiles * n_src;
@@ -1067,11 +1063,7 @@ static int launch_kmajor_ts(const TMaps& maps, KParams p, cudaStream_t s) {
 #endif
     const int smem = 1024 + bres + bytes() + kMiscBytes;
     auto kern = dense_kmajor_ts_kernel<N, B_RES, MODE>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        XB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        attr_set = true;
-    }
+    XB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));   // per device, cheap: set on every launch
     const int64_t tiles = (p.M + BM - 1) / BM;
     const int n_src = MODE == MODE_FWD ? (p.dual ? 2 : 1) : (p.n_split > 1 ? p.n_split : 1);
     const int64_t want = tiles * n_src;
@@ -1534,11 +1526,7 @@ static int launch_wgrad(const CUtensorMap& my0, const CUtensorMap& my1, const CU
 #endif
     const int smem = 1024 + (S + L) * stage + kWMiscBytes;
     auto kern = dense_wgrad_kernel<HIN>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        XB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        attr_set = true;
-    }
+    XB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));   // per device, cheap: set on every launch
     kern<<<grid, kThreads, smem, s>>>(my0, my1, mx, p);
     XB_LAUNCH_CHECK();
     return 0;

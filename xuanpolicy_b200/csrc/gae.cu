@@ -362,11 +362,7 @@ extern "C" int xb_gae(const float* rew, const float* val, const float* term, con
         CUtensorMap m_rew, m_val, m_term;
         if (!make_map_f32(&m_rew, rew, T, N) || !make_map_f32(&m_val, val, T, N) || !make_map_f32(&m_term, term, T, N))
             return XB_E_DRIVER;
-        static bool attr_set = false;
-        if (!attr_set) {
-            XB_CUDA(cudaFuncSetAttribute(gae_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaeSmem)));
-            attr_set = true;
-        }
+        XB_CUDA(cudaFuncSetAttribute(gae_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GaeSmem)));   // per device, cheap: set on every launch
         int grid = ceil_div_i64(N, kTileN);
         gae_tma_kernel<<<grid, kTmaThreads, sizeof(GaeSmem), s>>>(m_rew, m_val, m_term, p);
     } else {

@@ -1,4 +1,5 @@
-"""Env-sharded data parallelism: one process per GPU, NCCL over NVLink.
+"""Env-sharded data parallelism: one process per GPU; exchanges over NVLink peer memory (PeerComm, csrc/peer_comm.cu),
+NCCL all-reduces as the fallback.
 
 The reference is single-process; its only collective is the (disabled) mpi4py Allreduce of [sums..., count]
 inside RunningMeanStd (xuance/common/statistic_tools.py:6-32).  The PPO path shards by environment:
@@ -12,7 +13,10 @@ inside RunningMeanStd (xuance/common/statistic_tools.py:6-32).  The PPO path sha
          sum is the gradient of the global-minibatch mean; clip + Adam then run identically on every rank.
   Nothing is exchanged during the rollout or the GAE scan.
 
-These helpers are backend-agnostic (NCCL on GPUs, gloo in the CPU tests).
+The default exchange path is `PeerComm` below (kernels of ours over CUDA-IPC-mapped peer memory, inside the epoch
+graph).  `allreduce_adv_stats` / `allreduce_flat_grad` / `broadcast_parameters` are the torch.distributed form of the
+same exchanges: the agent and learner call them on the NCCL fallback path (XB_PEER_COMM=0 or no IPC) and the CPU
+tests drive them over gloo.
 """
 import ctypes as C
 import os

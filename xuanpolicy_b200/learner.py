@@ -1,15 +1,17 @@
-"""PPOCLIP_Learner drop-in: the loss + its backward run in one hand-written kernel; the MLP stays in torch.
+"""PPOCLIP_Learner drop-in (and the A2C / PG / PPO-KL / PPG learners that share its machinery).
 
 Mirrors PPOCLIP_Learner (xuance/torch/learners/policy_gradient/ppoclip_learner.py:4-65) and its base Learner
 (xuance/torch/learners/learner.py:10-52): same constructor, `update(obs_batch, act_batch, ret_batch, value_batch,
 adv_batch, old_logp) -> info`, `save_model`, `load_model`, `iterations`.
 
-`update` (compat): forwards the policy with torch, calls the fused loss kernel on the network outputs
-(csrc/ppo_loss.cu) to get dL/dlogits|dmu, dL/dlogstd, dL/dv, back-propagates them through the torch MLP, then
-uses the caller's torch optimizer / scheduler exactly like the reference.
-`update_from_buffer` (native): minibatch gather fused into the loss kernel, gradients in one flat buffer,
-clip + Adam + LinearLR in one fused device step (csrc/optim.cu), optional NCCL all-reduces for env-sharded
-data parallelism, and no host synchronisation (info scalars stay on the device until asked for).
+`update` (compat — what an unmodified PPOCLIP_Agent calls): forwards the policy's torch modules, runs the loss
+forward + backward w.r.t. the network outputs in one hand-written kernel (csrc/ppo_loss.cu), back-propagates through
+the torch MLP and uses the caller's torch optimizer / scheduler exactly like the reference.
+`update_from_buffer` / `stage_*` (native — what our vectorised agent calls): minibatch gather fused with the first MLP
+layer, the hidden layers on the tcgen05 dense kernels with the loss in their epilogue (csrc/dense_tc.cu), hand-written
+dgrad / wgrad into one flat gradient buffer, clip + Adam + LinearLR on the device (csrc/optim.cu); env-sharded, the
+gradient exchange is a kernel over NVLink peer memory fused with the norm pass (csrc/peer_comm.cu; NCCL all-reduce as
+the fallback).  No host synchronisation: the info scalars stay on the device until `info()` is asked for them.
 """
 import os
 
@@ -17,6 +19,7 @@ import numpy as np
 import torch
 
 from . import ops
+from . import dist as xdist
 from .fused_mlp import FusedActorCritic
 from .policies import old_dist_params
 
@@ -87,11 +90,15 @@ class FlatAdamState:
             if g is None:
                 v.zero_()
 
-    def adam(self, grad, fused=None, grad_scale=1.0):
-        """Second pass of the step (scalars already in `workspace`).  With the tensor-core MLP active the same launch
-        rewrites the tf32 hi/lo operand copies of the two hidden-layer weights (`fused.splits_fresh` tells the next
-        forward that no separate split launch is needed)."""
-        if fused is not None and fused.la1.weight.data_ptr() >= self.flat_param.data_ptr():
+    def can_split(self, fused):
+        """True if `adam` can rewrite `fused`'s operand copies in the same launch (its weights live in the flat buffer)."""
+        return fused is not None and fused.la1.weight.data_ptr() >= self.flat_param.data_ptr()
+
+    def adam(self, grad, fused=None, grad_scale=1.0, split=True):
+        """Second pass of the step (scalars already in `workspace`).  With the tensor-core MLP active (`fused`) and `split`
+        the same launch rewrites the tf32 hi/lo operand copies of the two hidden-layer weights (`fused.splits_fresh`
+        tells the next forward that no separate split launch is needed); otherwise the copies are marked stale."""
+        if split and self.can_split(fused):
             ops.adam_apply_split(self.flat_param, grad, self.exp_avg, self.exp_avg_sq, self.beta1, self.beta2, self.eps,
                                  grad_scale, self.workspace, fused.la1.weight.data, fused.wa_hi, fused.wa_lo,
                                  fused.lc1.weight.data, fused.wc_hi, fused.wc_lo, fused.wt_hi, fused.wt_lo)
@@ -99,8 +106,10 @@ class FlatAdamState:
         else:
             ops.adam_apply(self.flat_param, grad, self.exp_avg, self.exp_avg_sq, self.beta1, self.beta2, self.eps,
                            grad_scale, self.workspace)
+            if fused is not None:
+                fused.splits_fresh = False
 
-    def apply_peer(self, peer, max_norm, grad_scale=1.0, fused=None):
+    def apply_peer(self, peer, max_norm, grad_scale=1.0, fused=None, split=True):
         """Env-sharded step: ONE kernel pushes this rank's gradient to every peer over NVLink, sums the W gradients in rank
         order and takes the norm of the sum (csrc/peer_comm.cu); the Adam kernel then consumes the sum."""
         if self.grad_sum is None:
@@ -108,7 +117,7 @@ class FlatAdamState:
         ops.peer_allreduce_grad_norm(peer, self.flat_grad, self.grad_sum, peer.tickets, self.step, self.lr0, self.end_factor,
                                      self.total_iters, self.beta1, self.beta2, self.eps, max_norm, grad_scale,
                                      self.workspace, lr_out=self.lr, gnorm_out=self.gnorm)
-        self.adam(self.grad_sum, fused, grad_scale)
+        self.adam(self.grad_sum, fused, grad_scale, split)
 
     def apply(self, max_norm, grad_scale=1.0):
         ops.clip_adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step, self.lr0,
@@ -338,16 +347,34 @@ class PPOCLIP_Learner:
         """Stage 3: global-norm clip + Adam + LinearLR on the flat buffers (one fused device step).  Env-sharded over peer
         memory, the gradient exchange happens INSIDE this stage (fused with the norm pass)."""
         max_norm = self.clip_grad_norm if self.use_grad_clip else 0.0
-        fused = self._fused if (self._fused is not None and os.environ.get("XB_ADAM_SPLIT", "1") != "0") else None
+        fused, split = self._fused, os.environ.get("XB_ADAM_SPLIT", "1") != "0"
         if self._peer is not None:
-            self._flat.apply_peer(self._peer, max_norm, 1.0, fused)
-        elif self._fused is not None and self._fused.norm_done:     # norm + step scalars came out of the backward tail launch
-            self._flat.adam(self._flat.flat_grad, fused, 1.0)
-            self._fused.norm_done = False
+            self._flat.apply_peer(self._peer, max_norm, 1.0, fused, split)
+        elif fused is not None and fused.norm_done:     # norm + step scalars came out of the backward tail launch
+            self._flat.adam(self._flat.flat_grad, fused, 1.0, split)
+            fused.norm_done = False
         else:
             self._flat.apply(max_norm, 1.0)
             if self._fused is not None:
                 self._fused.splits_fresh = False
+
+    def adam_resplits(self):
+        """True if every `stage_optimizer` of the current configuration rewrites the fused MLP's tf32 operand copies
+        (adam_apply_split): the peer-memory path and the single-rank tail-norm path, with XB_ADAM_SPLIT on.  False for
+        the NCCL fallback / XB_TAIL_NORM=0 (clip_adam_step) and XB_ADAM_SPLIT=0 — there the first minibatch of every
+        epoch must re-split (agent._epoch_start)."""
+        if self._fused is None or self._flat is None or os.environ.get("XB_ADAM_SPLIT", "1") == "0":
+            return False
+        if not self._flat.can_split(self._fused):
+            return False
+        if self._peer is not None:
+            return True
+        return self.world_size == 1 and os.environ.get("XB_TAIL_NORM", "1") != "0" and self._fused_tail_norm_possible()
+
+    def _fused_tail_norm_possible(self):
+        f = self._fused
+        return f is not None and (not f.gaussian or (getattr(f.policy.actor, "logstd", None) is not None
+                                                     and f.policy.actor.logstd.numel() == 1))
 
     def update_from_buffer(self, memory, idx):
         """One PPO-Clip SGD step on the minibatch `idx` (CUDA int64 flat indices) of a native buffer.
@@ -357,10 +384,10 @@ class PPOCLIP_Learner:
             self.enable_fused_optimizer()
         mb = self.stage_gather(memory, idx)
         if self.world_size > 1 and memory.use_advnorm:
-            torch.distributed.all_reduce(mb["stats"], group=self.process_group)
+            xdist.allreduce_adv_stats(mb["stats"], self.process_group)
         self.stage_forward_backward(memory, idx, mb)
         if self.world_size > 1 and self._peer is None:
-            torch.distributed.all_reduce(self._flat.flat_grad, group=self.process_group)
+            xdist.allreduce_flat_grad(self._flat.flat_grad, self.process_group)
         self.stage_optimizer()
 
     def info(self, batch_size):
