@@ -1,22 +1,33 @@
 #!/usr/bin/env python
 """bench.py — PPO env-steps/s on B200 (BASELINE.json metric), with roofline, CPU baseline and clocks.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload auto|c1|c2|c3|c5]
 
-A "step" is one PPO iteration of the hot path: a rollout of `horizon` vector steps over the env batch, the
-batched GAE, and n_epoch x n_minibatch fused updates.  Default workload = BASELINE.json configs[1]
-("PPO-Clip Pendulum-v1 Gaussian policy, 4096 envs, horizon 128, on 1 B200"); with N GPUs every rank owns its own
-4096 envs (weak scaling, env-sharded data parallel; the only collectives are the advantage statistics and the
-flat gradient).  For N > 1 launch with torchrun (RANK/LOCAL_RANK/WORLD_SIZE from the env).
+A "step" is one PPO iteration of the hot path: a rollout of `horizon` vector steps over the env batch, the batched GAE,
+and n_epoch x n_minibatch fused updates.  Observation / reward normalisation is ON (the reference yaml default,
+xuance/configs/ppo/classic_control/*.yaml:34-35); the same measurement with it off rides along as `norm_off`.
+
+Workloads (BASELINE.json configs; `--workload auto`, the default, picks by N):
+  N = 1   headline = C2  "PPO-Clip Pendulum-v1 Gaussian policy, 4096 envs, horizon 128, on 1 B200";
+          extra keys: `c3` (configs[2] on one GPU: the base of the strong-scaling series), `c1` (configs[0]: ours and the
+          reference's CPU path on the full config), `e2e_compat`, `c4_gae`
+  N > 1   headline = C3  "PPO-Clip CartPole-v1, 65536 envs, env-sharded across 2/4/8 B200" (STRONG scaling: 65536/N envs
+          per rank); extra keys: `weak_c2` (C2 with 4096 envs on every rank), `c5` (configs[4], N = 8 only), `c4_gae`
+          (configs[3] sharded over the ranks), `rank_parity` (replicas bit-identical; peer-memory gradient sum == NCCL sum)
+For N > 1 launch with torchrun (RANK/LOCAL_RANK/WORLD_SIZE from the env).
 
 Printed keys (one JSON line, rank 0):
   value  env-steps/s with everything device-resident (index permutations drawn on the GPU)
   e2e    the same loop through the public API `PPOCLIP_Agent.train` with HOST-drawn minibatch permutations copied
          H2D from pinned memory every epoch and the log scalars read back D2H every iteration
+  e2e_compat    the three drop-ins in COMPAT mode (numpy in / numpy out, list-of-dict infos: what an unmodified reference
+                agent calls) driven by the reference's agent loop as restated in oracle/ref_port.PPOAgentPort
   roofline      the kernel of ours with the largest share of the step, timed alone with CUDA events
   kernels       the same measurement for every hand-written kernel on the path + the GAE micro-benchmark shape
-  cpu_baseline  the reference's algorithm (oracle/ref_port.py: per-env Python loops + torch CPU) on a bounded sample
-`--impl reference` times that CPU path alone (the reference itself is Python and does not travel to the GPU box).
+  cpu_baseline  the reference's CPU path on a FIXED sample of the workload (same policy as `--impl reference`)
+`--impl reference` times the reference's own CPU implementation: the unmodified `PPOCLIP_Agent.train` of the copy
+pip-installed into oracle/_ref (oracle/build_ref.py; kind "reference"), else its restatement oracle/ref_port.py (kind
+"port"), on a fixed 1024-env sample of the same config with a fixed thread policy.
 """
 import argparse
 import json
@@ -107,18 +118,39 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- our arm
-def build_agent(wl, world, shuffle, sync_info, pg=None):
+def build_agent(wl, world, shuffle, sync_info, norm=True, pg=None):
     from xuanpolicy_b200.configs import build_ppo
     n_local = wl["envs"] // world if wl.get("strong") else wl["envs"]
-    n_mb = 8
-    if wl.get("minibatch"):
-        n_mb = max(1, (wl["envs"] * wl["horizon"]) // wl["minibatch"])
     h = [wl["hidden"]]
+    # every rank gets the SAME config seed: the agent folds the rank into its sampling / permutation keys itself
     return build_ppo(wl["env_id"], device="cuda", process_group=pg, parallels=n_local, n_steps=wl["horizon"],
-                     gamma=wl["gamma"], gae_lambda=0.95, n_epoch=8, n_minibatch=n_mb, representation_hidden_size=h,
-                     actor_hidden_size=h, critic_hidden_size=h, shuffle=shuffle, sync_info=sync_info,
-                     seed=1 + 1000 * (torch.distributed.get_rank() if world > 1 else 0), policy_seed=1,
-                     running_steps=10 ** 9)
+                     gamma=wl["gamma"], gae_lambda=0.95, n_epoch=8, n_minibatch=n_minibatches(wl), representation_hidden_size=h,
+                     actor_hidden_size=h, critic_hidden_size=h, shuffle=shuffle, sync_info=sync_info, seed=1, policy_seed=1,
+                     use_obsnorm=norm, use_rewnorm=norm, running_steps=10 ** 9)
+
+
+def n_minibatches(wl):
+    if wl.get("minibatch"):
+        return max(1, (wl["envs"] * wl["horizon"]) // wl["minibatch"])
+    return 8
+
+
+def mlp_params(wl):
+    """Parameter count of the reference's actor-critic for this workload (Basic_MLP + ActorNet + CriticNet; + log-std)."""
+    obs, act, gauss = {"CartPole-v1": (4, 2, False), "Pendulum-v1": (3, 1, True)}[wl["env_id"]]
+    h = wl["hidden"]
+    return (obs * h + h) + 2 * (h * h + h) + (h * act + act) + (h + 1) + (act if gauss else 0)
+
+
+def config_of(wl, world):
+    """The `config` object of the JSON line: a pure function of (workload, N) so that both arms print the same one."""
+    n_local = wl["envs"] // world if wl.get("strong") else wl["envs"]
+    mb = n_minibatches(wl)
+    return {"workload": wl["name"], "envs_total": n_local * world, "envs_per_gpu": n_local, "horizon": wl["horizon"], "n_epoch": 8,
+            "n_minibatch": mb, "minibatch_per_gpu": n_local * wl["horizon"] // mb, "mlp_hidden": wl["hidden"],
+            "params": mlp_params(wl), "gamma": wl["gamma"], "gae_lambda": 0.95, "use_obsnorm": True, "use_rewnorm": True,
+            "parallelism": "env-sharded dp%d" % world,
+            "l2_flush": "256 MiB buffer written between timed steps (outside the event pairs)", "allow_tf32": False}
 
 
 def time_agent(agent, steps, warmup, flush, world):
@@ -172,7 +204,7 @@ def time_phases(agent, flush):
 
 def count_launches(agent):
     """Hand-written kernel launches inside one PPO iteration (counted from the calls the agent makes)."""
-    T, E, M = agent.n_steps, agent.n_epoch, agent.buffer_size // agent.batch_size
+    T, E, M = agent.n_steps, agent.n_epoch, agent.n_updates_per_epoch
     if agent.learner._fused is not None:
         # rollout: weight split (1); per step the one-launch forward + the fused sample/env/store step; bootstrap forward (1);
         # GAE + record packing (2); counter (1)
@@ -189,6 +221,12 @@ def count_launches(agent):
         per_rollout = T * (3 + 5) + 5 + 2 + 1  # per step: sample, env_step, store, 3 bias+act, 2 head; bootstrap fwd; GAE + pack; counter
         per_update = 1 + 1 + 2 + 5 + 3         # gather, loss, grad-norm + adam, fwd: 3 bias+act + 2 head, bwd: 2 head+act + 1 act+bias
     per_epoch = 2 if agent.shuffle != "host" else 0     # device permutation + its counter tick
+    if agent.use_obsnorm:                               # per step: moments + normalise; + the bootstrap normalise; state copy
+        per_rollout += 2 * T + 2
+    if agent.use_rewnorm:                               # per step: return tracker + scalar merge
+        per_rollout += 2 * T
+    if agent._norm_peer is not None:                    # env-sharded: one statistics exchange per step
+        per_rollout += T
     return per_rollout + E * (M * per_update + per_epoch)
 
 
@@ -263,6 +301,15 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
                 env_bytes + N * ((4 + 4 + 4) if gauss else (8 + 8 + 4)) + N * 36, T)
         agent._restore(snap)
         agent._cur = cur
+    if agent.use_obsnorm:
+        add("obs_moments", lambda: ops.moments4(x_cur[:N], agent._obs_sums, agent._obs_ws), N * 16, T)
+        add("obs_normalize", lambda: ops.rms_normalize(x_cur, od, agent._obs_sums, agent._obs_rms[0], agent._obs_rms[1],
+                                                       agent.obsnorm_range, agent._xn, 0), 2 * N * 32, T + 1)
+    if agent.use_rewnorm:
+        snap_r = agent._snapshot()
+        add("returns_track", lambda: ops.returns_track(agent._returns, env._rew, env._term, env._trunc, agent.gamma,
+                                                       agent._ret_sums, agent._ret_ws), N * (8 + 8 + 4 + 2), T)
+        agent._restore(snap_r)
     add("gae_and_pack", lambda: mem.finish_rollout(agent._boot_last), (20 + 1 + (64 if mem._rec is not None else 0)) * N * T, 1)
     idx = agent._perm[:B]
     agent._device_permutation()
@@ -284,6 +331,9 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
     dv = torch.empty_like(vp)
     kw = dict(clip_range=lr.clip_range, vf_coef=lr.vf_coef, ent_coef=lr.ent_coef, inv_batch=1.0 / B, adv_stats=mb["stats"],
               adv_count=B)
+    # with the loss riding in dense_fwd2's epilogue the stand-alone loss kernel is not launched in the step at all
+    # (launches_per_step 0: listed for its own roofline only, never counted into the step)
+    loss_launches = 0 if (fused is not None and lr._fused_loss_ok(mem, fused)) else launches_per_step["updates"]
     if mem.packed:
         kw.update(packed=mb["scal"])
         margs = (None, None, None, None)
@@ -297,12 +347,12 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
         dmu = torch.empty_like(mu)
         dls = torch.empty(mu.shape[1], dtype=torch.float64, device="cuda")
         add("ppo_loss_fwd_bwd", lambda: ops.ppo_loss_gaussian(mu, logstd, vp, *margs, dmu, dls, dv, lr._scalars, **kw),
-            B * (32 if mem.packed else 40), launches_per_step["updates"])
+            B * (32 if mem.packed else 40), loss_launches)
     else:
         logits = a_dist.get_param().contiguous()
         dl = torch.empty_like(logits)
         add("ppo_loss_fwd_bwd", lambda: ops.ppo_loss_categorical(logits, vp, *margs, dl, dv, lr._scalars, **kw),
-            B * (40 if mem.packed else 48), launches_per_step["updates"])
+            B * (40 if mem.packed else 48), loss_launches)
     H = agent.config.representation_hidden_size[-1]
     upd = launches_per_step["updates"]
     A_out = 1 if gauss else 2
@@ -357,19 +407,37 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
     agent._restore(snap)
     if with_c4:
         out.update(large_shape_rooflines(flush, peak))
-        # BASELINE.json configs[3]: GAE micro-benchmark, T=2048 x N=2^20 fp32 (sharded over ranks), both variants
-        Tc, Nc = 2048, (1 << 20) // world
-        gen = torch.Generator(device="cuda").manual_seed(1234 + (torch.distributed.get_rank() if world > 1 else 0))
-        rew = torch.randn((Tc, Nc), device="cuda", generator=gen)
-        val = torch.randn((Tc, Nc), device="cuda", generator=gen)
-        term = (torch.rand((Tc, Nc), device="cuda", generator=gen) < 1 / 200).float()
-        boot = torch.randn(Nc, device="cuda", generator=gen)
-        adv, ret = torch.empty_like(rew), torch.empty_like(rew)
-        for variant in ("ldg", "tma"):
-            add("gae_c4_" + variant, lambda: ops.gae(rew, val, term, boot, adv, ret, 0.99, 0.95, variant=variant),
-                20 * Tc * Nc, 0)
-        del rew, val, term, adv, ret
-        torch.cuda.empty_cache()
+    return out
+
+
+def c4_gae(flush, peak, world):
+    """BASELINE.json configs[3]: GAE/return micro-benchmark, T = 2048 x N = 2^20 envs fp32 synthetic rewards / values /
+    dones, the envs sharded over the ranks (no exchange: GAE is independent per env).  Both kernel variants; time = max
+    over ranks of the mean CUDA-event time; GB/s = 20 B/element x ALL ranks' elements / that time."""
+    from xuanpolicy_b200 import ops
+    Tc, Nc = 2048, (1 << 20) // world
+    rank = torch.distributed.get_rank() if world > 1 else 0
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    rew = torch.randn((Tc, Nc), device="cuda", generator=gen)
+    val = torch.randn((Tc, Nc), device="cuda", generator=gen)
+    term = (torch.rand((Tc, Nc), device="cuda", generator=gen) < 1 / 200).float()
+    boot = torch.randn(Nc, device="cuda", generator=gen)
+    adv, ret = torch.empty_like(rew), torch.empty_like(rew)
+    out = {"T": Tc, "N_total": Nc * world, "N_per_gpu": Nc, "bytes_per_element": 20}
+    for variant in ("ldg", "tma"):
+        if world > 1:
+            torch.distributed.barrier()
+        mean_ms, min_ms = time_kernel(lambda: ops.gae(rew, val, term, boot, adv, ret, 0.99, 0.95, variant=variant), flush, iters=10)
+        t = torch.tensor([mean_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+        gbs = 20.0 * Tc * Nc * world / (ms * 1e-3) / 1e9
+        out[variant] = {"ms": round(ms, 4), "min_ms_rank0": round(min_ms, 4), "achieved_gbs_all_gpus": round(gbs, 1),
+                        "frac_of_hbm_peak_per_gpu": round(gbs / world / peak, 4),
+                        "elements_per_s": round(Tc * Nc * world / (ms * 1e-3), 1)}
+    del rew, val, term, adv, ret
+    torch.cuda.empty_cache()
     return out
 
 
@@ -422,6 +490,107 @@ def large_shape_rooflines(flush, peak):
     return out
 
 
+def measure(wl, world, steps, warmup, flush, shuffle, sync_info, norm=True):
+    """Builds the agent for `wl`, times `steps` PPO iterations.  Returns (agent, env-steps/s over all ranks, ms per step)."""
+    agent = build_agent(wl, world, shuffle, sync_info, norm=norm)
+    secs = time_agent(agent, steps, warmup, flush, world)
+    return agent, agent.n_envs * agent.n_steps * steps * world / secs, secs / steps * 1e3
+
+
+def value_and_e2e(wl, world, steps, warmup, flush, norm=True, with_e2e=True):
+    """{"value", "ms_per_step", "e2e": {...}} for a secondary workload (no kernel table)."""
+    agent, value, ms = measure(wl, world, steps, warmup, flush, "device", False, norm)
+    out = {"workload": wl["name"], "scaling": "strong" if wl.get("strong") else "weak", "value": round(value, 1),
+           "unit": "env-steps/s", "ms_per_step": round(ms, 4), "steps": steps, "warmup": warmup,
+           "envs_per_gpu": agent.n_envs, "minibatch_per_gpu": agent.batch_size, "use_obsnorm": norm, "use_rewnorm": norm,
+           "gpu_launches_per_step": count_launches(agent)}
+    del agent
+    torch.cuda.empty_cache()
+    if with_e2e:
+        agent, e2e, ms = measure(wl, world, steps, warmup, flush, "host", True, norm)
+        iters = steps + warmup
+        out["e2e"] = {"value": round(e2e, 1), "unit": "env-steps/s", "ms_per_step": round(ms, 4),
+                      "h2d_bytes_per_step": int(agent.h2d_bytes // iters), "d2h_bytes_per_step": int(agent.d2h_bytes // iters)}
+        del agent
+        torch.cuda.empty_cache()
+    return out
+
+
+def rank_parity(agent, world):
+    """Self-check carried in the multi-GPU line: (1) the replicated parameters are bit-identical on every rank after the
+    timed iterations; (2) the fused peer-memory gradient exchange (csrc/peer_comm.cu) gives every rank the same bits, equal
+    to NCCL's all-reduce of the same data within fp32 summation-order rounding, and the norm of the sum."""
+    d = torch.distributed
+    fl, peer = agent.learner._flat, agent.learner._peer
+    mine = fl.flat_param.clone()
+    allp = [torch.empty_like(mine) for _ in range(world)]
+    d.all_gather(allp, mine)
+    out = {"params_bit_identical_across_ranks": bool(all(torch.equal(allp[0], x) for x in allp)),
+           "exchange": "peer-memory kernels" if peer is not None else "nccl all-reduce"}
+    if peer is not None:
+        snap = agent._snapshot()
+        gen = torch.Generator(device="cuda").manual_seed(100 + d.get_rank())
+        fl.flat_grad.copy_(torch.randn(fl.n, device="cuda", generator=gen))
+        ref = fl.flat_grad.clone()
+        d.all_reduce(ref)
+        fl.apply_peer(peer, 0.5, 1.0)
+        torch.cuda.synchronize()
+        sums = [torch.empty_like(fl.grad_sum) for _ in range(world)]
+        d.all_gather(sums, fl.grad_sum)
+        n_ref = float(ref.double().norm().item())
+        out.update({"peer_sum_bit_identical_across_ranks": bool(all(torch.equal(sums[0], x) for x in sums)),
+                    "peer_sum_vs_nccl_max_abs_err": float((fl.grad_sum - ref).abs().max().item()),
+                    "peer_sum_equals_nccl_sum": bool(torch.allclose(fl.grad_sum, ref, rtol=1e-6, atol=1e-6)),
+                    "norm_of_sum_rel_err": abs(float(fl.gnorm.item()) - n_ref) / n_ref})
+        agent._restore(snap)
+    return out
+
+
+def time_compat(wl, sample_envs, iters=2):
+    """`e2e_compat`: the drop-ins in compat mode — numpy in / numpy out, list-of-dict infos, per-env finish_path calls,
+    host-side normalisation — i.e. the calls an UNMODIFIED reference PPOCLIP_Agent makes, driven by
+    that agent's loop as restated in oracle/ref_port.PPOAgentPort.  Host<->device copies on every call are inside the
+    timed region.  The per-env Python loops of the reference's agent bound it, not the kernels."""
+    import xuanpolicy_b200 as xb
+    from oracle import ref_port
+    n, T = sample_envs, wl["horizon"]
+    torch.manual_seed(1)
+    np.random.seed(1)
+    envs = xb.DummyVecEnv_Gym(xb.make_env_fns(wl["env_id"], 1, n), device="cuda")
+    envs.reset()
+    policy = xb.make_policy(envs.observation_space, envs.action_space, hidden=(wl["hidden"],), device="cuda")
+    opt = torch.optim.Adam(policy.parameters(), 4e-4, eps=1e-5)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=10 ** 9)
+    memory = xb.DummyOnPolicyBuffer(envs.observation_space, envs.action_space, {"old_logp": ()}, n, T, True, True, wl["gamma"], 0.95)
+    learner = xb.PPOCLIP_Learner(policy, opt, sched, "cuda", "/tmp", vf_coef=0.25, ent_coef=0.01, clip_range=0.2,
+                                 clip_grad_norm=0.5, use_grad_clip=True)
+    agent = ref_port.PPOAgentPort(envs, policy, opt, sched, T, 8, n_minibatches(wl), wl["gamma"], 0.95, use_obsnorm=True,
+                                  use_rewnorm=True, memory=memory, update_fn=learner.update)
+    agent.train(T)                                   # warm-up iteration
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    agent.train(T * iters)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": round(n * T * iters / dt, 1), "unit": "env-steps/s", "ms_per_step": round(dt / iters * 1e3, 2),
+            "sample": "%d of %d envs x full horizon %d, %d timed PPO iterations after 1 warm-up (wall clock incl. every "
+                      "H2D/D2H copy); compat drop-ins (DummyVecEnv_Gym.step / DummyOnPolicyBuffer.store, finish_path, "
+                      "sample / PPOCLIP_Learner.update) under the reference agent's per-env Python loop" % (n, wl["envs"], T, iters)}
+
+
+def c1_line(flush):
+    """BASELINE.json configs[0] (CartPole-v1, MLP 64x64, 16 envs, horizon 256): ours (device-resident agent; the policy is
+    below the tensor-core path's width and batch, so the MLP runs in torch) next to the reference's CPU path on the FULL
+    config (the one config the reference runs as is)."""
+    wl = WORKLOADS["c1"]
+    agent, value, ms = measure(wl, 1, 5, 3, flush, "device", False, True)
+    del agent
+    torch.cuda.empty_cache()
+    ref = time_reference_cpu(wl, wl["envs"], threads=1, warmup=1, steps=3)
+    return {"workload": wl["name"], "ours": {"value": round(value, 1), "unit": "env-steps/s", "ms_per_step": round(ms, 3)},
+            "reference_cpu": ref}
+
+
 def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -430,64 +599,80 @@ def run_ours(args):
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
-    wl = WORKLOADS[args.workload]
+    key = args.workload if args.workload != "auto" else ("c2" if world == 1 else "c3")
+    wl = WORKLOADS[key]
     # strict fp32 GEMMs by default (the parity tolerances are stated for fp32); --tf32 lets cuBLAS use the TF32 tensor
-    # cores for the large-minibatch MLP GEMMs (north_star: "tensor cores only at the large-batch configs")
+    # cores where the torch MLP path runs (not the headline: the large-batch MLP runs on our 3xTF32 tcgen05 kernels)
     torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
     peak, peak_src = measured_peaks()
     flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")   # 256 MiB > 126 MB L2
     sampler = ClockSampler(local) if rank == 0 else None
+    extra = not args.headline_only
 
     # value: device-resident (permutations drawn on the GPU, one host sync at the end of train())
-    agent = build_agent(wl, world, "device", False)
-    secs = time_agent(agent, args.steps, args.warmup, flush, world)
-    env_steps = agent.n_envs * agent.n_steps * args.steps * world
-    value = env_steps / secs
+    agent, value, ms_step = measure(wl, world, args.steps, args.warmup, flush, "device", False, True)
     launches = count_launches(agent)
     phases = time_phases(agent, flush) if world == 1 else None
-    launches_per_step = {"updates": agent.n_epoch * (agent.buffer_size // agent.batch_size)}
-    kernels = kernel_rooflines(agent, flush, peak, launches_per_step, with_c4=not args.no_c4, world=world) if rank == 0 or world > 1 else {}
-    params = agent.learner._flat.n_params
+    launches_per_step = {"updates": agent.n_epoch * agent.n_updates_per_epoch}
+    # (all ranks when env-sharded: the optimiser stage contains the cross-GPU exchange kernel, which waits for every peer)
+    kernels = kernel_rooflines(agent, flush, peak, launches_per_step, with_c4=(extra and world == 1), world=world) if (rank == 0 or world > 1) else {}
+    parity = rank_parity(agent, world) if world > 1 else None
     fused_on = agent.learner._fused is not None and agent.batch_size >= agent.learner._fused.MIN_ROWS
     del agent
     torch.cuda.empty_cache()
 
     # e2e: public API with host-drawn permutations (H2D from pinned memory each epoch) and D2H of the log each iteration
-    agent = build_agent(wl, world, "host", True)
-    secs_e2e = time_agent(agent, args.steps, args.warmup, flush, world)
+    agent, e2e, ms_e2e = measure(wl, world, args.steps, args.warmup, flush, "host", True, True)
     iters = args.steps + args.warmup
     h2d, d2h = agent.h2d_bytes // iters, agent.d2h_bytes // iters
-    e2e = env_steps / secs_e2e
     info = agent.last_info
-    n_local, horizon, mb = agent.n_envs, agent.n_steps, agent.batch_size
     del agent
+    torch.cuda.empty_cache()
     clocks = sampler.stop() if sampler else None
 
+    side = {}
+    if extra:
+        short = dict(steps=min(args.steps, 5), warmup=3)
+        side["norm_off"] = value_and_e2e(wl, world, flush=flush, norm=False, **short)
+        side["norm_off"]["what"] = "the headline workload with use_obsnorm = use_rewnorm = False (round-1 setting)"
+        if world == 1:
+            if key != "c3":
+                side["c3"] = value_and_e2e(WORKLOADS["c3"], 1, flush=flush, with_e2e=False, steps=3, warmup=3)
+                side["c3"]["what"] = "BASELINE configs[2] on ONE GPU: the N = 1 point of the strong-scaling series bench.py --gpus 2/4/8 prints"
+        else:
+            if key != "c2":
+                side["weak_c2"] = value_and_e2e(WORKLOADS["c2"], world, flush=flush, **short)
+                side["weak_c2"]["what"] = "BASELINE configs[1] with 4096 envs on EVERY rank (weak scaling, round-1 headline)"
+            if world == 8 and key != "c5":
+                side["c5"] = value_and_e2e(WORKLOADS["c5"], world, flush=flush, with_e2e=False, steps=3, warmup=3)
+                side["c5"]["what"] = "BASELINE configs[4]: Pendulum-v1, MLP 256x256, 262144 envs, minibatch 65536, at 8 B200"
+        if not args.no_c4:
+            side["c4_gae"] = c4_gae(flush, peak, world)
     if rank != 0:
         return
+    if extra and world == 1:
+        side["e2e_compat"] = time_compat(wl, sample_envs=min(1024, wl["envs"]))
+        side["c1"] = c1_line(flush)
     step_share = {k: v["ms"] * v["launches_per_step"] for k, v in kernels.items() if v["launches_per_step"]}
     dom = max(step_share, key=step_share.get)
     kd = kernels[dom]
     traffic = None
     tpath = os.path.join(REPO, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath) and args.workload == "c2":      # ncu DRAM bytes per launch of the same kernel at this shape
+    if os.path.exists(tpath) and key == "c2":      # ncu DRAM bytes per launch of the same kernel at this shape
         traffic = json.load(open(tpath)).get(dom)
-    cpu = None if args.no_cpu_baseline else cpu_baseline(wl, budget_s=args.cpu_budget if args.cpu_budget else 25.0)
+    cpu = None if args.no_cpu_baseline else cpu_baseline(wl)
+    cfg = config_of(wl, world)
     line = {
         "metric": "PPO env-steps/s", "value": round(value, 1), "unit": "env-steps/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(secs / args.steps * 1e3, 4),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
         "higher_is_better": True, "scaling": "strong" if wl.get("strong") else "weak", "vs_baseline": None,
         "dtype": "tf32" if (args.tf32 and not fused_on) else "f32",
         "dtype_detail": ("f32-accurate MLP GEMMs (3xTF32 split on the tcgen05 tensor cores, fp32 accumulate)" if fused_on else
-                         ("tf32 MLP GEMMs" if args.tf32 else "f32 MLP GEMMs (cuBLAS SIMT)")) + ", f32 loss/optimizer, f64 GAE carry and env physics",
+                         ("tf32 MLP GEMMs" if args.tf32 else "f32 MLP GEMMs (cuBLAS SIMT)")) + ", f32 loss/optimizer, f64 GAE carry, env physics and running statistics",
         "data": "synthetic",
-        "config": {"workload": wl["name"], "envs_per_gpu": n_local, "horizon": horizon, "n_epoch": 8,
-                   "minibatch_per_gpu": mb, "mlp_hidden": wl["hidden"], "params": params, "gamma": wl["gamma"],
-                   "gae_lambda": 0.95, "use_obsnorm": False, "use_rewnorm": False, "parallelism": "env-sharded dp%d" % world,
-                   "l2_flush": "256 MiB buffer written between timed steps (outside the event pairs)",
-                   "allow_tf32": bool(torch.backends.cuda.matmul.allow_tf32)},
+        "config": cfg,
         "e2e": {"value": round(e2e, 1), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": round(secs_e2e / args.steps * 1e3, 4),
+                "ms_per_step": round(ms_e2e, 4),
                 "what": "PPOCLIP_Agent.train with host-drawn minibatch permutations (pinned H2D per epoch) and log scalars read back"},
         "gpu_launches": launches * args.steps,
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": kd["achieved_gbs"], "peak": peak, "unit": "GB/s",
@@ -495,21 +680,53 @@ def run_ours(args):
                      "tensor": {k: kd[k] for k in ("gemm_tflops", "tensor_pipe_tflops_tf32", "tensor_frac_of_tf32_peak") if k in kd},
                      "note": "kernel with the largest share of the step (CUDA-event time x launches per step); achieved = "
                              "algorithmic bytes / time.  Dense kernels: HBM time and 3xTF32 tensor-pipe time are about equal "
-                             "at this shape, both fractions are given.  See kernels.gae_c4_* for the pure HBM-bound shape"},
+                             "at this shape, both fractions are given.  See c4_gae for the pure HBM-bound shape"},
         "kernels": kernels,
         "phases": phases,
         "cpu_baseline": cpu,
         "clocks": clocks,
         "last_info": {k: (float(v) if not isinstance(v, (int, float)) else v) for k, v in info.items()},
     }
+    if parity is not None:
+        line["rank_parity"] = parity
+    line.update(side)
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------- CPU arms
-def _port_agent(wl, n_envs, threads):
+REF_SAMPLE_ENVS = 1024        # fixed sample of the env batch for the CPU arms (the reference's cost is linear in it)
+
+
+def cpu_threads(sample_envs):
+    """Fixed thread policy: tiny batches (C1) run fastest single-threaded (2674 vs 970 env-steps/s at
+    1 vs 8 threads), the 1024-env samples with every core (the minibatch GEMMs dominate)."""
+    return 1 if sample_envs < 256 else min(os.cpu_count() or 1, 32)
+
+
+def reference_kind():
+    """"reference": the unmodified reference is importable (pip-installed copy in oracle/_ref, or the source tree in the
+    build container); "port": only its restatement oracle/ref_port.py is."""
+    from oracle import ref_loader
+    return "reference" if ref_loader.available() else "port"
+
+
+def _cpu_agent(wl, n_envs, threads):
+    """(agent, kind): the LIVE reference PPOCLIP_Agent built by the reference's own get_runner on the restated libm physics
+    (what gym executes on a host), or the port with the same hyper-parameters."""
+    torch.set_num_threads(threads)
+    h = [wl["hidden"]]
+    if reference_kind() == "reference":
+        from oracle import ref_agent
+        runner = ref_agent.build_runner(wl["env_id"], trig="libm", parallels=n_envs, n_steps=wl["horizon"], seed=1, n_epoch=8,
+                                        n_minibatch=n_minibatches(wl), gamma=wl["gamma"], gae_lambda=0.95, use_obsnorm=True,
+                                        use_rewnorm=True, representation_hidden_size=h, actor_hidden_size=h, critic_hidden_size=h)
+        import xuance.torch.agents.policy_gradient.ppoclip_agent as mod
+        mod.tqdm = lambda x: x                         # no progress bar in the timed loop (module global, not a code edit)
+        runner.agent.writer.add_scalar = lambda *a, **k: None      # tensorboard file I/O out of the timed loop
+        runner.agent.writer.add_scalars = lambda *a, **k: None
+        return runner.agent, "reference"
     from oracle import ref_port
     from xuanpolicy_b200 import policies
-    torch.set_num_threads(threads)
     torch.manual_seed(1)
     np.random.seed(1)
     envs = ref_port.VecEnvPort(wl["env_id"], n_envs, seed=1, trig="libm")
@@ -517,68 +734,57 @@ def _port_agent(wl, n_envs, threads):
     pol = policies.make_policy(envs.observation_space, envs.action_space, hidden=(wl["hidden"],), device="cpu")
     opt = torch.optim.Adam(pol.parameters(), 4e-4, eps=1e-5)
     sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.0, total_iters=10 ** 9)
-    return ref_port.PPOAgentPort(envs, pol, opt, sched, wl["horizon"], 8, 8, wl["gamma"], 0.95)
+    return ref_port.PPOAgentPort(envs, pol, opt, sched, wl["horizon"], 8, n_minibatches(wl), wl["gamma"], 0.95,
+                                 use_obsnorm=True, use_rewnorm=True), "port"
 
 
-def _time_port(wl, n_envs, threads, iters):
-    agent = _port_agent(wl, n_envs, threads)
-    t0 = time.perf_counter()
-    agent.train(wl["horizon"] * iters)
-    dt = time.perf_counter() - t0
-    return n_envs * wl["horizon"] * iters / dt, dt
+def time_reference_cpu(wl, sample_envs, threads, warmup, steps):
+    agent, kind = _cpu_agent(wl, sample_envs, threads)
+    T = wl["horizon"]
+    if warmup:
+        agent.train(T * warmup)
+    per = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        agent.train(T)
+        per.append(time.perf_counter() - t0)
+    dt = float(sum(per))
+    what = ("unmodified xuance PPOCLIP_Agent.train (oracle/_ref) over DummyVecEnv_Gym / DummyOnPolicyBuffer / PPOCLIP_Learner, "
+            "torch CPU, restated gym 0.26.2 physics (libm)" if kind == "reference" else
+            "oracle/ref_port.py = the reference's per-env Python loops + torch-CPU learner over libm physics")
+    return {"value": round(sample_envs * T * steps / dt, 1), "unit": "env-steps/s", "cores": threads, "kind": kind,
+            "host_cores_available": os.cpu_count() or 1,
+            "ms_per_step_min_max": [round(min(per) * 1e3, 1), round(max(per) * 1e3, 1)],
+            "sample": "%d of %d envs x full horizon %d per step, %d timed PPO iterations (8 epochs x %d minibatches) after %d "
+                      "warm-up, use_obsnorm/use_rewnorm on; %s" % (sample_envs, wl["envs"], T, steps, n_minibatches(wl), warmup, what)}
 
 
-def _sample_envs(wl, budget_s, iters):
-    """Env count for which `iters` iterations of the reference algorithm take about budget_s on this host."""
-    probe_n = min(32, wl["envs"])
-    rate, _ = _time_port(wl, probe_n, 1, 1)
-    n = int(rate * budget_s / (wl["horizon"] * iters))
-    return max(8, min(wl["envs"], (n // 8) * 8))
-
-
-def cpu_baseline(wl, budget_s):
-    cores = os.cpu_count() or 1
-    n = _sample_envs(wl, budget_s / 2, 1)
-    best = None
-    for threads in sorted({1, cores}):
-        rate, dt = _time_port(wl, n, threads, 1)
-        if best is None or rate > best[0]:
-            best = (rate, threads, dt)
-    return {"value": round(best[0], 1), "unit": "env-steps/s", "cores": best[1], "kind": "port",
-            "host_cores_available": cores,
-            "sample": "%d of %d envs x full horizon %d, 1 PPO iteration (8 epochs x 8 minibatches), %.1f s; "
-                      "oracle/ref_port.py = the reference's per-env Python loops + torch-CPU learner over libm physics"
-                      % (n, wl["envs"], wl["horizon"], best[2])}
+def cpu_baseline(wl):
+    n = min(REF_SAMPLE_ENVS, wl["envs"])
+    return time_reference_cpu(wl, n, cpu_threads(n), warmup=1, steps=3)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
-    total_iters = args.steps + args.warmup
-    n = _sample_envs(wl, args.cpu_budget if args.cpu_budget else 150.0, total_iters)
-    # small MLPs run faster single-threaded, large minibatches with all cores: pick by a one-iteration trial
-    trial = {th: _time_port(wl, min(n, 64), th, 1)[0] for th in sorted({1, cores})}
-    threads = max(trial, key=trial.get)
-    agent = _port_agent(wl, n, threads)
-    agent.train(wl["horizon"] * args.warmup)
-    t0 = time.perf_counter()
-    agent.train(wl["horizon"] * args.steps)
-    dt = time.perf_counter() - t0
-    value = n * wl["horizon"] * args.steps / dt
-    sample = ("%d of %d envs x full horizon %d per step, %d timed PPO iterations; reference algorithm restated in "
-              "oracle/ref_port.py (the reference is Python at /root/reference and does not travel to the GPU box)"
-              % (n, wl["envs"], wl["horizon"], args.steps))
+    world = args.gpus
+    key = args.workload if args.workload != "auto" else ("c2" if world == 1 else "c3")
+    wl = WORKLOADS[key]
+    n = min(REF_SAMPLE_ENVS, wl["envs"])
+    threads = cpu_threads(n)
+    steps = max(3, args.steps)
+    # bound the run: ~2-7 s per step on 16-32 host cores; more than 12 timed steps add nothing but minutes
+    steps = min(steps, 12)
+    res = time_reference_cpu(wl, n, threads, warmup=max(1, min(args.warmup, 2)), steps=steps)
     print(json.dumps({
-        "impl": "reference", "metric": "PPO env-steps/s", "value": round(value, 1), "unit": "env-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "dtype_detail": "f32 torch CPU learner, f64 physics",
-        "data": "synthetic", "config": {"workload": wl["name"], "sample_envs": n, "horizon": wl["horizon"]},
-        "cpu_baseline": {"value": round(value, 1), "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample,
-                         "host_cores_available": cores},
-        "e2e": {"value": round(value, 1), "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "impl": "reference", "metric": "PPO env-steps/s", "value": res["value"], "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)),
+        "ms_per_step": round(n * wl["horizon"] / res["value"] * 1e3, 3),
+        "higher_is_better": True, "scaling": "strong" if wl.get("strong") else "weak", "vs_baseline": None, "dtype": "f32",
+        "dtype_detail": "f32 torch CPU learner, f64 physics", "data": "synthetic", "config": config_of(wl, world),
+        "cpu_baseline": res,
+        "e2e": {"value": res["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def main():
@@ -587,11 +793,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS))
     ap.add_argument("--no-c4", action="store_true", help="skip the 40 GiB GAE micro-benchmark arrays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="only the headline workload (no norm_off / c1 / c3 / weak_c2 / c5 / c4 keys)")
     ap.add_argument("--tf32", action="store_true", help="allow TF32 tensor-core GEMMs in the torch MLP (not the headline)")
-    ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of CPU work for the CPU arms (0 = default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

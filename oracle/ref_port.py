@@ -289,7 +289,11 @@ class PPOAgentPort:
     def __init__(self, envs, policy, optimizer, scheduler, n_steps, n_epoch, n_minibatch, gamma, gae_lam,
                  vf_coef=0.25, ent_coef=0.01, clip_range=0.2, clip_grad_norm=0.5, use_grad_clip=True,
                  use_gae=True, use_advnorm=True, use_obsnorm=False, use_rewnorm=False, obsnorm_range=5, rewnorm_range=5,
-                 memory=None, update_fn=None):
+                 memory=None, update_fn=None, action_tape=None, perm_tape=None):
+        # action_tape [steps, N(, A)] / perm_tape [n_shuffles, buffer_size]: replay the random draws of a recorded run
+        # (tests/golden/agent_ppo_*.npz from the live reference) instead of sampling / shuffling — everything else is
+        # computed here, so the comparison does not hinge on the host's RNG stream or last-bit GEMM differences
+        self.action_tape, self.perm_tape, self._tape_pos, self._perm_pos = action_tape, perm_tape, 0, 0
         self.envs, self.policy, self.optimizer, self.scheduler = envs, policy, optimizer, scheduler
         self.n_envs, self.n_steps, self.n_epoch = envs.num_envs, n_steps, n_epoch
         self.buffer_size = self.n_envs * n_steps
@@ -320,11 +324,21 @@ class PPOAgentPort:
             return r
         return np.clip(r / np.clip(self.ret_rms.std, 0.1, 100), -self.rewnorm_range, self.rewnorm_range)
 
-    def _action(self, obs):
+    def _action(self, obs, taped=None):
         _, dist, v = self.policy(obs)
-        a = dist.stochastic_sample()
+        if taped is None:
+            a = dist.stochastic_sample()
+        else:
+            a = torch.as_tensor(taped, device=v.device)
         lp = dist.log_prob(a)
         return a.detach().cpu().numpy(), v.detach().cpu().numpy(), lp.detach().cpu().numpy()
+
+    def _shuffle(self, indexes):
+        if self.perm_tape is None:
+            np.random.shuffle(indexes)
+        else:
+            indexes[:] = self.perm_tape[self._perm_pos]
+            self._perm_pos += 1
 
     def train(self, train_steps):
         obs = self.envs.buf_obs
@@ -332,7 +346,11 @@ class PPOAgentPort:
         for _ in range(train_steps):
             self.obs_rms.update(obs)
             obs = self._obs(obs)
-            acts, value, logps = self._action(obs)
+            taped = None
+            if self.action_tape is not None:
+                taped = self.action_tape[self._tape_pos]
+                self._tape_pos += 1
+            acts, value, logps = self._action(obs, taped)
             next_obs, rewards, terminals, truncations, infos = self.envs.step(acts)
             mem.store(obs, acts, self._rew(rewards), value, terminals, {"old_logp": logps})
             if mem.full:
@@ -341,7 +359,7 @@ class PPOAgentPort:
                     mem.finish_path(0.0 if terminals[i] else vals[i], i)
                 indexes = np.arange(self.buffer_size)
                 for _ in range(self.n_epoch):
-                    np.random.shuffle(indexes)
+                    self._shuffle(indexes)
                     for start in range(0, self.buffer_size, self.batch_size):
                         batch = mem.sample(indexes[start:start + self.batch_size])
                         if self.update_fn is not None:

@@ -10,7 +10,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
     d = {k: z[k] for k in z.files}
-    d["meta"] = json.loads(str(d["meta"]))
+    if "meta" in d:
+        d["meta"] = json.loads(str(d["meta"]))
     return d
 
 

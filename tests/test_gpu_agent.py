@@ -223,3 +223,56 @@ def test_train_accepts_any_step_count_and_ragged_minibatches():
     b.train(7)
     assert torch.equal(a.envs._state, b.envs._state) and torch.equal(a.memory._adv, b.memory._adv)
     assert torch.allclose(a.learner._flat.flat_param, b.learner._flat.flat_param, atol=1e-6)
+
+
+def test_learner_save_and_load_model(tmp_path):
+    """Learner.save_model / load_model (xuance/torch/learners/learner.py:24-45): state_dict round trip through the
+    reference's directory convention — `path/<...seed_{seed}...>/<sorted model files>`, newest (last sorted) wins,
+    `obs_rms.npy` is skipped — and the reference's own state_dict keys."""
+    import xuanpolicy_b200 as xb
+    agent = _build("Pendulum-v1", parallels=64, n_steps=32, n_epoch=1, n_minibatch=1, shuffle="device", seed=2)
+    lr = agent.learner
+    run_dir = tmp_path / "seed_2_SatOct18" 
+    run_dir.mkdir()
+    (tmp_path / "seed_9_other").mkdir()
+    lr.save_model(str(run_dir / "model_000.pth"))
+    first = {k: v.clone() for k, v in agent.policy.state_dict().items()}
+    agent.train(32)                                            # parameters move (flat-buffer Adam on the native path)
+    lr.save_model(str(run_dir / "model_001.pth"))
+    second = {k: v.clone() for k, v in agent.policy.state_dict().items()}
+    assert any(not torch.equal(first[k], second[k]) for k in first)
+    np.save(str(run_dir / "obs_rms.npy"), np.zeros(3))
+    saved = torch.load(str(run_dir / "model_001.pth"))
+    assert list(saved.keys()) == list(first.keys()) and "actor.logstd" in saved       # gaussian.py:25
+    # a fresh policy restores the newest file of the seed's directory
+    other = _build("Pendulum-v1", parallels=64, n_steps=32, n_epoch=1, n_minibatch=1, shuffle="device", seed=5, policy_seed=77)
+    assert any(not torch.equal(second[k], v) for k, v in other.policy.state_dict().items())
+    other.learner.load_model(str(tmp_path), seed=2)
+    for k, v in other.policy.state_dict().items():
+        assert torch.equal(v, second[k]), k
+    if other.learner._fused is not None:
+        assert not other.learner._fused.splits_fresh           # the tf32 operand copies must be rebuilt before the next forward
+    info = other.train(32)                                     # and training continues from the loaded weights
+    assert np.isfinite(info["critic-loss"])
+    # the flat parameter buffer still backs the modules after load_state_dict (in-place copy)
+    assert other.policy.actor.logstd.data_ptr() >= other.learner._flat.flat_param.data_ptr()
+
+
+@pytest.mark.parametrize("env_id,native", [("CartPole-v1", True), ("CartPole-v1", False), ("Pendulum-v1", True)])
+def test_agent_test_runs_evaluation_episodes(env_id, native):
+    """PPOCLIP_Agent.test(env_fn, test_episode) (ppoclip_agent.py:113-165): fresh envs from `env_fn`, stochastic actions,
+    returns the scores of the finished episodes (what Runner_DRL.run / benchmark consume)."""
+    import xuanpolicy_b200 as xb
+    agent = _build(env_id, parallels=16, n_steps=16, n_epoch=1, n_minibatch=1, shuffle="device", seed=2)
+    made = []
+
+    def env_fn():
+        e = xb.DummyVecEnv_Gym(xb.make_env_fns(env_id, 3, 4), device="cuda", native=native)
+        made.append(e)
+        return e
+    scores = agent.test(env_fn, 5)
+    assert len(scores) >= 5 and all(np.isfinite(s) for s in scores) and made[0].closed
+    if env_id == "CartPole-v1":
+        assert all(8 <= s <= 500 for s in scores)              # one reward per step, random-ish policy
+    else:
+        assert all(-2000 < s < 0 for s in scores)              # 200 steps of negative cost

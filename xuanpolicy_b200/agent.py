@@ -617,6 +617,23 @@ class PPOCLIP_Agent:
         info["mean_episode_steps"] = float(st[2] / st[0]) if st[0] > 0 else float("nan")
         return info
 
+    def _test_observation(self, obs):
+        """`self.obs_rms.update(obs); obs = self._process_observation(obs)` of the reference's test loop
+        (ppoclip_agent.py:126-127): evaluation observations are merged into the running statistics too."""
+        if not self.use_obsnorm:
+            return obs
+        od, st = self._obs_dim, self._obs_rms[self._rms_cur]
+        half = (st.numel() - 1) // 2
+        x = obs[:, :od].double()
+        n = x.shape[0]
+        mean, var, cnt = st[:od], st[half:half + od], st[2 * half]
+        delta, tot = x.mean(0) - mean, cnt + n
+        m2 = var * cnt + x.var(0, unbiased=False) * n + delta * delta * cnt * n / tot
+        mean.add_(delta * n / tot)
+        var.copy_(m2 / tot)
+        st[2 * half] = tot
+        return torch.clamp((x - mean) / (var.sqrt() + 1e-8), -self.obsnorm_range, self.obsnorm_range).float()
+
     def test(self, env_fn, test_episode):
         """Evaluation episodes on fresh envs (reference :113-165): stochastic actions, scores of finished episodes."""
         envs = env_fn()
@@ -624,7 +641,8 @@ class PPOCLIP_Agent:
         scores = []
         with torch.no_grad(), torch.cuda.device(self.device):
             while len(scores) < test_episode:
-                _, dist, _ = self.policy(obs if torch.is_tensor(obs) else torch.as_tensor(obs, device=self.device))
+                obs = obs if torch.is_tensor(obs) else torch.as_tensor(obs, device=self.device)
+                _, dist, _ = self.policy(self._test_observation(obs))
                 acts = dist.stochastic_sample()
                 obs, _, term, trunc, infos = envs.step(acts if envs.native else acts.cpu().numpy())
                 done = (term | trunc)
