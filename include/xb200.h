@@ -32,6 +32,10 @@ extern "C" {
 #define XB_ENV_PENDULUM 1 /* Pendulum-v1: state (theta, theta_dot), action float32 torque, limit 200 */
 #define XB_ENV_MOUNTAINCAR 2 /* MountainCar-v0: state (position, velocity), action int64 {0,1,2}, limit 200 */
 #define XB_ENV_ACROBOT 3 /* Acrobot-v1: state (theta1, theta2, dtheta1, dtheta2), action int64 {0,1,2}, limit 500; obs 6 floats = TWO float4 per row */
+/* MountainCar-v0 as the reference's make_envs builds it: MountainCar(Gym_Env), xuance/environment/gym/gym_env.py:50-83 —
+ * observation = the last 4 frames (oldest first), 8 floats = TWO float4 per row; state fp64 [8][N] = (position, velocity,
+ * frame t-3, frame t-2, frame t-1); same physics, action int64 {0,1,2}, limit 200 */
+#define XB_ENV_MOUNTAINCAR_STACK4 4
 
 #define XB_E_BADARG (-1)
 #define XB_E_UNSUPPORTED (-2)
@@ -54,8 +58,9 @@ const char* xb_error_string(int code);
  *           Gym_Env.reset / step                xuance/environment/gym/gym_env.py:36-49
  *           gym 0.26.2 CartPoleEnv / PendulumEnv / TimeLimit / np_random (third party, restated: SURVEY.md App. A/B)
  *
- * state     fp64 [S][N] (SoA; S = 4 CartPole / Acrobot, 2 Pendulum / MountainCar)
- * obs       f32 [N][4] rows (one float4 per env); Acrobot-v1: [N][8] (two float4: cos t1, sin t1, cos t2, sin t2 | dt1, dt2, 0, 0)
+ * state     fp64 [S][N] (SoA; S = 4 CartPole / Acrobot, 2 Pendulum / MountainCar, 8 MountainCar 4-frame stack)
+ * obs       f32 [N][4] rows (one float4 per env); Acrobot-v1: [N][8] (two float4: cos t1, sin t1, cos t2, sin t2 | dt1, dt2, 0, 0);
+ *           MountainCar 4-frame stack: [N][8] (p, v of frames t-3, t-2 | t-1, t)
  * rng       u64  [4][N] (SoA) numpy PCG64: state_hi, state_lo, inc_hi, inc_lo
  * elapsed   i32  [N]    TimeLimit._elapsed_steps == Gym_Env._episode_step
  * ep_score  fp64 [N]    Gym_Env._episode_score
@@ -291,7 +296,8 @@ int xb_bias_act_fwd(float* y, const float* bias, float slope, int64_t B, int H, 
 /* ------------------------------------------------------------------------------------------------------------
  * One vector step of the device-resident rollout in ONE launch: xb_sample_* + xb_env_step + xb_store fused per env
  * (PPOCLIP_Agent._action ppoclip_agent.py:50-57; DummyVecEnv_Gym.step_wait gym_vec_env.py:200-212;
- * DummyOnPolicyBuffer.store memory_tools.py:196-204).  CartPole-v1 / MountainCar-v0: act_param = logits [N][2] / [N][3], act_out int64 [N];
+ * DummyOnPolicyBuffer.store memory_tools.py:196-204).  CartPole-v1 / MountainCar-v0 (both forms) / Acrobot-v1: act_param = logits
+ * [N][2] / [N][3] / [N][3], act_out int64 [N]; wide-row envs (Acrobot, MountainCar stack): x_in / obs / obs_row are [N][8];
  * Pendulum-v1: act_param = mu [N][1], logstd [1], act_out f32 [N].  x_in = the observations the action was computed
  * from (stored as the transition's obs); all other arguments as in xb_env_step / xb_store.  Physics and store are
  * bit-identical to the three separate calls; the sampled action may differ from xb_sample_* in the last ulp of the

@@ -59,8 +59,14 @@ class VecEnvC:
 
     SPEC = {"CartPole-v1": dict(sdim=4, odim=4, max_steps=500, act=np.int64),
             "Pendulum-v1": dict(sdim=2, odim=3, max_steps=200, act=np.float32),
-            "MountainCar-v0": dict(sdim=2, odim=2, max_steps=200, act=np.int64),
+            "gym:MountainCar-v0": dict(sdim=2, odim=2, max_steps=200, act=np.int64),      # gym's bare env
             "Acrobot-v1": dict(sdim=4, odim=6, max_steps=500, act=np.int64)}
+
+    def __new__(cls, env_id, *a, **k):
+        # "MountainCar-v0" = what the reference's make_envs builds: the 4-frame wrapper (gym_env.py:50-83)
+        if env_id == "MountainCar-v0" and cls is VecEnvC:
+            return object.__new__(MountainCarStackC)
+        return object.__new__(cls)
 
     def __init__(self, env_id, n, seed=1, flavour="cr", n_warm_resets=2, seeds=None):
         sp = self.SPEC[env_id]
@@ -82,7 +88,7 @@ class VecEnvC:
         if self.env_id == "CartPole-v1":
             L.oc_cartpole_reset(_p(self.state), _p(self.rng), _p(self.elapsed), _p(self.ep_score), _p(self.obs),
                                 C.c_int(n_draws), C.c_long(self.n))
-        elif self.env_id == "MountainCar-v0":
+        elif self.env_id == "gym:MountainCar-v0":
             L.oc_mountaincar_reset(_p(self.state), _p(self.rng), _p(self.elapsed), _p(self.ep_score), _p(self.obs),
                                    C.c_int(n_draws), C.c_long(self.n))
         elif self.env_id == "Acrobot-v1":
@@ -103,11 +109,54 @@ class VecEnvC:
         ep_step = np.empty(n, np.int32)
         ep_score = np.empty(n, np.float64)
         fn = {"CartPole-v1": lib().oc_cartpole_step, "Pendulum-v1": lib().oc_pendulum_step,
-              "MountainCar-v0": lib().oc_mountaincar_step, "Acrobot-v1": lib().oc_acrobot_step}[self.env_id]
+              "gym:MountainCar-v0": lib().oc_mountaincar_step, "Acrobot-v1": lib().oc_acrobot_step}[self.env_id]
         fn(_p(self.state), _p(self.rng), _p(self.elapsed), _p(self.ep_score), _p(a), _p(self.obs), _p(rew), _p(term),
            _p(trunc), _p(reset_obs), _p(ep_step), _p(ep_score), C.c_int(self.max_steps), C.c_long(n), C.c_int(self.flavour))
         return dict(obs=self.obs.copy(), rew=rew, term=term.astype(bool), trunc=trunc.astype(bool),
                     reset_obs=reset_obs, ep_step=ep_step, ep_score=ep_score, state=self.state.copy())
+
+
+class MountainCarStackC(VecEnvC):
+    """`MountainCar(Gym_Env)` of the reference (xuance/environment/gym/gym_env.py:50-83) over the C oracle's bare env, batched:
+    observation = np.concatenate(last 4 frames, oldest first) (LazyFrames, :227-254); reset() fills all four frames with the
+    reset observation (:67-68); step() appends the new frame (:82).  `state` = [position, velocity, frame t-3, t-2, t-1]
+    (fp64 [n][8]) — the layout of the device kernel's state."""
+
+    def __init__(self, env_id, n, seed=1, flavour="cr", n_warm_resets=2, seeds=None):
+        self.raw = VecEnvC("gym:MountainCar-v0", n, seed, flavour, n_warm_resets, seeds)
+        self.env_id, self.n, self.sdim, self.odim, self.max_steps = env_id, n, 8, 8, self.raw.max_steps
+        self.act_dtype = np.int64
+        self._refill()
+
+    def _refill(self):
+        self.frames = np.repeat(self.raw.obs[:, None, :], 4, axis=1).copy()           # [n][4][2] float32
+        self.obs = self.frames.reshape(self.n, 8).copy()
+
+    @property
+    def state(self):
+        return np.concatenate([self.raw.state, self.frames[:, :3].reshape(self.n, 6).astype(np.float64)], axis=1)
+
+    @property
+    def rng(self):
+        return self.raw.rng
+
+    def reset_all(self, n_draws=1):
+        self.raw.reset_all(n_draws)
+        self._refill()
+        return self.obs.copy()
+
+    def step(self, actions):
+        o = self.raw.step(actions)
+        self.frames = np.concatenate([self.frames[:, 1:], o["obs"][:, None, :]], axis=1)
+        self.obs = self.frames.reshape(self.n, 8).copy()
+        done = o["term"] | o["trunc"]
+        reset_obs = np.zeros((self.n, 8), np.float32)
+        if done.any():
+            self.frames[done] = np.repeat(o["reset_obs"][done][:, None, :], 4, axis=1)
+            reset_obs[done] = self.frames[done].reshape(-1, 8)
+        out = dict(o)
+        out.update(obs=self.obs.copy(), reset_obs=reset_obs, state=self.state)
+        return out
 
 
 def gae(rew, val, term, boot_last, gamma, lam, segend=None, boot=None, use_gae=True):

@@ -170,11 +170,47 @@ def gen_rms(name, seed):
     print("wrote", name)
 
 
+def gen_vecenv_mountaincar(name, n, steps, seed=2):
+    """The reference's `make_envs` on MountainCar-v0: DummyVecEnv_Gym over `MountainCar(Gym_Env)` (4-frame stack,
+    xuance/environment/gym/gym_env.py:50-83, selected at xuance/environment/__init__.py:66-67) over the restated physics,
+    flavour "cr" (the device kernel must match bit for bit)."""
+    from argparse import Namespace
+    import xuance.environment as E
+    cfg = Namespace(env_name="Classic Control", env_id="MountainCar-v0", seed=seed, parallels=n, vectorize="Dummy_Gym",
+                    render_mode="rgb_array")
+    envs = E.make_envs(cfg)
+    assert type(envs.envs[0]).__name__ == "MountainCar" and envs.observation_space.shape == (8,)
+    obs0, _ = envs.reset()
+    rng = np.random.default_rng(13)
+    rec = dict(obs0=obs0, actions=[], obs=[], rew=[], term=[], trunc=[], ep_step=[], ep_score=[], reset_obs=[])
+    for t in range(steps):
+        # energy pumping (push along the velocity) on most envs so that some reach the goal; random actions on the rest
+        heur = np.where(envs.buf_obs[:, 7] > 0, 2, 0).astype(np.int64)
+        a = np.where(rng.random(n) < 0.9, heur, rng.integers(0, 3, n))
+        a[n // 2:] = rng.integers(0, 3, n - n // 2)
+        o, r, d, tr, infos = envs.step(a)
+        ro = np.full_like(o, np.nan)
+        for i, inf in enumerate(infos):
+            if "reset_obs" in inf:
+                ro[i] = np.asarray(inf["reset_obs"])
+        rec["actions"].append(a); rec["obs"].append(o); rec["rew"].append(r); rec["term"].append(d)
+        rec["trunc"].append(tr); rec["reset_obs"].append(ro)
+        rec["ep_step"].append([inf["episode_step"] for inf in infos])
+        rec["ep_score"].append([inf["episode_score"] for inf in infos])
+    out = {k: (np.asarray(v) if k != "obs0" else v) for k, v in rec.items()}
+    out["space_low"], out["space_high"] = np.asarray(envs.observation_space.low), np.asarray(envs.observation_space.high)
+    out["meta"] = np.array(json.dumps(dict(env_id="MountainCar-v0", n=n, steps=steps, seed=seed, trig="cr",
+                                           max_episode_length=int(envs.max_episode_length), n_actions=int(envs.action_space.n))))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, "terminals", int(out["term"].sum()), "truncations", int(out["trunc"].sum()))
+
+
 def main():
     assert ref_loader.source_tree_available(), "needs the reference source tree (/root/reference)"
     os.makedirs(OUT, exist_ok=True)
     ref_loader.load(trig="cr")
     gen_rms("rms_reference", 301)
+    gen_vecenv_mountaincar("vecenv_mountaincar_stack", 8, 460)
     gen_agent("agent_ppo_cartpole", "CartPole-v1", n_envs=8, n_steps=32, train_steps=3 * 32 + 5, hidden=32, n_epoch=2,
               n_minibatch=4, seed=3, gamma=0.98)
     gen_agent("agent_ppo_pendulum", "Pendulum-v1", n_envs=4, n_steps=128, train_steps=2 * 128 + 9, hidden=32, n_epoch=2,
@@ -182,4 +218,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "mountaincar":
+        ref_loader.load(trig="cr")
+        gen_vecenv_mountaincar("vecenv_mountaincar_stack", 8, 460)
+    else:
+        main()

@@ -27,6 +27,29 @@ from . import gym_restated
 
 
 # ------------------------------------------------------------------------------------------------ vec env
+class MountainCarStackPort:
+    """`MountainCar(Gym_Env)` restated (xuance/environment/gym/gym_env.py:50-83): a 4-frame stack over gym's env; the
+    observation is `LazyFrames(list(frames))` -> np.concatenate(frames, axis=-1) (:227-254), shape (8,)."""
+
+    def __init__(self, env):
+        from collections import deque
+        self.env, self._max_episode_steps, self.action_space = env, env._max_episode_steps, env.action_space
+        self.frames = deque([], maxlen=4)
+        lo, hi = np.array([-1.2, -0.07] * 4), np.array([0.6, 0.07] * 4)
+        self.observation_space = type(env.observation_space)(lo.astype(np.float32), hi.astype(np.float32))
+
+    def reset(self, **kw):
+        obs, info = self.env.reset(**kw)
+        for _ in range(4):
+            self.frames.append(obs)
+        return np.concatenate(list(self.frames), axis=-1), info
+
+    def step(self, action):
+        obs, rew, term, trunc, info = self.env.step(action)
+        self.frames.append(obs)
+        return np.concatenate(list(self.frames), axis=-1), rew, term, trunc, info
+
+
 class VecEnvPort:
     """Serial vector env with xuance's auto-reset protocol (terminal obs in buf_obs, reset obs in infos)."""
 
@@ -34,8 +57,10 @@ class VecEnvPort:
         self.num_envs = num_envs
         self.envs = []
         for _ in range(num_envs):
-            env = gym_restated.make(env_id, trig=trig)
+            env = gym_restated.make(env_id.replace("gym:", ""), trig=trig)
             env.reset(seed=seed)                          # gym_env.py:19 (every env gets the same seed)
+            if "MountainCar" in env_id and not env_id.startswith("gym:"):
+                env = MountainCarStackPort(env)           # make_envs: environment/__init__.py:66-67
             self.envs.append(env)
         self.max_episode_length = self.envs[0]._max_episode_steps
         self.observation_space = self.envs[0].observation_space

@@ -13,8 +13,8 @@ def _build(env_id, **kw):
     return build_ppo(env_id, **kw)
 
 
-@pytest.mark.parametrize("env_id,n,T", [("CartPole-v1", 64, 40), ("Pendulum-v1", 48, 230), ("MountainCar-v0", 40, 210),
-                                       ("Acrobot-v1", 24, 520)])
+@pytest.mark.parametrize("env_id,n,T", [("CartPole-v1", 64, 40), ("Pendulum-v1", 48, 230), ("gym:MountainCar-v0", 40, 210),
+                                       ("MountainCar-v0", 36, 210), ("Acrobot-v1", 24, 520)])
 @pytest.mark.parametrize("graphs", [True, False])
 def test_native_rollout_replays_bit_exact_through_the_oracle(env_id, n, T, graphs):
     """Take the actions the device loop drew, replay them through the C oracle from the same seed: the buffer's

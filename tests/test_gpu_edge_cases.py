@@ -9,7 +9,7 @@ from tests.helpers import gae_close
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("env_id", ["CartPole-v1", "Pendulum-v1", "MountainCar-v0", "Acrobot-v1"])
+@pytest.mark.parametrize("env_id", ["CartPole-v1", "Pendulum-v1", "gym:MountainCar-v0", "MountainCar-v0", "Acrobot-v1"])
 def test_single_env_steps_bit_exact(env_id):
     import xuanpolicy_b200 as xb
     from oracle import c_oracle

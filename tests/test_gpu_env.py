@@ -54,7 +54,8 @@ def test_env_tape_bit_exact_vs_golden(name):
 
 
 @pytest.mark.parametrize("env_id,n,steps", [("CartPole-v1", 4099, 520), ("Pendulum-v1", 4096, 410),
-                                            ("MountainCar-v0", 2051, 430), ("Acrobot-v1", 1027, 560)])
+                                            ("gym:MountainCar-v0", 2051, 430), ("MountainCar-v0", 1033, 430),
+                                            ("Acrobot-v1", 1027, 560)])
 def test_env_large_batch_bit_exact_vs_c_oracle(env_id, n, steps):
     """Ragged batch size, per-env divergent random actions, many resets: still bit-exact with the C oracle."""
     from oracle import c_oracle
@@ -68,8 +69,8 @@ def test_env_large_batch_bit_exact_vs_c_oracle(env_id, n, steps):
         if env_id == "CartPole-v1":
             heur = (obs[:, 2] + 0.5 * obs[:, 3] > 0).astype(np.int64)
             a = np.where(rng.random(n) < 0.8, heur, rng.integers(0, 2, n))
-        elif env_id == "MountainCar-v0":        # energy-pumping heuristic so that some cars reach the goal (terminated)
-            heur = np.where(obs[:, 1] > 0, 2, 0).astype(np.int64)
+        elif "MountainCar" in env_id:           # energy-pumping heuristic so that some cars reach the goal (terminated)
+            heur = np.where(obs[:, -1] > 0, 2, 0).astype(np.int64)      # velocity of the newest frame
             a = np.where(rng.random(n) < 0.9, heur, rng.integers(0, 3, n))
         elif env_id == "Acrobot-v1":            # torque along the second joint's velocity: swings up (terminated) in ~70 steps
             heur = np.where(obs[:, 5] > 0, 2, 0).astype(np.int64)
@@ -89,6 +90,33 @@ def test_env_large_batch_bit_exact_vs_c_oracle(env_id, n, steps):
     assert n_done > 0
     st = envs.ep_stats.cpu().numpy()
     assert st[0] == n_done
+
+
+def test_mountaincar_is_the_references_four_frame_wrapper():
+    """`make_envs` wraps MountainCar-v0 in `MountainCar(Gym_Env)` (xuance/environment/gym/gym_env.py:50-83): observation
+    space (8,), observation = the last four frames oldest first, all four = the reset observation after a reset.  Golden
+    recorded from the reference's own make_envs / DummyVecEnv_Gym over the restated physics (flavour "cr"): bit-exact."""
+    g = load_golden("vecenv_mountaincar_stack")
+    m = g["meta"]
+    envs = _envs("MountainCar-v0", m["n"], m["seed"])
+    assert envs.observation_space.shape == (8,) and envs.action_space.n == m["n_actions"]
+    assert np.array_equal(envs.observation_space.low, g["space_low"].astype(np.float32))
+    assert np.array_equal(envs.observation_space.high, g["space_high"].astype(np.float32))
+    assert envs.max_episode_length == m["max_episode_length"] and envs.buf_obs.shape == (m["n"], 8)
+    obs0, _ = envs.reset()
+    assert np.array_equal(obs0, g["obs0"]) and np.array_equal(obs0[:, 0:2], obs0[:, 6:8])
+    for t in range(m["steps"]):
+        obs, rew, term, trunc, infos = envs.step(g["actions"][t])
+        assert np.array_equal(obs, g["obs"][t]) and np.array_equal(rew, g["rew"][t]), t
+        assert np.array_equal(term, g["term"][t]) and np.array_equal(trunc, g["trunc"][t]), t
+        assert [i["episode_step"] for i in infos] == g["ep_step"][t].tolist()
+        assert [i["episode_score"] for i in infos] == g["ep_score"][t].tolist()
+        for i, inf in enumerate(infos):
+            if term[i] or trunc[i]:
+                assert np.array_equal(inf["reset_obs"], g["reset_obs"][t][i])
+            else:
+                assert "reset_obs" not in inf
+    assert g["term"].sum() > 0 and g["trunc"].sum() > 0
 
 
 @pytest.mark.parametrize("name", ["vecenv_cartpole", "vecenv_pendulum"])

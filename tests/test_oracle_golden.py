@@ -81,13 +81,16 @@ def test_physics_tape_c_and_python_agree(name):
                 assert np.array_equal(np.array(pe.env.state), g["state"][t][i])
 
 
-@pytest.mark.parametrize("name", ["vecenv_cartpole", "vecenv_pendulum"])
+@pytest.mark.parametrize("name", ["vecenv_cartpole", "vecenv_pendulum", "vecenv_mountaincar_stack"])
 def test_vecenv_port_matches_reference_golden(name):
-    """ref_port.VecEnvPort and the C oracle (libm flavour) vs the reference DummyVecEnv_Gym run."""
+    """ref_port.VecEnvPort and the C oracle vs the reference DummyVecEnv_Gym run (libm flavour; the MountainCar golden —
+    the reference's 4-frame `MountainCar` wrapper as built by its own make_envs — was recorded with the "cr" flavour)."""
     g = load_golden(name)
     m = g["meta"]
-    port = ref_port.VecEnvPort(m["env_id"], m["n"], seed=m["seed"], trig="libm")
-    cenv = c_oracle.VecEnvC(m["env_id"], m["n"], seed=m["seed"], flavour="libm")
+    port = ref_port.VecEnvPort(m["env_id"], m["n"], seed=m["seed"], trig=m["trig"])
+    cenv = c_oracle.VecEnvC(m["env_id"], m["n"], seed=m["seed"], flavour=m["trig"])
+    if "space_low" in g:
+        assert port.observation_space.shape == (8,) and np.array_equal(port.observation_space.low, g["space_low"].astype(np.float32))
     obs0, _ = port.reset()
     assert np.array_equal(obs0, g["obs0"]) and np.array_equal(cenv.obs, g["obs0"])
     assert port.max_episode_length == m["max_episode_length"]
@@ -240,7 +243,7 @@ def test_mountaincar_c_and_python_restatements_agree_and_kat():
     import math
     from oracle import c_oracle, gym_restated
     n = 6
-    ref = c_oracle.VecEnvC("MountainCar-v0", n, seed=3, flavour="libm", n_warm_resets=1)
+    ref = c_oracle.VecEnvC("gym:MountainCar-v0", n, seed=3, flavour="libm", n_warm_resets=1)
     envs = [gym_restated.make("MountainCar-v0", trig="libm") for _ in range(n)]
     obs = np.stack([e.reset(seed=3)[0] for e in envs])
     assert np.array_equal(obs, ref.obs)

@@ -176,7 +176,7 @@ class PPOCLIP_Agent:
         # one launch per vector step (sample + env step + store) for the two classic-control action shapes
         import os as _os
         self._fused_step = (_os.environ.get("XB_FUSED_STEP", "1") != "0" and
-                            ((self.discrete and int(self.action_space.n) == {0: 2, 2: 3}.get(envs._kind, -1)) or
+                            ((self.discrete and int(self.action_space.n) == {0: 2, 2: 3, 3: 3, 4: 3}.get(envs._kind, -1)) or
                              (not self.discrete and self.memory.act_dim == 1)))
         self._rollout_graph = None
         self._epoch_graph = None

@@ -1,4 +1,5 @@
-// env_classic.cu — batched CartPole-v1 / Pendulum-v1 / MountainCar-v0 / Acrobot-v1 step + auto-reset, one thread per environment.
+// env_classic.cu — batched CartPole-v1 / Pendulum-v1 / MountainCar-v0 (gym's, and the reference's 4-frame wrapper) /
+// Acrobot-v1 step + auto-reset, one thread per environment.
 //
 // Replaces the per-env Python loop of DummyVecEnv_Gym.step_wait (xuance/environment/gym/gym_vec_env.py:201-212)
 // over Gym_Env.step (xuance/environment/gym/gym_env.py:43-49) over gym 0.26.2's CartPoleEnv / PendulumEnv /
@@ -170,6 +171,44 @@ struct MountainCar {
         st[0] = position; st[1] = velocity;
         terminated = position >= goal_pos && velocity >= 0.0;
         return -1.0;
+    }
+};
+
+// MountainCar-v0 AS THE REFERENCE DEFINES IT: `make_envs` wraps every env id containing "MountainCar" in
+// xuance/environment/gym/gym_env.py:50-83 `MountainCar(Gym_Env)` (selected at xuance/environment/__init__.py:66-67): the
+// observation is the concatenation of the last FOUR frames, oldest first (`LazyFrames(list(self.frames))`, deque maxlen 4,
+// gym_env.py:227-254), shape (8,); `reset()` fills all four frames with the reset observation (:67-68).  The three previous
+// float32 frames ride in the fp64 state slots 2..7 (exact), so the generic step / reset / rollout kernels need no extra
+// argument; slots 0..1 are gym's (position, velocity) with the physics of `MountainCar` above, bit for bit.
+struct MountainCarStack {
+    static constexpr int kObsVec = 2;
+    static constexpr bool kTrigCache = false;
+    static constexpr int S = 8;
+    typedef int64_t action_t;
+    static constexpr bool kDiscrete = true;
+    static constexpr int kActions = 3;
+    __device__ static void draw(double (&st)[8], Pcg64& g) {
+        double b[2];
+        MountainCar::draw(b, g);
+        st[0] = b[0]; st[1] = b[1];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {           // for i in range(num_stack): frames.append(obs)
+            st[2 + 2 * k] = (double)(float)b[0];
+            st[3 + 2 * k] = (double)(float)b[1];
+        }
+    }
+    __device__ static void observe(const double (&st)[8], float4 (&o)[2]) {
+        o[0] = make_float4((float)st[2], (float)st[3], (float)st[4], (float)st[5]);
+        o[1] = make_float4((float)st[6], (float)st[7], (float)st[0], (float)st[1]);
+    }
+    __device__ static double step(double (&st)[8], action_t action, bool& terminated) {
+        double b[2] = {st[0], st[1]};
+        const float fp = (float)b[0], fv = (float)b[1];       // the frame appended by the previous step / reset
+        const double r = MountainCar::step(b, action, terminated);
+        st[2] = st[4]; st[3] = st[5]; st[4] = st[6]; st[5] = st[7];
+        st[6] = (double)fp; st[7] = (double)fv;
+        st[0] = b[0]; st[1] = b[1];
+        return r;
     }
 };
 
@@ -433,7 +472,8 @@ __global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs
     }
     a.logp_out[e] = logp;
     a.logp_row[e] = logp;
-    a.obs_row[e] = a.x_in[e];
+#pragma unroll
+    for (int v = 0; v < Env::kObsVec; ++v) a.obs_row[e * Env::kObsVec + v] = a.x_in[e * Env::kObsVec + v];
     a.val_row[e] = a.val[e];
     if (a.boot_row) a.boot_row[e] = a.boot_src[e];   // V(terminal obs) for envs truncated at step t-1 (ppoclip_agent.py:99)
     // ---- env step (identical arithmetic to env_step_kernel)
@@ -444,7 +484,7 @@ __global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs
     double score = a.ep_score[e];
     bool terminated;
     double reward;
-    float4 o;
+    float4 o[Env::kObsVec];
     double sc_s = 0.0, sc_c = 0.0;
     if constexpr (Env::kTrigCache) {
         bool hit = false;
@@ -455,15 +495,15 @@ __global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs
         if (!hit) sincos_cr(st[0], &sc_s, &sc_c);
         reward = Env::step_sc(st, act, terminated, sc_s);
         sincos_cr(st[0], &sc_s, &sc_c);            // of the NEW theta: this step's observation, the next step's dynamics
-        o = Env::observe_sc(st, sc_s, sc_c);
+        o[0] = Env::observe_sc(st, sc_s, sc_c);
     } else {
         reward = Env::step(st, act, terminated);
-        o = Env::observe(st);
+        observe_row<Env>(st, o);
     }
     el += 1;
     const bool truncated = el >= a.max_steps;
     score = __dadd_rn(score, reward);
-    a.obs[e] = o;
+    put_row<Env>(a.obs, e, o);
     const float r32 = (float)reward;
     a.rew[e] = r32;
     a.term[e] = terminated ? 1 : 0;
@@ -484,13 +524,13 @@ __global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs
         score = 0.0;
         if constexpr (Env::kTrigCache) {
             sincos_cr(st[0], &sc_s, &sc_c);
-            o = Env::observe_sc(st, sc_s, sc_c);
+            o[0] = Env::observe_sc(st, sc_s, sc_c);
         } else {
-            o = Env::observe(st);
+            observe_row<Env>(st, o);
         }
-        a.reset_obs[e] = o;
+        put_row<Env>(a.reset_obs, e, o);
     }
-    if (a.next_obs) a.next_obs[e] = o;
+    if (a.next_obs) put_row<Env>(a.next_obs, e, o);
     if constexpr (Env::kTrigCache) {
         if (a.trig_cache) {
             a.trig_cache[e] = st[0];
@@ -542,6 +582,8 @@ extern "C" int xb_env_reset(int env_kind, double* state, uint64_t* rng, int32_t*
         env_reset_kernel<MountainCar><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (float4*)obs, n_draws, N);
     else if (env_kind == XB_ENV_ACROBOT)
         env_reset_kernel<Acrobot><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (float4*)obs, n_draws, N);
+    else if (env_kind == XB_ENV_MOUNTAINCAR_STACK4)
+        env_reset_kernel<MountainCarStack><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (float4*)obs, n_draws, N);
     else
         return XB_E_UNSUPPORTED;
     XB_LAUNCH_CHECK();
@@ -577,6 +619,11 @@ extern "C" int xb_env_step(int env_kind, double* state, uint64_t* rng, int32_t* 
                                                         (float4*)obs, (float4*)next_obs, rew, term, trunc,
                                                         (float4*)reset_obs, ep_step_out, ep_score_out, ep_stats,
                                                         max_episode_steps, N);
+    else if (env_kind == XB_ENV_MOUNTAINCAR_STACK4)
+        env_step_kernel<MountainCarStack><<<grid, block, 0, s>>>(state, rng, elapsed, ep_score, (const int64_t*)actions,
+                                                                 (float4*)obs, (float4*)next_obs, rew, term, trunc,
+                                                                 (float4*)reset_obs, ep_step_out, ep_score_out, ep_stats,
+                                                                 max_episode_steps, N);
     else
         return XB_E_UNSUPPORTED;
     XB_LAUNCH_CHECK();
@@ -613,6 +660,8 @@ extern "C" int xb_rollout_step(int env_kind, const float* act_param, const float
     if (env_kind == XB_ENV_CARTPOLE) rollout_step_kernel<CartPole><<<grid, block, 0, s>>>(a);
     else if (env_kind == XB_ENV_PENDULUM) rollout_step_kernel<Pendulum><<<grid, block, 0, s>>>(a);
     else if (env_kind == XB_ENV_MOUNTAINCAR) rollout_step_kernel<MountainCar><<<grid, block, 0, s>>>(a);
+    else if (env_kind == XB_ENV_ACROBOT) rollout_step_kernel<Acrobot><<<grid, block, 0, s>>>(a);
+    else if (env_kind == XB_ENV_MOUNTAINCAR_STACK4) rollout_step_kernel<MountainCarStack><<<grid, block, 0, s>>>(a);
     else return XB_E_UNSUPPORTED;
     XB_LAUNCH_CHECK();
     return 0;

@@ -7,7 +7,7 @@ import torch
 
 from . import _lib
 
-ENV_KINDS = {"CartPole-v1": 0, "Pendulum-v1": 1, "MountainCar-v0": 2, "Acrobot-v1": 3}
+ENV_KINDS = {"CartPole-v1": 0, "Pendulum-v1": 1, "gym:MountainCar-v0": 2, "Acrobot-v1": 3, "MountainCar-v0": 4}
 GAE_VARIANTS = {"auto": 0, "ldg": 1, "tma": 2}
 
 

@@ -23,7 +23,10 @@ from .spaces import Box, Discrete
 SPECS = {
     "CartPole-v1": dict(kind=0, state_dim=4, obs_dim=4, max_steps=500),
     "Pendulum-v1": dict(kind=1, state_dim=2, obs_dim=3, max_steps=200),
-    "MountainCar-v0": dict(kind=2, state_dim=2, obs_dim=2, max_steps=200),
+    # the reference's make_envs wraps MountainCar in a 4-frame stack (gym_env.py:50-83; environment/__init__.py:66-67):
+    # that is what "MountainCar-v0" means under the drop-in; gym's bare 2-float env keeps the id "gym:MountainCar-v0"
+    "MountainCar-v0": dict(kind=4, state_dim=8, obs_dim=8, max_steps=200),
+    "gym:MountainCar-v0": dict(kind=2, state_dim=2, obs_dim=2, max_steps=200),
     "Acrobot-v1": dict(kind=3, state_dim=4, obs_dim=6, max_steps=500),
 }
 
@@ -45,7 +48,9 @@ def make_spaces(env_id):
     if env_id == "Pendulum-v1":
         high = np.array([1.0, 1.0, 8.0], np.float32)
         return Box(-high, high), Box(-2.0, 2.0, shape=(1,))
-    if env_id == "MountainCar-v0":
+    if env_id == "MountainCar-v0":       # gym_env.py:55-57
+        return Box(np.array([-1.2, -0.07] * 4, np.float32), np.array([0.6, 0.07] * 4, np.float32)), Discrete(3)
+    if env_id == "gym:MountainCar-v0":
         return Box(np.array([-1.2, -0.07], np.float32), np.array([0.6, 0.07], np.float32)), Discrete(3)
     if env_id == "Acrobot-v1":
         high = np.array([1.0, 1.0, 1.0, 1.0, 4 * np.pi, 9 * np.pi], np.float32)
