@@ -221,10 +221,15 @@ def count_launches(agent):
         per_rollout = T * (3 + 5) + 5 + 2 + 1  # per step: sample, env_step, store, 3 bias+act, 2 head; bootstrap fwd; GAE + pack; counter
         per_update = 1 + 1 + 2 + 5 + 3         # gather, loss, grad-norm + adam, fwd: 3 bias+act + 2 head, bwd: 2 head+act + 1 act+bias
     per_epoch = 2 if agent.shuffle != "host" else 0     # device permutation + its counter tick
-    if agent.use_obsnorm:                               # per step: moments + normalise; + the bootstrap normalise; state copy
-        per_rollout += 2 * T + 2
-    if agent.use_rewnorm:                               # per step: return tracker + scalar merge
-        per_rollout += 2 * T
+    if agent._fused_norm:                               # statistics ride in the fused step, normalisation in the forward
+        if agent.use_obsnorm and not (agent.learner._fused is not None and agent.learner._fused.fwd_from_obs_ok()
+                                      and 2 * agent.n_envs >= agent.learner._fused.MIN_ROWS):
+            per_rollout += T + 1                        # xb_rms_apply in front of a torch / multi-launch forward
+    else:
+        if agent.use_obsnorm:                           # per step: moments + normalise; + the bootstrap normalise; state copy
+            per_rollout += 2 * T + 2
+        if agent.use_rewnorm:                           # per step: return tracker + scalar merge
+            per_rollout += 2 * T
     if agent._norm_peer is not None:                    # env-sharded: one statistics exchange per step
         per_rollout += T
     return per_rollout + E * (M * per_update + per_epoch)
@@ -293,7 +298,7 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
             act_param = prm[:N] if not gauss else prm[0][:N]
             logstd = None if not gauss else agent.policy.actor.logstd.detach()
             add("rollout_step_fused", lambda: ops.rollout_step(
-                env._kind, act_param, logstd, v0[:N], agent.seed, agent._ctr, 0, env._state, env._rng, env._elapsed,
+                env._kind, act_param, logstd, v0[:N], agent._sample_seed, agent._ctr, 0, env._state, env._rng, env._elapsed,
                 env._ep_score, x_nxt[N:], x_nxt[:N], env._rew, env._term, env._trunc, env._reset_obs, env._ep_step_out,
                 env._ep_score_out, env.ep_stats, env.max_episode_length, x_cur[:N], agent._act, agent._logp, mem._obs[0],
                 mem._act[0], mem._rew[0], mem._val[0], mem._term[0], mem._trunc[0], mem._logp[0],
@@ -301,11 +306,11 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
                 env_bytes + N * ((4 + 4 + 4) if gauss else (8 + 8 + 4)) + N * 36, T)
         agent._restore(snap)
         agent._cur = cur
-    if agent.use_obsnorm:
+    if agent.use_obsnorm and not agent._fused_norm:
         add("obs_moments", lambda: ops.moments4(x_cur[:N], agent._obs_sums, agent._obs_ws), N * 16, T)
         add("obs_normalize", lambda: ops.rms_normalize(x_cur, od, agent._obs_sums, agent._obs_rms[0], agent._obs_rms[1],
                                                        agent.obsnorm_range, agent._xn, 0), 2 * N * 32, T + 1)
-    if agent.use_rewnorm:
+    if agent.use_rewnorm and not agent._fused_norm:
         snap_r = agent._snapshot()
         add("returns_track", lambda: ops.returns_track(agent._returns, env._rew, env._term, env._trunc, agent.gamma,
                                                        agent._ret_sums, agent._ret_ws), N * (8 + 8 + 4 + 2), T)

@@ -269,6 +269,17 @@ int xb_rms_normalize(const float* x, int dim, const double* sums, const double* 
 int xb_returns_track(double* returns, const float* rew, const uint8_t* term, const uint8_t* trunc, double gamma, int mask_terminal,
                      double* sums, double* workspace, int64_t N, xb_stream_t stream);
 int xb_rms_merge_scalar(const double* sums, double* state, float* rew_std, xb_stream_t stream);
+/* The same statistics for the fused path, where xb_rollout_step carries the merges (see there): observation rows of
+ * row_floats = 4 or 8 floats, state fp64 [2*row_floats + 1] = mean, var, count.
+ *   xb_rms_apply        out = normalise(x) with state_new for rows [0, n_new_rows) and state_old for the rest (no merge):
+ *                       the policy input when the MLP runs in torch (xb_mlp_fwd_from_obs normalises by itself)
+ *   xb_rms_update_rows  state_out = state_in merged with the batch moments of x [N rows] (`obs_rms.update(obs)`): used once,
+ *                       for the very first observations.  partials fp64 [148 * 20], ticket u32 [1] zero-initialised;
+ *                       ticket == NULL: deferred form, only the per-CTA partial sums are written (consumer: xb_mlp_fwd_from_obs). */
+int xb_rms_apply(const float* x, int row_floats, int dim, const double* state_new, const double* state_old, int64_t n_new_rows,
+                 float clip, float* out, int64_t N, xb_stream_t stream);
+int xb_rms_update_rows(const float* x, int row_floats, int dim, int64_t N, const double* state_in, double* state_out,
+                       double* partials, uint32_t* ticket, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Non-GEMM half of the MLP backward (the GEMMs stay in torch/cuBLAS): LeakyReLU' fused with the bias gradient.
@@ -308,6 +319,17 @@ int xb_bias_act_fwd(float* y, const float* bias, float slope, int64_t B, int H, 
  * trig_cache (nullable, fp64 [3][N], initialise the first row to NaN): Pendulum's observation (cos, sin of the new theta)
  * is the next step's dynamics input; the row (theta, sin, cos) is reused when its key equals the current theta bit for
  * bit, recomputed otherwise — the values are identical either way (correctly-rounded pure functions of theta).
+ * Running statistics carried by the same launch (stat_partials != NULL; csrc/normalize.cuh StepStats) — replaces, per step,
+ * `obs_rms.update(obs)` of the next loop iteration, the per-env return tracker and `ret_rms.update` (ppoclip_agent.py:62,
+ * 87-92; statistic_tools.py:63-112) and their four launches (xb_moments4, xb_rms_normalize, xb_returns_track,
+ * xb_rms_merge_scalar):
+ *   obs_state_in / obs_state_out (nullable pair, fp64 [2D+1], D = floats per obs row, DIFFERENT buffers): x_in holds RAW
+ *     observations, the stored row is normalise(x_in, obs_state_in); obs_state_out = obs_state_in merged (Chan, float32) with
+ *     the batch moments of next_obs; obs_dim real floats per row, obs_clip the clipping range;
+ *   ret_state (nullable, fp64 [3]) with rew_std_io (f32 [1]: read as this step's reward divisor — pass the same pointer as
+ *     rew_scale — and rewritten for the next step) and returns (fp64 [N] tracker), gamma, mask_terminal (1 = PPO, 0 = A2C);
+ *   stat_partials fp64 [grid * 20] / stat_ticket u32 [1] (zero-initialised once): per-CTA sums, added in CTA order by the
+ *     last CTA (deterministic).
  * ---------------------------------------------------------------------------------------------------------- */
 int xb_rollout_step(int env_kind, const float* act_param, const float* logstd, const float* val, uint64_t seed,
                     const uint64_t* counter_dev, uint64_t offset, double* state, uint64_t* rng, int32_t* elapsed,
@@ -316,7 +338,9 @@ int xb_rollout_step(int env_kind, const float* act_param, const float* logstd, c
                     int max_episode_steps, const float* x_in, void* act_out, float* logp_out, float* obs_row,
                     float* act_row, float* rew_row, float* val_row, float* term_row, uint8_t* trunc_row, float* logp_row,
                     const float* rew_scale, float rew_clip, const float* boot_src, float* boot_row, double* trig_cache,
-                    int64_t N, xb_stream_t stream);
+                    const double* obs_state_in, double* obs_state_out, int obs_dim, float obs_clip, double* ret_state,
+                    float* rew_std_io, double* returns, double gamma, int mask_terminal, double* stat_partials,
+                    uint32_t* stat_ticket, int64_t N, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Dense layers of the policy/value MLP at large batch on the tcgen05 tensor cores with fp32-level accuracy
@@ -384,7 +408,17 @@ int xb_dense_fwd2(const float* X, int64_t M, int K, int N, float slope, const fl
 /*   xb_mlp_fwd_from_obs     the whole actor-critic forward in ONE launch (rollout / inference): the trunk layer
  *                           h1 = leaky_relu(W0 obs + b0) is generated by the operand warps straight into tensor memory
  *                           (obs_dim <= 4, H in {64, 128}), then both hidden layers + heads as in xb_dense_fwd2.
- *                           Y0 / Y1 may both be NULL: only the head outputs are produced. */
+ *                           Y0 / Y1 may both be NULL: only the head outputs are produced.
+ *                           norm_new / norm_old (nullable pair, fp64 [9] observation-normaliser states): obs holds RAW
+ *                           observations; rows [0, norm_rows) are normalised with norm_new, the rest with norm_old
+ *                           (clip((obs - mean) / (sqrt(var) + 1e-8), +-norm_clip), agent.py:112-113) before the trunk layer.
+ *                           Deferred statistics merge (st_partials != NULL): the preceding xb_rollout_step was called in its
+ *                           deferred form (stat_ticket == NULL) and left st_ctas per-CTA partial sums; every CTA of this
+ *                           launch adds them up in its prologue (fixed order), st_obs = 1: merges the observation moments
+ *                           into norm_old -> used for rows [0, norm_rows) and published to norm_state_out (!= norm_old) by
+ *                           CTA 0 (norm_new is ignored); ret_state (nullable, fp64 [3]) is merged in place with the finished
+ *                           returns and rew_std (f32 [1]) republished.  xn_out (nullable, f32 [norm_rows][4]): the
+ *                           normalised observations of rows [0, norm_rows) (what the rollout stores as the transition's obs). */
 /* xb_dense_fwd2 (actor | critic hidden layers + heads) with xb_ppo_loss_* fused into its epilogue: the epilogue thread that
  * holds a row's head outputs turns them straight into dL/d(mu | logits) (actor CTA) and dL/dv (critic CTA) with the formulas of
  * ppoclip_learner.py:33-44 — no loss launch, no round trip of the head outputs.
@@ -405,7 +439,9 @@ int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const float* W0, 
                         float slope, const float* Whi0, const float* Wlo0, const float* bias0, float* Y0,
                         const float* head_w0, const float* head_b0, int n_head0, float* head_out0, const float* Whi1,
                         const float* Wlo1, const float* bias1, float* Y1, const float* head_w1, const float* head_b1,
-                        int n_head1, float* head_out1, xb_stream_t stream);
+                        int n_head1, float* head_out1, const double* norm_new, const double* norm_old, int64_t norm_rows,
+                        float norm_clip, const double* st_partials, int st_ctas, int st_obs, double* norm_state_out,
+                        double* ret_state, float* rew_std, float* xn_out, xb_stream_t stream);
 int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, int K0, const float* Y1,
                    const float* dout1, const float* w2_1, int nh1, int K1, int64_t M, const float* Wthi,
                    const float* Wtlo, int N, const float* H1, float slope, float* dZ1, xb_stream_t stream);

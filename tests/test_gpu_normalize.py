@@ -113,6 +113,97 @@ def test_native_rollout_with_obs_and_reward_normalisation():
                 returns[i] = 0.0
             ref.obs[done] = o["reset_obs"][done]
     st = agent._obs_rms[0].cpu().numpy()
+    if agent._fused_norm and not agent._defer_norm:      # the fused step already merged the observations the NEXT step will act on
+        obs_rms.update(ref.obs)                          # (deferred form: their partial sums wait for the next forward)
     assert np.allclose(st[:3], obs_rms.mean, rtol=1e-4, atol=2e-5) and abs(st[8] - obs_rms.count) < 1e-6 * obs_rms.count
     info = agent.train(T)
     assert np.isfinite(info["critic-loss"])
+
+
+@pytest.mark.parametrize("env_id,n", [("CartPole-v1", 96), ("Pendulum-v1", 1200), ("MountainCar-v0", 64), ("Acrobot-v1", 40)])
+def test_fused_statistics_rollout_vs_oracle_normalisers(env_id, n):
+    """The statistics carried by the fused rollout step (csrc/normalize.cuh: obs moments merged by the step that produces the
+    observations, return tracker + return normaliser, reward divisor) and the normalisation done inside the rollout forward
+    (Pendulum at 2400 rows: the one-launch tcgen05 forward; the others: xb_rms_apply + torch MLP; MountainCar / Acrobot:
+    8-float rows) against oracle/ref_port.RunningMeanStdPort fed with the raw observations / finished returns of the same
+    run, and against agent.py:104-123 applied with the oracle's statistics of each step."""
+    from oracle import ref_port
+    from xuanpolicy_b200.configs import build_ppo
+    T = 24 if env_id != "Pendulum-v1" else 210
+    agent = build_ppo(env_id, parallels=n, n_steps=T, n_epoch=1, n_minibatch=2, use_obsnorm=True, use_rewnorm=True,
+                      use_cuda_graphs=False, shuffle="device", seed=3, gamma=0.98)
+    assert agent._fused_norm and agent._fused_step
+    od = agent._obs_dim
+    raw, rews, terms, truncs = [], [], [], []
+    orig = agent._rollout_step
+
+    def step(t):
+        raw.append(agent._x[agent._cur][:n, :od].cpu().numpy().copy())
+        orig(t)
+        rews.append(agent.envs._rew.cpu().numpy().copy())
+        terms.append(agent.envs._term.cpu().numpy().astype(bool))
+        truncs.append(agent.envs._trunc.cpu().numpy().astype(bool))
+    agent._rollout_step = step
+    obs_rms, ret_rms = ref_port.RunningMeanStdPort((od,)), ref_port.RunningMeanStdPort(())
+    returns = np.zeros(n, np.float32)
+    snaps = []
+    orig_update = agent._update_phase
+    agent._update_phase = lambda: (snaps.append((agent.memory._obs.cpu().numpy().copy(), agent.memory._rew.cpu().numpy().copy())),
+                                   orig_update())
+    agent.train(2 * T)
+    assert len(raw) == 2 * T and len(snaps) == 2
+    for t in range(2 * T):
+        obs_rms.update(raw[t])                                                         # ppoclip_agent.py:62
+        want = np.clip((raw[t] - obs_rms.mean) / (obs_rms.std + 1e-8), -5, 5)          # agent.py:112-113
+        got = snaps[t // T][0][t % T][:, :od]
+        # a float32 rounding of the mean is amplified by 1 / (std + 1e-8): negligible except while every env still holds
+        # (nearly) the same observation — all envs are seeded alike — and std ~ 0
+        tol = 2e-5 + 4e-6 / (obs_rms.std + 1e-8)
+        assert np.all(np.abs(got - want) <= tol + 2e-5 * np.abs(want)), (t, np.abs(got - want).max())
+        std = np.clip(ret_rms.std, 0.1, 100)                                           # agent.py:119-120, before this step's update
+        want_r = np.clip(rews[t] / std, -5, 5)
+        assert np.allclose(snaps[t // T][1][t % T], want_r, rtol=2e-5, atol=1e-6), t
+        returns = (1 - terms[t]) * 0.98 * returns + rews[t]                            # ppoclip_agent.py:87
+        for i in np.nonzero(terms[t] | truncs[t])[0]:
+            ret_rms.update(returns[i:i + 1])
+            returns[i] = 0.0
+    st = agent._obs_rms[agent._rms_cur].cpu().numpy()
+    D = (st.size - 1) // 2
+    assert agent._defer_norm == (env_id == "Pendulum-v1")
+    if not agent._defer_norm:
+        # the device state already holds the moments of the observations the NEXT step will act on (deferred form: their
+        # partial sums are still waiting for the next rollout forward, which merges them)
+        obs_rms.update(agent._x[agent._cur][:n, :od].cpu().numpy())
+    assert np.allclose(st[:od], obs_rms.mean, rtol=1e-5, atol=1e-6) and np.allclose(st[D:D + od], obs_rms.var, rtol=1e-5, atol=1e-7)
+    assert np.isclose(st[2 * D], obs_rms.count, rtol=1e-12)
+    rs = agent._ret_rms.cpu().numpy()
+    if ret_rms.count > 1:
+        assert np.isclose(rs[0], float(ret_rms.mean), rtol=1e-6) and np.isclose(rs[1], float(ret_rms.var), rtol=1e-5, atol=1e-9)
+        assert np.isclose(rs[2], ret_rms.count, rtol=1e-12)
+    assert np.allclose(agent._returns.cpu().numpy(), returns, rtol=1e-6, atol=1e-6)
+
+
+def test_fused_statistics_path_equals_the_separate_launches(monkeypatch):
+    """XB_FUSED_NORM=0 keeps the four separate launches per step (the path the env-sharded agent uses): same trajectory
+    (CartPole: discrete actions), normalised observations / rewards and statistics within float32 rounding."""
+    from xuanpolicy_b200.configs import build_ppo
+    out = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("XB_FUSED_NORM", fused)
+        agent = build_ppo("CartPole-v1", parallels=128, n_steps=32, n_epoch=1, n_minibatch=2, use_obsnorm=True, use_rewnorm=True,
+                          shuffle="device", seed=5)
+        assert agent._fused_norm == (fused == "1")
+        with torch.cuda.device(agent.device):
+            agent._capture()
+            agent._rollout_graph.replay()
+            agent._rollout_graph.replay()
+        torch.cuda.synchronize()
+        mem = agent.memory
+        # (the observation normaliser's state itself is not comparable: on the fused path it already holds the moments of
+        # the observations the next step will act on; the normalised observations below prove the statistics agree)
+        out.append([t.clone() for t in (mem._act, mem._term, mem._obs, mem._rew, mem._val, agent._ret_rms, agent._returns,
+                                        agent.envs._state)])
+    a, b = out
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[7], b[7])
+    for x, y in zip(a[2:7], b[2:7]):
+        assert torch.allclose(x.double(), y.double(), rtol=1e-5, atol=1e-6), (x.double() - y.double()).abs().max()

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "sample.cuh"
 #include "crtrig.cuh"
+#include "normalize.cuh"
 
 namespace xb {
 
@@ -448,13 +449,24 @@ struct RolloutStepArgs {
     // never-written row (key NaN) just means the values are recomputed.  Halves the correctly-rounded trig work of Pendulum.
     double* trig_cache;
     int64_t N;
+    // optional (stats.partials != NULL): running statistics carried by this launch (normalize.cuh StepStats).  With
+    // stats.obs_state_in set, x_in holds RAW observations and the stored row is their normalised form (the same arithmetic
+    // as the forward kernel's, agent.py:112-113); the next observations' moments are merged into stats.obs_state_out.
+    StepStats stats;
 };
 
 template <class Env>
 __global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs a) {
+    constexpr int V = Env::kObsVec, D = 4 * V;
+    __shared__ double stat_smem[(2 * D + 3) * 32];
+    __shared__ bool stat_flag;
+    const bool with_stats = a.stats.partials != nullptr;
+    double acc[2 * D + 3];
+#pragma unroll
+    for (int k = 0; k < 2 * D + 3; ++k) acc[k] = 0.0;
     const int64_t N = a.N;
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= N) return;
+    if (e < N) {
     // ---- sample (sample.cuh)
     const Philox ph = philox_setup(a.seed, a.counter_dev, a.offset);
     typename Env::action_t act;
@@ -472,8 +484,28 @@ __global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs
     }
     a.logp_out[e] = logp;
     a.logp_row[e] = logp;
+    if (with_stats && a.stats.obs_state_in) {          // stored observation = the normalised one the policy acted on
 #pragma unroll
-    for (int v = 0; v < Env::kObsVec; ++v) a.obs_row[e * Env::kObsVec + v] = a.x_in[e * Env::kObsVec + v];
+        for (int v = 0; v < V; ++v) {
+            const float4 q = a.x_in[e * V + v];
+            const float in[4] = {q.x, q.y, q.z, q.w};
+            float o4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int d = 4 * v + k;
+                float mean, den;
+                o4[k] = 0.f;
+                if (d < a.stats.dim) {
+                    norm_coeffs(a.stats.obs_state_in, D, d, mean, den);
+                    o4[k] = norm_apply(in[k], mean, den, a.stats.obs_clip);
+                }
+            }
+            a.obs_row[e * V + v] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) a.obs_row[e * V + v] = a.x_in[e * V + v];
+    }
     a.val_row[e] = a.val[e];
     if (a.boot_row) a.boot_row[e] = a.boot_src[e];   // V(terminal obs) for envs truncated at step t-1 (ppoclip_agent.py:99)
     // ---- env step (identical arithmetic to env_step_kernel)
@@ -484,7 +516,7 @@ __global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs
     double score = a.ep_score[e];
     bool terminated;
     double reward;
-    float4 o[Env::kObsVec];
+    float4 o[V];
     double sc_s = 0.0, sc_c = 0.0;
     if constexpr (Env::kTrigCache) {
         bool hit = false;
@@ -551,6 +583,33 @@ __global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs
     a.rew_row[e] = r;
     a.term_row[e] = terminated ? 1.0f : 0.0f;
     if (a.trunc_row) a.trunc_row[e] = truncated ? 1 : 0;
+    // ---- running statistics (normalize.cu returns_track_kernel / moments): this env's contributions
+    if (with_stats) {
+        if (a.stats.obs_state_in || (!a.stats.ticket && a.stats.dim > 0)) {   // moments of the observation the policy acts on NEXT
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float in[4] = {o[v].x, o[v].y, o[v].z, o[v].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    acc[4 * v + k] = (double)in[k];
+                    acc[D + 4 * v + k] = (double)in[k] * (double)in[k];
+                }
+            }
+        }
+        if (a.stats.returns) {
+            // (1 - terminals) * gamma * returns + rewards (ppoclip_agent.py:87); A2C: gamma * returns + rewards (a2c_agent.py:85)
+            double R = ((terminated && a.stats.mask_terminal) ? 0.0 : 1.0) * a.stats.gamma * a.stats.returns[e] + (double)r32;
+            if (terminated || truncated) {
+                acc[2 * D] = R;
+                acc[2 * D + 1] = R * R;
+                acc[2 * D + 2] = 1.0;
+                R = 0.0;
+            }
+            a.stats.returns[e] = R;
+        }
+    }
+    }   // e < N
+    if (with_stats) step_stats_finish<D>(a.stats, acc, N, stat_smem, &stat_flag);
 }
 
 __global__ void sincos_kernel(const double* __restrict__ x, double* __restrict__ s, double* __restrict__ c, int64_t n) {
@@ -644,7 +703,10 @@ extern "C" int xb_rollout_step(int env_kind, const float* act_param, const float
                                double* ep_stats, int max_episode_steps, const float* x_in, void* act_out, float* logp_out,
                                float* obs_row, float* act_row, float* rew_row, float* val_row, float* term_row,
                                uint8_t* trunc_row, float* logp_row, const float* rew_scale, float rew_clip,
-                               const float* boot_src, float* boot_row, double* trig_cache, int64_t N, xb_stream_t stream) {
+                               const float* boot_src, float* boot_row, double* trig_cache, const double* obs_state_in,
+                               double* obs_state_out, int obs_dim, float obs_clip, double* ret_state, float* rew_std_io,
+                               double* returns, double gamma, int mask_terminal, double* stat_partials, uint32_t* stat_ticket,
+                               int64_t N, xb_stream_t stream) {
     if (N <= 0 || !act_param || !val || !state || !rng || !elapsed || !ep_score || !obs || !rew || !term || !trunc ||
         !reset_obs || !ep_step_out || !ep_score_out || !x_in || !act_out || !logp_out || !obs_row || !act_row ||
         !rew_row || !val_row || !term_row || !logp_row)
@@ -654,7 +716,16 @@ extern "C" int xb_rollout_step(int env_kind, const float* act_param, const float
     RolloutStepArgs a{act_param, logstd, val, seed, counter_dev, offset, state, rng, elapsed, ep_score, (float4*)obs,
                       (float4*)next_obs, rew, term, trunc, (float4*)reset_obs, ep_step_out, ep_score_out, ep_stats,
                       max_episode_steps, (const float4*)x_in, act_out, logp_out, (float4*)obs_row, act_row, rew_row,
-                      val_row, term_row, trunc_row, logp_row, rew_scale, rew_clip, boot_src, boot_row, trig_cache, N};
+                      val_row, term_row, trunc_row, logp_row, rew_scale, rew_clip, boot_src, boot_row, trig_cache, N, StepStats{}};
+    if (stat_partials) {
+        if (stat_ticket && !obs_state_in && !ret_state) return XB_E_BADARG;
+        if (!stat_ticket && (obs_state_in || obs_state_out || (obs_dim <= 0 && !returns))) return XB_E_BADARG;   // deferred form
+        if (obs_state_in && (!obs_state_out || obs_state_in == obs_state_out || obs_dim < 1 || obs_dim > 8)) return XB_E_BADARG;
+        if (stat_ticket && ((ret_state != nullptr) != (returns != nullptr) || (ret_state && !rew_std_io))) return XB_E_BADARG;
+        if (!stat_ticket && ret_state) return XB_E_BADARG;                   // deferred: the consumer owns the return normaliser
+        a.stats = StepStats{obs_state_in, obs_state_out, obs_dim, obs_clip, ret_state, rew_std_io, returns, gamma, mask_terminal,
+                            stat_partials, stat_ticket};
+    }
     cudaStream_t s = (cudaStream_t)stream;
     int block = env_block(N), grid = ceil_div_i64(N, block);
     if (env_kind == XB_ENV_CARTPOLE) rollout_step_kernel<CartPole><<<grid, block, 0, s>>>(a);

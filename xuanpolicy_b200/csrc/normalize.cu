@@ -12,24 +12,12 @@
 // `rms_normalize` (every thread re-derives the merged statistics — a handful of flops — and normalises its
 // row; one thread publishes the merged state into the OTHER state buffer, so readers never race the writer).
 #include "common.cuh"
+#include "normalize.cuh"
 
 namespace xb {
 
 constexpr int kNormBlock = 256;
 constexpr int kNormMaxGrid = kNumSMs * 8;
-
-// Chan et al. merge, in float32 like numpy does with float32 arrays and weak python scalars.
-__device__ __forceinline__ void chan_merge(float mean, float var, double count, float b_mean, float b_var,
-                                           double b_count, float& new_mean, float& new_var, double& new_count) {
-    const double tot = count + b_count;
-    const float fc = (float)count, fb = (float)b_count, ft = (float)tot;
-    const float delta = b_mean - mean;
-    new_mean = mean + delta * fb / ft;
-    const float m_a = var * fc, m_b = b_var * fb;
-    const float m2 = m_a + m_b + delta * delta * fc * fb / ft;
-    new_var = m2 / ft;
-    new_count = tot;
-}
 
 // sums[0..3] = sum x_d, sums[4..7] = sum x_d^2, sums[8] = N
 __global__ void __launch_bounds__(kNormBlock)
@@ -173,9 +161,104 @@ __global__ void rms_merge_scalar_kernel(const double* __restrict__ sums, double*
     if (rew_std) *rew_std = (float)fmin(fmax(sqrt(state[1]), 0.1), 100.0);
 }
 
+// ---- pieces of the fused-statistics rollout path (normalize.cuh) as launches of their own ----------------------------
+// out[i] = normalise(x[i]) with `state_new` for rows [0, n_new_rows) and `state_old` for the rest; V float4s per row.
+template <int V>
+__global__ void __launch_bounds__(kNormBlock)
+    rms_apply_kernel(const float4* __restrict__ x, int dim, const double* __restrict__ state_new,
+                     const double* __restrict__ state_old, int64_t n_new_rows, float clip, float4* __restrict__ out, int64_t N) {
+    constexpr int D = 4 * V;
+    float mn[D], dn[D], mo[D], dO[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        mn[d] = mo[d] = 0.f;
+        dn[d] = dO[d] = 1.f;
+        if (d < dim) {
+            norm_coeffs(state_new, D, d, mn[d], dn[d]);
+            norm_coeffs(state_old, D, d, mo[d], dO[d]);
+        }
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool nw = i < n_new_rows;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const float4 q = x[i * V + v];
+            const float in[4] = {q.x, q.y, q.z, q.w};
+            float o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int d = 4 * v + k;
+                o[k] = d < dim ? norm_apply(in[k], nw ? mn[d] : mo[d], nw ? dn[d] : dO[d], clip) : 0.f;
+            }
+            out[i * V + v] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+// state_out = state_in merged with the batch moments of rows x[0, N): `obs_rms.update(obs)` as one launch (used once, for
+// the very first observations; afterwards the fused rollout step carries the merge).
+template <int V>
+__global__ void __launch_bounds__(kNormBlock)
+    rms_update_rows_kernel(const float4* __restrict__ x, int64_t N, StepStats s) {
+    constexpr int D = 4 * V;
+    __shared__ double smem[(2 * D + 3) * 32];
+    __shared__ bool flag;
+    double acc[2 * D + 3];
+#pragma unroll
+    for (int k = 0; k < 2 * D + 3; ++k) acc[k] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const float4 q = x[i * V + v];
+            const float in[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                acc[4 * v + k] += (double)in[k];
+                acc[D + 4 * v + k] += (double)in[k] * (double)in[k];
+            }
+        }
+    }
+    step_stats_finish<D>(s, acc, N, smem, &flag);
+}
+
 }  // namespace xb
 
 using namespace xb;
+
+extern "C" int xb_rms_apply(const float* x, int row_floats, int dim, const double* state_new, const double* state_old,
+                            int64_t n_new_rows, float clip, float* out, int64_t N, xb_stream_t stream) {
+    if (N <= 0 || !x || !state_new || !state_old || !out || dim < 1 || dim > row_floats || n_new_rows < 0) return XB_E_BADARG;
+    if (row_floats != 4 && row_floats != 8) return XB_E_UNSUPPORTED;
+    const int grid = grid_for(N, kNormBlock, 2);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (row_floats == 4)
+        rms_apply_kernel<1><<<grid, kNormBlock, 0, s>>>((const float4*)x, dim, state_new, state_old, n_new_rows, clip, (float4*)out, N);
+    else
+        rms_apply_kernel<2><<<grid, kNormBlock, 0, s>>>((const float4*)x, dim, state_new, state_old, n_new_rows, clip, (float4*)out, N);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_rms_update_rows(const float* x, int row_floats, int dim, int64_t N, const double* state_in, double* state_out,
+                                  double* partials, uint32_t* ticket, xb_stream_t stream) {
+    // ticket == NULL: deferred form — only the per-CTA partial sums are written (state_in / state_out unused); the next
+    // xb_mlp_fwd_from_obs merges them (see there)
+    if (N <= 0 || !x || !partials || dim < 1 || dim > row_floats) return XB_E_BADARG;
+    if (ticket && (!state_in || !state_out || state_in == state_out)) return XB_E_BADARG;
+    if (row_floats != 4 && row_floats != 8) return XB_E_UNSUPPORTED;
+    StepStats st{};
+    st.obs_state_in = state_in;
+    st.obs_state_out = state_out;
+    st.dim = dim;
+    st.partials = partials;
+    st.ticket = ticket;
+    const int grid = grid_for(N, kNormBlock, 1);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (row_floats == 4) rms_update_rows_kernel<1><<<grid, kNormBlock, 0, s>>>((const float4*)x, N, st);
+    else rms_update_rows_kernel<2><<<grid, kNormBlock, 0, s>>>((const float4*)x, N, st);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int xb_moments4(const float* x, double* sums, double* workspace, int64_t N, xb_stream_t stream) {
     if (N <= 0 || !x || !sums || !workspace) return XB_E_BADARG;

@@ -1,0 +1,159 @@
+// normalize.cuh — device-side RunningMeanStd pieces shared by normalize.cu, env_classic.cu (fused rollout step) and
+// dense_tc.cu (rollout forward from raw observations).
+//
+// Reference: RunningMeanStd.update / update_from_moments  xuance/common/statistic_tools.py:63-112 (Chan merge)
+//            Agent._process_observation / _process_reward xuance/torch/agents/agent.py:104-123
+//            the per-env discounted-return tracker        ppoclip_agent.py:87,91-92
+// State of an observation normaliser: fp64 [2*D + 1] = mean[D], var[D], count, D = floats per observation ROW (4, or 8
+// for wide rows); mean / var hold float32 values (the reference keeps float32 arrays, statistic_tools.py:46-47).
+// State of the return normaliser: fp64 [3] = mean, var, count (it evolves in float64 in the reference, see normalize.cu).
+#pragma once
+#include "common.cuh"
+
+namespace xb {
+
+constexpr float kNormEps = 1e-8f;   // EPS of xuance/torch/agents/agent.py
+
+// Chan et al. merge, in float32 like numpy does with float32 arrays and weak python scalars.
+__device__ __forceinline__ void chan_merge(float mean, float var, double count, float b_mean, float b_var,
+                                           double b_count, float& new_mean, float& new_var, double& new_count) {
+    const double tot = count + b_count;
+    const float fc = (float)count, fb = (float)b_count, ft = (float)tot;
+    const float delta = b_mean - mean;
+    new_mean = mean + delta * fb / ft;
+    const float m_a = var * fc, m_b = b_var * fb;
+    const float m2 = m_a + m_b + delta * delta * fc * fb / ft;
+    new_var = m2 / ft;
+    new_count = tot;
+}
+
+// np.clip((obs - mean) / (std + EPS), -clip, clip)   (agent.py:112-113), float32 like the reference's arrays
+__device__ __forceinline__ float norm_apply(float v, float mean, float den, float clip) {
+    return fminf(fmaxf((v - mean) / den, -clip), clip);
+}
+__device__ __forceinline__ void norm_coeffs(const double* __restrict__ state, int D, int d, float& mean, float& den) {
+    mean = (float)state[d];
+    den = sqrtf((float)state[D + d]) + kNormEps;
+}
+
+// ---- statistics carried by the fused rollout step (env_classic.cu) ---------------------------------------------------
+// One launch per vector step also (a) merges the NEXT observations' batch moments into the observation normaliser
+// (`obs_rms.update(obs)` of the following loop iteration, ppoclip_agent.py:62), (b) advances the per-env return tracker and
+// merges the finished episodes' returns into the return normaliser (:87-92), publishing the reward divisor of the next
+// step.  Per-CTA partial sums -> ticket -> the last CTA adds them in CTA order (deterministic) and publishes.
+struct StepStats {
+    const double* obs_state_in;   // nullable: S_t, read by every thread (normalises the stored observation)
+    double* obs_state_out;        // S_{t+1} = S_t merged with the next observations' moments (a different buffer)
+    int dim;                      // observation floats (<= 4 * row float4s)
+    float obs_clip;
+    double* ret_state;            // nullable: (mean, var, count) of the return normaliser
+    float* rew_std;               // in: divisor of this step's rewards; out: clip(sqrt(var), 0.1, 100) for the next step
+    double* returns;              // per-env discounted-return tracker (fp64 [N])
+    double gamma;
+    int mask_terminal;            // PPO drops the running return on a terminal (:87); A2C does not (a2c_agent.py:85)
+    double* partials;             // scratch [grid][kStepStatSlots]
+    unsigned int* ticket;         // scratch, self-resetting.  NULL = DEFERRED merge: this launch only writes its per-CTA
+                                  // partials (no fence / atomic / last-CTA tail on the step's critical path); the next
+                                  // rollout forward (dense_tc.cu, xb_mlp_fwd_from_obs) adds them up in its prologue, merges
+                                  // and publishes.  Observation moments are then taken iff dim > 0.
+};
+constexpr int kStepStatSlots = 20;   // 8 sums + 8 sums of squares + (sum R, sum R^2, n finished) + pad
+
+// acc: [0, D) sum x_d | [D, 2D) sum x_d^2 | [2D, 2D+3) finished-return sums.  Called by EVERY thread of the CTA.
+template <int D>
+__device__ __forceinline__ void step_stats_finish(const StepStats& s, double (&acc)[2 * D + 3], int64_t N, double* smem,
+                                                  bool* flag) {
+    constexpr int K = 2 * D + 3;
+    block_sum<K>(acc, smem);
+    if (!s.ticket) {                            // deferred: the consumer reduces
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) s.partials[(int64_t)blockIdx.x * kStepStatSlots + k] = acc[k];
+        }
+        return;
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) s.partials[(int64_t)blockIdx.x * kStepStatSlots + k] = acc[k];
+        __threadfence();
+        *flag = (atomicAdd(s.ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!*flag) return;
+    __threadfence();
+    if (threadIdx.x >= 32) return;              // the rest happens in warp 0
+    {   // lane l adds the partials of CTAs l, l + 32, ... (all loads in flight at once), then a fixed-order butterfly:
+        // the association order depends only on the grid size, so every replay gives the same bits
+        const int lane = threadIdx.x;
+        double t[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) t[k] = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) {
+            const double* p = s.partials + (int64_t)b * kStepStatSlots;
+#pragma unroll
+            for (int k = 0; k < K; ++k) t[k] += __ldcg(p + k);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double v = warp_sum(t[k]);
+            if (lane == 0) smem[k] = v;
+        }
+    }
+    __syncwarp();
+    if (threadIdx.x < D && s.obs_state_in) {
+        const int d = threadIdx.x;
+        float nm = (float)s.obs_state_in[d], nv = (float)s.obs_state_in[D + d];
+        double new_count = s.obs_state_in[2 * D];
+        if (d < s.dim) {
+            const double bn = (double)N, bm = smem[d] / bn;
+            double bv = smem[D + d] / bn - bm * bm;           // np.square(np.std(x, axis=0))
+            bv = bv > 0.0 ? bv : 0.0;
+            chan_merge(nm, nv, s.obs_state_in[2 * D], (float)bm, (float)bv, bn, nm, nv, new_count);
+        }
+        s.obs_state_out[d] = (double)nm;
+        s.obs_state_out[D + d] = (double)nv;
+        if (d == 0) s.obs_state_out[2 * D] = s.obs_state_in[2 * D] + (double)N;
+    }
+    if (threadIdx.x == 0 && s.ret_state) {
+        const double n = smem[2 * D + 2];
+        if (n > 0.0) {
+            const double bm = smem[2 * D] / n;
+            double bv = smem[2 * D + 1] / n - bm * bm;
+            bv = bv > 0.0 ? bv : 0.0;
+            const double count = s.ret_state[2], tot = count + n, delta = bm - s.ret_state[0];   // Chan merge in fp64
+            const double m2 = s.ret_state[1] * count + bv * n + delta * delta * count * n / tot;
+            s.ret_state[0] = s.ret_state[0] + delta * n / tot;
+            s.ret_state[1] = m2 / tot;
+            s.ret_state[2] = tot;
+        }
+        *s.rew_std = (float)fmin(fmax(sqrt(s.ret_state[1]), 0.1), 100.0);     // agent.py:120
+    }
+    if (threadIdx.x == 0) *s.ticket = 0u;
+}
+
+// merged (mean, var) of feature d from the previous state and the batch sums (sum x, sum x^2 over n rows): what
+// step_stats_finish publishes, for consumers that merge by themselves (deferred form)
+__device__ __forceinline__ void merge_feature(const double* __restrict__ state_prev, int D, int d, double sum, double sumsq,
+                                              double n, float& mean, float& var) {
+    const double bm = sum / n;
+    double bv = sumsq / n - bm * bm;
+    bv = bv > 0.0 ? bv : 0.0;
+    double new_count;
+    chan_merge((float)state_prev[d], (float)state_prev[D + d], state_prev[2 * D], (float)bm, (float)bv, n, mean, var, new_count);
+}
+// return normaliser: merges (sum R, sum R^2, n) into state (mean, var, count) in fp64 and publishes the reward divisor
+__device__ __forceinline__ void merge_returns(double* __restrict__ state, double sum, double sumsq, double n, float* rew_std) {
+    if (n > 0.0) {
+        const double bm = sum / n;
+        double bv = sumsq / n - bm * bm;
+        bv = bv > 0.0 ? bv : 0.0;
+        const double count = state[2], tot = count + n, delta = bm - state[0];
+        const double m2 = state[1] * count + bv * n + delta * delta * count * n / tot;
+        state[0] = state[0] + delta * n / tot;
+        state[1] = m2 / tot;
+        state[2] = tot;
+    }
+    *rew_std = (float)fmin(fmax(sqrt(state[1]), 0.1), 100.0);     // agent.py:120
+}
+
+}  // namespace xb

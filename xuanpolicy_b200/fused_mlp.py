@@ -162,16 +162,23 @@ class FusedActorCritic:
                               (g(self.lc1.weight), g(self.lc1.bias), g(self.lc2.weight), g(self.lc2.bias)),
                               self.ws_trunk, self.obs_dim, g(self.l0.weight), g(self.l0.bias), dls64, dls32, norm=norm)
 
-    def forward_inference(self, obs):
+    def fwd_from_obs_ok(self):
+        """True if the one-launch rollout forward (trunk generated in-kernel) covers this policy."""
+        return self.obs_dim <= 4 and self.H <= 128
+
+    def forward_inference(self, obs, norm=None, merge=None):
         """Rollout forward (no activations kept): trunk + both hidden layers + heads in ONE launch for obs_dim <= 4,
-        H <= 128 (the trunk layer is generated inside the kernel); otherwise the training forward without refresh."""
-        if self.obs_dim > 4 or self.H > 128:
+        H <= 128 (the trunk layer is generated inside the kernel); otherwise the training forward without refresh.
+        norm = (state_new, state_old, n_new_rows, clip): `obs` is raw, the kernel normalises it (one-launch form only)."""
+        if not self.fwd_from_obs_ok():
+            assert norm is None and merge is None, "normalise the observations before the multi-launch forward"
             return self.forward(obs, refresh=False)
         B = obs.shape[0]
         b = self._buffers(B)
         ops.mlp_fwd_from_obs(obs, self.l0.weight.data, self.l0.bias.data, self.slope,
                              (self.wa_hi, self.wa_lo, self.la1.bias.data, None, self.la2.weight.data, self.la2.bias.data, b["act"]),
-                             (self.wc_hi, self.wc_lo, self.lc1.bias.data, None, self.lc2.weight.data, self.lc2.bias.data, b["v"]))
+                             (self.wc_hi, self.wc_lo, self.lc1.bias.data, None, self.lc2.weight.data, self.lc2.bias.data, b["v"]),
+                             norm=norm, merge=merge)
         return b["act"], b["v"][:, 0]
 
     # ---------------------------------------------------------------------------------------------- forward / backward

@@ -48,16 +48,23 @@ def env_step(kind, state, rng, elapsed, ep_score, actions, obs, next_obs, rew, t
 def rollout_step(kind, act_param, logstd, val, seed, counter, offset, state, rng, elapsed, ep_score, obs, next_obs, rew,
                  term, trunc, reset_obs, ep_step_out, ep_score_out, ep_stats, max_steps, x_in, act_out, logp_out, obs_row,
                  act_row, rew_row, val_row, term_row, trunc_row, logp_row, rew_std=None, rew_clip=0.0, boot_src=None,
-                 boot_row=None, trig_cache=None):
-    """sample + env step + store of one vector step in one launch (see xb_rollout_step in include/xb200.h)."""
+                 boot_row=None, trig_cache=None, stats=None):
+    """sample + env step + store of one vector step in one launch (see xb_rollout_step in include/xb200.h).
+    `stats` (dict, optional): running statistics carried by the launch — obs_in / obs_out (normaliser states), obs_dim,
+    obs_clip, ret_state, returns, gamma, mask_terminal, partials, ticket; `rew_std` is then also rewritten for the next step."""
     N = elapsed.numel()
+    st = stats or {}
     _lib.call("xb_rollout_step", kind, _p(act_param, F32), _p(logstd, F32), _p(val, F32), int(seed), _p(counter, I64),
               int(offset), _p(state, F64), _p(rng, I64), _p(elapsed, I32), _p(ep_score, F64), _p(obs, F32),
               _p(next_obs, F32), _p(rew, F32), _p(term, U8), _p(trunc, U8), _p(reset_obs, F32), _p(ep_step_out, I32),
               _p(ep_score_out, F64), _p(ep_stats, F64), max_steps, _p(x_in, F32), _p(act_out, F32 if kind == 1 else I64),
               _p(logp_out, F32), _p(obs_row, F32), _p(act_row, F32), _p(rew_row, F32), _p(val_row, F32),
               _p(term_row, F32), _p(trunc_row, U8), _p(logp_row, F32), _p(rew_std, F32), float(rew_clip), _p(boot_src, F32),
-              _p(boot_row, F32), _p(trig_cache, F64), N, _stream())
+              _p(boot_row, F32), _p(trig_cache, F64), _p(st.get("obs_in"), F64), _p(st.get("obs_out"), F64),
+              int(st.get("obs_dim", 0)), float(st.get("obs_clip", 0.0)), _p(st.get("ret_state"), F64),
+              _p(rew_std if st.get("ret_state") is not None else None, F32), _p(st.get("returns"), F64),
+              float(st.get("gamma", 0.0)), int(bool(st.get("mask_terminal", True))), _p(st.get("partials"), F64),
+              _p(st.get("ticket"), I32), N, _stream())
 
 
 def sincos_f64(x):
@@ -260,6 +267,16 @@ def rms_normalize(x, dim, sums, state_in, state_out, clip, out, n_merged_rows):
               _p(out, F32), x.shape[0], int(n_merged_rows), _stream())
 
 
+def rms_apply(x, dim, state_new, state_old, n_new_rows, clip, out):
+    _lib.call("xb_rms_apply", _p(x, F32), x.shape[1], int(dim), _p(state_new, F64), _p(state_old, F64), int(n_new_rows),
+              float(clip), _p(out, F32), x.shape[0], _stream())
+
+
+def rms_update_rows(x, dim, state_in, state_out, partials, ticket):
+    _lib.call("xb_rms_update_rows", _p(x, F32), x.shape[1], int(dim), x.shape[0], _p(state_in, F64), _p(state_out, F64),
+              _p(partials, F64), _p(ticket, I32), _stream())
+
+
 def returns_track(returns, rew, term, trunc, gamma, sums, workspace, mask_terminal=True):
     _lib.call("xb_returns_track", _p(returns, F64), _p(rew, F32), _p(term, U8), _p(trunc, U8), float(gamma),
               1 if mask_terminal else 0, _p(sums, F64), _p(workspace, F64), returns.numel(), _stream())
@@ -339,15 +356,22 @@ def dense_fwd2_loss(x, slope, layer0, layer1, scal, adv_stats, adv_count, clip_r
               _p(dlogstd, F64), _stream())
 
 
-def mlp_fwd_from_obs(obs, w0, b0, slope, layer0, layer1):
-    """Whole actor-critic forward in one launch; layerK = (w_hi, w_lo, bias, y or None, head_w, head_b, head_out)."""
+def mlp_fwd_from_obs(obs, w0, b0, slope, layer0, layer1, norm=None, merge=None):
+    """Whole actor-critic forward in one launch; layerK = (w_hi, w_lo, bias, y or None, head_w, head_b, head_out).
+    norm = (state_new, state_old, n_new_rows, clip): `obs` is raw and is normalised in front of the trunk layer.
+    merge (dict: partials, ctas, obs (bool), state_out, ret_state, rew_std, xn_out): deferred statistics merge, see
+    xb_mlp_fwd_from_obs in include/xb200.h."""
+    nn, no, nr, nc = norm if norm is not None else (None, None, 0, 0.0)
+    mg = merge or {}
     ptr, ld = _rows_ld(obs)
     args = []
     for w_hi, w_lo, bias, y, head_w, head_b, head_out in (layer0, layer1):
         args += [_p(w_hi, F32), _p(w_lo, F32), _p(bias, F32), _p(y, F32), _p(head_w, F32), _p(head_b, F32),
                  head_w.shape[0], _p(head_out, F32)]
     _lib.call("xb_mlp_fwd_from_obs", ptr, ld, obs.shape[1], _p(w0, F32), _p(b0, F32), obs.shape[0], w0.shape[0],
-              float(slope), *args, _stream())
+              float(slope), *args, _p(nn, F64), _p(no, F64), int(nr), float(nc), _p(mg.get("partials"), F64),
+              int(mg.get("ctas", 0)), int(bool(mg.get("obs", False))), _p(mg.get("state_out"), F64), _p(mg.get("ret_state"), F64),
+              _p(mg.get("rew_std"), F32), _p(mg.get("xn_out"), F32), _stream())
 
 
 def dense_dgrad(y0, dout0, w2_0, y1, dout1, w2_1, wt_hi, wt_lo, h1, slope, dz1):
