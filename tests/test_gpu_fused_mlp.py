@@ -307,3 +307,44 @@ def test_fused_loss_epilogue_update_matches_reference_golden(name):
         hi, lo = fused.wa_hi.clone(), fused.wa_lo.clone()
         fused.refresh_weights()
         assert torch.equal(hi, fused.wa_hi) and torch.equal(lo, fused.wa_lo)
+
+
+@pytest.mark.parametrize("env_id,hidden,B", [("Pendulum-v1", 128, 65536), ("CartPole-v1", 128, 4096 + 33), ("Pendulum-v1", 256, 4096)])
+def test_mask_form_dgrad_equals_general_form(env_id, hidden, B):
+    """dgrad with the w2-scaled weight operand and the two-constants-per-row A operand (csrc/dense_tc.cu KParams::mask_form;
+    one head per source, or a softmax pair of logit gradients) against the general form (dz generated element by element):
+    same 3xTF32 product, only the association of the fp32 roundings differs."""
+    import xuanpolicy_b200 as xb
+    from xuanpolicy_b200.fused_mlp import FusedActorCritic
+    from xuanpolicy_b200.learner import FlatAdamState
+    from xuanpolicy_b200.policies import make_policy
+    obs_space, act_space = xb.make_spaces(env_id)
+    policy = make_policy(obs_space, act_space, hidden=(hidden,), device="cuda", seed=4)
+    FlatAdamState(policy, torch.optim.Adam(policy.parameters(), 1e-3), None)
+    fused = FusedActorCritic(policy)
+    g = torch.Generator(device="cuda").manual_seed(B)
+    obs = torch.randn(B, 4, device="cuda", generator=g)[:, :obs_space.shape[0]]
+    fused.forward(obs)
+    assert fused._mask_ready
+    A = fused.A
+    d0 = torch.randn(B, 1, device="cuda", generator=g) / B
+    dact = d0 if A == 1 else torch.cat([d0, -d0], dim=1).contiguous()
+    dv2 = (torch.randn(B, 1, device="cuda", generator=g) / B).contiguous()
+    b = fused._last[1]
+    b["dz1"] = torch.empty(B, hidden, device="cuda")
+    fused.stage_dgrad(b, dact, dv2, softmax_pair=True)
+    masked = b["dz1"].clone()
+    fused._mask_ready = False
+    fused.stage_dgrad(b, dact, dv2, softmax_pair=True)
+    general = b["dz1"].clone()
+    # fp64 reference from the saved activations
+    w = lambda m: m.weight.detach().double()
+    slope = fused.slope
+    mk = lambda y: torch.where(y > 0, 1.0, slope).double()
+    dza = (dact.double() @ w(fused.la2)) * mk(b["ya"])
+    dzc = (dv2.double() @ w(fused.lc2)) * mk(b["yc"])
+    ref = (dza @ w(fused.la1) + dzc @ w(fused.lc1)) * mk(b["h1"])
+    em, eg, ed = _rel(masked, ref), _rel(general, ref), _rel(masked, general.double())
+    print("H=%d B=%d: mask form %.2e, general form %.2e vs fp64; mask vs general %.2e" % (hidden, B, em, eg, ed))
+    bar = 2e-5 if hidden == 128 else 1e-4           # the tensor core truncates its accumulator: the error grows with K = 2H
+    assert em < bar and eg < bar and ed < bar, (em, eg, ed)

@@ -120,8 +120,9 @@ def test_native_rollout_with_obs_and_reward_normalisation():
     assert np.isfinite(info["critic-loss"])
 
 
-@pytest.mark.parametrize("env_id,n", [("CartPole-v1", 96), ("Pendulum-v1", 1200), ("MountainCar-v0", 64), ("Acrobot-v1", 40)])
-def test_fused_statistics_rollout_vs_oracle_normalisers(env_id, n):
+@pytest.mark.parametrize("env_id,n,defer", [("CartPole-v1", 96, False), ("Pendulum-v1", 1200, False), ("Pendulum-v1", 1200, True),
+                                            ("MountainCar-v0", 64, False), ("Acrobot-v1", 40, False)])
+def test_fused_statistics_rollout_vs_oracle_normalisers(env_id, n, defer, monkeypatch):
     """The statistics carried by the fused rollout step (csrc/normalize.cuh: obs moments merged by the step that produces the
     observations, return tracker + return normaliser, reward divisor) and the normalisation done inside the rollout forward
     (Pendulum at 2400 rows: the one-launch tcgen05 forward; the others: xb_rms_apply + torch MLP; MountainCar / Acrobot:
@@ -129,10 +130,12 @@ def test_fused_statistics_rollout_vs_oracle_normalisers(env_id, n):
     run, and against agent.py:104-123 applied with the oracle's statistics of each step."""
     from oracle import ref_port
     from xuanpolicy_b200.configs import build_ppo
+    if defer:      # opt-in variant: the step leaves partial sums, the one-launch forward merges them in its prologue
+        monkeypatch.setenv("XB_DEFER_NORM", "1")
     T = 24 if env_id != "Pendulum-v1" else 210
     agent = build_ppo(env_id, parallels=n, n_steps=T, n_epoch=1, n_minibatch=2, use_obsnorm=True, use_rewnorm=True,
                       use_cuda_graphs=False, shuffle="device", seed=3, gamma=0.98)
-    assert agent._fused_norm and agent._fused_step
+    assert agent._fused_norm and agent._fused_step and agent._defer_norm == defer
     od = agent._obs_dim
     raw, rews, terms, truncs = [], [], [], []
     orig = agent._rollout_step
@@ -169,7 +172,6 @@ def test_fused_statistics_rollout_vs_oracle_normalisers(env_id, n):
             returns[i] = 0.0
     st = agent._obs_rms[agent._rms_cur].cpu().numpy()
     D = (st.size - 1) // 2
-    assert agent._defer_norm == (env_id == "Pendulum-v1")
     if not agent._defer_norm:
         # the device state already holds the moments of the observations the NEXT step will act on (deferred form: their
         # partial sums are still waiting for the next rollout forward, which merges them)

@@ -188,11 +188,13 @@ class PPOCLIP_Agent:
                                       "(single rank, XB_FUSED_STEP / XB_FUSED_NORM on)")
         self._stat_partials = torch.zeros(20 * max(148, N // 32 + 2), **f64)
         self._stat_ticket = torch.zeros(1, dtype=torch.int32, device=dev)
-        # DEFERRED merge: when the rollout forward is the one-launch tcgen05 kernel, the fused step only leaves per-CTA partial
-        # sums and that forward adds them up in its prologue (no fence / atomic / last-CTA tail between the two launches)
+        # DEFERRED merge (opt-in, XB_DEFER_NORM=1): when the rollout forward is the one-launch tcgen05 kernel, the fused step
+        # only leaves per-CTA partial sums and that forward adds them up in its prologue (no fence / atomic / last-CTA tail in
+        # the step kernel).  Measured SLOWER at C2 (3.11 vs 2.96 ms per rollout): the reduction + merge then sits in front of
+        # the forward's first operand tile, which is just as much on the critical path — so the producer-side merge stays.
         fz = self.learner._fused
         self._defer_norm = (self._fused_norm and fz is not None and fz.fwd_from_obs_ok() and 2 * N >= fz.MIN_ROWS
-                            and self.memory.obs_row == 4 and _os.environ.get("XB_DEFER_NORM", "1") != "0")
+                            and self.memory.obs_row == 4 and _os.environ.get("XB_DEFER_NORM", "0") == "1")
         self._step_ctas = -(-N // (32 if N <= 148 * 32 * 2 else (64 if N <= 148 * 64 * 4 else 128)))   # grid of xb_rollout_step
         self._rollout_graph = None
         self._epoch_graph = None

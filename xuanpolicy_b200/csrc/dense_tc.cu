@@ -129,7 +129,39 @@ struct KParams {
     float* dZ1;
     int n_split;        // DGRAD (TS kernels): the N output columns are split over n_split CTAs per tile, each with its
                         // N/n_split weight rows resident in shared memory (instead of streaming all of them per tile)
+    // DGRAD "mask form" (rank-1 head gradients: one head per source, or a 2-logit softmax head whose two gradients are
+    // opposite): dz_s[r][k] = e_s[r] * w2'_s[k] * leaky'(y_s[r][k]) with w2' = w2[0] (- w2[1]).  The column scale w2' moves
+    // into the weight operand (Wt'[n][k] = w2'[k] * W[k][n], prepared by the forward launch, see prep_*), so the A operand
+    // is e_s[r] or slope * e_s[r]: two hi/lo pairs per row and source, selected per element by the sign of y — no per-element
+    // multiply / split in the operand warps.
+    int mask_form;
+    // FWD: optional preparation of that weight operand for the dgrad launch that follows (done by the epilogue warps of
+    // every CTA before their first tile; 2 H^2 elements in total)
+    const float* prep_W[2];     // fp32 master weights [H][H] of the two hidden layers
+    const float* prep_w2[2];    // their head weights [nh][H]
+    int prep_nh[2];
+    float* prep_thi;            // [H][2H]: Wt'[n][s * H + k]
+    float* prep_tlo;
+    int prep_H;
 };
+
+// Wt'[n][s * H + k] = split_tf32(w2'_s[k] * W_s[k][n]) — `tid` in [0, 128), all CTAs share the work.
+__device__ __forceinline__ void prep_dgrad_operand(const KParams& p, int tid) {
+    if (!p.prep_thi) return;
+    const int H = p.prep_H, ldt = 2 * H;
+    const int total = 2 * H * H;
+    for (int i = blockIdx.x * 128 + tid; i < total; i += gridDim.x * 128) {
+        const int s = i / (H * H), j = i - s * H * H;
+        const int n = j / H, k = j - n * H;                 // consecutive threads: consecutive k -> coalesced stores
+        const float* w2 = p.prep_w2[s];
+        float c = w2[k];
+        if (p.prep_nh[s] == 2) c -= w2[H + k];
+        float hi, lo;
+        split_tf32(c * p.prep_W[s][k * H + n], hi, lo);
+        p.prep_thi[n * ldt + s * H + k] = hi;
+        p.prep_tlo[n * ldt + s * H + k] = lo;
+    }
+}
 
 struct TMaps {          // TMA descriptors: A sources, weight hi/lo, output, DGRAD mask tile; *1 = second layer of FWD dual mode
     CUtensorMap a0, a1, bhi, blo, out, h1, bhi1, blo1, out1;
@@ -562,6 +594,21 @@ __global__ void __launch_bounds__(kThreads, 1)
                 float4 xs[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) xs[i] = lds128(a_raw + sw128_off(r0 + 32 * i, c));
+                if (MODE == MODE_DGRAD && p.mask_form) {
+                    // rank-1 head gradients: the operand is e[r] (y > 0) or slope * e[r], split once per row
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = r0 + 32 * i;
+                        const uint32_t off = sw128_off(r, c);
+                        const float e = sdout[(lt & 1) * 512 + r * 4 + src * 2];
+                        float ph, pl, qh, ql;
+                        split_tf32(e, ph, pl);
+                        split_tf32(e * p.slope, qh, ql);
+                        const float4 x = xs[i];
+                        sts128(a_raw + off, make_float4(x.x > 0.f ? ph : qh, x.y > 0.f ? ph : qh, x.z > 0.f ? ph : qh, x.w > 0.f ? ph : qh));
+                        sts128(a_lo + off, make_float4(x.x > 0.f ? pl : ql, x.y > 0.f ? pl : ql, x.z > 0.f ? pl : ql, x.w > 0.f ? pl : ql));
+                    }
+                } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int r = r0 + 32 * i;
@@ -582,6 +629,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                     split_tf32(x.w, hi.w, lo.w);
                     sts128(a_raw + off, hi);
                     sts128(a_lo + off, lo);
+                }
                 }
                 if (t == 0) XB_TS(2, it, 2);
                 fence_proxy_async_smem();
@@ -606,6 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #ifdef XB_DENSE_TS
         c.ts = p.ts;
 #endif
+        if (MODE == MODE_FWD) prep_dgrad_operand(p, threadIdx.x);      // idle until the first accumulator is ready
         epilogue_warp<N, MODE>(c, warp, lane);
     }
 
@@ -1020,6 +1069,14 @@ __global__ void __launch_bounds__(kThreads, 1)
                     d11 = p.nh1 > 1 ? __ldg(p.dout1 + row * p.nh1 + 1) : 0.f;
                 }
             }
+            // mask form: hi/lo of e_s and slope * e_s for this row (e_s = the source's first head gradient)
+            float m0ph = 0.f, m0pl = 0.f, m0qh = 0.f, m0ql = 0.f, m1ph = 0.f, m1pl = 0.f, m1qh = 0.f, m1ql = 0.f;
+            if (MODE == MODE_DGRAD && p.mask_form) {
+                split_tf32(d00, m0ph, m0pl);
+                split_tf32(d00 * p.slope, m0qh, m0ql);
+                split_tf32(d10, m1ph, m1pl);
+                split_tf32(d10 * p.slope, m1qh, m1ql);
+            }
             float o4[4] = {0.f, 0.f, 0.f, 0.f};
             if (from_obs) {
                 const int64_t row = tile * BM + r;
@@ -1064,16 +1121,27 @@ __global__ void __launch_bounds__(kThreads, 1)
                     x[8] = xs[2].x; x[9] = xs[2].y; x[10] = xs[2].z; x[11] = xs[2].w;
                     x[12] = xs[3].x; x[13] = xs[3].y; x[14] = xs[3].z; x[15] = xs[3].w;
                 }
-                if (MODE == MODE_DGRAD) {
-                    const int src = kb >= p.kb_split;
-                    const float* w = sf + src * 512 + (src ? kb - p.kb_split : kb) * BK + 16 * ch;
-                    const float e0 = src ? d10 : d00, e1 = src ? d11 : d01;
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) x[q] = (e0 * w[q] + e1 * w[256 + q]) * (x[q] > 0.f ? 1.f : p.slope);
-                }
                 float hi[16], lo[16];
+                if (MODE == MODE_DGRAD && p.mask_form) {
+                    const int src = kb >= p.kb_split;
+                    const float ph = src ? m1ph : m0ph, pl = src ? m1pl : m0pl, qh = src ? m1qh : m0qh, ql = src ? m1ql : m0ql;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) split_tf32(x[q], hi[q], lo[q]);
+                    for (int q = 0; q < 16; ++q) {
+                        const bool pos = x[q] > 0.f;
+                        hi[q] = pos ? ph : qh;
+                        lo[q] = pos ? pl : ql;
+                    }
+                } else {
+                    if (MODE == MODE_DGRAD) {
+                        const int src = kb >= p.kb_split;
+                        const float* w = sf + src * 512 + (src ? kb - p.kb_split : kb) * BK + 16 * ch;
+                        const float e0 = src ? d10 : d00, e1 = src ? d11 : d01;
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) x[q] = (e0 * w[q] + e1 * w[256 + q]) * (x[q] > 0.f ? 1.f : p.slope);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) split_tf32(x[q], hi[q], lo[q]);
+                }
                 if (threadIdx.x == 128) XB_TS(2, it, 1);
                 {
                     uint32_t ok;
@@ -1113,6 +1181,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #ifdef XB_DENSE_TS
         c.ts = p.ts;
 #endif
+        if (MODE == MODE_FWD) prep_dgrad_operand(p, threadIdx.x);      // idle until the first accumulator is ready
         epilogue_warp<N, MODE>(c, warp, lane);
     }
 
@@ -1675,7 +1744,8 @@ struct TrunkArgs {
 static int dense_fwd_impl(const float* X, const TrunkArgs* trunk, int64_t M, int K, int N, float slope, int n_layers, const float* const* Whi,
                           const float* const* Wlo, const float* const* bias, float* const* Y, const float* const* head_w,
                           const float* const* head_b, const int* n_head, float* const* head_out, int b_resident,
-                          xb_stream_t stream, const FusedLoss* loss = nullptr) {
+                          xb_stream_t stream, const FusedLoss* loss = nullptr, const float* const* prep_W = nullptr,
+                          float* prep_thi = nullptr, float* prep_tlo = nullptr) {
     if ((!X && !trunk) || M <= 0) return XB_E_BADARG;
     if (K % BK != 0 || K < BK || K > 256 || (X && !al16(X))) return XB_E_UNSUPPORTED;
     if (trunk && (!trunk->obs || !trunk->W0 || !trunk->b0 || trunk->obs_dim < 1 || trunk->obs_dim > 4 ||
@@ -1744,6 +1814,17 @@ static int dense_fwd_impl(const float* X, const TrunkArgs* trunk, int64_t M, int
         if (n_layers != 2 || n_head[1] != 1 || n_head[0] != (loss->gaussian ? 1 : 2)) return XB_E_UNSUPPORTED;
         p.loss = *loss;
     }
+    if (prep_thi) {     // weight operand of the mask-form dgrad launch that follows (see KParams::mask_form)
+        if (n_layers != 2 || K != N || !prep_tlo || !prep_W || !prep_W[0] || !prep_W[1] || n_head[0] < 1 || n_head[1] < 1) return XB_E_BADARG;
+        for (int l = 0; l < 2; ++l) {
+            p.prep_W[l] = prep_W[l];
+            p.prep_w2[l] = head_w[l];
+            p.prep_nh[l] = n_head[l];
+        }
+        p.prep_thi = prep_thi;
+        p.prep_tlo = prep_tlo;
+        p.prep_H = N;
+    }
     return dispatch_kmajor<MODE_FWD>(N, b_resident != 0, maps, p, (cudaStream_t)stream);
 }
 
@@ -1758,7 +1839,7 @@ extern "C" int xb_dense_fwd2(const float* X, int64_t M, int K, int N, float slop
                              const float* bias0, float* Y0, const float* head_w0, const float* head_b0, int n_head0,
                              float* head_out0, const float* Whi1, const float* Wlo1, const float* bias1, float* Y1,
                              const float* head_w1, const float* head_b1, int n_head1, float* head_out1, int b_resident,
-                             xb_stream_t stream) {
+                             const float* prep_W0, const float* prep_W1, float* prep_thi, float* prep_tlo, xb_stream_t stream) {
     const float* Whi[2] = {Whi0, Whi1};
     const float* Wlo[2] = {Wlo0, Wlo1};
     const float* bias[2] = {bias0, bias1};
@@ -1767,7 +1848,9 @@ extern "C" int xb_dense_fwd2(const float* X, int64_t M, int K, int N, float slop
     const float* hb[2] = {head_b0, head_b1};
     const int nh[2] = {n_head0, n_head1};
     float* ho[2] = {head_out0, head_out1};
-    return dense_fwd_impl(X, nullptr, M, K, N, slope, 2, Whi, Wlo, bias, Y, hw, hb, nh, ho, b_resident, stream);
+    const float* pw[2] = {prep_W0, prep_W1};
+    return dense_fwd_impl(X, nullptr, M, K, N, slope, 2, Whi, Wlo, bias, Y, hw, hb, nh, ho, b_resident, stream, nullptr, pw,
+                          prep_thi, prep_tlo);
 }
 
 extern "C" int xb_dense_fwd2_loss(const float* X, int64_t M, int K, int N, float slope, const float* Whi0, const float* Wlo0,
@@ -1777,6 +1860,7 @@ extern "C" int xb_dense_fwd2_loss(const float* X, int64_t M, int K, int N, float
                                   const float* scal, const double* adv_stats, int64_t adv_count, float clip_range,
                                   float vf_coef, float ent_coef, float inv_batch, const float* logstd, float* dact, float* dv,
                                   double* loss_partials, uint32_t* loss_ticket, double* scalars, double* dlogstd,
+                                  const float* prep_W0, const float* prep_W1, float* prep_thi, float* prep_tlo,
                                   xb_stream_t stream) {
     if (!scal || !dact || !dv || !loss_partials || !loss_ticket || !scalars) return XB_E_BADARG;
     if (adv_stats && adv_count <= 0) return XB_E_BADARG;
@@ -1792,7 +1876,9 @@ extern "C" int xb_dense_fwd2_loss(const float* X, int64_t M, int K, int N, float
     float* ho[2] = {head_out0, head_out1};
     FusedLoss L{(const float4*)scal, adv_stats, adv_stats ? 1.0 / (double)adv_count : 0.0, clip_range, vf_coef, ent_coef,
                 inv_batch, logstd ? 1 : 0, logstd, dact, dv, loss_partials, loss_ticket, scalars, dlogstd};
-    return dense_fwd_impl(X, nullptr, M, K, N, slope, 2, Whi, Wlo, bias, Y, hw, hb, nh, ho, b_resident, stream, &L);
+    const float* pw[2] = {prep_W0, prep_W1};
+    return dense_fwd_impl(X, nullptr, M, K, N, slope, 2, Whi, Wlo, bias, Y, hw, hb, nh, ho, b_resident, stream, &L, pw, prep_thi,
+                          prep_tlo);
 }
 
 extern "C" int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const float* W0, const float* b0, int64_t M, int H,
@@ -1827,7 +1913,9 @@ extern "C" int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const 
 
 extern "C" int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, int K0, const float* Y1,
                               const float* dout1, const float* w2_1, int nh1, int K1, int64_t M, const float* Wthi,
-                              const float* Wtlo, int N, const float* H1, float slope, float* dZ1, xb_stream_t stream) {
+                              const float* Wtlo, int N, const float* H1, float slope, float* dZ1, int wt_form,
+                              xb_stream_t stream) {
+    if (wt_form != 0 && wt_form != 1) return XB_E_BADARG;
     if (!Y0 || !dout0 || !w2_0 || !Wthi || !Wtlo || !H1 || !dZ1 || M <= 0) return XB_E_BADARG;
     if (K0 % BK != 0 || K0 < BK || K0 > 256 || nh0 < 1 || nh0 > 2) return XB_E_UNSUPPORTED;
     if (Y1 && (K1 % BK != 0 || K1 < BK || K1 > 256 || nh1 < 1 || nh1 > 2 || !dout1 || !w2_1)) return XB_E_UNSUPPORTED;
@@ -1861,6 +1949,7 @@ extern "C" int xb_dense_dgrad(const float* Y0, const float* dout0, const float* 
     p.H1 = H1;
     p.dZ1 = dZ1;
     p.n_split = split ? 2 : 1;
+    p.mask_form = wt_form;
     return dispatch_kmajor<MODE_DGRAD>(N, false, maps, p, (cudaStream_t)stream);
 }
 

@@ -86,6 +86,10 @@ class FusedActorCritic:
         # hi/lo splits of the two H x H layers and their transposes concatenated along the reduction dim (dgrad operand)
         self.wa_hi, self.wa_lo, self.wc_hi, self.wc_lo = z(H, H), z(H, H), z(H, H), z(H, H)
         self.wt_hi, self.wt_lo = z(H, 2 * H), z(H, 2 * H)
+        # mask-form dgrad operand (w2-scaled transposed weights), rewritten by every training forward (stage_hidden)
+        self.wtm_hi, self.wtm_lo = z(H, 2 * H), z(H, 2 * H)
+        self.mask_dgrad = os.environ.get("XB_MASK_DGRAD", "1") != "0"
+        self._mask_ready = False
         self.ws_wgrad = ops.dense_wgrad_workspace(H, dev)
         self.ws_trunk = ops.mlp_trunk_wgrad_workspace(self.obs_dim, H, dev)
         self._buf = {}
@@ -123,8 +127,11 @@ class FusedActorCritic:
         kernel's epilogue — dL/d(act_out) lands in b["dact"], dL/dv in b["dv"]."""
         l0 = (self.wa_hi, self.wa_lo, self.la1.bias.data, b["ya"], self.la2.weight.data, self.la2.bias.data, b["act"])
         l1 = (self.wc_hi, self.wc_lo, self.lc1.bias.data, b["yc"], self.lc2.weight.data, self.lc2.bias.data, b["v"])
+        # the same launch writes the w2-scaled weight operand of the mask-form dgrad that follows (csrc/dense_tc.cu KParams)
+        prep = (self.la1.weight.data, self.lc1.weight.data, self.wtm_hi, self.wtm_lo) if self.mask_dgrad else None
+        self._mask_ready = prep is not None
         if loss is None:
-            ops.dense_fwd2(b["h1"], self.slope, l0, l1)
+            ops.dense_fwd2(b["h1"], self.slope, l0, l1, prep=prep)
             return
         if "dact" not in b:
             B = b["h1"].shape[0]
@@ -132,9 +139,16 @@ class FusedActorCritic:
             b["dv"] = torch.empty(B, 1, dtype=torch.float32, device=self.device)
         ops.dense_fwd2_loss(b["h1"], self.slope, l0, l1, loss["scal"], loss["adv_stats"], loss["adv_count"],
                             loss["clip_range"], loss["vf_coef"], loss["ent_coef"], loss["inv_batch"], loss["logstd"],
-                            b["dact"], b["dv"], self._loss_partials, self._loss_ticket, loss["scalars"], loss["dlogstd"])
+                            b["dact"], b["dv"], self._loss_partials, self._loss_ticket, loss["scalars"], loss["dlogstd"],
+                            prep=prep)
 
-    def stage_dgrad(self, b, dact, dv2):
+    def stage_dgrad(self, b, dact, dv2, softmax_pair=False):
+        """softmax_pair: `dact` [B, 2] are the gradients w.r.t. the two logits of a softmax head (they are opposite), so
+        the actor's head gradient is rank-1 like a one-head source and the mask-form operand applies."""
+        if self._mask_ready and (self.A == 1 or (self.A == 2 and softmax_pair)):
+            ops.dense_dgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, self.wtm_hi, self.wtm_lo,
+                            b["h1"], self.slope, b["dz1"], wt_form=1)
+            return
         ops.dense_dgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, self.wt_hi, self.wt_lo,
                         b["h1"], self.slope, b["dz1"])
 
@@ -200,7 +214,7 @@ class FusedActorCritic:
             return _OutParams(mu=act_out, std=None)
         return _OutParams(logits=act_out)
 
-    def backward(self, dact, dv, dls64=None, dls32=None):
+    def backward(self, dact, dv, dls64=None, dls32=None, softmax_pair=False):
         """dact [B, A], dv [B] = dL/d(act_out), dL/d(v) for the most recent `forward`; writes .grad of the ten
         Linear parameters (views of the flat gradient buffer) — plain stores, no accumulation.  dls64 -> dls32: the
         loss kernel's fp64 log-std gradient, converted in the same tail launch."""
@@ -218,13 +232,13 @@ class FusedActorCritic:
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.device)
             self._side.wait_stream(cur)
-            self.stage_dgrad(b, dact, dv2)
+            self.stage_dgrad(b, dact, dv2, softmax_pair)
             with torch.cuda.stream(self._side):
                 self.stage_wgrad(b, dact, dv2)
             self.stage_trunk_wgrad(obs, b)
             cur.wait_stream(self._side)
         else:
-            self.stage_dgrad(b, dact, dv2)
+            self.stage_dgrad(b, dact, dv2, softmax_pair)
             self.stage_wgrad(b, dact, dv2)
             self.stage_trunk_wgrad(obs, b)
         self.stage_tail(dls64, dls32)

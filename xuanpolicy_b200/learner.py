@@ -167,8 +167,8 @@ class PPOCLIP_Learner:
         """Fused loss fwd+bwd on the network outputs, then the MLP backward: torch autograd (into `.grad`, or — with
         `flat` — straight into the flat gradient buffer) or, with `fused`, the hand-written dgrad/wgrad kernels."""
         backward = torch.autograd.backward if flat is None else flat.backward_into
-        if fused is not None:
-            backward = lambda outs, grads: fused.backward(grads[0], grads[1])
+        if fused is not None:      # (categorical: the loss kernel's two logit gradients are a softmax pair)
+            backward = lambda outs, grads: fused.backward(grads[0], grads[1], softmax_pair=True)
         kind, p0, p1 = _dist_params(a_dist)
         v = v_pred.detach().contiguous()
         dv = torch.empty_like(v)
@@ -317,7 +317,7 @@ class PPOCLIP_Learner:
                 dls32 = flat.grad_views[[id(q) for q in flat.params].index(id(fused.policy.actor.logstd))]
                 fused.backward(b["dact"], b["dv"], self._dls64, dls32)
             else:
-                fused.backward(b["dact"], b["dv"])
+                fused.backward(b["dact"], b["dv"], softmax_pair=True)
             return
         if fused is not None:                        # tcgen05 dense kernels; weights re-split after every Adam step
             act_out, v_pred = fused.forward(mb["obs"], refresh=not fused.splits_fresh, trunk_done=mb.get("trunk_done", False))
