@@ -274,8 +274,7 @@ int xb_rms_merge_scalar(const double* sums, double* state, float* rew_std, xb_st
  *   xb_rms_apply        out = normalise(x) with state_new for rows [0, n_new_rows) and state_old for the rest (no merge):
  *                       the policy input when the MLP runs in torch (xb_mlp_fwd_from_obs normalises by itself)
  *   xb_rms_update_rows  state_out = state_in merged with the batch moments of x [N rows] (`obs_rms.update(obs)`): used once,
- *                       for the very first observations.  partials fp64 [148 * 20], ticket u32 [1] zero-initialised;
- *                       ticket == NULL: deferred form, only the per-CTA partial sums are written (consumer: xb_mlp_fwd_from_obs). */
+ *                       for the very first observations.  partials fp64 [148 * 20], ticket u32 [1] zero-initialised. */
 int xb_rms_apply(const float* x, int row_floats, int dim, const double* state_new, const double* state_old, int64_t n_new_rows,
                  float clip, float* out, int64_t N, xb_stream_t stream);
 int xb_rms_update_rows(const float* x, int row_floats, int dim, int64_t N, const double* state_in, double* state_out,
@@ -416,14 +415,7 @@ int xb_dense_fwd2(const float* X, int64_t M, int K, int N, float slope, const fl
  *                           Y0 / Y1 may both be NULL: only the head outputs are produced.
  *                           norm_new / norm_old (nullable pair, fp64 [9] observation-normaliser states): obs holds RAW
  *                           observations; rows [0, norm_rows) are normalised with norm_new, the rest with norm_old
- *                           (clip((obs - mean) / (sqrt(var) + 1e-8), +-norm_clip), agent.py:112-113) before the trunk layer.
- *                           Deferred statistics merge (st_partials != NULL): the preceding xb_rollout_step was called in its
- *                           deferred form (stat_ticket == NULL) and left st_ctas per-CTA partial sums; every CTA of this
- *                           launch adds them up in its prologue (fixed order), st_obs = 1: merges the observation moments
- *                           into norm_old -> used for rows [0, norm_rows) and published to norm_state_out (!= norm_old) by
- *                           CTA 0 (norm_new is ignored); ret_state (nullable, fp64 [3]) is merged in place with the finished
- *                           returns and rew_std (f32 [1]) republished.  xn_out (nullable, f32 [norm_rows][4]): the
- *                           normalised observations of rows [0, norm_rows) (what the rollout stores as the transition's obs). */
+ *                           (clip((obs - mean) / (sqrt(var) + 1e-8), +-norm_clip), agent.py:112-113) before the trunk layer. */
 /* xb_dense_fwd2 (actor | critic hidden layers + heads) with xb_ppo_loss_* fused into its epilogue: the epilogue thread that
  * holds a row's head outputs turns them straight into dL/d(mu | logits) (actor CTA) and dL/dv (critic CTA) with the formulas of
  * ppoclip_learner.py:33-44 — no loss launch, no round trip of the head outputs.
@@ -446,8 +438,7 @@ int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const float* W0, 
                         const float* head_w0, const float* head_b0, int n_head0, float* head_out0, const float* Whi1,
                         const float* Wlo1, const float* bias1, float* Y1, const float* head_w1, const float* head_b1,
                         int n_head1, float* head_out1, const double* norm_new, const double* norm_old, int64_t norm_rows,
-                        float norm_clip, const double* st_partials, int st_ctas, int st_obs, double* norm_state_out,
-                        double* ret_state, float* rew_std, float* xn_out, xb_stream_t stream);
+                        float norm_clip, xb_stream_t stream);
 int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, int K0, const float* Y1,
                    const float* dout1, const float* w2_1, int nh1, int K1, int64_t M, const float* Wthi,
                    const float* Wtlo, int N, const float* H1, float slope, float* dZ1, int wt_form, xb_stream_t stream);

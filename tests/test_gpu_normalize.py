@@ -113,16 +113,15 @@ def test_native_rollout_with_obs_and_reward_normalisation():
                 returns[i] = 0.0
             ref.obs[done] = o["reset_obs"][done]
     st = agent._obs_rms[0].cpu().numpy()
-    if agent._fused_norm and not agent._defer_norm:      # the fused step already merged the observations the NEXT step will act on
-        obs_rms.update(ref.obs)                          # (deferred form: their partial sums wait for the next forward)
+    if agent._fused_norm:      # the fused step already merged the observations the NEXT step will act on
+        obs_rms.update(ref.obs)
     assert np.allclose(st[:3], obs_rms.mean, rtol=1e-4, atol=2e-5) and abs(st[8] - obs_rms.count) < 1e-6 * obs_rms.count
     info = agent.train(T)
     assert np.isfinite(info["critic-loss"])
 
 
-@pytest.mark.parametrize("env_id,n,defer", [("CartPole-v1", 96, False), ("Pendulum-v1", 1200, False), ("Pendulum-v1", 1200, True),
-                                            ("MountainCar-v0", 64, False), ("Acrobot-v1", 40, False)])
-def test_fused_statistics_rollout_vs_oracle_normalisers(env_id, n, defer, monkeypatch):
+@pytest.mark.parametrize("env_id,n", [("CartPole-v1", 96), ("Pendulum-v1", 1200), ("MountainCar-v0", 64), ("Acrobot-v1", 40)])
+def test_fused_statistics_rollout_vs_oracle_normalisers(env_id, n):
     """The statistics carried by the fused rollout step (csrc/normalize.cuh: obs moments merged by the step that produces the
     observations, return tracker + return normaliser, reward divisor) and the normalisation done inside the rollout forward
     (Pendulum at 2400 rows: the one-launch tcgen05 forward; the others: xb_rms_apply + torch MLP; MountainCar / Acrobot:
@@ -130,12 +129,10 @@ def test_fused_statistics_rollout_vs_oracle_normalisers(env_id, n, defer, monkey
     run, and against agent.py:104-123 applied with the oracle's statistics of each step."""
     from oracle import ref_port
     from xuanpolicy_b200.configs import build_ppo
-    if defer:      # opt-in variant: the step leaves partial sums, the one-launch forward merges them in its prologue
-        monkeypatch.setenv("XB_DEFER_NORM", "1")
     T = 24 if env_id != "Pendulum-v1" else 210
     agent = build_ppo(env_id, parallels=n, n_steps=T, n_epoch=1, n_minibatch=2, use_obsnorm=True, use_rewnorm=True,
                       use_cuda_graphs=False, shuffle="device", seed=3, gamma=0.98)
-    assert agent._fused_norm and agent._fused_step and agent._defer_norm == defer
+    assert agent._fused_norm and agent._fused_step
     od = agent._obs_dim
     raw, rews, terms, truncs = [], [], [], []
     orig = agent._rollout_step
@@ -172,10 +169,8 @@ def test_fused_statistics_rollout_vs_oracle_normalisers(env_id, n, defer, monkey
             returns[i] = 0.0
     st = agent._obs_rms[agent._rms_cur].cpu().numpy()
     D = (st.size - 1) // 2
-    if not agent._defer_norm:
-        # the device state already holds the moments of the observations the NEXT step will act on (deferred form: their
-        # partial sums are still waiting for the next rollout forward, which merges them)
-        obs_rms.update(agent._x[agent._cur][:n, :od].cpu().numpy())
+    # the device state already holds the moments of the observations the NEXT step will act on
+    obs_rms.update(agent._x[agent._cur][:n, :od].cpu().numpy())
     assert np.allclose(st[:od], obs_rms.mean, rtol=1e-5, atol=1e-6) and np.allclose(st[D:D + od], obs_rms.var, rtol=1e-5, atol=1e-7)
     assert np.isclose(st[2 * D], obs_rms.count, rtol=1e-12)
     rs = agent._ret_rms.cpu().numpy()

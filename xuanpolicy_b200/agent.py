@@ -188,14 +188,6 @@ class PPOCLIP_Agent:
                                       "(single rank, XB_FUSED_STEP / XB_FUSED_NORM on)")
         self._stat_partials = torch.zeros(20 * max(148, N // 32 + 2), **f64)
         self._stat_ticket = torch.zeros(1, dtype=torch.int32, device=dev)
-        # DEFERRED merge (opt-in, XB_DEFER_NORM=1): when the rollout forward is the one-launch tcgen05 kernel, the fused step
-        # only leaves per-CTA partial sums and that forward adds them up in its prologue (no fence / atomic / last-CTA tail in
-        # the step kernel).  Measured SLOWER at C2 (3.11 vs 2.96 ms per rollout): the reduction + merge then sits in front of
-        # the forward's first operand tile, which is just as much on the critical path — so the producer-side merge stays.
-        fz = self.learner._fused
-        self._defer_norm = (self._fused_norm and fz is not None and fz.fwd_from_obs_ok() and 2 * N >= fz.MIN_ROWS
-                            and self.memory.obs_row == 4 and _os.environ.get("XB_DEFER_NORM", "0") == "1")
-        self._step_ctas = -(-N // (32 if N <= 148 * 32 * 2 else (64 if N <= 148 * 64 * 4 else 128)))   # grid of xb_rollout_step
         self._rollout_graph = None
         self._epoch_graph = None
         self._stage_graphs = None
@@ -207,13 +199,9 @@ class PPOCLIP_Agent:
         self._x[0][N:].copy_(envs._obs)
         if self._fused_norm and self.use_obsnorm:
             # `obs_rms.update(obs)` for the very first observations (ppoclip_agent.py:62); from here on every fused rollout
-            # step takes the moments of the observations it produces (deferred form: the partial sums wait for the forward)
-            if self._defer_norm:
-                ops.rms_update_rows(self._x[0][:N], obs_dim, None, None, self._stat_partials, None)
-            else:
-                ops.rms_update_rows(self._x[0][:N], obs_dim, self._obs_rms[0], self._obs_rms[1], self._stat_partials,
-                                    self._stat_ticket)
-                self._obs_rms[0].copy_(self._obs_rms[1])
+            # step merges the moments of the observations it produces
+            ops.rms_update_rows(self._x[0][:N], obs_dim, self._obs_rms[0], self._obs_rms[1], self._stat_partials, self._stat_ticket)
+            self._obs_rms[0].copy_(self._obs_rms[1])
 
     @staticmethod
     def _rank():
@@ -221,17 +209,15 @@ class PPOCLIP_Agent:
         return d.get_rank() if (d.is_available() and d.is_initialized()) else 0
 
     # ---------------------------------------------------------------------------------------------- rollout
-    def _policy_forward(self, x, norm=None, merge=None):
+    def _policy_forward(self, x, norm=None):
         """norm = (state_new, state_old, n_new_rows, clip): `x` holds raw observations (fused-statistics path); the
-        one-launch rollout forward normalises them itself, otherwise xb_rms_apply does in front of the MLP.
-        merge: deferred statistics merge carried by the one-launch forward (ops.mlp_fwd_from_obs)."""
+        one-launch rollout forward normalises them itself, otherwise xb_rms_apply does in front of the MLP."""
         fused = self.learner._fused
         if fused is not None and x.shape[0] >= fused.MIN_ROWS:     # weights were split at the start of the rollout
             if norm is not None and not fused.fwd_from_obs_ok():
                 x, norm = self._apply_norm(x, norm), None
-            act_out, v = fused.forward_inference(x[:, :self._obs_dim], norm=norm, merge=merge)
+            act_out, v = fused.forward_inference(x[:, :self._obs_dim], norm=norm)
             return fused.dist_params(act_out), v
-        assert merge is None
         if norm is not None:
             x = self._apply_norm(x, norm)
         _, dist, v = self.policy(x[:, :self._obs_dim])
@@ -263,24 +249,10 @@ class PPOCLIP_Agent:
         N, env, mem = self.n_envs, self.envs, self.memory
         x_cur, x_nxt = self._x[self._cur], self._x[self._cur ^ 1]
         if self._fused_norm:
-            x_store = x_cur
-            if self._defer_norm:
-                # forward(t) adds up the partial sums step t-1 left, merges them into the normalisers (publishing S_t into the
-                # other state buffer and the reward divisor), normalises rows [0, N) with S_t and rows [N, 2N) with S_{t-1}
-                c = self._rms_cur
-                merge = dict(partials=self._stat_partials, ctas=self._step_ctas, obs=self.use_obsnorm)
-                norm = None
-                if self.use_obsnorm:
-                    merge.update(state_out=self._obs_rms[c ^ 1], xn_out=self._xn)
-                    norm = (None, self._obs_rms[c], N, self.obsnorm_range)
-                    x_store = self._xn
-                if self.use_rewnorm:
-                    merge.update(ret_state=self._ret_rms, rew_std=self._rew_std)
-                dist, v = self._policy_forward(x_cur, norm, merge)
-                if self.use_obsnorm:
-                    self._rms_cur ^= 1
-            else:
-                dist, v = self._policy_forward(x_cur, self._obs_norm_args())
+            # (the step kernel folds the moments of the observations it produces into the normaliser: csrc/normalize.cuh.
+            # Leaving only per-CTA partial sums and merging them in the forward's prologue was tried and measured slower, 3.11 vs
+            # 2.96 ms per C2 rollout: the reduction then sits in front of the forward's first operand tile)
+            dist, v = self._policy_forward(x_cur, self._obs_norm_args())
             prm = dist.get_param()
             if self.discrete:
                 act_param, logstd = prm[:N], None
@@ -288,29 +260,23 @@ class PPOCLIP_Agent:
                 act_param = prm[0][:N]
                 logstd = getattr(getattr(self.policy, "actor", None), "logstd", None)
                 logstd = logstd.detach() if logstd is not None else prm[1].log().contiguous()
-            stats = dict(partials=self._stat_partials, gamma=self.gamma, mask_terminal=self._mask_terminal_returns)
-            if self._defer_norm:
-                if self.use_obsnorm:
-                    stats.update(obs_dim=self._obs_dim)
-                if self.use_rewnorm:
-                    stats.update(returns=self._returns)
-            else:
-                stats.update(ticket=self._stat_ticket)
-                if self.use_obsnorm:
-                    c = self._rms_cur
-                    stats.update(obs_in=self._obs_rms[c], obs_out=self._obs_rms[c ^ 1], obs_dim=self._obs_dim,
-                                 obs_clip=self.obsnorm_range)
-                if self.use_rewnorm:
-                    stats.update(ret_state=self._ret_rms, returns=self._returns)
+            stats = dict(partials=self._stat_partials, ticket=self._stat_ticket, gamma=self.gamma,
+                         mask_terminal=self._mask_terminal_returns)
+            if self.use_obsnorm:
+                c = self._rms_cur
+                stats.update(obs_in=self._obs_rms[c], obs_out=self._obs_rms[c ^ 1], obs_dim=self._obs_dim,
+                             obs_clip=self.obsnorm_range)
+            if self.use_rewnorm:
+                stats.update(ret_state=self._ret_rms, returns=self._returns)
             ops.rollout_step(env._kind, act_param, logstd, v[:N], self._sample_seed, self._ctr, t, env._state, env._rng,
                              env._elapsed, env._ep_score, x_nxt[N:], x_nxt[:N], env._rew, env._term, env._trunc,
                              env._reset_obs, env._ep_step_out, env._ep_score_out, env.ep_stats, env.max_episode_length,
-                             x_store[:N], self._act, self._logp, mem._obs[t], mem._act[t], mem._rew[t], mem._val[t],
+                             x_cur[:N], self._act, self._logp, mem._obs[t], mem._act[t], mem._rew[t], mem._val[t],
                              mem._term[t], mem._trunc[t], mem._logp[t],
                              rew_std=self._rew_std if self.use_rewnorm else None, rew_clip=self.rewnorm_range,
                              boot_src=v[N:] if t > 0 else None, boot_row=mem._boot[t - 1] if t > 0 else None,
                              trig_cache=self._trig_cache, stats=stats)
-            if self.use_obsnorm and not self._defer_norm:
+            if self.use_obsnorm:
                 self._rms_cur ^= 1
             self._cur ^= 1
             return
@@ -384,10 +350,7 @@ class PPOCLIP_Agent:
         """The bootstrap forward (:70), the batched GAE for every env and segment (:71-75), counter / ping-pong upkeep."""
         N = self.n_envs
         if self._fused_norm:      # terminal observations of the last step, normalised with that step's statistics
-            norm = self._obs_norm_args()
-            if self._defer_norm and norm is not None:      # the last step's partial sums stay pending for the next rollout
-                norm = (norm[0], norm[0], norm[2], norm[3])
-            _, v = self._policy_forward(self._x[self._cur], norm)
+            _, v = self._policy_forward(self._x[self._cur], self._obs_norm_args())
         else:
             _, v = self._policy_forward(self._normalize_obs(self._x[self._cur], update=False))
         self._boot_last.copy_(v[N:])
@@ -650,8 +613,6 @@ class PPOCLIP_Agent:
                    self._ret_rms, self._returns, self._rew_std]
         if self._norm_peer is not None:
             tensors.append(self._norm_local)      # pending return sums of the last step (merged at the next step)
-        if self._fused_norm:
-            tensors.append(self._stat_partials)   # deferred form: the last step's sums, merged by the next forward
         return [(t, t.clone()) for t in tensors] + [("cur", self._cur)]
 
     def _restore(self, snap):

@@ -101,16 +101,6 @@ struct KParams {
     const double* norm_old;   // rows [norm_rows, M)
     int64_t norm_rows;
     float norm_clip;
-    // deferred statistics merge (normalize.cuh StepStats with ticket == NULL): the previous xb_rollout_step left per-CTA
-    // partial sums; every CTA adds them up in its prologue (fixed order) and derives the merged normaliser itself, CTA 0
-    // publishes it.  norm_old is then the PREVIOUS state; the merged one is used for rows [0, norm_rows).
-    const double* st_partials;   // [st_ctas][kStepStatSlots]; NULL: explicit states above
-    int st_ctas;
-    int st_obs;                  // 1: observation moments present (merge into norm_state_out, normalise rows [0, norm_rows))
-    double* norm_state_out;      // fp64 [9]: merged observation-normaliser state (published by CTA 0)
-    double* ret_state;           // nullable fp64 [3]: return normaliser, merged in place by CTA 0
-    float* rew_std;              // its reward divisor (published by CTA 0)
-    float* xn_out;               // nullable f32 [norm_rows][4]: the normalised observations of rows [0, norm_rows)
     // FWD dual mode: odd CTAs evaluate a second layer on the same input (actor | critic in one launch)
     int dual;
     const float* bias1;
@@ -993,70 +983,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t lane_base = (uint32_t)(32 * lq) << 16;
         uint32_t s = 0, ph = 0, ta = 0, aph = 0, it = 0;
         const bool from_obs = MODE == MODE_FWD && p.obs != nullptr;
-        // observation normalisation in front of the trunk (from_obs): coefficients of the merged (rows < norm_rows) and the
-        // previous (other rows) statistics
-        float nm_mean[4] = {0.f, 0.f, 0.f, 0.f}, nm_den[4] = {1.f, 1.f, 1.f, 1.f};
-        float om_mean[4] = {0.f, 0.f, 0.f, 0.f}, om_den[4] = {1.f, 1.f, 1.f, 1.f};
-        if (from_obs && (p.norm_old || p.st_partials)) {
-            const int t = threadIdx.x - 128;
-            double tot[11];
-#pragma unroll
-            for (int k = 0; k < 11; ++k) tot[k] = 0.0;
-            if (p.st_partials) {
-                // deferred merge: 256 operand threads add the producer's per-CTA partials (thread t takes CTAs t, t + 256, ...;
-                // all loads in flight), warp butterfly, the 8 warps' sums are added in warp order -> every CTA gets the same bits
-                double* red = reinterpret_cast<double*>(sf + 1024);     // [8 warps][11] + [11]
-                double a[11];
-#pragma unroll
-                for (int k = 0; k < 11; ++k) a[k] = 0.0;
-                for (int b = t; b < p.st_ctas; b += kOperandWarps * 32) {
-                    const double* q = p.st_partials + (int64_t)b * kStepStatSlots;
-#pragma unroll
-                    for (int k = 0; k < 11; ++k) a[k] += __ldcg(q + k);
-                }
-#pragma unroll
-                for (int k = 0; k < 11; ++k) {
-                    const double v = warp_sum(a[k]);
-                    if (lane == 0) red[(warp - 4) * 11 + k] = v;
-                }
-                bar_sync_named(1, kOperandWarps * 32);
-#pragma unroll
-                for (int k = 0; k < 11; ++k) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int w = 0; w < kOperandWarps; ++w) v += red[w * 11 + k];
-                    tot[k] = v;
-                }
-            }
-            for (int i = 0; i < p.obs_dim && p.norm_old; ++i) {
-                norm_coeffs(p.norm_old, 4, i, om_mean[i], om_den[i]);
-                if (p.st_partials && p.st_obs) {
-                    float mean, var;
-                    merge_feature(p.norm_old, 4, i, tot[i], tot[4 + i], (double)p.norm_rows, mean, var);
-                    nm_mean[i] = mean;
-                    nm_den[i] = sqrtf(var) + kNormEps;
-                    if (blockIdx.x == 0 && t == 0) {
-                        p.norm_state_out[i] = (double)mean;
-                        p.norm_state_out[4 + i] = (double)var;
-                    }
-                } else if (p.norm_new) {
-                    norm_coeffs(p.norm_new, 4, i, nm_mean[i], nm_den[i]);
-                } else {
-                    nm_mean[i] = om_mean[i];
-                    nm_den[i] = om_den[i];
-                }
-            }
-            if (p.st_partials && blockIdx.x == 0 && t == 0) {
-                if (p.st_obs) {
-                    for (int i = p.obs_dim; i < 4; ++i) {
-                        p.norm_state_out[i] = p.norm_old[i];
-                        p.norm_state_out[4 + i] = p.norm_old[4 + i];
-                    }
-                    p.norm_state_out[8] = p.norm_old[8] + (double)p.norm_rows;
-                }
-                if (p.ret_state) merge_returns(p.ret_state, tot[8], tot[9], tot[10], p.rew_std);
-            }
-        }
         if (!from_obs && tile0 < n_tiles) XB_TRYWAIT_ISSUE(xb_pf, bar_full + 8 * s, ph);    // first stage's phase check
         for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
             float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;   // DGRAD: dL/d(head outputs) of this row
@@ -1082,12 +1008,13 @@ __global__ void __launch_bounds__(kThreads, 1)
                 const int64_t row = tile * BM + r;
                 if (row < p.M) {
                     for (int i = 0; i < p.obs_dim; ++i) o4[i] = __ldg(p.obs + row * p.obs_ld + i);
-                    if (p.norm_old) {
-                        const bool nw = row < p.norm_rows;
-                        for (int i = 0; i < p.obs_dim; ++i)
-                            o4[i] = norm_apply(o4[i], nw ? nm_mean[i] : om_mean[i], nw ? nm_den[i] : om_den[i], p.norm_clip);
-                        if (nw && p.xn_out && sel == 0 && ch == 0)      // one writer per row
-                            reinterpret_cast<float4*>(p.xn_out)[row] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+                    if (p.norm_new) {      // raw observations in: normalise in front of the trunk (agent.py:112-113)
+                        const double* st = row < p.norm_rows ? p.norm_new : p.norm_old;
+                        for (int i = 0; i < p.obs_dim; ++i) {
+                            float mean, den;
+                            norm_coeffs(st, 4, i, mean, den);
+                            o4[i] = norm_apply(o4[i], mean, den, p.norm_clip);
+                        }
                     }
                 }
             }
@@ -1733,12 +1660,6 @@ struct TrunkArgs {
     const double* norm_old;
     int64_t norm_rows;
     float norm_clip;
-    const double* st_partials;
-    int st_ctas, st_obs;
-    double* norm_state_out;
-    double* ret_state;
-    float* rew_std;
-    float* xn_out;
 };
 
 static int dense_fwd_impl(const float* X, const TrunkArgs* trunk, int64_t M, int K, int N, float slope, int n_layers, const float* const* Whi,
@@ -1784,13 +1705,6 @@ static int dense_fwd_impl(const float* X, const TrunkArgs* trunk, int64_t M, int
         p.norm_old = trunk->norm_old;
         p.norm_rows = trunk->norm_rows;
         p.norm_clip = trunk->norm_clip;
-        p.st_partials = trunk->st_partials;
-        p.st_ctas = trunk->st_ctas;
-        p.st_obs = trunk->st_obs;
-        p.norm_state_out = trunk->norm_state_out;
-        p.ret_state = trunk->ret_state;
-        p.rew_std = trunk->rew_std;
-        p.xn_out = trunk->xn_out;
     }
     p.M = M;
     p.KB = K / BK;
@@ -1887,17 +1801,8 @@ extern "C" int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const 
                                    const float* Whi1, const float* Wlo1, const float* bias1, float* Y1,
                                    const float* head_w1, const float* head_b1, int n_head1, float* head_out1,
                                    const double* norm_new, const double* norm_old, int64_t norm_rows, float norm_clip,
-                                   const double* st_partials, int st_ctas, int st_obs, double* norm_state_out,
-                                   double* ret_state, float* rew_std, float* xn_out, xb_stream_t stream) {
-    if (norm_new && !norm_old) return XB_E_BADARG;
-    if (st_partials) {      // deferred statistics merge: norm_old = the previous observation-normaliser state (the anchor)
-        if (st_ctas < 1 || (st_obs && (!norm_old || !norm_state_out || norm_state_out == norm_old)) || (ret_state && !rew_std) ||
-            (!st_obs && !ret_state))
-            return XB_E_BADARG;
-    } else if (norm_state_out || ret_state) {
-        return XB_E_BADARG;
-    }
-    if (xn_out && (!norm_old || ((uintptr_t)xn_out & 15u))) return XB_E_BADARG;
+                                   xb_stream_t stream) {
+    if ((norm_new != nullptr) != (norm_old != nullptr)) return XB_E_BADARG;
     const float* Whi[2] = {Whi0, Whi1};
     const float* Wlo[2] = {Wlo0, Wlo1};
     const float* bias[2] = {bias0, bias1};
@@ -1906,8 +1811,7 @@ extern "C" int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const 
     const float* hb[2] = {head_b0, head_b1};
     const int nh[2] = {n_head0, n_head1};
     float* ho[2] = {head_out0, head_out1};
-    TrunkArgs t{obs, ld, obs_dim, W0, b0, norm_new, norm_old, norm_rows, norm_clip, st_partials, st_ctas, st_obs,
-                norm_state_out, ret_state, rew_std, xn_out};
+    TrunkArgs t{obs, ld, obs_dim, W0, b0, norm_new, norm_old, norm_rows, norm_clip};
     return dense_fwd_impl(nullptr, &t, M, H, H, slope, 2, Whi, Wlo, bias, Y, hw, hb, nh, ho, 1, stream);
 }
 

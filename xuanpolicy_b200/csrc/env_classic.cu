@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs
     if (a.trunc_row) a.trunc_row[e] = truncated ? 1 : 0;
     // ---- running statistics (normalize.cu returns_track_kernel / moments): this env's contributions
     if (with_stats) {
-        if (a.stats.obs_state_in || (!a.stats.ticket && a.stats.dim > 0)) {   // moments of the observation the policy acts on NEXT
+        if (a.stats.obs_state_in) {                     // moments of the observation the policy acts on NEXT
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 const float in[4] = {o[v].x, o[v].y, o[v].z, o[v].w};
@@ -718,11 +718,9 @@ extern "C" int xb_rollout_step(int env_kind, const float* act_param, const float
                       max_episode_steps, (const float4*)x_in, act_out, logp_out, (float4*)obs_row, act_row, rew_row,
                       val_row, term_row, trunc_row, logp_row, rew_scale, rew_clip, boot_src, boot_row, trig_cache, N, StepStats{}};
     if (stat_partials) {
-        if (stat_ticket && !obs_state_in && !ret_state) return XB_E_BADARG;
-        if (!stat_ticket && (obs_state_in || obs_state_out || (obs_dim <= 0 && !returns))) return XB_E_BADARG;   // deferred form
+        if (!stat_ticket || (!obs_state_in && !ret_state)) return XB_E_BADARG;
         if (obs_state_in && (!obs_state_out || obs_state_in == obs_state_out || obs_dim < 1 || obs_dim > 8)) return XB_E_BADARG;
-        if (stat_ticket && ((ret_state != nullptr) != (returns != nullptr) || (ret_state && !rew_std_io))) return XB_E_BADARG;
-        if (!stat_ticket && ret_state) return XB_E_BADARG;                   // deferred: the consumer owns the return normaliser
+        if ((ret_state != nullptr) != (returns != nullptr) || (ret_state && !rew_std_io)) return XB_E_BADARG;
         a.stats = StepStats{obs_state_in, obs_state_out, obs_dim, obs_clip, ret_state, rew_std_io, returns, gamma, mask_terminal,
                             stat_partials, stat_ticket};
     }

@@ -241,10 +241,8 @@ extern "C" int xb_rms_apply(const float* x, int row_floats, int dim, const doubl
 
 extern "C" int xb_rms_update_rows(const float* x, int row_floats, int dim, int64_t N, const double* state_in, double* state_out,
                                   double* partials, uint32_t* ticket, xb_stream_t stream) {
-    // ticket == NULL: deferred form — only the per-CTA partial sums are written (state_in / state_out unused); the next
-    // xb_mlp_fwd_from_obs merges them (see there)
-    if (N <= 0 || !x || !partials || dim < 1 || dim > row_floats) return XB_E_BADARG;
-    if (ticket && (!state_in || !state_out || state_in == state_out)) return XB_E_BADARG;
+    if (N <= 0 || !x || !state_in || !state_out || state_in == state_out || !partials || !ticket || dim < 1 || dim > row_floats)
+        return XB_E_BADARG;
     if (row_floats != 4 && row_floats != 8) return XB_E_UNSUPPORTED;
     StepStats st{};
     st.obs_state_in = state_in;

@@ -52,10 +52,7 @@ struct StepStats {
     double gamma;
     int mask_terminal;            // PPO drops the running return on a terminal (:87); A2C does not (a2c_agent.py:85)
     double* partials;             // scratch [grid][kStepStatSlots]
-    unsigned int* ticket;         // scratch, self-resetting.  NULL = DEFERRED merge: this launch only writes its per-CTA
-                                  // partials (no fence / atomic / last-CTA tail on the step's critical path); the next
-                                  // rollout forward (dense_tc.cu, xb_mlp_fwd_from_obs) adds them up in its prologue, merges
-                                  // and publishes.  Observation moments are then taken iff dim > 0.
+    unsigned int* ticket;         // scratch, self-resetting
 };
 constexpr int kStepStatSlots = 20;   // 8 sums + 8 sums of squares + (sum R, sum R^2, n finished) + pad
 
@@ -65,13 +62,6 @@ __device__ __forceinline__ void step_stats_finish(const StepStats& s, double (&a
                                                   bool* flag) {
     constexpr int K = 2 * D + 3;
     block_sum<K>(acc, smem);
-    if (!s.ticket) {                            // deferred: the consumer reduces
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) s.partials[(int64_t)blockIdx.x * kStepStatSlots + k] = acc[k];
-        }
-        return;
-    }
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < K; ++k) s.partials[(int64_t)blockIdx.x * kStepStatSlots + k] = acc[k];
@@ -129,31 +119,6 @@ __device__ __forceinline__ void step_stats_finish(const StepStats& s, double (&a
         *s.rew_std = (float)fmin(fmax(sqrt(s.ret_state[1]), 0.1), 100.0);     // agent.py:120
     }
     if (threadIdx.x == 0) *s.ticket = 0u;
-}
-
-// merged (mean, var) of feature d from the previous state and the batch sums (sum x, sum x^2 over n rows): what
-// step_stats_finish publishes, for consumers that merge by themselves (deferred form)
-__device__ __forceinline__ void merge_feature(const double* __restrict__ state_prev, int D, int d, double sum, double sumsq,
-                                              double n, float& mean, float& var) {
-    const double bm = sum / n;
-    double bv = sumsq / n - bm * bm;
-    bv = bv > 0.0 ? bv : 0.0;
-    double new_count;
-    chan_merge((float)state_prev[d], (float)state_prev[D + d], state_prev[2 * D], (float)bm, (float)bv, n, mean, var, new_count);
-}
-// return normaliser: merges (sum R, sum R^2, n) into state (mean, var, count) in fp64 and publishes the reward divisor
-__device__ __forceinline__ void merge_returns(double* __restrict__ state, double sum, double sumsq, double n, float* rew_std) {
-    if (n > 0.0) {
-        const double bm = sum / n;
-        double bv = sumsq / n - bm * bm;
-        bv = bv > 0.0 ? bv : 0.0;
-        const double count = state[2], tot = count + n, delta = bm - state[0];
-        const double m2 = state[1] * count + bv * n + delta * delta * count * n / tot;
-        state[0] = state[0] + delta * n / tot;
-        state[1] = m2 / tot;
-        state[2] = tot;
-    }
-    *rew_std = (float)fmin(fmax(sqrt(state[1]), 0.1), 100.0);     // agent.py:120
 }
 
 }  // namespace xb

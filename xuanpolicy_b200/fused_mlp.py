@@ -180,19 +180,19 @@ class FusedActorCritic:
         """True if the one-launch rollout forward (trunk generated in-kernel) covers this policy."""
         return self.obs_dim <= 4 and self.H <= 128
 
-    def forward_inference(self, obs, norm=None, merge=None):
+    def forward_inference(self, obs, norm=None):
         """Rollout forward (no activations kept): trunk + both hidden layers + heads in ONE launch for obs_dim <= 4,
         H <= 128 (the trunk layer is generated inside the kernel); otherwise the training forward without refresh.
         norm = (state_new, state_old, n_new_rows, clip): `obs` is raw, the kernel normalises it (one-launch form only)."""
         if not self.fwd_from_obs_ok():
-            assert norm is None and merge is None, "normalise the observations before the multi-launch forward"
+            assert norm is None, "normalise the observations before the multi-launch forward"
             return self.forward(obs, refresh=False)
         B = obs.shape[0]
         b = self._buffers(B)
         ops.mlp_fwd_from_obs(obs, self.l0.weight.data, self.l0.bias.data, self.slope,
                              (self.wa_hi, self.wa_lo, self.la1.bias.data, None, self.la2.weight.data, self.la2.bias.data, b["act"]),
                              (self.wc_hi, self.wc_lo, self.lc1.bias.data, None, self.lc2.weight.data, self.lc2.bias.data, b["v"]),
-                             norm=norm, merge=merge)
+                             norm=norm)
         return b["act"], b["v"][:, 0]
 
     # ---------------------------------------------------------------------------------------------- forward / backward
