@@ -533,6 +533,9 @@ int xb_random_permutation(int64_t* out, int64_t n, uint64_t seed, const uint64_t
  * index feed, replacing np.random.shuffle(indexes) in PPOCLIP_Agent.train (ppoclip_agent.py:76-78).
  * ---------------------------------------------------------------------------------------------------------- */
 int xb_host_permutation(int64_t* out /* host */, int64_t n, uint64_t seed);
+/* 32-bit flavour (n < 2^31): half the pinned-memory / H2D bytes; above 2^16 indices a cache-friendly two-pass shuffle
+ * (Rao-Sandelius bucket scatter + in-bucket Fisher-Yates), still a uniform random permutation. */
+int xb_host_permutation32(int32_t* out, int64_t n, uint64_t seed);
 
 #ifdef __cplusplus
 }

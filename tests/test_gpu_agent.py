@@ -94,7 +94,7 @@ def test_cartpole_learns(shuffle):
     assert np.isfinite(info["actor-loss"]) and np.isfinite(info["critic-loss"])
     assert first < 40 and late > 2.5 * first, (first, late)
     if shuffle == "host":
-        assert agent.h2d_bytes == 31 * 4 * 256 * 64 * 8
+        assert agent.h2d_bytes == 31 * 4 * 256 * 64 * 4          # int32 permutations, one per epoch
 
 
 @pytest.mark.parametrize("env_id,obsnorm", [("CartPole-v1", True), ("Pendulum-v1", False)])

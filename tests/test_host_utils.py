@@ -39,6 +39,44 @@ def test_host_permutation_is_uniform():
     assert abs(np.mean(disp) / n - 1 / 3) < 0.01
 
 
+def _perm32(n, seed):
+    from xuanpolicy_b200 import _lib
+    out = np.empty(n, np.int32)
+    _lib.call("xb_host_permutation32", out.ctypes.data, n, seed)
+    return out
+
+
+@pytest.mark.parametrize("n", [1, 3, 65536, 65537, 200003, 1 << 21])
+def test_host_permutation32_is_a_permutation_and_reproducible(n):
+    """The e2e feeder's 32-bit shuffle: plain Fisher-Yates up to 2^16 indices, bucket scatter + in-bucket Fisher-Yates above."""
+    p = _perm32(n, 9)
+    assert p.dtype == np.int32 and np.array_equal(np.sort(p), np.arange(n, dtype=np.int32))
+    assert np.array_equal(p, _perm32(n, 9))
+    if n > 16:
+        assert not np.array_equal(p, _perm32(n, 10))
+
+
+def test_host_permutation32_bucketed_regime_is_uniform():
+    """Above 2^16 indices (Rao-Sandelius scatter): the position of a fixed element and the element at a fixed position are
+    uniform over the whole range (chi-square over 32 cells), also ACROSS bucket boundaries, and the mean displacement is n/3."""
+    n, K = 100000, 480
+    first, pos7, disp = [], [], []
+    for k in range(K):
+        p = _perm32(n, 5000 + k)
+        first.append(int(p[0]))
+        pos7.append(int(np.nonzero(p == 7)[0][0]))
+        if k < 40:
+            disp.append(np.mean(np.abs(p.astype(np.int64) - np.arange(n))))
+    for v in (first, pos7):
+        counts = np.bincount(np.asarray(v) * 32 // n, minlength=32)
+        chi2 = float(np.sum((counts - K / 32) ** 2 / (K / 32)))
+        assert chi2 < 66.0, chi2
+    assert abs(np.mean(disp) / n - 1 / 3) < 0.005
+    # neighbours in the input do not stay neighbours: the fraction of i with |p[i+1] - p[i]| == 1 is ~2/n
+    p = _perm32(n, 1)
+    assert np.mean(np.abs(np.diff(p.astype(np.int64))) == 1) < 1e-3
+
+
 def test_old_dist_params_accepts_the_reference_shapes():
     """learner / buffer helper for the {"old_dist": None} auxiliary: a batched wrapper, or the numpy object array of
     per-sample wrappers that split_distributions (xuance/torch/utils/operations.py:53-72) produces."""

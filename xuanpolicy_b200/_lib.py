@@ -43,6 +43,7 @@ SIGNATURES = {
     "xb_sample_gaussian": [_vp, _vp, _i32, _u64, _vp, _u64, _vp, _vp, _i64, _vp],
     "xb_counter_add": [_vp, _u64, _vp],
     "xb_host_permutation": [_vp, _i64, _u64],
+    "xb_host_permutation32": [_vp, _i64, _u64],
     "xb_random_permutation": [_vp, _i64, _u64, _vp, _u64, _vp],
     "xb_moments4": [_vp, _vp, _vp, _i64, _vp],
     "xb_rms_normalize": [_vp, _i32, _vp, _vp, _vp, _f32, _vp, _i64, _i64, _vp],

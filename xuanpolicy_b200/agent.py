@@ -40,19 +40,20 @@ from .spaces import is_discrete
 
 class HostPermutationFeeder:
     """Host side of the minibatch-index feed: the role of `np.random.shuffle(indexes)` (ppoclip_agent.py:76-78).
-    Permutations for rollout k+1 are drawn by worker threads (native xb_host_permutation, GIL released) into
-    pinned staging buffers while the GPU is busy with rollout k; two buffer sets alternate."""
+    Permutations for rollout k+1 are drawn by worker threads (native xb_host_permutation32, GIL released) into
+    pinned int32 staging buffers while the GPU is busy with rollout k; two buffer sets alternate.  32-bit indices halve the
+    pinned memory and the H2D bytes (the device widens them to the int64 the gather kernels take)."""
 
     def __init__(self, n, n_epoch, seed, workers=4):
         from concurrent.futures import ThreadPoolExecutor
         self.n, self.n_epoch, self.seed = n, n_epoch, seed
-        self.sets = [[torch.empty(n, dtype=torch.int64).pin_memory() for _ in range(n_epoch)] for _ in range(2)]
+        self.sets = [[torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(n_epoch)] for _ in range(2)]
         self.pool = ThreadPoolExecutor(max_workers=max(1, workers))
         self.futures = {}
         self.consumed = [None, None]
 
     def _draw(self, buf, seed):
-        _lib.call("xb_host_permutation", buf.data_ptr(), self.n, seed)
+        _lib.call("xb_host_permutation32", buf.data_ptr(), self.n, seed)
         return buf
 
     def prefetch(self, iteration):
@@ -131,15 +132,20 @@ class PPOCLIP_Agent:
         self._perm = torch.zeros(self.buffer_size, dtype=torch.int64, device=dev)
         self._perm_ctr = torch.zeros(1, dtype=torch.int64, device=dev)      # one tick per drawn device permutation
         self._mb_stats_all = torch.zeros(2 * max(1, self.buffer_size // self.batch_size), dtype=torch.float64, device=dev)
-        self._perm_bufs = [self._perm, torch.zeros_like(self._perm)]        # host shuffle: double-buffered H2D target
+        self._perm_bufs = [self._perm, torch.zeros_like(self._perm)]        # host shuffle: double-buffered, widened on device
+        self._perm32 = None
         self._perm_ready, self._perm_free, self._perm_staged = [None, None], [None, None], False
         self._copy_stream = torch.cuda.Stream(device=dev)
         self._epoch_graphs = None
         self._perm_seed = self.seed * 2654435761 + 7919 * self._rank() + 1
         self._feeder = None
         if self.shuffle == "host":
+            import os as _os0
+            local_world = int(_os0.environ.get("LOCAL_WORLD_SIZE", "1"))
+            auto = max(1, min(self.n_epoch, (_os0.cpu_count() or 4) // max(1, local_world)))   # one epoch's draw per thread
             self._feeder = HostPermutationFeeder(self.buffer_size, self.n_epoch, self.seed + 7919 * self._rank(),
-                                                 workers=int(getattr(config, "feeder_threads", 4)))
+                                                 workers=int(getattr(config, "feeder_threads", auto)))
+            self._perm32 = [torch.zeros(self.buffer_size, dtype=torch.int32, device=dev) for _ in range(2)]
             self._feeder.prefetch(0)
         self._iteration = 0
         self._t = 0                        # vector steps already taken in the current (unfinished) rollout
@@ -462,11 +468,12 @@ class PPOCLIP_Agent:
         if self._perm_free[k] is not None:
             cs.wait_event(self._perm_free[k])                      # the epoch that last read this buffer has finished
         with torch.cuda.stream(cs):
-            self._perm_bufs[k].copy_(src, non_blocking=True)       # from pinned memory
+            self._perm32[k].copy_(src, non_blocking=True)          # int32 from pinned memory
+            self._perm_bufs[k].copy_(self._perm32[k])              # widened on the device (copy stream)
             ev = torch.cuda.Event()
             ev.record(cs)
         self._perm_ready[k] = ev
-        self.h2d_bytes += src.numel() * 8
+        self.h2d_bytes += src.numel() * 4
 
     def _update_phase_overlapped(self):
         """Host-shuffle update phase with double-buffered permutations: two captured epoch graphs, one per buffer."""
@@ -497,8 +504,9 @@ class PPOCLIP_Agent:
         for ep in range(self.n_epoch):
             if self.shuffle == "host":
                 src = self._feeder.get(self._iteration, ep)
-                self._perm.copy_(src, non_blocking=True)           # H2D from pinned memory
-                self.h2d_bytes += src.numel() * 8
+                self._perm32[0].copy_(src, non_blocking=True)      # H2D from pinned memory (int32), widened on the device
+                self._perm.copy_(self._perm32[0])
+                self.h2d_bytes += src.numel() * 4
             elif self.world_size > 1 and self.learner._peer is None:   # otherwise drawn inside the epoch graph
                 self._device_permutation()
             if self._epoch_graph is not None:
