@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libxb200.so")
+# XB200_LIB: an alternative build of the same library (e.g. the instrumented one of tools/profile/dense_timeline.py)
+LIB_PATH = os.environ.get("XB200_LIB") or os.path.join(_PKG, "libxb200.so")
 
 _i64, _i32, _f32, _f64, _u64, _vp = C.c_int64, C.c_int, C.c_float, C.c_double, C.c_uint64, C.c_void_p
 

@@ -43,8 +43,8 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def _compile(src, extra, force, log):
-    obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+def _compile(src, extra, force, log, obj_dir=None):
+    obj = os.path.join(obj_dir or OBJ, src.replace(".cu", ".o"))
     deps = [os.path.join(HERE, src)] + [os.path.join(HERE, h) for h in HEADERS]
     if force or _stale(obj, deps):
         cmd = [NVCC] + ARCH + COMMON + extra + ["-c", os.path.join(HERE, src), "-o", obj]
@@ -55,22 +55,25 @@ def _compile(src, extra, force, log):
     return obj
 
 
-def build(force=False, verbose=False):
-    os.makedirs(OBJ, exist_ok=True)
+def build(force=False, verbose=False, out=None, obj_dir=None, extra=()):
+    """`out` / `obj_dir` / `extra`: a second, differently flagged build next to the product library (e.g. the
+    -DXB_DENSE_TS timeline build of tools/profile/dense_timeline.py); the defaults build xuanpolicy_b200/libxb200.so."""
+    out, obj_dir = out or OUT, obj_dir or OBJ
+    os.makedirs(obj_dir, exist_ok=True)
     log = []
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        objs = list(ex.map(lambda kv: _compile(kv[0], kv[1], force, log), SOURCES.items()))
-    if force or _stale(OUT, objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-cudart", "static"]
+        objs = list(ex.map(lambda kv: _compile(kv[0], kv[1] + list(extra), force, log, obj_dir), SOURCES.items()))
+    if force or _stale(out, objs):
+        cmd = [NVCC] + ARCH + ["-shared", "-o", out] + objs + ["-cudart", "static"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s%s" % (r.stdout, r.stderr))
-    with open(os.path.join(OBJ, "build.log"), "a") as f:
+    with open(os.path.join(obj_dir, "build.log"), "a") as f:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

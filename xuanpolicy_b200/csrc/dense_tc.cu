@@ -125,6 +125,10 @@ struct KParams {
     // is e_s[r] or slope * e_s[r]: two hi/lo pairs per row and source, selected per element by the sign of y — no per-element
     // multiply / split in the operand warps.
     int mask_form;
+    // TS kernels: the 8 operand warps work as TWO groups of 4 that convert alternate k-blocks (each warp all 32 k-columns of
+    // its 32 rows) instead of one group of 8 on every k-block (each warp 16 columns): the per-k-block latency chain
+    // (barrier check -> shared-memory read -> split -> tcgen05.st -> wait -> arrive) of one group overlaps the other's.
+    int alt_groups;
     // FWD: optional preparation of that weight operand for the dgrad launch that follows (done by the epilogue warps of
     // every CTA before their first tile; 2 H^2 elements in total)
     const float* prep_W[2];     // fp32 master weights [H][H] of the two hidden layers
@@ -238,8 +242,10 @@ __device__ __forceinline__ void epilogue_warp(const EpiCtx& c, int warp, int lan
             tmem_ld_32x32(taddr + cc * 32, v);
             const bool store = MODE != MODE_FWD || c.store_y;
             // the staging sub-tile about to be overwritten must have been read out by its previous TMA store
-            if (lane == 0 && store) {
-                if (c.O > 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (lane == 0 && store) {       // at most O - 1 of this warp's stores may still be reading their sub-tiles
+                if (c.O > 3) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+                else if (c.O == 3) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+                else if (c.O == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             }
             __syncwarp();
@@ -774,8 +780,6 @@ __device__ __forceinline__ uint32_t ts_kblock(uint32_t d_tmem, uint32_t a_hi, ui
         ".reg .pred pa, pb, p0, p1, c1, c2;\n"
         ".reg .b32 ah, al, r;\n"
         ".reg .b64 bh, bl;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 pa, [%8], %9;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 pb, [%10], %11;\n"
         "setp.ne.b32 p0, %7, 0;\n"
         "setp.ne.b32 p1, 1, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%3], %4, %6, p0;\n"
@@ -785,6 +789,11 @@ __device__ __forceinline__ uint32_t ts_kblock(uint32_t d_tmem, uint32_t a_hi, ui
         "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al], bh, %6, p1;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bl, %6, p1;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bh, %6, p1;\n"
+        // the NEXT k-block's phase checks go out in the middle of the MMA stream (timelines: issued in front of it they
+        // mostly come back "not yet" — the operand warps run less than one k-block ahead — and the blocking re-check then
+        // costs ~300 cycles in which the tensor pipe drains; issued here the remaining six MMAs still cover their latency)
+        "mbarrier.test_wait.parity.shared::cta.b64 pa, [%8], %9;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 pb, [%10], %11;\n"
         "add.u32 ah, %2, 16; add.u32 al, %3, 16; add.u64 bh, %4, 4;  add.u64 bl, %5, 4;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al], bh, %6, p1;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bl, %6, p1;\n"
@@ -855,15 +864,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     float* e_head_out = sel ? p.head_out1 : p.head_out;
 
     if (threadIdx.x == 0) {
+        const int n_conv = p.alt_groups ? kOperandWarps / 2 : kOperandWarps;    // operand warps per k-block
         for (int s = 0; s < S; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, kOperandWarps);          // released by the operand warps once they have read it
+            mbar_init(bar_empty + 8 * s, n_conv);                 // released by the operand warps once they have read it
         }
         for (int a = 0; a < kTA; ++a) {
-            mbar_init(bar_conv + 8 * a, kOperandWarps);
+            mbar_init(bar_conv + 8 * a, n_conv);
             mbar_init(bar_aempty + 8 * a, 1);
         }
-        for (int b = 0; b < 3; ++b) {
+        for (int b = 0; b < 4; ++b) {
             mbar_init(bar_bfull_r + 8 * b, 1);
             mbar_init(bar_bempty + 8 * b, 1);
         }
@@ -983,7 +993,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t lane_base = (uint32_t)(32 * lq) << 16;
         uint32_t s = 0, ph = 0, ta = 0, aph = 0, it = 0;
         const bool from_obs = MODE == MODE_FWD && p.obs != nullptr;
-        if (!from_obs && tile0 < n_tiles) XB_TRYWAIT_ISSUE(xb_pf, bar_full + 8 * s, ph);    // first stage's phase check
+        const bool alt = p.alt_groups != 0;     // ch is then the GROUP (k-block parity) instead of the column half
+        if (!from_obs && !alt && tile0 < n_tiles) XB_TRYWAIT_ISSUE(xb_pf, bar_full + 8 * s, ph);    // first stage's phase check
         for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
             float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;   // DGRAD: dL/d(head outputs) of this row
             if (MODE == MODE_DGRAD) {
@@ -1019,70 +1030,87 @@ __global__ void __launch_bounds__(kThreads, 1)
                 }
             }
             for (int kb = 0; kb < KB; ++kb, ++it) {
-                float x[16];
-                if (from_obs) {                       // trunk layer on the fly: x = leaky(b0 + W0 obs)
-                    XB_TRYWAIT_ISSUE(xb_pa, bar_aempty + 8 * ta, aph ^ 1);
-                    const int K = KB * BK;
-                    const float* w = sf + 3 * N + kb * BK + 16 * ch;
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        float a = w[4 * K + q];
-                        a += o4[0] * w[q];
-                        a += o4[1] * w[K + q];
-                        a += o4[2] * w[2 * K + q];
-                        a += o4[3] * w[3 * K + q];
-                        x[q] = a > 0.f ? a : a * p.slope;
-                    }
-                } else {
+                const uint32_t ns = s + 1 == (uint32_t)S ? 0 : s + 1, nph = s + 1 == (uint32_t)S ? ph ^ 1 : ph;
+                if (alt && (it & 1u) != (uint32_t)ch) {      // the other group's k-block
+                    if (!from_obs) { s = ns; ph = nph; }
+                    if (++ta == kTA) { ta = 0; aph ^= 1; }
+                    continue;
+                }
+                if (alt) {
+                    if (!from_obs) mbar_wait(bar_full + 8 * s, ph);
+                } else if (!from_obs) {
                     uint32_t ok;
                     XB_TRYWAIT_RESULT(xb_pf, ok);                      // issued one k-block ago
                     if (!ok) mbar_wait(bar_full + 8 * s, ph);
-                    if (threadIdx.x == 128) XB_TS(2, it, 0);
-                    const uint32_t a_raw = ring + s * kATile;
-                    float4 xs[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) xs[i] = lds128(a_raw + sw128_off(r, 4 * ch + i));
-                    XB_TRYWAIT_ISSUE(xb_pa, bar_aempty + 8 * ta, aph ^ 1);   // overlaps the transform + split below
-                    x[0] = xs[0].x; x[1] = xs[0].y; x[2] = xs[0].z; x[3] = xs[0].w;
-                    x[4] = xs[1].x; x[5] = xs[1].y; x[6] = xs[1].z; x[7] = xs[1].w;
-                    x[8] = xs[2].x; x[9] = xs[2].y; x[10] = xs[2].z; x[11] = xs[2].w;
-                    x[12] = xs[3].x; x[13] = xs[3].y; x[14] = xs[3].z; x[15] = xs[3].w;
                 }
-                float hi[16], lo[16];
-                if (MODE == MODE_DGRAD && p.mask_form) {
-                    const int src = kb >= p.kb_split;
-                    const float ph = src ? m1ph : m0ph, pl = src ? m1pl : m0pl, qh = src ? m1qh : m0qh, ql = src ? m1ql : m0ql;
+                if (threadIdx.x == 128) XB_TS(2, it, 0);
+                const uint32_t a_raw = ring + s * kATile;
+                const uint32_t acol0 = tmem_base + lane_base + kACol + ta * 64;
+                const int n_half = alt ? 2 : 1;
+                for (int hh = 0; hh < n_half; ++hh) {
+                    const int chh = alt ? hh : ch;             // which 16 of the 32 k-columns
+                    float x[16];
+                    if (from_obs) {                       // trunk layer on the fly: x = leaky(b0 + W0 obs)
+                        if (!alt) XB_TRYWAIT_ISSUE(xb_pa, bar_aempty + 8 * ta, aph ^ 1);
+                        const int K = KB * BK;
+                        const float* w = sf + 3 * N + kb * BK + 16 * chh;
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const bool pos = x[q] > 0.f;
-                        hi[q] = pos ? ph : qh;
-                        lo[q] = pos ? pl : ql;
+                        for (int q = 0; q < 16; ++q) {
+                            float a = w[4 * K + q];
+                            a += o4[0] * w[q];
+                            a += o4[1] * w[K + q];
+                            a += o4[2] * w[2 * K + q];
+                            a += o4[3] * w[3 * K + q];
+                            x[q] = a > 0.f ? a : a * p.slope;
+                        }
+                    } else {
+                        float4 xs[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) xs[i] = lds128(a_raw + sw128_off(r, 4 * chh + i));
+                        if (!alt) XB_TRYWAIT_ISSUE(xb_pa, bar_aempty + 8 * ta, aph ^ 1);   // overlaps the transform + split below
+                        x[0] = xs[0].x; x[1] = xs[0].y; x[2] = xs[0].z; x[3] = xs[0].w;
+                        x[4] = xs[1].x; x[5] = xs[1].y; x[6] = xs[1].z; x[7] = xs[1].w;
+                        x[8] = xs[2].x; x[9] = xs[2].y; x[10] = xs[2].z; x[11] = xs[2].w;
+                        x[12] = xs[3].x; x[13] = xs[3].y; x[14] = xs[3].z; x[15] = xs[3].w;
                     }
-                } else {
-                    if (MODE == MODE_DGRAD) {
+                    float hi[16], lo[16];
+                    if (MODE == MODE_DGRAD && p.mask_form) {
                         const int src = kb >= p.kb_split;
-                        const float* w = sf + src * 512 + (src ? kb - p.kb_split : kb) * BK + 16 * ch;
-                        const float e0 = src ? d10 : d00, e1 = src ? d11 : d01;
+                        const float ph_ = src ? m1ph : m0ph, pl_ = src ? m1pl : m0pl, qh_ = src ? m1qh : m0qh, ql_ = src ? m1ql : m0ql;
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) x[q] = (e0 * w[q] + e1 * w[256 + q]) * (x[q] > 0.f ? 1.f : p.slope);
+                        for (int q = 0; q < 16; ++q) {
+                            const bool pos = x[q] > 0.f;
+                            hi[q] = pos ? ph_ : qh_;
+                            lo[q] = pos ? pl_ : ql_;
+                        }
+                    } else {
+                        if (MODE == MODE_DGRAD) {
+                            const int src = kb >= p.kb_split;
+                            const float* w = sf + src * 512 + (src ? kb - p.kb_split : kb) * BK + 16 * chh;
+                            const float e0 = src ? d10 : d00, e1 = src ? d11 : d01;
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) x[q] = (e0 * w[q] + e1 * w[256 + q]) * (x[q] > 0.f ? 1.f : p.slope);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) split_tf32(x[q], hi[q], lo[q]);
                     }
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) split_tf32(x[q], hi[q], lo[q]);
+                    if (threadIdx.x == 128) XB_TS(2, it, 1);
+                    if (hh == 0) {
+                        if (alt) {
+                            mbar_wait(bar_aempty + 8 * ta, aph ^ 1);
+                        } else {
+                            uint32_t ok;
+                            XB_TRYWAIT_RESULT(xb_pa, ok);
+                            if (!ok) mbar_wait(bar_aempty + 8 * ta, aph ^ 1);
+                        }
+                        if (threadIdx.x == 128) XB_TS(2, it, 2);
+                        // the next raw stage's phase check overlaps the TMEM stores below
+                        if (!from_obs && !alt) XB_TRYWAIT_ISSUE(xb_pf, bar_full + 8 * ns, nph);
+                        tc_fence_after();
+                    }
+                    tmem_st_32x16(acol0 + 16 * chh, hi);
+                    tmem_st_32x16(acol0 + 16 * chh + 32, lo);
                 }
-                if (threadIdx.x == 128) XB_TS(2, it, 1);
-                {
-                    uint32_t ok;
-                    XB_TRYWAIT_RESULT(xb_pa, ok);
-                    if (!ok) mbar_wait(bar_aempty + 8 * ta, aph ^ 1);
-                }
-                if (threadIdx.x == 128) XB_TS(2, it, 2);
-                // the next raw stage's phase check overlaps the TMEM stores below
-                const uint32_t ns = s + 1 == (uint32_t)S ? 0 : s + 1, nph = s + 1 == (uint32_t)S ? ph ^ 1 : ph;
-                if (!from_obs) XB_TRYWAIT_ISSUE(xb_pf, bar_full + 8 * ns, nph);
-                tc_fence_after();
-                const uint32_t acol = tmem_base + lane_base + kACol + ta * 64 + 16 * ch;
-                tmem_st_32x16(acol, hi);
-                tmem_st_32x16(acol + 32, lo);
                 __syncwarp();
                 if (lane == 0 && !from_obs) mbar_arrive(bar_empty + 8 * s);   // the raw tile has been consumed: hand the slot back
                 tmem_st_wait();
@@ -1138,10 +1166,24 @@ static int launch_kmajor_ts(const TMaps& maps, KParams p, cudaStream_t s) {
     if (MODE == MODE_DGRAD) { ++HB; if (bytes() > avail) --HB; }
     while (S < 4) { ++S; if (bytes() > avail) { --S; break; } }
     if (!B_RES) { ++SB; if (bytes() > avail) --SB; }
+    {   // experiment knobs: XB_DENSE_S / XB_DENSE_O override the ring depths when they fit
+        static const int s_env = []() { const char* e = getenv("XB_DENSE_S"); return e ? atoi(e) : 0; }();
+        static const int o_env = []() { const char* e = getenv("XB_DENSE_O"); return e ? atoi(e) : 0; }();
+        static const int sb_env = []() { const char* e = getenv("XB_DENSE_SB"); return e ? atoi(e) : 0; }();
+        static const int hb_env = []() { const char* e = getenv("XB_DENSE_HB"); return e ? atoi(e) : 0; }();
+        const int S0 = S, O0 = O, SB0 = SB, HB0 = HB;
+        if (s_env >= 2 && s_env <= 4) S = s_env;
+        if (o_env >= 1 && o_env <= 4) O = o_env;
+        if (!B_RES && sb_env >= 2 && sb_env <= 4) SB = sb_env;
+        if (MODE == MODE_DGRAD && hb_env >= 1 && hb_env <= 2) HB = hb_env;
+        if (bytes() > avail) { S = S0; O = O0; SB = SB0; HB = HB0; }
+    }
     p.stages = S;
     p.lo_bufs = SB;
     p.out_bufs = O;
     p.h1_bufs = HB;
+    static const int alt_env = []() { const char* e = getenv("XB_DENSE_ALT"); return e ? atoi(e) : -1; }();
+    p.alt_groups = alt_env >= 0 ? alt_env : 0;
 #ifdef XB_DENSE_TS
     p.ts = g_xb_ts_host;
 #endif
