@@ -230,8 +230,8 @@ def count_launches(agent):
             per_rollout += 2 * T + 2
         if agent.use_rewnorm:                           # per step: return tracker + scalar merge
             per_rollout += 2 * T
-    if agent._norm_peer is not None:                    # env-sharded: one statistics exchange per step
-        per_rollout += T
+    if agent._norm_peer is not None:                    # env-sharded: one statistics exchange per step (+ the merge launch)
+        per_rollout += T * (2 if agent._fused_norm else 1)
     return per_rollout + E * (M * per_update + per_epoch)
 
 

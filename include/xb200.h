@@ -279,6 +279,11 @@ int xb_rms_apply(const float* x, int row_floats, int dim, const double* state_ne
                  float clip, float* out, int64_t N, xb_stream_t stream);
 int xb_rms_update_rows(const float* x, int row_floats, int dim, int64_t N, const double* state_in, double* state_out,
                        double* partials, uint32_t* ticket, xb_stream_t stream);
+/*   xb_rms_merge_sums   env-sharded form: sums fp64 [12] = the cross-rank totals of one step (layout of xb_moments4 + the three
+ *                       return sums); obs_state_out = obs_state_in merged with them (nullable pair, 4-float rows), ret_state
+ *                       merged in place and rew_std republished (nullable pair). */
+int xb_rms_merge_sums(const double* sums, const double* obs_state_in, double* obs_state_out, int dim, double* ret_state,
+                      float* rew_std, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Non-GEMM half of the MLP backward (the GEMMs stay in torch/cuBLAS): LeakyReLU' fused with the bias gradient.
@@ -328,7 +333,10 @@ int xb_bias_act_fwd(float* y, const float* bias, float slope, int64_t B, int H, 
  *   ret_state (nullable, fp64 [3]) with rew_std_io (f32 [1]: read as this step's reward divisor — pass the same pointer as
  *     rew_scale — and rewritten for the next step) and returns (fp64 [N] tracker), gamma, mask_terminal (1 = PPO, 0 = A2C);
  *   stat_partials fp64 [grid * 20] / stat_ticket u32 [1] (zero-initialised once): per-CTA sums, added in CTA order by the
- *     last CTA (deterministic).
+ *     last CTA (deterministic);
+ *   stat_sums_out (nullable, fp64 [2D + 4], env-sharded form): this rank's totals (sum x[D], sum x^2[D], N, sum R, sum R^2,
+ *     n finished) are written there INSTEAD of being merged (obs_state_out / ret_state unused); exchange them across ranks
+ *     (xb_peer_allreduce_f64) and merge with xb_rms_merge_sums.
  * ---------------------------------------------------------------------------------------------------------- */
 int xb_rollout_step(int env_kind, const float* act_param, const float* logstd, const float* val, uint64_t seed,
                     const uint64_t* counter_dev, uint64_t offset, double* state, uint64_t* rng, int32_t* elapsed,
@@ -339,7 +347,7 @@ int xb_rollout_step(int env_kind, const float* act_param, const float* logstd, c
                     const float* rew_scale, float rew_clip, const float* boot_src, float* boot_row, double* trig_cache,
                     const double* obs_state_in, double* obs_state_out, int obs_dim, float obs_clip, double* ret_state,
                     float* rew_std_io, double* returns, double gamma, int mask_terminal, double* stat_partials,
-                    uint32_t* stat_ticket, int64_t N, xb_stream_t stream);
+                    uint32_t* stat_ticket, double* stat_sums_out, int64_t N, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Dense layers of the policy/value MLP at large batch on the tcgen05 tensor cores with fp32-level accuracy

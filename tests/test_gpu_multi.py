@@ -68,7 +68,8 @@ if peer is not None:
     allst = [torch.empty_like(st) for _ in range(world)]
     torch.distributed.all_gather(allst, st)
     same_stats = all(torch.equal(allst[0], x) for x in allst)
-    count_ok = abs(float(st[8]) - (1e-4 + 2 * 24 * 96 * world)) < 1e-6       # every env of every rank merged every step
+    merged_steps = 2 * 24 + (1 if a2._fused_norm else 0)   # fused path: the observations of the NEXT step are merged already
+    count_ok = abs(float(st[8]) - (1e-4 + merged_steps * 96 * world)) < 1e-6       # every env of every rank merged every step
     flat2 = a2.learner._flat.flat_param
     g2 = [torch.empty_like(flat2) for _ in range(world)]
     torch.distributed.all_gather(g2, flat2)

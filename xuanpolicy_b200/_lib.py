@@ -20,7 +20,7 @@ SIGNATURES = {
     "xb_env_step": [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp],
     "xb_rollout_step": [_i32, _vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                         _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp,
-                        _vp, _vp, _i32, _f32, _vp, _vp, _vp, _f64, _i32, _vp, _vp, _i64, _vp],
+                        _vp, _vp, _i32, _f32, _vp, _vp, _vp, _f64, _i32, _vp, _vp, _vp, _i64, _vp],
     "xb_sincos_f64": [_vp, _vp, _vp, _i64, _vp],
     "xb_store": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _i64, _vp],
     "xb_gae": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f64, _f64, _i32, _i32, _vp],
@@ -52,6 +52,7 @@ SIGNATURES = {
     "xb_rms_merge_scalar": [_vp, _vp, _vp, _vp],
     "xb_rms_apply": [_vp, _i32, _i32, _vp, _vp, _i64, _f32, _vp, _i64, _vp],
     "xb_rms_update_rows": [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
+    "xb_rms_merge_sums": [_vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "xb_head_fwd": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
     "xb_head_bwd_act": [_vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
     "xb_bias_act_fwd": [_vp, _vp, _f32, _i64, _i32, _vp],

@@ -185,10 +185,13 @@ class PPOCLIP_Agent:
                             ((self.discrete and int(self.action_space.n) == {0: 2, 2: 3, 3: 3, 4: 3}.get(envs._kind, -1)) or
                              (not self.discrete and self.memory.act_dim == 1)))
         # running statistics carried by the fused rollout step (csrc/normalize.cuh StepStats): no moments / normalise /
-        # return-tracker launches per step; the rollout forward normalises the raw observations itself.  Single rank (the
-        # env-sharded form exchanges the per-step moments over peer memory and keeps the separate launches).
-        self._fused_norm = (self._fused_step and self.world_size == 1 and (self.use_obsnorm or self.use_rewnorm)
-                            and _os.environ.get("XB_FUSED_NORM", "1") != "0")
+        # return-tracker launches per step; the rollout forward normalises the raw observations itself.  Env-sharded, the
+        # step writes this rank's sums into the comm block, one peer-memory exchange adds the ranks' sums and a one-warp
+        # launch merges them (every rank keeps the GLOBAL statistics, bit-identical).
+        self._fused_norm = (self._fused_step and (self.use_obsnorm or self.use_rewnorm)
+                            and _os.environ.get("XB_FUSED_NORM", "1") != "0"
+                            and (self.world_size == 1 or (self._norm_peer is not None and self.memory.obs_row == 4)))
+        self._shard_norm = self._fused_norm and self.world_size > 1
         if self.use_obsnorm and not self._fused_norm and self.memory.obs_row != 4:
             raise NotImplementedError("observations wider than 4 floats are normalised on the fused rollout path only "
                                       "(single rank, XB_FUSED_STEP / XB_FUSED_NORM on)")
@@ -206,7 +209,14 @@ class PPOCLIP_Agent:
         if self._fused_norm and self.use_obsnorm:
             # `obs_rms.update(obs)` for the very first observations (ppoclip_agent.py:62); from here on every fused rollout
             # step merges the moments of the observations it produces
-            ops.rms_update_rows(self._x[0][:N], obs_dim, self._obs_rms[0], self._obs_rms[1], self._stat_partials, self._stat_ticket)
+            if self._shard_norm:
+                ops.moments4(self._x[0][:N], self._norm_local[:9], self._obs_ws)
+                ops.peer_allreduce_f64(self._norm_peer, 12, self._norm_global, offset=self._norm_off)
+                ops.rms_merge_sums(self._norm_global, self._obs_rms[0], self._obs_rms[1], obs_dim, None, None)
+                self._norm_local.zero_()
+            else:
+                ops.rms_update_rows(self._x[0][:N], obs_dim, self._obs_rms[0], self._obs_rms[1], self._stat_partials,
+                                    self._stat_ticket)
             self._obs_rms[0].copy_(self._obs_rms[1])
 
     @staticmethod
@@ -274,6 +284,8 @@ class PPOCLIP_Agent:
                              obs_clip=self.obsnorm_range)
             if self.use_rewnorm:
                 stats.update(ret_state=self._ret_rms, returns=self._returns)
+            if self._shard_norm:
+                stats.update(sums_out=self._norm_local)
             ops.rollout_step(env._kind, act_param, logstd, v[:N], self._sample_seed, self._ctr, t, env._state, env._rng,
                              env._elapsed, env._ep_score, x_nxt[N:], x_nxt[:N], env._rew, env._term, env._trunc,
                              env._reset_obs, env._ep_step_out, env._ep_score_out, env.ep_stats, env.max_episode_length,
@@ -282,6 +294,12 @@ class PPOCLIP_Agent:
                              rew_std=self._rew_std if self.use_rewnorm else None, rew_clip=self.rewnorm_range,
                              boot_src=v[N:] if t > 0 else None, boot_row=mem._boot[t - 1] if t > 0 else None,
                              trig_cache=self._trig_cache, stats=stats)
+            if self._shard_norm:      # the ranks' sums of this step -> global sums -> merged normalisers (for the next step)
+                c = self._rms_cur
+                ops.peer_allreduce_f64(self._norm_peer, 12, self._norm_global, offset=self._norm_off)
+                ops.rms_merge_sums(self._norm_global, self._obs_rms[c] if self.use_obsnorm else None,
+                                   self._obs_rms[c ^ 1] if self.use_obsnorm else None, self._obs_dim,
+                                   self._ret_rms if self.use_rewnorm else None, self._rew_std if self.use_rewnorm else None)
             if self.use_obsnorm:
                 self._rms_cur ^= 1
             self._cur ^= 1

@@ -706,7 +706,7 @@ extern "C" int xb_rollout_step(int env_kind, const float* act_param, const float
                                const float* boot_src, float* boot_row, double* trig_cache, const double* obs_state_in,
                                double* obs_state_out, int obs_dim, float obs_clip, double* ret_state, float* rew_std_io,
                                double* returns, double gamma, int mask_terminal, double* stat_partials, uint32_t* stat_ticket,
-                               int64_t N, xb_stream_t stream) {
+                               double* stat_sums_out, int64_t N, xb_stream_t stream) {
     if (N <= 0 || !act_param || !val || !state || !rng || !elapsed || !ep_score || !obs || !rew || !term || !trunc ||
         !reset_obs || !ep_step_out || !ep_score_out || !x_in || !act_out || !logp_out || !obs_row || !act_row ||
         !rew_row || !val_row || !term_row || !logp_row)
@@ -718,11 +718,14 @@ extern "C" int xb_rollout_step(int env_kind, const float* act_param, const float
                       max_episode_steps, (const float4*)x_in, act_out, logp_out, (float4*)obs_row, act_row, rew_row,
                       val_row, term_row, trunc_row, logp_row, rew_scale, rew_clip, boot_src, boot_row, trig_cache, N, StepStats{}};
     if (stat_partials) {
-        if (!stat_ticket || (!obs_state_in && !ret_state)) return XB_E_BADARG;
-        if (obs_state_in && (!obs_state_out || obs_state_in == obs_state_out || obs_dim < 1 || obs_dim > 8)) return XB_E_BADARG;
-        if ((ret_state != nullptr) != (returns != nullptr) || (ret_state && !rew_std_io)) return XB_E_BADARG;
+        if (!stat_ticket || (!obs_state_in && !returns)) return XB_E_BADARG;
+        if (obs_state_in && (obs_dim < 1 || obs_dim > 8)) return XB_E_BADARG;
+        if (!stat_sums_out) {     // merged here: needs the destinations
+            if (obs_state_in && (!obs_state_out || obs_state_in == obs_state_out)) return XB_E_BADARG;
+            if ((ret_state != nullptr) != (returns != nullptr) || (ret_state && !rew_std_io)) return XB_E_BADARG;
+        }
         a.stats = StepStats{obs_state_in, obs_state_out, obs_dim, obs_clip, ret_state, rew_std_io, returns, gamma, mask_terminal,
-                            stat_partials, stat_ticket};
+                            stat_partials, stat_ticket, stat_sums_out};
     }
     cudaStream_t s = (cudaStream_t)stream;
     int block = env_block(N), grid = ceil_div_i64(N, block);

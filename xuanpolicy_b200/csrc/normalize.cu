@@ -221,9 +221,27 @@ __global__ void __launch_bounds__(kNormBlock)
     step_stats_finish<D>(s, acc, N, smem, &flag);
 }
 
+// env-sharded form: `sums` [12] = the cross-rank totals (sum x[4], sum x^2[4], N, sum R, sum R^2, n finished) of one step
+__global__ void rms_merge_sums_kernel(const double* __restrict__ sums, const double* __restrict__ obs_state_in,
+                                      double* __restrict__ obs_state_out, int dim, double* __restrict__ ret_state,
+                                      float* __restrict__ rew_std) {
+    merge_step_stats<4>(obs_state_in, obs_state_out, dim, ret_state, rew_std, sums, sums + 4, sums[8], sums[9], sums[10], sums[11],
+                        threadIdx.x);
+}
+
 }  // namespace xb
 
 using namespace xb;
+
+extern "C" int xb_rms_merge_sums(const double* sums, const double* obs_state_in, double* obs_state_out, int dim,
+                                 double* ret_state, float* rew_std, xb_stream_t stream) {
+    if (!sums || (!obs_state_in && !ret_state) || (obs_state_in && (!obs_state_out || obs_state_in == obs_state_out || dim < 1 || dim > 4)) ||
+        (ret_state && !rew_std))
+        return XB_E_BADARG;
+    rms_merge_sums_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, obs_state_in, obs_state_out, dim, ret_state, rew_std);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int xb_rms_apply(const float* x, int row_floats, int dim, const double* state_new, const double* state_old,
                             int64_t n_new_rows, float clip, float* out, int64_t N, xb_stream_t stream) {
@@ -250,6 +268,7 @@ extern "C" int xb_rms_update_rows(const float* x, int row_floats, int dim, int64
     st.dim = dim;
     st.partials = partials;
     st.ticket = ticket;
+    st.sums_out = nullptr;
     const int grid = grid_for(N, kNormBlock, 1);
     cudaStream_t s = (cudaStream_t)stream;
     if (row_floats == 4) rms_update_rows_kernel<1><<<grid, kNormBlock, 0, s>>>((const float4*)x, N, st);

@@ -53,8 +53,47 @@ struct StepStats {
     int mask_terminal;            // PPO drops the running return on a terminal (:87); A2C does not (a2c_agent.py:85)
     double* partials;             // scratch [grid][kStepStatSlots]
     unsigned int* ticket;         // scratch, self-resetting
+    double* sums_out;             // nullable (env-sharded form): the last CTA writes THIS RANK's totals [2D + 4] = sum x[D],
+                                  // sum x^2[D], N, (sum R, sum R^2, n finished) there instead of merging; the ranks' sums are
+                                  // then exchanged (peer_comm.cu) and merged by xb_rms_merge_sums
 };
 constexpr int kStepStatSlots = 20;   // 8 sums + 8 sums of squares + (sum R, sum R^2, n finished) + pad
+
+// Merges batch sums into the two normalisers (threads 0..D-1 of one warp): observation state_in -> state_out (Chan, float32,
+// statistic_tools.py:101-112) from (sum x, sum x^2) over n rows; return state in place (fp64) from (sum R, sum R^2, n_ret),
+// publishing the reward divisor clip(sqrt(var), 0.1, 100) (agent.py:119-120).
+template <int D>
+__device__ __forceinline__ void merge_step_stats(const double* obs_state_in, double* obs_state_out, int dim, double* ret_state,
+                                                 float* rew_std, const double* sum, const double* sumsq, double n, double r_sum,
+                                                 double r_sumsq, double r_n, int tid) {
+    if (tid < D && obs_state_in) {
+        const int d = tid;
+        float nm = (float)obs_state_in[d], nv = (float)obs_state_in[D + d];
+        double new_count = obs_state_in[2 * D];
+        if (d < dim) {
+            const double bm = sum[d] / n;
+            double bv = sumsq[d] / n - bm * bm;           // np.square(np.std(x, axis=0))
+            bv = bv > 0.0 ? bv : 0.0;
+            chan_merge(nm, nv, obs_state_in[2 * D], (float)bm, (float)bv, n, nm, nv, new_count);
+        }
+        obs_state_out[d] = (double)nm;
+        obs_state_out[D + d] = (double)nv;
+        if (d == 0) obs_state_out[2 * D] = obs_state_in[2 * D] + n;
+    }
+    if (tid == 0 && ret_state) {
+        if (r_n > 0.0) {
+            const double bm = r_sum / r_n;
+            double bv = r_sumsq / r_n - bm * bm;
+            bv = bv > 0.0 ? bv : 0.0;
+            const double count = ret_state[2], tot = count + r_n, delta = bm - ret_state[0];   // Chan merge in fp64
+            const double m2 = ret_state[1] * count + bv * r_n + delta * delta * count * r_n / tot;
+            ret_state[0] = ret_state[0] + delta * r_n / tot;
+            ret_state[1] = m2 / tot;
+            ret_state[2] = tot;
+        }
+        *rew_std = (float)fmin(fmax(sqrt(ret_state[1]), 0.1), 100.0);     // agent.py:120
+    }
+}
 
 // acc: [0, D) sum x_d | [D, 2D) sum x_d^2 | [2D, 2D+3) finished-return sums.  Called by EVERY thread of the CTA.
 template <int D>
@@ -90,33 +129,17 @@ __device__ __forceinline__ void step_stats_finish(const StepStats& s, double (&a
         }
     }
     __syncwarp();
-    if (threadIdx.x < D && s.obs_state_in) {
-        const int d = threadIdx.x;
-        float nm = (float)s.obs_state_in[d], nv = (float)s.obs_state_in[D + d];
-        double new_count = s.obs_state_in[2 * D];
-        if (d < s.dim) {
-            const double bn = (double)N, bm = smem[d] / bn;
-            double bv = smem[D + d] / bn - bm * bm;           // np.square(np.std(x, axis=0))
-            bv = bv > 0.0 ? bv : 0.0;
-            chan_merge(nm, nv, s.obs_state_in[2 * D], (float)bm, (float)bv, bn, nm, nv, new_count);
+    if (s.sums_out) {
+        if (threadIdx.x < 2 * D) s.sums_out[threadIdx.x] = smem[threadIdx.x];
+        if (threadIdx.x == 0) {
+            s.sums_out[2 * D] = (double)N;
+            s.sums_out[2 * D + 1] = smem[2 * D];
+            s.sums_out[2 * D + 2] = smem[2 * D + 1];
+            s.sums_out[2 * D + 3] = smem[2 * D + 2];
         }
-        s.obs_state_out[d] = (double)nm;
-        s.obs_state_out[D + d] = (double)nv;
-        if (d == 0) s.obs_state_out[2 * D] = s.obs_state_in[2 * D] + (double)N;
-    }
-    if (threadIdx.x == 0 && s.ret_state) {
-        const double n = smem[2 * D + 2];
-        if (n > 0.0) {
-            const double bm = smem[2 * D] / n;
-            double bv = smem[2 * D + 1] / n - bm * bm;
-            bv = bv > 0.0 ? bv : 0.0;
-            const double count = s.ret_state[2], tot = count + n, delta = bm - s.ret_state[0];   // Chan merge in fp64
-            const double m2 = s.ret_state[1] * count + bv * n + delta * delta * count * n / tot;
-            s.ret_state[0] = s.ret_state[0] + delta * n / tot;
-            s.ret_state[1] = m2 / tot;
-            s.ret_state[2] = tot;
-        }
-        *s.rew_std = (float)fmin(fmax(sqrt(s.ret_state[1]), 0.1), 100.0);     // agent.py:120
+    } else {
+        merge_step_stats<D>(s.obs_state_in, s.obs_state_out, s.dim, s.ret_state, s.rew_std, smem, smem + D, (double)N,
+                            smem[2 * D], smem[2 * D + 1], smem[2 * D + 2], threadIdx.x);
     }
     if (threadIdx.x == 0) *s.ticket = 0u;
 }

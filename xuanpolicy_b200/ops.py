@@ -62,9 +62,9 @@ def rollout_step(kind, act_param, logstd, val, seed, counter, offset, state, rng
               _p(term_row, F32), _p(trunc_row, U8), _p(logp_row, F32), _p(rew_std, F32), float(rew_clip), _p(boot_src, F32),
               _p(boot_row, F32), _p(trig_cache, F64), _p(st.get("obs_in"), F64), _p(st.get("obs_out"), F64),
               int(st.get("obs_dim", 0)), float(st.get("obs_clip", 0.0)), _p(st.get("ret_state"), F64),
-              _p(rew_std if st.get("ret_state") is not None else None, F32), _p(st.get("returns"), F64),
+              _p(rew_std if st.get("returns") is not None else None, F32), _p(st.get("returns"), F64),
               float(st.get("gamma", 0.0)), int(bool(st.get("mask_terminal", True))), _p(st.get("partials"), F64),
-              _p(st.get("ticket"), I32), N, _stream())
+              _p(st.get("ticket"), I32), _p(st.get("sums_out"), F64), N, _stream())
 
 
 def sincos_f64(x):
@@ -275,6 +275,11 @@ def rms_apply(x, dim, state_new, state_old, n_new_rows, clip, out):
 def rms_update_rows(x, dim, state_in, state_out, partials, ticket):
     _lib.call("xb_rms_update_rows", _p(x, F32), x.shape[1], int(dim), x.shape[0], _p(state_in, F64), _p(state_out, F64),
               _p(partials, F64), _p(ticket, I32), _stream())
+
+
+def rms_merge_sums(sums, obs_in, obs_out, dim, ret_state, rew_std):
+    _lib.call("xb_rms_merge_sums", _p(sums, F64), _p(obs_in, F64), _p(obs_out, F64), int(dim), _p(ret_state, F64),
+              _p(rew_std, F32), _stream())
 
 
 def returns_track(returns, rew, term, trunc, gamma, sums, workspace, mask_terminal=True):
