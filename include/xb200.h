@@ -470,6 +470,13 @@ int xb_mlp_trunk_wgrad_workspace_floats(int obs_dim, int H);
 int xb_mlp_trunk_wgrad_parts(void);     /* number of partial sums per output in the workspace */
 int xb_mlp_trunk_wgrad(const float* dz1, const float* obs, int ld, int obs_dim, float* workspace, float* dW0, float* db0,
                        int64_t B, int H, xb_stream_t stream);
+/* Discrete(3) actor heads on the two-head dense kernels (MountainCar-v0 / Acrobot-v1; categorical.py:26-32 is generic in
+ * action_dim): softmax(z0, z1, z2) == softmax(z0 - z2, z1 - z2, 0), so the kernels run with FOLDED head parameters
+ *   xb_head3_fold           w2[j] = w3[j] - w3[2], b2[j] = b3[j] - b3[2] (j = 0, 1);  w3 f32 [3][H], w2 f32 [2][H]
+ *   xb_head3_unfold_grads   rows 0, 1 of gw3 [3][H] / gb3 [3] hold the two-head gradients; row 2 = -(row 0 + row 1)
+ * (dL/dz2 = -(dL/dz0 + dL/dz1) for any loss of the softmax).  The third logit is reported as 0. */
+int xb_head3_fold(const float* w3, const float* b3, float* w2, float* b2, int H, xb_stream_t stream);
+int xb_head3_unfold_grads(float* gw3, float* gb3, int H, xb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * (5b) Env-sharded data parallelism over NVLink / NVSwitch PEER MEMORY: the two exchanges of an

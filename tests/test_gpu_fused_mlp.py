@@ -348,3 +348,80 @@ def test_mask_form_dgrad_equals_general_form(env_id, hidden, B):
     print("H=%d B=%d: mask form %.2e, general form %.2e vs fp64; mask vs general %.2e" % (hidden, B, em, eg, ed))
     bar = 2e-5 if hidden == 128 else 1e-4           # the tensor core truncates its accumulator: the error grows with K = 2H
     assert em < bar and eg < bar and ed < bar, (em, eg, ed)
+
+
+@pytest.mark.parametrize("env_id,B", [("Acrobot-v1", 8192 + 5), ("MountainCar-v0", 4096)])
+def test_three_logit_heads_run_folded_on_the_two_head_kernels(env_id, B):
+    """Discrete(3) policies (Acrobot-v1, MountainCar-v0 with the reference's 8-float stacked observation): the actor head is
+    folded onto the two-head tensor-core kernels through the softmax's shift invariance (csrc/mlp_trunk.cu xb_head3_fold).
+    Log-probabilities equal the torch modules'; for gradients that come from a softmax loss (sum over the logits = 0) every
+    parameter gradient equals torch autograd's, incl. the third head row reconstructed as -(row 0 + row 1)."""
+    import xuanpolicy_b200 as xb
+    from xuanpolicy_b200.fused_mlp import FusedActorCritic
+    from xuanpolicy_b200.learner import FlatAdamState
+    from xuanpolicy_b200.policies import make_policy
+    torch.backends.cuda.matmul.allow_tf32 = False
+    obs_space, act_space = xb.make_spaces(env_id)
+    policy = make_policy(obs_space, act_space, hidden=(128,), device="cuda", seed=5)
+    with torch.no_grad():
+        for p in policy.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    FlatAdamState(policy, torch.optim.Adam(policy.parameters(), 1e-3), None)
+    assert FusedActorCritic.plan(policy) is not None
+    fused = FusedActorCritic(policy)
+    assert fused.fold3 and fused.A == 3 and fused.obs_dim == obs_space.shape[0]
+    g = torch.Generator(device="cuda").manual_seed(B)
+    obs = torch.randn(B, 8, device="cuda", generator=g)[:, :obs_space.shape[0]]
+    act_out, v = fused.forward(obs)
+    assert act_out.shape == (B, 3) and float(act_out[:, 2].abs().max()) == 0.0
+    buf = fused._buf[B]
+    pat = iter([buf["h1"], buf["ya"], buf["yc"]])
+    lk = lambda t: t * torch.where(next(pat) > 0, 1.0, 0.01).double()
+    names = [n for n, _ in policy.named_parameters()]
+    P = {n: q.detach().double().requires_grad_(True) for n, q in policy.named_parameters()}
+    h1 = lk(obs.double() @ P["representation.model.0.weight"].t() + P["representation.model.0.bias"])
+    ya = lk(h1 @ P["actor.model.0.weight"].t() + P["actor.model.0.bias"])
+    yc = lk(h1 @ P["critic.model.0.weight"].t() + P["critic.model.0.bias"])
+    ref_logits = ya @ P["actor.model.2.weight"].t() + P["actor.model.2.bias"]
+    ref_v = (yc @ P["critic.model.2.weight"].t() + P["critic.model.2.bias"])[:, 0]
+    assert _rel(torch.log_softmax(act_out.double(), 1), torch.log_softmax(ref_logits, 1)) < 1e-4 and _rel(v, ref_v) < 1e-4
+    # a softmax-loss gradient: rows sum to zero
+    d = torch.randn(B, 3, device="cuda", generator=g) / B
+    dact = (d - d.mean(1, keepdim=True)).contiguous()
+    dv = torch.randn(B, device="cuda", generator=g) / B
+    grads = torch.autograd.grad([ref_logits, ref_v], [P[n] for n in names], [dact.double(), dv.double()])
+    fused.backward(dact, dv, softmax_pair=True)
+    torch.cuda.synchronize()
+    mine = dict(policy.named_parameters())
+    for n, gref in zip(names, grads):
+        assert _rel(mine[n].grad, gref) < 1e-4, (n, _rel(mine[n].grad, gref))
+    # the rollout forward (multi-launch for these observation widths) reports the same folded logits
+    a_inf, v_inf = fused.forward_inference(obs)
+    assert _rel(torch.log_softmax(a_inf.double(), 1), torch.log_softmax(ref_logits, 1)) < 1e-4 and _rel(v_inf, ref_v) < 1e-4
+
+
+@pytest.mark.parametrize("env_id", ["Acrobot-v1", "MountainCar-v0"])
+def test_native_agent_on_three_action_envs_uses_the_tensor_core_mlp(env_id):
+    """Row f4 end to end: the device-resident PPO loop on the Discrete(3) envs with the yaml defaults (obs / reward
+    normalisation on) — fused rollout step, folded tensor-core MLP for the rollout forward and the updates — against the same
+    loop with the torch MLP (XB_FUSED_MLP=0): same trajectories (discrete actions), parameters within fp32 tolerance."""
+    import os
+    from xuanpolicy_b200.configs import build_ppo
+    out = []
+    for fused in ("1", "0"):
+        os.environ["XB_FUSED_MLP"] = fused
+        try:
+            agent = build_ppo(env_id, parallels=1024, n_steps=8, n_epoch=2, n_minibatch=2, shuffle="device", seed=6,
+                              use_obsnorm=True, use_rewnorm=True)
+        finally:
+            os.environ.pop("XB_FUSED_MLP", None)
+        assert (agent.learner._fused is not None) == (fused == "1") and agent._fused_step and agent._fused_norm
+        if fused == "1":
+            assert agent.learner._fused.fold3 and agent.batch_size >= agent.learner._fused.MIN_ROWS
+        info = agent.train(8)
+        out.append((agent.memory._act.clone(), agent.memory._obs.clone(), agent.learner._flat.flat_param.clone(), info))
+    assert torch.equal(out[0][0], out[1][0])                                   # same actions -> same trajectory
+    assert torch.allclose(out[0][1], out[1][1], atol=1e-5, rtol=1e-5)
+    assert torch.allclose(out[0][2], out[1][2], atol=2e-5, rtol=2e-4), (out[0][2] - out[1][2]).abs().max()
+    assert abs(out[0][3]["critic-loss"] - out[1][3]["critic-loss"]) <= 1e-4 * max(1.0, abs(out[1][3]["critic-loss"]))

@@ -78,6 +78,8 @@ SIGNATURES = {
                              _vp, _vp, _vp, _i32, _vp],
     "xb_mlp_backward_tail_norm": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                                   _vp, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _f32, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
+    "xb_head3_fold": [_vp, _vp, _vp, _vp, _i32, _vp],
+    "xb_head3_unfold_grads": [_vp, _vp, _i32, _vp],
     "xb_mlp_trunk_wgrad": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _i32, _vp],
     "xb_peer_stats_max": [],
     "xb_peer_alloc": [_vp, _i64],

@@ -167,3 +167,42 @@ extern "C" int xb_mlp_trunk_wgrad(const float* dz1, const float* obs, int ld, in
     XB_LAUNCH_CHECK();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ 3-logit heads
+// A softmax over (z0, z1, z2) equals the softmax over (z0 - z2, z1 - z2, 0): log-probabilities, entropy and every gradient of a
+// loss that depends on the logits through the softmax are unchanged, dL/dz2 = -(dL/dz0 + dL/dz1), and the hidden-layer
+// gradient sum_j dL/dz_j w_j equals dL/dz0 (w0 - w2) + dL/dz1 (w1 - w2).  So a Discrete(3) actor head (MountainCar-v0,
+// Acrobot-v1: xuance/torch/policies/categorical.py:26-32 is generic in action_dim) runs on the two-head dense kernels with
+// FOLDED head parameters; its third logit is reported as 0 (logits are defined up to a per-row constant).
+namespace xb {
+__global__ void head3_fold_kernel(const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ w2,
+                                  float* __restrict__ b2, int H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < H) {
+        const float c = w3[2 * H + i];
+        w2[i] = w3[i] - c;
+        w2[H + i] = w3[H + i] - c;
+    }
+    if (i < 2) b2[i] = b3[i] - b3[2];
+}
+// rows 0, 1 of gw3 / entries 0, 1 of gb3 hold the two-head gradients; row 2 = -(row 0 + row 1)
+__global__ void head3_unfold_grads_kernel(float* __restrict__ gw3, float* __restrict__ gb3, int H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < H) gw3[2 * H + i] = -(gw3[i] + gw3[H + i]);
+    if (i == 0) gb3[2] = -(gb3[0] + gb3[1]);
+}
+}  // namespace xb
+
+extern "C" int xb_head3_fold(const float* w3, const float* b3, float* w2, float* b2, int H, xb_stream_t stream) {
+    if (!w3 || !b3 || !w2 || !b2 || H < 2) return XB_E_BADARG;
+    xb::head3_fold_kernel<<<(H + 127) / 128, 128, 0, (cudaStream_t)stream>>>(w3, b3, w2, b2, H);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_head3_unfold_grads(float* gw3, float* gb3, int H, xb_stream_t stream) {
+    if (!gw3 || !gb3 || H < 1) return XB_E_BADARG;
+    xb::head3_unfold_grads_kernel<<<(H + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gw3, gb3, H);
+    XB_LAUNCH_CHECK();
+    return 0;
+}

@@ -11,8 +11,10 @@ policies/gaussian.py:8-77); this class only *evaluates* them at large batch:
               dgrad (dz_a | dz_c generated on the fly) -> dz1; wgrad (dWa1, dba1, dWa2, dba2, dWc1, ...); trunk wgrad.
 
 It replaces torch autograd + cuBLAS SIMT sgemm for the supported shape (one hidden layer per block, width 128 or 256,
-LeakyReLU, action dim <= 2, obs dim <= 8 — every classic-control config of the reference); anything else keeps the
-torch path.  No CPU path: construction requires CUDA parameters.
+LeakyReLU, obs dim <= 8, action dim <= 2 — or a Discrete(3) head, folded onto the two-head kernels through the shift
+invariance of the softmax (csrc/mlp_trunk.cu xb_head3_fold) — i.e. every classic-control config of the reference:
+CartPole, Pendulum, MountainCar, Acrobot); anything else keeps the torch path.  No CPU path: construction requires CUDA
+parameters.
 """
 import os
 
@@ -64,7 +66,8 @@ class FusedActorCritic:
         if H not in (128, 256) or la1.in_features != H or la1.out_features != H or lc1.in_features != H \
                 or lc1.out_features != H or la2.in_features != H or lc2.in_features != H:
             return None
-        if l0.in_features > 8 or la2.out_features > 2 or lc2.out_features != 1:
+        gaussian = hasattr(policy.actor, "logstd")
+        if l0.in_features > 8 or la2.out_features > (2 if gaussian else 3) or lc2.out_features != 1:
             return None
         for m in lins:
             for t in (m.weight, m.bias):
@@ -90,6 +93,10 @@ class FusedActorCritic:
         self.wtm_hi, self.wtm_lo = z(H, 2 * H), z(H, 2 * H)
         self.mask_dgrad = os.environ.get("XB_MASK_DGRAD", "1") != "0"
         self._mask_ready = False
+        # Discrete(3): folded head parameters (w_j - w_2, b_j - b_2), two-column head outputs / gradients
+        self.fold3 = (not self.gaussian) and self.A == 3
+        self.nh_a = 2 if self.fold3 else self.A
+        self.w2f, self.b2f = (z(2, H), z(2)) if self.fold3 else (None, None)
         self.ws_wgrad = ops.dense_wgrad_workspace(H, dev)
         self.ws_trunk = ops.mlp_trunk_wgrad_workspace(self.obs_dim, H, dev)
         self._buf = {}
@@ -104,8 +111,17 @@ class FusedActorCritic:
         self._side = None
 
     # every tensor below is read at launch time: parameters may have been re-pointed (FlatAdamState) since __init__
+    def _head_a(self):
+        """(weight, bias) of the actor head as the kernels see it."""
+        return (self.w2f, self.b2f) if self.fold3 else (self.la2.weight.data, self.la2.bias.data)
+
+    def fold_head(self):
+        if self.fold3:
+            ops.head3_fold(self.la2.weight.data, self.la2.bias.data, self.w2f, self.b2f)
+
     def refresh_weights(self):
         self.splits_fresh = True
+        self.fold_head()
         ops.dense_split_weights2(self.la1.weight.data, self.wa_hi, self.wa_lo, self.lc1.weight.data, self.wc_hi, self.wc_lo,
                                  self.wt_hi, self.wt_lo)
 
@@ -114,6 +130,9 @@ class FusedActorCritic:
         if b is None:
             e = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
             b = dict(h1=e(B, self.H), ya=e(B, self.H), yc=e(B, self.H), act=e(B, self.A), v=e(B, 1), dz1=None)
+            if self.fold3:      # the kernels write two logits; the reported third one is 0
+                b["act2"] = e(B, 2)
+                b["act"].zero_()
             self._buf[B] = b
         return b
 
@@ -125,13 +144,16 @@ class FusedActorCritic:
         """Actor + critic hidden layers and heads in one launch.  `loss` (dict: scal, adv_stats, adv_count, clip_range,
         vf_coef, ent_coef, inv_batch, logstd, scalars, dlogstd): also the PPO loss forward + backward, fused into the
         kernel's epilogue — dL/d(act_out) lands in b["dact"], dL/dv in b["dv"]."""
-        l0 = (self.wa_hi, self.wa_lo, self.la1.bias.data, b["ya"], self.la2.weight.data, self.la2.bias.data, b["act"])
+        hw, hb = self._head_a()
+        l0 = (self.wa_hi, self.wa_lo, self.la1.bias.data, b["ya"], hw, hb, b["act2"] if self.fold3 else b["act"])
         l1 = (self.wc_hi, self.wc_lo, self.lc1.bias.data, b["yc"], self.lc2.weight.data, self.lc2.bias.data, b["v"])
         # the same launch writes the w2-scaled weight operand of the mask-form dgrad that follows (csrc/dense_tc.cu KParams)
         prep = (self.la1.weight.data, self.lc1.weight.data, self.wtm_hi, self.wtm_lo) if self.mask_dgrad else None
         self._mask_ready = prep is not None
         if loss is None:
             ops.dense_fwd2(b["h1"], self.slope, l0, l1, prep=prep)
+            if self.fold3:
+                b["act"][:, :2].copy_(b["act2"])
             return
         if "dact" not in b:
             B = b["h1"].shape[0]
@@ -149,12 +171,12 @@ class FusedActorCritic:
             ops.dense_dgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, self.wtm_hi, self.wtm_lo,
                             b["h1"], self.slope, b["dz1"], wt_form=1)
             return
-        ops.dense_dgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, self.wt_hi, self.wt_lo,
+        ops.dense_dgrad(b["ya"], dact, self._head_a()[0], b["yc"], dv2, self.lc2.weight.data, self.wt_hi, self.wt_lo,
                         b["h1"], self.slope, b["dz1"])
 
     def stage_wgrad(self, b, dact, dv2):
         """Per-CTA partial sums only (into ws_wgrad); `stage_tail` finishes them."""
-        ops.dense_wgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, b["h1"], self.slope,
+        ops.dense_wgrad(b["ya"], dact, self._head_a()[0], b["yc"], dv2, self.lc2.weight.data, b["h1"], self.slope,
                         self.ws_wgrad, None, None, None, None)
 
     def stage_trunk_wgrad(self, obs, b):
@@ -166,15 +188,18 @@ class FusedActorCritic:
         and, when `norm_sink` is armed, their global norm + the clipped-Adam step scalars (optim workspace)."""
         g = lambda p: p.grad
         norm, self.norm_done = None, False
-        if self.norm_sink is not None and (not self.gaussian or dls64 is not None):   # every gradient passes through here
+        # (folded Discrete(3) head: its third gradient row is written after this launch, so the norm cannot be taken here)
+        if self.norm_sink is not None and not self.fold3 and (not self.gaussian or dls64 is not None):   # every gradient passes through here
             fl, max_norm = self.norm_sink
             norm = (fl.workspace, fl.step, fl.lr0, fl.end_factor, fl.total_iters, fl.beta1, fl.beta2, max_norm, 1.0, fl.lr,
                     fl.gnorm)
             self.norm_done = True
-        ops.mlp_backward_tail(self.ws_wgrad, self.H, self.H, self.la2.weight.shape[0], 1,
+        ops.mlp_backward_tail(self.ws_wgrad, self.H, self.H, self.nh_a, 1,
                               (g(self.la1.weight), g(self.la1.bias), g(self.la2.weight), g(self.la2.bias)),
                               (g(self.lc1.weight), g(self.lc1.bias), g(self.lc2.weight), g(self.lc2.bias)),
                               self.ws_trunk, self.obs_dim, g(self.l0.weight), g(self.l0.bias), dls64, dls32, norm=norm)
+        if self.fold3:      # third head row from the two the kernels produced: dL/dz2 = -(dL/dz0 + dL/dz1)
+            ops.head3_unfold_grads(g(self.la2.weight), g(self.la2.bias))
 
     def fwd_from_obs_ok(self):
         """True if the one-launch rollout forward (trunk generated in-kernel) covers this policy."""
@@ -190,9 +215,11 @@ class FusedActorCritic:
         B = obs.shape[0]
         b = self._buffers(B)
         ops.mlp_fwd_from_obs(obs, self.l0.weight.data, self.l0.bias.data, self.slope,
-                             (self.wa_hi, self.wa_lo, self.la1.bias.data, None, self.la2.weight.data, self.la2.bias.data, b["act"]),
+                             (self.wa_hi, self.wa_lo, self.la1.bias.data, None, *self._head_a(), b["act2"] if self.fold3 else b["act"]),
                              (self.wc_hi, self.wc_lo, self.lc1.bias.data, None, self.lc2.weight.data, self.lc2.bias.data, b["v"]),
                              norm=norm)
+        if self.fold3:
+            b["act"][:, :2].copy_(b["act2"])
         return b["act"], b["v"][:, 0]
 
     # ---------------------------------------------------------------------------------------------- forward / backward
@@ -203,6 +230,8 @@ class FusedActorCritic:
         b = self._buffers(B)
         if refresh:
             self.refresh_weights()
+        else:
+            self.fold_head()                # the head parameters move with every optimiser step
         if not trunk_done:              # the gather kernel already produced h1 for these rows (xb_gather_trunk_fwd)
             self.stage_trunk(obs, b)
         self.stage_hidden(b, loss)
@@ -223,6 +252,11 @@ class FusedActorCritic:
         if b["dz1"] is None:
             b["dz1"] = torch.empty(B, self.H, dtype=torch.float32, device=self.device)
         dv2 = dv.reshape(B, 1)
+        if self.fold3:                      # (d0, d1) drive the folded head; d2 = -(d0 + d1) is implied
+            if "dact2" not in b:
+                b["dact2"] = torch.empty(B, 2, dtype=torch.float32, device=self.device)
+            b["dact2"].copy_(dact[:, :2])
+            dact = b["dact2"]
         if self.fork_wgrad:
             # opt-in experiment (XB_FORK_WGRAD=1): dgrad -> trunk wgrad and the (independent) hidden-layer wgrad as two graph
             # branches, so that wgrad CTAs could fill the SMs dgrad's last, partially filled round of tiles leaves idle.

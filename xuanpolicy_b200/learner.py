@@ -373,7 +373,7 @@ class PPOCLIP_Learner:
 
     def _fused_tail_norm_possible(self):
         f = self._fused
-        return f is not None and (not f.gaussian or (getattr(f.policy.actor, "logstd", None) is not None
+        return f is not None and not f.fold3 and (not f.gaussian or (getattr(f.policy.actor, "logstd", None) is not None
                                                      and f.policy.actor.logstd.numel() == 1))
 
     def update_from_buffer(self, memory, idx):

@@ -434,3 +434,11 @@ def mlp_backward_tail(wgrad_ws, h_out, h_in, nh0, nh1, grads0, grads1, trunk_ws,
         _lib.call("xb_mlp_backward_tail_norm", *args, _p(ws, F64), _p(step_dev, I64), float(lr0), float(end_factor),
                   int(total_iters), float(beta1), float(beta2), float(max_norm), float(grad_scale), _p(lr_out, F32),
                   _p(gnorm_out, F32), _stream())
+
+
+def head3_fold(w3, b3, w2, b2):
+    _lib.call("xb_head3_fold", _p(w3, F32), _p(b3, F32), _p(w2, F32), _p(b2, F32), w3.shape[1], _stream())
+
+
+def head3_unfold_grads(gw3, gb3):
+    _lib.call("xb_head3_unfold_grads", _p(gw3, F32), _p(gb3, F32), gw3.shape[1], _stream())
