@@ -26,8 +26,8 @@ def _scratch_cwd():
         os.chdir(old)
 
 
-def build_runner(env_id, trig="libm", quiet=True, **overrides):
-    """The reference's Runner_DRL for method "ppo" on `env_id`; `overrides` are parser_args (parallels, n_steps, seed,
+def build_runner(env_id, trig="libm", quiet=True, method="ppo", **overrides):
+    """The reference's Runner_DRL for `method` ("ppo", "pg", "ppg", ...) on `env_id`; `overrides` are parser_args (parallels, n_steps, seed,
     representation_hidden_size, use_obsnorm, ...).  runner.agent is the live PPOCLIP_Agent, runner.envs its
     DummyVecEnv_Gym (already reset, runner_basic.py:12)."""
     ref_loader.load(trig=trig)
@@ -37,7 +37,7 @@ def build_runner(env_id, trig="libm", quiet=True, **overrides):
     out = io.StringIO()
     with _scratch_cwd():
         with (contextlib.redirect_stdout(out) if quiet else contextlib.nullcontext()):
-            runner = xuance.get_runner(method="ppo", env="classic_control", env_id=env_id, parser_args=Namespace(**args))
+            runner = xuance.get_runner(method=method, env="classic_control", env_id=env_id, parser_args=Namespace(**args))
     return runner
 
 

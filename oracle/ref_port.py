@@ -14,6 +14,8 @@ baseline timed beside the B200 numbers is the reference's algorithm, not a vecto
     ppo_clip_update     PPOCLIP_Learner.update                        xuance/torch/learners/policy_gradient/ppoclip_learner.py:24-65
     RunningMeanStdPort  RunningMeanStd                                xuance/common/statistic_tools.py:35-112
     PPOAgentPort.train  PPOCLIP_Agent.train                           xuance/torch/agents/policy_gradient/ppoclip_agent.py:59-111
+    PGAgentPort.train   PG_Agent.train + PG_Learner.update            .../pg_agent.py:49-96, learners/policy_gradient/pg_learner.py:17-45
+    PPGAgentPort.train  PPG_Agent.train                               .../ppg_agent.py:55-109
 
 PINNING: tests/test_oracle_vs_reference.py runs these against the live reference (through
 oracle/ref_loader.py) when /root/reference is present, and against tests/golden/*.npz (generated from the
@@ -173,6 +175,57 @@ class OnPolicyBufferPort:
             adv = (adv - np.mean(adv)) / (np.std(adv) + 1e-8)
         return (self.observations[env, step], self.actions[env, step], self.returns[env, step],
                 self.values[env, step], adv, {k: a[env, step] for k, a in self.auxiliary_infos.items()})
+
+
+class _OldDistRows(dict):
+    """`auxiliary_infos` of OldDistBufferPort: assigning "old_dist" a distribution wrapper over the flattened env-major
+    buffer (ppg_agent.py:93) stores its parameter rows."""
+
+    def __init__(self, owner):
+        super().__init__()
+        self._owner = owner
+
+    def __setitem__(self, key, value):
+        if key == "old_dist" and hasattr(value, "get_param"):
+            o = self._owner
+            value = o._rows(value, o.buffer_size).reshape(o.n_envs, o.n_size, -1)
+        dict.__setitem__(self, key, value)
+
+
+class OldDistBufferPort(OnPolicyBufferPort):
+    """The {"old_dist": None} buffer of PPG / PPO-KL (memory_tools.py:28-30 keeps one Python distribution object per
+    transition; here their parameters: logits [A], or mean | std [2A]).  `sample` hands the parameters back in the form
+    `ppg_update` / `ppokl_update` take as `old`."""
+
+    def clear(self):
+        super().clear()
+        self.auxiliary_infos = _OldDistRows(self)
+
+    @staticmethod
+    def _rows(dist, rows):
+        prm = dist.get_param()
+        if isinstance(prm, (tuple, list)):
+            mu = prm[0].detach().cpu().numpy().reshape(rows, -1)
+            std = np.broadcast_to(prm[1].detach().cpu().numpy().reshape(-1, mu.shape[1]), mu.shape)
+            return np.concatenate([mu, std], axis=1).astype(np.float32)
+        return prm.detach().cpu().numpy().reshape(rows, -1).astype(np.float32)
+
+    def store(self, obs, acts, rews, value, terminals, aux_info=None):
+        rows = self._rows(aux_info["old_dist"], self.n_envs)
+        if "old_dist" not in self.auxiliary_infos:
+            dict.__setitem__(self.auxiliary_infos, "old_dist", self._zeros((rows.shape[1],)))
+            self._gaussian = isinstance(aux_info["old_dist"].get_param(), (tuple, list))
+        p = self.ptr
+        super().store(obs, acts, rews, value, terminals, None)
+        self.auxiliary_infos["old_dist"][:, p] = rows
+
+    def sample(self, indexes):
+        obs, act, ret, val, adv, aux = super().sample(indexes)
+        w = torch.as_tensor(aux["old_dist"])
+        if self._gaussian:
+            A = w.shape[1] // 2
+            w = (w[:, :A], w[:, A:])
+        return obs, act, ret, val, adv, {"old_dist": w}
 
 
 # ------------------------------------------------------------------------------------------------ learner
@@ -409,32 +462,155 @@ class PPOAgentPort:
             self.current_step += self.n_envs
 
 
-class PPGAgentPort:
+def pg_update(policy, optimizer, scheduler, batch, ent_coef=0.005, clip_grad=0.5):
+    """One PG_Learner.update step (pg_learner.py:17-45): a_loss = -(returns * log_prob).mean(), entropy bonus, always clipped."""
+    obs, act, ret = batch
+    dev = next(policy.parameters()).device
+    act, ret = torch.as_tensor(act, device=dev), torch.as_tensor(ret, device=dev)
+    _, dist = policy(obs)
+    logp = dist.log_prob(act)
+    a_loss = -(ret * logp).mean()
+    e_loss = dist.entropy().mean()
+    loss = a_loss - ent_coef * e_loss
+    optimizer.zero_grad()
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(policy.parameters(), clip_grad)
+    optimizer.step()
+    if scheduler is not None:
+        scheduler.step()
+    return {"actor-loss": a_loss.item(), "entropy": e_loss.item(),
+            "learning_rate": optimizer.state_dict()["param_groups"][0]["lr"]}
+
+
+class _TapeMixin:
+    """Replay (or record) the random draws of a run: actions per vector step, minibatch permutations per shuffle."""
+
+    def _init_tapes(self, action_tape, perm_tape, record):
+        self.action_tape, self.perm_tape, self._tape_pos, self._perm_pos = action_tape, perm_tape, 0, 0
+        self.recorded_actions, self.recorded_perms = ([], []) if record else (None, None)
+
+    def _taped_action(self, dist):
+        if self.action_tape is not None:
+            a = torch.as_tensor(self.action_tape[self._tape_pos], device=self._device())
+            self._tape_pos += 1
+        else:
+            a = dist.stochastic_sample()
+        if self.recorded_actions is not None:
+            self.recorded_actions.append(a.detach().cpu().numpy().copy())
+        return a
+
+    def _shuffle(self, indexes):
+        if self.perm_tape is None:
+            np.random.shuffle(indexes)
+        else:
+            indexes[:] = self.perm_tape[self._perm_pos]
+            self._perm_pos += 1
+        if self.recorded_perms is not None:
+            self.recorded_perms.append(indexes.copy())
+
+    def _device(self):
+        return next(self.policy.parameters()).device
+
+
+class PGAgentPort(_TapeMixin):
+    """PG_Agent.train restated (xuance/torch/agents/policy_gradient/pg_agent.py:49-96; logging removed): actor-only policy,
+    value 0 stored, `finish_path(processed_reward[i], i)` for every env when the buffer is full (:60-62), `finish_path(0, i)` at
+    every episode end (:81), minibatch size = buffer_size // n_epoch (:28), the return tracker does not mask terminals (:74).
+    `memory` / `update_fn` let a test drive the product's drop-in buffer / PG_Learner through this loop."""
+
+    def __init__(self, envs, policy, optimizer, scheduler, n_steps, n_epoch, gamma, gae_lam, ent_coef=0.01, clip_grad=0.5,
+                 use_gae=False, use_advnorm=False, use_obsnorm=True, use_rewnorm=True, obsnorm_range=5, rewnorm_range=5,
+                 memory=None, update_fn=None, action_tape=None, perm_tape=None, record=False):
+        self.envs, self.policy, self.optimizer, self.scheduler = envs, policy, optimizer, scheduler
+        self.n_envs, self.n_steps, self.n_epoch, self.gamma = envs.num_envs, n_steps, n_epoch, gamma
+        self.buffer_size = self.n_envs * n_steps
+        self.batch_size = self.buffer_size // n_epoch
+        act_shape = () if not hasattr(envs.action_space, "low") else envs.action_space.shape
+        self.memory = memory if memory is not None else OnPolicyBufferPort(
+            envs.observation_space.shape, act_shape, self.n_envs, n_steps, use_gae, use_advnorm, gamma, gae_lam)
+        self.update_fn = update_fn
+        self.hp = dict(ent_coef=ent_coef, clip_grad=clip_grad)
+        self.use_obsnorm, self.use_rewnorm = use_obsnorm, use_rewnorm
+        self.obsnorm_range, self.rewnorm_range = obsnorm_range, rewnorm_range
+        self.obs_rms, self.ret_rms = RunningMeanStdPort(envs.observation_space.shape), RunningMeanStdPort(())
+        self.returns = np.zeros(self.n_envs, np.float32)
+        self.current_step, self.episodes, self.last_info = 0, 0, {}
+        self._init_tapes(action_tape, perm_tape, record)
+
+    _obs = PPOAgentPort._obs
+    _rew = PPOAgentPort._rew
+
+    def train(self, train_steps):
+        obs = self.envs.buf_obs
+        mem = self.memory
+        for _ in range(train_steps):
+            self.obs_rms.update(obs)
+            obs = self._obs(obs)
+            _, dist = self.policy(obs)
+            acts = self._taped_action(dist).detach().cpu().numpy()
+            next_obs, rewards, terminals, truncations, infos = self.envs.step(acts)
+            mem.store(obs, acts, self._rew(rewards), 0, terminals)
+            if mem.full:
+                proc = self._rew(rewards)
+                for i in range(self.n_envs):
+                    mem.finish_path(proc[i], i)
+                indexes = np.arange(self.buffer_size)
+                for _ in range(self.n_epoch):
+                    self._shuffle(indexes)
+                    for start in range(0, self.buffer_size, self.batch_size):
+                        obs_b, act_b, ret_b, _, _, _ = mem.sample(indexes[start:start + self.batch_size])
+                        if self.update_fn is not None:
+                            self.last_info = self.update_fn(obs_b, act_b, ret_b)
+                        else:
+                            self.last_info = pg_update(self.policy, self.optimizer, self.scheduler, (obs_b, act_b, ret_b), **self.hp)
+                mem.clear()
+            self.returns = self.gamma * self.returns + rewards
+            obs = next_obs
+            for i in range(self.n_envs):
+                if terminals[i] or truncations[i]:
+                    self.ret_rms.update(self.returns[i:i + 1])
+                    self.returns[i] = 0.0
+                    obs[i] = infos[i]["reset_obs"]
+                    mem.finish_path(0, i)
+                    self.episodes += 1
+            self.current_step += self.n_envs
+
+
+class PPGAgentPort(_TapeMixin):
     """PPG_Agent.train restated (xuance/torch/agents/policy_gradient/ppg_agent.py:55-109; logging removed): rollout with
     the old action distributions stored per transition, then the policy phase, the critic phase, the refresh of every
     stored old distribution from the current policy (:90-93) and the auxiliary phase.  `memory` and the three `update_*`
     callables let a test drive OTHER implementations (the product's drop-in buffer and PPG_Learner) through this loop.
     The reference wraps the distributions with split_distributions (one Python object per sample); the batched wrapper is
-    passed as is here — the drop-in buffer accepts both."""
+    passed as is here — the drop-in buffer accepts both.  Observation / reward normalisation as in the reference loop
+    (:58-59,63): obs_rms is updated every step; ret_rms is never updated by PPG_Agent, so `_process_reward` only clips."""
 
     def __init__(self, envs, policy, memory, update_policy, update_critic, update_auxiliary, n_steps, n_minibatch=4,
-                 policy_nepoch=1, value_nepoch=1, aux_nepoch=1):
+                 policy_nepoch=1, value_nepoch=1, aux_nepoch=1, use_obsnorm=False, use_rewnorm=False, obsnorm_range=5,
+                 rewnorm_range=5, action_tape=None, perm_tape=None, record=False):
         self.envs, self.policy, self.memory = envs, policy, memory
         self.update_policy, self.update_critic, self.update_auxiliary = update_policy, update_critic, update_auxiliary
         self.n_envs, self.n_steps = envs.num_envs, n_steps
         self.buffer_size = self.n_envs * n_steps
         self.batch_size = self.buffer_size // n_minibatch
         self.policy_nepoch, self.value_nepoch, self.aux_nepoch = policy_nepoch, value_nepoch, aux_nepoch
+        self.use_obsnorm, self.use_rewnorm = use_obsnorm, use_rewnorm
+        self.obsnorm_range, self.rewnorm_range = obsnorm_range, rewnorm_range
+        self.obs_rms, self.ret_rms = RunningMeanStdPort(envs.observation_space.shape), RunningMeanStdPort(())
         self.current_step, self.episodes, self.infos = 0, 0, {}
+        self._init_tapes(action_tape, perm_tape, record)
 
-    def _action(self, obs):
+    _obs = PPOAgentPort._obs
+    _rew = PPOAgentPort._rew
+
+    def _action(self, obs, sample=True):
         _, dists, vs, _ = self.policy(obs)
-        acts = dists.stochastic_sample()
+        acts = self._taped_action(dists) if sample else dists.stochastic_sample()
         return acts.detach().cpu().numpy(), vs.detach().cpu().numpy(), dists
 
     def _phase(self, n_epoch, update, indexes):
         for _ in range(n_epoch):
-            np.random.shuffle(indexes)
+            self._shuffle(indexes)
             for start in range(0, self.buffer_size, self.batch_size):
                 obs_b, act_b, ret_b, _, adv_b, aux_b = self.memory.sample(indexes[start:start + self.batch_size])
                 self.infos.update(update(obs_b, act_b, ret_b, adv_b, aux_b["old_dist"]))
@@ -443,18 +619,24 @@ class PPGAgentPort:
         obs = self.envs.buf_obs
         mem = self.memory
         for _ in range(train_steps):
+            self.obs_rms.update(obs)
+            obs = self._obs(obs)
             acts, rets, dists = self._action(obs)
             next_obs, rewards, terminals, truncations, infos = self.envs.step(acts)
-            mem.store(obs, acts, rewards, rets, terminals, {"old_dist": dists})
+            mem.store(obs, acts, self._rew(rewards), rets, terminals, {"old_dist": dists})
             if mem.full:
-                _, vals, _ = self._action(next_obs)
+                _, vals, _ = self._action(self._obs(next_obs), sample=False)
                 for i in range(self.n_envs):
                     mem.finish_path(vals[i], i)
                 indexes = np.arange(self.buffer_size)
                 self._phase(self.policy_nepoch, self.update_policy, indexes)
                 self._phase(self.value_nepoch, self.update_critic, indexes)
                 buffer_obs = mem.observations                                     # [n_envs, n_size, obs_dim]
-                _, new_dist, _, _ = self.policy(np.asarray(buffer_obs).reshape(self.buffer_size, -1))
+                if torch.is_tensor(buffer_obs):
+                    buffer_obs = buffer_obs.reshape(self.buffer_size, -1)
+                else:
+                    buffer_obs = np.asarray(buffer_obs).reshape(self.buffer_size, -1)
+                _, new_dist, _, _ = self.policy(buffer_obs)
                 mem.auxiliary_infos["old_dist"] = new_dist                         # ppg_agent.py:93
                 self._phase(self.aux_nepoch, self.update_auxiliary, indexes)
                 mem.clear()

@@ -79,6 +79,10 @@ class HostPermutationFeeder:
 
 class PPOCLIP_Agent:
     _mask_terminal_returns = True      # the reward normaliser's return tracker drops the running return on a terminal (:87)
+    _bootstrap_truncations = True      # a truncated episode is closed with V(terminal obs) (:96-100); PG / PPG close it with 0
+    _track_returns = True              # per-env return tracker + ret_rms.update (:87-92); PPG_Agent has neither
+    _graph_updates = True              # the update phase is captured (epoch graphs); False: eager phases through a compat learner
+    _aux_shape = {"old_logp": ()}
 
     def __init__(self, config, envs, policy, optimizer, scheduler=None, device=None, process_group=None):
         self.use_obsnorm = bool(getattr(config, "use_obsnorm", False))
@@ -101,17 +105,18 @@ class PPOCLIP_Agent:
         # Philox key of the action sampler: the rank is folded in so that ranks given the same config seed draw
         # different actions (otherwise W ranks would compute W bit-identical rollouts)
         self._sample_seed = self.seed + 1000003 * self._rank()
-        self.memory = DummyOnPolicyBuffer(self.observation_space, self.action_space, {"old_logp": ()}, self.n_envs,
+        self.memory = DummyOnPolicyBuffer(self.observation_space, self.action_space, dict(self._aux_shape), self.n_envs,
                                           self.n_steps, config.use_gae, config.use_advnorm, self.gamma, self.gae_lam,
                                           device=self.device, native=True,
                                           gae_variant=getattr(config, "gae_variant", "auto"))
-        self.learner = PPOCLIP_Learner(policy, optimizer, scheduler, self.device, getattr(config, "model_dir", "./"),
-                                       vf_coef=config.vf_coef, ent_coef=config.ent_coef, clip_range=config.clip_range,
-                                       clip_grad_norm=config.clip_grad_norm, use_grad_clip=config.use_grad_clip,
-                                       value_clip=getattr(config, "value_clip", None))
-        self.learner.enable_fused_optimizer(process_group)
+        self.learner = self._make_learner(config, policy, optimizer, scheduler)
+        if self._graph_updates:
+            self.learner.enable_fused_optimizer(process_group)
+        elif process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                           and torch.distributed.get_world_size() > 1):
+            raise NotImplementedError("%s trains on one GPU (its update phases are not env-sharded)" % type(self).__name__)
         self.world_size = self.learner.world_size
-        if self.world_size > 1:   # replicated policy: every rank starts from rank 0's parameters
+        if self.world_size > 1 and self._graph_updates:   # replicated policy: every rank starts from rank 0's parameters
             xdist.broadcast_parameters(self.learner._flat.flat_param, 0, process_group)
             if self.buffer_size % self.batch_size:
                 raise ValueError("env-sharded training needs n_envs * n_steps (%d) divisible by n_minibatch (%d): the ranks' "
@@ -197,6 +202,7 @@ class PPOCLIP_Agent:
                                       "(single rank, XB_FUSED_STEP / XB_FUSED_NORM on)")
         self._stat_partials = torch.zeros(20 * max(148, N // 32 + 2), **f64)
         self._stat_ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._zero_v = None
         self._rollout_graph = None
         self._epoch_graph = None
         self._stage_graphs = None
@@ -219,6 +225,15 @@ class PPOCLIP_Agent:
                                     self._stat_ticket)
             self._obs_rms[0].copy_(self._obs_rms[1])
 
+    def _make_learner(self, config, policy, optimizer, scheduler):
+        return PPOCLIP_Learner(policy, optimizer, scheduler, self.device, getattr(config, "model_dir", "./"),
+                               vf_coef=config.vf_coef, ent_coef=config.ent_coef, clip_range=config.clip_range,
+                               clip_grad_norm=config.clip_grad_norm, use_grad_clip=config.use_grad_clip,
+                               value_clip=getattr(config, "value_clip", None))
+
+    def _store_extra(self, t, dist):
+        """Per-step auxiliaries beyond old_logp (PPG: the old action distribution's parameters)."""
+
     @staticmethod
     def _rank():
         d = torch.distributed
@@ -236,8 +251,12 @@ class PPOCLIP_Agent:
             return fused.dist_params(act_out), v
         if norm is not None:
             x = self._apply_norm(x, norm)
-        _, dist, v = self.policy(x[:, :self._obs_dim])
-        return dist, v
+        out = self.policy(x[:, :self._obs_dim])       # (outputs, dist, v) | actor-only (outputs, dist) | PPG (outputs, dist, v, aux_v)
+        if len(out) < 3:
+            if self._zero_v is None or self._zero_v.shape[0] != x.shape[0]:
+                self._zero_v = torch.zeros(x.shape[0], dtype=torch.float32, device=self.device)
+            return out[1], self._zero_v
+        return out[1], out[2]
 
     def _apply_norm(self, x, norm):
         ops.rms_apply(x, self._obs_dim, norm[0], norm[1], norm[2], norm[3], self._xn)
@@ -282,17 +301,21 @@ class PPOCLIP_Agent:
                 c = self._rms_cur
                 stats.update(obs_in=self._obs_rms[c], obs_out=self._obs_rms[c ^ 1], obs_dim=self._obs_dim,
                              obs_clip=self.obsnorm_range)
-            if self.use_rewnorm:
+            if self.use_rewnorm and self._track_returns:
                 stats.update(ret_state=self._ret_rms, returns=self._returns)
             if self._shard_norm:
                 stats.update(sums_out=self._norm_local)
+            if "obs_in" not in stats and "returns" not in stats:
+                stats = None
+            self._store_extra(t, dist)
+            boot = t > 0 and self._bootstrap_truncations
             ops.rollout_step(env._kind, act_param, logstd, v[:N], self._sample_seed, self._ctr, t, env._state, env._rng,
                              env._elapsed, env._ep_score, x_nxt[N:], x_nxt[:N], env._rew, env._term, env._trunc,
                              env._reset_obs, env._ep_step_out, env._ep_score_out, env.ep_stats, env.max_episode_length,
                              x_cur[:N], self._act, self._logp, mem._obs[t], mem._act[t], mem._rew[t], mem._val[t],
                              mem._term[t], mem._trunc[t], mem._logp[t],
                              rew_std=self._rew_std if self.use_rewnorm else None, rew_clip=self.rewnorm_range,
-                             boot_src=v[N:] if t > 0 else None, boot_row=mem._boot[t - 1] if t > 0 else None,
+                             boot_src=v[N:] if boot else None, boot_row=mem._boot[t - 1] if boot else None,
                              trig_cache=self._trig_cache, stats=stats)
             if self._shard_norm:      # the ranks' sums of this step -> global sums -> merged normalisers (for the next step)
                 c = self._rms_cur
@@ -314,8 +337,10 @@ class PPOCLIP_Agent:
                 ops.rms_merge_scalar(self._norm_global[9:], self._ret_rms, self._rew_std)
         x_in = self._normalize_obs(x_cur, update=True)            # obs_rms.update(obs); _process_observation (:63-64)
         dist, v = self._policy_forward(x_in)                      # V on [obs_t ; terminal obs of step t-1]
-        if t > 0 and not self._fused_step:
+        boot = t > 0 and self._bootstrap_truncations
+        if boot and not self._fused_step:
             mem._boot[t - 1].copy_(v[N:])                         # bootstrap for envs truncated at step t-1 (:99)
+        self._store_extra(t, dist)
         if self._fused_step:
             # sample + env step + store in one launch (csrc/env_classic.cu: rollout_step_kernel)
             prm = dist.get_param()
@@ -331,7 +356,7 @@ class PPOCLIP_Agent:
                              x_in[:N], self._act, self._logp, mem._obs[t], mem._act[t], mem._rew[t], mem._val[t],
                              mem._term[t], mem._trunc[t], mem._logp[t],
                              rew_std=self._rew_std if self.use_rewnorm else None, rew_clip=self.rewnorm_range,
-                             boot_src=v[N:] if t > 0 else None, boot_row=mem._boot[t - 1] if t > 0 else None,
+                             boot_src=v[N:] if boot else None, boot_row=mem._boot[t - 1] if boot else None,
                              trig_cache=self._trig_cache)
         else:
             self._sample(dist, t)
@@ -340,7 +365,7 @@ class PPOCLIP_Agent:
                          env._ep_score_out, env.max_episode_length, ep_stats=env.ep_stats)
             mem.store_device(x_in[:N], self._act, env._rew, v[:N].contiguous(), env._term, env._trunc, self._logp, t,
                              rew_std=self._rew_std if self.use_rewnorm else None, rew_clip=self.rewnorm_range)
-        if self.use_rewnorm:                                      # returns tracker + ret_rms.update (:87,:91-92)
+        if self.use_rewnorm and self._track_returns:              # returns tracker + ret_rms.update (:87,:91-92)
             if self._norm_peer is not None:      # merged globally at the start of the next step (see above)
                 ops.returns_track(self._returns, env._rew, env._term, env._trunc, self.gamma, self._norm_local[9:], self._ret_ws,
                                   mask_terminal=self._mask_terminal_returns)
@@ -372,6 +397,10 @@ class PPOCLIP_Agent:
 
     def _rollout_end(self):
         """The bootstrap forward (:70), the batched GAE for every env and segment (:71-75), counter / ping-pong upkeep."""
+        self._close_paths()
+        self._rollout_upkeep()
+
+    def _close_paths(self):
         N = self.n_envs
         if self._fused_norm:      # terminal observations of the last step, normalised with that step's statistics
             _, v = self._policy_forward(self._x[self._cur], self._obs_norm_args())
@@ -379,6 +408,8 @@ class PPOCLIP_Agent:
             _, v = self._policy_forward(self._normalize_obs(self._x[self._cur], update=False))
         self._boot_last.copy_(v[N:])
         self.memory.finish_rollout(self._boot_last)
+
+    def _rollout_upkeep(self):
         ops.counter_add(self._ctr, self.n_steps)
         if self.n_steps % 2:   # keep the ping-pong phase identical for every replay of the captured graph
             self._x[self._cur ^ 1].copy_(self._x[self._cur])
@@ -546,9 +577,13 @@ class PPOCLIP_Agent:
         snap = self._snapshot()
         with torch.cuda.stream(s):
             self._rollout()
-            if self.shuffle == "host" or (self.world_size > 1 and self.learner._peer is None):
+            if not self._graph_updates:
+                pass
+            elif self.shuffle == "host" or (self.world_size > 1 and self.learner._peer is None):
                 self._device_permutation()                 # a valid permutation for the warm-up epoch
-            if self.world_size > 1:
+            if not self._graph_updates:
+                pass
+            elif self.world_size > 1:
                 self._epoch_distributed()
             else:
                 self._epoch_body()
@@ -558,6 +593,10 @@ class PPOCLIP_Agent:
         self._rollout_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._rollout_graph):
             self._rollout()
+        if not self._graph_updates:        # the update phases run eagerly through the learner's own methods
+            torch.cuda.synchronize(self.device)
+            self._restore(snap)
+            return
         peer = self.learner._peer is not None
         epoch = self._epoch_peer if peer else self._epoch_body
         if (self.world_size == 1 or peer) and self.shuffle == "host":
@@ -635,8 +674,9 @@ class PPOCLIP_Agent:
         """Everything a warm-up rollout/update mutates, so that capturing leaves training state untouched."""
         env, fl = self.envs, self.learner._flat
         tensors = [env._state, env._rng, env._elapsed, env._ep_score, env.ep_stats, self._ctr, self._perm_ctr, self._x[0], self._x[1],
-                   fl.flat_param, fl.exp_avg, fl.exp_avg_sq, fl.step, fl.lr, self._obs_rms[0], self._obs_rms[1],
-                   self._ret_rms, self._returns, self._rew_std]
+                   self._obs_rms[0], self._obs_rms[1], self._ret_rms, self._returns, self._rew_std]
+        if fl is not None:
+            tensors += [fl.flat_param, fl.exp_avg, fl.exp_avg_sq, fl.step, fl.lr]
         if self._norm_peer is not None:
             tensors.append(self._norm_local)      # pending return sums of the last step (merged at the next step)
         return [(t, t.clone()) for t in tensors] + [("cur", self._cur)]
@@ -770,4 +810,127 @@ class A2C_Agent(PPOCLIP_Agent):
     def _collect_info(self):
         info = super()._collect_info()
         info.pop("clip_ratio", None)                           # a2c_learner.py:42-48 logs no clip ratio
+        return info
+
+
+class PG_Agent(PPOCLIP_Agent):
+    """PG_Agent drop-in (xuance/torch/agents/policy_gradient/pg_agent.py:4-96): the device-resident loop above with the
+    reference's PG protocol — an actor-only policy (`policy(obs) -> (outputs, dist)`), value 0 stored (:59), every path
+    still open when the buffer fills closed with that step's processed reward as bootstrap (:60-62), paths that end inside
+    the rollout closed with 0 (:81, truncations included), minibatches of `buffer_size // n_epoch` samples (:28), the return
+    tracker of the reward normaliser not masked by terminals (:74), and PG_Learner's loss (pg_learner.py:17-31:
+    -(returns * log_prob).mean() - ent_coef * entropy, gradient norm clipped to `clip_grad`) — the fused loss kernels'
+    A2C surrogate with the returns as weights and no value term, so the whole update phase is the captured one."""
+    _mask_terminal_returns = False
+    _bootstrap_truncations = False
+    _aux_shape = {}
+
+    def __init__(self, config, envs, policy, optimizer, scheduler=None, device=None, process_group=None):
+        from argparse import Namespace
+        cfg = Namespace(**vars(config))
+        cfg.n_minibatch = config.n_epoch                       # batch_size = buffer_size // n_epoch (:28)
+        cfg.use_advnorm = False                                # `sample` normalises advantages nobody reads (:70)
+        cfg.clip_range, cfg.vf_coef = 0.0, 0.0
+        cfg.clip_grad_norm = getattr(config, "clip_grad", None)
+        cfg.use_grad_clip = cfg.clip_grad_norm is not None
+        super().__init__(cfg, envs, policy, optimizer, scheduler, device, process_group)
+        self._term_save = torch.zeros(self.n_envs, dtype=torch.float32, device=self.device)
+
+    def _close_paths(self):
+        mem, last = self.memory, self.n_steps - 1
+        self._boot_last.copy_(mem._rew[last])                  # finish_path(self._process_reward(rewards)[i], i)
+        if not mem.use_gae:
+            # discount_cumsum appends the bootstrap to the rewards whether or not the last step was terminal
+            # (memory_tools.py:224-225); the batched scan masks a terminal's bootstrap, so the flag is lifted for it
+            self._term_save.copy_(mem._term[last])
+            mem._term[last].zero_()
+        mem.finish_rollout(self._boot_last, adv_from_ret=True)
+        if not mem.use_gae:
+            mem._term[last].copy_(self._term_save)
+
+    def _collect_info(self):
+        info = super()._collect_info()
+        for k in ("critic-loss", "predict_value", "clip_ratio"):    # pg_learner.py:38-42 logs three scalars
+            info.pop(k, None)
+        return info
+
+
+class PPG_Agent(PPOCLIP_Agent):
+    """PPG_Agent drop-in (xuance/torch/agents/policy_gradient/ppg_agent.py:4-109).  The rollout is the captured device loop
+    above with PPG's protocol: `policy(obs) -> (outputs, dist, v, aux_v)`, the old action distribution's parameters stored
+    per transition (:63; device rows [T, N, W] instead of Python objects), paths that end inside the rollout closed with 0
+    (:103), no return tracker (`ret_rms` is never updated: `_process_reward` only clips), minibatches of
+    `buffer_size // n_epoch` samples (:29).  The update (:69-98) — policy phase, critic phase, refresh of every stored old
+    distribution from the current policy, auxiliary phase — runs on device minibatches (`memory.sample`, nothing crosses
+    PCIe) through PPG_Learner's three fused loss launches and the torch optimiser the caller built; single GPU."""
+    _bootstrap_truncations = False
+    _track_returns = False
+    _graph_updates = False
+    _aux_shape = {"old_dist": None}
+
+    def __init__(self, config, envs, policy, optimizer, scheduler=None, device=None, process_group=None):
+        from argparse import Namespace
+        cfg = Namespace(**vars(config))
+        cfg.n_minibatch = config.n_epoch                       # batch_size = buffer_size // n_epoch (:29)
+        cfg.shuffle = "device"                                 # np.random.shuffle -> one keyed-bijection launch per epoch
+        self.policy_nepoch, self.value_nepoch, self.aux_nepoch = config.policy_nepoch, config.value_nepoch, config.aux_nepoch
+        super().__init__(cfg, envs, policy, optimizer, scheduler, device, process_group)
+        mem, A = self.memory, (int(self.action_space.n) if self.discrete else self.memory.act_dim)
+        mem._dist_kind = "categorical" if self.discrete else "gaussian"
+        mem._dist = torch.zeros((self.n_steps, self.n_envs, A if self.discrete else 2 * A), dtype=torch.float32,
+                                device=self.device)
+        self._n_act = A
+
+    def _make_learner(self, config, policy, optimizer, scheduler):
+        from .learner import PPG_Learner
+        return PPG_Learner(policy, optimizer, scheduler, self.device, getattr(config, "model_dir", "./"),
+                           ent_coef=config.ent_coef, clip_range=config.clip_range, kl_beta=config.kl_beta)
+
+    def _dist_rows(self, dist, rows, out):
+        prm = dist.get_param()
+        if self.discrete:
+            out.copy_(prm[:rows])
+        else:
+            A = self._n_act
+            out[:, :A].copy_(prm[0][:rows])
+            out[:, A:].copy_(prm[1].reshape(-1, A).expand(rows, A) if prm[1].numel() == A else prm[1][:rows])
+
+    def _store_extra(self, t, dist):
+        self._dist_rows(dist, self.n_envs, self.memory._dist[t])          # {"old_dist": dists} (:63)
+
+    def _draw_permutation(self):
+        self._device_permutation()
+        return self._perm
+
+    def _phase(self, n_epoch, update):
+        mem, B, info = self.memory, self.batch_size, {}
+        for ep in range(n_epoch):
+            perm = self._draw_permutation()
+            for start in range(0, self.buffer_size, B):
+                obs, act, ret, _, adv, aux = mem.sample(perm[start:start + B])
+                # log scalars are read back for the last update of a phase only (one sync per phase, not per update)
+                self.learner.read_back = ep == n_epoch - 1 and start + B >= self.buffer_size
+                info = update(obs, act, ret, adv, aux["old_dist"])
+        self.learner.read_back = True
+        return info
+
+    def _update_phase(self):
+        mem, L, info = self.memory, self.learner, {}
+        info.update(self._phase(self.policy_nepoch, L.update_policy))
+        info.update(self._phase(self.value_nepoch, L.update_critic))
+        with torch.no_grad():            # old_dist <- the current policy on every stored observation (:90-93)
+            rows = mem._obs.reshape(self.buffer_size, mem.obs_row)[:, :self._obs_dim]
+            _, new_dist, _, _ = self.policy(rows)
+            self._dist_rows(new_dist, self.buffer_size, mem._dist.reshape(self.buffer_size, -1))
+        info.update(self._phase(self.aux_nepoch, L.update_auxiliary))
+        self._phase_info = info
+        self._iteration += 1
+
+    def _collect_info(self):
+        info = dict(getattr(self, "_phase_info", {}))
+        st = self.envs.ep_stats.cpu().numpy()
+        info["new_episodes"] = int(st[0]) - self.current_episode
+        info["episodes"] = self.current_episode = int(st[0])
+        info["mean_episode_score"] = float(st[1] / st[0]) if st[0] > 0 else float("nan")
+        info["mean_episode_steps"] = float(st[2] / st[0]) if st[0] > 0 else float("nan")
         return info

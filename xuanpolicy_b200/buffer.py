@@ -176,12 +176,15 @@ class DummyOnPolicyBuffer:
         self.start_ids[i] = self.ptr
         self._gae_valid = False
 
-    def finish_rollout(self, boot_last, variant=None):
+    def finish_rollout(self, boot_last, variant=None, adv_from_ret=False):
         """Native path: one GAE scan for the whole rollout.  Segment ends come from the stored terminal /
-        truncation flags, bootstrap values from `self._boot` (rows where trunc is set) and `boot_last` [N]."""
+        truncation flags, bootstrap values from `self._boot` (rows where trunc is set) and `boot_last` [N].
+        `adv_from_ret`: the policy-gradient weights are the returns themselves (PG_Learner, pg_learner.py:24)."""
         ops.gae(self._rew, self._val, self._term, boot_last, self._adv, self._ret, self.gamma, self.gae_lam,
                 trunc=self._trunc, boot=self._boot, stats=self._stats, use_gae=self.use_gae,
                 variant=variant or self.gae_variant)
+        if adv_from_ret:
+            self._adv.copy_(self._ret)
         if self._rec is not None:
             ops.pack_records(self._obs, self._act, self._logp, self._adv, self._ret, self._rec)
             self._rec_valid = True

@@ -43,3 +43,55 @@ def build_ppo(env_id, device="cuda", process_group=None, policy_seed=None, agent
                                                   total_iters=int(cfg.running_steps))    # runner_drl.py:72-73
     agent = (agent_class or PPOCLIP_Agent)(cfg, envs, policy, optimizer, scheduler, device, process_group=process_group)
     return agent
+
+
+# xuance/configs/pg/classic_control/*.yaml and xuance/configs/ppg/classic_control/*.yaml (activation: the yamls say ReLU)
+_PG = dict(_COMMON, agent="PG", n_steps=128, n_epoch=1, n_minibatch=1, clip_grad=0.5, use_gae=False, use_advnorm=False,
+           use_obsnorm=True, use_rewnorm=True, activation="ReLU", model_dir="./models/pg/", log_dir="./logs/pg/")
+_PPG = dict(_COMMON, agent="PPG", n_steps=256, n_epoch=1, n_minibatch=1, policy_nepoch=4, value_nepoch=8, aux_nepoch=8,
+            kl_beta=1.0, use_obsnorm=True, use_rewnorm=True, activation="ReLU", model_dir="./models/ppg/",
+            log_dir="./logs/ppg/")
+
+
+def _build(defaults, env_id, agent_name, policy_builder, device, overrides, agent_class=None):
+    import torch
+    from torch import nn
+
+    from . import agent as agents
+    from .policies import MLPRepresentation
+    from .vec_env import DummyVecEnv_Gym, make_env_fns
+    cfg = dict(defaults, env_id=env_id, device=device)
+    cfg.update(overrides)
+    cfg = Namespace(**cfg)
+    torch.manual_seed(cfg.seed)
+    envs = DummyVecEnv_Gym(make_env_fns(env_id, cfg.seed, cfg.parallels), device=device, native=True)
+    envs.reset()
+    act = {"ReLU": nn.ReLU, "LeakyReLU": nn.LeakyReLU}[cfg.activation]
+    rep = MLPRepresentation(envs.observation_space.shape, list(cfg.representation_hidden_size), activation=act, device=device)
+    policy = policy_builder(cfg, envs, rep, act)
+    optimizer = torch.optim.Adam(policy.parameters(), cfg.learning_rate, eps=1e-5)
+    scheduler = torch.optim.lr_scheduler.LinearLR(optimizer, start_factor=1.0, end_factor=0.0, total_iters=int(cfg.running_steps))
+    return (agent_class or getattr(agents, agent_name))(cfg, envs, policy, optimizer, scheduler, device)
+
+
+def build_pg(env_id, device="cuda", agent_class=None, **overrides):
+    """PG_Agent wired like Runner_DRL does for the pg yamls (Categorical_Actor / Gaussian_Actor policy)."""
+    from .policies import CategoricalActor, GaussianActor
+    from .spaces import is_discrete
+
+    def policy(cfg, envs, rep, act):
+        cls = CategoricalActor if is_discrete(envs.action_space) else GaussianActor
+        return cls(envs.action_space, rep, list(cfg.actor_hidden_size), activation=act, device=device)
+    return _build(_PG, env_id, "PG_Agent", policy, device, overrides, agent_class)
+
+
+def build_ppg(env_id, device="cuda", agent_class=None, **overrides):
+    """PPG_Agent wired like Runner_DRL does for the ppg yamls (Categorical_PPG / Gaussian_PPG policy)."""
+    from .policies import CategoricalPPGActorCritic, GaussianPPGActorCritic
+    from .spaces import is_discrete
+
+    def policy(cfg, envs, rep, act):
+        cls = CategoricalPPGActorCritic if is_discrete(envs.action_space) else GaussianPPGActorCritic
+        return cls(envs.action_space, rep, list(cfg.actor_hidden_size), list(cfg.critic_hidden_size), activation=act,
+                   device=device)
+    return _build(_PPG, env_id, "PPG_Agent", policy, device, overrides, agent_class)

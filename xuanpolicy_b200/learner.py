@@ -166,7 +166,11 @@ class PPOCLIP_Learner:
                        adv_stats=None, adv_count=0, packed=None, flat=None, fused=None):
         """Fused loss fwd+bwd on the network outputs, then the MLP backward: torch autograd (into `.grad`, or — with
         `flat` — straight into the flat gradient buffer) or, with `fused`, the hand-written dgrad/wgrad kernels."""
-        backward = torch.autograd.backward if flat is None else flat.backward_into
+        base = torch.autograd.backward if flat is None else flat.backward_into
+
+        def backward(outs, grads):      # (an actor-only policy's stand-in value output is not part of the graph)
+            live = [(o, g) for o, g in zip(outs, grads) if o.requires_grad]
+            base([o for o, _ in live], [g for _, g in live])
         if fused is not None:      # (categorical: the loss kernel's two logit gradients are a softmax pair)
             backward = lambda outs, grads: fused.backward(grads[0], grads[1], softmax_pair=True)
         kind, p0, p1 = _dist_params(a_dist)
@@ -323,7 +327,9 @@ class PPOCLIP_Learner:
             act_out, v_pred = fused.forward(mb["obs"], refresh=not fused.splits_fresh, trunk_done=mb.get("trunk_done", False))
             a_dist = fused.dist_params(act_out)
         else:
-            _, a_dist, v_pred = self.policy(mb["obs"])
+            out = self.policy(mb["obs"])
+            a_dist = out[1]
+            v_pred = out[2] if len(out) > 2 else torch.zeros(B, dtype=torch.float32, device=self.device)   # actor-only (PG)
         if memory.packed and self.value_clip <= 0:   # scalars already gathered, compact and coalesced
             self._loss_backward(a_dist, v_pred, None, None, None, None, None, 1.0 / (B * self.world_size),
                                 adv_stats=stats, adv_count=B * self.world_size, packed=mb["scal"], flat=self._flat,
@@ -557,6 +563,7 @@ class PPG_Learner(_DistLossLearner):
         self.kl_beta = kl_beta
         self.policy_iterations = 0
         self.value_iterations = 0
+        self.read_back = True       # False: the phase update returns {} without reading the log scalars back (no sync)
 
     def _forward(self, obs_batch):
         return self.policy(torch.as_tensor(obs_batch, device=self.device))
@@ -570,8 +577,10 @@ class PPG_Learner(_DistLossLearner):
             self._dist_loss_backward(a_dist, v, None, act, ret, adv, old_dists, clip_range=self.clip_range, surr_coef=1.0,
                                      kl_coef=0.0, vf_coef=0.0, ent_coef=self.ent_coef)
             lr = self._step()
+            self.policy_iterations += 1
+            if not self.read_back:
+                return {}
             s = self._scalars.cpu().numpy() / B
-        self.policy_iterations += 1
         return {"actor-loss": float(-s[0]), "entropy": float(s[2]), "learning_rate": lr,
                 "clip_ratio": torch.tensor(s[4], dtype=torch.float32)}
 
@@ -584,8 +593,10 @@ class PPG_Learner(_DistLossLearner):
             self._dist_loss_backward(a_dist, v, None, act, ret, adv, old_dists, clip_range=0.0, surr_coef=0.0, kl_coef=0.0,
                                      vf_coef=1.0, ent_coef=0.0)
             self._step(scheduler=False)                       # the reference steps no scheduler here (:63)
+            self.value_iterations += 1
+            if not self.read_back:
+                return {}
             s = self._scalars.cpu().numpy() / B
-        self.value_iterations += 1
         return {"critic-loss": float(s[1])}
 
     def update_auxiliary(self, obs_batch, act_batch, ret_batch, adv_batch, old_dists):
@@ -597,6 +608,8 @@ class PPG_Learner(_DistLossLearner):
             kl_count = self._dist_loss_backward(a_dist, v, aux_v, act, ret, adv, old_dists, clip_range=0.0, surr_coef=0.0,
                                                 kl_coef=self.kl_beta, vf_coef=1.0, ent_coef=0.0, aux_coef=1.0)
             self._step(scheduler=False)                       # (:84)
+            if not self.read_back:
+                return {}
             s = self._scalars.cpu().numpy()
         return {"kl-loss": float(s[6]) / B + self.kl_beta * float(s[5]) / kl_count + float(s[1]) / B}
 

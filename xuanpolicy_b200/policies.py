@@ -128,6 +128,14 @@ def _epilogue_ok(lin):
             and lin.weight.data_ptr() % 16 == 0)
 
 
+def _slope(mod):
+    """Negative-side slope of a (Leaky)ReLU module — ReLU (the PG / PPG yamls' activation) is the slope-0 case of the
+    same fused bias+activation kernels — or None for anything else."""
+    if isinstance(mod, nn.LeakyReLU):
+        return float(mod.negative_slope)
+    return 0.0 if isinstance(mod, nn.ReLU) else None
+
+
 class _DenseStack(nn.Sequential):
     """nn.Sequential of [Linear, LeakyReLU, ...] (same parameter names as the reference's Sequential).  On a CUDA
     device Linear+LeakyReLU pairs run as cuBLAS mm + the hand-written epilogue kernels (with a custom autograd
@@ -149,11 +157,11 @@ class _DenseStack(nn.Sequential):
             m = mods[k]
             nxt = mods[k + 1] if k + 1 < len(mods) else None
             head = mods[k + 2] if k + 2 == len(mods) - 1 else None
-            fusable = on_gpu and isinstance(m, nn.Linear) and isinstance(nxt, nn.LeakyReLU) and _epilogue_ok(m)
+            fusable = on_gpu and isinstance(m, nn.Linear) and _slope(nxt) is not None and _epilogue_ok(m)
             if (fusable and isinstance(head, nn.Linear) and head.out_features <= 4 and m.out_features <= 512
                     and head.weight.data_ptr() % 16 == 0):
                 # tail [Linear, LeakyReLU, Linear(<= 4 outputs)]: one autograd node, hand-written head kernels
-                slope = float(nxt.negative_slope)
+                slope = _slope(nxt)
                 if torch.is_grad_enabled() and (m.weight.requires_grad or x.requires_grad):
                     x = _HiddenThenHead.apply(x, m.weight, m.bias, head.weight, head.bias, slope, self._workspace(x.device))
                 else:
@@ -164,10 +172,10 @@ class _DenseStack(nn.Sequential):
                 k += 3
             elif fusable:
                 if torch.is_grad_enabled() and (m.weight.requires_grad or x.requires_grad):
-                    x = _LinearLeakyReLU.apply(x, m.weight, m.bias, float(nxt.negative_slope), self._workspace(x.device))
+                    x = _LinearLeakyReLU.apply(x, m.weight, m.bias, _slope(nxt), self._workspace(x.device))
                 else:
                     x = x @ m.weight.t()
-                    ops.bias_act_fwd(x, m.bias, float(nxt.negative_slope))
+                    ops.bias_act_fwd(x, m.bias, _slope(nxt))
                 k += 2
             elif on_gpu and isinstance(m, nn.Linear) and torch.is_grad_enabled() and m.weight.requires_grad:
                 x = _LinearHead.apply(x, m.weight, m.bias)
@@ -379,6 +387,22 @@ class CategoricalActor(nn.Module):
         self.representation_info_shape = representation.output_shapes
         self.actor = _CategoricalActor(representation.output_shapes["state"][0], self.action_dim, actor_hidden_size,
                                        activation, initialize, device)
+
+    def forward(self, observation):
+        outputs = self.representation(observation)
+        return outputs, self.actor(outputs["state"])
+
+
+class GaussianActor(nn.Module):
+    """Actor-only policy for Box actions (Gaussian_Actor: ActorPolicy, xuance/torch/policies/gaussian.py:80-100), used by PG."""
+
+    def __init__(self, action_space, representation, actor_hidden_size, normalize=None, initialize=nn.init.orthogonal_,
+                 activation=nn.LeakyReLU, device=None):
+        super().__init__()
+        self.action_dim, self.representation = action_space.shape[0], representation
+        self.representation_info_shape = representation.output_shapes
+        self.actor = _GaussianActor(representation.output_shapes["state"][0], self.action_dim, actor_hidden_size,
+                                    activation, initialize, device)
 
     def forward(self, observation):
         outputs = self.representation(observation)
