@@ -423,7 +423,13 @@ int xb_dense_fwd2(const float* X, int64_t M, int K, int N, float slope, const fl
  *                           Y0 / Y1 may both be NULL: only the head outputs are produced.
  *                           norm_new / norm_old (nullable pair, fp64 [9] observation-normaliser states): obs holds RAW
  *                           observations; rows [0, norm_rows) are normalised with norm_new, the rest with norm_old
- *                           (clip((obs - mean) / (sqrt(var) + 1e-8), +-norm_clip), agent.py:112-113) before the trunk layer. */
+ *                           (clip((obs - mean) / (sqrt(var) + 1e-8), +-norm_clip), agent.py:112-113) before the trunk layer.
+ *                           The launch carries the programmatic-serialization attribute (it may become resident while the
+ *                           launch before it still runs, and waits for it by itself).  flags: XB_FWD_WEIGHTS_STABLE = the
+ *                           caller vouches that the launch immediately before this one on the stream writes none of the
+ *                           weight / bias arrays: set-up and the resident-weight loads then overlap that launch (the
+ *                           rollout loop: every forward after the first follows xb_rollout_step). */
+#define XB_FWD_WEIGHTS_STABLE 1
 /* xb_dense_fwd2 (actor | critic hidden layers + heads) with xb_ppo_loss_* fused into its epilogue: the epilogue thread that
  * holds a row's head outputs turns them straight into dL/d(mu | logits) (actor CTA) and dL/dv (critic CTA) with the formulas of
  * ppoclip_learner.py:33-44 — no loss launch, no round trip of the head outputs.
@@ -446,7 +452,7 @@ int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const float* W0, 
                         const float* head_w0, const float* head_b0, int n_head0, float* head_out0, const float* Whi1,
                         const float* Wlo1, const float* bias1, float* Y1, const float* head_w1, const float* head_b1,
                         int n_head1, float* head_out1, const double* norm_new, const double* norm_old, int64_t norm_rows,
-                        float norm_clip, xb_stream_t stream);
+                        float norm_clip, int flags, xb_stream_t stream);
 int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, int K0, const float* Y1,
                    const float* dout1, const float* w2_1, int nh1, int K1, int64_t M, const float* Wthi,
                    const float* Wtlo, int N, const float* H1, float slope, float* dZ1, int wt_form, xb_stream_t stream);

@@ -203,6 +203,7 @@ class PPOCLIP_Agent:
         self._stat_partials = torch.zeros(20 * max(148, N // 32 + 2), **f64)
         self._stat_ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         self._zero_v = None
+        self._chain = False
         self._rollout_graph = None
         self._epoch_graph = None
         self._stage_graphs = None
@@ -247,7 +248,9 @@ class PPOCLIP_Agent:
         if fused is not None and x.shape[0] >= fused.MIN_ROWS:     # weights were split at the start of the rollout
             if norm is not None and not fused.fwd_from_obs_ok():
                 x, norm = self._apply_norm(x, norm), None
-            act_out, v = fused.forward_inference(x[:, :self._obs_dim], norm=norm)
+            # (`_chain`: the launch before this forward is a rollout step of this loop, which writes no weights — the
+            #  forward's set-up and weight loads may then overlap it: programmatic dependent launch, csrc/common.cuh)
+            act_out, v = fused.forward_inference(x[:, :self._obs_dim], norm=norm, weights_stable=self._chain)
             return fused.dist_params(act_out), v
         if norm is not None:
             x = self._apply_norm(x, norm)
@@ -326,6 +329,7 @@ class PPOCLIP_Agent:
             if self.use_obsnorm:
                 self._rms_cur ^= 1
             self._cur ^= 1
+            self._chain = True
             return
         if self._norm_peer is not None:
             # sharded: this step's observation moments + the previous step's return sums in ONE exchange, then the global
@@ -374,6 +378,7 @@ class PPOCLIP_Agent:
                                   mask_terminal=self._mask_terminal_returns)
                 ops.rms_merge_scalar(self._ret_sums, self._ret_rms, self._rew_std)
         self._cur ^= 1
+        self._chain = True            # (nothing in this loop writes weights)
 
     def _normalize_obs(self, x, update):
         """rows [0,N): the observations the agent acts on — merged into obs_rms first when `update`; rows [N,2N): the
@@ -392,6 +397,7 @@ class PPOCLIP_Agent:
         return self._xn
 
     def _rollout_begin(self):
+        self._chain = False
         if self.learner._fused is not None:
             self.learner._fused.refresh_weights()
 
@@ -410,6 +416,7 @@ class PPOCLIP_Agent:
         self.memory.finish_rollout(self._boot_last)
 
     def _rollout_upkeep(self):
+        self._chain = False
         ops.counter_add(self._ctr, self.n_steps)
         if self.n_steps % 2:   # keep the ping-pong phase identical for every replay of the captured graph
             self._x[self._cur ^ 1].copy_(self._x[self._cur])
@@ -712,6 +719,7 @@ class PPOCLIP_Agent:
                 else:                                              # partial rollout: the same launches, eagerly
                     k = min(remaining, self.n_steps - self._t)
                     with torch.no_grad():
+                        self._chain = False
                         if self._t == 0:
                             self._rollout_begin()
                         for t in range(self._t, self._t + k):

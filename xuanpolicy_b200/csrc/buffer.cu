@@ -248,6 +248,8 @@ __global__ void __launch_bounds__(256)
                             float* __restrict__ obs_out, float4* __restrict__ scal_out, double* __restrict__ stats,
                             float4* __restrict__ h1) {
     __shared__ double smem[64];
+    pdl_wait();                                 // (launched with the programmatic-serialization attribute, common.cuh)
+    pdl_trigger();
     const int tpr = H >> 2;                     // float4 outputs per row
     const int wpr = tpr >> 5;                   // warps per row (1 or 2)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -409,10 +411,10 @@ extern "C" int xb_gather_trunk_fwd(const int64_t* idx, int64_t B, int64_t T, int
     float4* so = (float4*)scal_out;
     float4* h = (float4*)h1;
     switch (obs_dim) {
-        case 4: gather_trunk_fwd_kernel<4><<<grid, 256, 0, s>>>(idx, B, T, N, r, W0, b0, slope, H, obs_out, so, stats, h); break;
-        case 3: gather_trunk_fwd_kernel<3><<<grid, 256, 0, s>>>(idx, B, T, N, r, W0, b0, slope, H, obs_out, so, stats, h); break;
-        case 2: gather_trunk_fwd_kernel<2><<<grid, 256, 0, s>>>(idx, B, T, N, r, W0, b0, slope, H, obs_out, so, stats, h); break;
-        default: gather_trunk_fwd_kernel<1><<<grid, 256, 0, s>>>(idx, B, T, N, r, W0, b0, slope, H, obs_out, so, stats, h); break;
+        case 4: XB_CUDA(launch_pdl(gather_trunk_fwd_kernel<4>, dim3(grid), dim3(256), 0, s, true, idx, B, T, N, r, W0, b0, slope, H, obs_out, so, stats, h)); break;
+        case 3: XB_CUDA(launch_pdl(gather_trunk_fwd_kernel<3>, dim3(grid), dim3(256), 0, s, true, idx, B, T, N, r, W0, b0, slope, H, obs_out, so, stats, h)); break;
+        case 2: XB_CUDA(launch_pdl(gather_trunk_fwd_kernel<2>, dim3(grid), dim3(256), 0, s, true, idx, B, T, N, r, W0, b0, slope, H, obs_out, so, stats, h)); break;
+        default: XB_CUDA(launch_pdl(gather_trunk_fwd_kernel<1>, dim3(grid), dim3(256), 0, s, true, idx, B, T, N, r, W0, b0, slope, H, obs_out, so, stats, h)); break;
     }
     XB_LAUNCH_CHECK();
     return 0;

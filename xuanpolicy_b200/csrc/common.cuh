@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/xb200.h"
 
@@ -29,6 +30,35 @@ static inline int grid_for(int64_t n, int block, int ctas_per_sm) {
     int64_t cap = (int64_t)kNumSMs * ctas_per_sm;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
+}
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------
+// A kernel launched with `launch_pdl(..., true, ...)` may become resident while the launch before it on the stream is still
+// running; `pdl_wait()` blocks until that launch has completed and its memory is visible (a no-op in a normally launched
+// kernel), `pdl_trigger()` lets the NEXT launch become resident.  Every kernel here triggers only after its own wait, so a
+// kernel's pre-wait prologue can overlap nothing older than its immediate predecessor.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+static inline bool pdl_enabled() {
+    static const bool on = []() { const char* e = getenv("XB_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -11,6 +11,13 @@
 // same source gives bit-identical results when compiled for the host (tests/host_crtrig.cpp does that).
 //
 // Valid for |x| <= 2^19 (Pendulum's |theta| stays below ~84 rad; CartPole's below 0.5 rad).
+//
+// Two phases (Ziv's strategy).  Phase 1 evaluates the tails of both series (terms z^4 and up) in plain double and only the
+// four leading Horner steps in double-double: relative error < 2^-72, a third of the dependent-instruction chain of the full
+// evaluation.  Its result (hi, lo) is accepted when rounding hi + (lo - E) and hi + (lo + E), E = 2^-68 |hi|, gives the same
+// double — that double is then the correctly-rounded value, i.e. exactly what phase 2 returns.  Otherwise (expected once in
+// ~2^14 calls) phase 2, the full double-double series, runs.  Both phases therefore return identical bits wherever phase 2
+// is correctly rounded; tests/test_trig_fast_path.py checks that and the fallback rate on the host build.
 #pragma once
 #include <math.h>
 
@@ -88,7 +95,47 @@ XB_HD void sincos_reduced(dd r, double* s, double* c) {
     *c = rc.hi;
 }
 
-XB_HD void sincos_cr(double x, double* s, double* c) {
+// Phase 1.  Returns false when either rounding test fails (the caller then runs the full evaluation).
+XB_HD dd dd_add_nocancel(dd a, dd b) {  // a + b where no heavy cancellation occurs: ~2^-104 relative
+    dd t = two_sum(a.hi, b.hi);
+    return quick_two_sum(t.hi, t.lo + (a.lo + b.lo));
+}
+XB_HD bool round_test(dd v, double* out) {
+    const double e = fabs(v.hi) * 0x1p-68;
+    const double a = v.hi + (v.lo + e), b = v.hi + (v.lo - e);
+    *out = a;
+    return a == b;
+}
+XB_HD bool sincos_reduced_fast(dd r, double* s, double* c) {
+    const dd S[XB_SIN_TERMS] = XB_SIN_COEFFS;
+    const dd C[XB_COS_TERMS] = XB_COS_COEFFS;
+    constexpr int kDD = 4;  // leading Horner steps carried in double-double
+    if (fabs(r.hi) < 0x1p-20) return false;  // (a tiny reduced argument: its own relative accuracy is the limit)
+    dd z = dd_mul(r, r);
+    double ts = S[XB_SIN_TERMS - 1].hi, tc = C[XB_COS_TERMS - 1].hi;
+#pragma unroll
+    for (int j = XB_SIN_TERMS - 2; j >= kDD; --j) ts = fma(ts, z.hi, S[j].hi);
+#pragma unroll
+    for (int j = XB_COS_TERMS - 2; j >= kDD; --j) tc = fma(tc, z.hi, C[j].hi);
+    dd ps = two_prod(z.hi, ts), pc = two_prod(z.hi, tc);
+    ps = dd_add_nocancel(ps, S[kDD - 1]);
+    pc = dd_add_nocancel(pc, C[kDD - 1]);
+#pragma unroll
+    for (int j = kDD - 2; j >= 0; --j) {
+        ps = dd_add_nocancel(dd_mul(ps, z), S[j]);
+        pc = dd_add_nocancel(dd_mul(pc, z), C[j]);
+    }
+    dd rs = dd_add(r, dd_mul(r, dd_mul(z, ps)));  // r + r*z*S(z)
+    dd rc = dd_add_d(dd_mul(z, pc), 1.0);         // 1 + z*C(z)
+    const bool ok_s = round_test(rs, s), ok_c = round_test(rc, c);
+    return ok_s && ok_c;
+}
+
+#ifndef XB_TRIG_FAST
+#define XB_TRIG_FAST 1
+#endif
+
+XB_HD void sincos_cr(double x, double* s, double* c, int* slow_path = nullptr) {
     double ax = fabs(x);
     if (ax < 0x1p-27) {  // sin x rounds to x and cos x to 1 (also keeps the sign of zero)
         *s = x;
@@ -99,7 +146,10 @@ XB_HD void sincos_cr(double x, double* s, double* c) {
     dd r = dd{x, 0.0};
     if (ax > 0.78539816339744828) r = reduce_pio2(x, &q);
     double sr, cr;
-    sincos_reduced(r, &sr, &cr);
+    if (!XB_TRIG_FAST || !sincos_reduced_fast(r, &sr, &cr)) {
+        sincos_reduced(r, &sr, &cr);
+        if (slow_path) *slow_path += 1;
+    }
     switch (q) {
         case 0: *s = sr; *c = cr; break;
         case 1: *s = cr; *c = -sr; break;

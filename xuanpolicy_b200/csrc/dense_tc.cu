@@ -80,6 +80,8 @@ struct KParams {
     int out_bufs;       // epilogue staging tiles (1 or 2)
     int h1_bufs;        // DGRAD mask tiles (1 or 2)
     float slope;
+    int pdl_launch;     // launch with the programmatic-serialization attribute (the kernel waits by itself, common.cuh)
+    int pdl_early;      // FWD: set-up and resident-weight loads may run before the wait (XB_FWD_WEIGHTS_STABLE)
 #ifdef XB_DENSE_TS
     long long* ts;
 #endif
@@ -827,6 +829,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     constexpr uint32_t kACol = 2 * N;                   // first TMEM column of the A ring
     extern __shared__ unsigned char smem_raw[];
     XB_DECLARE_PREDS();
+    // programmatic dependent launch: with `pdl_early` (the caller vouches that the launch before this one writes no weights)
+    // the set-up below and the resident-weight loads overlap that launch; everything else starts after pdl_wait()
+    const bool pdl_early = MODE == MODE_FWD && p.pdl_early != 0;
     if (threadIdx.x == 0) XB_TS(0, 62, 0);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int S = p.stages, SB = p.lo_bufs, O = p.out_bufs, HB = p.h1_bufs, KB = p.KB;   // lo_bufs doubles as B-ring depth
@@ -886,6 +891,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_fence_init();
     }
     if (warp == kMmaWarp) tmem_alloc<kTsTmemCols>(tmem_slot);
+    if (!pdl_early) pdl_wait();           // (barriers and tensor memory above: no global data touched)
     if (MODE == MODE_FWD) {
         for (int i = threadIdx.x; i < N; i += kThreads) {
             sf[i] = e_bias ? e_bias[i] : 0.f;
@@ -914,6 +920,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     if (threadIdx.x == 0) XB_TS(0, 62, 1);
+    const bool is_producer = warp == kProducerWarp && lane == 0;
+    if (!is_producer) {
+        if (pdl_early) pdl_wait();
+        pdl_trigger();
+    }
 
     if (warp == kProducerWarp) {
         // ============================================================ TMA producer (one thread)
@@ -929,6 +940,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                     tma_load_2d(bres + (KB + kb) * kBTile, map_blo, kb * BK, n_off, bar_bfull);
                 }
             }
+            if (pdl_early) pdl_wait();          // (the resident weights are on their way; activations only from here)
+            pdl_trigger();
             uint32_t s = 0, ph = 0, sb = 0, bph = 0, it = 0;
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
                 for (int kb = 0; kb < KB; ++kb, ++it) {
@@ -1194,7 +1207,7 @@ static int launch_kmajor_ts(const TMaps& maps, KParams p, cudaStream_t s) {
     const int n_src = MODE == MODE_FWD ? (p.dual ? 2 : 1) : (p.n_split > 1 ? p.n_split : 1);
     const int64_t want = tiles * n_src;
     const int grid = (int)(want < kNumSMs ? want : (kNumSMs / n_src) * n_src);
-    kern<<<grid, kThreads, smem, s>>>(maps, p);
+    XB_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), (size_t)smem, s, true, maps, p));
     XB_LAUNCH_CHECK();
     return 0;
 }
@@ -1335,6 +1348,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_fence_init();
     }
     if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
+    pdl_wait();                           // (set-up above overlaps the launch before this one, common.cuh)
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -1558,6 +1573,8 @@ __global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restri
     __shared__ float red[4][260];
     __shared__ double norm_smem[32];
     __shared__ bool norm_last;
+    pdl_wait();
+    pdl_trigger();
     const float gs = tail.hyper.grad_scale;
     double sq = 0.0;                                   // this thread's share of sum((grad * grad_scale)^2)
 #define XB_SQ(x) do { const double g__ = (double)((x) * gs); sq += g__ * g__; } while (0)
@@ -1653,7 +1670,7 @@ static int launch_wgrad(const CUtensorMap& my0, const CUtensorMap& my1, const CU
     const int smem = 1024 + (S + L) * stage + kWMiscBytes;
     auto kern = dense_wgrad_kernel<HIN>;
     XB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));   // per device, cheap: set on every launch
-    kern<<<grid, kThreads, smem, s>>>(my0, my1, mx, p);
+    XB_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), (size_t)smem, s, true, my0, my1, mx, p));
     XB_LAUNCH_CHECK();
     return 0;
 }
@@ -1702,6 +1719,7 @@ struct TrunkArgs {
     const double* norm_old;
     int64_t norm_rows;
     float norm_clip;
+    int flags;
 };
 
 static int dense_fwd_impl(const float* X, const TrunkArgs* trunk, int64_t M, int K, int N, float slope, int n_layers, const float* const* Whi,
@@ -1747,6 +1765,8 @@ static int dense_fwd_impl(const float* X, const TrunkArgs* trunk, int64_t M, int
         p.norm_old = trunk->norm_old;
         p.norm_rows = trunk->norm_rows;
         p.norm_clip = trunk->norm_clip;
+        p.pdl_launch = 1;
+        p.pdl_early = (trunk->flags & XB_FWD_WEIGHTS_STABLE) ? 1 : 0;
     }
     p.M = M;
     p.KB = K / BK;
@@ -1843,7 +1863,7 @@ extern "C" int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const 
                                    const float* Whi1, const float* Wlo1, const float* bias1, float* Y1,
                                    const float* head_w1, const float* head_b1, int n_head1, float* head_out1,
                                    const double* norm_new, const double* norm_old, int64_t norm_rows, float norm_clip,
-                                   xb_stream_t stream) {
+                                   int flags, xb_stream_t stream) {
     if ((norm_new != nullptr) != (norm_old != nullptr)) return XB_E_BADARG;
     const float* Whi[2] = {Whi0, Whi1};
     const float* Wlo[2] = {Wlo0, Wlo1};
@@ -1853,7 +1873,7 @@ extern "C" int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const 
     const float* hb[2] = {head_b0, head_b1};
     const int nh[2] = {n_head0, n_head1};
     float* ho[2] = {head_out0, head_out1};
-    TrunkArgs t{obs, ld, obs_dim, W0, b0, norm_new, norm_old, norm_rows, norm_clip};
+    TrunkArgs t{obs, ld, obs_dim, W0, b0, norm_new, norm_old, norm_rows, norm_clip, flags};
     return dense_fwd_impl(nullptr, &t, M, H, H, slope, 2, Whi, Wlo, bias, Y, hw, hb, nh, ho, 1, stream);
 }
 
@@ -1960,9 +1980,9 @@ static int backward_tail_impl(const float* wgrad_ws, int H_out, int H_in, int n_
     TailArgs tail{trunk_ws, trunk_parts, H_in, obs_dim, dWt, dbt, dls64, dls32, A, norm_ws, step_dev, hyper, lr_out, gnorm_out};
     const int tail_blocks = trunk_ws ? (H_in * (obs_dim + 1) + 15) / 16 : (dls64 ? 1 : 0);
     if (n_jobs * 128 + tail_blocks > xb::kOptMaxGrid) return XB_E_UNSUPPORTED;
-    wgrad_reduce_kernel<<<n_jobs * 128 + tail_blocks, 512, 0, stream>>>(
-        part, head_part, db2_part, grid, n_jobs, halves, H_in, H_out, dW0, db0, dw2_0, db2_0, nh0, dW1, db1, dw2_1, db2_1,
-        n_sources == 2 ? nh1 : 0, tail);
+    XB_CUDA(launch_pdl(wgrad_reduce_kernel, dim3(n_jobs * 128 + tail_blocks), dim3(512), 0, stream, true, part, head_part, db2_part,
+                       grid, n_jobs, halves, H_in, H_out, dW0, db0, dw2_0, db2_0, nh0, dW1, db1, dw2_1, db2_1,
+                       n_sources == 2 ? nh1 : 0, tail));
     XB_LAUNCH_CHECK();
     return 0;
 }

@@ -457,6 +457,10 @@ struct RolloutStepArgs {
 
 template <class Env>
 __global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs a) {
+    // launched with the programmatic-serialization attribute (common.cuh): resident early, starts when the forward before it
+    // has completed; the next forward may then run its weight-only prologue underneath this kernel
+    pdl_wait();
+    pdl_trigger();
     constexpr int V = Env::kObsVec, D = 4 * V;
     __shared__ double stat_smem[(2 * D + 3) * 32];
     __shared__ bool stat_flag;
@@ -729,11 +733,11 @@ extern "C" int xb_rollout_step(int env_kind, const float* act_param, const float
     }
     cudaStream_t s = (cudaStream_t)stream;
     int block = env_block(N), grid = ceil_div_i64(N, block);
-    if (env_kind == XB_ENV_CARTPOLE) rollout_step_kernel<CartPole><<<grid, block, 0, s>>>(a);
-    else if (env_kind == XB_ENV_PENDULUM) rollout_step_kernel<Pendulum><<<grid, block, 0, s>>>(a);
-    else if (env_kind == XB_ENV_MOUNTAINCAR) rollout_step_kernel<MountainCar><<<grid, block, 0, s>>>(a);
-    else if (env_kind == XB_ENV_ACROBOT) rollout_step_kernel<Acrobot><<<grid, block, 0, s>>>(a);
-    else if (env_kind == XB_ENV_MOUNTAINCAR_STACK4) rollout_step_kernel<MountainCarStack><<<grid, block, 0, s>>>(a);
+    if (env_kind == XB_ENV_CARTPOLE) XB_CUDA(launch_pdl(rollout_step_kernel<CartPole>, dim3(grid), dim3(block), 0, s, true, a));
+    else if (env_kind == XB_ENV_PENDULUM) XB_CUDA(launch_pdl(rollout_step_kernel<Pendulum>, dim3(grid), dim3(block), 0, s, true, a));
+    else if (env_kind == XB_ENV_MOUNTAINCAR) XB_CUDA(launch_pdl(rollout_step_kernel<MountainCar>, dim3(grid), dim3(block), 0, s, true, a));
+    else if (env_kind == XB_ENV_ACROBOT) XB_CUDA(launch_pdl(rollout_step_kernel<Acrobot>, dim3(grid), dim3(block), 0, s, true, a));
+    else if (env_kind == XB_ENV_MOUNTAINCAR_STACK4) XB_CUDA(launch_pdl(rollout_step_kernel<MountainCarStack>, dim3(grid), dim3(block), 0, s, true, a));
     else return XB_E_UNSUPPORTED;
     XB_LAUNCH_CHECK();
     return 0;

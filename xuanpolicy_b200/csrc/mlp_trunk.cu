@@ -48,6 +48,8 @@ template <int OBS>
 __global__ void __launch_bounds__(256) trunk_wgrad_kernel(const float4* __restrict__ dz1, const float* __restrict__ obs,
                                                           int ld, float* __restrict__ partial, int64_t B, int H) {
     extern __shared__ float red[];                 // [rows_per_block][H][OBS + 1]
+    pdl_wait();                                    // (launched with the programmatic-serialization attribute, common.cuh)
+    pdl_trigger();
     const int tpr = H >> 2;
     const int rows_per_block = blockDim.x / tpr;
     const int q = threadIdx.x % tpr, slot = threadIdx.x / tpr;
@@ -158,8 +160,10 @@ extern "C" int xb_mlp_trunk_wgrad(const float* dz1, const float* obs, int ld, in
     const int smem = rows_per_block * H * (obs_dim + 1) * (int)sizeof(float);
     if (smem > 48 * 1024) return XB_E_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
-    XB_OBS_SWITCH(obs_dim, (trunk_wgrad_kernel<O><<<kTrunkBlocks, 256, smem, s>>>(
-                               reinterpret_cast<const float4*>(dz1), obs, ld, workspace, B, H)));
+    cudaError_t err = cudaSuccess;
+    XB_OBS_SWITCH(obs_dim, (err = launch_pdl(trunk_wgrad_kernel<O>, dim3(kTrunkBlocks), dim3(256), (size_t)smem, s, true,
+                                             reinterpret_cast<const float4*>(dz1), obs, ld, workspace, B, H)));
+    XB_CUDA(err);
     XB_LAUNCH_CHECK();
     if (!dW0) return 0;                      // partials only: the caller finishes with xb_mlp_backward_tail
     const int n_out = H * (obs_dim + 1);

@@ -110,24 +110,36 @@ __device__ __forceinline__ void step_stats_finish(const StepStats& s, double (&a
     __syncthreads();
     if (!*flag) return;
     __threadfence();
-    if (threadIdx.x >= 32) return;              // the rest happens in warp 0
-    {   // lane l adds the partials of CTAs l, l + 32, ... (all loads in flight at once), then a fixed-order butterfly:
-        // the association order depends only on the grid size, so every replay gives the same bits
-        const int lane = threadIdx.x;
+    {   // every thread of the last CTA adds the partials of CTAs tid, tid + blockDim, ... — the loads of U rows in flight at
+        // once (one L2 round trip for up to U * blockDim CTAs) — then a fixed-order block reduction: the association order
+        // depends only on the launch geometry, so every replay gives the same bits
+        constexpr int U = D <= 4 ? 4 : 2;
+        const int nthr = blockDim.x, grid = gridDim.x;
         double t[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) t[k] = 0.0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) {
-            const double* p = s.partials + (int64_t)b * kStepStatSlots;
+        for (int b0 = threadIdx.x; b0 < grid; b0 += U * nthr) {
+            double u[U][K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) t[k] += __ldcg(p + k);
-        }
+            for (int j = 0; j < U; ++j) {
+                const int b = b0 + j * nthr;
+                const double* p = s.partials + (int64_t)(b < grid ? b : 0) * kStepStatSlots;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const double v = warp_sum(t[k]);
-            if (lane == 0) smem[k] = v;
+                for (int k = 0; k < K; ++k) u[j][k] = b < grid ? __ldcg(p + k) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j)
+#pragma unroll
+                for (int k = 0; k < K; ++k) t[k] += u[j][k];
         }
+        block_sum<K>(t, smem);                  // (uniform: the whole CTA took this branch)
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) smem[k] = t[k];
+        }
+        __syncthreads();
     }
+    if (threadIdx.x >= 32) return;              // the rest happens in warp 0
     __syncwarp();
     if (s.sums_out) {
         if (threadIdx.x < 2 * D) s.sums_out[threadIdx.x] = smem[threadIdx.x];

@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(kOptBlock)
 __global__ void __launch_bounds__(kOptBlock)
     adam_apply_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ exp_avg,
                       float* __restrict__ exp_avg_sq, int64_t n, AdamHyper h, const double* __restrict__ ws) {
+    pdl_wait();
+    pdl_trigger();
     const float gscale = h.grad_scale * (float)ws[1];
     const float step_size = (float)(ws[2] / ws[3]);
     const float bc2_sqrt = (float)ws[4];
@@ -71,6 +73,8 @@ __device__ __forceinline__ void split_tf32_opt(float x, float& hi, float& lo) {
 __global__ void __launch_bounds__(kOptBlock)
     adam_apply_split_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ exp_avg,
                             float* __restrict__ exp_avg_sq, int64_t n, AdamHyper h, const double* __restrict__ ws, AdamSplit sp) {
+    pdl_wait();                                 // (launched with the programmatic-serialization attribute, common.cuh)
+    pdl_trigger();
     const float gscale = h.grad_scale * (float)ws[1];
     const float step_size = (float)(ws[2] / ws[3]);
     const float bc2_sqrt = (float)ws[4];
@@ -128,7 +132,8 @@ extern "C" int xb_adam_apply(float* param, const float* grad, float* exp_avg, fl
     AdamHyper h{0.0f, 0.0f, beta1, beta2, eps, 0.0f, grad_scale, 0};
     int grid = grid_for(n, kOptBlock, 4);
     if (grid > kOptMaxGrid) grid = kOptMaxGrid;
-    adam_apply_kernel<<<grid, kOptBlock, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, h, workspace);
+    XB_CUDA(launch_pdl(adam_apply_kernel, dim3(grid), dim3(kOptBlock), 0, (cudaStream_t)stream, true, param, grad, exp_avg, exp_avg_sq, n, h,
+                       (const double*)workspace));
     XB_LAUNCH_CHECK();
     return 0;
 }
@@ -144,7 +149,8 @@ extern "C" int xb_adam_apply_split(float* param, const float* grad, float* exp_a
     AdamSplit sp{{w_off0, w_off1}, {hi0, hi1}, {lo0, lo1}, {0, N}, thi, tlo, N, K, 2 * N};
     int grid = grid_for(n, kOptBlock, 4);
     if (grid > kOptMaxGrid) grid = kOptMaxGrid;
-    adam_apply_split_kernel<<<grid, kOptBlock, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, h, workspace, sp);
+    XB_CUDA(launch_pdl(adam_apply_split_kernel, dim3(grid), dim3(kOptBlock), 0, (cudaStream_t)stream, true, param, grad, exp_avg, exp_avg_sq,
+                       n, h, workspace, sp));
     XB_LAUNCH_CHECK();
     return 0;
 }

@@ -205,10 +205,11 @@ class FusedActorCritic:
         """True if the one-launch rollout forward (trunk generated in-kernel) covers this policy."""
         return self.obs_dim <= 4 and self.H <= 128
 
-    def forward_inference(self, obs, norm=None):
+    def forward_inference(self, obs, norm=None, weights_stable=False):
         """Rollout forward (no activations kept): trunk + both hidden layers + heads in ONE launch for obs_dim <= 4,
         H <= 128 (the trunk layer is generated inside the kernel); otherwise the training forward without refresh.
-        norm = (state_new, state_old, n_new_rows, clip): `obs` is raw, the kernel normalises it (one-launch form only)."""
+        norm = (state_new, state_old, n_new_rows, clip): `obs` is raw, the kernel normalises it (one-launch form only).
+        weights_stable: the launch right before this one writes no weights (lets the kernel's set-up overlap it)."""
         if not self.fwd_from_obs_ok():
             assert norm is None, "normalise the observations before the multi-launch forward"
             return self.forward(obs, refresh=False)
@@ -217,7 +218,7 @@ class FusedActorCritic:
         ops.mlp_fwd_from_obs(obs, self.l0.weight.data, self.l0.bias.data, self.slope,
                              (self.wa_hi, self.wa_lo, self.la1.bias.data, None, *self._head_a(), b["act2"] if self.fold3 else b["act"]),
                              (self.wc_hi, self.wc_lo, self.lc1.bias.data, None, self.lc2.weight.data, self.lc2.bias.data, b["v"]),
-                             norm=norm)
+                             norm=norm, weights_stable=weights_stable)
         if self.fold3:
             b["act"][:, :2].copy_(b["act2"])
         return b["act"], b["v"][:, 0]

@@ -365,9 +365,10 @@ def dense_fwd2_loss(x, slope, layer0, layer1, scal, adv_stats, adv_count, clip_r
               _p(dlogstd, F64), _p(pw0, F32), _p(pw1, F32), _p(pthi, F32), _p(ptlo, F32), _stream())
 
 
-def mlp_fwd_from_obs(obs, w0, b0, slope, layer0, layer1, norm=None):
+def mlp_fwd_from_obs(obs, w0, b0, slope, layer0, layer1, norm=None, weights_stable=False):
     """Whole actor-critic forward in one launch; layerK = (w_hi, w_lo, bias, y or None, head_w, head_b, head_out).
-    norm = (state_new, state_old, n_new_rows, clip): `obs` is raw and is normalised in front of the trunk layer."""
+    norm = (state_new, state_old, n_new_rows, clip): `obs` is raw and is normalised in front of the trunk layer.
+    weights_stable: the launch right before this one on the stream writes no weight array (XB_FWD_WEIGHTS_STABLE)."""
     nn, no, nr, nc = norm if norm is not None else (None, None, 0, 0.0)
     ptr, ld = _rows_ld(obs)
     args = []
@@ -375,7 +376,7 @@ def mlp_fwd_from_obs(obs, w0, b0, slope, layer0, layer1, norm=None):
         args += [_p(w_hi, F32), _p(w_lo, F32), _p(bias, F32), _p(y, F32), _p(head_w, F32), _p(head_b, F32),
                  head_w.shape[0], _p(head_out, F32)]
     _lib.call("xb_mlp_fwd_from_obs", ptr, ld, obs.shape[1], _p(w0, F32), _p(b0, F32), obs.shape[0], w0.shape[0],
-              float(slope), *args, _p(nn, F64), _p(no, F64), int(nr), float(nc), _stream())
+              float(slope), *args, _p(nn, F64), _p(no, F64), int(nr), float(nc), 1 if weights_stable else 0, _stream())
 
 
 def dense_dgrad(y0, dout0, w2_0, y1, dout1, w2_1, wt_hi, wt_lo, h1, slope, dz1, wt_form=0):
