@@ -43,8 +43,10 @@ def run(which):
     dact, dv2 = torch.randn(B, 1, device="cuda") / B, torch.randn(B, 1, device="cuda") / B
     ts = torch.zeros(4 * 64 * 8, dtype=torch.int64, device="cuda")
     lib.xb_dense_debug_set_ts.argtypes = [C.c_void_p]
+    xr = torch.randn(8192, 4, device="cuda")            # the rollout forward at C2: [obs ; terminal obs] of 4096 envs
     fn = {"fwd2": lambda: fused.stage_hidden(b), "dgrad": lambda: fused.stage_dgrad(b, dact, dv2),
-          "wgrad": lambda: fused.stage_wgrad(b, dact, dv2)}[which]
+          "wgrad": lambda: fused.stage_wgrad(b, dact, dv2),
+          "infer": lambda: fused.forward_inference(xr[:, :3])}[which]
     for _ in range(3):
         fn()
     torch.cuda.synchronize()

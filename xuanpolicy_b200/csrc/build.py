@@ -33,7 +33,8 @@ SOURCES = {
     "dense_tc.cu": [],
     "mlp_trunk.cu": [],
 }
-HEADERS = ["common.cuh", "sm100.cuh", "sample.cuh", "optim.cuh", "crtrig.cuh", "crtrig_consts.inc", os.path.join("..", "..", "include", "xb200.h")]
+# every header in this directory (a forgotten one leaves stale objects behind: normalize.cuh once was)
+HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith((".cuh", ".inc"))) + [os.path.join("..", "..", "include", "xb200.h")]
 
 
 def _stale(target, deps):

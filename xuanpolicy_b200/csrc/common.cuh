@@ -61,6 +61,19 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+#ifdef XB_STEP_TS   // debug build only (tools/profile/step_timeline.py): %globaltimer stamps of the rollout's two kernels
+__device__ __forceinline__ void step_ts(unsigned long long* ts, unsigned long long tag) {
+    if (!ts) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long i = atomicAdd(ts, 1ull);
+    if (i < 30000ull) { ts[1 + 2 * i] = tag; ts[2 + 2 * i] = t; }
+}
+#define XB_STEP_STAMP(ts, tag) step_ts(ts, tag)
+#else
+#define XB_STEP_STAMP(ts, tag) do { } while (0)
+#endif
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -25,6 +25,10 @@
 #include "optim.cuh"
 #include "sm100.cuh"
 
+#ifdef XB_STEP_TS
+extern unsigned long long* g_xb_step_ts;    // env_classic.cu (debug build only)
+#endif
+
 namespace xb {
 namespace dense {
 
@@ -82,6 +86,9 @@ struct KParams {
     float slope;
     int pdl_launch;     // launch with the programmatic-serialization attribute (the kernel waits by itself, common.cuh)
     int pdl_early;      // FWD: set-up and resident-weight loads may run before the wait (XB_FWD_WEIGHTS_STABLE)
+#ifdef XB_STEP_TS
+    unsigned long long* sts;
+#endif
 #ifdef XB_DENSE_TS
     long long* ts;
 #endif
@@ -832,6 +839,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     // programmatic dependent launch: with `pdl_early` (the caller vouches that the launch before this one writes no weights)
     // the set-up below and the resident-weight loads overlap that launch; everything else starts after pdl_wait()
     const bool pdl_early = MODE == MODE_FWD && p.pdl_early != 0;
+#ifdef XB_STEP_TS
+    unsigned long long* const sts = (blockIdx.x == 0 && threadIdx.x == 0 && MODE == MODE_FWD && p.obs) ? p.sts : nullptr;
+#endif
+    XB_STEP_STAMP(sts, 200);
     if (threadIdx.x == 0) XB_TS(0, 62, 0);
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int S = p.stages, SB = p.lo_bufs, O = p.out_bufs, HB = p.h1_bufs, KB = p.KB;   // lo_bufs doubles as B-ring depth
@@ -922,7 +933,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (threadIdx.x == 0) XB_TS(0, 62, 1);
     const bool is_producer = warp == kProducerWarp && lane == 0;
     if (!is_producer) {
+        XB_STEP_STAMP(sts, 201);
         if (pdl_early) pdl_wait();
+        XB_STEP_STAMP(sts, 202);
         pdl_trigger();
     }
 
@@ -1156,6 +1169,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (threadIdx.x == 0) XB_TS(0, 63, 0);
     tc_fence_before();
     __syncthreads();
+    XB_STEP_STAMP(sts, 203);
     if (threadIdx.x == 0) XB_TS(0, 63, 1);
     if (warp == kMmaWarp) {
         tc_fence_after();
@@ -1199,6 +1213,9 @@ static int launch_kmajor_ts(const TMaps& maps, KParams p, cudaStream_t s) {
     p.alt_groups = alt_env >= 0 ? alt_env : 0;
 #ifdef XB_DENSE_TS
     p.ts = g_xb_ts_host;
+#endif
+#ifdef XB_STEP_TS
+    p.sts = g_xb_step_ts;
 #endif
     const int smem = 1024 + bres + bytes() + kMiscBytes;
     auto kern = dense_kmajor_ts_kernel<N, B_RES, MODE>;

@@ -453,13 +453,22 @@ struct RolloutStepArgs {
     // stats.obs_state_in set, x_in holds RAW observations and the stored row is their normalised form (the same arithmetic
     // as the forward kernel's, agent.py:112-113); the next observations' moments are merged into stats.obs_state_out.
     StepStats stats;
+#ifdef XB_STEP_TS
+    unsigned long long* ts;
+#endif
 };
 
 template <class Env>
-__global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs a) {
+__global__ void __launch_bounds__(128) rollout_step_kernel(RolloutStepArgs a) {
     // launched with the programmatic-serialization attribute (common.cuh): resident early, starts when the forward before it
     // has completed; the next forward may then run its weight-only prologue underneath this kernel
+#ifdef XB_STEP_TS
+    unsigned long long* const ts = (blockIdx.x == 0 && threadIdx.x == 0) ? a.ts : nullptr;
+    a.stats.ts = threadIdx.x == 0 ? a.ts : nullptr;
+#endif
+    XB_STEP_STAMP(ts, 100);
     pdl_wait();
+    XB_STEP_STAMP(ts, 101);
     pdl_trigger();
     constexpr int V = Env::kObsVec, D = 4 * V;
     __shared__ double stat_smem[(2 * D + 3) * 32];
@@ -613,6 +622,7 @@ __global__ void __launch_bounds__(128) rollout_step_kernel(const RolloutStepArgs
         }
     }
     }   // e < N
+    XB_STEP_STAMP(ts, 104);
     if (with_stats) step_stats_finish<D>(a.stats, acc, N, stat_smem, &stat_flag);
 }
 
@@ -631,6 +641,11 @@ static inline int env_block(int64_t N) {
 }  // namespace xb
 
 using namespace xb;
+
+#ifdef XB_STEP_TS
+unsigned long long* g_xb_step_ts = nullptr;
+extern "C" int xb_debug_set_step_ts(void* buf) { g_xb_step_ts = (unsigned long long*)buf; return 0; }
+#endif
 
 extern "C" int xb_env_reset(int env_kind, double* state, uint64_t* rng, int32_t* elapsed, double* ep_score,
                             float* obs, int n_draws, int64_t N, xb_stream_t stream) {
@@ -731,6 +746,9 @@ extern "C" int xb_rollout_step(int env_kind, const float* act_param, const float
         a.stats = StepStats{obs_state_in, obs_state_out, obs_dim, obs_clip, ret_state, rew_std_io, returns, gamma, mask_terminal,
                             stat_partials, stat_ticket, stat_sums_out};
     }
+#ifdef XB_STEP_TS
+    a.ts = g_xb_step_ts;
+#endif
     cudaStream_t s = (cudaStream_t)stream;
     int block = env_block(N), grid = ceil_div_i64(N, block);
     if (env_kind == XB_ENV_CARTPOLE) XB_CUDA(launch_pdl(rollout_step_kernel<CartPole>, dim3(grid), dim3(block), 0, s, true, a));

@@ -225,8 +225,9 @@ __global__ void __launch_bounds__(kNormBlock)
 __global__ void rms_merge_sums_kernel(const double* __restrict__ sums, const double* __restrict__ obs_state_in,
                                       double* __restrict__ obs_state_out, int dim, double* __restrict__ ret_state,
                                       float* __restrict__ rew_std) {
-    merge_step_stats<4>(obs_state_in, obs_state_out, dim, ret_state, rew_std, sums, sums + 4, sums[8], sums[9], sums[10], sums[11],
-                        threadIdx.x);
+    const int d = threadIdx.x < 4 ? threadIdx.x : 0;
+    merge_step_stats<4>(obs_state_in, obs_state_out, dim, ret_state, rew_std, sums[d], sums[4 + d], sums[8], sums[9], sums[10],
+                        sums[11], threadIdx.x);
 }
 
 }  // namespace xb
