@@ -412,7 +412,10 @@ int xb_dense_fwd2(const float* X, int64_t M, int K, int N, float slope, const fl
                   const float* bias0, float* Y0, const float* head_w0, const float* head_b0, int n_head0, float* head_out0,
                   const float* Whi1, const float* Wlo1, const float* bias1, float* Y1, const float* head_w1,
                   const float* head_b1, int n_head1, float* head_out1, int b_resident, const float* prep_W0,
-                  const float* prep_W1, float* prep_thi, float* prep_tlo, xb_stream_t stream);
+                  const float* prep_W1, float* prep_thi, float* prep_tlo, uint32_t* sign_out, xb_stream_t stream);
+/*   sign_out (nullable, xb_dense_fwd2 and xb_dense_fwd2_loss): u32 [M][2 * N / 32] activation SIGN WORDS — bit j of word
+ *   [row][layer * N / 32 + c] = (Y_layer[row][32 c + j] > 0).  The backward pass needs the hidden activations only through
+ *   leaky_relu' = (y > 0 ? 1 : slope): xb_dense_dgrad reads these words (32 B per row) instead of the two activation tiles. */
 /*   prep_W0 / prep_W1 / prep_thi / prep_tlo (nullable group, xb_dense_fwd2 and xb_dense_fwd2_loss): the fp32 master weights
  *   [N][N] of the two layers; the launch then also writes the weight operand of the MASK-FORM dgrad that follows:
  *   Wt'[n][s * N + k] = tf32 hi/lo split of w2'_s[k] * W_s[k][n], w2'_s = head_w_s[0] (- head_w_s[1] for a 2-logit head),
@@ -446,7 +449,7 @@ int xb_dense_fwd2_loss(const float* X, int64_t M, int K, int N, float slope, con
                        const float* scal, const double* adv_stats, int64_t adv_count, float clip_range, float vf_coef,
                        float ent_coef, float inv_batch, const float* logstd, float* dact, float* dv, double* loss_partials,
                        uint32_t* loss_ticket, double* scalars, double* dlogstd, const float* prep_W0, const float* prep_W1,
-                       float* prep_thi, float* prep_tlo, xb_stream_t stream);
+                       float* prep_thi, float* prep_tlo, uint32_t* sign_out, xb_stream_t stream);
 int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const float* W0, const float* b0, int64_t M, int H,
                         float slope, const float* Whi0, const float* Wlo0, const float* bias0, float* Y0,
                         const float* head_w0, const float* head_b0, int n_head0, float* head_out0, const float* Whi1,
@@ -455,12 +458,15 @@ int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const float* W0, 
                         float norm_clip, int flags, xb_stream_t stream);
 int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, int K0, const float* Y1,
                    const float* dout1, const float* w2_1, int nh1, int K1, int64_t M, const float* Wthi,
-                   const float* Wtlo, int N, const float* H1, float slope, float* dZ1, int wt_form, xb_stream_t stream);
+                   const float* Wtlo, int N, const float* H1, float slope, float* dZ1, int wt_form, const uint32_t* signs,
+                   xb_stream_t stream);
 /*   wt_form 0: Wthi / Wtlo = the plain transposed weights (xb_dense_split_weights*), any head gradients (nh <= 2).
  *   wt_form 1 ("mask form"): Wthi / Wtlo = the w2-scaled operand written by xb_dense_fwd2(_loss) (prep_*).  Valid when every
  *   source's head gradient is rank-1: one head, or two logits of a softmax head (whose gradients are opposite: dout[:, 1] is
  *   then NOT read, -dout[:, 0] is implied).  The operand warps then select per element between two per-row constants
- *   instead of multiplying and splitting — same 3xTF32 accuracy. */
+ *   instead of multiplying and splitting — same 3xTF32 accuracy.
+ *   signs (nullable): u32 [M][(K0 + K1) / 32] sign words of [Y0 | Y1] as written by xb_dense_fwd2(_loss) (sign_out); used by the
+ *   tensor-memory (N <= 128, K0 + K1 <= 256) kernel in place of Y0 / Y1 (which are then not read) — bit-identical results. */
 
 /* ------------------------------------------------------------------------------------------------------------
  * First (narrow-input) layer of the MLP, Linear(obs_dim, H) + LeakyReLU — Basic_MLP

@@ -425,3 +425,44 @@ def test_native_agent_on_three_action_envs_uses_the_tensor_core_mlp(env_id):
     assert torch.allclose(out[0][1], out[1][1], atol=1e-5, rtol=1e-5)
     assert torch.allclose(out[0][2], out[1][2], atol=2e-5, rtol=2e-4), (out[0][2] - out[1][2]).abs().max()
     assert abs(out[0][3]["critic-loss"] - out[1][3]["critic-loss"]) <= 1e-4 * max(1.0, abs(out[1][3]["critic-loss"]))
+
+
+@pytest.mark.parametrize("env_id,B", [("Pendulum-v1", 65536), ("CartPole-v1", 2048 + 77)])
+def test_sign_words_match_activations_and_dgrad_is_bit_identical(env_id, B):
+    """The forward's activation sign words (one bit per hidden activation) are exactly (y > 0), and the dgrad kernel fed with
+    them produces the bit-identical dZ1 of the kernel that TMA-loads the activation tiles (mask form and plain form)."""
+    import xuanpolicy_b200 as xb
+    from xuanpolicy_b200 import ops
+    from xuanpolicy_b200.fused_mlp import FusedActorCritic
+    from xuanpolicy_b200.policies import make_policy
+    obs_space, act_space = xb.make_spaces(env_id)
+    policy = make_policy(obs_space, act_space, hidden=(128,), device="cuda", seed=5)
+    fused = FusedActorCritic(policy)
+    assert fused.sign_bits
+    g = torch.Generator(device="cuda").manual_seed(B)
+    obs = torch.randn(B, 4, device="cuda", generator=g)[:, :obs_space.shape[0]]
+    act_out, v = fused.forward(obs)
+    b = fused._buf[B]
+    words = b["signs"].view(B, 2, 4).long() & 0xFFFFFFFF
+    for s, y in enumerate((b["ya"], b["yc"])):
+        bits = ((words[:, s, :, None] >> torch.arange(32, device="cuda")) & 1).reshape(B, 128).bool()
+        assert torch.equal(bits, y > 0)
+    A = act_out.shape[1]
+    dact = torch.randn(B, A, device="cuda", generator=g) / B
+    if A == 2:
+        dact[:, 1] = -dact[:, 0]            # softmax pair (what the mask form assumes)
+    dv2 = (torch.randn(B, device="cuda", generator=g) / B).reshape(B, 1)
+    outs = []
+    for signs in (b["signs"], None):
+        for form in (1, 0):
+            dz1 = torch.full((B, 128), float("nan"), device="cuda")
+            if form:
+                ops.dense_dgrad(b["ya"], dact, fused.la2.weight.data, b["yc"], dv2, fused.lc2.weight.data, fused.wtm_hi,
+                                fused.wtm_lo, b["h1"], fused.slope, dz1, wt_form=1, signs=signs)
+            else:
+                ops.dense_dgrad(b["ya"], dact, fused.la2.weight.data, b["yc"], dv2, fused.lc2.weight.data, fused.wt_hi,
+                                fused.wt_lo, b["h1"], fused.slope, dz1, signs=signs)
+            outs.append(dz1)
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])

@@ -62,8 +62,8 @@ def run(which):
     print("k-block iterations recorded (MMA role): %d" % n_it)
     print(" it | producer slot-free | operand: landed, transformed, tmem-free, arrived | mma: wait-start, wait-end, issued")
     for i in range(min(n_it, 40)):
-        print("%3d | %7d | %7d %7d %7d %7d | %7d %7d %7d" % (i, rel(t[0, i, 0]), rel(t[2, i, 0]), rel(t[2, i, 1]), rel(t[2, i, 2]),
-                                                         rel(t[2, i, 3]), rel(t[1, i, 0]), rel(t[1, i, 1]), rel(t[1, i, 3])))
+        print("%3d | %7d | %7d %7d %7d %7d | %7d %7d [%7d %7d %7d] %7d" % (i, rel(t[0, i, 0]), rel(t[2, i, 0]), rel(t[2, i, 1]), rel(t[2, i, 2]),
+                                                         rel(t[2, i, 3]), rel(t[1, i, 0]), rel(t[1, i, 1]), rel(t[1, i, 4]), rel(t[1, i, 5]), rel(t[1, i, 6]), rel(t[1, i, 3])))
     mma = np.array([rel(t[1, i, 3]) for i in range(n_it)])
     if n_it > 8:
         print("MMA issue-to-issue per k-block: mean %.0f cycles (all), median %.0f" % (np.diff(mma).mean(), np.median(np.diff(mma))))

@@ -61,13 +61,14 @@ SIGNATURES = {
     "xb_dense_split_weights2": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp],
     "xb_dense_fwd": [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _f32, _vp, _vp, _vp, _i32, _vp, _i32, _vp],
     "xb_dense_fwd2": [_vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
-                      _vp, _i32, _vp, _vp, _vp, _vp, _vp],
+                      _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
     "xb_dense_fwd2_loss": [_vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                            _i32, _vp, _i32, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                           _vp, _vp],
+                           _vp, _vp, _vp],
     "xb_mlp_fwd_from_obs": [_vp, _i32, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp,
                             _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _f32, _i32, _vp],
-    "xb_dense_dgrad": [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _i32, _vp, _f32, _vp, _i32, _vp],
+    "xb_dense_dgrad": [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _i32, _vp, _f32, _vp, _i32, _vp,
+                       _vp],
     "xb_dense_wgrad_workspace_floats": [_i32],
     "xb_dense_wgrad": [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
                        _vp, _vp, _vp, _vp],

@@ -146,6 +146,13 @@ struct KParams {
     float* prep_thi;            // [H][2H]: Wt'[n][s * H + k]
     float* prep_tlo;
     int prep_H;
+    // Activation SIGN WORDS.  The backward kernels need the hidden activations only through leaky'(y) = (y > 0 ? 1 : slope), so
+    // the FWD epilogue can leave one bit per element: sign_out[row * sign_ld + layer * (N / 32) + c] bit j = (y[row][32 c + j] > 0)
+    // (layer = 0 actor, 1 critic in dual mode), and the TS-form DGRAD reads `signs` [M][KB] (one word per row and k-block, the
+    // same layout) instead of TMA-loading the two activation tiles: no raw A ring, no A loads, a deeper weight ring.
+    uint32_t* sign_out;
+    int sign_ld;
+    const uint32_t* signs;
 };
 
 // Wt'[n][s * H + k] = split_tf32(w2'_s[k] * W_s[k][n]) — `tid` in [0, 128), all CTAs share the work.
@@ -197,6 +204,8 @@ struct EpiCtx {
     bool store_y;      // FWD: false = only the fused head outputs are wanted (rollout / inference)
     FusedLoss loss;    // FWD: fused PPO loss (loss.scal != NULL)
     int sel;           // FWD dual: 0 = actor CTA, 1 = critic CTA
+    uint32_t* sign_out;   // FWD: nullable activation sign words (KParams::sign_out), already offset to this CTA's layer
+    int sign_ld;
     double* red;       // shared memory [4 warps][8] for the per-CTA loss sums
 #ifdef XB_DENSE_TS
     long long* ts;
@@ -209,6 +218,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiCtx& c, int warp, int lan
     constexpr uint32_t kSub = 32 * 128;                               // one warp's sub-tile: 32 rows x 128 B
     const uint32_t bar_h1 = c.bar_h1w + warp * 16;                    // 2 barriers per warp
     uint32_t lt = 0, g = 0;
+    const uint32_t elected = elect_one_pred();     // the lane that issues this warp's TMA loads / stores (and owns its bulk group)
     // fused loss state (FWD only): advantage normalisation, Gaussian constants, this thread's partial sums
     const bool with_loss = MODE == MODE_FWD && c.loss.scal != nullptr;
     float l_mean = 0.f, l_denom = 1.f, l_ls = 0.f, l_inv_var = 1.f;
@@ -228,9 +238,9 @@ __device__ __forceinline__ void epilogue_warp(const EpiCtx& c, int warp, int lan
             l_inv_var = 1.0f / (sd * sd);
         }
     }
-    if (MODE == MODE_DGRAD && lane == 0 && c.tile0 < c.n_tiles) {
-        mbar_arrive_expect_tx(bar_h1, kSub);
-        tma_load_2d(c.h1_ring + warp * kSub, c.map_h1, c.n_off, (int)(c.tile0 * BM + warp * 32), bar_h1);
+    if (MODE == MODE_DGRAD && c.tile0 < c.n_tiles) {
+        mbar_arrive_expect_tx_if(elected, bar_h1, kSub);
+        tma_load_2d_if(elected, c.h1_ring + warp * kSub, c.map_h1, c.n_off, (int)(c.tile0 * BM + warp * 32), bar_h1);
     }
     for (int64_t tile = c.tile0; tile < c.n_tiles; tile += c.tile_step, ++lt) {
         const uint32_t acc = lt & 1, tph = (lt >> 1) & 1;
@@ -251,7 +261,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiCtx& c, int warp, int lan
             tmem_ld_32x32(taddr + cc * 32, v);
             const bool store = MODE != MODE_FWD || c.store_y;
             // the staging sub-tile about to be overwritten must have been read out by its previous TMA store
-            if (lane == 0 && store) {       // at most O - 1 of this warp's stores may still be reading their sub-tiles
+            if (elected && store) {         // at most O - 1 of this warp's stores may still be reading their sub-tiles
                 if (c.O > 3) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
                 else if (c.O == 3) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
                 else if (c.O == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -262,21 +272,22 @@ __device__ __forceinline__ void epilogue_warp(const EpiCtx& c, int warp, int lan
             uint32_t hbuf = 0;
             if (MODE == MODE_DGRAD) {
                 const uint32_t hb = c.HB > 1 ? (g & 1) : 0, hph = c.HB > 1 ? ((g >> 1) & 1) : (g & 1);
-                if (lane == 0) {       // prefetch the next chunk's mask sub-tile (or, single-buffered, load this chunk's now)
+                {                      // prefetch the next chunk's mask sub-tile (or, single-buffered, load this chunk's now)
                     int ncc = cc + (c.HB > 1 ? 1 : 0);
                     int64_t ntile = tile;
                     if (ncc == kChunks) { ncc = 0; ntile = tile + c.tile_step; }
                     if (c.HB > 1 ? ntile < c.n_tiles : g > 0) {
                         const uint32_t nb = c.HB > 1 ? ((g + 1) & 1) : 0;
-                        mbar_arrive_expect_tx(bar_h1 + 8 * nb, kSub);
-                        tma_load_2d(c.h1_ring + nb * kATile + warp * kSub, c.map_h1, c.n_off + ncc * 32,
-                                    (int)(ntile * BM + warp * 32), bar_h1 + 8 * nb);
+                        mbar_arrive_expect_tx_if(elected, bar_h1 + 8 * nb, kSub);
+                        tma_load_2d_if(elected, c.h1_ring + nb * kATile + warp * kSub, c.map_h1, c.n_off + ncc * 32,
+                                       (int)(ntile * BM + warp * 32), bar_h1 + 8 * nb);
                     }
                 }
                 hbuf = c.h1_ring + hb * kATile + warp * kSub;
                 mbar_wait(bar_h1 + 8 * hb, hph);
             }
             tmem_ld_wait();
+            uint32_t sign_word = 0u;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 float4 f = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
@@ -284,6 +295,8 @@ __device__ __forceinline__ void epilogue_warp(const EpiCtx& c, int warp, int lan
                 if (MODE == MODE_FWD) {
                     const float* b = c.sf + cc * 32 + 4 * q;
                     f.x += b[0]; f.y += b[1]; f.z += b[2]; f.w += b[3];
+                    sign_word |= (f.x > 0.f ? 1u : 0u) << (4 * q) | (f.y > 0.f ? 2u : 0u) << (4 * q) |
+                                 (f.z > 0.f ? 4u : 0u) << (4 * q) | (f.w > 0.f ? 8u : 0u) << (4 * q);
                     f.x = f.x > 0.f ? f.x : f.x * c.slope;
                     f.y = f.y > 0.f ? f.y : f.y * c.slope;
                     f.z = f.z > 0.f ? f.z : f.z * c.slope;
@@ -300,13 +313,11 @@ __device__ __forceinline__ void epilogue_warp(const EpiCtx& c, int warp, int lan
                 }
                 if (store) sts128(obuf + sw128_off(lane, q), f);
             }
+            if (MODE == MODE_FWD && c.sign_out && row < c.M) c.sign_out[row * c.sign_ld + cc] = sign_word;
             if (store) {
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
-                    tma_store_2d(c.map_out, obuf, c.n_off + cc * 32, (int)(tile * BM + warp * 32));
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
+                tma_store_2d_commit_if(elected, c.map_out, obuf, c.n_off + cc * 32, (int)(tile * BM + warp * 32));
             }
         }
         tc_fence_before();
@@ -375,7 +386,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiCtx& c, int warp, int lan
             }
         }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (with_loss) {                                                // this warp's sums -> shared memory (finished by the CTA)
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
@@ -656,6 +667,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         c.store_y = MODE != MODE_FWD || p.Y != nullptr;
         c.n_off = 0;
         c.loss = p.loss; c.sel = sel; c.red = reinterpret_cast<double*>(misc_ptr + kLossRedOff);
+        c.sign_out = (MODE == MODE_FWD && p.sign_out) ? p.sign_out + sel * (N / 32) : nullptr;
+        c.sign_ld = p.sign_ld;
 #ifdef XB_DENSE_TS
         c.ts = p.ts;
 #endif
@@ -748,6 +761,12 @@ constexpr int kTA = 4;                    // TMEM A-operand stages
 // function-scope predicate register P (declared once with XB_DECLARE_PREDS at the top of the kernel) and returns at once;
 // `xb_trywait_result_P()` consumes it later.  Independent work placed in between hides the ~250-cycle latency of the
 // check; a false result (phase not complete yet) falls back to the blocking wait.
+// timing experiment only (-DXB_HACK_MMA2: WRONG results): drop the hi x hi MMA of every k-step to measure what a 2-MMA form would cost
+#ifdef XB_HACK_MMA2
+#define XB_MMA3(s) ""
+#else
+#define XB_MMA3(s) s
+#endif
 #define XB_DECLARE_PREDS() asm volatile(".reg .pred xb_pf, xb_pa;")
 #define XB_TRYWAIT_ISSUE(P, bar, parity) \
     asm volatile("mbarrier.test_wait.parity.shared::cta.b64 " #P ", [%0], %1;" ::"r"(bar), "r"(parity) : "memory")
@@ -782,38 +801,42 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 __device__ __forceinline__ uint32_t ts_kblock(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t db_hi,
                                               uint64_t db_lo, uint32_t idesc, uint32_t accumulate_first,
                                               uint32_t next_bar_a, uint32_t next_par_a, uint32_t next_bar_b,
-                                              uint32_t next_par_b, uint32_t commit0, uint32_t commit1, uint32_t commit2) {
+                                              uint32_t next_par_b, uint32_t commit0, uint32_t commit1, uint32_t commit2,
+                                              uint32_t elected) {
     uint32_t ready;
     asm volatile(
         "{\n"
-        ".reg .pred pa, pb, p0, p1, c1, c2;\n"
+        ".reg .pred pa, pb, p0, p1, c1, c2, pe;\n"
+        "setp.ne.b32 pe, %15, 0;\n"
         ".reg .b32 ah, al, r;\n"
         ".reg .b64 bh, bl;\n"
         "setp.ne.b32 p0, %7, 0;\n"
         "setp.ne.b32 p1, 1, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%3], %4, %6, p0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %5, %6, p1;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %4, %6, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [%3], %4, %6, p0;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %5, %6, p1;\n"
+        XB_MMA3("@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [%2], %4, %6, p1;\n")
         "add.u32 ah, %2, 8;  add.u32 al, %3, 8;  add.u64 bh, %4, 2;  add.u64 bl, %5, 2;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al], bh, %6, p1;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bl, %6, p1;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bh, %6, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [al], bh, %6, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bl, %6, p1;\n"
+        XB_MMA3("@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bh, %6, p1;\n")
         // the NEXT k-block's phase checks go out in the middle of the MMA stream (timelines: issued in front of it they
         // mostly come back "not yet" — the operand warps run less than one k-block ahead — and the blocking re-check then
         // costs ~300 cycles in which the tensor pipe drains; issued here the remaining six MMAs still cover their latency)
         "mbarrier.test_wait.parity.shared::cta.b64 pa, [%8], %9;\n"
         "mbarrier.test_wait.parity.shared::cta.b64 pb, [%10], %11;\n"
         "add.u32 ah, %2, 16; add.u32 al, %3, 16; add.u64 bh, %4, 4;  add.u64 bl, %5, 4;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al], bh, %6, p1;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bl, %6, p1;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bh, %6, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [al], bh, %6, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bl, %6, p1;\n"
+        XB_MMA3("@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bh, %6, p1;\n")
         "add.u32 ah, %2, 24; add.u32 al, %3, 24; add.u64 bh, %4, 6;  add.u64 bl, %5, 6;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [al], bh, %6, p1;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bl, %6, p1;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bh, %6, p1;\n"
-        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [al], bh, %6, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bl, %6, p1;\n"
+        XB_MMA3("@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], [ah], bh, %6, p1;\n")
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n"
         "setp.ne.b32 c1, %13, 0;\n"
         "setp.ne.b32 c2, %14, 0;\n"
+        "and.pred c1, c1, pe;\n"
+        "and.pred c2, c2, pe;\n"
         "@c1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%13];\n"
         "@c2 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%14];\n"
         "selp.u32 %0, 1, 0, pa;\n"
@@ -822,10 +845,70 @@ __device__ __forceinline__ uint32_t ts_kblock(uint32_t d_tmem, uint32_t a_hi, ui
         "}\n"
         : "=r"(ready)
         : "r"(d_tmem), "r"(a_hi), "r"(a_lo), "l"(db_hi), "l"(db_lo), "r"(idesc), "r"(accumulate_first), "r"(next_bar_a),
-          "r"(next_par_a), "r"(next_bar_b), "r"(next_par_b), "r"(commit0), "r"(commit1), "r"(commit2)
+          "r"(next_par_a), "r"(next_bar_b), "r"(next_par_b), "r"(commit0), "r"(commit1), "r"(commit2), "r"(elected)
         : "memory");
     return ready;
 }
+
+#ifdef XB_DENSE_TS
+__device__ __forceinline__ uint32_t ts_kblock_timed(long long* tq, uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t db_hi,
+                                              uint64_t db_lo, uint32_t idesc, uint32_t accumulate_first,
+                                              uint32_t next_bar_a, uint32_t next_par_a, uint32_t next_bar_b,
+                                              uint32_t next_par_b, uint32_t commit0, uint32_t commit1, uint32_t commit2,
+                                              uint32_t elected) {
+    uint32_t ready;
+    long long t1, t2, t3;
+    asm volatile(
+        "{\n"
+        ".reg .pred pa, pb, p0, p1, c1, c2, pe;\n"
+        "setp.ne.b32 pe, %18, 0;\n"
+        ".reg .b32 ah, al, r;\n"
+        ".reg .b64 bh, bl;\n"
+        "setp.ne.b32 p0, %10, 0;\n"
+        "setp.ne.b32 p1, 1, 0;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%4], [%6], %7, %9, p0;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%4], [%5], %8, %9, p1;\n"
+        XB_MMA3("@pe tcgen05.mma.cta_group::1.kind::tf32 [%4], [%5], %7, %9, p1;\n")
+        "add.u32 ah, %5, 8;  add.u32 al, %6, 8;  add.u64 bh, %7, 2;  add.u64 bl, %8, 2;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%4], [al], bh, %9, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%4], [ah], bl, %9, p1;\n"
+        XB_MMA3("@pe tcgen05.mma.cta_group::1.kind::tf32 [%4], [ah], bh, %9, p1;\n")
+        // the NEXT k-block's phase checks go out in the middle of the MMA stream (timelines: issued in front of it they
+        // mostly come back "not yet" — the operand warps run less than one k-block ahead — and the blocking re-check then
+        // costs ~300 cycles in which the tensor pipe drains; issued here the remaining six MMAs still cover their latency)
+        "mov.u64 %1, %%clock64;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 pa, [%11], %12;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 pb, [%13], %14;\n"
+        "add.u32 ah, %5, 16; add.u32 al, %6, 16; add.u64 bh, %7, 4;  add.u64 bl, %8, 4;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%4], [al], bh, %9, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%4], [ah], bl, %9, p1;\n"
+        XB_MMA3("@pe tcgen05.mma.cta_group::1.kind::tf32 [%4], [ah], bh, %9, p1;\n")
+        "add.u32 ah, %5, 24; add.u32 al, %6, 24; add.u64 bh, %7, 6;  add.u64 bl, %8, 6;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%4], [al], bh, %9, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%4], [ah], bl, %9, p1;\n"
+        XB_MMA3("@pe tcgen05.mma.cta_group::1.kind::tf32 [%4], [ah], bh, %9, p1;\n")
+        "mov.u64 %2, %%clock64;\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%15];\n"
+        "setp.ne.b32 c1, %16, 0;\n"
+        "setp.ne.b32 c2, %17, 0;\n"
+        "and.pred c1, c1, pe;\n"
+        "and.pred c2, c2, pe;\n"
+        "@c1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%16];\n"
+        "@c2 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%17];\n"
+        "mov.u64 %3, %%clock64;\n"
+        "selp.u32 %0, 1, 0, pa;\n"
+        "selp.u32 r, 2, 0, pb;\n"
+        "or.b32 %0, %0, r;\n"
+        "}\n"
+        : "=r"(ready), "=l"(t1), "=l"(t2), "=l"(t3)
+        : "r"(d_tmem), "r"(a_hi), "r"(a_lo), "l"(db_hi), "l"(db_lo), "r"(idesc), "r"(accumulate_first), "r"(next_bar_a),
+          "r"(next_par_a), "r"(next_bar_b), "r"(next_par_b), "r"(commit0), "r"(commit1), "r"(commit2), "r"(elected)
+        : "memory");
+    if (tq) { tq[4] = t1; tq[5] = t2; tq[6] = t3; }
+    return ready;
+}
+
+#endif
 
 template <int N, bool B_RES, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -931,7 +1014,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     if (threadIdx.x == 0) XB_TS(0, 62, 1);
-    const bool is_producer = warp == kProducerWarp && lane == 0;
+    const bool is_producer = warp == kProducerWarp;     // (the whole warp: it walks the producer loop converged)
     if (!is_producer) {
         XB_STEP_STAMP(sts, 201);
         if (pdl_early) pdl_wait();
@@ -940,17 +1023,22 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
 
     if (warp == kProducerWarp) {
-        // ============================================================ TMA producer (one thread)
-        if (lane == 0) {
-            tma_prefetch_desc(map_a0);
-            tma_prefetch_desc(map_bhi);
-            tma_prefetch_desc(map_blo);
-            if (MODE == MODE_DGRAD) tma_prefetch_desc(map_a1);
+        // ============================================================ TMA producer: the whole warp walks the loop, one elected
+        // lane issues (uniform operands: no R2UR waterfall around every UTMALDG, see tma_load_2d_if)
+        {
+            const uint32_t elected = elect_one_pred();
+            if (lane == 0) {
+                tma_prefetch_desc(map_a0);
+                tma_prefetch_desc(map_bhi);
+                tma_prefetch_desc(map_blo);
+                if (MODE == MODE_DGRAD) tma_prefetch_desc(map_a1);
+            }
+            __syncwarp();
             if (B_RES) {
-                mbar_arrive_expect_tx(bar_bfull, 2u * KB * kBTile);
+                mbar_arrive_expect_tx_if(elected, bar_bfull, 2u * KB * kBTile);
                 for (int kb = 0; kb < KB; ++kb) {
-                    tma_load_2d(bres + kb * kBTile, map_bhi, kb * BK, n_off, bar_bfull);
-                    tma_load_2d(bres + (KB + kb) * kBTile, map_blo, kb * BK, n_off, bar_bfull);
+                    tma_load_2d_if(elected, bres + kb * kBTile, map_bhi, kb * BK, n_off, bar_bfull);
+                    tma_load_2d_if(elected, bres + (KB + kb) * kBTile, map_blo, kb * BK, n_off, bar_bfull);
                 }
             }
             if (pdl_early) pdl_wait();          // (the resident weights are on their way; activations only from here)
@@ -958,29 +1046,35 @@ __global__ void __launch_bounds__(kThreads, 1)
             uint32_t s = 0, ph = 0, sb = 0, bph = 0, it = 0;
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
                 for (int kb = 0; kb < KB; ++kb, ++it) {
-                    if (!(MODE == MODE_FWD && p.obs)) {
+                    if (!(MODE == MODE_FWD && p.obs) && !(MODE == MODE_DGRAD && p.signs)) {
                         mbar_wait(bar_empty + 8 * s, ph ^ 1);
                         XB_TS(0, it, 0);
-                        mbar_arrive_expect_tx(bar_full + 8 * s, kATile);
+                        mbar_arrive_expect_tx_if(elected, bar_full + 8 * s, kATile);
                         const bool src1 = (MODE == MODE_DGRAD) && kb >= p.kb_split;
                         const int kcol = (src1 ? kb - p.kb_split : kb) * BK;
-                        tma_load_2d(ring + s * kATile, src1 ? map_a1 : map_a0, kcol, (int)(tile * BM), bar_full + 8 * s);
+                        tma_load_2d_if(elected, ring + s * kATile, src1 ? map_a1 : map_a0, kcol, (int)(tile * BM), bar_full + 8 * s);
                         if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                     }
                     if (!B_RES) {
                         mbar_wait(bar_bempty + 8 * sb, bph ^ 1);
                         const uint32_t bs = b_ring + sb * 2 * kBTile;
-                        mbar_arrive_expect_tx(bar_bfull_r + 8 * sb, 2 * kBTile);
-                        tma_load_2d(bs, map_bhi, kb * BK, n_off, bar_bfull_r + 8 * sb);
-                        tma_load_2d(bs + kBTile, map_blo, kb * BK, n_off, bar_bfull_r + 8 * sb);
+                        mbar_arrive_expect_tx_if(elected, bar_bfull_r + 8 * sb, 2 * kBTile);
+                        tma_load_2d_if(elected, bs, map_bhi, kb * BK, n_off, bar_bfull_r + 8 * sb);
+                        tma_load_2d_if(elected, bs + kBTile, map_blo, kb * BK, n_off, bar_bfull_r + 8 * sb);
                         if (++sb == (uint32_t)SB) { sb = 0; bph ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == kMmaWarp) {
-        // ============================================================ MMA issuer (one thread)
-        if (lane == 0) {
+        // ============================================================ MMA issuer
+        // The WHOLE warp walks the loop and one elected lane issues: with the loop inside `if (lane == 0)` every descriptor /
+        // address operand of tcgen05.mma lives in a per-thread register and ptxas wraps each instruction in an ELECT + 4 x
+        // R2UR.BROADCAST "waterfall" (~80 cycles per MMA in the issuing thread — more than the 64 cycles the MMA itself takes:
+        // the timelines' real limiter).  Warp-uniform operands go through the uniform datapath instead.
+        {
+            const uint32_t elected = elect_one_pred();
+            const uint32_t tmem_base_u = __reduce_max_sync(0xffffffffu, tmem_base);     // same value, provably warp-uniform
             if (B_RES) mbar_wait(bar_bfull, 0);
             // a barrier/parity pair that always tests complete, for the unused prefetch slot
             const uint32_t dummy_bar = bar_bfull, dummy_par = B_RES ? 0u : 1u;
@@ -989,23 +1083,28 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++lt) {
                 const uint32_t acc = lt & 1, tph = (lt >> 1) & 1;
                 mbar_wait(bar_tempty + 8 * acc, tph ^ 1);
-                const uint32_t d_tmem = tmem_base + acc * N;
+                const uint32_t d_tmem = tmem_base_u + acc * N;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     XB_TS(1, it, 0);
                     if (!(ready & 1)) mbar_wait(bar_conv + 8 * ta, aph);
                     if (!B_RES && !(ready & 2)) mbar_wait(bar_bfull_r + 8 * sb, bph);
                     XB_TS(1, it, 1);
                     tc_fence_after();
-                    const uint32_t a_hi = tmem_base + kACol + ta * 64, a_lo = a_hi + 32;
+                    const uint32_t a_hi = tmem_base_u + kACol + ta * 64, a_lo = a_hi + 32;
                     const uint32_t b_hi = B_RES ? bres + kb * kBTile : b_ring + sb * 2 * kBTile;
                     const uint32_t b_lo = B_RES ? bres + (KB + kb) * kBTile : b_hi + kBTile;
                     // next k-block's stages (the tile boundary does not matter: the rings run continuously)
                     const uint32_t nta = ta + 1 == kTA ? 0 : ta + 1, naph = ta + 1 == kTA ? aph ^ 1 : aph;
                     const uint32_t nsb = sb + 1 == (uint32_t)SB ? 0 : sb + 1, nbph = sb + 1 == (uint32_t)SB ? bph ^ 1 : bph;
+#ifdef XB_DENSE_TS
+                    ready = ts_kblock_timed((p.ts && blockIdx.x == 0 && it < 64) ? p.ts + (1 * 64 + it) * 8 : nullptr,
+                                      d_tmem, a_hi, a_lo, umma_desc_sw128(b_hi, 16, 1024), umma_desc_sw128(b_lo, 16, 1024),
+#else
                     ready = ts_kblock(d_tmem, a_hi, a_lo, umma_desc_sw128(b_hi, 16, 1024), umma_desc_sw128(b_lo, 16, 1024),
+#endif
                                       kIdesc, kb != 0, bar_conv + 8 * nta, naph, B_RES ? dummy_bar : bar_bfull_r + 8 * nsb,
                                       B_RES ? dummy_par : nbph, bar_aempty + 8 * ta, B_RES ? 0u : bar_bempty + 8 * sb,
-                                      kb == KB - 1 ? bar_tfull + 8 * acc : 0u);
+                                      kb == KB - 1 ? bar_tfull + 8 * acc : 0u, elected);
                     XB_TS(1, it, 3);
                     ta = nta; aph = naph;
                     if (!B_RES) { sb = nsb; bph = nbph; }
@@ -1018,7 +1117,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int r = 32 * lq + lane;                     // row of the tile = TMEM lane
         const uint32_t lane_base = (uint32_t)(32 * lq) << 16;
         uint32_t s = 0, ph = 0, ta = 0, aph = 0, it = 0;
-        const bool from_obs = MODE == MODE_FWD && p.obs != nullptr;
+        const bool from_bits = MODE == MODE_DGRAD && p.signs != nullptr;    // activation sign words instead of activation tiles
+        const bool from_obs = (MODE == MODE_FWD && p.obs != nullptr) || from_bits;   // = no raw A ring: the operand is generated
         const bool alt = p.alt_groups != 0;     // ch is then the GROUP (k-block parity) instead of the column half
         if (!from_obs && !alt && tile0 < n_tiles) XB_TRYWAIT_ISSUE(xb_pf, bar_full + 8 * s, ph);    // first stage's phase check
         for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
@@ -1040,8 +1140,17 @@ __global__ void __launch_bounds__(kThreads, 1)
                 split_tf32(d10, m1ph, m1pl);
                 split_tf32(d10 * p.slope, m1qh, m1ql);
             }
+            uint32_t sw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};       // from_bits: this row's sign words (KB <= 8)
+            if (from_bits) {
+                const int64_t row = tile * BM + r;
+                if (row < p.M) {
+                    const uint32_t* sp = p.signs + row * KB;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) sw[j] = j < KB ? __ldg(sp + j) : 0u;
+                }
+            }
             float o4[4] = {0.f, 0.f, 0.f, 0.f};
-            if (from_obs) {
+            if (MODE == MODE_FWD && from_obs) {
                 const int64_t row = tile * BM + r;
                 if (row < p.M) {
                     for (int i = 0; i < p.obs_dim; ++i) o4[i] = __ldg(p.obs + row * p.obs_ld + i);
@@ -1076,7 +1185,14 @@ __global__ void __launch_bounds__(kThreads, 1)
                 for (int hh = 0; hh < n_half; ++hh) {
                     const int chh = alt ? hh : ch;             // which 16 of the 32 k-columns
                     float x[16];
-                    if (from_obs) {                       // trunk layer on the fly: x = leaky(b0 + W0 obs)
+                    uint32_t w16 = 0u;                    // from_bits: the 16 sign bits of this thread's columns
+                    if (from_bits) {
+                        if (!alt) XB_TRYWAIT_ISSUE(xb_pa, bar_aempty + 8 * ta, aph ^ 1);
+                        uint32_t word = sw[0];
+#pragma unroll
+                        for (int j = 1; j < 8; ++j) word = kb == j ? sw[j] : word;
+                        w16 = word >> (16 * chh);
+                    } else if (from_obs) {                // trunk layer on the fly: x = leaky(b0 + W0 obs)
                         if (!alt) XB_TRYWAIT_ISSUE(xb_pa, bar_aempty + 8 * ta, aph ^ 1);
                         const int K = KB * BK;
                         const float* w = sf + 3 * N + kb * BK + 16 * chh;
@@ -1103,19 +1219,33 @@ __global__ void __launch_bounds__(kThreads, 1)
                     if (MODE == MODE_DGRAD && p.mask_form) {
                         const int src = kb >= p.kb_split;
                         const float ph_ = src ? m1ph : m0ph, pl_ = src ? m1pl : m0pl, qh_ = src ? m1qh : m0qh, ql_ = src ? m1ql : m0ql;
+                        if (from_bits) {
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) {
-                            const bool pos = x[q] > 0.f;
-                            hi[q] = pos ? ph_ : qh_;
-                            lo[q] = pos ? pl_ : ql_;
+                            for (int q = 0; q < 16; ++q) {
+                                const bool pos = (w16 >> q) & 1u;
+                                hi[q] = pos ? ph_ : qh_;
+                                lo[q] = pos ? pl_ : ql_;
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {
+                                const bool pos = x[q] > 0.f;
+                                hi[q] = pos ? ph_ : qh_;
+                                lo[q] = pos ? pl_ : ql_;
+                            }
                         }
                     } else {
                         if (MODE == MODE_DGRAD) {
                             const int src = kb >= p.kb_split;
                             const float* w = sf + src * 512 + (src ? kb - p.kb_split : kb) * BK + 16 * chh;
                             const float e0 = src ? d10 : d00, e1 = src ? d11 : d01;
+                            if (from_bits) {
 #pragma unroll
-                            for (int q = 0; q < 16; ++q) x[q] = (e0 * w[q] + e1 * w[256 + q]) * (x[q] > 0.f ? 1.f : p.slope);
+                                for (int q = 0; q < 16; ++q) x[q] = (e0 * w[q] + e1 * w[256 + q]) * (((w16 >> q) & 1u) ? 1.f : p.slope);
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) x[q] = (e0 * w[q] + e1 * w[256 + q]) * (x[q] > 0.f ? 1.f : p.slope);
+                            }
                         }
 #pragma unroll
                         for (int q = 0; q < 16; ++q) split_tf32(x[q], hi[q], lo[q]);
@@ -1159,6 +1289,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         c.store_y = MODE != MODE_FWD || p.Y != nullptr;
         c.n_off = n_off;
         c.loss = p.loss; c.sel = sel; c.red = reinterpret_cast<double*>(misc_ptr + kLossRedOff);
+        c.sign_out = (MODE == MODE_FWD && p.sign_out) ? p.sign_out + sel * (N / 32) : nullptr;
+        c.sign_ld = p.sign_ld;
 #ifdef XB_DENSE_TS
         c.ts = p.ts;
 #endif
@@ -1186,20 +1318,22 @@ static int launch_kmajor_ts(const TMaps& maps, KParams p, cudaStream_t s) {
     const int bres = B_RES ? 2 * p.KB * kBTile : 0;
     const int avail = kMaxSmem - 1024 - kMiscBytes - bres;
     // minimum: 2 raw stages, (2 weight stages), 1 staging tile (+ 1 mask tile); then deepen
-    int S = 2, SB = B_RES ? 0 : 2, O = 1, HB = MODE == MODE_DGRAD ? 1 : 0;
+    const bool no_raw = MODE == MODE_DGRAD && p.signs != nullptr;    // sign words: no raw A ring, a deeper weight ring instead
+    int S = no_raw ? 0 : 2, SB = B_RES ? 0 : 2, O = 1, HB = MODE == MODE_DGRAD ? 1 : 0;
     auto bytes = [&]() { return (S + O + HB) * kATile + SB * 2 * kBTile; };
     if (bytes() > avail) return XB_E_UNSUPPORTED;
     ++O; if (bytes() > avail) --O;
     if (MODE == MODE_DGRAD) { ++HB; if (bytes() > avail) --HB; }
-    while (S < 4) { ++S; if (bytes() > avail) { --S; break; } }
+    while (!no_raw && S < 4) { ++S; if (bytes() > avail) { --S; break; } }
     if (!B_RES) { ++SB; if (bytes() > avail) --SB; }
+    if (!B_RES && no_raw && SB == 3) { ++SB; if (bytes() > avail) --SB; }      // (4 weight-stage barriers exist)
     {   // experiment knobs: XB_DENSE_S / XB_DENSE_O override the ring depths when they fit
         static const int s_env = []() { const char* e = getenv("XB_DENSE_S"); return e ? atoi(e) : 0; }();
         static const int o_env = []() { const char* e = getenv("XB_DENSE_O"); return e ? atoi(e) : 0; }();
         static const int sb_env = []() { const char* e = getenv("XB_DENSE_SB"); return e ? atoi(e) : 0; }();
         static const int hb_env = []() { const char* e = getenv("XB_DENSE_HB"); return e ? atoi(e) : 0; }();
         const int S0 = S, O0 = O, SB0 = SB, HB0 = HB;
-        if (s_env >= 2 && s_env <= 4) S = s_env;
+        if (!no_raw && s_env >= 2 && s_env <= 4) S = s_env;
         if (o_env >= 1 && o_env <= 4) O = o_env;
         if (!B_RES && sb_env >= 2 && sb_env <= 4) SB = sb_env;
         if (MODE == MODE_DGRAD && hb_env >= 1 && hb_env <= 2) HB = hb_env;
@@ -1210,7 +1344,7 @@ static int launch_kmajor_ts(const TMaps& maps, KParams p, cudaStream_t s) {
     p.out_bufs = O;
     p.h1_bufs = HB;
     static const int alt_env = []() { const char* e = getenv("XB_DENSE_ALT"); return e ? atoi(e) : -1; }();
-    p.alt_groups = alt_env >= 0 ? alt_env : 0;
+    p.alt_groups = alt_env >= 0 ? alt_env : (no_raw ? 1 : 0);    // sign-word DGRAD: two groups of 4 operand warps on alternate k-blocks (measured -5 %)
 #ifdef XB_DENSE_TS
     p.ts = g_xb_ts_host;
 #endif
@@ -1230,7 +1364,8 @@ static int launch_kmajor_ts(const TMaps& maps, KParams p, cudaStream_t s) {
 }
 
 template <int MODE>
-static int dispatch_kmajor(int N, bool bres, const TMaps& maps, const KParams& p, cudaStream_t s) {
+static int dispatch_kmajor(int N, bool bres, const TMaps& maps, const KParams& p_in, cudaStream_t s) {
+    const KParams& p = p_in;
     const int kBTile = N * BK * 4;
     static const bool use_ts = []() { const char* e = getenv("XB_DENSE_SS"); return !(e && e[0] == '1'); }();
     if (use_ts && MODE == MODE_DGRAD && p.n_split == 2 && N == 128)      // two CTAs per tile, 64 columns each, weights resident
@@ -1244,13 +1379,15 @@ static int dispatch_kmajor(int N, bool bres, const TMaps& maps, const KParams& p
         return XB_E_UNSUPPORTED;
     }
     if (bres && (kMaxSmem - 1024 - kMiscBytes - 2 * p.KB * kBTile) < (2 + 1 + 1 + (MODE == MODE_DGRAD)) * kATile) bres = false;
+    KParams q = p_in;
+    q.signs = nullptr;          // the SS-form DGRAD reads the activation tiles
     switch (N) {
         case 64:
-            return bres ? launch_kmajor<64, true, MODE>(maps, p, s) : launch_kmajor<64, false, MODE>(maps, p, s);
+            return bres ? launch_kmajor<64, true, MODE>(maps, q, s) : launch_kmajor<64, false, MODE>(maps, q, s);
         case 128:
-            return bres ? launch_kmajor<128, true, MODE>(maps, p, s) : launch_kmajor<128, false, MODE>(maps, p, s);
+            return bres ? launch_kmajor<128, true, MODE>(maps, q, s) : launch_kmajor<128, false, MODE>(maps, q, s);
         case 256:
-            return launch_kmajor<256, false, MODE>(maps, p, s);
+            return launch_kmajor<256, false, MODE>(maps, q, s);
         default:
             return XB_E_UNSUPPORTED;
     }
@@ -1272,39 +1409,41 @@ static int dispatch_kmajor(int N, bool bres, const TMaps& maps, const KParams& p
 __device__ __forceinline__ uint32_t ss_kblock_mn(uint32_t d_tmem, uint64_t da_hi, uint64_t da_lo, uint64_t db_hi,
                                                  uint64_t db_lo, uint32_t idesc, uint32_t accumulate_first,
                                                  uint32_t next_bar, uint32_t next_par, uint32_t commit0,
-                                                 uint32_t commit1, uint32_t commit2) {
+                                                 uint32_t commit1, uint32_t commit2, uint32_t elected) {
     uint32_t ready;
     asm volatile(
         "{\n"
-        ".reg .pred pn, p0, p1, c2;\n"
+        ".reg .pred pn, p0, p1, c2, pe;\n"
+        "setp.ne.b32 pe, %13, 0;\n"
         ".reg .b64 ah, al, bh, bl;\n"
         "mbarrier.test_wait.parity.shared::cta.b64 pn, [%8], %9;\n"
         "setp.ne.b32 p0, %7, 0;\n"
         "setp.ne.b32 p1, 1, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %4, %6, p0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], %2, %5, %6, p1;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], %2, %4, %6, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %4, %6, p0;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], %2, %5, %6, p1;\n"
+        XB_MMA3("@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], %2, %4, %6, p1;\n")
         "add.u64 ah, %2, 64;  add.u64 al, %3, 64;  add.u64 bh, %4, 64;  add.u64 bl, %5, 64;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bh, %6, p1;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bl, %6, p1;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bh, %6, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bh, %6, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bl, %6, p1;\n"
+        XB_MMA3("@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bh, %6, p1;\n")
         "add.u64 ah, %2, 128; add.u64 al, %3, 128; add.u64 bh, %4, 128; add.u64 bl, %5, 128;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bh, %6, p1;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bl, %6, p1;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bh, %6, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bh, %6, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bl, %6, p1;\n"
+        XB_MMA3("@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bh, %6, p1;\n")
         "add.u64 ah, %2, 192; add.u64 al, %3, 192; add.u64 bh, %4, 192; add.u64 bl, %5, 192;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bh, %6, p1;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bl, %6, p1;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bh, %6, p1;\n"
-        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n"
-        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], al, bh, %6, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bl, %6, p1;\n"
+        XB_MMA3("@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], ah, bh, %6, p1;\n")
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n"
         "setp.ne.b32 c2, %12, 0;\n"
+        "and.pred c2, c2, pe;\n"
         "@c2 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n"
         "selp.u32 %0, 1, 0, pn;\n"
         "}\n"
         : "=r"(ready)
         : "r"(d_tmem), "l"(da_hi), "l"(da_lo), "l"(db_hi), "l"(db_lo), "r"(idesc), "r"(accumulate_first), "r"(next_bar),
-          "r"(next_par), "r"(commit0), "r"(commit1), "r"(commit2)
+          "r"(next_par), "r"(commit0), "r"(commit1), "r"(commit2), "r"(elected)
         : "memory");
     return ready;
 }
@@ -1374,27 +1513,35 @@ __global__ void __launch_bounds__(kThreads, 1)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == kProducerWarp) {
-        // ============================================================ TMA producer
-        if (lane == 0) {
+        // ============================================================ TMA producer (whole warp walks, one elected lane issues)
+        {
+            const uint32_t elected = elect_one_pred();
             const CUtensorMap* my = src ? &map_y1 : &map_y0;
-            tma_prefetch_desc(my);
-            tma_prefetch_desc(&map_x);
+            if (lane == 0) {
+                tma_prefetch_desc(my);
+                tma_prefetch_desc(&map_x);
+            }
+            __syncwarp();
+            uint32_t s = 0, ph = 0;
             for (int it = 0; it < nkb; ++it) {
-                const uint32_t s = it % S, ph = (it / S) & 1;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
                 XB_TS(0, it, 0);
                 const uint32_t st = ring + s * kStage;
-                mbar_arrive_expect_tx(bar_full + 8 * s, kStage);
+                mbar_arrive_expect_tx_if(elected, bar_full + 8 * s, kStage);
                 const int row = (int)((blk0 + it) * 32);
 #pragma unroll
-                for (int g = 0; g < 4; ++g) tma_load_2d(st + g * kBox, my, m0 + g * 32, row, bar_full + 8 * s);
+                for (int g = 0; g < 4; ++g) tma_load_2d_if(elected, st + g * kBox, my, m0 + g * 32, row, bar_full + 8 * s);
 #pragma unroll
-                for (int g = 0; g < NBX; ++g) tma_load_2d(st + (4 + g) * kBox, &map_x, g * 32, row, bar_full + 8 * s);
+                for (int g = 0; g < NBX; ++g) tma_load_2d_if(elected, st + (4 + g) * kBox, &map_x, g * 32, row, bar_full + 8 * s);
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == kMmaWarp) {
-        // ============================================================ MMA issuer (one thread)
-        if (lane == 0) {
+        // ============================================================ MMA issuer: the whole warp walks the loop, one elected lane
+        // issues (warp-uniform descriptors go through the uniform datapath — see the K-major TS kernel)
+        {
+            const uint32_t elected = elect_one_pred();
+            const uint32_t tmem_base_u = __reduce_max_sync(0xffffffffu, tmem_base);
             uint32_t s = 0, ph = 0, j = 0, ready = 0;
             for (int it = 0; it < nkb; ++it) {
                 XB_TS(1, it, 0);
@@ -1404,10 +1551,10 @@ __global__ void __launch_bounds__(kThreads, 1)
                 const uint32_t a_hi = ring + s * kStage, b_hi = a_hi + 4 * kBox;
                 const uint32_t a_lo = lo_ring + j * kStage, b_lo = a_lo + 4 * kBox;
                 const uint32_t ns = s + 1 == (uint32_t)S ? 0 : s + 1, nph = s + 1 == (uint32_t)S ? ph ^ 1 : ph;
-                ready = ss_kblock_mn(tmem_base, umma_desc_sw128_base32(a_hi, kBox, 512), umma_desc_sw128_base32(a_lo, kBox, 512),
+                ready = ss_kblock_mn(tmem_base_u, umma_desc_sw128_base32(a_hi, kBox, 512), umma_desc_sw128_base32(a_lo, kBox, 512),
                                      umma_desc_sw128_base32(b_hi, kBox, 512), umma_desc_sw128_base32(b_lo, kBox, 512),
                                      kIdescMain, it != 0, bar_conv + 8 * ns, nph, bar_empty + 8 * s, bar_loempty + 8 * j,
-                                     it == nkb - 1 ? bar_tfull : 0u);
+                                     it == nkb - 1 ? bar_tfull : 0u, elected);
                 XB_TS(1, it, 3);
                 s = ns;
                 ph = nph;
@@ -1743,7 +1890,7 @@ static int dense_fwd_impl(const float* X, const TrunkArgs* trunk, int64_t M, int
                           const float* const* Wlo, const float* const* bias, float* const* Y, const float* const* head_w,
                           const float* const* head_b, const int* n_head, float* const* head_out, int b_resident,
                           xb_stream_t stream, const FusedLoss* loss = nullptr, const float* const* prep_W = nullptr,
-                          float* prep_thi = nullptr, float* prep_tlo = nullptr) {
+                          float* prep_thi = nullptr, float* prep_tlo = nullptr, uint32_t* sign_out = nullptr) {
     if ((!X && !trunk) || M <= 0) return XB_E_BADARG;
     if (K % BK != 0 || K < BK || K > 256 || (X && !al16(X))) return XB_E_UNSUPPORTED;
     if (trunk && (!trunk->obs || !trunk->W0 || !trunk->b0 || trunk->obs_dim < 1 || trunk->obs_dim > 4 ||
@@ -1818,6 +1965,8 @@ static int dense_fwd_impl(const float* X, const TrunkArgs* trunk, int64_t M, int
         p.prep_tlo = prep_tlo;
         p.prep_H = N;
     }
+    p.sign_out = sign_out;
+    p.sign_ld = n_layers * (N / 32);
     return dispatch_kmajor<MODE_FWD>(N, b_resident != 0, maps, p, (cudaStream_t)stream);
 }
 
@@ -1832,7 +1981,8 @@ extern "C" int xb_dense_fwd2(const float* X, int64_t M, int K, int N, float slop
                              const float* bias0, float* Y0, const float* head_w0, const float* head_b0, int n_head0,
                              float* head_out0, const float* Whi1, const float* Wlo1, const float* bias1, float* Y1,
                              const float* head_w1, const float* head_b1, int n_head1, float* head_out1, int b_resident,
-                             const float* prep_W0, const float* prep_W1, float* prep_thi, float* prep_tlo, xb_stream_t stream) {
+                             const float* prep_W0, const float* prep_W1, float* prep_thi, float* prep_tlo, uint32_t* sign_out,
+                             xb_stream_t stream) {
     const float* Whi[2] = {Whi0, Whi1};
     const float* Wlo[2] = {Wlo0, Wlo1};
     const float* bias[2] = {bias0, bias1};
@@ -1843,7 +1993,7 @@ extern "C" int xb_dense_fwd2(const float* X, int64_t M, int K, int N, float slop
     float* ho[2] = {head_out0, head_out1};
     const float* pw[2] = {prep_W0, prep_W1};
     return dense_fwd_impl(X, nullptr, M, K, N, slope, 2, Whi, Wlo, bias, Y, hw, hb, nh, ho, b_resident, stream, nullptr, pw,
-                          prep_thi, prep_tlo);
+                          prep_thi, prep_tlo, sign_out);
 }
 
 extern "C" int xb_dense_fwd2_loss(const float* X, int64_t M, int K, int N, float slope, const float* Whi0, const float* Wlo0,
@@ -1854,7 +2004,7 @@ extern "C" int xb_dense_fwd2_loss(const float* X, int64_t M, int K, int N, float
                                   float vf_coef, float ent_coef, float inv_batch, const float* logstd, float* dact, float* dv,
                                   double* loss_partials, uint32_t* loss_ticket, double* scalars, double* dlogstd,
                                   const float* prep_W0, const float* prep_W1, float* prep_thi, float* prep_tlo,
-                                  xb_stream_t stream) {
+                                  uint32_t* sign_out, xb_stream_t stream) {
     if (!scal || !dact || !dv || !loss_partials || !loss_ticket || !scalars) return XB_E_BADARG;
     if (adv_stats && adv_count <= 0) return XB_E_BADARG;
     if (logstd && !dlogstd) return XB_E_BADARG;
@@ -1871,7 +2021,7 @@ extern "C" int xb_dense_fwd2_loss(const float* X, int64_t M, int K, int N, float
                 inv_batch, logstd ? 1 : 0, logstd, dact, dv, loss_partials, loss_ticket, scalars, dlogstd};
     const float* pw[2] = {prep_W0, prep_W1};
     return dense_fwd_impl(X, nullptr, M, K, N, slope, 2, Whi, Wlo, bias, Y, hw, hb, nh, ho, b_resident, stream, &L, pw, prep_thi,
-                          prep_tlo);
+                          prep_tlo, sign_out);
 }
 
 extern "C" int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const float* W0, const float* b0, int64_t M, int H,
@@ -1897,7 +2047,7 @@ extern "C" int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const 
 extern "C" int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, int K0, const float* Y1,
                               const float* dout1, const float* w2_1, int nh1, int K1, int64_t M, const float* Wthi,
                               const float* Wtlo, int N, const float* H1, float slope, float* dZ1, int wt_form,
-                              xb_stream_t stream) {
+                              const uint32_t* signs, xb_stream_t stream) {
     if (wt_form != 0 && wt_form != 1) return XB_E_BADARG;
     if (!Y0 || !dout0 || !w2_0 || !Wthi || !Wtlo || !H1 || !dZ1 || M <= 0) return XB_E_BADARG;
     if (K0 % BK != 0 || K0 < BK || K0 > 256 || nh0 < 1 || nh0 > 2) return XB_E_UNSUPPORTED;
@@ -1933,6 +2083,7 @@ extern "C" int xb_dense_dgrad(const float* Y0, const float* dout0, const float* 
     p.dZ1 = dZ1;
     p.n_split = split ? 2 : 1;
     p.mask_form = wt_form;
+    p.signs = (K / BK <= 8) ? signs : nullptr;       // (the operand warps keep a row's <= 8 words in registers)
     return dispatch_kmajor<MODE_DGRAD>(N, false, maps, p, (cudaStream_t)stream);
 }
 

@@ -23,6 +23,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// 1 in exactly one lane of the (fully converged) warp, 0 in the others
+__device__ __forceinline__ uint32_t elect_one_pred() {
+    uint32_t e;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(e));
+    return e;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     // bounded: a protocol bug traps (launch error) instead of hanging the GPU
     uint32_t done = 0, spins = 0;
@@ -45,6 +57,40 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(smem_dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+// Predicated forms for a fully converged warp in which ONE lane (`elected`, from elect_one_pred) issues: the operands stay
+// warp-uniform, so ptxas feeds the uniform-datapath instruction (UTMALDG / UTMASTG / UTCHMMA / UTCBAR) from uniform registers.
+// Inside `if (lane == 0)` the same operands are per-thread registers and every such instruction is wrapped in an
+// ELECT + R2UR.BROADCAST "waterfall" loop (~80 cycles each, measured on the tcgen05.mma stream).
+__device__ __forceinline__ void tma_load_2d_if(uint32_t elected, uint32_t smem_dst, const CUtensorMap* map, int c0, int c1,
+                                               uint32_t bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe;\n"
+        "setp.ne.b32 pe, %5, 0;\n"
+        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+        "}\n" ::"r"(smem_dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar), "r"(elected)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_if(uint32_t elected, uint32_t bar, uint32_t bytes) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe;\n"
+        "setp.ne.b32 pe, %2, 0;\n"
+        "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+        "}\n" ::"r"(bar), "r"(bytes), "r"(elected)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_commit_if(uint32_t elected, const CUtensorMap* map, uint32_t smem_src, int c0,
+                                                       int c1) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe;\n"
+        "setp.ne.b32 pe, %4, 0;\n"
+        "@pe cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n"
+        "@pe cp.async.bulk.commit_group;\n"
+        "}\n" ::"l"((uint64_t)map), "r"(c0), "r"(c1), "r"(smem_src), "r"(elected)
         : "memory");
 }
 // shared -> global tile store, tracked by the issuing thread's bulk async-group (commit_group / wait_group)

@@ -92,6 +92,8 @@ class FusedActorCritic:
         # mask-form dgrad operand (w2-scaled transposed weights), rewritten by every training forward (stage_hidden)
         self.wtm_hi, self.wtm_lo = z(H, 2 * H), z(H, 2 * H)
         self.mask_dgrad = os.environ.get("XB_MASK_DGRAD", "1") != "0"
+        # activation sign words: the forward leaves one bit per hidden activation, dgrad reads those instead of ya / yc
+        self.sign_bits = os.environ.get("XB_SIGN_BITS", "1") != "0" and H == 128
         self._mask_ready = False
         # Discrete(3): folded head parameters (w_j - w_2, b_j - b_2), two-column head outputs / gradients
         self.fold3 = (not self.gaussian) and self.A == 3
@@ -130,6 +132,7 @@ class FusedActorCritic:
         if b is None:
             e = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
             b = dict(h1=e(B, self.H), ya=e(B, self.H), yc=e(B, self.H), act=e(B, self.A), v=e(B, 1), dz1=None)
+            b["signs"] = torch.empty(B, 2 * self.H // 32, dtype=torch.int32, device=self.device) if self.sign_bits else None
             if self.fold3:      # the kernels write two logits; the reported third one is 0
                 b["act2"] = e(B, 2)
                 b["act"].zero_()
@@ -151,7 +154,7 @@ class FusedActorCritic:
         prep = (self.la1.weight.data, self.lc1.weight.data, self.wtm_hi, self.wtm_lo) if self.mask_dgrad else None
         self._mask_ready = prep is not None
         if loss is None:
-            ops.dense_fwd2(b["h1"], self.slope, l0, l1, prep=prep)
+            ops.dense_fwd2(b["h1"], self.slope, l0, l1, prep=prep, sign_out=b["signs"])
             if self.fold3:
                 b["act"][:, :2].copy_(b["act2"])
             return
@@ -162,17 +165,17 @@ class FusedActorCritic:
         ops.dense_fwd2_loss(b["h1"], self.slope, l0, l1, loss["scal"], loss["adv_stats"], loss["adv_count"],
                             loss["clip_range"], loss["vf_coef"], loss["ent_coef"], loss["inv_batch"], loss["logstd"],
                             b["dact"], b["dv"], self._loss_partials, self._loss_ticket, loss["scalars"], loss["dlogstd"],
-                            prep=prep)
+                            prep=prep, sign_out=b["signs"])
 
     def stage_dgrad(self, b, dact, dv2, softmax_pair=False):
         """softmax_pair: `dact` [B, 2] are the gradients w.r.t. the two logits of a softmax head (they are opposite), so
         the actor's head gradient is rank-1 like a one-head source and the mask-form operand applies."""
         if self._mask_ready and (self.A == 1 or (self.A == 2 and softmax_pair)):
             ops.dense_dgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, self.wtm_hi, self.wtm_lo,
-                            b["h1"], self.slope, b["dz1"], wt_form=1)
+                            b["h1"], self.slope, b["dz1"], wt_form=1, signs=b["signs"])
             return
         ops.dense_dgrad(b["ya"], dact, self._head_a()[0], b["yc"], dv2, self.lc2.weight.data, self.wt_hi, self.wt_lo,
-                        b["h1"], self.slope, b["dz1"])
+                        b["h1"], self.slope, b["dz1"], signs=b["signs"])
 
     def stage_wgrad(self, b, dact, dv2):
         """Per-CTA partial sums only (into ws_wgrad); `stage_tail` finishes them."""

@@ -335,9 +335,10 @@ def dense_fwd(x, w_hi, w_lo, bias, slope, y, head_w=None, head_b=None, head_out=
               1 if b_resident else 0, _stream())
 
 
-def dense_fwd2(x, slope, layer0, layer1, b_resident=True, prep=None):
+def dense_fwd2(x, slope, layer0, layer1, b_resident=True, prep=None, sign_out=None):
     """layerK = (w_hi, w_lo, bias, y, head_w, head_b, head_out): two layers on the same input in one launch.
-    prep = (W0, W1, thi, tlo): also write the mask-form dgrad weight operand (see xb_dense_fwd2 in include/xb200.h)."""
+    prep = (W0, W1, thi, tlo): also write the mask-form dgrad weight operand (see xb_dense_fwd2 in include/xb200.h).
+    sign_out: int32 [M, 2 * N / 32] activation sign words for dense_dgrad(signs=...)."""
     pw0, pw1, pthi, ptlo = prep if prep is not None else (None, None, None, None)
     M, K = x.shape
     N = layer0[0].shape[0]
@@ -346,11 +347,11 @@ def dense_fwd2(x, slope, layer0, layer1, b_resident=True, prep=None):
         args += [_p(w_hi, F32), _p(w_lo, F32), _p(bias, F32), _p(y, F32), _p(head_w, F32), _p(head_b, F32),
                  head_w.shape[0] if head_w is not None else 0, _p(head_out, F32)]
     _lib.call("xb_dense_fwd2", _p(x, F32), M, K, N, float(slope), *args, 1 if b_resident else 0, _p(pw0, F32), _p(pw1, F32),
-              _p(pthi, F32), _p(ptlo, F32), _stream())
+              _p(pthi, F32), _p(ptlo, F32), _p(sign_out, I32), _stream())
 
 
 def dense_fwd2_loss(x, slope, layer0, layer1, scal, adv_stats, adv_count, clip_range, vf_coef, ent_coef, inv_batch, logstd,
-                    dact, dv, partials, ticket, scalars, dlogstd, b_resident=True, prep=None):
+                    dact, dv, partials, ticket, scalars, dlogstd, b_resident=True, prep=None, sign_out=None):
     """dense_fwd2 with the PPO loss forward + backward fused into its epilogue (xb_dense_fwd2_loss)."""
     pw0, pw1, pthi, ptlo = prep if prep is not None else (None, None, None, None)
     M, K = x.shape
@@ -362,7 +363,7 @@ def dense_fwd2_loss(x, slope, layer0, layer1, scal, adv_stats, adv_count, clip_r
     _lib.call("xb_dense_fwd2_loss", _p(x, F32), M, K, N, float(slope), *args, 1 if b_resident else 0, _p(scal, F32),
               _p(adv_stats, F64), int(adv_count), float(clip_range), float(vf_coef), float(ent_coef), float(inv_batch),
               _p(logstd, F32), _p(dact, F32), _p(dv, F32), _p(partials, F64), _p(ticket, I32), _p(scalars, F64),
-              _p(dlogstd, F64), _p(pw0, F32), _p(pw1, F32), _p(pthi, F32), _p(ptlo, F32), _stream())
+              _p(dlogstd, F64), _p(pw0, F32), _p(pw1, F32), _p(pthi, F32), _p(ptlo, F32), _p(sign_out, I32), _stream())
 
 
 def mlp_fwd_from_obs(obs, w0, b0, slope, layer0, layer1, norm=None, weights_stable=False):
@@ -379,12 +380,13 @@ def mlp_fwd_from_obs(obs, w0, b0, slope, layer0, layer1, norm=None, weights_stab
               float(slope), *args, _p(nn, F64), _p(no, F64), int(nr), float(nc), 1 if weights_stable else 0, _stream())
 
 
-def dense_dgrad(y0, dout0, w2_0, y1, dout1, w2_1, wt_hi, wt_lo, h1, slope, dz1, wt_form=0):
+def dense_dgrad(y0, dout0, w2_0, y1, dout1, w2_1, wt_hi, wt_lo, h1, slope, dz1, wt_form=0, signs=None):
+    """signs: int32 [M, (K0 + K1) / 32] sign words of [y0 | y1] (dense_fwd2's sign_out); the kernel then does not read y0 / y1."""
     M, K0 = y0.shape
     _lib.call("xb_dense_dgrad", _p(y0, F32), _p(dout0, F32), _p(w2_0, F32), w2_0.shape[0], K0, _p(y1, F32),
               _p(dout1, F32), _p(w2_1, F32), w2_1.shape[0] if w2_1 is not None else 0,
               y1.shape[1] if y1 is not None else 0, M, _p(wt_hi, F32), _p(wt_lo, F32), wt_hi.shape[0], _p(h1, F32),
-              float(slope), _p(dz1, F32), int(wt_form), _stream())
+              float(slope), _p(dz1, F32), int(wt_form), _p(signs, I32), _stream())
 
 
 def dense_wgrad_workspace(h_in, device):
