@@ -183,10 +183,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_ma
 }
 
 // x = hi + lo with hi exactly representable in TF32 (round-to-nearest); lo = x - hi is exact in fp32.
+// cvt.rna.tf32.f32 (nearest, ties away from zero) is emulated in SASS as add 0x1000 / Inf-NaN guard (FSETP + SEL) / mask: the
+// guard is dropped here — the operands are finite activations, weights and gradients — which leaves IADD + LOP3 + FADD per
+// element instead of five instructions (the operand warps of the dense kernels are instruction-bound); bit-identical to
+// cvt.rna for every finite x below 2^128 - 2^104.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
     lo = x - hi;
 }
 
