@@ -406,6 +406,24 @@ int xb_dense_wgrad(const float* Y0, const float* dout0, const float* w2_0, int n
                    const float* w2_1, int nh1, const float* X, int64_t B, int H_out, int H_in, float slope,
                    float* workspace, float* dW0, float* db0, float* dw2_0, float* db2_0, float* dW1, float* db1,
                    float* dw2_1, float* db2_1, xb_stream_t stream);
+/*   xb_dense_wgrad_bin      BINARY form of xb_dense_wgrad for rank-1 head gradients (nh = 1, or nh = 2 = the two opposite logit
+ *                           gradients of a softmax pair: only dout[:, 0] is read).  leaky' = slope + (1 - slope) [y > 0] turns the
+ *                           weight gradient into  w2'[m] ((1 - slope) sum_b [y > 0][b][m] (e[b] x[b][n]) + slope sum_b e[b] x[b][n]):
+ *                           the MMA's A operand is the 0/1 matrix read from the forward's activation SIGN WORDS (xb_dense_fwd2's
+ *                           sign_out; exact in TF32: 2 MMAs per k-step instead of 3) and the activations Y are not read at all.
+ *                           Leaves partial sums in `workspace` (same size as xb_dense_wgrad's); xb_mlp_backward_tail_bin finishes
+ *                           them, including the head-weight gradient dw2[m] = sum_n W[m][n] Gm[m][n] + b[m] gm[m]  (= sum_b e y).
+ *   xb_mlp_backward_tail_bin  xb_mlp_backward_tail(_norm) for those partials: W_s [H_out][H_in], b_s [H_out], w2_s [nh_s][H_out] are
+ *                           the hidden layer's master weights / bias and the head weights; norm_workspace == NULL: no norm pass. */
+int xb_dense_wgrad_bin(const uint32_t* signs, int sign_ld, const float* dout0, int nh0, const float* dout1, int nh1,
+                       const float* X, int64_t B, int H_out, int H_in, float* workspace, xb_stream_t stream);
+int xb_mlp_backward_tail_bin(const float* wgrad_ws, int H_out, int H_in, int n_sources, int nh0, int nh1, float* dW0,
+                             float* db0, float* dw2_0, float* db2_0, float* dW1, float* db1, float* dw2_1, float* db2_1,
+                             const float* trunk_ws, int trunk_parts, int obs_dim, float* dWt, float* dbt, const double* dls64,
+                             float* dls32, int A, double* norm_workspace, int64_t* step_dev, float lr0, float lr_end_factor,
+                             int64_t lr_total_iters, float beta1, float beta2, float max_norm, float grad_scale, float* lr_out,
+                             float* gnorm_out, const float* W0, const float* b0, const float* w2_0, const float* W1,
+                             const float* b1, const float* w2_1, float slope, xb_stream_t stream);
 /*   xb_dense_fwd2           two layers that share the input X in ONE launch (actor and critic hidden layers + their heads):
  *                           even CTAs evaluate layer 0, odd CTAs layer 1, each with its weights resident in shared memory. */
 int xb_dense_fwd2(const float* X, int64_t M, int K, int N, float slope, const float* Whi0, const float* Wlo0,

@@ -466,3 +466,49 @@ def test_sign_words_match_activations_and_dgrad_is_bit_identical(env_id, B):
     torch.cuda.synchronize()
     assert torch.isfinite(outs[0]).all()
     assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
+
+
+@pytest.mark.parametrize("env_id,B", [("Pendulum-v1", 65536), ("CartPole-v1", 8192 + 33)])
+def test_binary_form_wgrad_matches_the_three_mma_form(env_id, B):
+    """xb_dense_wgrad_bin + xb_mlp_backward_tail_bin (0/1 A operand from the sign words, head-weight gradient rebuilt from the
+    weight-gradient partials) against xb_dense_wgrad + xb_mlp_backward_tail on the same inputs: every hidden-layer and head
+    gradient within 5e-5 of the gradient's scale (both are TF32-split sums in different orders; each is within 2e-5 of fp64)."""
+    import xuanpolicy_b200 as xb
+    from xuanpolicy_b200.fused_mlp import FusedActorCritic
+    from xuanpolicy_b200.learner import FlatAdamState
+    from xuanpolicy_b200.policies import make_policy
+    obs_space, act_space = xb.make_spaces(env_id)
+    policy = make_policy(obs_space, act_space, hidden=(128,), device="cuda", seed=11)
+    with torch.no_grad():
+        for p in policy.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    FlatAdamState(policy, torch.optim.Adam(policy.parameters(), 1e-3), None)
+    fused = FusedActorCritic(policy)
+    assert fused.bin_wgrad
+    g = torch.Generator(device="cuda").manual_seed(B)
+    obs = torch.randn(B, 4, device="cuda", generator=g)[:, :obs_space.shape[0]]
+    act_out, v = fused.forward(obs)
+    A = act_out.shape[1]
+    dact = torch.randn(B, A, device="cuda", generator=g) / B
+    if A == 2:
+        dact[:, 1] = -dact[:, 0]
+    dv = torch.randn(B, device="cuda", generator=g) / B
+    names = [n for n, q in policy.named_parameters() if q.grad is not None and "logstd" not in n]
+    out = {}
+    for mode in (True, False):
+        fused.bin_wgrad = mode
+        for q in policy.parameters():
+            if q.grad is not None:
+                q.grad.fill_(float("nan"))
+        fused.backward(dact, dv, softmax_pair=True)
+        torch.cuda.synchronize()
+        assert fused._bin_now == mode
+        out[mode] = {n: dict(policy.named_parameters())[n].grad.clone() for n in names}
+    for n in names:
+        a, b = out[True][n].double(), out[False][n].double()
+        assert torch.isfinite(a).all(), n
+        scale = b.pow(2).mean().sqrt().clamp_min(1e-30)
+        err = float((a - b).abs().max() / scale)
+        print("   %-32s %.2e" % (n, err))
+        assert err < 5e-5, (n, err)      # (measured against fp64: binary form <= 1e-5, three-MMA form <= 2.1e-5)

@@ -30,5 +30,9 @@ for name, signs in (("signs", b["signs"]), ("tiles", None)):
                                 fused.wtm_lo, b["h1"], fused.slope, b["dz1"], wt_form=1, signs=signs)
     print("dgrad", name, "median %.1f us  min %.1f us" % timeit(f))
 print("fwd2 (+signs) median %.1f min %.1f" % timeit(lambda: fused.stage_hidden(b)))
+print("fwd2 (signs, no Y) median %.1f min %.1f" % timeit(lambda: fused.stage_hidden(b, keep_y=False)))
+fused.stage_hidden(b)
 dv = dv2
-print("wgrad median %.1f min %.1f" % timeit(lambda: fused.stage_wgrad(b, dact, dv2)))
+print("wgrad (binary) median %.1f min %.1f" % timeit(lambda: fused.stage_wgrad(b, dact, dv2)))
+fused.bin_wgrad = False
+print("wgrad (3 MMA) median %.1f min %.1f" % timeit(lambda: fused.stage_wgrad(b, dact, dv2)))

@@ -79,6 +79,10 @@ SIGNATURES = {
                              _vp, _vp, _vp, _i32, _vp],
     "xb_mlp_backward_tail_norm": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                                   _vp, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _f32, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
+    "xb_mlp_backward_tail_bin": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
+                                 _vp, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _f32, _i64, _f32, _f32, _f32, _f32, _vp, _vp,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp],
+    "xb_dense_wgrad_bin": [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _i64, _i32, _i32, _vp, _vp],
     "xb_head3_fold": [_vp, _vp, _vp, _vp, _i32, _vp],
     "xb_head3_unfold_grads": [_vp, _vp, _i32, _vp],
     "xb_mlp_trunk_wgrad": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _i32, _vp],

@@ -1707,6 +1707,282 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
 }
 
+
+// ================================================================================================ weight gradients, BINARY form
+// Rank-1 head gradients (one head per source, or the two opposite logit gradients of a softmax pair):
+//     dz_s[b][m] = e_s[b] * w2'_s[m] * leaky'(y_s[b][m]),   leaky' = slope + (1 - slope) * bin,   bin = (y > 0) in {0, 1}
+// so with   A[m][n] = sum_b bin[b][m] * (e[b] x[b][n]),   G[n] = sum_b e[b] x[b][n],   S[m] = sum_b e[b] bin[b][m],   E = sum_b e[b]:
+//     Gm[m][n] = (1 - slope) A[m][n] + slope G[n]         gm[m] = (1 - slope) S[m] + slope E
+//     dW[m][n] = w2'[m] Gm[m][n]      db[m] = w2'[m] gm[m]      dw2[m] = sum_n W[m][n] Gm[m][n] + b[m] gm[m]  (= sum_b e y)      db2 = E
+// The MMA's A operand is the 0/1 matrix `bin`, which TF32 holds EXACTLY: only the B operand (e x) needs the hi/lo split, i.e.
+// 2 MMAs per k-step instead of 3, no lo copy of A, and — with the forward's activation sign words — no load of the activations
+// at all (the head-weight gradient comes out of Gm in the reduce kernel).  Shared-memory traffic per 32-row k-block drops from
+// 224 KB to 144 KB and the operand warps' work from ~1 k to ~0.4 k instructions.  Partials: part[cta][m][0..HIN) = A, [HIN] = S;
+// head_part[cta][0..HIN) = G; db2_part[cta][0] = E.  The scaling above happens in wgrad_reduce_kernel (BinArgs).
+__device__ __forceinline__ uint32_t ss_kblock_mn_bin(uint32_t d_tmem, uint64_t da, uint64_t db_hi, uint64_t db_lo, uint32_t idesc,
+                                                     uint32_t accumulate_first, uint32_t next_bar, uint32_t next_par,
+                                                     uint32_t commit0, uint32_t commit1, uint32_t commit2, uint32_t elected) {
+    uint32_t ready;
+    asm volatile(
+        "{\n"
+        ".reg .pred pn, p0, p1, c2, pe;\n"
+        ".reg .b64 a, bh, bl;\n"
+        "setp.ne.b32 pe, %12, 0;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 pn, [%7], %8;\n"
+        "setp.ne.b32 p0, %6, 0;\n"
+        "setp.ne.b32 p1, 1, 0;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], %2, %3, %5, p0;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], %2, %4, %5, p1;\n"
+        "add.u64 a, %2, 64;  add.u64 bh, %3, 64;  add.u64 bl, %4, 64;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], a, bh, %5, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], a, bl, %5, p1;\n"
+        "add.u64 a, %2, 128; add.u64 bh, %3, 128; add.u64 bl, %4, 128;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], a, bh, %5, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], a, bl, %5, p1;\n"
+        "add.u64 a, %2, 192; add.u64 bh, %3, 192; add.u64 bl, %4, 192;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], a, bh, %5, p1;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%1], a, bl, %5, p1;\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n"
+        "setp.ne.b32 c2, %11, 0;\n"
+        "and.pred c2, c2, pe;\n"
+        "@c2 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n"
+        "selp.u32 %0, 1, 0, pn;\n"
+        "}\n"
+        : "=r"(ready)
+        : "r"(d_tmem), "l"(da), "l"(db_hi), "l"(db_lo), "r"(idesc), "r"(accumulate_first), "r"(next_bar), "r"(next_par),
+          "r"(commit0), "r"(commit1), "r"(commit2), "r"(elected)
+        : "memory");
+    return ready;
+}
+
+struct WBinParams {
+    int64_t B;
+    int n_jobs, halves, H_out;
+    int stages, lo_bufs;
+    const float* dout[2];      // e_s[b] = dout_s[b * nh_s]  (nh = 2: softmax pair, the second gradient is -e and is not read)
+    int nh[2];
+    const uint32_t* signs;     // [B][sign_ld] activation sign words: source s, features 32 c .. 32 c + 31 -> word s * (H_out / 32) + c
+    int sign_ld;
+    float* part;
+    float* head_part;
+    float* db2_part;
+};
+
+template <int HIN>
+__global__ void __launch_bounds__(kThreads, 1)
+    dense_wgrad_bin_kernel(const __grid_constant__ CUtensorMap map_x, const WBinParams p) {
+    constexpr int NBX = HIN / 32;                  // 32-feature boxes of x
+    constexpr int kBox = 32 * 128;                 // one box: 32 batch rows x 128 B
+    constexpr int kStage = 4 * kBox + NBX * kBox;  // bin operand (128 features, written by the operand warps) | x operand -> hi
+    constexpr int kLo = NBX * kBox;                // lo half of the x operand
+    constexpr int kTmemCols = HIN;
+    constexpr uint32_t kIdescMain = umma_idesc_tf32(128, HIN, 1, 1);
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int S = p.stages, L = p.lo_bufs;
+    const uint32_t ring = base, lo_ring = ring + (uint32_t)S * kStage, misc = lo_ring + (uint32_t)L * kLo;
+    const uint32_t bar_full = misc, bar_conv = misc + 64, bar_empty = misc + 128, bar_loempty = misc + 192;
+    const uint32_t bar_tfull = misc + 256, tmem_slot = misc + 264;
+    unsigned char* misc_ptr = smem_raw + (misc - smem_u32(smem_raw));
+    float* sf = reinterpret_cast<float*>(misc_ptr + 2048);   // reduction scratch: [8 warps][128 S | HIN G] + [8] E
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int job = blockIdx.x % p.n_jobs, q = blockIdx.x / p.n_jobs;
+    const int cj = (gridDim.x - job + p.n_jobs - 1) / p.n_jobs;          // CTAs working on this job
+    const int src = job / p.halves, m0 = (job % p.halves) * 128;
+    const int64_t nblk = (p.B + 31) / 32;
+    const int64_t blk0 = nblk * q / cj, blk1 = nblk * (q + 1) / cj;
+    const int nkb = (int)(blk1 - blk0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_conv + 8 * s, kOperandWarps / 2);   // one group of 4 operand warps per k-block
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int j = 0; j < L; ++j) mbar_init(bar_loempty + 8 * j, 1);
+        mbar_init(bar_tfull, 1);
+        mbar_fence_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
+    pdl_wait();
+    pdl_trigger();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == kProducerWarp) {
+        // ============================================================ TMA producer: x boxes only (whole warp, one elected lane)
+        const uint32_t elected = elect_one_pred();
+        if (lane == 0) tma_prefetch_desc(&map_x);
+        __syncwarp();
+        uint32_t s = 0, ph = 0;
+        for (int it = 0; it < nkb; ++it) {
+            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            const uint32_t st = ring + s * kStage;
+            mbar_arrive_expect_tx_if(elected, bar_full + 8 * s, NBX * kBox);
+            const int row = (int)((blk0 + it) * 32);
+#pragma unroll
+            for (int g = 0; g < NBX; ++g) tma_load_2d_if(elected, st + (4 + g) * kBox, &map_x, g * 32, row, bar_full + 8 * s);
+            if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+        }
+    } else if (warp == kMmaWarp) {
+        // ============================================================ MMA issuer (whole warp, one elected lane): 8 MMAs per k-block
+        const uint32_t elected = elect_one_pred();
+        const uint32_t tmem_base_u = __reduce_max_sync(0xffffffffu, tmem_base);
+        uint32_t s = 0, ph = 0, j = 0, ready = 0;
+        for (int it = 0; it < nkb; ++it) {
+            if (!ready) mbar_wait(bar_conv + 8 * s, ph);
+            tc_fence_after();
+            const uint32_t a = ring + s * kStage, b_hi = a + 4 * kBox, b_lo = lo_ring + j * kLo;
+            const uint32_t ns = s + 1 == (uint32_t)S ? 0 : s + 1, nph = s + 1 == (uint32_t)S ? ph ^ 1 : ph;
+            ready = ss_kblock_mn_bin(tmem_base_u, umma_desc_sw128_base32(a, kBox, 512), umma_desc_sw128_base32(b_hi, kBox, 512),
+                                     umma_desc_sw128_base32(b_lo, kBox, 512), kIdescMain, it != 0, bar_conv + 8 * ns, nph,
+                                     bar_empty + 8 * s, bar_loempty + 8 * j, it == nkb - 1 ? bar_tfull : 0u, elected);
+            s = ns;
+            ph = nph;
+            if (++j == (uint32_t)L) j = 0;
+        }
+    } else if (warp >= 4) {
+        // ============================================================ operand warps: two groups of 4 on alternate k-blocks
+        const int t = threadIdx.x - 128;
+        const int w = t >> 5;                       // 0..7: slot of this warp's partial sums in the final reduction
+        const int grp = w >> 2, wr = w & 3;         // group (k-block parity), row group: rows 8 wr .. 8 wr + 7
+        const int g = (t & 31) >> 3, c = t & 7;     // feature box, 16-byte chunk: features m0 + 32 g + 4 c .. + 3
+        const int nh = p.nh[src];
+        const float* dout = p.dout[src];
+        const int word = src * (p.H_out >> 5) + (m0 >> 5) + g;      // this thread's sign word of a row
+        float sacc[4] = {0, 0, 0, 0};               // S[m]: sum_b e[b] bin[b][m] for this thread's 4 features
+        float gacc[NBX / 4][4];                     // G[n]: sum_b e[b] x[b][n] for this thread's x columns
+#pragma unroll
+        for (int gg = 0; gg < NBX / 4; ++gg)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) gacc[gg][e] = 0.f;
+        float esum = 0.f;
+        float d0[8];
+        uint32_t sw[8];
+        auto prefetch = [&](int it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t b = (blk0 + it) * 32 + 8 * wr + i;
+                const bool ok = it < nkb && b < p.B;
+                d0[i] = ok ? __ldg(dout + b * nh) : 0.f;
+                sw[i] = ok ? __ldg(p.signs + b * p.sign_ld + word) : 0u;
+            }
+        };
+        prefetch(grp);
+        for (int it = grp; it < nkb; it += 2) {
+            const uint32_t s = it % S, ph = (it / S) & 1, j = it % L;
+            float ev[8];
+            uint32_t bits[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ev[i] = d0[i]; bits[i] = sw[i] >> (4 * c); }
+            prefetch(it + 2);                        // this group's next k-block
+            mbar_wait(bar_full + 8 * s, ph);         // (x landed; the stage was released by the MMAs of its previous use)
+            mbar_wait(bar_loempty + 8 * j, ((it / L) & 1) ^ 1);
+            const uint32_t raw = ring + s * kStage, lo_b = lo_ring + j * kLo;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {            // A operand: the 0/1 matrix itself
+                const uint32_t off = g * kBox + sw32_off(8 * wr + i, c);
+                const float e = ev[i];
+                float4 a;
+                a.x = (bits[i] & 1u) ? 1.f : 0.f;
+                a.y = (bits[i] & 2u) ? 1.f : 0.f;
+                a.z = (bits[i] & 4u) ? 1.f : 0.f;
+                a.w = (bits[i] & 8u) ? 1.f : 0.f;
+                sacc[0] += e * a.x; sacc[1] += e * a.y; sacc[2] += e * a.z; sacc[3] += e * a.w;
+                esum += e;
+                sts128(raw + off, a);
+            }
+#pragma unroll
+            for (int gg = 0; gg < NBX / 4; ++gg) {   // B operand: e[b] x[b][n], split hi (in place) / lo
+                float4 xs[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xs[i] = lds128(raw + (4 + 4 * gg + g) * kBox + sw32_off(8 * wr + i, c));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t off = (4 * gg + g) * kBox + sw32_off(8 * wr + i, c);
+                    const float e = ev[i];
+                    float4 v = make_float4(e * xs[i].x, e * xs[i].y, e * xs[i].z, e * xs[i].w);
+                    gacc[gg][0] += v.x; gacc[gg][1] += v.y; gacc[gg][2] += v.z; gacc[gg][3] += v.w;
+                    float4 hi, lo;
+                    split_tf32(v.x, hi.x, lo.x);
+                    split_tf32(v.y, hi.y, lo.y);
+                    split_tf32(v.z, hi.z, lo.z);
+                    split_tf32(v.w, hi.w, lo.w);
+                    sts128(raw + 4 * kBox + off, hi);
+                    sts128(lo_b + off, lo);
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+        }
+        // column sums: the 8 warps' partials in a fixed order
+        constexpr int kCols = 128 + HIN;
+        float* hs = sf + w * kCols;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) hs[32 * g + 4 * c + e] = sacc[e];
+#pragma unroll
+        for (int gg = 0; gg < NBX / 4; ++gg)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hs[128 + 32 * (4 * gg + g) + 4 * c + e] = gacc[gg][e];
+        // (esum: every thread of a warp saw the same 8 rows per k-block; one lane per warp reports it)
+        if ((t & 31) == 0) sf[8 * kCols + w] = esum;
+        bar_sync_named(1, kOperandWarps * 32);
+        for (int i = t; i < kCols; i += kOperandWarps * 32) {
+            const float v = ((sf[i] + sf[kCols + i]) + (sf[2 * kCols + i] + sf[3 * kCols + i])) +
+                            ((sf[4 * kCols + i] + sf[5 * kCols + i]) + (sf[6 * kCols + i] + sf[7 * kCols + i]));
+            if (i < 128) p.part[((int64_t)blockIdx.x * 128 + i) * (HIN + 4) + HIN] = v;       // S[m]: the bias column
+            else p.head_part[(int64_t)blockIdx.x * 256 + (i - 128)] = v;                     // G[n]
+        }
+        if (t == 0) {
+            const float* es = sf + 8 * kCols;
+            p.db2_part[(int64_t)blockIdx.x * 2] = ((es[0] + es[1]) + (es[2] + es[3])) + ((es[4] + es[5]) + (es[6] + es[7]));
+            p.db2_part[(int64_t)blockIdx.x * 2 + 1] = 0.f;
+        }
+    } else {
+        // ============================================================ epilogue: partial [128][HIN + 4]
+        float* out = p.part + ((int64_t)blockIdx.x * 128 + warp * 32 + lane) * (HIN + 4);
+        if (nkb > 0) {
+            mbar_wait(bar_tfull, 0);
+            tc_fence_after();
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int cc = 0; cc < HIN / 32; ++cc) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + cc * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                reinterpret_cast<float4*>(out + cc * 32)[e] =
+                    nkb > 0 ? make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]),
+                                          __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// Finishing the BINARY-form partials in wgrad_reduce_kernel (see dense_wgrad_bin_kernel): per source the master weights
+// W [H_out][HIN] and bias [H_out] of the hidden layer, the head weights w2 [nh][H_out] (nh = 2: softmax pair, w2' = w2[0] - w2[1]).
+struct BinArgs {
+    int on;
+    float slope;
+    const float* W[2];
+    const float* b[2];
+    const float* w2[2];
+};
+
 // Sums the per-CTA partials of the wgrad kernel in a fixed order (deterministic) and scatters them to the parameter
 // gradients.  One block per (job, output row m): 4 thread groups each add a quarter of the CTAs' partials for their
 // column (loads unrolled so many are in flight), then the groups are combined through shared memory.
@@ -1733,8 +2009,9 @@ struct TailArgs {
 __global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ head_part,
                                     const float* __restrict__ db2_part, int grid, int n_jobs, int halves, int HIN,
                                     int H_out, float* dW0, float* db0, float* dw2_0, float* db2_0, int nh0, float* dW1,
-                                    float* db1, float* dw2_1, float* db2_1, int nh1, TailArgs tail) {
+                                    float* db1, float* dw2_1, float* db2_1, int nh1, TailArgs tail, BinArgs bin) {
     __shared__ float red[4][260];
+    __shared__ float bin_g[256], bin_red[4], bin_e;
     __shared__ double norm_smem[32];
     __shared__ bool norm_last;
     pdl_wait();
@@ -1772,7 +2049,7 @@ __global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restri
         const int nh = src ? nh1 : nh0;
         const int grp = threadIdx.x >> 7, t = threadIdx.x & 127;
         const int n_cta = (grid - job + n_jobs - 1) / n_jobs;          // CTAs that worked on this job: job, job + n_jobs, ...
-        const int ncol = HIN + 3;                                       // HIN weights | bias | head 0 | head 1
+        const int ncol = bin.on ? HIN + 1 : HIN + 3;                    // HIN weights | bias | head 0 | head 1
         for (int n = t; n < ncol; n += 128) {
             float acc = 0.f;
             const float* src_ptr;
@@ -1795,8 +2072,57 @@ __global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restri
             for (int c = grp + 80; c < n_cta; c += 4) acc += src_ptr[c * stride];
             red[grp][n] = acc;
         }
+        if (bin.on) {
+            // BINARY form (dense_wgrad_bin_kernel): column sums G[n] (head_part rows of this job's CTAs) and E (db2_part), every
+            // block for itself; then Gm = (1 - slope) A + slope G, gm = (1 - slope) S + slope E and the scalings by w2' / W / b
+            for (int n = threadIdx.x; n < HIN; n += 512) {
+                float a4[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int c = 0; c < n_cta; ++c) a4[c & 3] += head_part[(int64_t)(job + c * n_jobs) * 256 + n];
+                bin_g[n] = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+            }
+            if (threadIdx.x >= 480) {                                   // last warp: E
+                float e = 0.f;
+                for (int c = t - 96; c < n_cta; c += 32) e += db2_part[(int64_t)(job + c * n_jobs) * 2];
+                e = warp_sum(e);
+                if (t == 96) bin_e = e;
+            }
+        }
         __syncthreads();
-        if (grp == 0) {
+        if (bin.on) {
+            const float* w2p = bin.w2[src];
+            const float w2m = nh > 1 ? w2p[m] - w2p[H_out + m] : w2p[m];
+            const float sl = bin.slope, om = 1.0f - bin.slope;
+            float dot = 0.f;                                            // this thread's share of sum_n W[m][n] Gm[n]
+            if (grp == 0) {
+                for (int n = t; n < HIN; n += 128) {
+                    const float A = (red[0][n] + red[1][n]) + (red[2][n] + red[3][n]);
+                    const float gm_n = om * A + sl * bin_g[n];
+                    const float gw = w2m * gm_n;
+                    dW[(int64_t)m * HIN + n] = gw;
+                    XB_SQ(gw);
+                    dot += bin.W[src][(int64_t)m * HIN + n] * gm_n;
+                }
+                dot = warp_sum(dot);
+                if ((t & 31) == 0) bin_red[t >> 5] = dot;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const float S = (red[0][HIN] + red[1][HIN]) + (red[2][HIN] + red[3][HIN]);
+                const float gm = om * S + sl * bin_e;
+                const float gb = w2m * gm;
+                db[m] = gb;
+                XB_SQ(gb);
+                const float g2 = ((bin_red[0] + bin_red[1]) + (bin_red[2] + bin_red[3])) + bin.b[src][m] * gm;
+                dw2[m] = g2;
+                XB_SQ(g2);
+                if (nh > 1) { dw2[H_out + m] = -g2; XB_SQ(g2); }
+                if (m == 0) {
+                    db2[0] = bin_e;
+                    XB_SQ(bin_e);
+                    if (nh > 1) { db2[1] = -bin_e; XB_SQ(bin_e); }
+                }
+            }
+        } else if (grp == 0) {
             for (int n = t; n < ncol; n += 128) {
                 const float acc = (red[0][n] + red[1][n]) + (red[2][n] + red[3][n]);
                 if (n < HIN) { dW[(int64_t)m * HIN + n] = acc; XB_SQ(acc); }
@@ -1804,7 +2130,7 @@ __global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restri
                 else if (n - HIN - 1 < nh) { dw2[(int64_t)(n - HIN - 1) * H_out + m] = acc; XB_SQ(acc); }
             }
         }
-        if (m == 0 && grp >= 1 && grp - 1 < nh && t < 32) {             // db2: this job's CTAs cover the whole batch; one warp per head
+        if (!bin.on && m == 0 && grp >= 1 && grp - 1 < nh && t < 32) {  // db2: this job's CTAs cover the whole batch; one warp per head
             const int h = grp - 1;
             float s = 0.f;
             for (int c = t; c < n_cta; c += 32) s += db2_part[(int64_t)(job + c * n_jobs) * 2 + h];
@@ -2125,7 +2451,7 @@ extern "C" int xb_dense_wgrad(const float* Y0, const float* dout0, const float* 
     TailArgs tail{};
     wgrad_reduce_kernel<<<p.n_jobs * 128, 512, 0, s>>>(p.part, p.head_part, p.db2_part, grid, p.n_jobs, p.halves, H_in,
                                                       H_out, dW0, db0, dw2_0, db2_0, nh0, dW1, db1, dw2_1, db2_1,
-                                                      Y1 ? nh1 : 0, tail);
+                                                      Y1 ? nh1 : 0, tail, BinArgs{});
     XB_LAUNCH_CHECK();
     return 0;
 }
@@ -2134,7 +2460,8 @@ static int backward_tail_impl(const float* wgrad_ws, int H_out, int H_in, int n_
                               float* db0, float* dw2_0, float* db2_0, float* dW1, float* db1, float* dw2_1, float* db2_1,
                               const float* trunk_ws, int trunk_parts, int obs_dim, float* dWt, float* dbt,
                               const double* dls64, float* dls32, int A, double* norm_ws, int64_t* step_dev,
-                              const xb::AdamHyper& hyper, float* lr_out, float* gnorm_out, cudaStream_t stream) {
+                              const xb::AdamHyper& hyper, float* lr_out, float* gnorm_out, cudaStream_t stream,
+                              const BinArgs& bin = BinArgs{}) {
     if (!wgrad_ws || !dW0 || !db0 || !dw2_0 || !db2_0 || (n_sources == 2 && (!dW1 || !db1 || !dw2_1 || !db2_1)))
         return XB_E_BADARG;
     if ((H_out != 128 && H_out != 256) || (H_in != 128 && H_in != 256) || n_sources < 1 || n_sources > 2) return XB_E_UNSUPPORTED;
@@ -2150,7 +2477,7 @@ static int backward_tail_impl(const float* wgrad_ws, int H_out, int H_in, int n_
     if (n_jobs * 128 + tail_blocks > xb::kOptMaxGrid) return XB_E_UNSUPPORTED;
     XB_CUDA(launch_pdl(wgrad_reduce_kernel, dim3(n_jobs * 128 + tail_blocks), dim3(512), 0, stream, true, part, head_part, db2_part,
                        grid, n_jobs, halves, H_in, H_out, dW0, db0, dw2_0, db2_0, nh0, dW1, db1, dw2_1, db2_1,
-                       n_sources == 2 ? nh1 : 0, tail));
+                       n_sources == 2 ? nh1 : 0, tail, bin));
     XB_LAUNCH_CHECK();
     return 0;
 }
@@ -2179,4 +2506,68 @@ extern "C" int xb_mlp_backward_tail_norm(const float* wgrad_ws, int H_out, int H
     return backward_tail_impl(wgrad_ws, H_out, H_in, n_sources, nh0, nh1, dW0, db0, dw2_0, db2_0, dW1, db1, dw2_1, db2_1,
                               trunk_ws, trunk_parts, obs_dim, dWt, dbt, dls64, dls32, A, norm_workspace, step_dev, h, lr_out,
                               gnorm_out, (cudaStream_t)stream);
+}
+
+
+// ------------------------------------------------------------------------------------------------ binary-form weight gradients
+template <int HIN>
+static int launch_wgrad_bin(const CUtensorMap& mx, WBinParams p, int grid, cudaStream_t s) {
+    const int stage = (4 + HIN / 32) * 4096, lo = (HIN / 32) * 4096;
+    const int avail = kMaxSmem - 1024 - kWMiscBytes;
+    int L = 2, S = (avail - L * lo) / stage;
+    if (S < 2) return XB_E_UNSUPPORTED;
+    if (S > 6) S = 6;
+    if ((avail - S * stage) / lo >= 3) L = 3;
+    p.stages = S;
+    p.lo_bufs = L;
+    const int smem = 1024 + S * stage + L * lo + kWMiscBytes;
+    auto kern = dense_wgrad_bin_kernel<HIN>;
+    XB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    XB_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), (size_t)smem, s, true, mx, p));
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_dense_wgrad_bin(const uint32_t* signs, int sign_ld, const float* dout0, int nh0, const float* dout1, int nh1,
+                                  const float* X, int64_t B, int H_out, int H_in, float* workspace, xb_stream_t stream) {
+    if (!signs || !dout0 || !X || !workspace || B <= 0) return XB_E_BADARG;
+    if ((H_out != 128 && H_out != 256) || (H_in != 128 && H_in != 256) || nh0 < 1 || nh0 > 2) return XB_E_UNSUPPORTED;
+    if (dout1 && (nh1 < 1 || nh1 > 2)) return XB_E_BADARG;
+    const int n_src = dout1 ? 2 : 1;
+    if (sign_ld < n_src * (H_out / 32)) return XB_E_BADARG;
+    if (!al16(X) || !al16(workspace)) return XB_E_UNSUPPORTED;
+    CUtensorMap mx;
+    if (!xb_make_map_f32_2d(&mx, X, B, H_in, H_in, 32, 32, 2)) return XB_E_DRIVER;
+    WBinParams p{};
+    p.B = B;
+    p.halves = H_out / 128;
+    p.n_jobs = n_src * p.halves;
+    p.H_out = H_out;
+    p.dout[0] = dout0; p.nh[0] = nh0;
+    p.dout[1] = dout1; p.nh[1] = dout1 ? nh1 : 0;
+    p.signs = signs;
+    p.sign_ld = sign_ld;
+    const int grid = kNumSMs;
+    p.part = workspace;
+    p.head_part = workspace + (int64_t)grid * 128 * (H_in + 4);
+    p.db2_part = p.head_part + (int64_t)grid * 256;
+    return H_in == 128 ? launch_wgrad_bin<128>(mx, p, grid, (cudaStream_t)stream) : launch_wgrad_bin<256>(mx, p, grid, (cudaStream_t)stream);
+}
+
+extern "C" int xb_mlp_backward_tail_bin(const float* wgrad_ws, int H_out, int H_in, int n_sources, int nh0, int nh1,
+                                        float* dW0, float* db0, float* dw2_0, float* db2_0, float* dW1, float* db1,
+                                        float* dw2_1, float* db2_1, const float* trunk_ws, int trunk_parts, int obs_dim,
+                                        float* dWt, float* dbt, const double* dls64, float* dls32, int A,
+                                        double* norm_workspace, int64_t* step_dev, float lr0, float lr_end_factor,
+                                        int64_t lr_total_iters, float beta1, float beta2, float max_norm, float grad_scale,
+                                        float* lr_out, float* gnorm_out, const float* W0, const float* b0, const float* w2_0,
+                                        const float* W1, const float* b1, const float* w2_1, float slope, xb_stream_t stream) {
+    if (!W0 || !b0 || !w2_0 || (n_sources == 2 && (!W1 || !b1 || !w2_1))) return XB_E_BADARG;
+    if (norm_workspace && (!step_dev || !trunk_ws)) return XB_E_BADARG;
+    xb::AdamHyper h{lr0, lr_end_factor, beta1, beta2, 0.0f, max_norm, grad_scale, lr_total_iters};
+    if (!norm_workspace) h.grad_scale = 1.0f;
+    BinArgs bin{1, slope, {W0, W1}, {b0, b1}, {w2_0, w2_1}};
+    return backward_tail_impl(wgrad_ws, H_out, H_in, n_sources, nh0, nh1, dW0, db0, dw2_0, db2_0, dW1, db1, dw2_1, db2_1,
+                              trunk_ws, trunk_parts, obs_dim, dWt, dbt, dls64, dls32, A, norm_workspace, step_dev, h, lr_out,
+                              gnorm_out, (cudaStream_t)stream, bin);
 }

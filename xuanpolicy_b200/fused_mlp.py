@@ -94,6 +94,9 @@ class FusedActorCritic:
         self.mask_dgrad = os.environ.get("XB_MASK_DGRAD", "1") != "0"
         # activation sign words: the forward leaves one bit per hidden activation, dgrad reads those instead of ya / yc
         self.sign_bits = os.environ.get("XB_SIGN_BITS", "1") != "0" and H == 128
+        # binary-form weight gradients (rank-1 head gradients: 0/1 A operand from the sign words, 2 MMAs per k-step, no read of ya / yc)
+        self.bin_wgrad = self.sign_bits and os.environ.get("XB_BIN_WGRAD", "1") != "0"
+        self._bin_now = False
         self._mask_ready = False
         # Discrete(3): folded head parameters (w_j - w_2, b_j - b_2), two-column head outputs / gradients
         self.fold3 = (not self.gaussian) and self.A == 3
@@ -143,13 +146,19 @@ class FusedActorCritic:
     def stage_trunk(self, obs, b):
         ops.mlp_trunk_fwd(obs, self.l0.weight.data, self.l0.bias.data, self.slope, b["h1"])
 
-    def stage_hidden(self, b, loss=None):
+    def can_skip_y(self, softmax_pair=False):
+        """True if a backward with these head gradients reads the hidden activations only through their sign words (sign-word
+        dgrad + binary-form wgrad): the training forward then need not write ya / yc at all (67 MB per 65 536-row minibatch)."""
+        return self.sign_bits and self.bin_wgrad and self._rank1(softmax_pair)
+
+    def stage_hidden(self, b, loss=None, keep_y=True):
         """Actor + critic hidden layers and heads in one launch.  `loss` (dict: scal, adv_stats, adv_count, clip_range,
         vf_coef, ent_coef, inv_batch, logstd, scalars, dlogstd): also the PPO loss forward + backward, fused into the
         kernel's epilogue — dL/d(act_out) lands in b["dact"], dL/dv in b["dv"]."""
         hw, hb = self._head_a()
-        l0 = (self.wa_hi, self.wa_lo, self.la1.bias.data, b["ya"], hw, hb, b["act2"] if self.fold3 else b["act"])
-        l1 = (self.wc_hi, self.wc_lo, self.lc1.bias.data, b["yc"], self.lc2.weight.data, self.lc2.bias.data, b["v"])
+        b["y_valid"] = keep_y
+        l0 = (self.wa_hi, self.wa_lo, self.la1.bias.data, b["ya"] if keep_y else None, hw, hb, b["act2"] if self.fold3 else b["act"])
+        l1 = (self.wc_hi, self.wc_lo, self.lc1.bias.data, b["yc"] if keep_y else None, self.lc2.weight.data, self.lc2.bias.data, b["v"])
         # the same launch writes the w2-scaled weight operand of the mask-form dgrad that follows (csrc/dense_tc.cu KParams)
         prep = (self.la1.weight.data, self.lc1.weight.data, self.wtm_hi, self.wtm_lo) if self.mask_dgrad else None
         self._mask_ready = prep is not None
@@ -170,6 +179,7 @@ class FusedActorCritic:
     def stage_dgrad(self, b, dact, dv2, softmax_pair=False):
         """softmax_pair: `dact` [B, 2] are the gradients w.r.t. the two logits of a softmax head (they are opposite), so
         the actor's head gradient is rank-1 like a one-head source and the mask-form operand applies."""
+        assert b.get("y_valid", True) or b.get("signs") is not None, "forward(keep_y=False) needs the sign-word dgrad"
         if self._mask_ready and (self.A == 1 or (self.A == 2 and softmax_pair)):
             ops.dense_dgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, self.wtm_hi, self.wtm_lo,
                             b["h1"], self.slope, b["dz1"], wt_form=1, signs=b["signs"])
@@ -177,8 +187,16 @@ class FusedActorCritic:
         ops.dense_dgrad(b["ya"], dact, self._head_a()[0], b["yc"], dv2, self.lc2.weight.data, self.wt_hi, self.wt_lo,
                         b["h1"], self.slope, b["dz1"], signs=b["signs"])
 
-    def stage_wgrad(self, b, dact, dv2):
+    def _rank1(self, softmax_pair):
+        return (not self.fold3) and (self.A == 1 or (self.A == 2 and softmax_pair))
+
+    def stage_wgrad(self, b, dact, dv2, softmax_pair=False):
         """Per-CTA partial sums only (into ws_wgrad); `stage_tail` finishes them."""
+        self._bin_now = self.bin_wgrad and self._rank1(softmax_pair) and b.get("signs") is not None
+        if self._bin_now:
+            ops.dense_wgrad_bin(b["signs"], dact, self.A, dv2, 1, b["h1"], self.H, self.ws_wgrad)
+            return
+        assert b.get("y_valid", True), "forward(keep_y=False) needs the binary-form wgrad (rank-1 head gradients)"
         ops.dense_wgrad(b["ya"], dact, self._head_a()[0], b["yc"], dv2, self.lc2.weight.data, b["h1"], self.slope,
                         self.ws_wgrad, None, None, None, None)
 
@@ -197,10 +215,15 @@ class FusedActorCritic:
             norm = (fl.workspace, fl.step, fl.lr0, fl.end_factor, fl.total_iters, fl.beta1, fl.beta2, max_norm, 1.0, fl.lr,
                     fl.gnorm)
             self.norm_done = True
+        bin_form = None
+        if self._bin_now:
+            bin_form = (self.la1.weight.data, self.la1.bias.data, self.la2.weight.data, self.lc1.weight.data, self.lc1.bias.data,
+                        self.lc2.weight.data, self.slope)
         ops.mlp_backward_tail(self.ws_wgrad, self.H, self.H, self.nh_a, 1,
                               (g(self.la1.weight), g(self.la1.bias), g(self.la2.weight), g(self.la2.bias)),
                               (g(self.lc1.weight), g(self.lc1.bias), g(self.lc2.weight), g(self.lc2.bias)),
-                              self.ws_trunk, self.obs_dim, g(self.l0.weight), g(self.l0.bias), dls64, dls32, norm=norm)
+                              self.ws_trunk, self.obs_dim, g(self.l0.weight), g(self.l0.bias), dls64, dls32, norm=norm,
+                              bin_form=bin_form)
         if self.fold3:      # third head row from the two the kernels produced: dL/dz2 = -(dL/dz0 + dL/dz1)
             ops.head3_unfold_grads(g(self.la2.weight), g(self.la2.bias))
 
@@ -227,7 +250,7 @@ class FusedActorCritic:
         return b["act"], b["v"][:, 0]
 
     # ---------------------------------------------------------------------------------------------- forward / backward
-    def forward(self, obs, refresh=True, trunk_done=False, loss=None):
+    def forward(self, obs, refresh=True, trunk_done=False, loss=None, keep_y=True):
         """obs: CUDA fp32 [B, obs_dim] with contiguous rows (a column slice of the float4 observation rows is fine).
         Returns (act_out [B, A], v [B]); the activations stay in per-batch-size buffers for `backward`."""
         B = obs.shape[0]
@@ -238,7 +261,7 @@ class FusedActorCritic:
             self.fold_head()                # the head parameters move with every optimiser step
         if not trunk_done:              # the gather kernel already produced h1 for these rows (xb_gather_trunk_fwd)
             self.stage_trunk(obs, b)
-        self.stage_hidden(b, loss)
+        self.stage_hidden(b, loss, keep_y)
         self._last = (obs, b)
         return b["act"], b["v"][:, 0]
 
@@ -272,11 +295,11 @@ class FusedActorCritic:
             self._side.wait_stream(cur)
             self.stage_dgrad(b, dact, dv2, softmax_pair)
             with torch.cuda.stream(self._side):
-                self.stage_wgrad(b, dact, dv2)
+                self.stage_wgrad(b, dact, dv2, softmax_pair)
             self.stage_trunk_wgrad(obs, b)
             cur.wait_stream(self._side)
         else:
             self.stage_dgrad(b, dact, dv2, softmax_pair)
-            self.stage_wgrad(b, dact, dv2)
+            self.stage_wgrad(b, dact, dv2, softmax_pair)
             self.stage_trunk_wgrad(obs, b)
         self.stage_tail(dls64, dls32)

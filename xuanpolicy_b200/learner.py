@@ -314,7 +314,9 @@ class PPOCLIP_Learner:
             loss = dict(scal=mb["scal"], adv_stats=stats, adv_count=B * self.world_size, clip_range=self.clip_range,
                         vf_coef=self.vf_coef, ent_coef=self.ent_coef, inv_batch=1.0 / (B * self.world_size), logstd=logstd,
                         scalars=self._scalars, dlogstd=self._dls64 if fused.gaussian else None)
-            fused.forward(mb["obs"], refresh=not fused.splits_fresh, trunk_done=mb.get("trunk_done", False), loss=loss)
+            # (rank-1 head gradients: the backward reads the hidden activations only through their sign words — not stored)
+            fused.forward(mb["obs"], refresh=not fused.splits_fresh, trunk_done=mb.get("trunk_done", False), loss=loss,
+                          keep_y=not fused.can_skip_y(softmax_pair=not fused.gaussian))
             b = fused._last[1]
             if fused.gaussian:
                 flat = self._flat

@@ -420,17 +420,33 @@ def mlp_trunk_wgrad(dz1, obs, workspace, dw0, db0):
               obs.shape[0], dz1.shape[1], _stream())
 
 
+def dense_wgrad_bin(signs, dout0, nh0, dout1, nh1, x, h_out, workspace):
+    """Binary-form weight-gradient partials (xb_dense_wgrad_bin): rank-1 head gradients, activation sign words instead of Y."""
+    B, h_in = x.shape
+    _lib.call("xb_dense_wgrad_bin", _p(signs, I32), signs.shape[1], _p(dout0, F32), nh0, _p(dout1, F32), nh1, _p(x, F32), B,
+              h_out, h_in, _p(workspace, F32), _stream())
+
+
 def mlp_backward_tail(wgrad_ws, h_out, h_in, nh0, nh1, grads0, grads1, trunk_ws, obs_dim, dwt, dbt, dls64=None, dls32=None,
-                      norm=None):
+                      norm=None, bin_form=None):
     """grads0/grads1 = (dW, db, dw2, db2) of the actor / critic; finishes xb_dense_wgrad + xb_mlp_trunk_wgrad partials.
     norm = (workspace, step_dev, lr0, lr_end_factor, lr_total_iters, beta1, beta2, max_norm, grad_scale, lr_out, gnorm_out):
-    also take the global gradient norm and derive the clipped-Adam scalars in the same launch."""
+    also take the global gradient norm and derive the clipped-Adam scalars in the same launch.
+    bin_form = (W0, b0, w2_0, W1, b1, w2_1, slope): the partials come from dense_wgrad_bin (xb_mlp_backward_tail_bin)."""
     parts = _lib.load().xb_mlp_trunk_wgrad_parts()
     args = [_p(wgrad_ws, F32), h_out, h_in, 2 if grads1 is not None else 1, nh0, nh1,
             *[_p(g, F32) for g in grads0], *([_p(g, F32) for g in grads1] if grads1 is not None else [None] * 4),
             _p(trunk_ws, F32), parts, obs_dim, _p(dwt, F32), _p(dbt, F32), _p(dls64, F64), _p(dls32, F32),
             dls64.numel() if dls64 is not None else 0]
-    if norm is None:
+    if bin_form is not None:
+        ws, step_dev, lr0, end_factor, total_iters, beta1, beta2, max_norm, grad_scale, lr_out, gnorm_out = \
+            norm if norm is not None else (None, None, 0.0, 1.0, 1, 0.9, 0.999, 0.0, 1.0, None, None)
+        W0, b0, w2_0, W1, b1, w2_1, slope = bin_form
+        _lib.call("xb_mlp_backward_tail_bin", *args, _p(ws, F64), _p(step_dev, I64), float(lr0), float(end_factor),
+                  int(total_iters), float(beta1), float(beta2), float(max_norm), float(grad_scale), _p(lr_out, F32),
+                  _p(gnorm_out, F32), _p(W0, F32), _p(b0, F32), _p(w2_0, F32), _p(W1, F32), _p(b1, F32), _p(w2_1, F32),
+                  float(slope), _stream())
+    elif norm is None:
         _lib.call("xb_mlp_backward_tail", *args, _stream())
     else:
         ws, step_dev, lr0, end_factor, total_iters, beta1, beta2, max_norm, grad_scale, lr_out, gnorm_out = norm
