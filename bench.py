@@ -57,6 +57,24 @@ WORKLOADS = {
 HBM_FALLBACK_GBS = 6650.0
 
 
+def roofline_of(dom, kd, peak, peak_src, traffic):
+    """The dominant kernel (largest CUDA-event time x launches per step) against the roof that bounds it: the tensor pipe when
+    its TF32-pass fraction exceeds its HBM fraction (round 2: the dense kernels no longer move the hidden activations), else HBM."""
+    hbm = {"achieved": kd["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": kd["frac"], "bytes_per_launch": kd["bytes_per_launch"]}
+    note = ("kernel with the largest share of the step (CUDA-event time x launches per step); HBM: achieved = algorithmic bytes / "
+            "time; tensor: achieved = fp32-equivalent GEMM flops x TF32 passes / time against 1/2 of the measured bf16 peak.  "
+            "See c4_gae for the pure HBM-bound shape")
+    if kd.get("tensor_frac_of_tf32_peak", 0.0) > kd["frac"]:
+        return {"kernel": dom, "bound": "tensor", "achieved": kd["tensor_pipe_tflops_tf32"], "peak": round(measured_tf32_peak(), 1),
+                "unit": "TFLOP/s", "frac": kd["tensor_frac_of_tf32_peak"], "traffic": traffic,
+                "peak_source": "1/2 x measured cuBLAS bf16 (MEASURED_PEAKS.json)", "tf32_passes": kd.get("tf32_passes"),
+                "gemm_tflops": kd.get("gemm_tflops"), "hbm": hbm, "note": note}
+    return {"kernel": dom, "bound": "hbm", "achieved": kd["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": kd["frac"],
+            "traffic": traffic, "peak_source": peak_src,
+            "tensor": {k: kd[k] for k in ("gemm_tflops", "tensor_pipe_tflops_tf32", "tensor_frac_of_tf32_peak") if k in kd},
+            "note": note}
+
+
 def measured_tf32_peak():
     """Dense TF32 tensor-pipe ceiling in TFLOP/s: half the measured cuBLAS bf16 burst throughput (same pipe, K per
     instruction halves), else half the fallback."""
@@ -261,15 +279,15 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
     out = {}
     tf32_peak = measured_tf32_peak()
 
-    def add(name, fn, bytes_per_launch, launches, flops=None):
+    def add(name, fn, bytes_per_launch, launches, flops=None, passes=3):
         mean_ms, min_ms = time_kernel(fn, flush)
         gbs = bytes_per_launch / (mean_ms * 1e-3) / 1e9
         out[name] = {"ms": round(mean_ms, 5), "min_ms": round(min_ms, 5), "launches_per_step": launches,
                      "bytes_per_launch": int(bytes_per_launch), "achieved_gbs": round(gbs, 2), "frac": round(gbs / peak, 5)}
-        if flops:   # tensor-core kernels: fp32-equivalent GEMM flops (2MNK); the 3xTF32 split issues 3x that on the tensor pipe
-            tf = flops / (mean_ms * 1e-3) / 1e12
-            out[name].update({"gemm_tflops": round(tf, 2), "tensor_pipe_tflops_tf32": round(3 * tf, 2),
-                              "tensor_frac_of_tf32_peak": round(3 * tf / tf32_peak, 4)})
+        if flops:   # tensor-core kernels: fp32-equivalent GEMM flops (2MNK); the TF32 split issues `passes` x that on the tensor
+            tf = flops / (mean_ms * 1e-3) / 1e12      # pipe (3: hi/lo of both operands; 2: binary-form wgrad, one operand exact)
+            out[name].update({"gemm_tflops": round(tf, 2), "tf32_passes": passes, "tensor_pipe_tflops_tf32": round(passes * tf, 2),
+                              "tensor_frac_of_tf32_peak": round(passes * tf / tf32_peak, 4)})
 
     with torch.no_grad():
         dist, v = agent._policy_forward(agent._x[agent._cur])
@@ -373,10 +391,21 @@ def kernel_rooflines(agent, flush, peak, launches_per_step, with_c4, world):
         adam_split = os.environ.get("XB_ADAM_SPLIT", "1") != "0"
         add("mlp_split_weights", lambda: fused.refresh_weights(), 2 * H * H * 4 * 5, 1 if adam_split else upd + 1)
         add("mlp_trunk_fwd", lambda: fused.stage_trunk(obs_u, bu), B * od * 4 + f4, 0 if mb.get("trunk_done") else upd)
-        add("dense_fwd2_tc", lambda: fused.stage_hidden(bu), 3 * f4 + B * (A_out + 1) * 4, upd, flops=2 * 2.0 * B * H * H)
-        add("dense_dgrad_tc", lambda: fused.stage_dgrad(bu, dact, dv2), 4 * f4 + B * (A_out + 1) * 4, upd, flops=2.0 * B * 2 * H * H)
-        add("dense_wgrad_tc", lambda: fused.stage_wgrad(bu, dact, dv2), 3 * f4 + B * (A_out + 1) * 4, upd,
-            flops=2 * 2.0 * B * H * (H + 1))
+        # round 2: with rank-1 head gradients (every BASELINE config) the hidden activations ya / yc are never stored — the
+        # forward leaves one SIGN BIT per activation (B x 2H/32 words), dgrad and the binary-form wgrad read those
+        pair = not gauss                               # categorical: the two logit gradients are a softmax pair
+        if pair:
+            dact[:, 1] = -dact[:, 0]
+        skip_y = fused.can_skip_y(softmax_pair=pair)
+        sgn = B * (2 * H // 32) * 4 if fused.sign_bits else 0
+        heads = B * (A_out + 1) * 4
+        add("dense_fwd2_tc", lambda: fused.stage_hidden(bu, keep_y=not skip_y), (1 if skip_y else 3) * f4 + sgn + heads, upd,
+            flops=2 * 2.0 * B * H * H)
+        add("dense_dgrad_tc", lambda: fused.stage_dgrad(bu, dact, dv2, softmax_pair=pair),
+            (2 * f4 + sgn if fused.sign_dgrad else 4 * f4) + heads, upd, flops=2.0 * B * 2 * H * H)
+        binw = fused.bin_wgrad and fused._rank1(pair)
+        add("dense_wgrad_tc", lambda: fused.stage_wgrad(bu, dact, dv2, softmax_pair=pair), (f4 + sgn if binw else 3 * f4) + heads,
+            upd, flops=2 * 2.0 * B * H * (H + 1), passes=2 if binw else 3)
         add("mlp_trunk_wgrad", lambda: fused.stage_trunk_wgrad(obs_u, bu), f4 + B * od * 4, upd)
         add("mlp_backward_tail", lambda: fused.stage_tail(), fused.ws_wgrad.numel() * 4 + fused.ws_trunk.numel() * 4, upd)
         # rollout shape: 2N rows (the obs to act on + the previous step's terminal obs)
@@ -680,12 +709,7 @@ def run_ours(args):
                 "ms_per_step": round(ms_e2e, 4),
                 "what": "PPOCLIP_Agent.train with host-drawn minibatch permutations (pinned H2D per epoch) and log scalars read back"},
         "gpu_launches": launches * args.steps,
-        "roofline": {"kernel": dom, "bound": "hbm", "achieved": kd["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": kd["frac"], "traffic": traffic, "peak_source": peak_src,
-                     "tensor": {k: kd[k] for k in ("gemm_tflops", "tensor_pipe_tflops_tf32", "tensor_frac_of_tf32_peak") if k in kd},
-                     "note": "kernel with the largest share of the step (CUDA-event time x launches per step); achieved = "
-                             "algorithmic bytes / time.  Dense kernels: HBM time and 3xTF32 tensor-pipe time are about equal "
-                             "at this shape, both fractions are given.  See c4_gae for the pure HBM-bound shape"},
+        "roofline": roofline_of(dom, kd, peak, peak_src, traffic),
         "kernels": kernels,
         "phases": phases,
         "cpu_baseline": cpu,

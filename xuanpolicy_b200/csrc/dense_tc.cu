@@ -505,16 +505,20 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     if (warp == kProducerWarp) {
         // ============================================================ TMA producer (one thread)
-        if (lane == 0) {
-            tma_prefetch_desc(map_a0);
-            tma_prefetch_desc(map_bhi);
-            tma_prefetch_desc(map_blo);
-            if (MODE == MODE_DGRAD) tma_prefetch_desc(map_a1);
+        {   // the whole warp walks the loop, one elected lane issues (uniform operands, see tma_load_2d_if)
+            const uint32_t elected = elect_one_pred();
+            if (lane == 0) {
+                tma_prefetch_desc(map_a0);
+                tma_prefetch_desc(map_bhi);
+                tma_prefetch_desc(map_blo);
+                if (MODE == MODE_DGRAD) tma_prefetch_desc(map_a1);
+            }
+            __syncwarp();
             if (B_RES) {
-                mbar_arrive_expect_tx(bar_bfull, 2u * KB * kBTile);
+                mbar_arrive_expect_tx_if(elected, bar_bfull, 2u * KB * kBTile);
                 for (int kb = 0; kb < KB; ++kb) {
-                    tma_load_2d(bres + kb * kBTile, map_bhi, kb * BK, 0, bar_bfull);
-                    tma_load_2d(bres + (KB + kb) * kBTile, map_blo, kb * BK, 0, bar_bfull);
+                    tma_load_2d_if(elected, bres + kb * kBTile, map_bhi, kb * BK, 0, bar_bfull);
+                    tma_load_2d_if(elected, bres + (KB + kb) * kBTile, map_blo, kb * BK, 0, bar_bfull);
                 }
             }
             uint32_t s = 0, ph = 0, it = 0;
@@ -523,27 +527,29 @@ __global__ void __launch_bounds__(kThreads, 1)
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
                     XB_TS(0, it, 0);
                     const uint32_t st = ring + s * stage_bytes;
-                    mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
+                    mbar_arrive_expect_tx_if(elected, bar_full + 8 * s, stage_bytes);
                     const bool src1 = (MODE == MODE_DGRAD) && kb >= p.kb_split;
                     const int kcol = (src1 ? kb - p.kb_split : kb) * BK;
-                    tma_load_2d(st, src1 ? map_a1 : map_a0, kcol, (int)(tile * BM), bar_full + 8 * s);
+                    tma_load_2d_if(elected, st, src1 ? map_a1 : map_a0, kcol, (int)(tile * BM), bar_full + 8 * s);
                     if (!B_RES) {
-                        tma_load_2d(st + kATile, map_bhi, kb * BK, 0, bar_full + 8 * s);
-                        tma_load_2d(st + kATile + kBTile, map_blo, kb * BK, 0, bar_full + 8 * s);
+                        tma_load_2d_if(elected, st + kATile, map_bhi, kb * BK, 0, bar_full + 8 * s);
+                        tma_load_2d_if(elected, st + kATile + kBTile, map_blo, kb * BK, 0, bar_full + 8 * s);
                     }
                     if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == kMmaWarp) {
-        // ============================================================ MMA issuer (one thread)
-        if (lane == 0) {
+        // ============================================================ MMA issuer (whole warp walks, one elected lane issues)
+        {
+            const uint32_t elected = elect_one_pred();
+            const uint32_t tmem_base_u = __reduce_max_sync(0xffffffffu, tmem_base);
             if (B_RES) mbar_wait(bar_bfull, 0);
             uint32_t s = 0, ph = 0, j = 0, lt = 0, it = 0;
             for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++lt) {
                 const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
                 mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
-                const uint32_t d_tmem = tmem_base + acc * N;
+                const uint32_t d_tmem = tmem_base_u + acc * N;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     XB_TS(1, it, 0);
                     mbar_wait(bar_conv + 8 * s, ph);          // operand warps arrive after they saw the TMA bytes land
@@ -559,14 +565,14 @@ __global__ void __launch_bounds__(kThreads, 1)
                         const uint64_t da_lo = umma_desc_sw128(a_lo + k * 32, 16, 1024);
                         const uint64_t db_hi = umma_desc_sw128(b_hi + k * 32, 16, 1024);
                         const uint64_t db_lo = umma_desc_sw128(b_lo + k * 32, 16, 1024);
-                        mma_tf32_ss(d_tmem, da_lo, db_hi, kIdesc, (kb | k) != 0);
-                        mma_tf32_ss(d_tmem, da_hi, db_lo, kIdesc, 1);
-                        mma_tf32_ss(d_tmem, da_hi, db_hi, kIdesc, 1);
+                        mma_tf32_ss_if(elected, d_tmem, da_lo, db_hi, kIdesc, (kb | k) != 0);
+                        mma_tf32_ss_if(elected, d_tmem, da_hi, db_lo, kIdesc, 1);
+                        mma_tf32_ss_if(elected, d_tmem, da_hi, db_hi, kIdesc, 1);
                     }
                     XB_TS(1, it, 2);
-                    mma_commit(bar_empty + 8 * s);
-                    mma_commit(bar_loempty + 8 * j);
-                    if (kb == KB - 1) mma_commit(bar_tfull + 8 * acc);
+                    mma_commit_if(elected, bar_empty + 8 * s);
+                    mma_commit_if(elected, bar_loempty + 8 * j);
+                    if (kb == KB - 1) mma_commit_if(elected, bar_tfull + 8 * acc);
                     XB_TS(1, it, 3);
                     if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                     if (++j == (uint32_t)L) j = 0;
@@ -2011,7 +2017,7 @@ __global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restri
                                     int H_out, float* dW0, float* db0, float* dw2_0, float* db2_0, int nh0, float* dW1,
                                     float* db1, float* dw2_1, float* db2_1, int nh1, TailArgs tail, BinArgs bin) {
     __shared__ float red[4][260];
-    __shared__ float bin_g[256], bin_red[4], bin_e;
+    __shared__ float bin_g[256], bin_g4[4][256], bin_red[4], bin_e;
     __shared__ double norm_smem[32];
     __shared__ bool norm_last;
     pdl_wait();
@@ -2050,6 +2056,17 @@ __global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restri
         const int grp = threadIdx.x >> 7, t = threadIdx.x & 127;
         const int n_cta = (grid - job + n_jobs - 1) / n_jobs;          // CTAs that worked on this job: job, job + n_jobs, ...
         const int ncol = bin.on ? HIN + 1 : HIN + 3;                    // HIN weights | bias | head 0 | head 1
+        // BINARY form: the scaling operands, loaded up front so that they travel with the partials' round trip
+        float bw[2] = {0.f, 0.f}, w2m = 0.f, bias_m = 0.f;
+        if (bin.on) {
+            const float* w2p = bin.w2[src];
+            w2m = nh > 1 ? w2p[m] - w2p[H_out + m] : w2p[m];
+            bias_m = bin.b[src][m];
+            if (grp == 0) {
+                bw[0] = bin.W[src][(int64_t)m * HIN + t];
+                if (HIN > 128) bw[1] = bin.W[src][(int64_t)m * HIN + 128 + t];
+            }
+        }
         for (int n = t; n < ncol; n += 128) {
             float acc = 0.f;
             const float* src_ptr;
@@ -2067,19 +2084,30 @@ __global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restri
                 const int c = grp + 4 * u;
                 v[u] = c < n_cta ? src_ptr[c * stride] : 0.f;
             }
+            // BINARY form: the column sums G[n] (head_part rows of this job's CTAs) ride in the same round trip
+            const bool with_g = bin.on && n < HIN;
+            const float* g_ptr = head_part + (int64_t)job * 256 + n;
+            const int64_t g_stride = (int64_t)n_jobs * 256;
+            float v2[20], acc2 = 0.f;
+#pragma unroll
+            for (int u = 0; u < 20; ++u) {
+                const int c = grp + 4 * u;
+                v2[u] = (with_g && c < n_cta) ? g_ptr[c * g_stride] : 0.f;
+            }
 #pragma unroll
             for (int u = 0; u < 20; ++u) acc += v[u];
             for (int c = grp + 80; c < n_cta; c += 4) acc += src_ptr[c * stride];
             red[grp][n] = acc;
+            if (with_g) {
+#pragma unroll
+                for (int u = 0; u < 20; ++u) acc2 += v2[u];
+                for (int c = grp + 80; c < n_cta; c += 4) acc2 += g_ptr[c * g_stride];
+                bin_g4[grp][n] = acc2;
+            }
         }
         if (bin.on) {
             // BINARY form (dense_wgrad_bin_kernel): column sums G[n] (head_part rows of this job's CTAs) and E (db2_part), every
             // block for itself; then Gm = (1 - slope) A + slope G, gm = (1 - slope) S + slope E and the scalings by w2' / W / b
-            for (int n = threadIdx.x; n < HIN; n += 512) {
-                float a4[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int c = 0; c < n_cta; ++c) a4[c & 3] += head_part[(int64_t)(job + c * n_jobs) * 256 + n];
-                bin_g[n] = (a4[0] + a4[1]) + (a4[2] + a4[3]);
-            }
             if (threadIdx.x >= 480) {                                   // last warp: E
                 float e = 0.f;
                 for (int c = t - 96; c < n_cta; c += 32) e += db2_part[(int64_t)(job + c * n_jobs) * 2];
@@ -2089,8 +2117,8 @@ __global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restri
         }
         __syncthreads();
         if (bin.on) {
-            const float* w2p = bin.w2[src];
-            const float w2m = nh > 1 ? w2p[m] - w2p[H_out + m] : w2p[m];
+            for (int n = threadIdx.x; n < HIN; n += 512) bin_g[n] = (bin_g4[0][n] + bin_g4[1][n]) + (bin_g4[2][n] + bin_g4[3][n]);
+            __syncthreads();
             const float sl = bin.slope, om = 1.0f - bin.slope;
             float dot = 0.f;                                            // this thread's share of sum_n W[m][n] Gm[n]
             if (grp == 0) {
@@ -2100,7 +2128,7 @@ __global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restri
                     const float gw = w2m * gm_n;
                     dW[(int64_t)m * HIN + n] = gw;
                     XB_SQ(gw);
-                    dot += bin.W[src][(int64_t)m * HIN + n] * gm_n;
+                    dot += bw[n >> 7] * gm_n;
                 }
                 dot = warp_sum(dot);
                 if ((t & 31) == 0) bin_red[t >> 5] = dot;
@@ -2112,7 +2140,7 @@ __global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restri
                 const float gb = w2m * gm;
                 db[m] = gb;
                 XB_SQ(gb);
-                const float g2 = ((bin_red[0] + bin_red[1]) + (bin_red[2] + bin_red[3])) + bin.b[src][m] * gm;
+                const float g2 = ((bin_red[0] + bin_red[1]) + (bin_red[2] + bin_red[3])) + bias_m * gm;
                 dw2[m] = g2;
                 XB_SQ(g2);
                 if (nh > 1) { dw2[H_out + m] = -g2; XB_SQ(g2); }

@@ -130,6 +130,27 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uin
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// predicated forms for a converged warp with one issuing lane (see tma_load_2d_if)
+__device__ __forceinline__ void mma_tf32_ss_if(uint32_t elected, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, pe;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "setp.ne.b32 pe, %5, 0;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(elected)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_if(uint32_t elected, uint32_t bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe;\n"
+        "setp.ne.b32 pe, %1, 0;\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(bar), "r"(elected)
+        : "memory");
+}
 // all previously issued tcgen05.mma of this thread complete -> one arrival on the mbarrier
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -93,7 +93,8 @@ class FusedActorCritic:
         self.wtm_hi, self.wtm_lo = z(H, 2 * H), z(H, 2 * H)
         self.mask_dgrad = os.environ.get("XB_MASK_DGRAD", "1") != "0"
         # activation sign words: the forward leaves one bit per hidden activation, dgrad reads those instead of ya / yc
-        self.sign_bits = os.environ.get("XB_SIGN_BITS", "1") != "0" and H == 128
+        self.sign_bits = os.environ.get("XB_SIGN_BITS", "1") != "0"
+        self.sign_dgrad = self.sign_bits and H == 128       # (the tensor-memory dgrad kernel; H = 256 runs the SS form on ya / yc)
         # binary-form weight gradients (rank-1 head gradients: 0/1 A operand from the sign words, 2 MMAs per k-step, no read of ya / yc)
         self.bin_wgrad = self.sign_bits and os.environ.get("XB_BIN_WGRAD", "1") != "0"
         self._bin_now = False
@@ -149,7 +150,7 @@ class FusedActorCritic:
     def can_skip_y(self, softmax_pair=False):
         """True if a backward with these head gradients reads the hidden activations only through their sign words (sign-word
         dgrad + binary-form wgrad): the training forward then need not write ya / yc at all (67 MB per 65 536-row minibatch)."""
-        return self.sign_bits and self.bin_wgrad and self._rank1(softmax_pair)
+        return self.sign_dgrad and self.bin_wgrad and self._rank1(softmax_pair)
 
     def stage_hidden(self, b, loss=None, keep_y=True):
         """Actor + critic hidden layers and heads in one launch.  `loss` (dict: scal, adv_stats, adv_count, clip_range,
@@ -179,7 +180,7 @@ class FusedActorCritic:
     def stage_dgrad(self, b, dact, dv2, softmax_pair=False):
         """softmax_pair: `dact` [B, 2] are the gradients w.r.t. the two logits of a softmax head (they are opposite), so
         the actor's head gradient is rank-1 like a one-head source and the mask-form operand applies."""
-        assert b.get("y_valid", True) or b.get("signs") is not None, "forward(keep_y=False) needs the sign-word dgrad"
+        assert b.get("y_valid", True) or (self.sign_dgrad and b.get("signs") is not None), "forward(keep_y=False) needs the sign-word dgrad"
         if self._mask_ready and (self.A == 1 or (self.A == 2 and softmax_pair)):
             ops.dense_dgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, self.wtm_hi, self.wtm_lo,
                             b["h1"], self.slope, b["dz1"], wt_form=1, signs=b["signs"])
