@@ -148,7 +148,10 @@ int xb_gather_records(const int64_t* idx, int64_t B, int64_t T, int64_t N, const
  * latency-bound gather hides behind the store-bound layer — one launch instead of two per update. */
 int xb_gather_trunk_fwd(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* rec, int obs_dim, const float* W0,
                         const float* b0, float slope, int H, float* obs_out, float* scal_out, double* stats, float* h1,
-                        xb_stream_t stream);
+                        uint32_t* h1_signs, xb_stream_t stream);
+/*   h1_signs (nullable, xb_gather_trunk_fwd and xb_mlp_trunk_fwd; H a multiple of 128): u32 [B][H / 32] sign words of h1, four
+ *   per 128-feature slice s — bit l of word 4 s + e = (h1[b][128 s + 4 l + e] > 0), the order the warp ballots produce them —
+ *   for xb_dense_dgrad's epilogue mask. */
 
 /* ------------------------------------------------------------------------------------------------------------
  * (4b) PPO-Clip loss forward + backward, fused with the gather of the per-transition scalars.
@@ -468,6 +471,19 @@ int xb_dense_fwd2_loss(const float* X, int64_t M, int K, int N, float slope, con
                        float ent_coef, float inv_batch, const float* logstd, float* dact, float* dv, double* loss_partials,
                        uint32_t* loss_ticket, double* scalars, double* dlogstd, const float* prep_W0, const float* prep_W1,
                        float* prep_thi, float* prep_tlo, uint32_t* sign_out, xb_stream_t stream);
+/* xb_mlp_fwd_from_obs for TRAINING: the trunk layer generated in the kernel plus everything xb_dense_fwd2_loss adds (Y0 / Y1,
+ * sign_out, prep_*, and — with scal != NULL — the fused PPO loss).  h1_out f32 [M][H] receives the trunk activations
+ * leaky_relu(W0 obs + b0) (stored by the operand warps of the layer-0 CTAs): the backward kernels read them, this launch does not.
+ * Replaces xb_mlp_trunk_fwd / the first-layer half of xb_gather_trunk_fwd + the h1 read of xb_dense_fwd2_loss. */
+int xb_mlp_fwd_from_obs_train(const float* obs, int ld, int obs_dim, const float* W0, const float* b0, int64_t M, int H,
+                              float slope, const float* Whi0, const float* Wlo0, const float* bias0, float* Y0,
+                              const float* head_w0, const float* head_b0, int n_head0, float* head_out0, const float* Whi1,
+                              const float* Wlo1, const float* bias1, float* Y1, const float* head_w1, const float* head_b1,
+                              int n_head1, float* head_out1, float* h1_out, const float* scal, const double* adv_stats,
+                              int64_t adv_count, float clip_range, float vf_coef, float ent_coef, float inv_batch,
+                              const float* logstd, float* dact, float* dv, double* loss_partials, uint32_t* loss_ticket,
+                              double* scalars, double* dlogstd, const float* prep_W0, const float* prep_W1, float* prep_thi,
+                              float* prep_tlo, uint32_t* sign_out, xb_stream_t stream);
 int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const float* W0, const float* b0, int64_t M, int H,
                         float slope, const float* Whi0, const float* Wlo0, const float* bias0, float* Y0,
                         const float* head_w0, const float* head_b0, int n_head0, float* head_out0, const float* Whi1,
@@ -477,14 +493,16 @@ int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const float* W0, 
 int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, int K0, const float* Y1,
                    const float* dout1, const float* w2_1, int nh1, int K1, int64_t M, const float* Wthi,
                    const float* Wtlo, int N, const float* H1, float slope, float* dZ1, int wt_form, const uint32_t* signs,
-                   xb_stream_t stream);
+                   const uint32_t* h1_signs, xb_stream_t stream);
 /*   wt_form 0: Wthi / Wtlo = the plain transposed weights (xb_dense_split_weights*), any head gradients (nh <= 2).
  *   wt_form 1 ("mask form"): Wthi / Wtlo = the w2-scaled operand written by xb_dense_fwd2(_loss) (prep_*).  Valid when every
  *   source's head gradient is rank-1: one head, or two logits of a softmax head (whose gradients are opposite: dout[:, 1] is
  *   then NOT read, -dout[:, 0] is implied).  The operand warps then select per element between two per-row constants
  *   instead of multiplying and splitting — same 3xTF32 accuracy.
  *   signs (nullable): u32 [M][(K0 + K1) / 32] sign words of [Y0 | Y1] as written by xb_dense_fwd2(_loss) (sign_out); used by the
- *   tensor-memory (N <= 128, K0 + K1 <= 256) kernel in place of Y0 / Y1 (which are then not read) — bit-identical results. */
+ *   tensor-memory (N <= 128, K0 + K1 <= 256) kernel in place of Y0 / Y1 (which are then not read) — bit-identical results.
+ *   h1_signs (nullable, with signs, N = 128): u32 [M][4] sign words of H1 (xb_gather_trunk_fwd / xb_mlp_trunk_fwd): the
+ *   epilogue mask leaky'(H1) without loading the H1 tiles (H1 is then not read; 16-byte aligned). */
 
 /* ------------------------------------------------------------------------------------------------------------
  * First (narrow-input) layer of the MLP, Linear(obs_dim, H) + LeakyReLU — Basic_MLP
@@ -495,7 +513,7 @@ int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int n
  * workspace (xb_mlp_backward_tail finishes them together with the hidden layers' partials in one launch).
  * ---------------------------------------------------------------------------------------------------------- */
 int xb_mlp_trunk_fwd(const float* obs, int ld, int obs_dim, const float* W0, const float* b0, float slope, float* h1,
-                     int64_t B, int H, xb_stream_t stream);
+                     int64_t B, int H, uint32_t* h1_signs, xb_stream_t stream);
 int xb_mlp_trunk_wgrad_workspace_floats(int obs_dim, int H);
 int xb_mlp_trunk_wgrad_parts(void);     /* number of partial sums per output in the workspace */
 int xb_mlp_trunk_wgrad(const float* dz1, const float* obs, int ld, int obs_dim, float* workspace, float* dW0, float* db0,

@@ -181,9 +181,16 @@ def test_gather_trunk_fwd_equals_gather_then_trunk(obs_dim, H, B):
     ops.mlp_trunk_fwd(obs_a, w0, b0, 0.01, h_a)
     obs_b, scal_b = torch.empty_like(obs_a), torch.empty_like(scal_a)
     st_b, h_b = torch.zeros_like(st_a), torch.empty_like(h_a)
-    ops.gather_trunk_fwd(idx, T, N, rec, obs_dim, w0, b0, 0.01, obs_b, scal_b, h_b, stats=st_b)
+    hs_a = torch.zeros((B, H // 32), dtype=torch.int32, device="cuda")
+    hs_b = torch.zeros_like(hs_a)
+    ops.mlp_trunk_fwd(obs_a, w0, b0, 0.01, h_a, h1_signs=hs_a)
+    ops.gather_trunk_fwd(idx, T, N, rec, obs_dim, w0, b0, 0.01, obs_b, scal_b, h_b, stats=st_b, h1_signs=hs_b)
     assert torch.equal(obs_a, obs_b) and torch.equal(scal_a, scal_b) and torch.equal(h_a, h_b)
     assert torch.allclose(st_a, st_b, rtol=1e-12, atol=1e-9)
+    # both kernels' sign words of h1: bit l of word 4 s + e = h1[:, 128 s + 4 l + e] > 0
+    bits = (((hs_b.long() & 0xFFFFFFFF)[:, :, None] >> torch.arange(32, device="cuda")) & 1).bool()      # [B, H/32, l]
+    bits = bits.reshape(B, H // 128, 4, 32).permute(0, 1, 3, 2).reshape(B, H)                             # [s][l][e] -> feature
+    assert torch.equal(hs_a, hs_b) and torch.equal(bits, h_b > 0)
 
 
 @pytest.mark.parametrize("env_id,hidden,B,clip,advnorm", [("Pendulum-v1", 128, 65536, 0.2, True), ("CartPole-v1", 128, 5000, 0.2, True),
@@ -430,7 +437,8 @@ def test_native_agent_on_three_action_envs_uses_the_tensor_core_mlp(env_id):
 @pytest.mark.parametrize("env_id,B", [("Pendulum-v1", 65536), ("CartPole-v1", 2048 + 77)])
 def test_sign_words_match_activations_and_dgrad_is_bit_identical(env_id, B):
     """The forward's activation sign words (one bit per hidden activation) are exactly (y > 0), and the dgrad kernel fed with
-    them produces the bit-identical dZ1 of the kernel that TMA-loads the activation tiles (mask form and plain form)."""
+    them produces the bit-identical dZ1 of the kernel that TMA-loads the activation tiles (mask form and plain form); the same for
+    the trunk's sign words in place of the h1 mask tiles."""
     import xuanpolicy_b200 as xb
     from xuanpolicy_b200 import ops
     from xuanpolicy_b200.fused_mlp import FusedActorCritic
@@ -452,20 +460,27 @@ def test_sign_words_match_activations_and_dgrad_is_bit_identical(env_id, B):
     if A == 2:
         dact[:, 1] = -dact[:, 0]            # softmax pair (what the mask form assumes)
     dv2 = (torch.randn(B, device="cuda", generator=g) / B).reshape(B, 1)
+    # trunk sign words (the dgrad epilogue's mask, opt-in): bit l of word e = h1[:, 4 l + e] > 0
+    b["h1s"] = torch.zeros(B, 4, dtype=torch.int32, device="cuda")
+    ops.mlp_trunk_fwd(obs, fused.l0.weight.data, fused.l0.bias.data, fused.slope, b["h1"], h1_signs=b["h1s"])
+    hwords = b["h1s"].view(B, 4).long() & 0xFFFFFFFF
+    hbits = ((hwords[:, :, None] >> torch.arange(32, device="cuda")) & 1).bool().permute(0, 2, 1).reshape(B, 128)
+    assert torch.equal(hbits, b["h1"] > 0)
     outs = []
-    for signs in (b["signs"], None):
+    for signs, h1s in ((b["signs"], b["h1s"]), (b["signs"], None), (None, None)):
         for form in (1, 0):
             dz1 = torch.full((B, 128), float("nan"), device="cuda")
             if form:
                 ops.dense_dgrad(b["ya"], dact, fused.la2.weight.data, b["yc"], dv2, fused.lc2.weight.data, fused.wtm_hi,
-                                fused.wtm_lo, b["h1"], fused.slope, dz1, wt_form=1, signs=signs)
+                                fused.wtm_lo, b["h1"], fused.slope, dz1, wt_form=1, signs=signs, h1_signs=h1s)
             else:
                 ops.dense_dgrad(b["ya"], dact, fused.la2.weight.data, b["yc"], dv2, fused.lc2.weight.data, fused.wt_hi,
-                                fused.wt_lo, b["h1"], fused.slope, dz1, signs=signs)
+                                fused.wt_lo, b["h1"], fused.slope, dz1, signs=signs, h1_signs=h1s)
             outs.append(dz1)
     torch.cuda.synchronize()
     assert torch.isfinite(outs[0]).all()
-    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
+    assert torch.equal(outs[0], outs[4]) and torch.equal(outs[1], outs[5])
+    assert torch.equal(outs[2], outs[4]) and torch.equal(outs[3], outs[5])
 
 
 @pytest.mark.parametrize("env_id,B", [("Pendulum-v1", 65536), ("CartPole-v1", 8192 + 33)])
@@ -512,3 +527,33 @@ def test_binary_form_wgrad_matches_the_three_mma_form(env_id, B):
         err = float((a - b).abs().max() / scale)
         print("   %-32s %.2e" % (n, err))
         assert err < 5e-5, (n, err)      # (measured against fp64: binary form <= 1e-5, three-MMA form <= 2.1e-5)
+
+
+@pytest.mark.parametrize("env_id,B", [("Pendulum-v1", 65536), ("CartPole-v1", 4096 + 5)])
+def test_training_forward_with_the_trunk_generated_in_the_kernel(env_id, B):
+    """xb_mlp_fwd_from_obs_train (the first MLP layer generated by the hidden-layer launch's operand warps, which also store h1)
+    against xb_mlp_trunk_fwd + xb_dense_fwd2: h1, head outputs, sign words and hidden activations bit-identical."""
+    import xuanpolicy_b200 as xb
+    from xuanpolicy_b200.fused_mlp import FusedActorCritic
+    from xuanpolicy_b200.policies import make_policy
+    obs_space, act_space = xb.make_spaces(env_id)
+    policy = make_policy(obs_space, act_space, hidden=(128,), device="cuda", seed=9)
+    with torch.no_grad():
+        for p in policy.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    fused = FusedActorCritic(policy)
+    assert fused.fwd_from_obs_ok()
+    g = torch.Generator(device="cuda").manual_seed(B)
+    obs = torch.randn(B, obs_space.shape[0], device="cuda", generator=g)
+    out = {}
+    for mode in (False, True):
+        b = fused._buffers(B)
+        for k in ("h1", "ya", "yc", "act", "v"):
+            b[k].fill_(float("nan"))
+        b["signs"].zero_()
+        a, v = fused.forward(obs, trunk_in_kernel=mode)
+        torch.cuda.synchronize()
+        out[mode] = {k: b[k].clone() for k in ("h1", "ya", "yc", "act", "v", "signs")}
+    for k in out[True]:
+        assert torch.equal(out[True][k], out[False][k]), k

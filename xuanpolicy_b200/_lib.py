@@ -39,7 +39,7 @@ SIGNATURES = {
     "xb_kl_coef_adapt": [_vp, _vp, _f32, _i64, _vp],
     "xb_pack_records": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "xb_gather_records": [_vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp],
-    "xb_gather_trunk_fwd": [_vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "xb_gather_trunk_fwd": [_vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
     "xb_sample_categorical": [_vp, _i32, _u64, _vp, _u64, _vp, _vp, _i64, _vp],
     "xb_sample_gaussian": [_vp, _vp, _i32, _u64, _vp, _u64, _vp, _vp, _i64, _vp],
     "xb_counter_add": [_vp, _u64, _vp],
@@ -67,12 +67,15 @@ SIGNATURES = {
                            _vp, _vp, _vp],
     "xb_mlp_fwd_from_obs": [_vp, _i32, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp,
                             _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _f32, _i32, _vp],
+    "xb_mlp_fwd_from_obs_train": [_vp, _i32, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
+                                  _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp,
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "xb_dense_dgrad": [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _i32, _vp, _f32, _vp, _i32, _vp,
-                       _vp],
+                       _vp, _vp],
     "xb_dense_wgrad_workspace_floats": [_i32],
     "xb_dense_wgrad": [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
                        _vp, _vp, _vp, _vp],
-    "xb_mlp_trunk_fwd": [_vp, _i32, _i32, _vp, _vp, _f32, _vp, _i64, _i32, _vp],
+    "xb_mlp_trunk_fwd": [_vp, _i32, _i32, _vp, _vp, _f32, _vp, _i64, _i32, _vp, _vp],
     "xb_mlp_trunk_wgrad_workspace_floats": [_i32, _i32],
     "xb_mlp_trunk_wgrad_parts": [],
     "xb_mlp_backward_tail": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp,

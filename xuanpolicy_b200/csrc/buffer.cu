@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(256)
     gather_trunk_fwd_kernel(const int64_t* __restrict__ idx, int64_t B, int64_t T, int64_t N, const Record* __restrict__ rec,
                             const float* __restrict__ W0, const float* __restrict__ b0, float slope, int H,
                             float* __restrict__ obs_out, float4* __restrict__ scal_out, double* __restrict__ stats,
-                            float4* __restrict__ h1) {
+                            float4* __restrict__ h1, uint32_t* __restrict__ h1_signs) {
     __shared__ double smem[64];
     pdl_wait();                                 // (launched with the programmatic-serialization attribute, common.cuh)
     pdl_trigger();
@@ -303,6 +303,12 @@ __global__ void __launch_bounds__(256)
                 o[e] = a > 0.f ? a : a * slope;
             }
             h1[(c * 32 + j) * tpr + q] = make_float4(o[0], o[1], o[2], o[3]);
+            if (h1_signs) {     // sign words of the row's 128-feature slice: bit l of word e = (h1[128 half + 4 l + e] > 0)
+                const uint32_t b0_ = __ballot_sync(0xffffffffu, o[0] > 0.f), b1_ = __ballot_sync(0xffffffffu, o[1] > 0.f);
+                const uint32_t b2_ = __ballot_sync(0xffffffffu, o[2] > 0.f), b3_ = __ballot_sync(0xffffffffu, o[3] > 0.f);
+                if (lane < 4)
+                    h1_signs[(c * 32 + j) * (H >> 5) + half * 4 + lane] = lane == 0 ? b0_ : (lane == 1 ? b1_ : (lane == 2 ? b2_ : b3_));
+            }
         }
     }
     if (stats) finish_stats(s, ss, g_partials, &g_ticket, stats, smem);
@@ -398,7 +404,7 @@ extern "C" int xb_gather_records(const int64_t* idx, int64_t B, int64_t T, int64
 
 extern "C" int xb_gather_trunk_fwd(const int64_t* idx, int64_t B, int64_t T, int64_t N, const float* rec, int obs_dim,
                                    const float* W0, const float* b0, float slope, int H, float* obs_out, float* scal_out,
-                                   double* stats, float* h1, xb_stream_t stream) {
+                                   double* stats, float* h1, uint32_t* h1_signs, xb_stream_t stream) {
     if (B <= 0 || T <= 0 || N <= 0 || !idx || !rec || !W0 || !b0 || !obs_out || !scal_out || !h1) return XB_E_BADARG;
     if (obs_dim < 1 || obs_dim > 4 || (H != 128 && H != 256)) return XB_E_UNSUPPORTED;
     if (((uintptr_t)rec & 31u) || ((uintptr_t)scal_out & 15u) || ((uintptr_t)h1 & 15u) ||
@@ -411,10 +417,10 @@ extern "C" int xb_gather_trunk_fwd(const int64_t* idx, int64_t B, int64_t T, int
     float4* so = (float4*)scal_out;
     float4* h = (float4*)h1;
     switch (obs_dim) {
-        case 4: XB_CUDA(launch_pdl(gather_trunk_fwd_kernel<4>, dim3(grid), dim3(256), 0, s, true, idx, B, T, N, r, W0, b0, slope, H, obs_out, so, stats, h)); break;
-        case 3: XB_CUDA(launch_pdl(gather_trunk_fwd_kernel<3>, dim3(grid), dim3(256), 0, s, true, idx, B, T, N, r, W0, b0, slope, H, obs_out, so, stats, h)); break;
-        case 2: XB_CUDA(launch_pdl(gather_trunk_fwd_kernel<2>, dim3(grid), dim3(256), 0, s, true, idx, B, T, N, r, W0, b0, slope, H, obs_out, so, stats, h)); break;
-        default: XB_CUDA(launch_pdl(gather_trunk_fwd_kernel<1>, dim3(grid), dim3(256), 0, s, true, idx, B, T, N, r, W0, b0, slope, H, obs_out, so, stats, h)); break;
+        case 4: XB_CUDA(launch_pdl(gather_trunk_fwd_kernel<4>, dim3(grid), dim3(256), 0, s, true, idx, B, T, N, r, W0, b0, slope, H, obs_out, so, stats, h, h1_signs)); break;
+        case 3: XB_CUDA(launch_pdl(gather_trunk_fwd_kernel<3>, dim3(grid), dim3(256), 0, s, true, idx, B, T, N, r, W0, b0, slope, H, obs_out, so, stats, h, h1_signs)); break;
+        case 2: XB_CUDA(launch_pdl(gather_trunk_fwd_kernel<2>, dim3(grid), dim3(256), 0, s, true, idx, B, T, N, r, W0, b0, slope, H, obs_out, so, stats, h, h1_signs)); break;
+        default: XB_CUDA(launch_pdl(gather_trunk_fwd_kernel<1>, dim3(grid), dim3(256), 0, s, true, idx, B, T, N, r, W0, b0, slope, H, obs_out, so, stats, h, h1_signs)); break;
     }
     XB_LAUNCH_CHECK();
     return 0;

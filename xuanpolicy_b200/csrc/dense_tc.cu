@@ -105,6 +105,7 @@ struct KParams {
     int obs_ld, obs_dim;
     const float* W0;    // [K][obs_dim]
     const float* b0;    // [K]
+    float* h1_out;      // nullable [M][K]: the layer-0 CTAs also store the trunk activations (training: wgrad / dgrad read them)
     // optional observation normalisation in front of the trunk (raw observations in, agent.py:112-113): states fp64 [9]
     const double* norm_new;   // rows [0, norm_rows)
     const double* norm_old;   // rows [norm_rows, M)
@@ -153,6 +154,9 @@ struct KParams {
     uint32_t* sign_out;
     int sign_ld;
     const uint32_t* signs;
+    // DGRAD epilogue mask dZ1 = acc * leaky'(H1) from the trunk's sign words h1_signs [M][4] (bit l of word e = H1[4 l + e] > 0; xb_gather_trunk_fwd /
+    // xb_mlp_trunk_fwd) instead of TMA-loaded H1 tiles: no mask ring, no 4 N B/row read (N = 128, with `signs` only)
+    const uint32_t* h1_signs;
 };
 
 // Wt'[n][s * H + k] = split_tf32(w2'_s[k] * W_s[k][n]) — `tid` in [0, 128), all CTAs share the work.
@@ -206,6 +210,7 @@ struct EpiCtx {
     int sel;           // FWD dual: 0 = actor CTA, 1 = critic CTA
     uint32_t* sign_out;   // FWD: nullable activation sign words (KParams::sign_out), already offset to this CTA's layer
     int sign_ld;
+    const uint32_t* h1_signs;   // DGRAD: nullable trunk sign words [M][4] (N = 128): the mask without the H1 tiles
     double* red;       // shared memory [4 warps][8] for the per-CTA loss sums
 #ifdef XB_DENSE_TS
     long long* ts;
@@ -238,13 +243,16 @@ __device__ __forceinline__ void epilogue_warp(const EpiCtx& c, int warp, int lan
             l_inv_var = 1.0f / (sd * sd);
         }
     }
-    if (MODE == MODE_DGRAD && c.tile0 < c.n_tiles) {
+    const bool mask_bits = MODE == MODE_DGRAD && c.h1_signs != nullptr;
+    if (MODE == MODE_DGRAD && !mask_bits && c.tile0 < c.n_tiles) {
         mbar_arrive_expect_tx_if(elected, bar_h1, kSub);
         tma_load_2d_if(elected, c.h1_ring + warp * kSub, c.map_h1, c.n_off, (int)(c.tile0 * BM + warp * 32), bar_h1);
     }
     for (int64_t tile = c.tile0; tile < c.n_tiles; tile += c.tile_step, ++lt) {
         const uint32_t acc = lt & 1, tph = (lt >> 1) & 1;
         const int64_t row = tile * BM + warp * 32 + lane;
+        uint4 hw4 = make_uint4(0u, 0u, 0u, 0u);                        // mask_bits: this row's 128 trunk sign bits
+        if (mask_bits && row < c.M) hw4 = __ldg(reinterpret_cast<const uint4*>(c.h1_signs) + row);
         mbar_wait(c.bar_tfull + 8 * acc, tph);
 #ifdef XB_DENSE_TS
         if (threadIdx.x == 0 && c.ts && blockIdx.x == 0 && lt < 64) c.ts[(3 * 64 + lt) * 8 + 0] = clock64();
@@ -270,7 +278,9 @@ __device__ __forceinline__ void epilogue_warp(const EpiCtx& c, int warp, int lan
             __syncwarp();
             const uint32_t obuf = c.out_ring + (g % (uint32_t)c.O) * kATile + warp * kSub;
             uint32_t hbuf = 0;
-            if (MODE == MODE_DGRAD) {
+            // (word e of the row holds bit l = feature 4 l + e: this chunk's columns 32 cc + 4 q + e are bits 8 cc + q)
+            const uint32_t hx = hw4.x >> (8 * cc), hy = hw4.y >> (8 * cc), hz = hw4.z >> (8 * cc), hw_ = hw4.w >> (8 * cc);
+            if (MODE == MODE_DGRAD && !mask_bits) {
                 const uint32_t hb = c.HB > 1 ? (g & 1) : 0, hph = c.HB > 1 ? ((g >> 1) & 1) : (g & 1);
                 {                      // prefetch the next chunk's mask sub-tile (or, single-buffered, load this chunk's now)
                     int ncc = cc + (c.HB > 1 ? 1 : 0);
@@ -304,6 +314,11 @@ __device__ __forceinline__ void epilogue_warp(const EpiCtx& c, int warp, int lan
                     const float* w = b + N;
                     h0 += f.x * w[0] + f.y * w[1] + f.z * w[2] + f.w * w[3];
                     h1 += f.x * w[N] + f.y * w[N + 1] + f.z * w[N + 2] + f.w * w[N + 3];
+                } else if (mask_bits) {
+                    f.x *= ((hx >> q) & 1u) ? 1.f : c.slope;
+                    f.y *= ((hy >> q) & 1u) ? 1.f : c.slope;
+                    f.z *= ((hz >> q) & 1u) ? 1.f : c.slope;
+                    f.w *= ((hw_ >> q) & 1u) ? 1.f : c.slope;
                 } else {
                     const float4 m = lds128(hbuf + sw128_off(lane, q));
                     f.x *= m.x > 0.f ? 1.f : c.slope;
@@ -675,6 +690,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         c.loss = p.loss; c.sel = sel; c.red = reinterpret_cast<double*>(misc_ptr + kLossRedOff);
         c.sign_out = (MODE == MODE_FWD && p.sign_out) ? p.sign_out + sel * (N / 32) : nullptr;
         c.sign_ld = p.sign_ld;
+        c.h1_signs = nullptr;
 #ifdef XB_DENSE_TS
         c.ts = p.ts;
 #endif
@@ -943,7 +959,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t misc = h1_ring + (MODE == MODE_DGRAD ? (uint32_t)HB * kATile : 0u);
     const uint32_t bar_full = misc, bar_conv = misc + 64, bar_empty = misc + 128, bar_aempty = misc + 192;
     const uint32_t bar_tfull = misc + 224, bar_tempty = misc + 240, bar_bfull = misc + 256;
-    const uint32_t tmem_slot = misc + 264, bar_h1w = misc + 352, bar_bfull_r = misc + 288, bar_bempty = misc + 320;
+    // (sign-word DGRAD: no raw ring, so the weight ring takes the raw ring's 8 + 8 barrier slots and may be up to 8 deep)
+    const bool no_raw_k = MODE == MODE_DGRAD && p.signs != nullptr;
+    const uint32_t tmem_slot = misc + 264, bar_h1w = misc + 352;
+    const uint32_t bar_bfull_r = no_raw_k ? misc : misc + 288, bar_bempty = no_raw_k ? misc + 128 : misc + 320;
     unsigned char* misc_ptr = smem_raw + (misc - smem_u32(smem_raw));
     float* sf = reinterpret_cast<float*>(misc_ptr + 512);
 
@@ -978,7 +997,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             mbar_init(bar_conv + 8 * a, n_conv);
             mbar_init(bar_aempty + 8 * a, 1);
         }
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < (no_raw_k ? 8 : 4); ++b) {
             mbar_init(bar_bfull_r + 8 * b, 1);
             mbar_init(bar_bempty + 8 * b, 1);
         }
@@ -1211,6 +1230,14 @@ __global__ void __launch_bounds__(kThreads, 1)
                             a += o4[3] * w[3 * K + q];
                             x[q] = a > 0.f ? a : a * p.slope;
                         }
+                        if (MODE == MODE_FWD && p.h1_out && sel == 0) {     // 64 contiguous bytes of this row's trunk activations
+                            const int64_t row = tile * BM + r;
+                            if (row < p.M) {
+                                float4* dst = reinterpret_cast<float4*>(p.h1_out + row * (int64_t)K + kb * BK + 16 * chh);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) dst[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+                            }
+                        }
                     } else {
                         float4 xs[4];
 #pragma unroll
@@ -1297,6 +1324,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         c.loss = p.loss; c.sel = sel; c.red = reinterpret_cast<double*>(misc_ptr + kLossRedOff);
         c.sign_out = (MODE == MODE_FWD && p.sign_out) ? p.sign_out + sel * (N / 32) : nullptr;
         c.sign_ld = p.sign_ld;
+        c.h1_signs = (MODE == MODE_DGRAD && N == 128 && p.n_split <= 1) ? p.h1_signs : nullptr;
 #ifdef XB_DENSE_TS
         c.ts = p.ts;
 #endif
@@ -1325,14 +1353,16 @@ static int launch_kmajor_ts(const TMaps& maps, KParams p, cudaStream_t s) {
     const int avail = kMaxSmem - 1024 - kMiscBytes - bres;
     // minimum: 2 raw stages, (2 weight stages), 1 staging tile (+ 1 mask tile); then deepen
     const bool no_raw = MODE == MODE_DGRAD && p.signs != nullptr;    // sign words: no raw A ring, a deeper weight ring instead
-    int S = no_raw ? 0 : 2, SB = B_RES ? 0 : 2, O = 1, HB = MODE == MODE_DGRAD ? 1 : 0;
+    const bool mask_bits = no_raw && p.h1_signs != nullptr && N == 128 && p.n_split <= 1;      // no H1 mask tiles either
+    int S = no_raw ? 0 : 2, SB = B_RES ? 0 : 2, O = 1, HB = (MODE == MODE_DGRAD && !mask_bits) ? 1 : 0;
     auto bytes = [&]() { return (S + O + HB) * kATile + SB * 2 * kBTile; };
     if (bytes() > avail) return XB_E_UNSUPPORTED;
     ++O; if (bytes() > avail) --O;
-    if (MODE == MODE_DGRAD) { ++HB; if (bytes() > avail) --HB; }
+    if (MODE == MODE_DGRAD && !mask_bits) { ++HB; if (bytes() > avail) --HB; }
     while (!no_raw && S < 4) { ++S; if (bytes() > avail) { --S; break; } }
     if (!B_RES) { ++SB; if (bytes() > avail) --SB; }
-    if (!B_RES && no_raw && SB == 3) { ++SB; if (bytes() > avail) --SB; }      // (4 weight-stage barriers exist)
+    // sign-word DGRAD: whatever is left goes to the streamed weight ring (8 barrier slots; L2 -> smem latency ~1.5 k cycles)
+    while (!B_RES && no_raw && SB < 8) { ++SB; if (bytes() > avail) { --SB; break; } }
     {   // experiment knobs: XB_DENSE_S / XB_DENSE_O override the ring depths when they fit
         static const int s_env = []() { const char* e = getenv("XB_DENSE_S"); return e ? atoi(e) : 0; }();
         static const int o_env = []() { const char* e = getenv("XB_DENSE_O"); return e ? atoi(e) : 0; }();
@@ -1341,8 +1371,8 @@ static int launch_kmajor_ts(const TMaps& maps, KParams p, cudaStream_t s) {
         const int S0 = S, O0 = O, SB0 = SB, HB0 = HB;
         if (!no_raw && s_env >= 2 && s_env <= 4) S = s_env;
         if (o_env >= 1 && o_env <= 4) O = o_env;
-        if (!B_RES && sb_env >= 2 && sb_env <= 4) SB = sb_env;
-        if (MODE == MODE_DGRAD && hb_env >= 1 && hb_env <= 2) HB = hb_env;
+        if (!B_RES && sb_env >= 2 && sb_env <= (no_raw ? 8 : 4)) SB = sb_env;
+        if (MODE == MODE_DGRAD && !mask_bits && hb_env >= 1 && hb_env <= 2) HB = hb_env;
         if (bytes() > avail) { S = S0; O = O0; SB = SB0; HB = HB0; }
     }
     p.stages = S;
@@ -1387,6 +1417,7 @@ static int dispatch_kmajor(int N, bool bres, const TMaps& maps, const KParams& p
     if (bres && (kMaxSmem - 1024 - kMiscBytes - 2 * p.KB * kBTile) < (2 + 1 + 1 + (MODE == MODE_DGRAD)) * kATile) bres = false;
     KParams q = p_in;
     q.signs = nullptr;          // the SS-form DGRAD reads the activation tiles
+    q.h1_signs = nullptr;
     switch (N) {
         case 64:
             return bres ? launch_kmajor<64, true, MODE>(maps, q, s) : launch_kmajor<64, false, MODE>(maps, q, s);
@@ -2238,6 +2269,7 @@ struct TrunkArgs {
     int64_t norm_rows;
     float norm_clip;
     int flags;
+    float* h1_out;
 };
 
 static int dense_fwd_impl(const float* X, const TrunkArgs* trunk, int64_t M, int K, int N, float slope, int n_layers, const float* const* Whi,
@@ -2285,6 +2317,8 @@ static int dense_fwd_impl(const float* X, const TrunkArgs* trunk, int64_t M, int
         p.norm_clip = trunk->norm_clip;
         p.pdl_launch = 1;
         p.pdl_early = (trunk->flags & XB_FWD_WEIGHTS_STABLE) ? 1 : 0;
+        if (trunk->h1_out && !al16(trunk->h1_out)) return XB_E_UNSUPPORTED;
+        p.h1_out = trunk->h1_out;
     }
     p.M = M;
     p.KB = K / BK;
@@ -2394,15 +2428,16 @@ extern "C" int xb_mlp_fwd_from_obs(const float* obs, int ld, int obs_dim, const 
     const float* hb[2] = {head_b0, head_b1};
     const int nh[2] = {n_head0, n_head1};
     float* ho[2] = {head_out0, head_out1};
-    TrunkArgs t{obs, ld, obs_dim, W0, b0, norm_new, norm_old, norm_rows, norm_clip, flags};
+    TrunkArgs t{obs, ld, obs_dim, W0, b0, norm_new, norm_old, norm_rows, norm_clip, flags, nullptr};
     return dense_fwd_impl(nullptr, &t, M, H, H, slope, 2, Whi, Wlo, bias, Y, hw, hb, nh, ho, 1, stream);
 }
 
 extern "C" int xb_dense_dgrad(const float* Y0, const float* dout0, const float* w2_0, int nh0, int K0, const float* Y1,
                               const float* dout1, const float* w2_1, int nh1, int K1, int64_t M, const float* Wthi,
                               const float* Wtlo, int N, const float* H1, float slope, float* dZ1, int wt_form,
-                              const uint32_t* signs, xb_stream_t stream) {
+                              const uint32_t* signs, const uint32_t* h1_signs, xb_stream_t stream) {
     if (wt_form != 0 && wt_form != 1) return XB_E_BADARG;
+    if (h1_signs && ((uintptr_t)h1_signs & 15u)) return XB_E_BADARG;
     if (!Y0 || !dout0 || !w2_0 || !Wthi || !Wtlo || !H1 || !dZ1 || M <= 0) return XB_E_BADARG;
     if (K0 % BK != 0 || K0 < BK || K0 > 256 || nh0 < 1 || nh0 > 2) return XB_E_UNSUPPORTED;
     if (Y1 && (K1 % BK != 0 || K1 < BK || K1 > 256 || nh1 < 1 || nh1 > 2 || !dout1 || !w2_1)) return XB_E_UNSUPPORTED;
@@ -2438,6 +2473,7 @@ extern "C" int xb_dense_dgrad(const float* Y0, const float* dout0, const float* 
     p.n_split = split ? 2 : 1;
     p.mask_form = wt_form;
     p.signs = (K / BK <= 8) ? signs : nullptr;       // (the operand warps keep a row's <= 8 words in registers)
+    p.h1_signs = (p.signs && N == 128) ? h1_signs : nullptr;
     return dispatch_kmajor<MODE_DGRAD>(N, false, maps, p, (cudaStream_t)stream);
 }
 
@@ -2598,4 +2634,38 @@ extern "C" int xb_mlp_backward_tail_bin(const float* wgrad_ws, int H_out, int H_
     return backward_tail_impl(wgrad_ws, H_out, H_in, n_sources, nh0, nh1, dW0, db0, dw2_0, db2_0, dW1, db1, dw2_1, db2_1,
                               trunk_ws, trunk_parts, obs_dim, dWt, dbt, dls64, dls32, A, norm_workspace, step_dev, h, lr_out,
                               gnorm_out, (cudaStream_t)stream, bin);
+}
+
+
+// The TRAINING forward with the trunk layer generated in the kernel (xb_mlp_fwd_from_obs) and everything xb_dense_fwd2_loss adds:
+// the operand warps of the layer-0 CTAs also store h1 = leaky_relu(W0 obs + b0) (h1_out: wgrad's x operand, dgrad's mask), so the
+// separate first-layer launch (xb_gather_trunk_fwd's second half) and the read of h1 by this launch disappear.
+extern "C" int xb_mlp_fwd_from_obs_train(const float* obs, int ld, int obs_dim, const float* W0, const float* b0, int64_t M, int H,
+                                         float slope, const float* Whi0, const float* Wlo0, const float* bias0, float* Y0,
+                                         const float* head_w0, const float* head_b0, int n_head0, float* head_out0,
+                                         const float* Whi1, const float* Wlo1, const float* bias1, float* Y1,
+                                         const float* head_w1, const float* head_b1, int n_head1, float* head_out1, float* h1_out,
+                                         const float* scal, const double* adv_stats, int64_t adv_count, float clip_range,
+                                         float vf_coef, float ent_coef, float inv_batch, const float* logstd, float* dact,
+                                         float* dv, double* loss_partials, uint32_t* loss_ticket, double* scalars, double* dlogstd,
+                                         const float* prep_W0, const float* prep_W1, float* prep_thi, float* prep_tlo,
+                                         uint32_t* sign_out, xb_stream_t stream) {
+    if (!h1_out) return XB_E_BADARG;
+    if (scal && (!dact || !dv || !loss_partials || !loss_ticket || !scalars || ((uintptr_t)scal & 15u))) return XB_E_BADARG;
+    if (adv_stats && adv_count <= 0) return XB_E_BADARG;
+    if (logstd && !dlogstd) return XB_E_BADARG;
+    const float* Whi[2] = {Whi0, Whi1};
+    const float* Wlo[2] = {Wlo0, Wlo1};
+    const float* bias[2] = {bias0, bias1};
+    float* Y[2] = {Y0, Y1};
+    const float* hw[2] = {head_w0, head_w1};
+    const float* hb[2] = {head_b0, head_b1};
+    const int nh[2] = {n_head0, n_head1};
+    float* ho[2] = {head_out0, head_out1};
+    FusedLoss L{(const float4*)scal, adv_stats, adv_stats ? 1.0 / (double)adv_count : 0.0, clip_range, vf_coef, ent_coef,
+                inv_batch, logstd ? 1 : 0, logstd, dact, dv, loss_partials, loss_ticket, scalars, dlogstd};
+    const float* pw[2] = {prep_W0, prep_W1};
+    TrunkArgs t{obs, ld, obs_dim, W0, b0, nullptr, nullptr, 0, 0.f, 0, h1_out};
+    return dense_fwd_impl(nullptr, &t, M, H, H, slope, 2, Whi, Wlo, bias, Y, hw, hb, nh, ho, 1, stream, scal ? &L : nullptr, pw,
+                          prep_thi, prep_tlo, sign_out);
 }

@@ -15,12 +15,13 @@ constexpr int kMaxObs = 8;
 template <int OBS>
 __global__ void __launch_bounds__(256) trunk_fwd_kernel(const float* __restrict__ obs, int ld, const float* __restrict__ W0,
                                                         const float* __restrict__ b0, float slope, float4* __restrict__ h1,
-                                                        int64_t B, int H) {
+                                                        int64_t B, int H, uint32_t* __restrict__ h1_signs) {
     const int tpr = H >> 2;                        // threads per row
     const int rows_per_block = blockDim.x / tpr;
     const int q = threadIdx.x % tpr, slot = threadIdx.x / tpr;
     if (slot >= rows_per_block) return;
-    float w[4][OBS], bias[4];
+    const int lane = threadIdx.x & 31;             // (h1_signs: tpr is a multiple of 32, so q % 8 == lane % 8 and a row's threads
+    float w[4][OBS], bias[4];                      //  fill whole warps — the shuffles below stay inside one row)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         bias[e] = b0[4 * q + e];
@@ -40,6 +41,12 @@ __global__ void __launch_bounds__(256) trunk_fwd_kernel(const float* __restrict_
             o[e] = a > 0.f ? a : a * slope;
         }
         h1[b * tpr + q] = make_float4(o[0], o[1], o[2], o[3]);
+        if (h1_signs) {         // bit l of word e of a 128-feature slice = (h1[128 slice + 4 l + e] > 0), as xb_gather_trunk_fwd
+            const uint32_t b0_ = __ballot_sync(0xffffffffu, o[0] > 0.f), b1_ = __ballot_sync(0xffffffffu, o[1] > 0.f);
+            const uint32_t b2_ = __ballot_sync(0xffffffffu, o[2] > 0.f), b3_ = __ballot_sync(0xffffffffu, o[3] > 0.f);
+            if (lane < 4)
+                h1_signs[b * (H >> 5) + (q >> 5) * 4 + lane] = lane == 0 ? b0_ : (lane == 1 ? b1_ : (lane == 2 ? b2_ : b3_));
+        }
     }
 }
 
@@ -138,13 +145,14 @@ static inline bool trunk_shape_ok(int obs_dim, int H) {
 }
 
 extern "C" int xb_mlp_trunk_fwd(const float* obs, int ld, int obs_dim, const float* W0, const float* b0, float slope,
-                                float* h1, int64_t B, int H, xb_stream_t stream) {
+                                float* h1, int64_t B, int H, uint32_t* h1_signs, xb_stream_t stream) {
     if (!obs || !W0 || !b0 || !h1 || B <= 0 || ld < obs_dim) return XB_E_BADARG;
     if (!trunk_shape_ok(obs_dim, H) || ((uintptr_t)h1 & 15u)) return XB_E_UNSUPPORTED;
+    if (h1_signs && H % 128 != 0) return XB_E_UNSUPPORTED;       // (a row's threads must fill whole warps)
     const int rows_per_block = 256 / (H / 4);
     const int grid = grid_for((B + rows_per_block - 1) / rows_per_block * 256, 256, 4);
     XB_OBS_SWITCH(obs_dim, (trunk_fwd_kernel<O><<<grid, 256, 0, (cudaStream_t)stream>>>(
-                               obs, ld, W0, b0, slope, reinterpret_cast<float4*>(h1), B, H)));
+                               obs, ld, W0, b0, slope, reinterpret_cast<float4*>(h1), B, H, h1_signs)));
     XB_LAUNCH_CHECK();
     return 0;
 }

@@ -98,6 +98,7 @@ class FusedActorCritic:
         # binary-form weight gradients (rank-1 head gradients: 0/1 A operand from the sign words, 2 MMAs per k-step, no read of ya / yc)
         self.bin_wgrad = self.sign_bits and os.environ.get("XB_BIN_WGRAD", "1") != "0"
         self._bin_now = False
+        self.h1_signs = self.sign_dgrad and os.environ.get("XB_H1_SIGNS", "0") == "1"
         self._mask_ready = False
         # Discrete(3): folded head parameters (w_j - w_2, b_j - b_2), two-column head outputs / gradients
         self.fold3 = (not self.gaussian) and self.A == 3
@@ -137,6 +138,10 @@ class FusedActorCritic:
             e = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
             b = dict(h1=e(B, self.H), ya=e(B, self.H), yc=e(B, self.H), act=e(B, self.A), v=e(B, 1), dz1=None)
             b["signs"] = torch.empty(B, 2 * self.H // 32, dtype=torch.int32, device=self.device) if self.sign_bits else None
+            # trunk sign words (written by whichever kernel produces h1): the dgrad epilogue's mask without the h1 tiles.
+            # Opt-in (XB_H1_SIGNS=1): measured at 65 536 x 128, dgrad 34.5 -> 32.5 us but the gather + trunk launch that has to
+            # produce the words 16.4 -> 18.5 (shuffle-packed) / 20.5 us (ballots) — a net loss, the h1 mask tiles stay.
+            b["h1s"] = torch.empty(B, self.H // 32, dtype=torch.int32, device=self.device) if self.h1_signs else None
             if self.fold3:      # the kernels write two logits; the reported third one is 0
                 b["act2"] = e(B, 2)
                 b["act"].zero_()
@@ -145,14 +150,14 @@ class FusedActorCritic:
 
     # ---------------------------------------------------------------------------------------------- stages (one launch each)
     def stage_trunk(self, obs, b):
-        ops.mlp_trunk_fwd(obs, self.l0.weight.data, self.l0.bias.data, self.slope, b["h1"])
+        ops.mlp_trunk_fwd(obs, self.l0.weight.data, self.l0.bias.data, self.slope, b["h1"], h1_signs=b.get("h1s"))
 
     def can_skip_y(self, softmax_pair=False):
         """True if a backward with these head gradients reads the hidden activations only through their sign words (sign-word
         dgrad + binary-form wgrad): the training forward then need not write ya / yc at all (67 MB per 65 536-row minibatch)."""
         return self.sign_dgrad and self.bin_wgrad and self._rank1(softmax_pair)
 
-    def stage_hidden(self, b, loss=None, keep_y=True):
+    def stage_hidden(self, b, loss=None, keep_y=True, obs=None):
         """Actor + critic hidden layers and heads in one launch.  `loss` (dict: scal, adv_stats, adv_count, clip_range,
         vf_coef, ent_coef, inv_batch, logstd, scalars, dlogstd): also the PPO loss forward + backward, fused into the
         kernel's epilogue — dL/d(act_out) lands in b["dact"], dL/dv in b["dv"]."""
@@ -163,15 +168,26 @@ class FusedActorCritic:
         # the same launch writes the w2-scaled weight operand of the mask-form dgrad that follows (csrc/dense_tc.cu KParams)
         prep = (self.la1.weight.data, self.lc1.weight.data, self.wtm_hi, self.wtm_lo) if self.mask_dgrad else None
         self._mask_ready = prep is not None
+        if loss is not None and "dact" not in b:
+            B = b["h1"].shape[0]
+            b["dact"] = torch.empty(B, self.A, dtype=torch.float32, device=self.device)
+            b["dv"] = torch.empty(B, 1, dtype=torch.float32, device=self.device)
+        if obs is not None:
+            # `obs`: the trunk layer is generated INSIDE this launch (the operand warps also store h1 for the backward kernels):
+            # no first-layer launch, no read of h1 here
+            lt = None if loss is None else (loss["scal"], loss["adv_stats"], loss["adv_count"], loss["clip_range"], loss["vf_coef"],
+                                            loss["ent_coef"], loss["inv_batch"], loss["logstd"], b["dact"], b["dv"],
+                                            self._loss_partials, self._loss_ticket, loss["scalars"], loss["dlogstd"])
+            ops.mlp_fwd_from_obs_train(obs, self.l0.weight.data, self.l0.bias.data, self.slope, l0, l1, b["h1"], loss=lt,
+                                       prep=prep, sign_out=b["signs"])
+            if self.fold3 and loss is None:
+                b["act"][:, :2].copy_(b["act2"])
+            return
         if loss is None:
             ops.dense_fwd2(b["h1"], self.slope, l0, l1, prep=prep, sign_out=b["signs"])
             if self.fold3:
                 b["act"][:, :2].copy_(b["act2"])
             return
-        if "dact" not in b:
-            B = b["h1"].shape[0]
-            b["dact"] = torch.empty(B, self.A, dtype=torch.float32, device=self.device)
-            b["dv"] = torch.empty(B, 1, dtype=torch.float32, device=self.device)
         ops.dense_fwd2_loss(b["h1"], self.slope, l0, l1, loss["scal"], loss["adv_stats"], loss["adv_count"],
                             loss["clip_range"], loss["vf_coef"], loss["ent_coef"], loss["inv_batch"], loss["logstd"],
                             b["dact"], b["dv"], self._loss_partials, self._loss_ticket, loss["scalars"], loss["dlogstd"],
@@ -183,10 +199,10 @@ class FusedActorCritic:
         assert b.get("y_valid", True) or (self.sign_dgrad and b.get("signs") is not None), "forward(keep_y=False) needs the sign-word dgrad"
         if self._mask_ready and (self.A == 1 or (self.A == 2 and softmax_pair)):
             ops.dense_dgrad(b["ya"], dact, self.la2.weight.data, b["yc"], dv2, self.lc2.weight.data, self.wtm_hi, self.wtm_lo,
-                            b["h1"], self.slope, b["dz1"], wt_form=1, signs=b["signs"])
+                            b["h1"], self.slope, b["dz1"], wt_form=1, signs=b["signs"], h1_signs=b.get("h1s"))
             return
         ops.dense_dgrad(b["ya"], dact, self._head_a()[0], b["yc"], dv2, self.lc2.weight.data, self.wt_hi, self.wt_lo,
-                        b["h1"], self.slope, b["dz1"], signs=b["signs"])
+                        b["h1"], self.slope, b["dz1"], signs=b["signs"], h1_signs=b.get("h1s"))
 
     def _rank1(self, softmax_pair):
         return (not self.fold3) and (self.A == 1 or (self.A == 2 and softmax_pair))
@@ -251,7 +267,7 @@ class FusedActorCritic:
         return b["act"], b["v"][:, 0]
 
     # ---------------------------------------------------------------------------------------------- forward / backward
-    def forward(self, obs, refresh=True, trunk_done=False, loss=None, keep_y=True):
+    def forward(self, obs, refresh=True, trunk_done=False, loss=None, keep_y=True, trunk_in_kernel=False):
         """obs: CUDA fp32 [B, obs_dim] with contiguous rows (a column slice of the float4 observation rows is fine).
         Returns (act_out [B, A], v [B]); the activations stay in per-batch-size buffers for `backward`."""
         B = obs.shape[0]
@@ -260,9 +276,10 @@ class FusedActorCritic:
             self.refresh_weights()
         else:
             self.fold_head()                # the head parameters move with every optimiser step
-        if not trunk_done:              # the gather kernel already produced h1 for these rows (xb_gather_trunk_fwd)
+        in_kernel = trunk_in_kernel and not trunk_done and self.fwd_from_obs_ok()
+        if not trunk_done and not in_kernel:    # (trunk_done: the gather kernel already produced h1, xb_gather_trunk_fwd)
             self.stage_trunk(obs, b)
-        self.stage_hidden(b, loss, keep_y)
+        self.stage_hidden(b, loss, keep_y, obs=obs if in_kernel else None)
         self._last = (obs, b)
         return b["act"], b["v"][:, 0]
 

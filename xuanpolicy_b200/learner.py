@@ -278,13 +278,17 @@ class PPOCLIP_Learner:
         want = memory.use_advnorm and compute_stats
         fused = self._fused if (self._fused is not None and idx.numel() >= FusedActorCritic.MIN_ROWS) else None
         mb["trunk_done"] = False
-        if (fused is not None and memory.packed and self.value_clip <= 0 and fused.obs_dim <= 4
+        # the first MLP layer: by the gather launch (xb_gather_trunk_fwd) or its own launch; XB_TRUNK_IN_FWD=1 generates it inside
+        # the hidden-layer launch instead (xb_mlp_fwd_from_obs_train, bit-identical) — measured SLOWER at 65 536 x 128 (45 us
+        # against 16.4 + 31.8 - 11.3 for gather+trunk, forward, plain gather: the operand warps become the forward's bottleneck)
+        mb["trunk_in_fwd"] = fused is not None and fused.fwd_from_obs_ok() and os.environ.get("XB_TRUNK_IN_FWD", "0") == "1"
+        if (fused is not None and memory.packed and self.value_clip <= 0 and fused.obs_dim <= 4 and not mb["trunk_in_fwd"]
                 and os.environ.get("XB_GATHER_TRUNK", "1") != "0"):
             # gather + the MLP's first layer in one launch: the gathered rows feed the layer from registers
             b = fused._buffers(idx.numel())
             ops.gather_trunk_fwd(idx, memory.n_size, memory.n_envs, memory._rec, memory.obs_dim, fused.l0.weight.data,
                                  fused.l0.bias.data, fused.slope, mb["obs"], mb["scal"], b["h1"],
-                                 stats=mb["stats"] if want else None)
+                                 stats=mb["stats"] if want else None, h1_signs=b.get("h1s"))
             mb["trunk_done"] = True
         elif memory.packed and self.value_clip <= 0:   # one 32-byte record per sample: obs + {act, old_logp, adv, ret}
             ops.gather_records(idx, memory.n_size, memory.n_envs, memory._rec, memory.obs_dim, mb["obs"], mb["scal"],
@@ -316,7 +320,8 @@ class PPOCLIP_Learner:
                         scalars=self._scalars, dlogstd=self._dls64 if fused.gaussian else None)
             # (rank-1 head gradients: the backward reads the hidden activations only through their sign words — not stored)
             fused.forward(mb["obs"], refresh=not fused.splits_fresh, trunk_done=mb.get("trunk_done", False), loss=loss,
-                          keep_y=not fused.can_skip_y(softmax_pair=not fused.gaussian))
+                          keep_y=not fused.can_skip_y(softmax_pair=not fused.gaussian),
+                          trunk_in_kernel=mb.get("trunk_in_fwd", False))
             b = fused._last[1]
             if fused.gaussian:
                 flat = self._flat
@@ -326,7 +331,8 @@ class PPOCLIP_Learner:
                 fused.backward(b["dact"], b["dv"], softmax_pair=True)
             return
         if fused is not None:                        # tcgen05 dense kernels; weights re-split after every Adam step
-            act_out, v_pred = fused.forward(mb["obs"], refresh=not fused.splits_fresh, trunk_done=mb.get("trunk_done", False))
+            act_out, v_pred = fused.forward(mb["obs"], refresh=not fused.splits_fresh, trunk_done=mb.get("trunk_done", False),
+                                            trunk_in_kernel=mb.get("trunk_in_fwd", False))
             a_dist = fused.dist_params(act_out)
         else:
             out = self.policy(mb["obs"])

@@ -181,10 +181,11 @@ def gather_records(idx, T, N, rec, obs_dim, obs_out, scal_out, stats=None):
               _p(scal_out, F32), _p(stats, F64), _stream())
 
 
-def gather_trunk_fwd(idx, T, N, rec, obs_dim, w0, b0, slope, obs_out, scal_out, h1, stats=None):
-    """gather_records + the MLP's first layer in one launch (xb_gather_trunk_fwd)."""
+def gather_trunk_fwd(idx, T, N, rec, obs_dim, w0, b0, slope, obs_out, scal_out, h1, stats=None, h1_signs=None):
+    """gather_records + the MLP's first layer in one launch (xb_gather_trunk_fwd).  h1_signs: int32 [B, H / 32] sign words."""
     _lib.call("xb_gather_trunk_fwd", _p(idx, I64), idx.numel(), T, N, _p(rec, F32), obs_dim, _p(w0, F32), _p(b0, F32),
-              float(slope), w0.shape[0], _p(obs_out, F32), _p(scal_out, F32), _p(stats, F64), _p(h1, F32), _stream())
+              float(slope), w0.shape[0], _p(obs_out, F32), _p(scal_out, F32), _p(stats, F64), _p(h1, F32), _p(h1_signs, I32),
+              _stream())
 
 
 def sample_categorical(logits, seed, counter, offset, act_out, logp_out):
@@ -380,13 +381,35 @@ def mlp_fwd_from_obs(obs, w0, b0, slope, layer0, layer1, norm=None, weights_stab
               float(slope), *args, _p(nn, F64), _p(no, F64), int(nr), float(nc), 1 if weights_stable else 0, _stream())
 
 
-def dense_dgrad(y0, dout0, w2_0, y1, dout1, w2_1, wt_hi, wt_lo, h1, slope, dz1, wt_form=0, signs=None):
+def mlp_fwd_from_obs_train(obs, w0, b0, slope, layer0, layer1, h1_out, loss=None, prep=None, sign_out=None):
+    """Training forward with the trunk layer generated in the kernel (xb_mlp_fwd_from_obs_train): layerK as in dense_fwd2,
+    h1_out receives the trunk activations; loss = (scal, adv_stats, adv_count, clip_range, vf_coef, ent_coef, inv_batch, logstd,
+    dact, dv, partials, ticket, scalars, dlogstd) fuses the PPO loss into the epilogue."""
+    pw0, pw1, pthi, ptlo = prep if prep is not None else (None, None, None, None)
+    ptr, ld = _rows_ld(obs)
+    args = []
+    for w_hi, w_lo, bias, y, head_w, head_b, head_out in (layer0, layer1):
+        args += [_p(w_hi, F32), _p(w_lo, F32), _p(bias, F32), _p(y, F32), _p(head_w, F32), _p(head_b, F32),
+                 head_w.shape[0], _p(head_out, F32)]
+    if loss is None:
+        largs = [None, None, 0, 0.0, 0.0, 0.0, 0.0, None, None, None, None, None, None, None]
+    else:
+        scal, adv_stats, adv_count, clip_range, vf_coef, ent_coef, inv_batch, logstd, dact, dv, partials, ticket, scalars, dls = loss
+        largs = [_p(scal, F32), _p(adv_stats, F64), int(adv_count), float(clip_range), float(vf_coef), float(ent_coef),
+                 float(inv_batch), _p(logstd, F32), _p(dact, F32), _p(dv, F32), _p(partials, F64), _p(ticket, I32),
+                 _p(scalars, F64), _p(dls, F64)]
+    _lib.call("xb_mlp_fwd_from_obs_train", ptr, ld, obs.shape[1], _p(w0, F32), _p(b0, F32), obs.shape[0], w0.shape[0],
+              float(slope), *args, _p(h1_out, F32), *largs, _p(pw0, F32), _p(pw1, F32), _p(pthi, F32), _p(ptlo, F32),
+              _p(sign_out, I32), _stream())
+
+
+def dense_dgrad(y0, dout0, w2_0, y1, dout1, w2_1, wt_hi, wt_lo, h1, slope, dz1, wt_form=0, signs=None, h1_signs=None):
     """signs: int32 [M, (K0 + K1) / 32] sign words of [y0 | y1] (dense_fwd2's sign_out); the kernel then does not read y0 / y1."""
     M, K0 = y0.shape
     _lib.call("xb_dense_dgrad", _p(y0, F32), _p(dout0, F32), _p(w2_0, F32), w2_0.shape[0], K0, _p(y1, F32),
               _p(dout1, F32), _p(w2_1, F32), w2_1.shape[0] if w2_1 is not None else 0,
               y1.shape[1] if y1 is not None else 0, M, _p(wt_hi, F32), _p(wt_lo, F32), wt_hi.shape[0], _p(h1, F32),
-              float(slope), _p(dz1, F32), int(wt_form), _p(signs, I32), _stream())
+              float(slope), _p(dz1, F32), int(wt_form), _p(signs, I32), _p(h1_signs, I32), _stream())
 
 
 def dense_wgrad_workspace(h_in, device):
@@ -404,10 +427,10 @@ def dense_wgrad(y0, dout0, w2_0, y1, dout1, w2_1, x, slope, workspace, dW0, db0,
 
 
 # ------------------------------------------------------------------------------------------------ trunk layer (SIMT)
-def mlp_trunk_fwd(obs, w0, b0, slope, h1):
+def mlp_trunk_fwd(obs, w0, b0, slope, h1, h1_signs=None):
     ptr, ld = _rows_ld(obs)
     _lib.call("xb_mlp_trunk_fwd", ptr, ld, obs.shape[1], _p(w0, F32), _p(b0, F32), float(slope), _p(h1, F32),
-              obs.shape[0], w0.shape[0], _stream())
+              obs.shape[0], w0.shape[0], _p(h1_signs, I32), _stream())
 
 
 def mlp_trunk_wgrad_workspace(obs_dim, h, device):
