@@ -2043,7 +2043,7 @@ struct TailArgs {
     float* gnorm_out;
 };
 
-__global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ head_part,
+__global__ void __launch_bounds__(512, 2) wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ head_part,
                                     const float* __restrict__ db2_part, int grid, int n_jobs, int halves, int HIN,
                                     int H_out, float* dW0, float* db0, float* dw2_0, float* db2_0, int nh0, float* dW1,
                                     float* db1, float* dw2_1, float* db2_1, int nh1, TailArgs tail, BinArgs bin) {
