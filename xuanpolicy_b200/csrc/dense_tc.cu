@@ -1814,6 +1814,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     constexpr int kStage = 4 * kBox + NBX * kBox;  // bin operand (128 features, written by the operand warps) | x operand -> hi
     constexpr int kLo = NBX * kBox;                // lo half of the x operand
     constexpr int kTmemCols = HIN;
+    constexpr int kGroups = HIN == 128 ? 3 : 2;   // operand-warp groups (HIN = 256: the reduction scratch of 12 warps would not fit)
+    constexpr int kOw = 4 * kGroups;               // operand warps
     constexpr uint32_t kIdescMain = umma_idesc_tf32(128, HIN, 1, 1);
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1883,11 +1885,14 @@ __global__ void __launch_bounds__(kThreads, 1)
             ph = nph;
             if (++j == (uint32_t)L) j = 0;
         }
-    } else if (warp >= 4) {
-        // ============================================================ operand warps: two groups of 4 on alternate k-blocks
-        const int t = threadIdx.x - 128;
-        const int w = t >> 5;                       // 0..7: slot of this warp's partial sums in the final reduction
-        const int grp = w >> 2, wr = w & 3;         // group (k-block parity), row group: rows 8 wr .. 8 wr + 7
+    } else {
+      // ============================================================ operand warps: groups of 4 on k-blocks it = grp (mod kGroups).
+      // HIN = 128: THREE groups — the epilogue warps 0-3 are idle until the accumulator is complete and the loop is bound by the
+      // operand warps' latency chains (measured 1 550 cycles per k-block with two groups against a 1 125-cycle shared-memory floor)
+      if (warp >= 4 || kGroups == 3) {
+        const int w = warp >= 4 ? warp - 4 : warp + 8;   // 0..11: slot of this warp's partial sums in the final reduction
+        const int t = w * 32 + lane;
+        const int grp = w >> 2, wr = w & 3;         // group, row group: rows 8 wr .. 8 wr + 7
         const int g = (t & 31) >> 3, c = t & 7;     // feature box, 16-byte chunk: features m0 + 32 g + 4 c .. + 3
         const int nh = p.nh[src];
         const float* dout = p.dout[src];
@@ -1911,13 +1916,13 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
         };
         prefetch(grp);
-        for (int it = grp; it < nkb; it += 2) {
+        for (int it = grp; it < nkb; it += kGroups) {
             const uint32_t s = it % S, ph = (it / S) & 1, j = it % L;
             float ev[8];
             uint32_t bits[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { ev[i] = d0[i]; bits[i] = sw[i] >> (4 * c); }
-            prefetch(it + 2);                        // this group's next k-block
+            prefetch(it + kGroups);                  // this group's next k-block
             mbar_wait(bar_full + 8 * s, ph);         // (x landed; the stage was released by the MMAs of its previous use)
             mbar_wait(bar_loempty + 8 * j, ((it / L) & 1) ^ 1);
             const uint32_t raw = ring + s * kStage, lo_b = lo_ring + j * kLo;
@@ -1958,7 +1963,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_conv + 8 * s);
         }
-        // column sums: the 8 warps' partials in a fixed order
+        // column sums: the operand warps' partials in a fixed order
         constexpr int kCols = 128 + HIN;
         float* hs = sf + w * kCols;
 #pragma unroll
@@ -1968,20 +1973,24 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
             for (int e = 0; e < 4; ++e) hs[128 + 32 * (4 * gg + g) + 4 * c + e] = gacc[gg][e];
         // (esum: every thread of a warp saw the same 8 rows per k-block; one lane per warp reports it)
-        if ((t & 31) == 0) sf[8 * kCols + w] = esum;
-        bar_sync_named(1, kOperandWarps * 32);
-        for (int i = t; i < kCols; i += kOperandWarps * 32) {
-            const float v = ((sf[i] + sf[kCols + i]) + (sf[2 * kCols + i] + sf[3 * kCols + i])) +
-                            ((sf[4 * kCols + i] + sf[5 * kCols + i]) + (sf[6 * kCols + i] + sf[7 * kCols + i]));
+        if ((t & 31) == 0) sf[kOw * kCols + w] = esum;
+        bar_sync_named(1, kOw * 32);
+        for (int i = t; i < kCols; i += kOw * 32) {
+            float v = ((sf[i] + sf[kCols + i]) + (sf[2 * kCols + i] + sf[3 * kCols + i])) +
+                      ((sf[4 * kCols + i] + sf[5 * kCols + i]) + (sf[6 * kCols + i] + sf[7 * kCols + i]));
+            if (kGroups == 3) v += (sf[8 * kCols + i] + sf[9 * kCols + i]) + (sf[10 * kCols + i] + sf[11 * kCols + i]);
             if (i < 128) p.part[((int64_t)blockIdx.x * 128 + i) * (HIN + 4) + HIN] = v;       // S[m]: the bias column
             else p.head_part[(int64_t)blockIdx.x * 256 + (i - 128)] = v;                     // G[n]
         }
         if (t == 0) {
-            const float* es = sf + 8 * kCols;
-            p.db2_part[(int64_t)blockIdx.x * 2] = ((es[0] + es[1]) + (es[2] + es[3])) + ((es[4] + es[5]) + (es[6] + es[7]));
+            const float* es = sf + kOw * kCols;
+            float e = ((es[0] + es[1]) + (es[2] + es[3])) + ((es[4] + es[5]) + (es[6] + es[7]));
+            if (kGroups == 3) e += (es[8] + es[9]) + (es[10] + es[11]);
+            p.db2_part[(int64_t)blockIdx.x * 2] = e;
             p.db2_part[(int64_t)blockIdx.x * 2 + 1] = 0.f;
         }
-    } else {
+      }
+      if (warp < 4) {
         // ============================================================ epilogue: partial [128][HIN + 4]
         float* out = p.part + ((int64_t)blockIdx.x * 128 + warp * 32 + lane) * (HIN + 4);
         if (nkb > 0) {
@@ -2001,6 +2010,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                                           __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+      }
     }
     tc_fence_before();
     __syncthreads();
