@@ -483,7 +483,7 @@ def test_sign_words_match_activations_and_dgrad_is_bit_identical(env_id, B):
     assert torch.equal(outs[2], outs[4]) and torch.equal(outs[3], outs[5])
 
 
-@pytest.mark.parametrize("env_id,B", [("Pendulum-v1", 65536), ("CartPole-v1", 8192 + 33)])
+@pytest.mark.parametrize("env_id,B", [("Pendulum-v1", 65536), ("CartPole-v1", 8192 + 33), ("Pendulum-v1", 2048 + 5)])
 def test_binary_form_wgrad_matches_the_three_mma_form(env_id, B):
     """xb_dense_wgrad_bin + xb_mlp_backward_tail_bin (0/1 A operand from the sign words, head-weight gradient rebuilt from the
     weight-gradient partials) against xb_dense_wgrad + xb_mlp_backward_tail on the same inputs: every hidden-layer and head
