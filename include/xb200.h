@@ -576,6 +576,15 @@ int xb_adam_apply_split(float* param, const float* grad, float* exp_avg, float* 
                         xb_stream_t stream);
 int xb_peer_allreduce_f64(const void* const* peer_bases /* host [W] */, int rank, int W, int offset, int n, double* out,
                           uint32_t* tickets, xb_stream_t stream);
+/*   xb_peer_allreduce_merge   the per-vector-step statistics exchange of the env-sharded normalisers as ONE kernel with ONE
+ *                             cross-GPU barrier + the merge of xb_rms_merge_sums: every rank pushes src[0..n) (n <= 16) into a
+ *                             parity double-buffered inbox at doubles [inbox_offset, inbox_offset + 256) of every peer's
+ *                             statistics area, out[0..n) = the totals (rank order, bit-identical on every rank); with
+ *                             obs_state_in / ret_state (n = 12: sum x[4], sum x^2[4], N, sum R, sum R^2, n finished) the
+ *                             normaliser states are merged in the same launch (mpi_moments, statistic_tools.py:6-32). */
+int xb_peer_allreduce_merge(const void* const* peer_bases, int rank, int W, const double* src, int n, int inbox_offset,
+                            double* out, uint32_t* tickets, const double* obs_state_in, double* obs_state_out, int dim,
+                            double* ret_state, float* rew_std, xb_stream_t stream);
 int xb_adv_stats_minibatches(const int64_t* idx, int64_t n_minibatches, int64_t B, int64_t T, int64_t N, const float* adv,
                              int64_t stride, double* stats, xb_stream_t stream);
 

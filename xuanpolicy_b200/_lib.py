@@ -101,6 +101,7 @@ SIGNATURES = {
     "xb_adam_apply_split": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _i32,
                             _vp, _vp, _vp],
     "xb_peer_allreduce_f64": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
+    "xb_peer_allreduce_merge": [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "xb_adv_stats_minibatches": [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp],
     "xb_clip_adam_step": [_vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _i64, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp],
 }

@@ -197,6 +197,7 @@ class PPOCLIP_Agent:
                             and _os.environ.get("XB_FUSED_NORM", "1") != "0"
                             and (self.world_size == 1 or (self._norm_peer is not None and self.memory.obs_row == 4)))
         self._shard_norm = self._fused_norm and self.world_size > 1
+        self._norm_push = _os.environ.get("XB_NORM_PUSH", "1") != "0"      # one-barrier push exchange + merge in one launch
         if self.use_obsnorm and not self._fused_norm and self.memory.obs_row != 4:
             raise NotImplementedError("observations wider than 4 floats are normalised on the fused rollout path only "
                                       "(single rank, XB_FUSED_STEP / XB_FUSED_NORM on)")
@@ -282,6 +283,8 @@ class PPOCLIP_Agent:
             logstd = logstd.detach() if logstd is not None else std.log().contiguous()
             ops.sample_gaussian(mu[:N].contiguous(), logstd, self._sample_seed, self._ctr, offset, self._act, self._logp)
 
+    _NORM_INBOX = 1024      # doubles [1024, 1280) of the comm block's statistics area (the epoch's advantage sums use [0, 2 M))
+
     def _rollout_step(self, t):
         """One vector step into buffer row t (reference loop body, ppoclip_agent.py:62-68,88,101)."""
         N, env, mem = self.n_envs, self.envs, self.memory
@@ -322,10 +325,18 @@ class PPOCLIP_Agent:
                              trig_cache=self._trig_cache, stats=stats)
             if self._shard_norm:      # the ranks' sums of this step -> global sums -> merged normalisers (for the next step)
                 c = self._rms_cur
-                ops.peer_allreduce_f64(self._norm_peer, 12, self._norm_global, offset=self._norm_off)
-                ops.rms_merge_sums(self._norm_global, self._obs_rms[c] if self.use_obsnorm else None,
-                                   self._obs_rms[c ^ 1] if self.use_obsnorm else None, self._obs_dim,
-                                   self._ret_rms if self.use_rewnorm else None, self._rew_std if self.use_rewnorm else None)
+                if self._norm_push:
+                    # one kernel, one cross-GPU barrier (push into a parity double-buffered inbox), merge included
+                    ops.peer_allreduce_merge(self._norm_peer, self._norm_local, 12, self._norm_global, self._NORM_INBOX,
+                                             self._obs_rms[c] if self.use_obsnorm else None,
+                                             self._obs_rms[c ^ 1] if self.use_obsnorm else None, self._obs_dim,
+                                             self._ret_rms if self.use_rewnorm else None,
+                                             self._rew_std if self.use_rewnorm else None)
+                else:                 # pull form: two barriers + a separate merge launch
+                    ops.peer_allreduce_f64(self._norm_peer, 12, self._norm_global, offset=self._norm_off)
+                    ops.rms_merge_sums(self._norm_global, self._obs_rms[c] if self.use_obsnorm else None,
+                                       self._obs_rms[c ^ 1] if self.use_obsnorm else None, self._obs_dim,
+                                       self._ret_rms if self.use_rewnorm else None, self._rew_std if self.use_rewnorm else None)
             if self.use_obsnorm:
                 self._rms_cur ^= 1
             self._cur ^= 1

@@ -22,12 +22,13 @@
 // come from a per-CTA device counter, so a captured CUDA graph replays correctly.
 #include <cstring>
 
+#include "normalize.cuh"
 #include "optim.cuh"
 
 namespace xb {
 
 constexpr int kPeerMaxRanks = 8;
-constexpr int kPeerSlots = 64;       // CTA slots: [0, kPeerSlots-2) gradient all-reduce, [62] error flag (tickets only), [63] the stats exchange
+constexpr int kPeerSlots = 64;       // CTA slots: [0, kPeerSlots-3) gradient all-reduce, [61] the push-form statistics exchange, [62] error flag (tickets only), [63] the pull-form stats exchange
 constexpr int kPeerStatsMax = 2048;  // doubles (two per minibatch of an epoch)
 constexpr int64_t kPeerFlagsBytes = (int64_t)kPeerSlots * kPeerMaxRanks * sizeof(uint32_t);
 constexpr int64_t kPeerStatsOff = kPeerFlagsBytes;
@@ -146,6 +147,50 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x == 0) tickets[slot] = base_ticket + 2;
 }
 
+// The per-vector-step exchange of the running-statistics sums (env-sharded use_obsnorm / use_rewnorm) as ONE kernel with ONE
+// cross-GPU barrier, followed in the same kernel by the normaliser merge (normalize.cuh merge_step_stats = xb_rms_merge_sums):
+// every rank PUSHES its n <= 16 sums into row [parity][rank] of an inbox inside every peer's statistics area, signals, waits, and
+// adds the W rows in rank order out of LOCAL memory (bit-identical totals on every rank).  parity = the launch counter's low bit
+// (a device counter: graph replays and odd horizons are fine); a row can only be overwritten two launches later, after a
+// barrier this rank enters only once it has read it — so no second barrier (the pull form above needs two), and no separate
+// merge launch.  Launched with the programmatic-serialization attribute: the rollout forward that follows may become resident
+// (set-up, resident weights) while this kernel waits for its peers.
+constexpr int kPeerPushSlot = kPeerSlots - 3;
+constexpr int kPeerPushMax = 16;
+__global__ void __launch_bounds__(128)
+    peer_allreduce_merge_kernel(PeerTable t, int rank, int W, int inbox_off, int n, const double* __restrict__ src,
+                                double* __restrict__ out, uint32_t* __restrict__ tickets, const double* __restrict__ obs_state_in,
+                                double* __restrict__ obs_state_out, int dim, double* __restrict__ ret_state,
+                                float* __restrict__ rew_std) {
+    __shared__ double sums[kPeerPushMax];
+    pdl_wait();
+    pdl_trigger();
+    const uint32_t ticket = tickets[kPeerPushSlot] + 1;
+    const int parity = (int)(ticket & 1u);
+    for (int i = threadIdx.x; i < n * W; i += blockDim.x) {
+        const int peer = i / n, j = i - peer * n;
+        double* dst = reinterpret_cast<double*>(t.base[peer] + kPeerStatsOff) + inbox_off + (parity * kPeerMaxRanks + rank) * kPeerPushMax + j;
+        *dst = src[j];
+    }
+    peer_barrier(t, rank, W, kPeerPushSlot, ticket, tickets);
+    if ((int)threadIdx.x < kPeerPushMax) {
+        double s = 0.0;
+        if ((int)threadIdx.x < n) {
+            const double* in = reinterpret_cast<const double*>(t.base[rank] + kPeerStatsOff) + inbox_off + parity * kPeerMaxRanks * kPeerPushMax;
+            for (int r = 0; r < W; ++r) s += ld_peer_f64(in + r * kPeerPushMax + threadIdx.x);
+            out[threadIdx.x] = s;
+        }
+        sums[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) tickets[kPeerPushSlot] = ticket;
+    if (threadIdx.x < 32 && (obs_state_in || ret_state)) {
+        const int d = threadIdx.x < 4 ? threadIdx.x : 0;
+        merge_step_stats<4>(obs_state_in, obs_state_out, dim, ret_state, rew_std, sums[d], sums[4 + d], sums[8], sums[9], sums[10],
+                            sums[11], threadIdx.x);
+    }
+}
+
 // (sum, sumsq) of the advantages of every minibatch of an epoch in one pass over the permutation:
 // stats[m] += over i in [m*B, (m+1)*B) of adv[row(idx[i])].  `adv` has element stride `stride` floats per row.
 __global__ void __launch_bounds__(256)
@@ -228,7 +273,7 @@ extern "C" int xb_peer_allreduce_grad_norm(const void* const* peer_bases /* host
     AdamHyper h{lr0, lr_end_factor, beta1, beta2, eps, max_norm, grad_scale, lr_total_iters};
     const int64_t n4 = n / 4;
     int grid = (int)((n4 + kPeerBlock - 1) / kPeerBlock);
-    if (grid > kPeerSlots - 2) grid = kPeerSlots - 2;
+    if (grid > kPeerSlots - 3) grid = kPeerSlots - 3;
     peer_allreduce_grad_norm_kernel<<<grid, kPeerBlock, 0, (cudaStream_t)stream>>>(t, rank, W, n4, grad_in, grad_out, tickets, step_dev,
                                                                                   h, workspace, lr_out, gnorm_out);
     XB_LAUNCH_CHECK();
@@ -242,6 +287,24 @@ extern "C" int xb_peer_allreduce_f64(const void* const* peer_bases /* host [W] *
     if (rc) return rc;
     if (n <= 0 || offset < 0 || offset + n > kPeerStatsMax || !out || !tickets) return XB_E_BADARG;
     peer_allreduce_f64_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(t, rank, W, offset, n, out, tickets);
+    XB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xb_peer_allreduce_merge(const void* const* peer_bases /* host [W] */, int rank, int W, const double* src, int n,
+                                       int inbox_offset, double* out, uint32_t* tickets, const double* obs_state_in,
+                                       double* obs_state_out, int dim, double* ret_state, float* rew_std, xb_stream_t stream) {
+    PeerTable t;
+    int rc = make_table(peer_bases, rank, W, &t);
+    if (rc) return rc;
+    if (!src || !out || !tickets || n <= 0 || n > kPeerPushMax || inbox_offset < 0 ||
+        inbox_offset + 2 * kPeerMaxRanks * kPeerPushMax > kPeerStatsMax)
+        return XB_E_BADARG;
+    if ((obs_state_in || ret_state) && n != 12) return XB_E_BADARG;       // the merge reads the 12 step sums
+    if (obs_state_in && (!obs_state_out || obs_state_in == obs_state_out || dim < 1 || dim > 4)) return XB_E_BADARG;
+    if (ret_state && !rew_std) return XB_E_BADARG;
+    XB_CUDA(launch_pdl(peer_allreduce_merge_kernel, dim3(1), dim3(128), 0, (cudaStream_t)stream, true, t, rank, W, inbox_offset, n, src,
+                       out, tickets, obs_state_in, obs_state_out, dim, ret_state, rew_std));
     XB_LAUNCH_CHECK();
     return 0;
 }

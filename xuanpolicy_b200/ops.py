@@ -248,6 +248,12 @@ def peer_allreduce_f64(peer, n, out, offset=0):
               _p(peer.tickets, I32), _stream())
 
 
+def peer_allreduce_merge(peer, src, n, out, inbox_offset, obs_in=None, obs_out=None, obs_dim=0, ret_state=None, rew_std=None):
+    """One-barrier push exchange of `src[:n]` (out[:n] = totals over ranks) + the normaliser merge (xb_peer_allreduce_merge)."""
+    _lib.call("xb_peer_allreduce_merge", peer.bases, peer.rank, peer.world, _p(src, F64), int(n), int(inbox_offset), _p(out, F64),
+              _p(peer.tickets, I32), _p(obs_in, F64), _p(obs_out, F64), int(obs_dim), _p(ret_state, F64), _p(rew_std, F32), _stream())
+
+
 def adv_stats_minibatches(idx, n_minibatches, B, T, N, adv, stride, stats):
     _lib.call("xb_adv_stats_minibatches", _p(idx, I64), int(n_minibatches), int(B), int(T), int(N), _p(adv, F32), int(stride),
               _p(stats, F64), _stream())
