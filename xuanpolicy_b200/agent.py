@@ -191,8 +191,8 @@ class PPOCLIP_Agent:
                              (not self.discrete and self.memory.act_dim == 1)))
         # running statistics carried by the fused rollout step (csrc/normalize.cuh StepStats): no moments / normalise /
         # return-tracker launches per step; the rollout forward normalises the raw observations itself.  Env-sharded, the
-        # step writes this rank's sums into the comm block, one peer-memory exchange adds the ranks' sums and a one-warp
-        # launch merges them (every rank keeps the GLOBAL statistics, bit-identical).
+        # step writes this rank's sums and ONE launch with one cross-GPU barrier exchanges them over peer memory and merges the
+        # normalisers (xb_peer_allreduce_merge; every rank keeps the GLOBAL statistics, bit-identical).
         self._fused_norm = (self._fused_step and (self.use_obsnorm or self.use_rewnorm)
                             and _os.environ.get("XB_FUSED_NORM", "1") != "0"
                             and (self.world_size == 1 or (self._norm_peer is not None and self.memory.obs_row == 4)))
