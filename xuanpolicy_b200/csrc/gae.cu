@@ -186,6 +186,25 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d_if(uint32_t elected, void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe;\n"
+        "setp.ne.b32 pe, %5, 0;\n"
+        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+        "}\n" ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "r"(elected)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_if(uint32_t elected, uint64_t* bar, uint32_t bytes) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe;\n"
+        "setp.ne.b32 pe, %2, 0;\n"
+        "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(bytes), "r"(elected)
+        : "memory");
+}
+
 constexpr int kTileN = 128;   // envs per CTA (512 B rows)
 constexpr int kTileT = 8;     // time steps per stage
 constexpr int kStages = 4;
@@ -222,16 +241,25 @@ __global__ void __launch_bounds__(kTmaThreads)
 
     double sum = 0.0, sumsq = 0.0;
     if (warp == kConsumers / 32) {
-        // ===== producer: one elected lane streams tiles from the last time tile down to the first =====
-        if ((threadIdx.x & 31) == 0) {
+        // ===== producer: the whole warp walks the loop, one elected lane streams tiles from the last time tile down to the first
+        // (warp-uniform operands: inside `if (lane == 0)` ptxas wraps every UTMALDG in an ELECT / R2UR.BROADCAST waterfall) =====
+        {
+            uint32_t elected;
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "elect.sync _|p, 0xffffffff;\n"
+                "selp.u32 %0, 1, 0, p;\n"
+                "}\n"
+                : "=r"(elected));
             int stage = 0;
             uint32_t phase = 0;
             for (int j = ntiles - 1; j >= 0; --j) {
                 mbar_wait(&sm.empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&sm.full[stage], kStageBytes);
-                tma_load_2d(sm.tile[stage][0], &map_rew, (int)e0, j * kTileT, &sm.full[stage]);
-                tma_load_2d(sm.tile[stage][1], &map_val, (int)e0, j * kTileT, &sm.full[stage]);
-                tma_load_2d(sm.tile[stage][2], &map_term, (int)e0, j * kTileT, &sm.full[stage]);
+                mbar_arrive_expect_tx_if(elected, &sm.full[stage], kStageBytes);
+                tma_load_2d_if(elected, sm.tile[stage][0], &map_rew, (int)e0, j * kTileT, &sm.full[stage]);
+                tma_load_2d_if(elected, sm.tile[stage][1], &map_val, (int)e0, j * kTileT, &sm.full[stage]);
+                tma_load_2d_if(elected, sm.tile[stage][2], &map_term, (int)e0, j * kTileT, &sm.full[stage]);
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
