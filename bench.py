@@ -561,6 +561,15 @@ def rank_parity(agent, world):
     d.all_gather(allp, mine)
     out = {"params_bit_identical_across_ranks": bool(all(torch.equal(allp[0], x) for x in allp)),
            "exchange": "peer-memory kernels" if peer is not None else "nccl all-reduce"}
+    # (3) env-sharded running statistics: every rank must hold the SAME global RunningMeanStd state after the timed rollouts
+    #     (the per-step exchange + merge of xb_peer_allreduce_merge; the replicated parameters alone would not show a divergence)
+    states = [getattr(agent, n, None) for n in ("_obs_rms", "_ret_rms", "_rew_std")]
+    states = [t for s_ in states if s_ is not None for t in (s_ if isinstance(s_, (list, tuple)) else [s_]) if torch.is_tensor(t)]
+    if states and (agent.use_obsnorm or agent.use_rewnorm):
+        flat = torch.cat([t.detach().reshape(-1).double() for t in states])
+        alls = [torch.empty_like(flat) for _ in range(world)]
+        d.all_gather(alls, flat)
+        out["normaliser_state_bit_identical_across_ranks"] = bool(all(torch.equal(alls[0], x) for x in alls))
     if peer is not None:
         snap = agent._snapshot()
         gen = torch.Generator(device="cuda").manual_seed(100 + d.get_rank())
